@@ -1,0 +1,203 @@
+"""Per-video frame loop: the drop-in for
+cutie.inference.inference_core.InferenceCore (cutie/inference/inference_core.py:18-345).
+
+Same constructor, `step` signature, return value ([1+K, H, W] probabilities) and public attributes
+(memory, object_manager, max_internal_size, mem_every, ...), so scripting_demo.py / eval_vos.py /
+process_video.py drive it unchanged.  The memory read it calls is the fused-kernel path of
+cutie_b200.inference.memory_manager.
+"""
+import logging
+from typing import Iterable, List, Optional
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from cutie_b200.inference.image_feature_store import ImageFeatureStore
+from cutie_b200.inference.memory_manager import MemoryManager
+from cutie_b200.inference.object_manager import ObjectManager
+from cutie_b200.utils.tensor_utils import aggregate, pad_divide_by, unpad
+
+log = logging.getLogger()
+
+
+class InferenceCore:
+    def __init__(self, network, cfg, *, image_feature_store: ImageFeatureStore = None):
+        self.network = network
+        self.cfg = cfg
+        self.mem_every = cfg.mem_every
+        self.chunk_size = cfg.chunk_size
+        self.save_aux = cfg.save_aux
+        self.max_internal_size = cfg.max_internal_size
+        self.flip_aug = cfg.flip_aug
+
+        self.curr_ti = -1
+        self.last_mem_ti = 0
+        # offsets (in frames since the last memory frame) at which the sensory memory is refreshed
+        stagger = cfg.stagger_updates
+        if stagger >= self.mem_every:
+            self.stagger_ti = set(range(1, self.mem_every + 1))
+        else:
+            self.stagger_ti = set(np.round(np.linspace(1, self.mem_every, stagger)).astype(int))
+        self.object_manager = ObjectManager()
+        self.memory = MemoryManager(cfg=cfg, object_manager=self.object_manager)
+        self.image_feature_store = image_feature_store or ImageFeatureStore(self.network)
+        self.last_mask = None
+        self.last_logits = None      # network.segment(...)[1] of the latest segmented frame (parity hook)
+
+    # -- memory control ------------------------------------------------------------------------
+    def _reset_clock(self):
+        self.curr_ti = -1
+        self.last_mem_ti = 0
+
+    def clear_memory(self):
+        self._reset_clock()
+        self.memory = MemoryManager(cfg=self.cfg, object_manager=self.object_manager)
+
+    def clear_non_permanent_memory(self):
+        self._reset_clock()
+        self.memory.clear_non_permanent_memory()
+
+    def clear_sensory_memory(self):
+        self._reset_clock()
+        self.memory.clear_sensory_memory()
+
+    def update_config(self, cfg):
+        self.mem_every = cfg['mem_every']
+        self.memory.update_config(cfg)
+
+    # -- the two halves of a step ------------------------------------------------------------------
+    def _add_memory(self, image, pix_feat, prob, key, shrinkage, selection, *, is_deep_update: bool = True,
+                    force_permanent: bool = False) -> None:
+        """Encode the (predicted or given) masks and append one frame of tokens to the memory."""
+        if prob.shape[1] == 0:
+            log.warn('Trying to add an empty object mask to memory!')
+            return
+        ids = self.object_manager.all_obj_ids
+        self.memory.initialize_sensory_if_needed(key, ids)
+        msk_value, sensory, obj_value, _ = self.network.encode_mask(
+            image, pix_feat, self.memory.get_sensory(ids), prob, deep_update=is_deep_update,
+            chunk_size=self.chunk_size, need_weights=self.save_aux)
+        self.memory.add_memory(key, shrinkage, msk_value, obj_value, ids, selection=selection,
+                               as_permanent='all' if force_permanent else 'first')
+        self.last_mem_ti = self.curr_ti
+        if is_deep_update:
+            self.memory.update_sensory(sensory, ids)
+
+    def _segment(self, key, selection, pix_feat, ms_features: Iterable[torch.Tensor],
+                 update_sensory: bool = True) -> torch.Tensor:
+        """Memory read -> decoder.  Returns [1+K, H, W] probabilities (channel 0 = background)."""
+        bs = key.shape[0]
+        assert bs == (2 if self.flip_aug else 1)
+        if not self.memory.engaged:
+            log.warn('Trying to segment without any memory!')
+            return torch.zeros((1, key.shape[-2] * 16, key.shape[-1] * 16), device=key.device, dtype=key.dtype)
+
+        readout = self.memory.read(pix_feat, key, selection, self.last_mask, self.network)
+        readout = self.object_manager.realize_dict(readout)
+        ids = self.object_manager.all_obj_ids
+        sensory, logits, prob = self.network.segment(ms_features, readout, self.memory.get_sensory(ids),
+                                                     chunk_size=self.chunk_size, update_sensory=update_sensory)
+        self.last_logits = logits
+        if self.flip_aug:
+            prob = (prob[0] + torch.flip(prob[1], dims=[-1])) / 2
+        else:
+            prob = prob[0]
+        if update_sensory:
+            self.memory.update_sensory(sensory, ids)
+        return prob
+
+    def step(self, image: torch.Tensor, mask: Optional[torch.Tensor] = None,
+             objects: Optional[List[int]] = None, *, idx_mask: bool = True, end: bool = False,
+             delete_buffer: bool = True, force_permanent: bool = False) -> torch.Tensor:
+        """One frame.  image [3,H,W] in [0,1]; mask [H,W] ids (idx_mask) or [K,H,W] soft masks or None;
+        objects: ids present in `mask`.  With a mask the listed objects are memorised (and any others
+        are propagated first); without, the frame is segmented from memory.  Returns [1+K,H,W]."""
+        if objects is None and mask is not None:
+            assert not idx_mask
+            objects = list(range(1, mask.shape[0] + 1))
+
+        # optional internal down-scaling (the GUI / demo path)
+        resize_needed = False
+        if self.max_internal_size > 0:
+            h, w = image.shape[-2:]
+            short = min(h, w)
+            if short > self.max_internal_size:
+                resize_needed = True
+                new_hw = (int(h / short * self.max_internal_size), int(w / short * self.max_internal_size))
+                image = F.interpolate(image[None], size=new_hw, mode='bilinear', align_corners=False)[0]
+                if mask is not None:
+                    if idx_mask:
+                        mask = F.interpolate(mask[None, None].float(), size=new_hw,
+                                             mode='nearest-exact')[0, 0].round().long()
+                    else:
+                        mask = F.interpolate(mask[None], size=new_hw, mode='bilinear', align_corners=False)[0]
+
+        self.curr_ti += 1
+        image, self.pad = pad_divide_by(image, 16)
+        image = image.unsqueeze(0)
+        if self.flip_aug:
+            image = torch.cat([image, torch.flip(image, dims=[-1])], dim=0)
+
+        since_mem = self.curr_ti - self.last_mem_ti
+        is_mem_frame = (since_mem >= self.mem_every or mask is not None) and not end
+        need_segment = mask is None or (self.object_manager.num_obj > 0 and not self.object_manager.has_all(objects))
+        update_sensory = (since_mem in self.stagger_ti) and not end
+
+        ms_feat, pix_feat = self.image_feature_store.get_features(self.curr_ti, image)
+        key, shrinkage, selection = self.image_feature_store.get_key(self.curr_ti, image)
+
+        if need_segment:
+            prob_with_bg = self._segment(key, selection, pix_feat, ms_feat, update_sensory=update_sensory)
+
+        if mask is not None:
+            tmp_ids, _ = self.object_manager.add_new_objects(objects)
+            mask, _ = pad_divide_by(mask, 16)
+            if need_segment:
+                # merge the propagated prediction with the (partial) input mask; input wins where it is set
+                prob_no_bg = prob_with_bg[1:]
+                if idx_mask:
+                    prob_no_bg[:, mask > 0] = 0
+                else:
+                    prob_no_bg[:, mask.max(0) > 0.5] = 0
+                extra = []
+                for mask_pos, tmp_id in enumerate(tmp_ids):
+                    plane = (mask == objects[mask_pos]).type_as(prob_no_bg) if idx_mask else mask[tmp_id]
+                    if tmp_id > prob_no_bg.shape[0]:
+                        extra.append(plane.unsqueeze(0))
+                    else:
+                        prob_no_bg[tmp_id - 1] = plane
+                mask = torch.cat([prob_no_bg, *extra], dim=0)
+            elif idx_mask:
+                if len(objects) == 0:
+                    if delete_buffer:
+                        self.image_feature_store.delete(self.curr_ti)
+                    log.warn('Trying to insert an empty mask as memory!')
+                    return torch.zeros((1, key.shape[-2] * 16, key.shape[-1] * 16), device=key.device,
+                                       dtype=key.dtype)
+                mask = torch.stack([mask == objects[i] for i, _ in enumerate(tmp_ids)], dim=0)
+            prob_with_bg = torch.softmax(aggregate(mask, dim=0), dim=0)
+
+        self.last_mask = prob_with_bg[1:].unsqueeze(0)
+        if self.flip_aug:
+            self.last_mask = torch.cat([self.last_mask, torch.flip(self.last_mask, dims=[-1])], dim=0)
+
+        if is_mem_frame or force_permanent:
+            self._add_memory(image, pix_feat, self.last_mask, key, shrinkage, selection,
+                             force_permanent=force_permanent)
+
+        if delete_buffer:
+            self.image_feature_store.delete(self.curr_ti)
+
+        out = unpad(prob_with_bg, self.pad)
+        if resize_needed:
+            out = F.interpolate(out[None], size=(h, w), mode='bilinear', align_corners=False)[0]
+        return out
+
+    def delete_objects(self, objects: List[int]) -> None:
+        self.object_manager.delete_objects(objects)
+        self.memory.purge_except(self.object_manager.all_obj_ids)
+
+    def output_prob_to_mask(self, output_prob: torch.Tensor) -> torch.Tensor:
+        """argmax over channels, then tmp-id -> object-id remap."""
+        return self.object_manager.tmp_to_obj_cls(torch.argmax(output_prob, dim=0))

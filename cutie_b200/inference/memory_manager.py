@@ -1,0 +1,249 @@
+"""Working / long-term / sensory / object memory and THE READOUT.
+
+Public surface and semantics follow cutie/inference/memory_manager.py:14-383; the execution plan does not:
+
+  read()         one fused affinity pass per bucket (similarity -> exact top-k -> softmax, never
+                 materialising the [N, HW] matrix the reference builds four times, memory_utils.py:28-66),
+                 then a sparse k-row gather readout instead of a dense [K*CV, N] x [N, HW] GEMM
+                 (memory_manager.py:77-88); no per-frame torch.stack of the value bank (:90-110).
+  add_memory()   new tokens are transposed straight into preallocated token-major arena slots; FIFO and
+                 consolidation evictions advance a ring head.
+  consolidation  prototype rows are gathered and potentiated by kernels writing directly into the
+                 long-term arena.
+"""
+import logging
+from typing import Dict, List, Optional
+
+import torch
+
+from cutie_b200 import kernels as K_
+from cutie_b200.inference.memory_bank import KeyValueMemoryStore
+from cutie_b200.inference.object_manager import ObjectManager
+
+log = logging.getLogger()
+
+
+class MemoryManager:
+    def __init__(self, cfg, object_manager: ObjectManager):
+        self.object_manager = object_manager
+        self.sensory_dim = cfg.model.sensory_dim
+        self.top_k = cfg.top_k
+        self.chunk_size = cfg.chunk_size
+        self.save_aux = cfg.save_aux
+        self.use_long_term = cfg.use_long_term
+        self.count_long_term_usage = cfg.long_term.count_usage
+        self._read_sizes(cfg)
+
+        self.CK = self.CV = None
+        self.H = self.W = None
+        self.sensory: Dict[int, torch.Tensor] = {}      # obj -> [B, C, h, w]
+        self.obj_v: Dict[int, torch.Tensor] = {}        # obj -> [B, Q, E+1] running sums | area
+        self.work_mem = KeyValueMemoryStore(save_selection=self.use_long_term, save_usage=self.use_long_term,
+                                            ring=True)
+        if self.use_long_term:
+            self.long_mem = KeyValueMemoryStore(save_usage=self.count_long_term_usage, ring=False)
+        self.config_stale = True
+        self.engaged = False
+        self.aux = None
+
+    def _read_sizes(self, cfg):
+        # the first frame lives in permanent memory and is not counted (memory_manager.py:27-38)
+        if self.use_long_term:
+            lt = cfg.long_term
+            self.max_mem_frames = lt.max_mem_frames - 1
+            self.min_mem_frames = lt.min_mem_frames - 1
+            self.num_prototypes = lt.num_prototypes
+            self.max_long_tokens = lt.max_num_tokens
+            self.buffer_tokens = lt.buffer_tokens
+        else:
+            self.max_mem_frames = cfg.max_mem_frames - 1
+
+    def update_config(self, cfg) -> None:
+        self.config_stale = True
+        self.top_k = cfg['top_k']
+        assert self.use_long_term == cfg.use_long_term, 'cannot update this'
+        assert self.count_long_term_usage == cfg.long_term.count_usage, 'cannot update this'
+        self._read_sizes(cfg)
+
+    # -- helpers -----------------------------------------------------------------------------
+    def _get_mask_by_ids(self, mask: torch.Tensor, obj_ids: List[int]) -> torch.Tensor:
+        return mask[:, [self.object_manager.find_tmp_by_id(o) - 1 for o in obj_ids]]
+
+    def _get_sensory_by_ids(self, obj_ids: List[int]) -> torch.Tensor:
+        return torch.stack([self.sensory[o] for o in obj_ids], dim=1)
+
+    def _get_object_mem_by_ids(self, obj_ids: List[int]) -> Optional[torch.Tensor]:
+        if obj_ids[0] not in self.obj_v:
+            return None
+        return torch.stack([self.obj_v[o] for o in obj_ids], dim=1)
+
+    def _segments(self, bucket_id: int, obj_ids: List[int]):
+        segs = []
+        if self.use_long_term and self.long_mem.engaged(bucket_id):
+            segs += self.long_mem.segments(bucket_id, obj_ids)
+        return segs + self.work_mem.segments(bucket_id, obj_ids)
+
+    # -- the readout ---------------------------------------------------------------------------
+    def read(self, pix_feat: torch.Tensor, query_key: torch.Tensor, selection: torch.Tensor,
+             last_mask: torch.Tensor, network) -> Dict[int, torch.Tensor]:
+        """pix_feat [B,C,h,w]; query_key/selection [B,CK,h,w]; last_mask [B,K,H,W] -> {obj: [B,CV,h,w]}."""
+        h, w = pix_feat.shape[-2:]
+        bs = pix_feat.shape[0]
+        assert query_key.shape[0] == bs
+        assert selection.shape[0] == bs
+        assert last_mask.shape[0] == bs
+        qk = query_key.flatten(2).contiguous()
+        qe = selection.flatten(2).contiguous()
+
+        out: Dict[int, torch.Tensor] = {}
+        for bucket_id, bucket in self.work_mem.buckets.items():
+            long_n = self.long_mem.size(bucket_id) if (self.use_long_term and self.long_mem.engaged(bucket_id)) else 0
+            key_segs = self._segments(bucket_id, [])
+            n_total = sum(s.n for s in key_segs)
+            usage_acc = None
+            if self.use_long_term:
+                usage_acc = torch.zeros(bs, n_total, dtype=torch.int64, device=qk.device)
+            idx, wgt, _ = K_.affinity_topk(key_segs, qk, qe, self.top_k, usage_acc=usage_acc)
+            if self.use_long_term:
+                # usage of the temporary working tokens; permanent tokens are skipped (kv:157)
+                self.work_mem.update_bucket_usage(bucket_id, usage_acc,
+                                                  long_n + self.work_mem.perm_size(bucket_id))
+                if long_n and self.count_long_term_usage:
+                    self.long_mem.update_bucket_usage(bucket_id, usage_acc, 0)
+
+            if self.chunk_size < 1:
+                chunks = [bucket]
+            else:
+                chunks = [bucket[i:i + self.chunk_size] for i in range(0, len(bucket), self.chunk_size)]
+            for objects in chunks:
+                this_sensory = self._get_sensory_by_ids(objects)
+                this_last_mask = self._get_mask_by_ids(last_mask, objects)
+                visual = K_.readout_gather(idx, wgt, self._segments(bucket_id, objects))
+                visual = visual.view(bs, len(objects), self.CV, h, w)
+                pixel_readout = network.pixel_fusion(pix_feat, visual, this_sensory, this_last_mask)
+                obj_mem = self._get_object_mem_by_ids(objects)
+                obj_mem = obj_mem.unsqueeze(2) if obj_mem is not None else None
+                readout_memory, aux_features = network.readout_query(pixel_readout, obj_mem)
+                for i, o in enumerate(objects):
+                    out[o] = readout_memory[:, i]
+                if self.save_aux:
+                    self.aux = {
+                        'sensory': this_sensory,
+                        'pixel_readout': pixel_readout,
+                        'q_logits': aux_features['logits'] if aux_features else None,
+                        'q_weights': aux_features['q_weights'] if aux_features else None,
+                        'p_weights': aux_features['p_weights'] if aux_features else None,
+                        'attn_mask': (network.object_transformer.attn_mask_from_fg(aux_features['fg_map']).float()
+                                      if aux_features else None),
+                    }
+        return out
+
+    # -- insertion -----------------------------------------------------------------------------
+    def add_memory(self, key: torch.Tensor, shrinkage: torch.Tensor, msk_value: torch.Tensor,
+                   obj_value: Optional[torch.Tensor], objects: List[int],
+                   selection: Optional[torch.Tensor] = None, *, as_permanent='no') -> None:
+        """key [B,CK,h,w]; shrinkage [B,1,h,w]; msk_value [B,K,CV,h,w]; obj_value [B,K,Q,E+1]."""
+        bs = key.shape[0]
+        assert shrinkage.shape[0] == bs
+        assert msk_value.shape[0] == bs
+        assert obj_value is None or obj_value.shape[0] == bs
+
+        self.engaged = True
+        if self.H is None or self.config_stale:
+            self.config_stale = False
+            self.H, self.W = msk_value.shape[-2:]
+            self.HW = self.H * self.W
+            self.max_work_tokens = self.max_mem_frames * self.HW
+            if self.use_long_term:
+                self.min_work_tokens = self.min_mem_frames * self.HW
+                self.long_mem.set_capacity_hint(temp_tokens=self.max_long_tokens + self.num_prototypes)
+            self.work_mem.set_capacity_hint(temp_tokens=self.max_work_tokens + self.HW, perm_tokens=self.HW)
+
+        key = key.flatten(2)
+        shrinkage = shrinkage.flatten(2)
+        self.CK = key.shape[1]
+        msk_value = msk_value.flatten(3)
+        self.CV = msk_value.shape[2]
+        if selection is not None:
+            selection = selection.flatten(2)
+
+        if obj_value is not None:                       # streaming sums (memory_manager.py:252-271)
+            for i, obj in enumerate(objects):
+                new = obj_value[:, i].contiguous()
+                if obj in self.obj_v:
+                    K_.obj_summary_accumulate(self.obj_v[obj], new)
+                else:
+                    self.obj_v[obj] = new.clone()
+
+        values = {obj: msk_value[:, i] for i, obj in enumerate(objects)}
+        self.work_mem.add(key, values, shrinkage, selection=selection, as_permanent=as_permanent)
+
+        for bucket_id in self.work_mem.buckets.keys():
+            if self.use_long_term:
+                if self.work_mem.non_perm_size(bucket_id) >= self.max_work_tokens:
+                    if self.long_mem.non_perm_size(bucket_id) >= (self.max_long_tokens - self.num_prototypes):
+                        self.long_mem.remove_obsolete_features(
+                            bucket_id, self.max_long_tokens - self.num_prototypes - self.buffer_tokens)
+                    self.compress_features(bucket_id)
+            else:
+                self.work_mem.remove_old_memory(bucket_id, self.max_work_tokens)
+
+    def purge_except(self, obj_keep_idx: List[int]) -> None:
+        """memory_manager.py:298-307 -- including its quirk: obj_v entries of purged objects are kept."""
+        self.work_mem.purge_except(obj_keep_idx)
+        if self.use_long_term and self.long_mem.engaged():
+            self.long_mem.purge_except(obj_keep_idx)
+        self.sensory = {k: v for k, v in self.sensory.items() if k in obj_keep_idx}
+        if not self.work_mem.engaged():
+            self.engaged = False
+
+    # -- long-term consolidation (memory_manager.py:309-358) -------------------------------------
+    def compress_features(self, bucket_id: int) -> None:
+        n_temp = self.work_mem.non_perm_size(bucket_id)
+        n_cand = n_temp - self.min_work_tokens
+        self.consolidation(bucket_id, n_cand)
+        self.work_mem.sieve_by_range(bucket_id, 0, -self.min_work_tokens, min_size=self.min_work_tokens)
+
+    def consolidation(self, bucket_id: int, n_cand: int) -> None:
+        """Candidates = the n_cand oldest temporary working tokens.  Prototypes = the num_prototypes most
+        used candidates (:339); their values/shrinkage are the dense-softmax readout of all candidates
+        (:348-356).  Results are written straight into new long-term arena slots."""
+        objs = self.work_mem.buckets[bucket_id]
+        arena, runs = self.work_mem.temp_runs(bucket_id, 0, n_cand)
+        bs = arena.B
+        dev = arena.device
+        use = torch.cat([arena.view('use', r) for r in runs], 1)
+        life = torch.cat([arena.view('life', r) for r in runs], 1)
+        proto_idx = torch.topk(use / life, k=self.num_prototypes, dim=-1, sorted=True)[1]     # [B, P]
+        P = self.num_prototypes
+        slots = self.long_mem.slots_for_add(objs, P, bs, self.CK, self.CV, dev, supposed_bucket_id=bucket_id)
+        (_, larena, lruns, _), = slots
+        (lrun,) = lruns
+        K_.bank_gather([arena.view('key', r) for r in runs], proto_idx, larena.view('key', lrun))
+        proto_sel = torch.empty(bs, P, self.CK, dtype=torch.float32, device=dev)
+        K_.bank_gather([arena.view('sel', r) for r in runs], proto_idx, proto_sel)
+        cand = self.work_mem.segments(bucket_id, objs, perm=False, temp_start=0, temp_len=n_cand)
+        K_.consolidate(cand, larena.view('key', lrun), proto_sel,
+                       [larena.view(('val', o), lrun) for o in objs], larena.view('shr', lrun))
+
+    # -- sensory memory ------------------------------------------------------------------------------
+    def initialize_sensory_if_needed(self, sample_key: torch.Tensor, ids: List[int]):
+        for obj in ids:
+            if obj not in self.sensory:
+                bs, _, h, w = sample_key.shape
+                self.sensory[obj] = torch.zeros((bs, self.sensory_dim, h, w), device=sample_key.device)
+
+    def update_sensory(self, sensory: torch.Tensor, ids: List[int]):
+        for i, obj in enumerate(ids):
+            self.sensory[obj] = sensory[:, i]
+
+    def get_sensory(self, ids: List[int]):
+        return self._get_sensory_by_ids(ids)
+
+    def clear_non_permanent_memory(self):
+        self.work_mem.clear_non_permanent_memory()
+        if self.use_long_term:
+            self.long_mem.clear_non_permanent_memory()
+
+    def clear_sensory_memory(self):
+        self.sensory = {}

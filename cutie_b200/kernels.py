@@ -1,0 +1,366 @@
+"""ctypes binding of libcutie_b200.so -- the hand-written sm_100a kernels behind the C-ABI in
+include/cutie_b200.h.  Every function here takes CUDA torch tensors (PyTorch owns all memory, kernels
+borrow pointers), enqueues on torch.cuda.current_stream() and never synchronises.
+
+There is NO fallback: if the shared library is missing, or a tensor is not a CUDA fp32/int tensor,
+these functions raise.  (tests/ swap this module's functions for oracle-backed CPU emulations to
+exercise the host logic without a GPU; the product never does.)
+"""
+import ctypes
+import os
+from typing import List, NamedTuple, Optional, Sequence, Tuple
+
+import torch
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib', 'libcutie_b200.so')
+_lib = None
+
+USAGE_FIXED_POINT_BITS = 40     # usage accumulators are uint64 fixed point, 2^-40 resolution
+
+
+class KernelError(RuntimeError):
+    pass
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise KernelError(f'{_LIB_PATH} not found: build it with `python __graft_entry__.py build` '
+                              '(there is no CPU or PyTorch fallback for the Cutie hot path)')
+        _lib = ctypes.CDLL(_LIB_PATH)
+        _lib.cutie_b200_last_error.restype = ctypes.c_char_p
+        _lib.cutie_affinity_workspace_bytes.restype = ctypes.c_size_t
+        _lib.cutie_affinity_workspace_bytes.argtypes = [ctypes.c_int64] * 3 + [ctypes.c_int]
+    return _lib
+
+
+def _check(status: int, what: str):
+    if status != 0:
+        msg = lib().cutie_b200_last_error()
+        raise KernelError(f'{what} failed (status {status}): {msg.decode() if msg else "?"}')
+
+
+def _stream() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor], dtype=torch.float32) -> ctypes.c_void_p:
+    if t is None:
+        return ctypes.c_void_p(0)
+    if not t.is_cuda:
+        raise KernelError('cutie_b200 kernels need CUDA tensors (no CPU path exists)')
+    if t.dtype != dtype:
+        raise KernelError(f'expected {dtype}, got {t.dtype}')
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _i64(v) -> ctypes.c_int64:
+    return ctypes.c_int64(int(v))
+
+
+class BankSegment(NamedTuple):
+    """One physically contiguous run of memory tokens (token-major).
+
+    key [B, n, CK], shrinkage [B, n], values: per-object list of [B, n, CV]; the token axis and the
+    channel axis are contiguous, the batch stride is arbitrary (views into the arena).
+    """
+    key: torch.Tensor
+    shrinkage: torch.Tensor
+    values: Tuple[torch.Tensor, ...] = ()
+
+    @property
+    def n(self) -> int:
+        return self.key.shape[1]
+
+
+def _rows_view_ok(t: torch.Tensor):
+    if t.dim() == 3:
+        assert t.stride(2) == 1 and t.stride(1) == t.shape[2], 'token-major rows must be dense'
+    else:
+        assert t.stride(1) == 1
+
+
+# ---------------------------------------------------------------------------------------------
+# memory readout
+# ---------------------------------------------------------------------------------------------
+def kpad_for(top_k: int) -> int:
+    if top_k <= 32:
+        return 32
+    if top_k <= 64:
+        return 64
+    raise KernelError('top_k > 64 is not supported by the sm_100a top-k kernels')
+
+
+def affinity_topk(segments: Sequence[BankSegment], qk: torch.Tensor, qe: torch.Tensor, top_k: int,
+                  usage_acc: Optional[torch.Tensor] = None, want_sim: bool = False):
+    """Anisotropic-L2 similarity of every query against every memory token of `segments`, exact
+    top-k per query, softmax over the k winners.
+
+    qk, qe: [B, CK, Q] (channel-major, as the key projection emits them).
+    Returns (idx int32 [B,Q,kpad], w f32 [B,Q,kpad], sim f32 [B,Q,kpad] or None); entries >= top_k are
+    (-1, 0).  idx counts tokens across `segments` in order.  Winners are ordered by descending
+    similarity, ties toward the lower index.  If usage_acc (int64 [B, N_total], zeroed by the caller) is
+    given, w * 2^40 is accumulated per token (deterministic integer adds).
+    """
+    B, CK, Q = qk.shape
+    n_total = sum(s.n for s in segments)
+    if n_total < top_k:
+        raise KernelError(f'selected index k out of range: top_k={top_k} > {n_total} memory tokens')
+    kpad = kpad_for(top_k)
+    dev = qk.device
+    idx = torch.empty(B, Q, kpad, dtype=torch.int32, device=dev)
+    w = torch.empty(B, Q, kpad, dtype=torch.float32, device=dev)
+    sim = torch.empty(B, Q, kpad, dtype=torch.float32, device=dev) if want_sim else None
+    L = lib()
+    ws_bytes = L.cutie_affinity_workspace_bytes(B, Q, n_total, top_k)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    ns = len(segments)
+    assert 1 <= ns <= 4
+    for s in segments:
+        _rows_view_ok(s.key), _rows_view_ok(s.shrinkage)
+        assert s.key.shape[2] == CK
+    assert qk.is_contiguous() and qe.is_contiguous()
+    PA, IA = ctypes.c_void_p * ns, ctypes.c_int64 * ns
+    st = L.cutie_affinity_topk(
+        ctypes.c_int(ns), PA(*[s.key.data_ptr() for s in segments]),
+        PA(*[s.shrinkage.data_ptr() for s in segments]), IA(*[s.n for s in segments]),
+        IA(*[s.key.stride(0) for s in segments]), IA(*[s.shrinkage.stride(0) for s in segments]),
+        _ptr(qk), _ptr(qe), _i64(B), _i64(CK), _i64(Q), ctypes.c_int(top_k), ctypes.c_int(kpad),
+        _ptr(idx, torch.int32), _ptr(w), _ptr(sim), _ptr(usage_acc, torch.int64), _i64(n_total),
+        _ptr(ws, torch.uint8), ctypes.c_size_t(ws_bytes), _stream())
+    _check(st, 'cutie_affinity_topk')
+    return idx, w, sim
+
+
+def readout_gather(idx: torch.Tensor, w: torch.Tensor, segments: Sequence[BankSegment],
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[b,k,c,q] = sum_j w[b,q,j] * V_k[idx[b,q,j], c]  ->  [B, K, CV, Q] (a6, evaluated sparsely)."""
+    B, Q, kpad = idx.shape
+    K = len(segments[0].values)
+    CV = segments[0].values[0].shape[2]
+    if out is None:
+        out = torch.empty(B, K, CV, Q, dtype=torch.float32, device=idx.device)
+    ns = len(segments)
+    ptrs, strides = [], []
+    for s in segments:
+        assert len(s.values) == K
+        for v in s.values:
+            _rows_view_ok(v)
+            ptrs.append(v.data_ptr())
+            strides.append(v.stride(0))
+    PA, IA, IS = ctypes.c_void_p * (ns * K), ctypes.c_int64 * (ns * K), ctypes.c_int64 * ns
+    st = lib().cutie_readout_gather(_ptr(idx, torch.int32), _ptr(w), _i64(B), _i64(Q), ctypes.c_int(kpad),
+                                    ctypes.c_int(ns), IS(*[s.n for s in segments]), PA(*ptrs), IA(*strides),
+                                    _i64(K), _i64(CV), _ptr(out), _stream())
+    _check(st, 'cutie_readout_gather')
+    return out
+
+
+def usage_commit(use_cnt: torch.Tensor, life_cnt: torch.Tensor, usage_acc: torch.Tensor, acc_offset: int):
+    """use_cnt[b,i] += usage_acc[b, acc_offset+i] * 2^-40 ; life_cnt[b,i] += 1   (kv_memory_store.py:151-162)."""
+    B, n = use_cnt.shape
+    if n == 0:
+        return
+    st = lib().cutie_usage_commit(_ptr(use_cnt), _i64(use_cnt.stride(0)), _ptr(life_cnt), _i64(life_cnt.stride(0)),
+                                  _ptr(usage_acc, torch.int64), _i64(usage_acc.stride(0)), _i64(acc_offset),
+                                  _i64(B), _i64(n), _stream())
+    _check(st, 'cutie_usage_commit')
+
+
+# ---------------------------------------------------------------------------------------------
+# memory bank maintenance (a17, a18)
+# ---------------------------------------------------------------------------------------------
+def bank_append(src: torch.Tensor, dst_rows: torch.Tensor):
+    """dst_rows[b, i, c] = src[b, c, i]: channel-major feature map [B, C, n] -> token-major rows [B, n, C]."""
+    B, C, n = src.shape
+    assert dst_rows.shape == (B, n, C)
+    _rows_view_ok(dst_rows)
+    assert src.stride(2) == 1 and src.stride(1) == n
+    st = lib().cutie_bank_append(_ptr(src), _i64(src.stride(0)), _ptr(dst_rows), _i64(dst_rows.stride(0)),
+                                 _i64(B), _i64(C), _i64(n), _stream())
+    _check(st, 'cutie_bank_append')
+
+
+def bank_export(rows: torch.Tensor, dst: torch.Tensor):
+    """dst[b, c, i] = rows[b, i, c] (token-major -> channel-major; used for the reference-shaped views)."""
+    B, n, C = rows.shape
+    assert dst.shape == (B, C, n) and dst.is_contiguous()
+    _rows_view_ok(rows)
+    st = lib().cutie_bank_export(_ptr(rows), _i64(rows.stride(0)), _ptr(dst), _i64(dst.stride(0)),
+                                 _i64(B), _i64(C), _i64(n), _stream())
+    _check(st, 'cutie_bank_export')
+
+
+def bank_gather(segments_rows: Sequence[torch.Tensor], index: torch.Tensor, dst_rows: torch.Tensor):
+    """dst_rows[b, j, :] = concat(segments_rows)[b, index[b, j], :]   (token-major gather; a18 eviction /
+    prototype selection).  index int64 [B, m]."""
+    B, m = index.shape
+    C = dst_rows.shape[2]
+    assert dst_rows.shape[:2] == (B, m)
+    ns = len(segments_rows)
+    assert 1 <= ns <= 4
+    for r in segments_rows:
+        _rows_view_ok(r)
+    _rows_view_ok(dst_rows)
+    PA, IA = ctypes.c_void_p * ns, ctypes.c_int64 * ns
+    st = lib().cutie_bank_gather(ctypes.c_int(ns), PA(*[r.data_ptr() for r in segments_rows]),
+                                 IA(*[r.shape[1] for r in segments_rows]), IA(*[r.stride(0) for r in segments_rows]),
+                                 _ptr(index, torch.int64), _ptr(dst_rows), _i64(dst_rows.stride(0)),
+                                 _i64(B), _i64(m), _i64(C), _stream())
+    _check(st, 'cutie_bank_gather')
+
+
+def consolidate(segments: Sequence[BankSegment], proto_key: torch.Tensor, proto_sel: torch.Tensor,
+                out_values: Sequence[torch.Tensor], out_shrinkage: torch.Tensor):
+    """Potentiation (memory_manager.py:345-356): dense max-subtracted softmax over all candidate tokens
+    of `segments` for each prototype, then weighted sums of candidate values and shrinkage.
+
+    proto_key, proto_sel: [B, P, CK] token-major.  out_values[k]: [B, P, CV] rows; out_shrinkage [B, P].
+    """
+    B, P, CK = proto_key.shape
+    ns = len(segments)
+    K = len(out_values)
+    n_total = sum(s.n for s in segments)
+    ws = torch.empty(B * P * n_total, dtype=torch.float32, device=proto_key.device)
+    PA, IA = ctypes.c_void_p * ns, ctypes.c_int64 * ns
+    VA, VI = ctypes.c_void_p * (ns * K), ctypes.c_int64 * (ns * K)
+    OA, OI = ctypes.c_void_p * K, ctypes.c_int64 * K
+    vp, vs = [], []
+    for s in segments:
+        for v in s.values:
+            vp.append(v.data_ptr()), vs.append(v.stride(0))
+    for t in (proto_key, proto_sel):
+        _rows_view_ok(t)
+    st = lib().cutie_consolidate(
+        ctypes.c_int(ns), PA(*[s.key.data_ptr() for s in segments]), PA(*[s.shrinkage.data_ptr() for s in segments]),
+        IA(*[s.n for s in segments]), IA(*[s.key.stride(0) for s in segments]),
+        IA(*[s.shrinkage.stride(0) for s in segments]), VA(*vp), VI(*vs), _i64(K),
+        _ptr(proto_key), _i64(proto_key.stride(0)), _ptr(proto_sel), _i64(proto_sel.stride(0)),
+        _i64(B), _i64(P), _i64(CK), _i64(out_values[0].shape[2] if K else 0),
+        OA(*[v.data_ptr() for v in out_values]), OI(*[v.stride(0) for v in out_values]),
+        _ptr(out_shrinkage), _i64(out_shrinkage.stride(0)), _ptr(ws), _i64(n_total), _stream())
+    _check(st, 'cutie_consolidate')
+
+
+def obj_summary_accumulate(acc: torch.Tensor, new: torch.Tensor):
+    """acc += new  (streaming object-memory sum, memory_manager.py:252-271).  Both [B, Q, E+1] dense."""
+    assert acc.is_contiguous() and new.is_contiguous() and acc.shape == new.shape
+    st = lib().cutie_obj_summary_accumulate(_ptr(acc), _ptr(new), _i64(acc.numel()), _stream())
+    _check(st, 'cutie_obj_summary_accumulate')
+
+
+# ---------------------------------------------------------------------------------------------
+# object transformer (a9-a15)
+# ---------------------------------------------------------------------------------------------
+def qt_linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], *,
+              ln: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, pe: Optional[torch.Tensor] = None,
+              summary_norm: bool = False, relu: bool = False, residual: Optional[torch.Tensor] = None,
+              residual_mod: int = 0, xhat_out: Optional[torch.Tensor] = None,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Skinny fused linear for the [B*K*16, 256] query tile:
+         xin = x                                   (or sums/(area+1e-4) if summary_norm: x is [M, Kd+1])
+         xin = LayerNorm(xin; ln) if ln else xin   (xhat_out <- this, if given)
+         xin = xin + pe if pe is not None
+         y   = xin @ weight^T + bias ; relu ; + residual[m % residual_mod if residual_mod else m]
+    x [M, Kd(+1)], weight [N, Kd] (row-major, may be a row-slice view), returns y [M, N].
+    """
+    M = x.shape[0]
+    N, Kd = weight.shape
+    assert weight.stride(1) == 1
+    assert x.is_contiguous() and x.shape[1] == Kd + (1 if summary_norm else 0)
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=x.device)
+    if ln is not None:
+        assert Kd == 256, 'fused LayerNorm supports embed_dim 256'
+    st = lib().cutie_qt_linear(
+        _ptr(x), _i64(M), _i64(Kd), _ptr(weight), _i64(weight.stride(0)), _i64(N), _ptr(bias),
+        _ptr(ln[0] if ln else None), _ptr(ln[1] if ln else None), _ptr(pe), ctypes.c_int(int(summary_norm)),
+        ctypes.c_int(int(relu)), _ptr(residual), _i64(residual_mod), _ptr(xhat_out), _ptr(out), _stream())
+    _check(st, 'cutie_qt_linear')
+    return out
+
+
+def qt_head_fold(a: torch.Tensor, weight: torch.Tensor, *, transpose_w: bool, scale: float,
+                 bias_vec: Optional[torch.Tensor] = None, num_heads: int = 8):
+    """Per-head fold of a projected [M, E] tile into the other side's input space:
+         out[m, h, c] = scale * sum_{d<E/H} a[m, h*d_h + d] * Wx[h*d_h + d, c],  Wx = W or W^T
+         dots[m, h]   = scale * sum_d a[m, h*d_h + d] * bias_vec[h*d_h + d]   (if bias_vec)
+    Returns (out [M, H, E], dots [M, H] or None).
+    """
+    M, E = a.shape
+    assert weight.shape == (E, E) and weight.stride(1) == 1
+    out = torch.empty(M, num_heads, E, dtype=torch.float32, device=a.device)
+    dots = torch.empty(M, num_heads, dtype=torch.float32, device=a.device) if bias_vec is not None else None
+    st = lib().cutie_qt_head_fold(_ptr(a), _i64(M), _i64(E), ctypes.c_int(num_heads), _ptr(weight),
+                                  _i64(weight.stride(0)), ctypes.c_int(int(transpose_w)), ctypes.c_float(scale),
+                                  _ptr(bias_vec), _ptr(out), _ptr(dots), _stream())
+    _check(st, 'cutie_qt_head_fold')
+    return out, dots
+
+
+def qt_self_attention(qk: torch.Tensor, v: torch.Tensor, num_queries: int, num_heads: int = 8) -> torch.Tensor:
+    """softmax(Q_h K_h^T / sqrt(d)) V_h for every (object, head); qk [M, 2E] = [Q | K], v [M, E] -> [M, E]."""
+    M, E2 = qk.shape
+    E = E2 // 2
+    out = torch.empty(M, E, dtype=torch.float32, device=qk.device)
+    st = lib().cutie_qt_self_attention(_ptr(qk), _ptr(v), _i64(M), _i64(E), ctypes.c_int(num_queries),
+                                       ctypes.c_int(num_heads), _ptr(out), _stream())
+    _check(st, 'cutie_qt_self_attention')
+    return out
+
+
+def qt_aux_mask(pixel: torch.Tensor, w: torch.Tensor, b: torch.Tensor, B: int, K: int):
+    """mask_pred + sigmoid + aggregate + foreground test (a15) in one pass over pixel [B*K, E, HW].
+    Returns (aux_logits f32 [B,K,HW], fg uint8 [B,K,HW], fg_count int32 [B*K])."""
+    BK, E, HW = pixel.shape
+    dev = pixel.device
+    logits = torch.empty(B, K, HW, dtype=torch.float32, device=dev)
+    fg = torch.empty(B, K, HW, dtype=torch.uint8, device=dev)
+    cnt = torch.zeros(BK, dtype=torch.int32, device=dev)
+    st = lib().cutie_qt_aux_mask(_ptr(pixel), _ptr(w), _ptr(b), _i64(B), _i64(K), _i64(E), _i64(HW),
+                                 _ptr(logits), _ptr(fg, torch.uint8), _ptr(cnt, torch.int32), _stream())
+    _check(st, 'cutie_qt_aux_mask')
+    return logits, fg, cnt
+
+
+def qt_pixel_to_query(qfold: torch.Tensor, pixel: torch.Tensor, pixel_pe: torch.Tensor, fg: torch.Tensor,
+                      fg_count: torch.Tensor, wv: torch.Tensor, bv: torch.Tensor, num_queries: int,
+                      num_heads: int = 8) -> torch.Tensor:
+    """read_from_pixel attention core (a11) for all objects/heads:
+         scores[(i,h), p] = qfold[m=(bk,i), h, :] . (pixel+pixel_pe)[bk, :, p]  (scale pre-folded)
+         foreground queries (i < Q/2) see only fg pixels, background queries only non-fg (a15 rules),
+         P = softmax_p(scores), Z = P . pixel^T, attn[m, h*d+e] = Z[(i,h), :] . wv[h*d+e, :] + bv[h*d+e]
+    Returns attn [M, E] (to be passed through the output projection by qt_linear)."""
+    M, H, E = qfold.shape
+    BK, _, HW = pixel.shape
+    dev = pixel.device
+    out = torch.empty(M, E, dtype=torch.float32, device=dev)
+    L = lib()
+    L.cutie_qt_pixel_to_query_splits.restype = ctypes.c_int
+    splits = L.cutie_qt_pixel_to_query_splits(_i64(BK), _i64(HW), ctypes.c_int(num_heads))
+    ws = torch.empty(BK * num_heads * splits * num_queries * (E + 2), dtype=torch.float32, device=dev)
+    st = L.cutie_qt_pixel_to_query(_ptr(qfold), _ptr(pixel), _ptr(pixel_pe), _ptr(fg, torch.uint8),
+                                   _ptr(fg_count, torch.int32), _ptr(wv), _i64(wv.stride(0)), _ptr(bv),
+                                   _i64(BK), _i64(E), _i64(HW), ctypes.c_int(num_queries), ctypes.c_int(num_heads),
+                                   ctypes.c_int(splits), _ptr(ws), _ptr(out), _stream())
+    _check(st, 'cutie_qt_pixel_to_query')
+    return out
+
+
+def qt_query_to_pixel(kfold: torch.Tensor, kdots: torch.Tensor, vfold: torch.Tensor, out_bias: torch.Tensor,
+                      pixel: torch.Tensor, pixel_pe: torch.Tensor, num_queries: int, num_heads: int = 8,
+                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """read_from_query (a13) fully fused on the pixel side, channel-major in and out:
+         s[p, (j,h)] = (pixel+pixel_pe)[:, p] . kfold[(bk,j), h, :] + kdots[(bk,j), h]
+         P = softmax over the Q queries j within each head
+         out[:, p] = pixel[:, p] + out_bias + sum_{j,h} P[p,(j,h)] * vfold[(bk,j), h, :]
+    """
+    BK, E, HW = pixel.shape
+    if out is None:
+        out = torch.empty_like(pixel)
+    st = lib().cutie_qt_query_to_pixel(_ptr(kfold), _ptr(kdots), _ptr(vfold), _ptr(out_bias), _ptr(pixel),
+                                       _ptr(pixel_pe), _i64(BK), _i64(E), _i64(HW), ctypes.c_int(num_queries),
+                                       ctypes.c_int(num_heads), _ptr(out), _stream())
+    _check(st, 'cutie_qt_query_to_pixel')
+    return out

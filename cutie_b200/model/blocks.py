@@ -1,0 +1,138 @@
+"""Per-object ("group") convolution blocks around the hot path -- cuDNN via PyTorch, unchanged in role.
+
+Tensors named g carry an object axis: [B, K, C, H, W]; x tensors are shared across objects [B, C, H, W].
+State-dict names mirror the reference (cutie/model/group_modules.py:39-126, cutie/model/channel_attn.py:7-39,
+cutie/model/modules.py:8-85) so checkpoints load; the code is a fresh restatement.
+"""
+import math
+from typing import List
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+def fold(g: torch.Tensor) -> torch.Tensor:
+    return g.reshape(g.shape[0] * g.shape[1], *g.shape[2:])
+
+
+def unfold(t: torch.Tensor, B: int) -> torch.Tensor:
+    return t.reshape(B, t.shape[0] // B, *t.shape[1:])
+
+
+def resize_objects(g: torch.Tensor, ratio: float, mode: str) -> torch.Tensor:
+    B = g.shape[0]
+    kw = dict(align_corners=False) if mode == 'bilinear' else {}
+    return unfold(F.interpolate(fold(g), scale_factor=ratio, mode=mode, **kw), B)
+
+
+class ObjConv2d(nn.Conv2d):
+    """nn.Conv2d applied independently to every object (group_modules.py:39-43)."""
+
+    def forward(self, g: torch.Tensor) -> torch.Tensor:
+        return unfold(super().forward(fold(g)), g.shape[0])
+
+
+class ChannelAttnResBlock(nn.Module):
+    """relu-conv3x3-relu-conv3x3, ECA channel gate, residual (channel_attn.py:7-39)."""
+
+    def __init__(self, c_in: int, c_out: int):
+        super().__init__()
+        self.conv1 = nn.Conv2d(c_in, c_out, 3, padding=1)
+        self.conv2 = nn.Conv2d(c_out, c_out, 3, padding=1)
+        t = int((abs(math.log2(c_out)) + 1) // 2)
+        k = t if t % 2 else t + 1
+        self.conv = nn.Conv1d(1, 1, k, padding=(k - 1) // 2, bias=False)
+        self.downsample = nn.Identity() if c_in == c_out else nn.Conv2d(c_in, c_out, 1)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        y = self.conv2(F.relu(self.conv1(F.relu(x))))
+        gate = self.conv(y.mean(dim=(2, 3)).unsqueeze(1)).sigmoid().transpose(1, 2).unsqueeze(-1)
+        return y * gate + self.downsample(x)
+
+
+class ObjResBlock(nn.Module):
+    """group_modules.py:46-64."""
+
+    def __init__(self, c_in: int, c_out: int):
+        super().__init__()
+        self.downsample = nn.Identity() if c_in == c_out else ObjConv2d(c_in, c_out, 1)
+        self.conv1 = ObjConv2d(c_in, c_out, 3, padding=1)
+        self.conv2 = ObjConv2d(c_out, c_out, 3, padding=1)
+
+    def forward(self, g):
+        y = self.conv2(F.relu(self.conv1(F.relu(g))))
+        return y + self.downsample(g)
+
+
+class _AddDistributor(nn.Module):
+    """x_transform(x) broadcast over objects + g_transform(g) (group_modules.py:67-104, method='add')."""
+
+    def __init__(self, x_dim: int, g_dim: int, out_dim: int):
+        super().__init__()
+        self.x_transform = nn.Conv2d(x_dim, out_dim, 1)
+        self.g_transform = ObjConv2d(g_dim, out_dim, 1)
+
+    def forward(self, x, g):
+        return self.x_transform(x).unsqueeze(1) + self.g_transform(g)
+
+
+class FeatureFusion(nn.Module):
+    """group_modules.py:107-126: fuse a shared feature map into per-object features."""
+
+    def __init__(self, x_dim: int, g_dim: int, out_dim: int):
+        super().__init__()
+        self.distributor = _AddDistributor(x_dim, g_dim, out_dim)
+        self.block1 = ChannelAttnResBlock(out_dim, out_dim)
+        self.block2 = ChannelAttnResBlock(out_dim, out_dim)
+
+    def forward(self, x, g):
+        B = g.shape[0]
+        return unfold(self.block2(self.block1(fold(self.distributor(x, g)))), B)
+
+
+class UpsampleBlock(nn.Module):
+    """modules.py:8-20: x2 bilinear upsample of g, add skip feature, ObjResBlock."""
+
+    def __init__(self, c_in: int, c_out: int):
+        super().__init__()
+        self.out_conv = ObjResBlock(c_in, c_out)
+
+    def forward(self, g, skip):
+        return self.out_conv(resize_objects(g, 2, 'bilinear') + skip.unsqueeze(1))
+
+
+def gated_update(h: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
+    """modules.py:37-45: GRU-like update; v carries [forget | update | candidate] along channels."""
+    d = v.shape[2] // 3
+    f = torch.sigmoid(v[:, :, :d])
+    u = torch.sigmoid(v[:, :, d:2 * d])
+    n = torch.tanh(v[:, :, 2 * d:])
+    return f * h * (1 - u) + u * n
+
+
+class MultiScaleSensoryUpdater(nn.Module):
+    """modules.py:46-68 (decoder side): fuse stride-16/8/4 object features into the sensory memory."""
+
+    def __init__(self, g_dims: List[int], mid_dim: int, sensory_dim: int):
+        super().__init__()
+        self.g16_conv = ObjConv2d(g_dims[0], mid_dim, 1)
+        self.g8_conv = ObjConv2d(g_dims[1], mid_dim, 1)
+        self.g4_conv = ObjConv2d(g_dims[2], mid_dim, 1)
+        self.transform = ObjConv2d(mid_dim + sensory_dim, sensory_dim * 3, 3, padding=1)
+
+    def forward(self, g16, g8, g4, h):
+        g = self.g16_conv(g16) + self.g8_conv(resize_objects(g8, 1 / 2, 'area')) + \
+            self.g4_conv(resize_objects(g4, 1 / 4, 'area'))
+        return gated_update(h.float(), self.transform(torch.cat([g.float(), h.float()], 2)))
+
+
+class DeepSensoryUpdater(nn.Module):
+    """modules.py:71-85 (mask-encoder side)."""
+
+    def __init__(self, f_dim: int, sensory_dim: int):
+        super().__init__()
+        self.transform = ObjConv2d(f_dim + sensory_dim, sensory_dim * 3, 3, padding=1)
+
+    def forward(self, g, h):
+        return gated_update(h.float(), self.transform(torch.cat([g.float(), h.float()], 2)))

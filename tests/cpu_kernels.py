@@ -1,0 +1,214 @@
+"""TEST-ONLY CPU emulation of cutie_b200.kernels, built on oracle/ math.
+
+Lets the `-m "not gpu"` suite exercise the HOST logic (arena bookkeeping, bucket/permanence rules,
+consolidation schedule, the folded-attention algebra in QueryTransformer, InferenceCore.step control
+flow) in a container without a GPU, by monkeypatching the ctypes wrappers with functions that honour
+exactly the same contracts.  The product never imports this file; on a GPU box the real kernels run and
+are compared against the same oracle in tests/test_gpu_*.py.
+"""
+import math
+
+import torch
+
+from oracle import memory_math as mm
+
+
+def _cat_rows(rows):
+    return torch.cat(list(rows), dim=1)
+
+
+def affinity_topk(segments, qk, qe, top_k, usage_acc=None, want_sim=False):
+    from cutie_b200.kernels import kpad_for, KernelError
+    keys = _cat_rows([s.key for s in segments])                 # [B,N,CK]
+    shr = _cat_rows([s.shrinkage for s in segments])            # [B,N]
+    B, N, CK = keys.shape
+    if N < top_k:
+        raise KernelError('selected index k out of range')
+    sim = mm.similarity_direct(keys.transpose(1, 2), shr.unsqueeze(1), qk, qe, dtype=torch.float64)
+    # descending similarity, ties toward the lower index (the kernels' documented rule)
+    order = torch.argsort(-sim, dim=1, stable=True)[:, :top_k]          # [B,k,Q]
+    vals = torch.gather(sim, 1, order).float()
+    e = (vals - vals[:, :1]).exp()
+    w = e / e.sum(1, keepdim=True)
+    kpad = kpad_for(top_k)
+    Q = qk.shape[-1]
+    idx_o = torch.full((B, Q, kpad), -1, dtype=torch.int32)
+    w_o = torch.zeros(B, Q, kpad)
+    idx_o[:, :, :top_k] = order.transpose(1, 2).int()
+    w_o[:, :, :top_k] = w.transpose(1, 2)
+    sim_o = None
+    if want_sim:
+        sim_o = torch.zeros(B, Q, kpad)
+        sim_o[:, :, :top_k] = vals.transpose(1, 2)
+    if usage_acc is not None:
+        fx = (w.double() * 2.0 ** 40).to(torch.int64)                   # [B,k,Q]
+        for b in range(B):
+            usage_acc[b].index_add_(0, order[b].reshape(-1), fx[b].reshape(-1))
+    return idx_o, w_o, sim_o
+
+
+def readout_gather(idx, w, segments, out=None):
+    K = len(segments[0].values)
+    vals = [_cat_rows([s.values[k] for s in segments]) for k in range(K)]   # K x [B,N,CV]
+    B, Q, kpad = idx.shape
+    CV = vals[0].shape[2]
+    res = torch.zeros(B, K, CV, Q)
+    safe = idx.clamp(min=0).long()
+    for b in range(B):
+        for k in range(K):
+            g = vals[k][b][safe[b].reshape(-1)].reshape(Q, kpad, CV)         # [Q,kpad,CV]
+            res[b, k] = (g * w[b].unsqueeze(-1)).sum(1).t()
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
+
+
+def usage_commit(use_cnt, life_cnt, usage_acc, acc_offset):
+    n = use_cnt.shape[1]
+    use_cnt += (usage_acc[:, acc_offset:acc_offset + n].double() * 2.0 ** -40).float()
+    life_cnt += 1
+
+
+def bank_append(src, dst_rows):
+    dst_rows.copy_(src.transpose(1, 2))
+
+
+def bank_export(rows, dst):
+    dst.copy_(rows.transpose(1, 2))
+
+
+def bank_gather(segments_rows, index, dst_rows):
+    allr = _cat_rows(segments_rows)
+    for b in range(index.shape[0]):
+        dst_rows[b] = allr[b][index[b]]
+
+
+def consolidate(segments, proto_key, proto_sel, out_values, out_shrinkage):
+    keys = _cat_rows([s.key for s in segments]).transpose(1, 2)         # [B,CK,N]
+    shr = _cat_rows([s.shrinkage for s in segments]).unsqueeze(1)       # [B,1,N]
+    sim = mm.similarity_expanded(keys, shr, proto_key.transpose(1, 2), proto_sel.transpose(1, 2))
+    aff = mm.dense_softmax(sim)                                          # [B,N,P]
+    for k, ov in enumerate(out_values):
+        v = _cat_rows([s.values[k] for s in segments])                   # [B,N,CV]
+        ov.copy_(torch.matmul(aff.transpose(1, 2), v))
+    out_shrinkage.copy_(torch.matmul(aff.transpose(1, 2), shr.transpose(1, 2)).squeeze(-1))
+
+
+def obj_summary_accumulate(acc, new):
+    acc += new
+
+
+def qt_linear(x, weight, bias, *, ln=None, pe=None, summary_norm=False, relu=False, residual=None,
+              residual_mod=0, xhat_out=None, out=None):
+    xin = x
+    if summary_norm:
+        xin = x[:, :-1] / (x[:, -1:] + 1e-4)
+    if ln is not None:
+        xin = torch.nn.functional.layer_norm(xin, (xin.shape[-1],), ln[0], ln[1], 1e-5)
+        if xhat_out is not None:
+            xhat_out.copy_(xin)
+    if pe is not None:
+        xin = xin + pe
+    y = xin @ weight.t()
+    if bias is not None:
+        y = y + bias
+    if relu:
+        y = torch.relu(y)
+    if residual is not None:
+        if residual_mod:
+            y = y + residual[torch.arange(y.shape[0]) % residual_mod]
+        else:
+            y = y + residual
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
+def qt_head_fold(a, weight, *, transpose_w, scale, bias_vec=None, num_heads=8):
+    M, E = a.shape
+    d = E // num_heads
+    wx = weight.t() if transpose_w else weight                # Wx[r, c]
+    ah = a.reshape(M, num_heads, d)
+    out = scale * torch.einsum('mhd,hdc->mhc', ah, wx.reshape(num_heads, d, E))
+    dots = None
+    if bias_vec is not None:
+        dots = scale * torch.einsum('mhd,hd->mh', ah, bias_vec.reshape(num_heads, d))
+    return out.contiguous(), dots
+
+
+def qt_self_attention(qk, v, num_queries, num_heads=8):
+    M, E2 = qk.shape
+    E = E2 // 2
+    d = E // num_heads
+    n = M // num_queries
+    q = qk[:, :E].reshape(n, num_queries, num_heads, d).transpose(1, 2)
+    k = qk[:, E:].reshape(n, num_queries, num_heads, d).transpose(1, 2)
+    vv = v.reshape(n, num_queries, num_heads, d).transpose(1, 2)
+    p = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(d), -1)
+    return (p @ vv).transpose(1, 2).reshape(M, E)
+
+
+def qt_aux_mask(pixel, w, b, B, K):
+    BK, E, HW = pixel.shape
+    logits = (torch.relu(pixel) * w.view(1, E, 1)).sum(1) + b                 # [BK,HW]
+    logits = logits.view(B, K, HW)
+    p = logits.sigmoid()
+    bg = torch.prod(1 - p, dim=1, keepdim=True)
+    allp = torch.cat([bg, p], 1).clamp(1e-7, 1 - 1e-7)
+    lg = torch.log(allp / (1 - allp))
+    fg = (lg[:, 1:] >= lg.max(1, keepdim=True)[0])
+    return logits, fg.to(torch.uint8), fg.reshape(BK, HW).sum(1).int()
+
+
+def qt_pixel_to_query(qfold, pixel, pixel_pe, fg, fg_count, wv, bv, num_queries, num_heads=8):
+    M, H, E = qfold.shape
+    BK, _, HW = pixel.shape
+    Q = num_queries
+    d = E // H
+    kin = pixel + pixel_pe                                                    # [BK,E,HW]
+    qf = qfold.reshape(BK, Q, H, E)
+    s = torch.einsum('nqhc,ncp->nqhp', qf, kin)                               # [BK,Q,H,HW]
+    f = fg.reshape(BK, HW).bool()
+    half = Q // 2
+    blocked = torch.cat([(~f)[:, None].expand(BK, half, HW), f[:, None].expand(BK, half, HW)], 1).clone()
+    none_fg = (fg_count == 0)
+    all_fg = (fg_count == HW)
+    blocked[none_fg, :half] = False
+    blocked[all_fg, half:] = False
+    s = s.masked_fill(blocked[:, :, None, :], float('-inf'))
+    p = torch.softmax(s, -1)
+    z = torch.einsum('nqhp,ncp->nqhc', p, pixel)                              # [BK,Q,H,E]
+    attn = torch.einsum('nqhc,hdc->nqhd', z, wv.reshape(H, d, E)) + bv.reshape(H, d)
+    return attn.reshape(M, E)
+
+
+def qt_query_to_pixel(kfold, kdots, vfold, out_bias, pixel, pixel_pe, num_queries, num_heads=8, out=None):
+    BK, E, HW = pixel.shape
+    Q, H = num_queries, num_heads
+    kf = kfold.reshape(BK, Q, H, E)
+    s = torch.einsum('ncp,nqhc->nphq', pixel + pixel_pe, kf) + kdots.reshape(BK, Q, H).permute(0, 2, 1)[:, None]
+    p = torch.softmax(s, -1)                                                  # over the Q queries
+    upd = torch.einsum('nphq,nqhc->ncp', p, vfold.reshape(BK, Q, H, E))
+    res = pixel + upd + out_bias.view(1, E, 1)
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
+
+
+ALL = ['affinity_topk', 'readout_gather', 'usage_commit', 'bank_append', 'bank_export', 'bank_gather',
+       'consolidate', 'obj_summary_accumulate', 'qt_linear', 'qt_head_fold', 'qt_self_attention',
+       'qt_aux_mask', 'qt_pixel_to_query', 'qt_query_to_pixel']
+
+
+def install(monkeypatch=None):
+    """Swap the ctypes wrappers for the emulations above (test-only)."""
+    import cutie_b200.kernels as K_
+    g = globals()
+    for name in ALL:
+        if monkeypatch is not None:
+            monkeypatch.setattr(K_, name, g[name])
+        else:
+            setattr(K_, name, g[name])
