@@ -1,0 +1,593 @@
+// Object-transformer kernels for sm_100a (fp32).  Shapes are the model's fixed ones: embed 256, 8 heads
+// of 32, 16 object queries; the pixel axis (HW) and the number of objects are free.
+// All pixel-side tensors are channel-major [B*K, 256, HW] (what the cuDNN convolutions around these
+// kernels produce and consume), so lanes run along the contiguous pixel axis.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace cutie {
+
+constexpr int E_ = 256;   // embed dim
+constexpr int H_ = 8;     // heads
+constexpr int DH = 32;    // head dim
+constexpr int NQ = 16;    // object queries
+
+// ------------------------------------------------------------------------------------------------
+// skinny fused linear: y[M,N] = epi( pro(x)[M,Kd] . W[N,Kd]^T )
+// CTA tile 32 rows x BN cols, 256 threads, K chunks of 32 through smem.
+struct LinearParams {
+  const float* x;
+  long long M, Kd, ldx;
+  const float* W;
+  long long ldw, N;
+  const float* bias;
+  const float* ln_w;
+  const float* ln_b;
+  const float* pe;
+  int summary_norm, relu;
+  const float* residual;
+  long long residual_mod;
+  float* xhat_out;
+  float* y;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(256) qt_linear_kernel(const LinearParams p) {
+  constexpr int BM = 32, BK = 32;
+  constexpr int OPT = BN / 8;  // outputs per thread
+  __shared__ float xs[BM][BK + 1];
+  __shared__ float wsm[BN][BK + 1];
+  __shared__ float mean_s[BM], rstd_s[BM], den_s[BM];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long m0 = (long long)blockIdx.y * BM, n0 = (long long)blockIdx.x * BN;
+  // ---- prologue: per-row statistics ----
+  for (int r = warp; r < BM; r += 8) {
+    const long long m = m0 + r;
+    float den = 1.f, mean = 0.f, rstd = 1.f;
+    if (m < p.M) {
+      if (p.summary_norm) den = 1.f / (p.x[m * p.ldx + p.Kd] + 1e-4f);
+      if (p.ln_w) {
+        float s = 0.f;
+        for (long long k = lane; k < p.Kd; k += 32) s += p.x[m * p.ldx + k] * den;
+        mean = warp_sum(s) / (float)p.Kd;
+        float v = 0.f;
+        for (long long k = lane; k < p.Kd; k += 32) {
+          float d = p.x[m * p.ldx + k] * den - mean;
+          v += d * d;
+        }
+        rstd = rsqrtf(warp_sum(v) / (float)p.Kd + 1e-5f);
+      }
+    }
+    if (lane == 0) { mean_s[r] = mean; rstd_s[r] = rstd; den_s[r] = den; }
+  }
+  __syncthreads();
+  const int r_t = tid >> 3, cg = tid & 7;
+  float acc[OPT];
+#pragma unroll
+  for (int u = 0; u < OPT; ++u) acc[u] = 0.f;
+  for (long long k0 = 0; k0 < p.Kd; k0 += BK) {
+    for (int i = tid; i < BM * BK; i += 256) {
+      const int r = i / BK, kk = i % BK;
+      const long long m = m0 + r, k = k0 + kk;
+      float v = 0.f;
+      if (m < p.M && k < p.Kd) {
+        v = p.x[m * p.ldx + k] * den_s[r];
+        if (p.ln_w) {
+          v = (v - mean_s[r]) * rstd_s[r] * p.ln_w[k] + p.ln_b[k];
+          if (p.xhat_out && blockIdx.x == 0) p.xhat_out[m * p.Kd + k] = v;
+        }
+        if (p.pe) v += p.pe[m * p.Kd + k];
+      }
+      xs[r][kk] = v;
+    }
+    for (int i = tid; i < BN * BK; i += 256) {
+      const int c = i / BK, kk = i % BK;
+      const long long n = n0 + c, k = k0 + kk;
+      wsm[c][kk] = (n < p.N && k < p.Kd) ? p.W[n * p.ldw + k] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float xv = xs[r_t][kk];
+#pragma unroll
+      for (int u = 0; u < OPT; ++u) acc[u] = fmaf(xv, wsm[cg + 8 * u][kk], acc[u]);
+    }
+    __syncthreads();
+  }
+  const long long m = m0 + r_t;
+  if (m < p.M) {
+#pragma unroll
+    for (int u = 0; u < OPT; ++u) {
+      const long long n = n0 + cg + 8 * u;
+      if (n < p.N) {
+        float v = acc[u] + (p.bias ? p.bias[n] : 0.f);
+        if (p.relu) v = fmaxf(v, 0.f);
+        if (p.residual) v += p.residual[(p.residual_mod ? (m % p.residual_mod) : m) * p.N + n];
+        p.y[m * p.N + n] = v;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// out[m,h,c] = scale * sum_d a[m,h*32+d] * Wx[h*32+d, c];  grid M, block 256 (thread == c)
+__global__ void __launch_bounds__(256) qt_head_fold_kernel(const float* __restrict__ a, const float* __restrict__ W,
+                                                           long long ldw, int transpose_w, float scale,
+                                                           const float* __restrict__ bias_vec, float* __restrict__ out,
+                                                           float* __restrict__ dots) {
+  __shared__ float as[E_];
+  const long long m = blockIdx.x;
+  const int c = threadIdx.x;
+  as[c] = a[m * E_ + c];
+  __syncthreads();
+  for (int h = 0; h < H_; ++h) {
+    float acc = 0.f;
+#pragma unroll 8
+    for (int d = 0; d < DH; ++d) {
+      const int r = h * DH + d;
+      const float w = transpose_w ? W[(long long)c * ldw + r] : W[(long long)r * ldw + c];
+      acc = fmaf(as[r], w, acc);
+    }
+    out[(m * H_ + h) * E_ + c] = acc * scale;
+  }
+  if (dots) {
+    const int h = c >> 5, d = c & 31;
+    float v = as[h * DH + d] * bias_vec[h * DH + d];
+    v = warp_sum(v);
+    if (d == 0) dots[m * H_ + h] = v * scale;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// self attention core: grid = objects (M/16), block 256 = 8 warps = 8 heads
+__global__ void __launch_bounds__(256) qt_self_attention_kernel(const float* __restrict__ qk, const float* __restrict__ v,
+                                                                float* __restrict__ out) {
+  __shared__ float ks[H_][NQ][DH], vs[H_][NQ][DH], ps[H_][NQ][NQ + 1];
+  const int tid = threadIdx.x, lane = tid & 31, h = tid >> 5;
+  const long long m0 = (long long)blockIdx.x * NQ;
+  for (int i = tid; i < NQ * E_; i += 256) {
+    const int r = i / E_, c = i % E_;
+    ks[c / DH][r][c % DH] = qk[(m0 + r) * 2 * E_ + E_ + c];
+    vs[c / DH][r][c % DH] = v[(m0 + r) * E_ + c];
+  }
+  const float scale = rsqrtf((float)DH);
+  const int i = lane & 15, jh = lane >> 4;
+  float qreg[DH];
+  {
+    const float4* qrow = reinterpret_cast<const float4*>(qk + (m0 + i) * 2 * E_ + h * DH);
+#pragma unroll
+    for (int d4 = 0; d4 < DH / 4; ++d4) {
+      const float4 t = qrow[d4];
+      qreg[4 * d4 + 0] = t.x; qreg[4 * d4 + 1] = t.y; qreg[4 * d4 + 2] = t.z; qreg[4 * d4 + 3] = t.w;
+    }
+  }
+  __syncthreads();
+  float s[8], mx = -CUDART_INF_F;
+#pragma unroll
+  for (int jj = 0; jj < 8; ++jj) {
+    const int j = jh * 8 + jj;
+    float acc = 0.f;
+#pragma unroll
+    for (int d = 0; d < DH; ++d) acc = fmaf(qreg[d], ks[h][j][d], acc);
+    s[jj] = acc * scale;
+    mx = fmaxf(mx, s[jj]);
+  }
+  mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+  float sum = 0.f;
+#pragma unroll
+  for (int jj = 0; jj < 8; ++jj) { s[jj] = expf(s[jj] - mx); sum += s[jj]; }
+  sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+  const float inv = 1.f / sum;
+#pragma unroll
+  for (int jj = 0; jj < 8; ++jj) ps[h][i][jh * 8 + jj] = s[jj] * inv;
+  __syncwarp();
+  for (int r = 0; r < NQ; ++r) {
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < NQ; ++j) acc = fmaf(ps[h][r][j], vs[h][j][lane], acc);
+    out[(m0 + r) * E_ + h * DH + lane] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// mask_pred + sigmoid + aggregate + foreground test.  grid (ceil(HW/32), B), block 256:
+// lane == pixel, warp == group of 32 channels.
+constexpr int AUX_MAX_K = 32;
+__global__ void __launch_bounds__(256) qt_aux_mask_kernel(const float* __restrict__ pixel, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, long long K, long long HW,
+                                                          float* __restrict__ logits, uint8_t* __restrict__ fg,
+                                                          int* __restrict__ fg_count) {
+  __shared__ float part[AUX_MAX_K][8][33];
+  __shared__ float wsm[E_];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long b = blockIdx.y, px = (long long)blockIdx.x * 32 + lane;
+  wsm[tid] = w[tid];
+  __syncthreads();
+  for (int k = 0; k < K; ++k) {
+    const float* base = pixel + ((b * K + k) * E_ + warp * 32) * HW;
+    float acc = 0.f;
+    if (px < HW) {
+#pragma unroll 8
+      for (int c = 0; c < 32; ++c) acc = fmaf(wsm[warp * 32 + c], fmaxf(base[(long long)c * HW + px], 0.f), acc);
+    }
+    part[k][warp][lane] = acc;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float lg[AUX_MAX_K];
+    float bgp = 1.f;
+    for (int k = 0; k < K; ++k) {
+      float v = bias[0];
+#pragma unroll
+      for (int g = 0; g < 8; ++g) v += part[k][g][lane];
+      lg[k] = v;
+      const float pr = 1.f / (1.f + expf(-v));
+      bgp *= (1.f - pr);
+    }
+    // log-odds after clamping to [1e-7, 1-1e-7] (tensor_utils.py:50-52)
+    const float bc = fminf(fmaxf(bgp, 1e-7f), 1.f - 1e-7f);
+    float mx = logf(bc / (1.f - bc));
+    float lo[AUX_MAX_K];
+    for (int k = 0; k < K; ++k) {
+      const float pr = fminf(fmaxf(1.f / (1.f + expf(-lg[k])), 1e-7f), 1.f - 1e-7f);
+      lo[k] = logf(pr / (1.f - pr));
+      mx = fmaxf(mx, lo[k]);
+    }
+    for (int k = 0; k < K; ++k) {
+      const bool f = (px < HW) && (lo[k] >= mx);
+      if (px < HW) {
+        logits[(b * K + k) * HW + px] = lg[k];
+        fg[(b * K + k) * HW + px] = f ? 1 : 0;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, f);
+      if (lane == 0 && m) atomicAdd(&fg_count[b * K + k], __popc(m));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// read_from_pixel core, pass 1: grid (splits, heads, BK); each CTA streams its pixel range in chunks of
+// 32, online softmax for the 16 rows of one head, Z[16][256] accumulators (thread == channel).
+struct P2QParams {
+  const float* qfold;   // [BK*16, 8, 256]
+  const float* pixel;   // [BK, 256, HW]
+  const float* pe;
+  const uint8_t* fg;    // [BK, HW]
+  const int* fg_count;  // [BK]
+  long long HW;
+  int splits, chunks_per_split;
+  float* ws;            // [BK][H][splits][16*(256+2)]
+};
+
+constexpr int P2Q_WS = NQ * (E_ + 2);
+
+__global__ void __launch_bounds__(256) qt_p2q_partial_kernel(const P2QParams p) {
+  extern __shared__ __align__(16) float dsm[];
+  float(*qf)[E_] = reinterpret_cast<float(*)[E_]>(dsm);                       // [16][256]
+  float(*kin)[33] = reinterpret_cast<float(*)[33]>(dsm + NQ * E_);            // [256][33]
+  float(*pix)[33] = reinterpret_cast<float(*)[33]>(dsm + NQ * E_ + E_ * 33);  // [256][33]
+  float(*ps)[33] = reinterpret_cast<float(*)[33]>(dsm + NQ * E_ + 2 * E_ * 33);  // [16][33]
+  float* sc = dsm + NQ * E_ + 2 * E_ * 33 + NQ * 33;                          // [16] rescale factors
+  float* rm = sc + NQ;                                                        // running max
+  float* rl = rm + NQ;                                                        // running sum
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int split = blockIdx.x, h = blockIdx.y;
+  const long long bk = blockIdx.z;
+  for (int i = tid; i < NQ * E_; i += 256) {
+    const int r = i / E_, c = i % E_;
+    qf[r][c] = p.qfold[((bk * NQ + r) * H_ + h) * E_ + c];
+  }
+  if (tid < NQ) { rm[tid] = -CUDART_INF_F; rl[tid] = 0.f; }
+  const int cnt = p.fg_count[bk];
+  const bool open_fg = (cnt == 0);           // no foreground pixel at all: foreground queries see everything
+  const bool open_bg = (cnt == (int)p.HW);   // everything foreground: background queries see everything
+  float z[NQ];
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) z[i] = 0.f;
+  const float* pbase = p.pixel + bk * E_ * p.HW;
+  const float* ebase = p.pe + bk * E_ * p.HW;
+  const long long p_begin = (long long)split * p.chunks_per_split * 32;
+  for (int ch = 0; ch < p.chunks_per_split; ++ch) {
+    const long long p0 = p_begin + (long long)ch * 32;
+    if (p0 >= p.HW) break;
+    __syncthreads();
+    const long long px = p0 + lane;
+    for (int c = warp; c < E_; c += 8) {
+      float a = 0.f, e = 0.f;
+      if (px < p.HW) { a = pbase[(long long)c * p.HW + px]; e = ebase[(long long)c * p.HW + px]; }
+      pix[c][lane] = a;
+      kin[c][lane] = a + e;
+    }
+    __syncthreads();
+    // scores for rows (warp, warp+8) x pixel lane
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+    for (int c = 0; c < E_; ++c) {
+      const float kv = kin[c][lane];
+      s0 = fmaf(qf[warp][c], kv, s0);
+      s1 = fmaf(qf[warp + 8][c], kv, s1);
+    }
+    const bool f = (px < p.HW) ? (p.fg[bk * p.HW + px] != 0) : false;
+    const bool ok0 = (px < p.HW) && (f || open_fg);     // rows 0..7: foreground queries
+    const bool ok1 = (px < p.HW) && (!f || open_bg);    // rows 8..15: background queries
+    s0 = ok0 ? s0 : -CUDART_INF_F;
+    s1 = ok1 ? s1 : -CUDART_INF_F;
+    {
+      const float cm = warp_max(s0);
+      const float mo = rm[warp], mn = fmaxf(mo, cm);
+      const float e = (mn == -CUDART_INF_F) ? 0.f : expf(s0 - mn);
+      const float scl = (mo == -CUDART_INF_F) ? 0.f : expf(mo - mn);
+      const float su = warp_sum(e);
+      ps[warp][lane] = e;
+      if (lane == 0) { sc[warp] = scl; rl[warp] = rl[warp] * scl + su; rm[warp] = mn; }
+    }
+    {
+      const float cm = warp_max(s1);
+      const float mo = rm[warp + 8], mn = fmaxf(mo, cm);
+      const float e = (mn == -CUDART_INF_F) ? 0.f : expf(s1 - mn);
+      const float scl = (mo == -CUDART_INF_F) ? 0.f : expf(mo - mn);
+      const float su = warp_sum(e);
+      ps[warp + 8][lane] = e;
+      if (lane == 0) { sc[warp + 8] = scl; rl[warp + 8] = rl[warp + 8] * scl + su; rm[warp + 8] = mn; }
+    }
+    __syncthreads();
+    // Z[i][c=tid] = Z*scale + sum_p P[i][p] * pix[c][p]
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) z[i] *= sc[i];
+#pragma unroll 4
+    for (int pp = 0; pp < 32; ++pp) {
+      const float v = pix[tid][pp];
+#pragma unroll
+      for (int i = 0; i < NQ; ++i) z[i] = fmaf(ps[i][pp], v, z[i]);
+    }
+  }
+  __syncthreads();
+  float* w = p.ws + (((bk * H_ + h) * p.splits) + split) * P2Q_WS;
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) w[i * E_ + tid] = z[i];
+  if (tid < NQ) { w[NQ * E_ + tid] = rm[tid]; w[NQ * E_ + NQ + tid] = rl[tid]; }
+}
+
+// pass 2: grid (heads, BK): merge splits, normalise, apply the per-head value projection.
+__global__ void __launch_bounds__(256) qt_p2q_combine_kernel(const float* __restrict__ ws, int splits,
+                                                             const float* __restrict__ wv, long long ldwv,
+                                                             const float* __restrict__ bv, float* __restrict__ attn) {
+  __shared__ float zn[NQ][E_ + 1];
+  __shared__ float coef[64][NQ];   // per split, per row: exp(m_s - M) / L
+  const int tid = threadIdx.x;
+  const int h = blockIdx.x;
+  const long long bk = blockIdx.y;
+  const float* base = ws + ((bk * H_ + h) * splits) * (long long)P2Q_WS;
+  if (tid < NQ) {
+    float M = -CUDART_INF_F;
+    for (int s = 0; s < splits; ++s) M = fmaxf(M, base[(long long)s * P2Q_WS + NQ * E_ + tid]);
+    float L = 0.f;
+    for (int s = 0; s < splits; ++s) {
+      const float ms = base[(long long)s * P2Q_WS + NQ * E_ + tid];
+      const float f = (ms == -CUDART_INF_F) ? 0.f : expf(ms - M);
+      coef[s][tid] = f;
+      L += f * base[(long long)s * P2Q_WS + NQ * E_ + NQ + tid];
+    }
+    const float inv = 1.f / L;
+    for (int s = 0; s < splits; ++s) coef[s][tid] *= inv;
+  }
+  __syncthreads();
+  for (int i = 0; i < NQ; ++i) {
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc = fmaf(coef[s][i], base[(long long)s * P2Q_WS + i * E_ + tid], acc);
+    zn[i][tid] = acc;
+  }
+  __syncthreads();
+  // attn[(bk*16+i), h*32+e] = zn[i] . wv[h*32+e, :] + bv[h*32+e];  512 outputs, 2 per thread
+  for (int o = tid; o < NQ * DH; o += 256) {
+    const int i = o / DH, e = o % DH;
+    const float* wr = wv + (long long)(h * DH + e) * ldwv;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int c = 0; c < E_; ++c) acc = fmaf(zn[i][c], wr[c], acc);
+    attn[(bk * NQ + i) * E_ + h * DH + e] = acc + bv[h * DH + e];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// read_from_query fused: grid (ceil(HW/32), BK), block 256 (lane == pixel, warp == head in stage A,
+// warp == channel phase in stage B).
+struct Q2PParams {
+  const float* kfold;   // [BK*16, 8, 256]  row r = j*8 + h
+  const float* kdots;   // [BK*16, 8]
+  const float* vfold;   // [BK*16, 8, 256]
+  const float* out_bias;
+  const float* pixel;
+  const float* pe;
+  long long HW;
+  float* out;
+};
+
+__global__ void __launch_bounds__(256) qt_q2p_kernel(const Q2PParams p) {
+  extern __shared__ __align__(16) float dsm[];
+  float(*qin)[33] = reinterpret_cast<float(*)[33]>(dsm);                    // [256][33]
+  float(*stage)[33] = reinterpret_cast<float(*)[33]>(dsm + E_ * 33);        // [128][33]: kfold chunk (A)
+  float(*ps)[33] = reinterpret_cast<float(*)[33]>(dsm + E_ * 33 + 128 * 33);  // [128][33] probabilities
+  float* vf = dsm + E_ * 33 + 2 * 128 * 33;                                  // [32][256] vfold chunk (B)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long bk = blockIdx.y, p0 = (long long)blockIdx.x * 32, px = p0 + lane;
+  const float* pbase = p.pixel + bk * E_ * p.HW;
+  const float* ebase = p.pe + bk * E_ * p.HW;
+  for (int c = warp; c < E_; c += 8) {
+    float v = 0.f;
+    if (px < p.HW) v = pbase[(long long)c * p.HW + px] + ebase[(long long)c * p.HW + px];
+    qin[c][lane] = v;
+  }
+  // ---- stage A: scores for head `warp`, queries j = 0..15 (row r = j*8 + warp) ----
+  float s[NQ];
+#pragma unroll
+  for (int j = 0; j < NQ; ++j) s[j] = 0.f;
+  const float* kf = p.kfold + bk * NQ * H_ * E_;
+  for (int c0 = 0; c0 < E_; c0 += 32) {
+    __syncthreads();
+    for (int r = warp; r < 128; r += 8) stage[r][lane] = kf[(long long)r * E_ + c0 + lane];
+    __syncthreads();
+#pragma unroll 4
+    for (int cc = 0; cc < 32; ++cc) {
+      const float x = qin[c0 + cc][lane];
+#pragma unroll
+      for (int j = 0; j < NQ; ++j) s[j] = fmaf(x, stage[j * 8 + warp][cc], s[j]);
+    }
+  }
+  float mx = -CUDART_INF_F;
+#pragma unroll
+  for (int j = 0; j < NQ; ++j) {
+    s[j] += p.kdots[(bk * NQ + j) * H_ + warp];
+    mx = fmaxf(mx, s[j]);
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < NQ; ++j) { s[j] = expf(s[j] - mx); sum += s[j]; }
+  const float inv = 1.f / sum;
+#pragma unroll
+  for (int j = 0; j < NQ; ++j) ps[j * 8 + warp][lane] = s[j] * inv;
+  // ---- stage B: out[c][p] = pixel + bias + sum_r P[r][p] * vfold[r][c],  c = warp + 8 v ----
+  float acc[32];
+#pragma unroll
+  for (int v = 0; v < 32; ++v) acc[v] = 0.f;
+  const float* vfg = p.vfold + bk * NQ * H_ * E_;
+  for (int r0 = 0; r0 < 128; r0 += 32) {
+    __syncthreads();
+    for (int i = tid; i < 32 * E_; i += 256) vf[i] = vfg[(long long)r0 * E_ + i];
+    __syncthreads();
+#pragma unroll 2
+    for (int rr = 0; rr < 32; ++rr) {
+      const float pr = ps[r0 + rr][lane];
+#pragma unroll
+      for (int v = 0; v < 32; ++v) acc[v] = fmaf(pr, vf[rr * E_ + warp + 8 * v], acc[v]);
+    }
+  }
+  if (px < p.HW) {
+    float* ob = p.out + bk * E_ * p.HW;
+#pragma unroll
+    for (int v = 0; v < 32; ++v) {
+      const int c = warp + 8 * v;
+      ob[(long long)c * p.HW + px] = pbase[(long long)c * p.HW + px] + p.out_bias[c] + acc[v];
+    }
+  }
+}
+
+}  // namespace cutie
+
+using namespace cutie;
+
+extern "C" int cutie_qt_linear(const float* x, int64_t M, int64_t Kd, const float* W, int64_t ldw, int64_t N,
+                               const float* bias, const float* ln_w, const float* ln_b, const float* pe,
+                               int summary_norm, int relu, const float* residual, int64_t residual_mod,
+                               float* xhat_out, float* y, void* stream) {
+  CUTIE_REQUIRE(x && W && y && M >= 1 && N >= 1 && Kd >= 1, "null/empty argument");
+  CUTIE_REQUIRE((ln_w == nullptr) == (ln_b == nullptr), "ln_w and ln_b must be given together");
+  CUTIE_REQUIRE(xhat_out == nullptr || ln_w != nullptr, "xhat_out needs LayerNorm");
+  LinearParams p;
+  p.x = x; p.M = M; p.Kd = Kd; p.ldx = Kd + (summary_norm ? 1 : 0);
+  p.W = W; p.ldw = ldw; p.N = N; p.bias = bias; p.ln_w = ln_w; p.ln_b = ln_b; p.pe = pe;
+  p.summary_norm = summary_norm; p.relu = relu; p.residual = residual; p.residual_mod = residual_mod;
+  p.xhat_out = xhat_out; p.y = y;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned my = (unsigned)((M + 31) / 32);
+  if (Kd >= 1024 || N <= 256) {
+    qt_linear_kernel<8><<<dim3((unsigned)((N + 7) / 8), my), 256, 0, st>>>(p);
+  } else {
+    qt_linear_kernel<32><<<dim3((unsigned)((N + 31) / 32), my), 256, 0, st>>>(p);
+  }
+  CUTIE_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int cutie_qt_head_fold(const float* a, int64_t M, int64_t E, int num_heads, const float* W, int64_t ldw,
+                                  int transpose_w, float scale, const float* bias_vec, float* out, float* dots,
+                                  void* stream) {
+  CUTIE_REQUIRE(a && W && out && M >= 1, "null/empty argument");
+  CUTIE_REQUIRE(E == E_ && num_heads == H_, "embed_dim must be 256 with 8 heads");
+  CUTIE_REQUIRE((dots == nullptr) == (bias_vec == nullptr), "dots and bias_vec must be given together");
+  qt_head_fold_kernel<<<(unsigned)M, 256, 0, (cudaStream_t)stream>>>(a, W, ldw, transpose_w, scale, bias_vec, out, dots);
+  CUTIE_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int cutie_qt_self_attention(const float* qk, const float* v, int64_t M, int64_t E, int num_queries,
+                                       int num_heads, float* out, void* stream) {
+  CUTIE_REQUIRE(qk && v && out && M >= 1, "null/empty argument");
+  CUTIE_REQUIRE(E == E_ && num_heads == H_ && num_queries == NQ && M % NQ == 0,
+                "embed_dim 256, 8 heads, 16 queries");
+  qt_self_attention_kernel<<<(unsigned)(M / NQ), 256, 0, (cudaStream_t)stream>>>(qk, v, out);
+  CUTIE_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int cutie_qt_aux_mask(const float* pixel, const float* w, const float* b, int64_t B, int64_t K, int64_t E,
+                                 int64_t HW, float* logits, uint8_t* fg, int32_t* fg_count, void* stream) {
+  CUTIE_REQUIRE(pixel && w && b && logits && fg && fg_count, "null argument");
+  CUTIE_REQUIRE(E == E_, "embed_dim must be 256");
+  CUTIE_REQUIRE(K >= 1 && K <= AUX_MAX_K && B >= 1 && HW >= 1, "1..32 objects");
+  dim3 grid((unsigned)((HW + 31) / 32), (unsigned)B);
+  qt_aux_mask_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pixel, w, b, K, HW, logits, fg, fg_count);
+  CUTIE_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int cutie_qt_pixel_to_query_splits(int64_t BK, int64_t HW, int num_heads) {
+  const long long chunks = (HW + 31) / 32;
+  long long s = (2 * num_sms() + BK * num_heads - 1) / (BK * num_heads);
+  if (s < 1) s = 1;
+  if (s > chunks) s = chunks;
+  if (s > 64) s = 64;
+  // make every split non-empty
+  const long long cps = (chunks + s - 1) / s;
+  s = (chunks + cps - 1) / cps;
+  return (int)s;
+}
+
+extern "C" int cutie_qt_pixel_to_query(const float* qfold, const float* pixel, const float* pixel_pe,
+                                       const uint8_t* fg, const int32_t* fg_count, const float* wv, int64_t ldwv,
+                                       const float* bv, int64_t BK, int64_t E, int64_t HW, int num_queries,
+                                       int num_heads, int splits, float* workspace, float* attn_out, void* stream) {
+  CUTIE_REQUIRE(qfold && pixel && pixel_pe && fg && fg_count && wv && bv && workspace && attn_out, "null argument");
+  CUTIE_REQUIRE(E == E_ && num_heads == H_ && num_queries == NQ, "embed_dim 256, 8 heads, 16 queries");
+  CUTIE_REQUIRE(splits >= 1 && splits <= 64 && BK >= 1 && HW >= 1, "1..64 splits");
+  P2QParams p;
+  p.qfold = qfold; p.pixel = pixel; p.pe = pixel_pe; p.fg = fg; p.fg_count = fg_count; p.HW = HW;
+  p.splits = splits;
+  const long long chunks = (HW + 31) / 32;
+  p.chunks_per_split = (int)((chunks + splits - 1) / splits);
+  p.ws = workspace;
+  const size_t smem = (size_t)(NQ * E_ + 2 * E_ * 33 + NQ * 33 + 3 * NQ) * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(qt_p2q_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_done = true;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  qt_p2q_partial_kernel<<<dim3((unsigned)splits, H_, (unsigned)BK), 256, smem, st>>>(p);
+  CUTIE_CHECK_LAUNCH();
+  qt_p2q_combine_kernel<<<dim3(H_, (unsigned)BK), 256, 0, st>>>(workspace, splits, wv, ldwv, bv, attn_out);
+  CUTIE_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int cutie_qt_query_to_pixel(const float* kfold, const float* kdots, const float* vfold,
+                                       const float* out_bias, const float* pixel, const float* pixel_pe, int64_t BK,
+                                       int64_t E, int64_t HW, int num_queries, int num_heads, float* out,
+                                       void* stream) {
+  CUTIE_REQUIRE(kfold && kdots && vfold && out_bias && pixel && pixel_pe && out, "null argument");
+  CUTIE_REQUIRE(E == E_ && num_heads == H_ && num_queries == NQ, "embed_dim 256, 8 heads, 16 queries");
+  CUTIE_REQUIRE(BK >= 1 && HW >= 1, "empty");
+  Q2PParams p;
+  p.kfold = kfold; p.kdots = kdots; p.vfold = vfold; p.out_bias = out_bias; p.pixel = pixel; p.pe = pixel_pe;
+  p.HW = HW; p.out = out;
+  const size_t smem = (size_t)(E_ * 33 + 2 * 128 * 33 + 32 * E_) * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(qt_q2p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_done = true;
+  }
+  qt_q2p_kernel<<<dim3((unsigned)((HW + 31) / 32), (unsigned)BK), 256, smem, (cudaStream_t)stream>>>(p);
+  CUTIE_CHECK_LAUNCH();
+  return 0;
+}

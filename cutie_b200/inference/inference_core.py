@@ -71,7 +71,7 @@ class InferenceCore:
                     force_permanent: bool = False) -> None:
         """Encode the (predicted or given) masks and append one frame of tokens to the memory."""
         if prob.shape[1] == 0:
-            log.warn('Trying to add an empty object mask to memory!')
+            log.warning('Trying to add an empty object mask to memory!')
             return
         ids = self.object_manager.all_obj_ids
         self.memory.initialize_sensory_if_needed(key, ids)
@@ -90,7 +90,7 @@ class InferenceCore:
         bs = key.shape[0]
         assert bs == (2 if self.flip_aug else 1)
         if not self.memory.engaged:
-            log.warn('Trying to segment without any memory!')
+            log.warning('Trying to segment without any memory!')
             return torch.zeros((1, key.shape[-2] * 16, key.shape[-1] * 16), device=key.device, dtype=key.dtype)
 
         readout = self.memory.read(pix_feat, key, selection, self.last_mask, self.network)
@@ -172,7 +172,7 @@ class InferenceCore:
                 if len(objects) == 0:
                     if delete_buffer:
                         self.image_feature_store.delete(self.curr_ti)
-                    log.warn('Trying to insert an empty mask as memory!')
+                    log.warning('Trying to insert an empty mask as memory!')
                     return torch.zeros((1, key.shape[-2] * 16, key.shape[-1] * 16), device=key.device,
                                        dtype=key.dtype)
                 mask = torch.stack([mask == objects[i] for i, _ in enumerate(tmp_ids)], dim=0)

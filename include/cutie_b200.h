@@ -1,0 +1,143 @@
+/*
+ * cutie_b200.h -- C-ABI of libcutie_b200.so: hand-written sm_100a kernels for the Cutie per-frame
+ * hot path (pixel-memory readout + object-transformer attention).
+ *
+ * The reference (hkchengrex/Cutie) has no FFI layer: its "operator interface" for this path is a set
+ * of Python functions/methods that call PyTorch library kernels.  Each entry point below names the
+ * reference call site(s) it replaces (paths relative to the reference root).  A replacement
+ * implementation must export exactly these symbols; cutie_b200/kernels.py binds them with ctypes and
+ * INTEGRATION.md shows the reference-side binding a maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers + int64 sizes/strides (strides in ELEMENTS); no torch types cross this boundary;
+ *   - every buffer (inputs, outputs, workspaces) is allocated and owned by the caller; kernels borrow
+ *     pointers for the duration of the enqueued work and never allocate;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises;
+ *   - return 0 on success, <0 on invalid argument (-1) or launch failure (-2); never throws;
+ *     cutie_b200_last_error() returns a thread-local message for the last failure;
+ *   - all floating point is fp32 (the reference runs this path with amp=False, eval_config.yaml:13);
+ *   - "token-major" = [B, n, C] with the channel axis contiguous (one memory token per row);
+ *     "channel-major" = [B, C, n] as PyTorch convolutions emit feature maps.
+ */
+#ifndef CUTIE_B200_H_
+#define CUTIE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CUTIE_B200_ABI_VERSION 1
+#define CUTIE_B200_MAX_SEGMENTS 4       /* long | permanent | ring piece a | ring piece b */
+#define CUTIE_B200_USAGE_FRAC_BITS 40   /* usage accumulators: uint64 fixed point, 2^-40 */
+
+int cutie_b200_abi_version(void);
+const char* cutie_b200_last_error(void);
+
+/* ---- pixel-memory readout ------------------------------------------------------------------------ */
+
+/* Fused similarity -> exact top-k -> softmax over the winners.
+ * Replaces get_similarity (cutie/model/utils/memory_utils.py:7-46) + do_softmax(top_k=..., return_usage)
+ * (memory_utils.py:49-77) as called from MemoryManager.read (cutie/inference/memory_manager.py:144-172),
+ * including the torch.cat of long-term and working keys (:137-143): the bank is passed as up to 4
+ * token-major segments, indices count tokens across segments in order.
+ *   S[n,q] = -shrinkage[n]/sqrt(CK) * sum_c qe[c,q] * (key[n,c] - qk[c,q])^2      (== memory_utils.py:28-42)
+ *   out_idx/out_w [B,Q,kpad]: the top_k tokens per query by (S desc, index asc) and exp(S)/sum exp(S) over
+ *   them; slots >= top_k hold (-1, 0).  out_sim (optional) the winners' S.  usage_acc (optional, uint64
+ *   [B, n_total], zeroed by the caller) += w * 2^40 per winner (deterministic integer accumulation of
+ *   memory_utils.py:74-75).
+ * CK must be 64; top_k <= kpad, kpad in {32, 64}. */
+size_t cutie_affinity_workspace_bytes(int64_t B, int64_t Q, int64_t n_total, int top_k);
+int cutie_affinity_topk(int num_segments, const void* const* seg_key, const void* const* seg_shrinkage,
+                        const int64_t* seg_len, const int64_t* seg_key_bstride, const int64_t* seg_shr_bstride,
+                        const float* qk, const float* qe, int64_t B, int64_t CK, int64_t Q, int top_k, int kpad,
+                        int32_t* out_idx, float* out_w, float* out_sim, unsigned long long* usage_acc,
+                        int64_t n_total, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Sparse value readout out[b,k,c,q] = sum_j w[b,q,j] * V_k[idx[b,q,j], c].
+ * Replaces MemoryManager._readout (memory_manager.py:77-88; dense [K*CV,N]x[N,Q] GEMM against a matrix
+ * with top_k non-zeros per column) and _get_visual_values_by_ids (:101-110; torch.stack/cat of the whole
+ * value bank every frame).  seg_val[s*K + k] -> token-major values of object k in segment s. */
+int cutie_readout_gather(const int32_t* idx, const float* w, int64_t B, int64_t Q, int kpad, int num_segments,
+                         const int64_t* seg_len, const void* const* seg_val, const int64_t* seg_val_bstride,
+                         int64_t K, int64_t CV, float* out, void* stream);
+
+/* use_cnt += usage_acc * 2^-40 ; life_cnt += 1  for n tokens.
+ * Replaces KeyValueMemoryStore.update_bucket_usage (cutie/inference/kv_memory_store.py:151-162). */
+int cutie_usage_commit(float* use_cnt, int64_t use_bstride, float* life_cnt, int64_t life_bstride,
+                       const unsigned long long* usage_acc, int64_t acc_bstride, int64_t acc_offset, int64_t B,
+                       int64_t n, void* stream);
+
+/* ---- memory bank maintenance ------------------------------------------------------------------------ */
+
+/* dst[b,i,c] = src[b,c,i]  (channel-major feature map -> token-major arena rows).
+ * Replaces the flatten + torch.cat growth of KeyValueMemoryStore.add (kv_memory_store.py:6-16,:136-149). */
+int cutie_bank_append(const float* src, int64_t src_bstride, float* dst_rows, int64_t dst_bstride, int64_t B,
+                      int64_t C, int64_t n, void* stream);
+/* dst[b,c,i] = rows[b,i,c]  (token-major -> channel-major; reference-shaped views for inspection). */
+int cutie_bank_export(const float* rows, int64_t rows_bstride, float* dst, int64_t dst_bstride, int64_t B,
+                      int64_t C, int64_t n, void* stream);
+/* dst_rows[b,j,:] = concat(segments)[b, index[b,j], :].  Replaces the advanced-index gathers of
+ * remove_obsolete_features (kv_memory_store.py:226-242) and consolidation (memory_manager.py:340-344). */
+int cutie_bank_gather(int num_segments, const void* const* seg_rows, const int64_t* seg_len,
+                      const int64_t* seg_bstride, const int64_t* index, float* dst_rows, int64_t dst_bstride,
+                      int64_t B, int64_t m, int64_t C, void* stream);
+/* Long-term potentiation: for every prototype p, A[:,p] = softmax_n(S[n,p]) over ALL candidate tokens
+ * (max-subtracted, memory_utils.py:68-71), out_val_k[b,p,:] = sum_n A[n,p] V_k[n,:], out_shr[b,p] = sum_n A[n,p] shr[n].
+ * Replaces MemoryManager.consolidation (memory_manager.py:345-356).  workspace: B*P*n_total floats. */
+int cutie_consolidate(int num_segments, const void* const* seg_key, const void* const* seg_shrinkage,
+                      const int64_t* seg_len, const int64_t* seg_key_bstride, const int64_t* seg_shr_bstride,
+                      const void* const* seg_val, const int64_t* seg_val_bstride, int64_t K,
+                      const float* proto_key, int64_t pk_bstride, const float* proto_sel, int64_t ps_bstride,
+                      int64_t B, int64_t P, int64_t CK, int64_t CV, void* const* out_val,
+                      const int64_t* out_val_bstride, float* out_shr, int64_t out_shr_bstride, float* workspace,
+                      int64_t n_total, void* stream);
+/* acc[i] += add[i].  Replaces the streaming object-memory sum (memory_manager.py:252-271). */
+int cutie_obj_summary_accumulate(float* acc, const float* add, int64_t n, void* stream);
+
+/* ---- object transformer ----------------------------------------------------------------------------- */
+
+/* Skinny fused linear on the [M = B*K*16, Kd] query tile:
+ *   xin = x  (or x[:, :Kd] / (x[:, Kd] + 1e-4) when summary_norm: row stride Kd+1; object_transformer.py:126-132)
+ *   xin = LayerNorm(xin) * ln_w + ln_b   (Kd == 256; xhat_out <- this)           transformer_layers.py:34,75,115
+ *   xin += pe                                                                      transformer_layers.py:36,77
+ *   y = xin . W^T + bias ; relu ; y += residual[(m % residual_mod) or m]           nn.Linear / in_proj / out_proj
+ * Replaces the addmm/layer_norm/add/relu ATen launches of SelfAttention, CrossAttention, FFN
+ * (transformer_layers.py:12-118) and the query initialisation (object_transformer.py:133-138). */
+int cutie_qt_linear(const float* x, int64_t M, int64_t Kd, const float* W, int64_t ldw, int64_t N,
+                    const float* bias, const float* ln_w, const float* ln_b, const float* pe, int summary_norm,
+                    int relu, const float* residual, int64_t residual_mod, float* xhat_out, float* y, void* stream);
+/* out[m,h,c] = scale * sum_d a[m, h*dh+d] * Wx[h*dh+d, c]  (Wx = W or W^T), dots[m,h] = scale * a_h . bias_h.
+ * Folds one side's per-head projection into the other side's input space so the per-pixel K/V (or Q/out)
+ * projections of nn.MultiheadAttention (transformer_layers.py:88-93) never run. */
+int cutie_qt_head_fold(const float* a, int64_t M, int64_t E, int num_heads, const float* W, int64_t ldw,
+                       int transpose_w, float scale, const float* bias_vec, float* out, float* dots, void* stream);
+/* 16x16 self attention per (object, head): SelfAttention core (transformer_layers.py:40). */
+int cutie_qt_self_attention(const float* qk, const float* v, int64_t M, int64_t E, int num_queries, int num_heads,
+                            float* out, void* stream);
+/* mask_pred 1x1 conv on relu(pixel) + sigmoid + aggregate + foreground test + per-object foreground count.
+ * Replaces mask_pred[i] and QueryTransformer._get_aux_mask (object_transformer.py:153-155,165-167,179-205;
+ * cutie/utils/tensor_utils.py:47-54).  The [(B*K*heads),Q,HW] bool mask is represented by fg + fg_count. */
+int cutie_qt_aux_mask(const float* pixel, const float* w, const float* b, int64_t B, int64_t K, int64_t E,
+                      int64_t HW, float* logits, uint8_t* fg, int32_t* fg_count, void* stream);
+/* read_from_pixel attention core (masked, queries <- pixels), channel-major pixels, flash-style split over
+ * pixels + combine + V projection.  Replaces CrossAttention.cross_attn for read_from_pixel
+ * (transformer_layers.py:88-93 via object_transformer.py:51-56).  workspace: BK*H*splits*Q*(E+2) floats. */
+int cutie_qt_pixel_to_query_splits(int64_t BK, int64_t HW, int num_heads);
+int cutie_qt_pixel_to_query(const float* qfold, const float* pixel, const float* pixel_pe, const uint8_t* fg,
+                            const int32_t* fg_count, const float* wv, int64_t ldwv, const float* bv, int64_t BK,
+                            int64_t E, int64_t HW, int num_queries, int num_heads, int splits, float* workspace,
+                            float* attn_out, void* stream);
+/* read_from_query (pixels <- queries) fused through softmax, value fold, output bias and residual,
+ * channel-major in/out.  Replaces CrossAttention for read_from_query (object_transformer.py:61-65) and the
+ * NLC<->NCHW permutes around it (:50, transformer_layers.py:131-132). */
+int cutie_qt_query_to_pixel(const float* kfold, const float* kdots, const float* vfold, const float* out_bias,
+                            const float* pixel, const float* pixel_pe, int64_t BK, int64_t E, int64_t HW,
+                            int num_queries, int num_heads, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUTIE_B200_H_ */

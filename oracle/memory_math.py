@@ -131,20 +131,23 @@ def consolidate(cand_key: torch.Tensor, cand_shrinkage: torch.Tensor, cand_selec
 
 
 def topk_set_agreement(sim_test_idx: torch.Tensor, truth64: torch.Tensor, top_k: int,
-                       noise_floor: float):
+                       rel_noise: float):
     """Compare a [B,k,Q] index selection with the float64 ground-truth similarity `truth64` [B,N,Q].
 
     A query column counts as *decidable* when the gap between the k-th and (k+1)-th true similarity
-    exceeds `noise_floor` (SURVEY.md Appendix B take-away 5).  Returns
+    exceeds rel_noise * |k-th similarity| -- the rounding noise of an fp32 evaluation of that element
+    (SURVEY.md Appendix B take-away 5).  Returns
     (n_decidable, n_decidable_equal, n_total_equal, n_total).
     """
     B, N, Q = truth64.shape
     kk = min(top_k + 1, N)
     tv, ti = torch.topk(truth64, k=kk, dim=1)
-    gap = (tv[:, top_k - 1] - tv[:, top_k]) if kk > top_k else torch.full((B, Q), float('inf'),
-                                                                          dtype=truth64.dtype)
+    if kk > top_k:
+        gap = tv[:, top_k - 1] - tv[:, top_k]
+        decidable = gap > rel_noise * tv[:, top_k - 1].abs()
+    else:
+        decidable = torch.ones(B, Q, dtype=torch.bool)
     true_sets = ti[:, :top_k].sort(dim=1)[0]
     test_sets = sim_test_idx.sort(dim=1)[0]
     same = (true_sets == test_sets).all(dim=1)          # [B,Q]
-    decidable = gap > noise_floor
     return int(decidable.sum()), int((same & decidable).sum()), int(same.sum()), int(same.numel())

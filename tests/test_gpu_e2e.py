@@ -1,0 +1,138 @@
+"""GPU end-to-end parity: InferenceCore.step on the fused CUDA path vs (a) the committed reference
+fixtures, free-running, and (b) the CPU oracle's full-frame restatement at a larger size, both
+free-running and teacher-forced.  Bar: <= 1e-3 max-abs on segmentation logits (BASELINE.json)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+LT_SMALL = dict(max_mem_frames=4, min_mem_frames=2, num_prototypes=16, max_num_tokens=60, buffer_tokens=20)
+
+
+def _net(cfg, cuda=True):
+    from cutie_b200.model.cutie import CUTIE
+    from oracle.synth import synthetic_state_dict
+    net = CUTIE(cfg).eval()
+    net.load_state_dict(synthetic_state_dict(net.state_dict(), 0))
+    return net.cuda() if cuda else net
+
+
+def _sizes(proc):
+    m = proc.memory
+    row = []
+    for b in sorted(m.work_mem.buckets):
+        row += [b, m.work_mem.size(b), m.work_mem.perm_size(b), m.long_mem.size(b) if m.use_long_term else 0]
+    return row
+
+
+@pytest.mark.parametrize('name,over,T,K', [
+    ('fifo', dict(mem_every=2, max_mem_frames=3), 10, 3),
+    ('longterm', dict(mem_every=1, use_long_term=True, long_term=LT_SMALL), 14, 2),
+])
+def test_free_running_vs_reference_fixture(name, over, T, K):
+    from cutie_b200.config import default_config
+    from cutie_b200.inference.inference_core import InferenceCore
+    from oracle.synth import synthetic_video
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = np.load(os.path.join(GOLDEN, f'e2e_{name}.npz'))
+    cfg = default_config(**over)
+    proc = InferenceCore(_net(cfg), cfg=cfg)
+    frames, mask = synthetic_video(T, 96, 160, K, seed=3)
+    li, worst = 0, 0.0
+    with torch.inference_mode():
+        for ti in range(T):
+            if ti == 0:
+                prob = proc.step(frames[0].cuda(), mask.cuda(), objects=list(range(1, K + 1)))
+            else:
+                prob = proc.step(frames[ti].cuda())
+            assert _sizes(proc) == [int(x) for x in g['sizes'][ti] if x >= 0]
+            if ti > 0:
+                worst = max(worst, float(np.abs(proc.last_logits.cpu().numpy() - g['logits'][li:li + 1]).max()))
+                li += 1
+    assert worst < 1e-3, worst
+    assert float((prob.cpu() - torch.from_numpy(g['final_prob'])).abs().max()) < 1e-3
+
+
+def test_buckets_and_delete_vs_reference_fixture():
+    """Second object introduced later -> second bucket; then an object is deleted."""
+    from cutie_b200.config import default_config
+    from cutie_b200.inference.inference_core import InferenceCore
+    from oracle.synth import synthetic_video
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = np.load(os.path.join(GOLDEN, 'e2e_buckets.npz'))
+    cfg = default_config(mem_every=2, max_mem_frames=3)
+    proc = InferenceCore(_net(cfg), cfg=cfg)
+    frames, _ = synthetic_video(8, 96, 160, 3, seed=3)
+    first, second = torch.from_numpy(g['first_mask']).cuda(), torch.from_numpy(g['second_mask']).cuda()
+    with torch.inference_mode():
+        for ti in range(8):
+            if ti == 0:
+                prob = proc.step(frames[0].cuda(), first, objects=[1, 2])
+            elif ti == 3:
+                prob = proc.step(frames[3].cuda(), second, objects=[7])
+            elif ti == 6:
+                proc.delete_objects([1])
+                prob = proc.step(frames[6].cuda())
+            else:
+                prob = proc.step(frames[ti].cuda())
+            if ti == 4:
+                assert float(np.abs(proc.last_logits.cpu().numpy() - g['logits_f4']).max()) < 1e-3
+                assert len(proc.memory.work_mem.buckets) == 2
+    assert float(np.abs(proc.last_logits.cpu().numpy() - g['logits']).max()) < 1e-3
+    assert float((prob.cpu() - torch.from_numpy(g['final_prob'])).abs().max()) < 1e-3
+
+
+@pytest.mark.parametrize('over,H,W,K,T', [
+    (dict(mem_every=3, max_mem_frames=4), 240, 432, 3, 12),
+    (dict(mem_every=2, use_long_term=True, long_term=dict(max_mem_frames=4, min_mem_frames=2, num_prototypes=64,
+                                                          max_num_tokens=600, buffer_tokens=100)), 240, 432, 3, 16),
+    (dict(mem_every=3, max_mem_frames=4, flip_aug=True, chunk_size=1), 240, 432, 3, 8),
+    (dict(mem_every=2, max_mem_frames=3, top_k=50), 480, 854, 3, 5),          # 480p: 30x54 = 1620 tokens/frame
+])
+def test_teacher_forced_vs_cpu_oracle(over, H, W, K, T):
+    """Sizes the fixtures do not cover.  Every frame starts from the CPU oracle's exact state (a random-weight
+    recurrent net amplifies 1e-5 differences chaotically when free-running), runs ONE step on each side and
+    compares the segmentation logits, the new memory tokens and the sensory state."""
+    from cutie_b200.config import default_config
+    from cutie_b200.inference.inference_core import InferenceCore
+    from oracle.cpu_core import OracleCore
+    from oracle.synth import synthetic_video
+    from tests.state_sync import load_state_from_oracle
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg = default_config(**over)
+    proc, oracle = InferenceCore(_net(cfg), cfg=cfg), OracleCore(_net(cfg, cuda=False), cfg)
+    frames, mask = synthetic_video(T, H, W, K, seed=5)
+    objs = list(range(1, K + 1))
+    worst = 0.0
+    with torch.inference_mode():
+        for ti in range(T):
+            load_state_from_oracle(proc, oracle, 'cuda')
+            if ti == 0:
+                pg = proc.step(frames[0].cuda(), mask.cuda(), objects=objs)
+                pc = oracle.step(frames[0], mask, objects=objs)
+            else:
+                pg = proc.step(frames[ti].cuda())
+                pc = oracle.step(frames[ti])
+                worst = max(worst, float((proc.last_logits.cpu() - oracle.last_logits).abs().max()))
+            assert float((pg.cpu() - pc).abs().max()) < 1e-3
+            m = proc.memory
+            assert m.work_mem.size(0) == oracle.work.size(0)
+            assert torch.allclose(m.work_mem.key[0].cpu(), oracle.work.k[0], atol=1e-4)
+            assert torch.allclose(m.work_mem.value[objs[-1]].cpu(), oracle.work.v[objs[-1]], rtol=1e-3, atol=2e-3)
+            if cfg.use_long_term:
+                assert m.long_mem.size(0) == oracle.long.size(0)
+                assert torch.allclose(m.work_mem.use_cnt[0].cpu(), oracle.work.use[0], atol=1e-4)
+                if m.long_mem.size(0):
+                    assert torch.allclose(m.long_mem.key[0].cpu(), oracle.long.k[0], atol=1e-4)
+                    assert torch.allclose(m.long_mem.value[objs[0]].cpu(), oracle.long.v[objs[0]], rtol=1e-3, atol=2e-3)
+            for o in objs:
+                assert float((m.sensory[o].cpu() - oracle.sensory[o]).abs().max()) < 2e-3
+    assert worst < 1e-3, worst
