@@ -1,0 +1,327 @@
+"""bench.py -- frames/sec of the Cutie per-frame path on B200 (BASELINE.json metric), with the
+roofline of the dominant kernel and the reference's CPU path timed beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|northstar]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload = "cfg2", BASELINE.json configs[1]): synthetic 480p (854x480 -> 864x480
+padded, 30x54 = 1620 tokens/frame) video, 3 objects, 256-frame working memory (max_mem_frames=256,
+use_long_term=False, mem_every=5, top_k=30): a steady-state bank of 414 720 tokens (1.38 GB), pre-filled
+with seeded N(0,1) keys/values and 1+N(0,1)^2 shrinkage; random-init weights of
+the cutie-base architecture (oracle/synth.py).  A *step* is one InferenceCore.step on one frame; every
+5th step is a memory frame (mask encoder + append + FIFO eviction).  N>1: one independent video stream per
+GPU (weak scaling, no data-path collective -- SURVEY.md section 8(e).1).
+
+One JSON line on stdout (rank 0); everything else goes to stderr.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+WORKLOADS = {
+    # name: (H, W, objects, memory frames, top_k)
+    'cfg2': dict(H=480, W=854, K=3, mem_frames=256, top_k=30,
+                 desc='synthetic 480p video, 3 objects, 256-frame working memory (414720 tokens), 1xB200'),
+    'northstar': dict(H=480, W=854, K=3, mem_frames=6, top_k=30,
+                      desc='synthetic 480p video, 3 objects, ~10k-key working memory (9720 tokens)'),
+}
+
+
+def make_cfg(wl):
+    from cutie_b200.config import default_config
+    return default_config(mem_every=5, max_mem_frames=wl['mem_frames'], use_long_term=False, top_k=wl['top_k'])
+
+
+def make_net(cfg):
+    from cutie_b200.model.cutie import CUTIE
+    from oracle.synth import synthetic_state_dict      # synthetic weights only (no oracle math)
+    net = CUTIE(cfg).eval()
+    net.load_state_dict(synthetic_state_dict(net.state_dict(), 0))
+    return net
+
+
+def synthetic_bank_chunks(wl, chunk_frames=16, seed=1234):
+    """Yields (key [1,64,n], shrinkage [1,1,n], values [1,K,256,n]) CPU chunks of the steady-state bank."""
+    HW = (wl['H'] // 16) * (-(-wl['W'] // 16))
+    total = (wl['mem_frames'] - 2) * HW          # perm frame + this many temp frames = one short of the FIFO limit
+    g = torch.Generator().manual_seed(seed)
+    done = 0
+    while done < total:
+        n = min(chunk_frames * HW, total - done)
+        yield (torch.randn(1, 64, n, generator=g), 1 + torch.randn(1, 1, n, generator=g) ** 2,
+               torch.randn(1, wl['K'], 256, n, generator=g))
+        done += n
+
+
+def nvsmi_sampler(stop, out, idx):
+    q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+    while not stop.is_set():
+        try:
+            r = subprocess.run(['nvidia-smi', f'--id={idx}', f'--query-gpu={q}', '--format=csv,noheader,nounits'],
+                               capture_output=True, text=True, timeout=5)
+            if r.returncode == 0 and r.stdout.strip():
+                out.append([x.strip() for x in r.stdout.strip().split('\n')[0].split(',')])
+        except Exception:
+            pass
+        stop.wait(0.2)
+
+
+def summarize_clocks(samples):
+    if not samples:
+        return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+    sm = [float(s[0]) for s in samples if s[0].replace('.', '').isdigit()]
+    reasons = set()
+    for s in samples:
+        for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), s[3:7]):
+            if v.lower().startswith('active'):
+                reasons.add(name)
+    return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': float(samples[0][1]),
+            'power_w_max': max(float(s[2]) for s in samples), 'reasons': sorted(reasons), 'samples': len(samples)}
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args, wl, rank, world, dev):
+    import cutie_b200.kernels as K_
+    from cutie_b200.inference.inference_core import InferenceCore
+    from oracle.synth import synthetic_video
+    K_.lib()                                             # fail loudly if the CUDA library is missing
+    torch.backends.cudnn.benchmark = True
+    cfg = make_cfg(wl)
+    net = make_net(cfg).to(dev)
+    n_frames = args.warmup + args.steps + 2
+    frames, mask = synthetic_video(n_frames, wl['H'], wl['W'], wl['K'], seed=rank)
+    objs = list(range(1, wl['K'] + 1))
+    proc = InferenceCore(net, cfg=cfg)
+    with torch.inference_mode():
+        proc.step(frames[0].to(dev), mask.to(dev), objects=objs)          # permanent first frame
+        for key, shr, vals in synthetic_bank_chunks(wl):                   # steady-state bank
+            proc.memory.work_mem.add(key.to(dev), {o: vals[:, i].to(dev) for i, o in enumerate(objs)},
+                                     shr.to(dev), None, as_permanent='no')
+    n_tokens = proc.memory.work_mem.size(0)
+    log(f'[rank {rank}] bank prefilled: {n_tokens} tokens, '
+        f'{torch.cuda.memory_allocated(dev) / 2**30:.2f} GiB allocated')
+    frames_dev = frames.to(dev)
+    frames_pin = frames.pin_memory()
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident arm: inputs already in HBM ----
+    with torch.inference_mode():
+        t = 1
+        for _ in range(args.warmup):
+            proc.step(frames_dev[t]); t += 1
+        barrier()
+        stop, samples = threading.Event(), []
+        th = threading.Thread(target=nvsmi_sampler, args=(stop, samples, dev.index or 0), daemon=True)
+        th.start()
+        K_.PROFILE = []
+        launches0 = K_.LAUNCH_COUNT
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(args.steps):
+            proc.step(frames_dev[t]); t += 1
+        ev1.record()
+        barrier()
+        stop.set(); th.join()
+        launches = K_.LAUNCH_COUNT - launches0
+        prof, K_.PROFILE = K_.PROFILE, None
+        ms_total = ev0.elapsed_time(ev1)
+    kernel_ms = {}
+    for name, a, b in prof:
+        kernel_ms.setdefault(name, []).append(a.elapsed_time(b))
+    # ---- end-to-end arm: pinned host frame in, uint8 mask out, copies inside the timed region ----
+    proc2 = proc                                          # same stream state continues (steady state)
+    host_out = torch.empty(wl['H'], wl['W'], dtype=torch.uint8).pin_memory()
+    with torch.inference_mode():
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tt = 1 + args.warmup
+        e0.record()
+        for i in range(args.steps):
+            img = frames_pin[tt + i].to(dev, non_blocking=True)
+            prob = proc2.step(img)
+            host_out.copy_(proc2.output_prob_to_mask(prob).to(torch.uint8), non_blocking=True)
+        e1.record()
+        barrier()
+        ms_e2e = e0.elapsed_time(e1)
+    times = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(times, op=torch.distributed.ReduceOp.MAX)
+    ms_total, ms_e2e = float(times[0]), float(times[1])
+    return dict(ms_total=ms_total, ms_e2e=ms_e2e, kernel_ms=kernel_ms, launches=launches, n_tokens=n_tokens,
+                clocks=summarize_clocks(samples), h2d=frames_pin[0].numel() * 4, d2h=host_out.numel())
+
+
+def run_cpu_reference(args, wl, max_seconds, steps, warmup):
+    """The reference's algorithm on the host cores: oracle/cpu_core.py (pinned to the reference by
+    tests/test_oracle_golden.py), same weights, same synthetic video, same pre-filled bank."""
+    from oracle.cpu_core import OracleCore
+    from oracle.synth import synthetic_video
+    cfg = make_cfg(wl)
+    net = make_net(cfg)
+    frames, mask = synthetic_video(warmup + steps + 2, wl['H'], wl['W'], wl['K'], seed=0)
+    objs = list(range(1, wl['K'] + 1))
+    oc = OracleCore(net, cfg)
+    t_begin = time.perf_counter()
+    with torch.inference_mode():
+        oc.step(frames[0], mask, objects=objs)
+        ks, ss, vs = [oc.work.k[0]], [oc.work.s[0]], {o: [oc.work.v[o]] for o in objs}
+        for key, shr, vals in synthetic_bank_chunks(wl):
+            ks.append(key), ss.append(shr)
+            for i, o in enumerate(objs):
+                vs[o].append(vals[:, i])
+        oc.work.k[0], oc.work.s[0] = torch.cat(ks, -1), torch.cat(ss, -1)
+        for o in objs:
+            oc.work.v[o] = torch.cat(vs[o], -1)
+        del ks, ss, vs
+        log(f'[cpu] bank prefilled: {oc.work.size(0)} tokens; threads={torch.get_num_threads()}')
+        per_frame = []
+        t = 1
+        for i in range(warmup + steps):
+            if per_frame and (time.perf_counter() - t_begin) + max(per_frame) > max_seconds and i >= warmup + 1:
+                break
+            t0 = time.perf_counter()
+            oc.step(frames[t]); t += 1
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                per_frame.append(dt)
+            log(f'[cpu] frame {i} {"(warmup) " if i < warmup else ""}{dt:.2f} s')
+    return per_frame
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=40)
+    ap.add_argument('--warmup', type=int, default=10)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-seconds', type=float, default=150.0)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    HW = (wl['H'] // 16) * (-(-wl['W'] // 16))
+    config = {'workload': f"{args.workload}: {wl['desc']}", 'resolution': [wl['H'], wl['W']], 'objects': wl['K'],
+              'tokens_per_frame': HW, 'memory_tokens': (wl['mem_frames'] - 1) * HW, 'top_k': wl['top_k'],
+              'mem_every': 5, 'streams': world, 'parallelism': f'{world} independent streams (1 per GPU)',
+              'l2': 'no flush: the bank scanned every frame is larger than the 126 MB L2'
+                    if args.workload == 'cfg2' else 'bank fits L2 (north-star size); stated, not flushed',
+              'weights': 'seeded random init (no checkpoint offline)'}
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        cores = os.cpu_count()
+        torch.set_num_threads(cores)
+        per = run_cpu_reference(args, wl, max_seconds=max(args.cpu_seconds, 60.0), steps=args.steps,
+                                warmup=min(args.warmup, 1))
+        fps = len(per) / sum(per)
+        line = {'impl': 'reference', 'metric': 'frames/sec @480p 3-obj', 'value': fps, 'unit': 'frames/s',
+                'n_gpus': args.gpus, 'steps': len(per), 'warmup': min(args.warmup, 1),
+                'ms_per_step': 1000 * sum(per) / len(per), 'higher_is_better': True, 'scaling': 'weak',
+                'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config,
+                'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+                                 'sample': f'{len(per)} full frame(s) of the same workload (time-bounded; '
+                                           f'{args.steps} requested)'},
+                'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+                'gpu_launches': 0}
+        print(json.dumps(line), flush=True)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: there is no CPU fallback for the product path '
+                         '(use --impl reference for the CPU arm)')
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        torch.distributed.init_process_group('nccl', device_id=dev)
+    res = run_ours(args, wl, rank, world, dev)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count())
+        per = run_cpu_reference(args, wl, max_seconds=40.0, steps=1, warmup=0)
+        cpu = {'value': len(per) / sum(per), 'unit': 'frames/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+               'sample': f'{len(per)} full frame of the same workload (same weights, same pre-filled bank) '
+                         f'through oracle/cpu_core.py'}
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    if rank != 0:
+        return
+    peaks = {'hbm_gbs': 6650.0, 'bf16_tflops_sustained': 1400.0, 'src': 'fallback'}
+    pk = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(pk):
+        peaks = dict(json.load(open(pk)), src='measured')
+    N = res['n_tokens']
+    scan = res['kernel_ms'].get('affinity_topk', [])
+    scan_ms = sum(scan) / len(scan) if scan else None
+    flops = 2.0 * N * 128 * HW                       # one K=128 contraction [mk^2|mk].[−qe;2qk.qe]
+    bytes_alg = N * 65 * 4 + HW * 128 * 4 + HW * 32 * 8
+    gather = res['kernel_ms'].get('readout_gather', [])
+    gather_ms = sum(gather) / len(gather) if gather else None
+    gather_bytes = min(N, HW * wl['top_k']) * wl['K'] * 256 * 4 + HW * wl['K'] * 256 * 4 + HW * 32 * 8
+    tensor_bound = flops / (peaks['bf16_tflops_sustained'] * 1e12) > bytes_alg / (peaks['hbm_gbs'] * 1e9)
+    if scan_ms:
+        if tensor_bound:
+            ach = flops / (scan_ms * 1e-3) / 1e12
+            roof = {'bound': 'tensor', 'kernel': 'affinity_scan_kernel+topk_merge_kernel (cutie_affinity_topk)',
+                    'achieved': ach, 'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
+                    'frac': ach / peaks['bf16_tflops_sustained'], 'traffic': None,
+                    'peak_source': f"{peaks['src']} bf16 sustained (kernel timed inside a long step)",
+                    'algorithmic_flops_per_launch': flops, 'avg_launch_ms': scan_ms,
+                    'hbm_view': {'algorithmic_bytes': bytes_alg, 'achieved_gbs': bytes_alg / (scan_ms * 1e-3) / 1e9,
+                                 'frac': bytes_alg / (scan_ms * 1e-3) / 1e9 / peaks['hbm_gbs']},
+                    'note': 'fp32 CUDA-core direct-form evaluation (exact top-k); tcgen05 path is round-2 work'}
+        else:
+            ach = bytes_alg / (scan_ms * 1e-3) / 1e9
+            roof = {'bound': 'hbm', 'kernel': 'affinity_scan_kernel+topk_merge_kernel (cutie_affinity_topk)',
+                    'achieved': ach, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': ach / peaks['hbm_gbs'],
+                    'traffic': None, 'peak_source': f"{peaks['src']} copy bandwidth",
+                    'algorithmic_bytes_per_launch': bytes_alg, 'avg_launch_ms': scan_ms}
+        if gather_ms:
+            roof['readout_gather'] = {'bound': 'hbm', 'algorithmic_bytes': gather_bytes, 'avg_launch_ms': gather_ms,
+                                      'achieved_gbs': gather_bytes / (gather_ms * 1e-3) / 1e9,
+                                      'frac': gather_bytes / (gather_ms * 1e-3) / 1e9 / peaks['hbm_gbs']}
+    else:
+        roof = None
+    kshare = {k: {'avg_ms': sum(v) / len(v), 'calls_per_step': len(v) / args.steps,
+                  'share_of_step': sum(v) / res['ms_total']} for k, v in res['kernel_ms'].items()}
+    fps = world * args.steps / (res['ms_total'] * 1e-3)
+    fps_e2e = world * args.steps / (res['ms_e2e'] * 1e-3)
+    line = {'metric': 'frames/sec @480p 3-obj', 'value': fps, 'unit': 'frames/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': res['ms_total'] / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': config, 'clocks': res['clocks'],
+            'e2e': {'value': fps_e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': res['h2d'],
+                    'd2h_bytes_per_step': res['d2h'], 'ms_per_step': res['ms_e2e'] / args.steps},
+            'gpu_launches': res['launches'], 'roofline': roof, 'cpu_baseline': cpu, 'kernels': kshare}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == '__main__':
+    main()

@@ -395,13 +395,20 @@ class KeyValueMemoryStore:
     # reference attribute aliases (memory_manager / GUI code reads .k/.v/.s/.e in places)
     k, v, s, e = key, value, shrinkage, selection
 
+    def _temp_counter(self, name) -> Dict[int, torch.Tensor]:
+        out = {}
+        for b, bk in self._b.items():
+            parts = [bk.temp.view(name, r) for r in bk.temp.pieces()]
+            out[b] = torch.cat(parts, 1) if parts else torch.zeros(bk.temp.B, 0, device=bk.temp.device)
+        return out
+
     @property
     def use_cnt(self) -> Dict[int, torch.Tensor]:
-        return {b: torch.cat([bk.temp.view('use', r) for r in bk.temp.pieces()], 1) for b, bk in self._b.items()}
+        return self._temp_counter('use')
 
     @property
     def life_cnt(self) -> Dict[int, torch.Tensor]:
-        return {b: torch.cat([bk.temp.view('life', r) for r in bk.temp.pieces()], 1) for b, bk in self._b.items()}
+        return self._temp_counter('life')
 
     def set_capacity_hint(self, temp_tokens: int = 0, perm_tokens: int = 0):
         self.temp_hint, self.perm_hint = int(temp_tokens), int(perm_tokens)

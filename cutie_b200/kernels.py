@@ -17,6 +17,32 @@ _lib = None
 
 USAGE_FIXED_POINT_BITS = 40     # usage accumulators are uint64 fixed point, 2^-40 resolution
 
+LAUNCH_COUNT = 0                # number of cutie_b200 CUDA kernels enqueued so far (bench.py reports the delta)
+PROFILE = None                  # set to a list to collect (name, start_event, end_event) per C-ABI call
+
+
+class _call:
+    """Counts the kernels a C-ABI call launches and, when PROFILE is a list, brackets it with CUDA events
+    on the launching stream (bench.py's live per-kernel timing)."""
+
+    def __init__(self, name: str, launches: int):
+        self.name, self.launches = name, launches
+
+    def __enter__(self):
+        global LAUNCH_COUNT
+        LAUNCH_COUNT += self.launches
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None and exc[0] is None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            PROFILE.append((self.name, self.e0, e1))
+        return False
+
 
 class KernelError(RuntimeError):
     pass
@@ -122,13 +148,15 @@ def affinity_topk(segments: Sequence[BankSegment], qk: torch.Tensor, qe: torch.T
         assert s.key.shape[2] == CK
     assert qk.is_contiguous() and qe.is_contiguous()
     PA, IA = ctypes.c_void_p * ns, ctypes.c_int64 * ns
-    st = L.cutie_affinity_topk(
-        ctypes.c_int(ns), PA(*[s.key.data_ptr() for s in segments]),
-        PA(*[s.shrinkage.data_ptr() for s in segments]), IA(*[s.n for s in segments]),
-        IA(*[s.key.stride(0) for s in segments]), IA(*[s.shrinkage.stride(0) for s in segments]),
-        _ptr(qk), _ptr(qe), _i64(B), _i64(CK), _i64(Q), ctypes.c_int(top_k), ctypes.c_int(kpad),
-        _ptr(idx, torch.int32), _ptr(w), _ptr(sim), _ptr(usage_acc, torch.int64), _i64(n_total),
-        _ptr(ws, torch.uint8), ctypes.c_size_t(ws_bytes), _stream())
+    _L = lib()
+    with _call('affinity_topk', 2):
+        st = L.cutie_affinity_topk(
+            ctypes.c_int(ns), PA(*[s.key.data_ptr() for s in segments]),
+            PA(*[s.shrinkage.data_ptr() for s in segments]), IA(*[s.n for s in segments]),
+            IA(*[s.key.stride(0) for s in segments]), IA(*[s.shrinkage.stride(0) for s in segments]),
+            _ptr(qk), _ptr(qe), _i64(B), _i64(CK), _i64(Q), ctypes.c_int(top_k), ctypes.c_int(kpad),
+            _ptr(idx, torch.int32), _ptr(w), _ptr(sim), _ptr(usage_acc, torch.int64), _i64(n_total),
+            _ptr(ws, torch.uint8), ctypes.c_size_t(ws_bytes), _stream())
     _check(st, 'cutie_affinity_topk')
     return idx, w, sim
 
@@ -150,9 +178,11 @@ def readout_gather(idx: torch.Tensor, w: torch.Tensor, segments: Sequence[BankSe
             ptrs.append(v.data_ptr())
             strides.append(v.stride(0))
     PA, IA, IS = ctypes.c_void_p * (ns * K), ctypes.c_int64 * (ns * K), ctypes.c_int64 * ns
-    st = lib().cutie_readout_gather(_ptr(idx, torch.int32), _ptr(w), _i64(B), _i64(Q), ctypes.c_int(kpad),
-                                    ctypes.c_int(ns), IS(*[s.n for s in segments]), PA(*ptrs), IA(*strides),
-                                    _i64(K), _i64(CV), _ptr(out), _stream())
+    _L = lib()
+    with _call('readout_gather', 1):
+        st = _L.cutie_readout_gather(_ptr(idx, torch.int32), _ptr(w), _i64(B), _i64(Q), ctypes.c_int(kpad),
+                                        ctypes.c_int(ns), IS(*[s.n for s in segments]), PA(*ptrs), IA(*strides),
+                                        _i64(K), _i64(CV), _ptr(out), _stream())
     _check(st, 'cutie_readout_gather')
     return out
 
@@ -162,9 +192,10 @@ def usage_commit(use_cnt: torch.Tensor, life_cnt: torch.Tensor, usage_acc: torch
     B, n = use_cnt.shape
     if n == 0:
         return
-    st = lib().cutie_usage_commit(_ptr(use_cnt), _i64(use_cnt.stride(0)), _ptr(life_cnt), _i64(life_cnt.stride(0)),
-                                  _ptr(usage_acc, torch.int64), _i64(usage_acc.stride(0)), _i64(acc_offset),
-                                  _i64(B), _i64(n), _stream())
+    with _call('usage_commit', 1):
+        st = lib().cutie_usage_commit(_ptr(use_cnt), _i64(use_cnt.stride(0)), _ptr(life_cnt), _i64(life_cnt.stride(0)),
+                                      _ptr(usage_acc, torch.int64), _i64(usage_acc.stride(0)), _i64(acc_offset),
+                                      _i64(B), _i64(n), _stream())
     _check(st, 'cutie_usage_commit')
 
 
@@ -177,8 +208,9 @@ def bank_append(src: torch.Tensor, dst_rows: torch.Tensor):
     assert dst_rows.shape == (B, n, C)
     _rows_view_ok(dst_rows)
     assert src.stride(2) == 1 and src.stride(1) == n
-    st = lib().cutie_bank_append(_ptr(src), _i64(src.stride(0)), _ptr(dst_rows), _i64(dst_rows.stride(0)),
-                                 _i64(B), _i64(C), _i64(n), _stream())
+    with _call('bank_append', 1):
+        st = lib().cutie_bank_append(_ptr(src), _i64(src.stride(0)), _ptr(dst_rows), _i64(dst_rows.stride(0)),
+                                     _i64(B), _i64(C), _i64(n), _stream())
     _check(st, 'cutie_bank_append')
 
 
@@ -187,8 +219,9 @@ def bank_export(rows: torch.Tensor, dst: torch.Tensor):
     B, n, C = rows.shape
     assert dst.shape == (B, C, n) and dst.is_contiguous()
     _rows_view_ok(rows)
-    st = lib().cutie_bank_export(_ptr(rows), _i64(rows.stride(0)), _ptr(dst), _i64(dst.stride(0)),
-                                 _i64(B), _i64(C), _i64(n), _stream())
+    with _call('bank_export', 1):
+        st = lib().cutie_bank_export(_ptr(rows), _i64(rows.stride(0)), _ptr(dst), _i64(dst.stride(0)),
+                                     _i64(B), _i64(C), _i64(n), _stream())
     _check(st, 'cutie_bank_export')
 
 
@@ -204,10 +237,11 @@ def bank_gather(segments_rows: Sequence[torch.Tensor], index: torch.Tensor, dst_
         _rows_view_ok(r)
     _rows_view_ok(dst_rows)
     PA, IA = ctypes.c_void_p * ns, ctypes.c_int64 * ns
-    st = lib().cutie_bank_gather(ctypes.c_int(ns), PA(*[r.data_ptr() for r in segments_rows]),
-                                 IA(*[r.shape[1] for r in segments_rows]), IA(*[r.stride(0) for r in segments_rows]),
-                                 _ptr(index, torch.int64), _ptr(dst_rows), _i64(dst_rows.stride(0)),
-                                 _i64(B), _i64(m), _i64(C), _stream())
+    with _call('bank_gather', 1):
+        st = lib().cutie_bank_gather(ctypes.c_int(ns), PA(*[r.data_ptr() for r in segments_rows]),
+                                     IA(*[r.shape[1] for r in segments_rows]), IA(*[r.stride(0) for r in segments_rows]),
+                                     _ptr(index, torch.int64), _ptr(dst_rows), _i64(dst_rows.stride(0)),
+                                     _i64(B), _i64(m), _i64(C), _stream())
     _check(st, 'cutie_bank_gather')
 
 
@@ -232,21 +266,23 @@ def consolidate(segments: Sequence[BankSegment], proto_key: torch.Tensor, proto_
             vp.append(v.data_ptr()), vs.append(v.stride(0))
     for t in (proto_key, proto_sel):
         _rows_view_ok(t)
-    st = lib().cutie_consolidate(
-        ctypes.c_int(ns), PA(*[s.key.data_ptr() for s in segments]), PA(*[s.shrinkage.data_ptr() for s in segments]),
-        IA(*[s.n for s in segments]), IA(*[s.key.stride(0) for s in segments]),
-        IA(*[s.shrinkage.stride(0) for s in segments]), VA(*vp), VI(*vs), _i64(K),
-        _ptr(proto_key), _i64(proto_key.stride(0)), _ptr(proto_sel), _i64(proto_sel.stride(0)),
-        _i64(B), _i64(P), _i64(CK), _i64(out_values[0].shape[2] if K else 0),
-        OA(*[v.data_ptr() for v in out_values]), OI(*[v.stride(0) for v in out_values]),
-        _ptr(out_shrinkage), _i64(out_shrinkage.stride(0)), _ptr(ws), _i64(n_total), _stream())
+    with _call('consolidate', 1):
+        st = lib().cutie_consolidate(
+            ctypes.c_int(ns), PA(*[s.key.data_ptr() for s in segments]), PA(*[s.shrinkage.data_ptr() for s in segments]),
+            IA(*[s.n for s in segments]), IA(*[s.key.stride(0) for s in segments]),
+            IA(*[s.shrinkage.stride(0) for s in segments]), VA(*vp), VI(*vs), _i64(K),
+            _ptr(proto_key), _i64(proto_key.stride(0)), _ptr(proto_sel), _i64(proto_sel.stride(0)),
+            _i64(B), _i64(P), _i64(CK), _i64(out_values[0].shape[2] if K else 0),
+            OA(*[v.data_ptr() for v in out_values]), OI(*[v.stride(0) for v in out_values]),
+            _ptr(out_shrinkage), _i64(out_shrinkage.stride(0)), _ptr(ws), _i64(n_total), _stream())
     _check(st, 'cutie_consolidate')
 
 
 def obj_summary_accumulate(acc: torch.Tensor, new: torch.Tensor):
     """acc += new  (streaming object-memory sum, memory_manager.py:252-271).  Both [B, Q, E+1] dense."""
     assert acc.is_contiguous() and new.is_contiguous() and acc.shape == new.shape
-    st = lib().cutie_obj_summary_accumulate(_ptr(acc), _ptr(new), _i64(acc.numel()), _stream())
+    with _call('obj_summary_accumulate', 1):
+        st = lib().cutie_obj_summary_accumulate(_ptr(acc), _ptr(new), _i64(acc.numel()), _stream())
     _check(st, 'cutie_obj_summary_accumulate')
 
 
@@ -273,10 +309,11 @@ def qt_linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor
         out = torch.empty(M, N, dtype=torch.float32, device=x.device)
     if ln is not None:
         assert Kd == 256, 'fused LayerNorm supports embed_dim 256'
-    st = lib().cutie_qt_linear(
-        _ptr(x), _i64(M), _i64(Kd), _ptr(weight), _i64(weight.stride(0)), _i64(N), _ptr(bias),
-        _ptr(ln[0] if ln else None), _ptr(ln[1] if ln else None), _ptr(pe), ctypes.c_int(int(summary_norm)),
-        ctypes.c_int(int(relu)), _ptr(residual), _i64(residual_mod), _ptr(xhat_out), _ptr(out), _stream())
+    with _call('qt_linear', 1):
+        st = lib().cutie_qt_linear(
+            _ptr(x), _i64(M), _i64(Kd), _ptr(weight), _i64(weight.stride(0)), _i64(N), _ptr(bias),
+            _ptr(ln[0] if ln else None), _ptr(ln[1] if ln else None), _ptr(pe), ctypes.c_int(int(summary_norm)),
+            ctypes.c_int(int(relu)), _ptr(residual), _i64(residual_mod), _ptr(xhat_out), _ptr(out), _stream())
     _check(st, 'cutie_qt_linear')
     return out
 
@@ -292,9 +329,10 @@ def qt_head_fold(a: torch.Tensor, weight: torch.Tensor, *, transpose_w: bool, sc
     assert weight.shape == (E, E) and weight.stride(1) == 1
     out = torch.empty(M, num_heads, E, dtype=torch.float32, device=a.device)
     dots = torch.empty(M, num_heads, dtype=torch.float32, device=a.device) if bias_vec is not None else None
-    st = lib().cutie_qt_head_fold(_ptr(a), _i64(M), _i64(E), ctypes.c_int(num_heads), _ptr(weight),
-                                  _i64(weight.stride(0)), ctypes.c_int(int(transpose_w)), ctypes.c_float(scale),
-                                  _ptr(bias_vec), _ptr(out), _ptr(dots), _stream())
+    with _call('qt_head_fold', 1):
+        st = lib().cutie_qt_head_fold(_ptr(a), _i64(M), _i64(E), ctypes.c_int(num_heads), _ptr(weight),
+                                      _i64(weight.stride(0)), ctypes.c_int(int(transpose_w)), ctypes.c_float(scale),
+                                      _ptr(bias_vec), _ptr(out), _ptr(dots), _stream())
     _check(st, 'cutie_qt_head_fold')
     return out, dots
 
@@ -304,8 +342,9 @@ def qt_self_attention(qk: torch.Tensor, v: torch.Tensor, num_queries: int, num_h
     M, E2 = qk.shape
     E = E2 // 2
     out = torch.empty(M, E, dtype=torch.float32, device=qk.device)
-    st = lib().cutie_qt_self_attention(_ptr(qk), _ptr(v), _i64(M), _i64(E), ctypes.c_int(num_queries),
-                                       ctypes.c_int(num_heads), _ptr(out), _stream())
+    with _call('qt_self_attention', 1):
+        st = lib().cutie_qt_self_attention(_ptr(qk), _ptr(v), _i64(M), _i64(E), ctypes.c_int(num_queries),
+                                           ctypes.c_int(num_heads), _ptr(out), _stream())
     _check(st, 'cutie_qt_self_attention')
     return out
 
@@ -318,8 +357,9 @@ def qt_aux_mask(pixel: torch.Tensor, w: torch.Tensor, b: torch.Tensor, B: int, K
     logits = torch.empty(B, K, HW, dtype=torch.float32, device=dev)
     fg = torch.empty(B, K, HW, dtype=torch.uint8, device=dev)
     cnt = torch.zeros(BK, dtype=torch.int32, device=dev)
-    st = lib().cutie_qt_aux_mask(_ptr(pixel), _ptr(w), _ptr(b), _i64(B), _i64(K), _i64(E), _i64(HW),
-                                 _ptr(logits), _ptr(fg, torch.uint8), _ptr(cnt, torch.int32), _stream())
+    with _call('qt_aux_mask', 1):
+        st = lib().cutie_qt_aux_mask(_ptr(pixel), _ptr(w), _ptr(b), _i64(B), _i64(K), _i64(E), _i64(HW),
+                                     _ptr(logits), _ptr(fg, torch.uint8), _ptr(cnt, torch.int32), _stream())
     _check(st, 'cutie_qt_aux_mask')
     return logits, fg, cnt
 
@@ -340,10 +380,12 @@ def qt_pixel_to_query(qfold: torch.Tensor, pixel: torch.Tensor, pixel_pe: torch.
     L.cutie_qt_pixel_to_query_splits.restype = ctypes.c_int
     splits = L.cutie_qt_pixel_to_query_splits(_i64(BK), _i64(HW), ctypes.c_int(num_heads))
     ws = torch.empty(BK * num_heads * splits * num_queries * (E + 2), dtype=torch.float32, device=dev)
-    st = L.cutie_qt_pixel_to_query(_ptr(qfold), _ptr(pixel), _ptr(pixel_pe), _ptr(fg, torch.uint8),
-                                   _ptr(fg_count, torch.int32), _ptr(wv), _i64(wv.stride(0)), _ptr(bv),
-                                   _i64(BK), _i64(E), _i64(HW), ctypes.c_int(num_queries), ctypes.c_int(num_heads),
-                                   ctypes.c_int(splits), _ptr(ws), _ptr(out), _stream())
+    _L = lib()
+    with _call('qt_pixel_to_query', 2):
+        st = L.cutie_qt_pixel_to_query(_ptr(qfold), _ptr(pixel), _ptr(pixel_pe), _ptr(fg, torch.uint8),
+                                       _ptr(fg_count, torch.int32), _ptr(wv), _i64(wv.stride(0)), _ptr(bv),
+                                       _i64(BK), _i64(E), _i64(HW), ctypes.c_int(num_queries), ctypes.c_int(num_heads),
+                                       ctypes.c_int(splits), _ptr(ws), _ptr(out), _stream())
     _check(st, 'cutie_qt_pixel_to_query')
     return out
 
@@ -359,8 +401,9 @@ def qt_query_to_pixel(kfold: torch.Tensor, kdots: torch.Tensor, vfold: torch.Ten
     BK, E, HW = pixel.shape
     if out is None:
         out = torch.empty_like(pixel)
-    st = lib().cutie_qt_query_to_pixel(_ptr(kfold), _ptr(kdots), _ptr(vfold), _ptr(out_bias), _ptr(pixel),
-                                       _ptr(pixel_pe), _i64(BK), _i64(E), _i64(HW), ctypes.c_int(num_queries),
-                                       ctypes.c_int(num_heads), _ptr(out), _stream())
+    with _call('qt_query_to_pixel', 1):
+        st = lib().cutie_qt_query_to_pixel(_ptr(kfold), _ptr(kdots), _ptr(vfold), _ptr(out_bias), _ptr(pixel),
+                                           _ptr(pixel_pe), _i64(BK), _i64(E), _i64(HW), ctypes.c_int(num_queries),
+                                           ctypes.c_int(num_heads), _ptr(out), _stream())
     _check(st, 'cutie_qt_query_to_pixel')
     return out

@@ -172,6 +172,8 @@ class OracleCore:
         self.engaged = False
         self.HW = None
         self.read_trace = None                 # filled with (idx, weights, usage) of the last read when set to {}
+        self.selection_hook = None
+        self.chunk_size = cfg.chunk_size
 
     # -- memory read (memory_manager.py:112-208) -----------------------------------------------
     def _read(self, pix_feat, key, selection):
@@ -187,6 +189,12 @@ class OracleCore:
                 mk, ms = self.work.k[b], self.work.s[b]
             sim = mm.similarity_expanded(mk, ms, qk, qe)
             idx, wts = mm.topk_softmax(sim, self.top_k)
+            if self.selection_hook is not None:
+                # test-only: lets a checker substitute an equally valid selection on near-tie queries
+                # (SURVEY.md Appendix B take-away 5); weights are still exp(S)/sum exp(S) of THIS similarity
+                idx = self.selection_hook(b, mk, ms, qk, qe, sim, idx)
+                e = torch.gather(sim, 1, idx).exp()
+                wts = e / e.sum(dim=1, keepdim=True)
             aff = mm.scatter_affinity(idx, wts, mk.shape[-1])
             if self.read_trace is not None:
                 self.read_trace[b] = dict(idx=idx, weights=wts, sim=sim, affinity=aff)
@@ -195,17 +203,20 @@ class OracleCore:
                 self.work.update_usage(b, usage[:, long_n:])
                 if long_n and self.count_long_usage:
                     self.long.update_usage(b, usage[:, :long_n])
-            vals = torch.stack([self.work.v[o] for o in objs], 1)
-            if long_n:
-                vals = torch.cat([torch.stack([self.long.v[o] for o in objs], 1), vals], -1)
-            visual = mm.readout(aff, vals).view(B, len(objs), -1, h, w)
-            sens = torch.stack([self.sensory[o] for o in objs], 1)
-            lm = self.last_mask[:, [self.objects.index(o) for o in objs]]
-            fused = self.net.pixel_fusion(pix_feat, visual, sens, lm)
-            obj_mem = torch.stack([self.obj_v[o] for o in objs], 1).unsqueeze(2)
-            pix, _ = query_transformer(fused, obj_mem, self.sd)
-            for i, o in enumerate(objs):
-                out[o] = pix[:, i]
+            cs = self.chunk_size
+            chunks = [objs] if cs < 1 else [objs[i:i + cs] for i in range(0, len(objs), cs)]
+            for chunk in chunks:                                  # memory_manager.py:176-206
+                vals = torch.stack([self.work.v[o] for o in chunk], 1)
+                if long_n:
+                    vals = torch.cat([torch.stack([self.long.v[o] for o in chunk], 1), vals], -1)
+                visual = mm.readout(aff, vals).view(B, len(chunk), -1, h, w)
+                sens = torch.stack([self.sensory[o] for o in chunk], 1)
+                lm = self.last_mask[:, [self.objects.index(o) for o in chunk]]
+                fused = self.net.pixel_fusion(pix_feat, visual, sens, lm)
+                obj_mem = torch.stack([self.obj_v[o] for o in chunk], 1).unsqueeze(2)
+                pix, _ = query_transformer(fused, obj_mem, self.sd)
+                for i, o in enumerate(chunk):
+                    out[o] = pix[:, i]
         return out
 
     # -- memory write (memory_manager.py:210-296) ----------------------------------------------
@@ -216,7 +227,7 @@ class OracleCore:
             if o not in self.sensory:
                 self.sensory[o] = torch.zeros(key.shape[0], self.cfg.model.sensory_dim, *key.shape[-2:])
         sens = torch.stack([self.sensory[o] for o in self.objects], 1)
-        value, new_sens, summaries, _ = self.net.encode_mask(image, pix_feat, sens, prob)
+        value, new_sens, summaries, _ = self.net.encode_mask(image, pix_feat, sens, prob, chunk_size=self.chunk_size)
         self.engaged = True
         if self.HW is None:
             self.HW = value.shape[-1] * value.shape[-2]
@@ -294,7 +305,8 @@ class OracleCore:
                 ro = self._read(pix_feat, key, selection)
                 ro = torch.stack([ro[o] for o in self.objects], 1)
                 sens = torch.stack([self.sensory[o] for o in self.objects], 1)
-                new_sens, logits, prob = self.net.segment(ms, ro, sens, update_sensory=upd_sens)
+                new_sens, logits, prob = self.net.segment(ms, ro, sens, chunk_size=self.chunk_size,
+                                                             update_sensory=upd_sens)
                 self.last_logits = logits
                 prob = (prob[0] + prob[1].flip(-1)) / 2 if self.flip_aug else prob[0]
                 if upd_sens:

@@ -37,6 +37,8 @@ def load_state_from_oracle(proc, oc, device):
         # recreate bucket ids faithfully: buckets are created in increasing id order
         m.work_mem.global_bucket_id = b
         sel = oc.work.e.get(b) if m.use_long_term else None
+        if m.use_long_term and sel is None:
+            sel = torch.zeros(k.shape[0], k.shape[1], 0)
         if p > 0:
             m.work_mem.add(d(k[:, :, :p]), {o: d(v[:, :, :p]) for o, v in vals.items()}, d(s[:, :, :p]),
                            selection=d(sel[:, :, :0]) if sel is not None else None, as_permanent='first')
@@ -63,3 +65,41 @@ def load_state_from_oracle(proc, oc, device):
     for o, t in oc.obj_v.items():
         m.obj_v[o] = d(t).clone()
     m.engaged = oc.engaged
+
+
+class SelectionReconciler:
+    """Near-tie arbitration for teacher-forced comparisons.
+
+    The CUDA path ranks by the cancellation-free fp32 form, the oracle (like the reference) by the fp32
+    three-term expansion whose rounding noise (~1e-4 absolute on O(100) terms) exceeds the gap between the
+    k-th and (k+1)-th similarity on a few queries per frame.  For every query where the two top-k SETS
+    differ, this hook checks -- against the float64 direct-form ground truth -- that the CUDA selection is a
+    valid top-k (every chosen token is within `rel_tol` of the true k-th value) and, if so, lets the oracle
+    adopt it, so everything downstream can be compared to 1e-3.  An invalid selection raises."""
+
+    def __init__(self, top_k, rel_tol=2e-5, max_frac=0.02):
+        self.top_k, self.rel_tol, self.max_frac = top_k, rel_tol, max_frac
+        self.gpu_idx = None        # [B,Q,kpad] int32 captured from kernels.affinity_topk
+        self.flips = 0
+        self.queries = 0
+
+    def __call__(self, bucket, mk, ms, qk, qe, sim, idx):
+        from oracle import memory_math as mm
+        k = self.top_k
+        g = self.gpu_idx[:, :, :k].transpose(1, 2).long().cpu()            # [B,k,Q]
+        diff = (g.sort(1)[0] != idx.sort(1)[0]).any(1)                      # [B,Q]
+        self.queries += diff.numel()
+        if not diff.any():
+            return idx
+        out = idx.clone()
+        for b, q in diff.nonzero().tolist():
+            truth = mm.similarity_direct(mk[b:b + 1], ms[b:b + 1], qk[b:b + 1, :, q:q + 1], qe[b:b + 1, :, q:q + 1])[0, :, 0]
+            kth = torch.topk(truth, k)[0][-1]
+            chosen = truth[g[b, :, q]]
+            tol = self.rel_tol * float(kth.abs()) + 1e-7
+            assert float((kth - chosen).max()) <= tol, \
+                f'CUDA top-k picked a token {float((kth - chosen).max()):.3e} below the true k-th (tol {tol:.1e})'
+            out[b, :, q] = g[b, :, q]
+            self.flips += 1
+        assert self.flips <= self.max_frac * self.queries + 2, 'too many near-tie disagreements'
+        return out
