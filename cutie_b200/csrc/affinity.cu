@@ -295,7 +295,12 @@ __global__ void __launch_bounds__(256) topk_merge_kernel(const MergeParams p) {
     const long long o = (((long long)b * p.nsplit) * p.Q + q) * kp;
     for (int u = 0; u < NS; ++u) {
       int slot = lane + 32 * u;
-      if (slot < p.top_k) { lv[warp][slot] = p.part_val[o + slot]; li[warp][slot] = p.part_idx[o + slot]; }
+      if (slot < p.top_k) {
+        const int ci = p.part_idx[o + slot];
+        const bool dead = ci < 0 || ci == INT_MAX;          // -1 (public output format) or INT_MAX (scan lists)
+        lv[warp][slot] = dead ? -CUDART_INF_F : p.part_val[o + slot];
+        li[warp][slot] = dead ? INT_MAX : ci;
+      }
     }
     __syncwarp();
   }
@@ -304,7 +309,7 @@ __global__ void __launch_bounds__(256) topk_merge_kernel(const MergeParams p) {
     for (int j = 0; j < p.top_k; ++j) {
       const float cv = p.part_val[o + j];
       const int ci = p.part_idx[o + j];
-      if (ci == INT_MAX) break;                       // end of this split's list
+      if (ci == INT_MAX || ci < 0) break;             // end of this split's list
       const float kth = lv[warp][p.top_k - 1];
       const int kthi = li[warp][p.top_k - 1];
       if (!(cv > kth || (cv == kth && ci < kthi))) break;   // sorted: the rest are worse too
@@ -369,19 +374,38 @@ __global__ void __launch_bounds__(256) readout_gather_kernel(const GatherParams 
       for (int u = 0; u < ns; ++u) {
         const int myi = p.idx[o + lane + 32 * u];
         const float myw = p.w[o + lane + 32 * u];
-        const unsigned livem = __ballot_sync(0xffffffffu, myi >= 0);
-        const int nlive = __popc(livem);       // winners are packed at the front
-#pragma unroll 6
-        for (int j = 0; j < nlive; ++j) {
-          const int id = __shfl_sync(0xffffffffu, myi, j);
-          const float wj = __shfl_sync(0xffffffffu, myw, j);
-          const int s = seg_of(p.segs.begin, p.segs.nseg, id);
-          const float* row = p.segs.rows[s * p.segs.nobj + k] + (long long)b * p.segs.bs[s * p.segs.nobj + k] +
-                             ((long long)id - p.segs.begin[s]) * 256;
-          const float4 v0 = __ldg(reinterpret_cast<const float4*>(row) + lane);
-          const float4 v1 = __ldg(reinterpret_cast<const float4*>(row) + 32 + lane);
-          a0.x = fmaf(wj, v0.x, a0.x); a0.y = fmaf(wj, v0.y, a0.y); a0.z = fmaf(wj, v0.z, a0.z); a0.w = fmaf(wj, v0.w, a0.w);
-          a1.x = fmaf(wj, v1.x, a1.x); a1.y = fmaf(wj, v1.y, a1.y); a1.z = fmaf(wj, v1.z, a1.z); a1.w = fmaf(wj, v1.w, a1.w);
+        unsigned livem = __ballot_sync(0xffffffffu, myi >= 0);   // holes allowed (sharded banks own a subset)
+        while (livem) {
+          // up to 4 winners per trip so several 1 KB row reads are in flight
+          int js[4];
+          int cnt = 0;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            if (livem) { js[t] = __ffs(livem) - 1; livem &= livem - 1; ++cnt; } else { js[t] = -1; }
+          }
+          float4 v0[4], v1[4];
+          float wj[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            if (t < cnt) {
+              const int id = __shfl_sync(0xffffffffu, myi, js[t]);
+              wj[t] = __shfl_sync(0xffffffffu, myw, js[t]);
+              const int s = seg_of(p.segs.begin, p.segs.nseg, id);
+              const float* row = p.segs.rows[s * p.segs.nobj + k] + (long long)b * p.segs.bs[s * p.segs.nobj + k] +
+                                 ((long long)id - p.segs.begin[s]) * 256;
+              v0[t] = __ldg(reinterpret_cast<const float4*>(row) + lane);
+              v1[t] = __ldg(reinterpret_cast<const float4*>(row) + 32 + lane);
+            }
+          }
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            if (t < cnt) {
+              a0.x = fmaf(wj[t], v0[t].x, a0.x); a0.y = fmaf(wj[t], v0[t].y, a0.y);
+              a0.z = fmaf(wj[t], v0[t].z, a0.z); a0.w = fmaf(wj[t], v0[t].w, a0.w);
+              a1.x = fmaf(wj[t], v1[t].x, a1.x); a1.y = fmaf(wj[t], v1[t].y, a1.y);
+              a1.z = fmaf(wj[t], v1[t].z, a1.z); a1.w = fmaf(wj[t], v1[t].w, a1.w);
+            }
+          }
         }
       }
     }
@@ -505,6 +529,33 @@ extern "C" int cutie_affinity_topk(int num_segments, const void* const* seg_key,
     topk_merge_kernel<1><<<mgrid, 256, 0, st>>>(mp);
   else
     topk_merge_kernel<2><<<mgrid, 256, 0, st>>>(mp);
+  CUTIE_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int cutie_topk_merge(const float* part_val, const int32_t* part_idx, int64_t B, int64_t nparts, int64_t Q,
+                                int top_k, int kpad, int32_t* out_idx, float* out_w, float* out_sim,
+                                unsigned long long* usage_acc, int64_t n_total, void* stream) {
+  CUTIE_REQUIRE(part_val && part_idx && out_idx && out_w, "null argument");
+  CUTIE_REQUIRE(kpad == 32 || kpad == 64, "kpad must be 32 or 64");
+  CUTIE_REQUIRE(top_k >= 1 && top_k <= kpad && nparts >= 1 && B >= 1 && Q >= 1, "bad sizes");
+  MergeParams mp;
+  mp.part_val = part_val;
+  mp.part_idx = part_idx;
+  mp.Q = Q;
+  mp.n_total = n_total;
+  mp.nsplit = (int)nparts;
+  mp.top_k = top_k;
+  mp.kpad = kpad;
+  mp.out_idx = out_idx;
+  mp.out_w = out_w;
+  mp.out_sim = out_sim;
+  mp.usage_acc = usage_acc;
+  dim3 mgrid((unsigned)((Q + 7) / 8), (unsigned)B);
+  if (kpad == 32)
+    topk_merge_kernel<1><<<mgrid, 256, 0, (cudaStream_t)stream>>>(mp);
+  else
+    topk_merge_kernel<2><<<mgrid, 256, 0, (cudaStream_t)stream>>>(mp);
   CUTIE_CHECK_LAUNCH();
   return 0;
 }

@@ -161,6 +161,24 @@ def affinity_topk(segments: Sequence[BankSegment], qk: torch.Tensor, qe: torch.T
     return idx, w, sim
 
 
+def topk_merge(part_val: torch.Tensor, part_idx: torch.Tensor, top_k: int, n_total: int,
+               usage_acc: Optional[torch.Tensor] = None, want_sim: bool = False):
+    """Merge per-shard sorted candidate lists [B, parts, Q, kpad] (dead slots: idx < 0) into the global
+    top-k + softmax.  Same outputs as affinity_topk; idx are whatever index space part_idx uses."""
+    B, parts, Q, kpad = part_val.shape
+    assert part_val.is_contiguous() and part_idx.is_contiguous() and kpad == kpad_for(top_k)
+    dev = part_val.device
+    idx = torch.empty(B, Q, kpad, dtype=torch.int32, device=dev)
+    w = torch.empty(B, Q, kpad, dtype=torch.float32, device=dev)
+    sim = torch.empty(B, Q, kpad, dtype=torch.float32, device=dev) if want_sim else None
+    with _call('topk_merge', 1):
+        st = lib().cutie_topk_merge(_ptr(part_val), _ptr(part_idx, torch.int32), _i64(B), _i64(parts), _i64(Q),
+                                    ctypes.c_int(top_k), ctypes.c_int(kpad), _ptr(idx, torch.int32), _ptr(w),
+                                    _ptr(sim), _ptr(usage_acc, torch.int64), _i64(n_total), _stream())
+    _check(st, 'cutie_topk_merge')
+    return idx, w, sim
+
+
 def readout_gather(idx: torch.Tensor, w: torch.Tensor, segments: Sequence[BankSegment],
                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[b,k,c,q] = sum_j w[b,q,j] * V_k[idx[b,q,j], c]  ->  [B, K, CV, Q] (a6, evaluated sparsely)."""

@@ -56,6 +56,14 @@ int cutie_affinity_topk(int num_segments, const void* const* seg_key, const void
                         int32_t* out_idx, float* out_w, float* out_sim, unsigned long long* usage_acc,
                         int64_t n_total, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Merge `nparts` sorted candidate lists per query (part_val/part_idx [B, nparts, Q, kpad], unused slots
+ * idx = INT32_MAX or -1 with val = -inf) into the global top_k + softmax; same outputs as cutie_affinity_topk.
+ * Used by the key-sharded multi-GPU read after the NCCL all-gather of per-shard candidates;
+ * there is no reference counterpart (the reference is single-GPU). */
+int cutie_topk_merge(const float* part_val, const int32_t* part_idx, int64_t B, int64_t nparts, int64_t Q,
+                     int top_k, int kpad, int32_t* out_idx, float* out_w, float* out_sim,
+                     unsigned long long* usage_acc, int64_t n_total, void* stream);
+
 /* Sparse value readout out[b,k,c,q] = sum_j w[b,q,j] * V_k[idx[b,q,j], c].
  * Replaces MemoryManager._readout (memory_manager.py:77-88; dense [K*CV,N]x[N,Q] GEMM against a matrix
  * with top_k non-zeros per column) and _get_visual_values_by_ids (:101-110; torch.stack/cat of the whole

@@ -47,6 +47,37 @@ def affinity_topk(segments, qk, qe, top_k, usage_acc=None, want_sim=False):
     return idx_o, w_o, sim_o
 
 
+def topk_merge(part_val, part_idx, top_k, n_total, usage_acc=None, want_sim=False):
+    from cutie_b200.kernels import kpad_for
+    B, parts, Q, kpad = part_val.shape
+    v = part_val.permute(0, 2, 1, 3).reshape(B, Q, parts * kpad).double().clone()
+    i = part_idx.permute(0, 2, 1, 3).reshape(B, Q, parts * kpad).long()
+    v[i < 0] = float('-inf')
+    # order by (value desc, index asc)
+    order = torch.argsort(i, dim=-1, stable=True)
+    v, i = torch.gather(v, -1, order), torch.gather(i, -1, order)
+    order = torch.argsort(-v, dim=-1, stable=True)[..., :top_k]
+    v, i = torch.gather(v, -1, order), torch.gather(i, -1, order)
+    live = torch.isfinite(v)
+    e = torch.where(live, (v - v[..., :1]).exp(), torch.zeros_like(v))
+    w = (e / e.sum(-1, keepdim=True)).float()
+    kp = kpad_for(top_k)
+    idx_o = torch.full((B, Q, kp), -1, dtype=torch.int32)
+    w_o = torch.zeros(B, Q, kp)
+    idx_o[..., :top_k] = torch.where(live, i, torch.full_like(i, -1)).int()
+    w_o[..., :top_k] = w
+    sim_o = None
+    if want_sim:
+        sim_o = torch.zeros(B, Q, kp)
+        sim_o[..., :top_k] = torch.where(live, v, torch.zeros_like(v)).float()
+    if usage_acc is not None:
+        fx = (w.double() * 2.0 ** 40).to(torch.int64)
+        for b in range(B):
+            m = live[b].reshape(-1)
+            usage_acc[b].index_add_(0, i[b].reshape(-1)[m], fx[b].reshape(-1)[m])
+    return idx_o, w_o, sim_o
+
+
 def readout_gather(idx, w, segments, out=None):
     K = len(segments[0].values)
     vals = [_cat_rows([s.values[k] for s in segments]) for k in range(K)]   # K x [B,N,CV]
@@ -198,7 +229,7 @@ def qt_query_to_pixel(kfold, kdots, vfold, out_bias, pixel, pixel_pe, num_querie
     return res
 
 
-ALL = ['affinity_topk', 'readout_gather', 'usage_commit', 'bank_append', 'bank_export', 'bank_gather',
+ALL = ['affinity_topk', 'topk_merge', 'readout_gather', 'usage_commit', 'bank_append', 'bank_export', 'bank_gather',
        'consolidate', 'obj_summary_accumulate', 'qt_linear', 'qt_head_fold', 'qt_self_attention',
        'qt_aux_mask', 'qt_pixel_to_query', 'qt_query_to_pixel']
 
