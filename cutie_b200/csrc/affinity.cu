@@ -12,21 +12,19 @@
 //   the winners, optional fixed-point usage accumulation (deterministic).
 // Kernel 3  readout_gather_kernel  one warp per query x object: gathers the k winning 1 KB value rows,
 //   accumulates in registers, transposes through smem to the channel-major [B,K,CV,Q] output.
-#include <limits.h>
-#include <math_constants.h>
+#include <stdlib.h>
 
-#include "common.cuh"
+#include "topk_common.cuh"
+#include "affinity_internal.cuh"
 
 namespace cutie {
 thread_local char g_last_error[512] = "";
 
-constexpr int CKD = 64;    // key channels
 constexpr int TQ = 64;     // queries per CTA
 constexpr int TK = 128;    // memory tokens per tile
 constexpr int NT = 256;    // threads per CTA
 constexpr int LDT = 68;    // padded smem row stride (floats)
 constexpr int QCAP = TQ * TK;
-constexpr int KPAD_MAX = 64;
 
 struct ScanParams {
   KeySegments segs;
@@ -34,6 +32,7 @@ struct ScanParams {
   const float* qe;
   long long Q;
   long long n_total;
+  long long samp_begin, samp_stride, samp_count;   // virtual index i -> token samp_begin + i*samp_stride
   int top_k;
   int kpad;
   int tiles_per_split;
@@ -54,62 +53,16 @@ struct ScanSmem {
   int qcount[2];
 };
 
-// Insert candidate (s, idx) into a descending (value, then ascending index) list of `top_k` live slots
-// stored at lv/li[0..32*NS).  Executed by one full warp.  Returns the list's k-th value afterwards.
-template <int NS>
-__device__ __forceinline__ float list_insert(float* lv, int* li, int lane, int top_k, float s, int idx) {
-  const unsigned full = 0xffffffffu;
-  float v[NS];
-  int ix[NS];
-  int pos = 0;
-#pragma unroll
-  for (int u = 0; u < NS; ++u) {
-    v[u] = lv[lane + 32 * u];
-    ix[u] = li[lane + 32 * u];
-    bool better = (v[u] > s) || (v[u] == s && ix[u] < idx);
-    pos += __popc(__ballot_sync(full, better));
-  }
-  float tau = 0.f;
-  if (pos < top_k) {
-    float nv[NS];
-    int ni[NS];
-#pragma unroll
-    for (int u = 0; u < NS; ++u) {
-      int slot = lane + 32 * u;
-      float pv = __shfl_up_sync(full, v[u], 1);
-      int pi = __shfl_up_sync(full, ix[u], 1);
-      if (u > 0) {
-        float cv = __shfl_sync(full, v[u > 0 ? u - 1 : 0], 31);
-        int ci = __shfl_sync(full, ix[u > 0 ? u - 1 : 0], 31);
-        if (lane == 0) { pv = cv; pi = ci; }
-      }
-      nv[u] = slot < pos ? v[u] : (slot == pos ? s : pv);
-      ni[u] = slot < pos ? ix[u] : (slot == pos ? idx : pi);
-      if (slot >= top_k) { nv[u] = -CUDART_INF_F; ni[u] = INT_MAX; }
-      lv[slot] = nv[u];
-      li[slot] = ni[u];
-    }
-#pragma unroll
-    for (int u = 0; u < NS; ++u)
-      if (u == ((top_k - 1) >> 5)) tau = __shfl_sync(full, nv[u], (top_k - 1) & 31);
-  } else {
-#pragma unroll
-    for (int u = 0; u < NS; ++u)
-      if (u == ((top_k - 1) >> 5)) tau = __shfl_sync(full, v[u], (top_k - 1) & 31);
-  }
-  __syncwarp();
-  return tau;
-}
-
-__device__ __forceinline__ void load_key_tile(ScanSmem& sm, int stage, const ScanParams& p, int b, long long g0,
-                                              long long g_end, int tid) {
+__device__ __forceinline__ void load_key_tile(ScanSmem& sm, int stage, const ScanParams& p, int b, long long i0,
+                                              long long i_end, int tid) {
   const int c4 = tid & 15;
 #pragma unroll
   for (int it = 0; it < TK / 16; ++it) {
     int r = (tid >> 4) + 16 * it;
-    long long g = g0 + r;
+    long long i = i0 + r;
     float* dst = &sm.ks[stage][r][4 * c4];
-    if (g < g_end) {
+    if (i < i_end) {
+      const long long g = p.samp_begin + i * p.samp_stride;
       int s = seg_of(p.segs.begin, p.segs.nseg, g);
       const float* src = p.segs.key[s] + (long long)b * p.segs.key_bs[s] + (g - p.segs.begin[s]) * CKD + 4 * c4;
       cp_async16(dst, src);
@@ -118,8 +71,9 @@ __device__ __forceinline__ void load_key_tile(ScanSmem& sm, int stage, const Sca
     }
   }
   if (tid < TK) {
-    long long g = g0 + tid;
-    if (g < g_end) {
+    long long i = i0 + tid;
+    if (i < i_end) {
+      const long long g = p.samp_begin + i * p.samp_stride;
       int s = seg_of(p.segs.begin, p.segs.nseg, g);
       cp_async4(&sm.sh[stage][tid], p.segs.shr[s] + (long long)b * p.segs.shr_bs[s] + (g - p.segs.begin[s]));
     } else {
@@ -137,7 +91,7 @@ __global__ void __launch_bounds__(NT, 1) affinity_scan_kernel(const ScanParams p
   const long long q0 = (long long)blockIdx.x * TQ;
   const long long split_begin = (long long)split * p.tiles_per_split * TK;
   long long split_end = split_begin + (long long)p.tiles_per_split * TK;
-  if (split_end > p.n_total) split_end = p.n_total;
+  if (split_end > p.samp_count) split_end = p.samp_count;
   const int ntiles = split_end > split_begin ? (int)((split_end - split_begin + TK - 1) / TK) : 0;
   const float scale = rsqrtf((float)CKD);
 
@@ -244,7 +198,7 @@ __global__ void __launch_bounds__(NT, 1) affinity_scan_kernel(const ScanParams p
         const unsigned long long ce = __shfl_sync(0xffffffffu, ent, src);
         const float s = __uint_as_float((unsigned)(ce >> 32));
         const int ql = (int)((ce >> 24) & 0xffu);
-        const int idx = (int)(split_begin + (long long)(ce & 0xffffffu));
+        const int idx = (int)(p.samp_begin + (split_begin + (long long)(ce & 0xffffffu)) * p.samp_stride);
         const float kth = sm.lval[ql][p.top_k - 1];
         if (s > kth || (s == kth && idx < sm.lidx[ql][p.top_k - 1])) {
           float tau = list_insert<NS>(&sm.lval[ql][0], &sm.lidx[ql][0], lane, p.top_k, s, idx);
@@ -316,34 +270,10 @@ __global__ void __launch_bounds__(256) topk_merge_kernel(const MergeParams p) {
       list_insert<NS>(&lv[warp][0], &li[warp][0], lane, p.top_k, cv, ci);
     }
   }
-  // softmax over the winners (max-subtracted: equals exp(S)/sum exp(S) of memory_utils.py:60-61 whenever
-  // that expression is finite)
-  const float smax = lv[warp][0];
-  float e[NS], sum = 0.f;
-#pragma unroll
-  for (int u = 0; u < NS; ++u) {
-    int slot = lane + 32 * u;
-    e[u] = (slot < p.top_k && li[warp][slot] != INT_MAX) ? expf(lv[warp][slot] - smax) : 0.f;
-    sum += e[u];
-  }
-  sum = warp_sum(sum);
-  const float inv = 1.f / sum;
   const long long oo = ((long long)b * p.Q + q) * kp;
-#pragma unroll
-  for (int u = 0; u < NS; ++u) {
-    int slot = lane + 32 * u;
-    if (slot < kp) {
-      const bool live = slot < p.top_k && li[warp][slot] != INT_MAX;
-      const float w = live ? e[u] * inv : 0.f;
-      const int id = live ? li[warp][slot] : -1;
-      p.out_idx[oo + slot] = id;
-      p.out_w[oo + slot] = w;
-      if (p.out_sim) p.out_sim[oo + slot] = live ? lv[warp][slot] : 0.f;
-      if (p.usage_acc && live)
-        atomicAdd(&p.usage_acc[(long long)b * p.n_total + id],
-                  (unsigned long long)((double)w * (double)(1ull << CUTIE_B200_USAGE_FRAC_BITS)));
-    }
-  }
+  finalize_topk<NS>(&lv[warp][0], &li[warp][0], lane, p.top_k, kp, p.out_idx + oo, p.out_w + oo,
+                    p.out_sim ? p.out_sim + oo : nullptr,
+                    p.usage_acc ? p.usage_acc + (long long)b * p.n_total : nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -432,14 +362,184 @@ __global__ void usage_commit_kernel(float* use, long long ubs, float* life, long
   }
 }
 
-static int pick_splits(long long B, long long Q, long long n_total) {
+static int pick_splits(long long B, long long Q, long long count) {
   const long long qtiles = (Q + TQ - 1) / TQ;
-  const long long ntiles = (n_total + TK - 1) / TK;
+  const long long ntiles = (count + TK - 1) / TK;
   long long s = num_sms() / (qtiles * B);
   if (s < 1) s = 1;
   if (s > ntiles) s = ntiles;
   if (s < 1) s = 1;
   return (int)s;
+}
+
+// ---- plan: which passes run for a bank of n_total tokens ------------------------------------------------
+// exact   : n_total <  tc_min                      exact scan of everything
+// 2-level : tc_min <= n_total < 3-level threshold  exact scan of a strided sample -> tau -> tcgen05 filter of everything -> re-rank
+// 3-level : larger banks                            exact(sample s0) -> tc(sample s1)+re-rank -> tc(all)+re-rank
+// Samples are nested (s1 divides s0, same origin) so each level re-examines the previous level's winners.
+struct Plan {
+  int levels;             // 1, 2 or 3
+  long long s0, s1;       // strides of the exact sample and of the intermediate tensor pass
+};
+constexpr int TC_CAP = 512;            // candidate slots per (query, split)
+constexpr long long SAMPLE0 = 2048;    // target size of the exact-scan sample
+
+static long long g_tc_min_override = -1;
+
+static long long tc_min_tokens() {
+  if (g_tc_min_override >= 0) return g_tc_min_override;
+  static long long v = -1;
+  if (v < 0) {
+    const char* e = getenv("CUTIE_B200_TC_MIN");
+    v = e ? atoll(e) : 8192;
+    const char* off = getenv("CUTIE_B200_NO_TC");
+    if (off && off[0] == '1') v = (1ll << 40);
+  }
+  return v;
+}
+
+static long long ceil_pow2(long long x) {
+  long long p = 1;
+  while (p < x) p <<= 1;
+  return p;
+}
+
+static Plan make_plan(long long n_total, int top_k) {
+  Plan pl;
+  pl.levels = 1;
+  pl.s0 = pl.s1 = 1;
+  if (n_total < tc_min_tokens() || n_total < 4 * (long long)top_k) return pl;
+  const long long floor_s = 2 * (long long)top_k;      // smallest useful sample
+  if (n_total <= 32 * SAMPLE0) {
+    pl.levels = 2;
+    pl.s0 = ceil_pow2((n_total + SAMPLE0 - 1) / SAMPLE0);
+    if (pl.s0 < 2) pl.s0 = 2;
+    while (pl.s0 > 1 && (n_total + pl.s0 - 1) / pl.s0 < floor_s) pl.s0 >>= 1;
+    if (pl.s0 <= 1) { pl.s0 = 1; pl.levels = 1; }
+    return pl;
+  }
+  pl.levels = 3;
+  pl.s1 = 16;
+  pl.s0 = 16 * ceil_pow2((n_total / 16 + SAMPLE0 - 1) / SAMPLE0);
+  return pl;
+}
+
+struct WsLayout {
+  size_t part, cand, count, lvl;   // byte offsets
+  size_t total;
+};
+
+static WsLayout ws_layout(long long B, long long Q, long long n_total, int top_k) {
+  const int kpad = top_k <= 32 ? 32 : 64;
+  const Plan pl = make_plan(n_total, top_k);
+  WsLayout w;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+  const long long cnt0 = (n_total + pl.s0 - 1) / pl.s0;
+  w.part = take((size_t)B * pick_splits(B, Q, cnt0) * Q * kpad * 8);
+  long long max_tc_splits = 0;
+  if (pl.levels >= 2) {
+    max_tc_splits = tc_split_count(B, Q, n_total);
+    if (pl.levels == 3) {
+      const long long c1 = tc_split_count(B, Q, (n_total + pl.s1 - 1) / pl.s1);
+      if (c1 > max_tc_splits) max_tc_splits = c1;
+    }
+  }
+  w.cand = take((size_t)B * max_tc_splits * Q * TC_CAP * 4);
+  w.count = take((size_t)B * max_tc_splits * Q * 4);
+  w.lvl = take((size_t)B * Q * kpad * 12 * 2);     // two intermediate (idx, w, sim) result sets
+  w.total = off + 256;
+  return w;
+}
+
+static int run_exact(const ScanParams& base, long long B, int nsplit, int* out_idx, float* out_w, float* out_sim,
+                     unsigned long long* usage_acc, cudaStream_t st) {
+  ScanParams sp = base;
+  const long long ntiles = (sp.samp_count + TK - 1) / TK;
+  sp.nsplit = nsplit;
+  sp.tiles_per_split = (int)((ntiles + nsplit - 1) / nsplit);
+  if ((long long)sp.tiles_per_split * TK >= (1ll << 24)) return fail(-1, "%s: split too long", "run_exact");
+  dim3 grid((unsigned)((sp.Q + TQ - 1) / TQ), (unsigned)nsplit, (unsigned)B);
+  const size_t smem = sizeof(ScanSmem);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(affinity_scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(affinity_scan_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_done = true;
+  }
+  if (sp.kpad == 32)
+    affinity_scan_kernel<1><<<grid, NT, smem, st>>>(sp);
+  else
+    affinity_scan_kernel<2><<<grid, NT, smem, st>>>(sp);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error("affinity_scan_kernel", e);
+  MergeParams mp;
+  mp.part_val = sp.part_val;
+  mp.part_idx = sp.part_idx;
+  mp.Q = sp.Q;
+  mp.n_total = sp.n_total;
+  mp.nsplit = nsplit;
+  mp.top_k = sp.top_k;
+  mp.kpad = sp.kpad;
+  mp.out_idx = out_idx;
+  mp.out_w = out_w;
+  mp.out_sim = out_sim;
+  mp.usage_acc = usage_acc;
+  dim3 mgrid((unsigned)((sp.Q + 7) / 8), (unsigned)B);
+  if (sp.kpad == 32)
+    topk_merge_kernel<1><<<mgrid, 256, 0, st>>>(mp);
+  else
+    topk_merge_kernel<2><<<mgrid, 256, 0, st>>>(mp);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error("topk_merge_kernel", e);
+  return 0;
+}
+
+static int run_tc_level(const ScanParams& base, long long B, long long stride, const float* tau, long long tau_stride,
+                        int* cand, int* count, int* out_idx, float* out_w, float* out_sim,
+                        unsigned long long* usage_acc, float* dbg_energy, cudaStream_t st) {
+  TcFilterParams fp;
+  memset(&fp, 0, sizeof(fp));
+  fp.segs = base.segs;
+  fp.qk = base.qk;
+  fp.qe = base.qe;
+  fp.Q = base.Q;
+  fp.samp_begin = 0;
+  fp.samp_stride = stride;
+  fp.samp_count = (base.n_total + stride - 1) / stride;
+  fp.nsplit = tc_split_count(B, base.Q, fp.samp_count);
+  const long long ntiles = (fp.samp_count + 127) / 128;
+  fp.tiles_per_split = (int)((ntiles + fp.nsplit - 1) / fp.nsplit);
+  fp.tau = tau;
+  fp.tau_stride = tau_stride;
+  fp.cand = cand;
+  fp.count = count;
+  fp.cap = TC_CAP;
+  fp.dbg_energy = dbg_energy;
+  int rc = launch_tc_filter(fp, B, st);
+  if (rc) return rc;
+  RerankParams rp;
+  memset(&rp, 0, sizeof(rp));
+  rp.segs = base.segs;
+  rp.qk = base.qk;
+  rp.qe = base.qe;
+  rp.Q = base.Q;
+  rp.n_total = base.n_total;
+  rp.samp_begin = 0;
+  rp.samp_stride = stride;
+  rp.samp_count = fp.samp_count;
+  rp.tiles_per_split = fp.tiles_per_split;
+  rp.nsplit = fp.nsplit;
+  rp.cand = cand;
+  rp.count = count;
+  rp.cap = TC_CAP;
+  rp.top_k = base.top_k;
+  rp.kpad = base.kpad;
+  rp.out_idx = out_idx;
+  rp.out_w = out_w;
+  rp.out_sim = out_sim;
+  rp.usage_acc = usage_acc;
+  return launch_rerank(rp, B, st);
 }
 
 }  // namespace cutie
@@ -450,9 +550,44 @@ extern "C" int cutie_b200_abi_version(void) { return CUTIE_B200_ABI_VERSION; }
 extern "C" const char* cutie_b200_last_error(void) { return g_last_error; }
 
 extern "C" size_t cutie_affinity_workspace_bytes(int64_t B, int64_t Q, int64_t n_total, int top_k) {
-  const int kpad = top_k <= 32 ? 32 : 64;
-  const int ns = pick_splits(B, Q, n_total);
-  return (size_t)B * ns * Q * kpad * 8 + 256;
+  return ws_layout(B, Q, n_total, top_k).total;
+}
+
+// Banks with fewer tokens than this use the exact scan only (default 8192; env CUTIE_B200_TC_MIN /
+// CUTIE_B200_NO_TC=1).  Negative restores the default.  Process-wide; meant for tests and tuning.
+extern "C" void cutie_set_tc_min_tokens(int64_t n) { g_tc_min_override = n; }
+
+// Which plan cutie_affinity_topk will use: 1 = exact scan only, 2/3 = tcgen05 filter levels (see make_plan).
+extern "C" int cutie_affinity_plan_levels(int64_t n_total, int top_k) { return make_plan(n_total, top_k).levels; }
+
+static int fill_scan_params(ScanParams& sp, int num_segments, const void* const* seg_key,
+                            const void* const* seg_shrinkage, const int64_t* seg_len,
+                            const int64_t* seg_key_bstride, const int64_t* seg_shr_bstride, const float* qk,
+                            const float* qe, int64_t Q, int top_k, int kpad, int64_t n_total) {
+  memset(&sp, 0, sizeof(sp));
+  long long tot = 0;
+  for (int s = 0; s < num_segments; ++s) {
+    if (seg_len[s] < 0) return fail(-1, "%s: negative segment length", "cutie_affinity_topk");
+    sp.segs.key[s] = (const float*)seg_key[s];
+    sp.segs.shr[s] = (const float*)seg_shrinkage[s];
+    sp.segs.key_bs[s] = seg_key_bstride[s];
+    sp.segs.shr_bs[s] = seg_shr_bstride[s];
+    sp.segs.begin[s] = tot;
+    tot += seg_len[s];
+  }
+  for (int s = num_segments; s <= kMaxSeg; ++s) sp.segs.begin[s] = tot;
+  sp.segs.nseg = num_segments;
+  if (tot != n_total) return fail(-1, "%s: n_total != sum of segment lengths", "cutie_affinity_topk");
+  sp.qk = qk;
+  sp.qe = qe;
+  sp.Q = Q;
+  sp.n_total = n_total;
+  sp.top_k = top_k;
+  sp.kpad = kpad;
+  sp.samp_begin = 0;
+  sp.samp_stride = 1;
+  sp.samp_count = n_total;
+  return 0;
 }
 
 extern "C" int cutie_affinity_topk(int num_segments, const void* const* seg_key, const void* const* seg_shrinkage,
@@ -466,71 +601,63 @@ extern "C" int cutie_affinity_topk(int num_segments, const void* const* seg_key,
   CUTIE_REQUIRE(kpad == 32 || kpad == 64, "kpad must be 32 or 64");
   CUTIE_REQUIRE(top_k >= 1 && top_k <= kpad, "1 <= top_k <= kpad");
   CUTIE_REQUIRE(B >= 1 && Q >= 1 && qk && qe && out_idx && out_w && workspace, "null/empty argument");
-  ScanParams sp;
-  memset(&sp, 0, sizeof(sp));
-  long long tot = 0;
-  for (int s = 0; s < num_segments; ++s) {
-    CUTIE_REQUIRE(seg_len[s] >= 0, "negative segment length");
-    sp.segs.key[s] = (const float*)seg_key[s];
-    sp.segs.shr[s] = (const float*)seg_shrinkage[s];
-    sp.segs.key_bs[s] = seg_key_bstride[s];
-    sp.segs.shr_bs[s] = seg_shr_bstride[s];
-    sp.segs.begin[s] = tot;
-    tot += seg_len[s];
-  }
-  for (int s = num_segments; s <= kMaxSeg; ++s) sp.segs.begin[s] = tot;
-  sp.segs.nseg = num_segments;
-  CUTIE_REQUIRE(tot == n_total, "n_total != sum of segment lengths");
   CUTIE_REQUIRE(n_total >= top_k, "selected index k out of range (top_k > number of memory tokens)");
   CUTIE_REQUIRE(n_total < (1ll << 31), "bank too large for int32 indices");
-  const int nsplit = pick_splits(B, Q, n_total);
-  const long long ntiles = (n_total + TK - 1) / TK;
-  sp.tiles_per_split = (int)((ntiles + nsplit - 1) / nsplit);
-  CUTIE_REQUIRE((long long)sp.tiles_per_split * TK < (1ll << 24), "split too long for the 24-bit queue index");
-  sp.nsplit = nsplit;
-  sp.qk = qk;
-  sp.qe = qe;
-  sp.Q = Q;
-  sp.n_total = n_total;
-  sp.top_k = top_k;
-  sp.kpad = kpad;
-  const size_t need = (size_t)B * nsplit * Q * kpad * 8;
-  CUTIE_REQUIRE(workspace_bytes >= need, "workspace too small");
-  sp.part_val = (float*)workspace;
-  sp.part_idx = (int*)((char*)workspace + (size_t)B * nsplit * Q * kpad * 4);
+  ScanParams sp;
+  int rc = fill_scan_params(sp, num_segments, seg_key, seg_shrinkage, seg_len, seg_key_bstride, seg_shr_bstride, qk,
+                            qe, Q, top_k, kpad, n_total);
+  if (rc) return rc;
+  const WsLayout wl = ws_layout(B, Q, n_total, top_k);
+  CUTIE_REQUIRE(workspace_bytes >= wl.total, "workspace too small");
+  char* ws = (char*)workspace;
   cudaStream_t st = (cudaStream_t)stream;
-  dim3 grid((unsigned)((Q + TQ - 1) / TQ), (unsigned)nsplit, (unsigned)B);
-  const size_t smem = sizeof(ScanSmem);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(affinity_scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(affinity_scan_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_done = true;
+  const Plan pl = make_plan(n_total, top_k);
+  // level 0: exact scan (of everything, or of the stride-s0 sample)
+  sp.samp_stride = pl.s0;
+  sp.samp_count = (n_total + pl.s0 - 1) / pl.s0;
+  const int ns0 = pick_splits(B, Q, sp.samp_count);
+  sp.part_val = (float*)(ws + wl.part);
+  sp.part_idx = (int*)(ws + wl.part + (size_t)B * ns0 * Q * kpad * 4);
+  if (pl.levels == 1) return run_exact(sp, B, ns0, out_idx, out_w, out_sim, usage_acc, st);
+  const size_t set_bytes = (size_t)B * Q * kpad * 4;
+  int* l_idx[2] = {(int*)(ws + wl.lvl), (int*)(ws + wl.lvl + 3 * set_bytes)};
+  float* l_w[2] = {(float*)(ws + wl.lvl + set_bytes), (float*)(ws + wl.lvl + 4 * set_bytes)};
+  float* l_sim[2] = {(float*)(ws + wl.lvl + 2 * set_bytes), (float*)(ws + wl.lvl + 5 * set_bytes)};
+  rc = run_exact(sp, B, ns0, l_idx[0], l_w[0], l_sim[0], nullptr, st);
+  if (rc) return rc;
+  int* cand = (int*)(ws + wl.cand);
+  int* count = (int*)(ws + wl.count);
+  const float* tau = l_sim[0] + (top_k - 1);      // k-th best exact similarity of the sample, per query
+  if (pl.levels == 3) {
+    rc = run_tc_level(sp, B, pl.s1, tau, kpad, cand, count, l_idx[1], l_w[1], l_sim[1], nullptr, nullptr, st);
+    if (rc) return rc;
+    tau = l_sim[1] + (top_k - 1);
   }
-  if (kpad == 32)
-    affinity_scan_kernel<1><<<grid, NT, smem, st>>>(sp);
-  else
-    affinity_scan_kernel<2><<<grid, NT, smem, st>>>(sp);
-  CUTIE_CHECK_LAUNCH();
-  MergeParams mp;
-  mp.part_val = sp.part_val;
-  mp.part_idx = sp.part_idx;
-  mp.Q = Q;
-  mp.n_total = n_total;
-  mp.nsplit = nsplit;
-  mp.top_k = top_k;
-  mp.kpad = kpad;
-  mp.out_idx = out_idx;
-  mp.out_w = out_w;
-  mp.out_sim = out_sim;
-  mp.usage_acc = usage_acc;
-  dim3 mgrid((unsigned)((Q + 7) / 8), (unsigned)B);
-  if (kpad == 32)
-    topk_merge_kernel<1><<<mgrid, 256, 0, st>>>(mp);
-  else
-    topk_merge_kernel<2><<<mgrid, 256, 0, st>>>(mp);
-  CUTIE_CHECK_LAUNCH();
-  return 0;
+  return run_tc_level(sp, B, 1, tau, kpad, cand, count, out_idx, out_w, out_sim, usage_acc, nullptr, st);
+}
+
+// Test hook: TF32 energies E[b,q,n] = -8 S of the tcgen05 filter for the whole bank (no threshold), plus the
+// candidate machinery exercised with tau = -inf.  dbg_energy [B, Q, n_total] floats.
+extern "C" int cutie_debug_tc_energy(int num_segments, const void* const* seg_key, const void* const* seg_shrinkage,
+                                     const int64_t* seg_len, const int64_t* seg_key_bstride,
+                                     const int64_t* seg_shr_bstride, const float* qk, const float* qe, int64_t B,
+                                     int64_t Q, int64_t n_total, float* dbg_energy, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
+  CUTIE_REQUIRE(num_segments >= 1 && num_segments <= kMaxSeg && dbg_energy && workspace, "bad argument");
+  ScanParams sp;
+  int rc = fill_scan_params(sp, num_segments, seg_key, seg_shrinkage, seg_len, seg_key_bstride, seg_shr_bstride, qk,
+                            qe, Q, 1, 32, n_total);
+  if (rc) return rc;
+  const int nsplit = tc_split_count(B, Q, n_total);
+  const size_t need = (size_t)B * nsplit * Q * TC_CAP * 4 + (size_t)B * nsplit * Q * 4 + (size_t)B * Q * 32 * 12 + 1024;
+  CUTIE_REQUIRE(workspace_bytes >= need, "workspace too small");
+  char* ws = (char*)workspace;
+  int* cand = (int*)ws;
+  int* count = (int*)(ws + (size_t)B * nsplit * Q * TC_CAP * 4);
+  char* o = ws + (size_t)B * nsplit * Q * TC_CAP * 4 + (((size_t)B * nsplit * Q * 4 + 255) / 256) * 256;
+  const size_t set_bytes = (size_t)B * Q * 32 * 4;
+  return run_tc_level(sp, B, 1, nullptr, 0, cand, count, (int*)o, (float*)(o + set_bytes), (float*)(o + 2 * set_bytes),
+                      nullptr, dbg_energy, (cudaStream_t)stream);
 }
 
 extern "C" int cutie_topk_merge(const float* part_val, const int32_t* part_idx, int64_t B, int64_t nparts, int64_t Q,

@@ -1,0 +1,398 @@
+// tcgen05 candidate filter + exact re-rank for the pixel-memory affinity (sm_100a).
+//
+// The exact scan (affinity.cu) spends 2 fp32 FFMA per (token, query, channel) on CUDA cores.  Here the dense
+// contraction runs on the 5th-gen tensor cores in TF32 and is used only as a FILTER:
+//
+//   E[q,n] = -8 S[q,n] = shr_n * sum_c qe_c (k_c - qk_c)^2
+//          = [qe | -2 qe qk | b2_hi 1 b2_lo] . [shr k^2 | shr k | shr BIG*invalid shr]      (K = 128 + 8)
+//
+//   A operand (M = 128 queries, resident for the CTA's lifetime) and B operand (N = 128 memory tokens per
+//   tile, double buffered) are K-major, 4 x [128 rows x 128 B] SWIZZLE_128B blocks + one [128 x 32 B]
+//   un-swizzled tail block; tcgen05.mma.kind::tf32 accumulates into TMEM (2 x 128 columns).
+//   Epilogue thread == query (TMEM lane): the threshold and the candidate list are thread-private, no atomics:
+//   a token is a candidate iff  E_tf32 < Emax_q + delta,  where Emax_q = -8 * (k-th best EXACT similarity over
+//   a subset scanned earlier) and delta = eps * (P_tile + R_tile * sqrt(b2_q))^2 bounds the TF32 rounding error
+//   (P_tile = max sqrt(shr |k|^2), R_tile = max sqrt(shr) over the tile).  A true top-k member therefore always
+//   survives.  Survivors are re-ranked by the exact fp32 direct form (affinity_rerank_kernel), so the final
+//   selection and weights are bit-identical to the exact scan's.
+//
+// Warp roles (288 threads): warps 0-3 epilogue (TMEM lane quarters), warps 4-7 producers (global fp32 rows ->
+// scaled/squared/tf32-rounded swizzled smem), warp 8 TMEM allocator + single-thread MMA issuer.
+#include "topk_common.cuh"
+#include "affinity_internal.cuh"
+
+namespace cutie {
+
+constexpr int QT = 128;                 // queries per CTA (MMA M)
+constexpr int KTILE = 128;              // memory tokens per tile (MMA N)
+constexpr int BLK_BYTES = 128 * 128;    // one SW128 K-block: 128 rows x 128 B
+constexpr int TAIL_BYTES = 128 * 32;    // tail block: 128 rows x 8 tf32
+constexpr int OPER_BYTES = 4 * BLK_BYTES + TAIL_BYTES;   // 69632
+constexpr int TC_THREADS = 288;
+constexpr float TF32_EPS = 1.953125e-3f;   // 2^-9: products of two RN-rounded tf32 operands + fp32 accumulation
+constexpr float BIG_E = 1e30f;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// K-major SWIZZLE_128B descriptor for a [rows x 128 B] block at `addr` (+32 B per k-step of 8 tf32).
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);        // start address
+  d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset: 8 rows x 128 B
+  d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+  return d;
+}
+// K-major un-swizzled (interleaved 8x16B core matrices) descriptor for the [128 x 32 B] tail block:
+// chunk-major: 16 row-groups of chunk 0 (128 B each), then chunk 1 at +2048 B.
+__device__ __forceinline__ uint64_t desc_tail(uint32_t addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)(2048 >> 4) << 16;              // LBO: distance between the two 16-B K chunks
+  d |= (uint64_t)(128 >> 4) << 32;               // SBO: distance between 8-row groups
+  d |= (uint64_t)1 << 46;
+  return d;                                      // layout type 0 = SWIZZLE_NONE
+}
+// byte offsets inside an operand buffer
+__device__ __forceinline__ int off_main(int row, int elem) {     // elem in [0,128): 4 K-blocks of 32
+  const int blk = elem >> 5, chunk = (elem & 31) >> 2, within = elem & 3;
+  return blk * BLK_BYTES + row * 128 + ((chunk ^ (row & 7)) << 4) + within * 4;
+}
+__device__ __forceinline__ int off_tail(int row, int elem) {     // elem in [0,8)
+  return 4 * BLK_BYTES + (elem >> 2) * 2048 + (row >> 3) * 128 + (row & 7) * 16 + (elem & 3) * 4;
+}
+
+struct TcSmemTail {
+  unsigned long long full[2], empty[2], tfull[2], tempty[2];
+  float stats[4][4][2];     // [tile % 4][producer warp][P, R]
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) affinity_tc_filter_kernel(const TcFilterParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* A = smem;                              // queries
+  unsigned char* Bst = smem + OPER_BYTES;               // 2 stages of keys
+  TcSmemTail& T = *reinterpret_cast<TcSmemTail*>(smem + 3 * OPER_BYTES);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.z, split = blockIdx.y;
+  const long long q0 = (long long)blockIdx.x * QT;
+  const long long i_begin = (long long)split * p.tiles_per_split * KTILE;
+  long long i_end = i_begin + (long long)p.tiles_per_split * KTILE;
+  if (i_end > p.samp_count) i_end = p.samp_count;
+  const int ntiles = i_end > i_begin ? (int)((i_end - i_begin + KTILE - 1) / KTILE) : 0;
+
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&T.full[s]), 128);
+      mbar_init(smem_u32(&T.empty[s]), 1);
+      mbar_init(smem_u32(&T.tfull[s]), 1);
+      mbar_init(smem_u32(&T.tempty[s]), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&T.tmem_base)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  // ---- query operand: row = query, [qe | -2 qe qk] + tail [b2_hi, 1, b2_lo, 0...] ----
+  float vq = 0.f, emax = -1.f;     // epilogue thread state (tid < 128)
+  if (tid < QT) {
+    const long long q = q0 + tid;
+    float b2 = 0.f;
+    for (int c = 0; c < CKD; ++c) {
+      float e = 0.f, k = 0.f;
+      if (q < p.Q) {
+        const long long off = ((long long)b * CKD + c) * p.Q + q;
+        e = p.qe[off];
+        k = p.qk[off];
+      }
+      b2 = fmaf(e * k, k, b2);
+      *reinterpret_cast<float*>(A + off_main(tid, c)) = to_tf32(e);
+      *reinterpret_cast<float*>(A + off_main(tid, 64 + c)) = to_tf32(-2.f * e * k);
+    }
+    const float b2_hi = to_tf32(b2), b2_lo = to_tf32(b2 - b2_hi);
+    float tl[8] = {b2_hi, 1.f, b2_lo, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) *reinterpret_cast<float*>(A + off_tail(tid, i)) = tl[i];
+    vq = sqrtf(b2);
+    if (q < p.Q) {
+      // Emax = -8 * tau_q  (tau = k-th best exact similarity of an earlier subset; may be -inf => +inf)
+      const float tau = p.tau ? p.tau[((long long)b * p.Q + q) * p.tau_stride] : -CUDART_INF_F;
+      emax = -8.f * tau;
+      emax += fabsf(emax) * 1e-6f;      // the exact re-rank evaluates in fp32: keep boundary ties
+    }
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = T.tmem_base;
+
+  if (warp < 4) {
+    // =========================== epilogue: thread == query ===========================
+    const long long q = q0 + tid;
+    int cnt = 0;
+    bool ovf = false;
+    int* my = p.cand + (((long long)b * p.nsplit + split) * p.Q + (q < p.Q ? q : 0)) * p.cap;
+    for (int t = 0; t < ntiles; ++t) {
+      const int a = t & 1;
+      mbar_wait(smem_u32(&T.tfull[a]), (t >> 1) & 1);
+      tc_fence_after();
+      float P = 0.f, R = 0.f;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) { P = fmaxf(P, T.stats[t & 3][w][0]); R = fmaxf(R, T.stats[t & 3][w][1]); }
+      const float s_ = P + R * vq;
+      const float thr = (q < p.Q) ? (emax + TF32_EPS * s_ * s_) : -CUDART_INF_F;
+      const long long ibase = i_begin + (long long)t * KTILE;
+#pragma unroll 1
+      for (int cg = 0; cg < 4; ++cg) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * KTILE + cg * 32);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float e = __uint_as_float(r[j]);
+          if (p.dbg_energy && q < p.Q) {
+            const long long i = ibase + cg * 32 + j;
+            if (i < p.samp_count) p.dbg_energy[((long long)b * p.Q + q) * p.samp_count + i] = e;
+          }
+          if (e < thr) {
+            if (cnt < p.cap) {
+              my[cnt] = (int)(p.samp_begin + (ibase + cg * 32 + j) * p.samp_stride);
+              ++cnt;
+            } else {
+              ovf = true;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(smem_u32(&T.tempty[a]));
+    }
+    if (q < p.Q) p.count[((long long)b * p.nsplit + split) * p.Q + q] = ovf ? -1 : cnt;
+  } else if (warp < 8) {
+    // =========================== producers: thread == token row ===========================
+    const int row = tid - 128;
+    const int pw = warp - 4;
+    for (int t = 0; t < ntiles; ++t) {
+      const int s = t & 1;
+      mbar_wait(smem_u32(&T.empty[s]), ((t >> 1) & 1) ^ 1);
+      unsigned char* Bs = Bst + s * OPER_BYTES;
+      const long long i = i_begin + (long long)t * KTILE + row;
+      const bool valid = i < i_end;
+      float shr = 0.f, n2 = 0.f;
+      float4 kf[16];
+      if (valid) {
+        const long long g = p.samp_begin + i * p.samp_stride;
+        const int sg = seg_of(p.segs.begin, p.segs.nseg, g);
+        const float4* src = reinterpret_cast<const float4*>(p.segs.key[sg] + (long long)b * p.segs.key_bs[sg] +
+                                                            (g - p.segs.begin[sg]) * CKD);
+#pragma unroll
+        for (int c4 = 0; c4 < 16; ++c4) kf[c4] = __ldg(src + c4);
+        shr = p.segs.shr[sg][(long long)b * p.segs.shr_bs[sg] + (g - p.segs.begin[sg])];
+      } else {
+#pragma unroll
+        for (int c4 = 0; c4 < 16; ++c4) kf[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int c4 = 0; c4 < 16; ++c4) {
+        const float4 v = kf[c4];
+        n2 += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        float4 sq = make_float4(to_tf32(shr * v.x * v.x), to_tf32(shr * v.y * v.y), to_tf32(shr * v.z * v.z),
+                                to_tf32(shr * v.w * v.w));
+        float4 ln = make_float4(to_tf32(shr * v.x), to_tf32(shr * v.y), to_tf32(shr * v.z), to_tf32(shr * v.w));
+        *reinterpret_cast<float4*>(Bs + off_main(row, 4 * c4)) = sq;
+        *reinterpret_cast<float4*>(Bs + off_main(row, 64 + 4 * c4)) = ln;
+      }
+      const float shr_t = to_tf32(shr);
+      // tail: [shr, BIG if invalid, shr, 0, | 0 0 0 0]
+      *reinterpret_cast<float4*>(Bs + off_tail(row, 0)) = make_float4(shr_t, valid ? 0.f : BIG_E, shr_t, 0.f);
+      *reinterpret_cast<float4*>(Bs + off_tail(row, 4)) = make_float4(0.f, 0.f, 0.f, 0.f);
+      float Pm = warp_max(sqrtf(shr * n2)), Rm = warp_max(sqrtf(shr));
+      if (lane == 0) { T.stats[t & 3][pw][0] = Pm; T.stats[t & 3][pw][1] = Rm; }
+      fence_proxy_async();
+      mbar_arrive(smem_u32(&T.full[s]));
+    }
+  } else {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      // instruction descriptor: D=F32, A=B=TF32, K-major both, N=128, M=128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(KTILE >> 3) << 17) | ((uint32_t)(QT >> 4) << 24);
+      const uint32_t a_base = smem_u32(A);
+      for (int t = 0; t < ntiles; ++t) {
+        const int s = t & 1;
+        mbar_wait(smem_u32(&T.full[s]), (t >> 1) & 1);
+        mbar_wait(smem_u32(&T.tempty[s]), ((t >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t b_base = smem_u32(Bst + s * OPER_BYTES);
+        const uint32_t d = tmem + (uint32_t)(s * KTILE);
+#pragma unroll
+        for (int blk = 0; blk < 4; ++blk)
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            tc_mma_tf32(d, desc_sw128(a_base + blk * BLK_BYTES + ks * 32), desc_sw128(b_base + blk * BLK_BYTES + ks * 32),
+                        idesc, (blk | ks) ? 1u : 0u);
+        tc_mma_tf32(d, desc_tail(a_base + 4 * BLK_BYTES), desc_tail(b_base + 4 * BLK_BYTES), idesc, 1u);
+        tc_commit(smem_u32(&T.empty[s]));
+        tc_commit(smem_u32(&T.tfull[s]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Exact re-rank: one warp per query.  Candidates of all splits -> exact fp32 similarity -> sorted top-k ->
+// softmax / usage.  A split whose candidate list overflowed is rescanned exhaustively (rare).
+template <int NS>
+__global__ void __launch_bounds__(256) affinity_rerank_kernel(const RerankParams p) {
+  __shared__ float lv[8][KPAD_MAX];
+  __shared__ int li[8][KPAD_MAX];
+  __shared__ float qa[8][CKD], qb[8][CKD];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y;
+  const long long q = (long long)blockIdx.x * 8 + warp;
+  if (q >= p.Q) return;
+  for (int u = 0; u < NS; ++u) { lv[warp][lane + 32 * u] = -CUDART_INF_F; li[warp][lane + 32 * u] = INT_MAX; }
+  for (int c = lane; c < CKD; c += 32) {
+    const long long off = ((long long)b * CKD + c) * p.Q + q;
+    const float a = sqrtf(p.qe[off]);
+    qa[warp][c] = a;
+    qb[warp][c] = a * p.qk[off];
+  }
+  __syncwarp();
+  for (int s = 0; s < p.nsplit; ++s) {
+    const long long lb = ((long long)b * p.nsplit + s) * p.Q + q;
+    int n = p.count[lb];
+    const int* cl = p.cand + lb * p.cap;
+    long long i_begin = 0;
+    const bool exhaustive = n < 0;
+    if (exhaustive) {                        // overflow: walk the split's whole index range
+      i_begin = (long long)s * p.tiles_per_split * KTILE;
+      long long i_end = i_begin + (long long)p.tiles_per_split * KTILE;
+      if (i_end > p.samp_count) i_end = p.samp_count;
+      n = (int)(i_end > i_begin ? i_end - i_begin : 0);
+    }
+    for (int base = 0; base < n; base += 32) {
+      const int j = base + lane;
+      float sv = -CUDART_INF_F;
+      int id = INT_MAX;
+      if (j < n) {
+        id = exhaustive ? (int)(p.samp_begin + (i_begin + j) * p.samp_stride) : cl[j];
+        const int sg = seg_of(p.segs.begin, p.segs.nseg, id);
+        const float* krow = p.segs.key[sg] + (long long)b * p.segs.key_bs[sg] + ((long long)id - p.segs.begin[sg]) * CKD;
+        const float shr = p.segs.shr[sg][(long long)b * p.segs.shr_bs[sg] + ((long long)id - p.segs.begin[sg])];
+        sv = exact_similarity(krow, shr, qa[warp], qb[warp]);
+      }
+      const float kth = lv[warp][p.top_k - 1];
+      const int kthi = li[warp][p.top_k - 1];
+      unsigned bits = __ballot_sync(0xffffffffu, (j < n) && (sv > kth || (sv == kth && id < kthi)));
+      while (bits) {
+        const int src = __ffs(bits) - 1;
+        bits &= bits - 1;
+        const float cs = __shfl_sync(0xffffffffu, sv, src);
+        const int ci = __shfl_sync(0xffffffffu, id, src);
+        const float k2 = lv[warp][p.top_k - 1];
+        if (cs > k2 || (cs == k2 && ci < li[warp][p.top_k - 1]))
+          list_insert<NS>(&lv[warp][0], &li[warp][0], lane, p.top_k, cs, ci);
+      }
+    }
+  }
+  const long long oo = ((long long)b * p.Q + q) * p.kpad;
+  finalize_topk<NS>(&lv[warp][0], &li[warp][0], lane, p.top_k, p.kpad, p.out_idx + oo, p.out_w + oo,
+                    p.out_sim ? p.out_sim + oo : nullptr,
+                    p.usage_acc ? p.usage_acc + (long long)b * p.n_total : nullptr);
+}
+
+size_t tc_filter_smem_bytes() { return (size_t)3 * OPER_BYTES + sizeof(TcSmemTail) + 64; }
+
+int launch_tc_filter(const TcFilterParams& p, long long B, cudaStream_t st) {
+  static bool attr_done = false;
+  const size_t smem = tc_filter_smem_bytes();
+  if (!attr_done) {
+    cudaFuncSetAttribute(affinity_tc_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_done = true;
+  }
+  dim3 grid((unsigned)((p.Q + QT - 1) / QT), (unsigned)p.nsplit, (unsigned)B);
+  affinity_tc_filter_kernel<<<grid, TC_THREADS, smem, st>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error("affinity_tc_filter_kernel", e);
+  return 0;
+}
+
+int launch_rerank(const RerankParams& p, long long B, cudaStream_t st) {
+  dim3 grid((unsigned)((p.Q + 7) / 8), (unsigned)B);
+  if (p.kpad == 32)
+    affinity_rerank_kernel<1><<<grid, 256, 0, st>>>(p);
+  else
+    affinity_rerank_kernel<2><<<grid, 256, 0, st>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error("affinity_rerank_kernel", e);
+  return 0;
+}
+
+int tc_split_count(long long B, long long Q, long long samp_count) {
+  const long long qtiles = (Q + QT - 1) / QT;
+  const long long ntiles = (samp_count + KTILE - 1) / KTILE;
+  long long s = num_sms() / (qtiles * B);
+  if (s < 1) s = 1;
+  if (s > ntiles) s = ntiles;
+  if (s < 1) s = 1;
+  return (int)s;
+}
+
+}  // namespace cutie

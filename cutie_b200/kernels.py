@@ -149,7 +149,7 @@ def affinity_topk(segments: Sequence[BankSegment], qk: torch.Tensor, qe: torch.T
     assert qk.is_contiguous() and qe.is_contiguous()
     PA, IA = ctypes.c_void_p * ns, ctypes.c_int64 * ns
     _L = lib()
-    with _call('affinity_topk', 2):
+    with _call('affinity_topk', 2 * _L.cutie_affinity_plan_levels(_i64(n_total), ctypes.c_int(top_k))):
         st = L.cutie_affinity_topk(
             ctypes.c_int(ns), PA(*[s.key.data_ptr() for s in segments]),
             PA(*[s.shrinkage.data_ptr() for s in segments]), IA(*[s.n for s in segments]),
@@ -159,6 +159,35 @@ def affinity_topk(segments: Sequence[BankSegment], qk: torch.Tensor, qe: torch.T
             _ptr(ws, torch.uint8), ctypes.c_size_t(ws_bytes), _stream())
     _check(st, 'cutie_affinity_topk')
     return idx, w, sim
+
+
+def set_tc_min_tokens(n: int):
+    """Banks with fewer tokens than n use the exact fp32 scan only; larger ones add the tcgen05 filter levels."""
+    lib().cutie_set_tc_min_tokens(_i64(n))
+
+
+def affinity_plan_levels(n_total: int, top_k: int) -> int:
+    return int(lib().cutie_affinity_plan_levels(_i64(n_total), ctypes.c_int(top_k)))
+
+
+def debug_tc_energy(segments: Sequence[BankSegment], qk: torch.Tensor, qe: torch.Tensor) -> torch.Tensor:
+    """Test hook: TF32 energies -8*S [B, Q, N] straight out of the tcgen05 filter."""
+    B, CK, Q = qk.shape
+    n_total = sum(s.n for s in segments)
+    out = torch.zeros(B, Q, n_total, dtype=torch.float32, device=qk.device)
+    ns = len(segments)
+    PA, IA = ctypes.c_void_p * ns, ctypes.c_int64 * ns
+    ws_bytes = 148 * 512 * 4 * B * Q + 4 * 148 * B * Q + B * Q * 32 * 12 + (1 << 20)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=qk.device)
+    with _call('debug_tc_energy', 2):
+        st = lib().cutie_debug_tc_energy(
+            ctypes.c_int(ns), PA(*[s.key.data_ptr() for s in segments]),
+            PA(*[s.shrinkage.data_ptr() for s in segments]), IA(*[s.n for s in segments]),
+            IA(*[s.key.stride(0) for s in segments]), IA(*[s.shrinkage.stride(0) for s in segments]),
+            _ptr(qk), _ptr(qe), _i64(B), _i64(Q), _i64(n_total), _ptr(out), _ptr(ws, torch.uint8),
+            ctypes.c_size_t(ws_bytes), _stream())
+    _check(st, 'cutie_debug_tc_energy')
+    return out
 
 
 def topk_merge(part_val: torch.Tensor, part_idx: torch.Tensor, top_k: int, n_total: int,

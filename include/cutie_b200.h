@@ -56,6 +56,19 @@ int cutie_affinity_topk(int num_segments, const void* const* seg_key, const void
                         int32_t* out_idx, float* out_w, float* out_sim, unsigned long long* usage_acc,
                         int64_t n_total, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Execution plan of cutie_affinity_topk for a bank of n_total tokens: 1 = exact fp32 scan only; 2 / 3 = exact
+ * scan of a strided sample, then tcgen05 (TF32) candidate filter(s) + exact fp32 re-rank.  All plans return the
+ * same selection and weights (the filter only discards tokens that provably cannot be in the top-k).
+ * cutie_set_tc_min_tokens: banks smaller than n use plan 1 (default 8192; negative restores the default). */
+int cutie_affinity_plan_levels(int64_t n_total, int top_k);
+void cutie_set_tc_min_tokens(int64_t n);
+/* Test hook: raw TF32 energies E[b,q,n] = -8*S[n,q] computed by the tcgen05 filter over the whole bank
+ * (dbg_energy [B,Q,n_total]); workspace >= cutie_affinity_workspace_bytes(B,Q,n_total,30) + B*Q*n_total*0. */
+int cutie_debug_tc_energy(int num_segments, const void* const* seg_key, const void* const* seg_shrinkage,
+                          const int64_t* seg_len, const int64_t* seg_key_bstride, const int64_t* seg_shr_bstride,
+                          const float* qk, const float* qe, int64_t B, int64_t Q, int64_t n_total,
+                          float* dbg_energy, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Merge `nparts` sorted candidate lists per query (part_val/part_idx [B, nparts, Q, kpad], unused slots
  * idx = INT32_MAX or -1 with val = -inf) into the global top_k + softmax; same outputs as cutie_affinity_topk.
  * Used by the key-sharded multi-GPU read after the NCCL all-gather of per-shard candidates;
