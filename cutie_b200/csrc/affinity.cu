@@ -373,16 +373,15 @@ static int pick_splits(long long B, long long Q, long long count) {
 }
 
 // ---- plan: which passes run for a bank of n_total tokens ------------------------------------------------
-// exact   : n_total <  tc_min                      exact scan of everything
-// 2-level : tc_min <= n_total < 3-level threshold  exact scan of a strided sample -> tau -> tcgen05 filter of everything -> re-rank
-// 3-level : larger banks                            exact(sample s0) -> tc(sample s1)+re-rank -> tc(all)+re-rank
-// Samples are nested (s1 divides s0, same origin) so each level re-examines the previous level's winners.
+// exact  (levels == 0): n_total < tc_min                 exact fp32 scan of everything (affinity_scan_kernel)
+// filter (levels >= 1): nested strided samples, coarsest first (strides ... 256, 16, 1).  The coarsest sample has
+//                       <= TC_CAP tokens so every one of them is a candidate; each level hands an upper bound of its
+//                       k-th smallest energy to the next; the last level (stride 1) is re-ranked exactly.
 struct Plan {
-  int levels;             // 1, 2 or 3
-  long long s0, s1;       // strides of the exact sample and of the intermediate tensor pass
+  int levels;             // 0 = exact scan only
+  long long stride[8];    // coarsest first, last == 1
 };
-constexpr int TC_CAP = 512;            // candidate slots per (query, split)
-constexpr long long SAMPLE0 = 2048;    // target size of the exact-scan sample
+constexpr int TC_CAP = 4096;           // candidate slots per query
 
 static long long g_tc_min_override = -1;
 
@@ -398,34 +397,24 @@ static long long tc_min_tokens() {
   return v;
 }
 
-static long long ceil_pow2(long long x) {
-  long long p = 1;
-  while (p < x) p <<= 1;
-  return p;
-}
-
 static Plan make_plan(long long n_total, int top_k) {
   Plan pl;
-  pl.levels = 1;
-  pl.s0 = pl.s1 = 1;
-  if (n_total < tc_min_tokens() || n_total < 4 * (long long)top_k) return pl;
-  const long long floor_s = 2 * (long long)top_k;      // smallest useful sample
-  if (n_total <= 32 * SAMPLE0) {
-    pl.levels = 2;
-    pl.s0 = ceil_pow2((n_total + SAMPLE0 - 1) / SAMPLE0);
-    if (pl.s0 < 2) pl.s0 = 2;
-    while (pl.s0 > 1 && (n_total + pl.s0 - 1) / pl.s0 < floor_s) pl.s0 >>= 1;
-    if (pl.s0 <= 1) { pl.s0 = 1; pl.levels = 1; }
-    return pl;
-  }
-  pl.levels = 3;
-  pl.s1 = 16;
-  pl.s0 = 16 * ceil_pow2((n_total / 16 + SAMPLE0 - 1) / SAMPLE0);
+  pl.levels = 0;
+  if (n_total < tc_min_tokens() || n_total < 2 * (long long)top_k) return pl;
+  long long st[8];
+  int n = 0;
+  st[n++] = 1;
+  while ((n_total + st[n - 1] - 1) / st[n - 1] > TC_CAP && n < 8) { st[n] = st[n - 1] * 16; ++n; }
+  // the coarsest sample must still hold at least 2k tokens to give a meaningful bound
+  while (n > 1 && (n_total + st[n - 1] - 1) / st[n - 1] < 2 * (long long)top_k) --n;
+  if ((n_total + st[n - 1] - 1) / st[n - 1] > TC_CAP) return pl;      // cannot seed the thresholds: exact scan
+  pl.levels = n;
+  for (int i = 0; i < n; ++i) pl.stride[i] = st[n - 1 - i];
   return pl;
 }
 
 struct WsLayout {
-  size_t part, cand, count, lvl;   // byte offsets
+  size_t part, cand_idx, cand_e, count, dmax, emax0, emax1;   // byte offsets
   size_t total;
 };
 
@@ -433,21 +422,19 @@ static WsLayout ws_layout(long long B, long long Q, long long n_total, int top_k
   const int kpad = top_k <= 32 ? 32 : 64;
   const Plan pl = make_plan(n_total, top_k);
   WsLayout w;
+  memset(&w, 0, sizeof(w));
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
-  const long long cnt0 = (n_total + pl.s0 - 1) / pl.s0;
-  w.part = take((size_t)B * pick_splits(B, Q, cnt0) * Q * kpad * 8);
-  long long max_tc_splits = 0;
-  if (pl.levels >= 2) {
-    max_tc_splits = tc_split_count(B, Q, n_total);
-    if (pl.levels == 3) {
-      const long long c1 = tc_split_count(B, Q, (n_total + pl.s1 - 1) / pl.s1);
-      if (c1 > max_tc_splits) max_tc_splits = c1;
-    }
+  if (pl.levels == 0) {
+    w.part = take((size_t)B * pick_splits(B, Q, n_total) * Q * kpad * 8);
+  } else {
+    w.cand_idx = take((size_t)B * Q * TC_CAP * 4);
+    w.cand_e = take((size_t)B * Q * TC_CAP * 4);
+    w.count = take((size_t)B * Q * 4);
+    w.dmax = take((size_t)B * Q * 4);
+    w.emax0 = take((size_t)B * Q * 4);
+    w.emax1 = take((size_t)B * Q * 4);
   }
-  w.cand = take((size_t)B * max_tc_splits * Q * TC_CAP * 4);
-  w.count = take((size_t)B * max_tc_splits * Q * 4);
-  w.lvl = take((size_t)B * Q * kpad * 12 * 2);     // two intermediate (idx, w, sim) result sets
   w.total = off + 256;
   return w;
 }
@@ -495,9 +482,9 @@ static int run_exact(const ScanParams& base, long long B, int nsplit, int* out_i
   return 0;
 }
 
-static int run_tc_level(const ScanParams& base, long long B, long long stride, const float* tau, long long tau_stride,
-                        int* cand, int* count, int* out_idx, float* out_w, float* out_sim,
-                        unsigned long long* usage_acc, float* dbg_energy, cudaStream_t st) {
+// One filter level: zero the per-query counters, tcgen05 filter over the stride-`stride` sample.
+static int run_filter_level(const ScanParams& base, long long B, long long stride, const float* emax_in, char* ws,
+                            const WsLayout& wl, float* dbg_energy, cudaStream_t st) {
   TcFilterParams fp;
   memset(&fp, 0, sizeof(fp));
   fp.segs = base.segs;
@@ -510,14 +497,41 @@ static int run_tc_level(const ScanParams& base, long long B, long long stride, c
   fp.nsplit = tc_split_count(B, base.Q, fp.samp_count);
   const long long ntiles = (fp.samp_count + 127) / 128;
   fp.tiles_per_split = (int)((ntiles + fp.nsplit - 1) / fp.nsplit);
-  fp.tau = tau;
-  fp.tau_stride = tau_stride;
-  fp.cand = cand;
-  fp.count = count;
+  fp.emax_in = emax_in;
+  fp.cand_idx = (int*)(ws + wl.cand_idx);
+  fp.cand_e = (float*)(ws + wl.cand_e);
+  fp.count = (int*)(ws + wl.count);
+  fp.dmax = (float*)(ws + wl.dmax);
   fp.cap = TC_CAP;
   fp.dbg_energy = dbg_energy;
-  int rc = launch_tc_filter(fp, B, st);
-  if (rc) return rc;
+  cudaError_t e = cudaMemsetAsync(ws + wl.count, 0, (size_t)(wl.emax0 - wl.count), st);   // count + dmax
+  if (e != cudaSuccess) return set_cuda_error("cudaMemsetAsync", e);
+  return launch_tc_filter(fp, B, st);
+}
+
+static int run_filtered(const ScanParams& base, long long B, const Plan& pl, char* ws, const WsLayout& wl,
+                        int* out_idx, float* out_w, float* out_sim, unsigned long long* usage_acc,
+                        float* dbg_energy, cudaStream_t st) {
+  float* emax[2] = {(float*)(ws + wl.emax0), (float*)(ws + wl.emax1)};
+  const float* emax_in = nullptr;
+  for (int l = 0; l < pl.levels; ++l) {
+    const bool last = (l == pl.levels - 1);
+    int rc = run_filter_level(base, B, pl.stride[l], emax_in, ws, wl, last ? dbg_energy : nullptr, st);
+    if (rc) return rc;
+    if (!last) {
+      SelectParams sp;
+      sp.Q = base.Q;
+      sp.cand_e = (const float*)(ws + wl.cand_e);
+      sp.count = (const int*)(ws + wl.count);
+      sp.dmax = (const float*)(ws + wl.dmax);
+      sp.cap = TC_CAP;
+      sp.top_k = base.top_k;
+      sp.emax_out = emax[l & 1];
+      rc = launch_level_select(sp, B, base.kpad, st);
+      if (rc) return rc;
+      emax_in = emax[l & 1];
+    }
+  }
   RerankParams rp;
   memset(&rp, 0, sizeof(rp));
   rp.segs = base.segs;
@@ -525,13 +539,8 @@ static int run_tc_level(const ScanParams& base, long long B, long long stride, c
   rp.qe = base.qe;
   rp.Q = base.Q;
   rp.n_total = base.n_total;
-  rp.samp_begin = 0;
-  rp.samp_stride = stride;
-  rp.samp_count = fp.samp_count;
-  rp.tiles_per_split = fp.tiles_per_split;
-  rp.nsplit = fp.nsplit;
-  rp.cand = cand;
-  rp.count = count;
+  rp.cand_idx = (const int*)(ws + wl.cand_idx);
+  rp.count = (const int*)(ws + wl.count);
   rp.cap = TC_CAP;
   rp.top_k = base.top_k;
   rp.kpad = base.kpad;
@@ -612,52 +621,46 @@ extern "C" int cutie_affinity_topk(int num_segments, const void* const* seg_key,
   char* ws = (char*)workspace;
   cudaStream_t st = (cudaStream_t)stream;
   const Plan pl = make_plan(n_total, top_k);
-  // level 0: exact scan (of everything, or of the stride-s0 sample)
-  sp.samp_stride = pl.s0;
-  sp.samp_count = (n_total + pl.s0 - 1) / pl.s0;
-  const int ns0 = pick_splits(B, Q, sp.samp_count);
-  sp.part_val = (float*)(ws + wl.part);
-  sp.part_idx = (int*)(ws + wl.part + (size_t)B * ns0 * Q * kpad * 4);
-  if (pl.levels == 1) return run_exact(sp, B, ns0, out_idx, out_w, out_sim, usage_acc, st);
-  const size_t set_bytes = (size_t)B * Q * kpad * 4;
-  int* l_idx[2] = {(int*)(ws + wl.lvl), (int*)(ws + wl.lvl + 3 * set_bytes)};
-  float* l_w[2] = {(float*)(ws + wl.lvl + set_bytes), (float*)(ws + wl.lvl + 4 * set_bytes)};
-  float* l_sim[2] = {(float*)(ws + wl.lvl + 2 * set_bytes), (float*)(ws + wl.lvl + 5 * set_bytes)};
-  rc = run_exact(sp, B, ns0, l_idx[0], l_w[0], l_sim[0], nullptr, st);
-  if (rc) return rc;
-  int* cand = (int*)(ws + wl.cand);
-  int* count = (int*)(ws + wl.count);
-  const float* tau = l_sim[0] + (top_k - 1);      // k-th best exact similarity of the sample, per query
-  if (pl.levels == 3) {
-    rc = run_tc_level(sp, B, pl.s1, tau, kpad, cand, count, l_idx[1], l_w[1], l_sim[1], nullptr, nullptr, st);
-    if (rc) return rc;
-    tau = l_sim[1] + (top_k - 1);
+  if (pl.levels == 0) {
+    const int ns0 = pick_splits(B, Q, n_total);
+    sp.part_val = (float*)(ws + wl.part);
+    sp.part_idx = (int*)(ws + wl.part + (size_t)B * ns0 * Q * kpad * 4);
+    return run_exact(sp, B, ns0, out_idx, out_w, out_sim, usage_acc, st);
   }
-  return run_tc_level(sp, B, 1, tau, kpad, cand, count, out_idx, out_w, out_sim, usage_acc, nullptr, st);
+  return run_filtered(sp, B, pl, ws, wl, out_idx, out_w, out_sim, usage_acc, nullptr, st);
 }
 
-// Test hook: TF32 energies E[b,q,n] = -8 S of the tcgen05 filter for the whole bank (no threshold), plus the
-// candidate machinery exercised with tau = -inf.  dbg_energy [B, Q, n_total] floats.
+// Test hook: TF32 energies E[b,q,n] = -8 S of the tcgen05 filter for the whole bank (single level, no
+// threshold; n_total <= 4096 so that every token fits the candidate list).  dbg_energy [B, Q, n_total] floats.
 extern "C" int cutie_debug_tc_energy(int num_segments, const void* const* seg_key, const void* const* seg_shrinkage,
                                      const int64_t* seg_len, const int64_t* seg_key_bstride,
                                      const int64_t* seg_shr_bstride, const float* qk, const float* qe, int64_t B,
                                      int64_t Q, int64_t n_total, float* dbg_energy, void* workspace,
                                      size_t workspace_bytes, void* stream) {
   CUTIE_REQUIRE(num_segments >= 1 && num_segments <= kMaxSeg && dbg_energy && workspace, "bad argument");
+  CUTIE_REQUIRE(n_total <= TC_CAP, "debug hook handles at most 4096 tokens");
   ScanParams sp;
   int rc = fill_scan_params(sp, num_segments, seg_key, seg_shrinkage, seg_len, seg_key_bstride, seg_shr_bstride, qk,
                             qe, Q, 1, 32, n_total);
   if (rc) return rc;
-  const int nsplit = tc_split_count(B, Q, n_total);
-  const size_t need = (size_t)B * nsplit * Q * TC_CAP * 4 + (size_t)B * nsplit * Q * 4 + (size_t)B * Q * 32 * 12 + 1024;
-  CUTIE_REQUIRE(workspace_bytes >= need, "workspace too small");
+  WsLayout wl;
+  memset(&wl, 0, sizeof(wl));
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+  wl.cand_idx = take((size_t)B * Q * TC_CAP * 4);
+  wl.cand_e = take((size_t)B * Q * TC_CAP * 4);
+  wl.count = take((size_t)B * Q * 4);
+  wl.dmax = take((size_t)B * Q * 4);
+  wl.emax0 = take((size_t)B * Q * 4);
+  wl.emax1 = take((size_t)B * Q * 4);
+  const size_t o_idx = take((size_t)B * Q * 32 * 4), o_w = take((size_t)B * Q * 32 * 4);
+  CUTIE_REQUIRE(workspace_bytes >= off, "workspace too small");
+  Plan pl;
+  pl.levels = 1;
+  pl.stride[0] = 1;
   char* ws = (char*)workspace;
-  int* cand = (int*)ws;
-  int* count = (int*)(ws + (size_t)B * nsplit * Q * TC_CAP * 4);
-  char* o = ws + (size_t)B * nsplit * Q * TC_CAP * 4 + (((size_t)B * nsplit * Q * 4 + 255) / 256) * 256;
-  const size_t set_bytes = (size_t)B * Q * 32 * 4;
-  return run_tc_level(sp, B, 1, nullptr, 0, cand, count, (int*)o, (float*)(o + set_bytes), (float*)(o + 2 * set_bytes),
-                      nullptr, dbg_energy, (cudaStream_t)stream);
+  return run_filtered(sp, B, pl, ws, wl, (int*)(ws + o_idx), (float*)(ws + o_w), nullptr, nullptr, dbg_energy,
+                      (cudaStream_t)stream);
 }
 
 extern "C" int cutie_topk_merge(const float* part_val, const int32_t* part_idx, int64_t B, int64_t nparts, int64_t Q,

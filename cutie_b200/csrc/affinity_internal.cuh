@@ -1,12 +1,12 @@
 // Internal (non-ABI) interfaces between affinity.cu (exact scan, orchestration) and affinity_tc.cu
-// (tcgen05 candidate filter, exact re-rank).
+// (tcgen05 candidate filter, level threshold hand-over, exact re-rank).
 #pragma once
 #include "common.cuh"
 
 namespace cutie {
 
 // A "sample" of the bank: virtual indices i in [0, samp_count) map to tokens g = samp_begin + i * samp_stride
-// of the concatenated segments.  stride 1 = the whole bank.
+// of the concatenated segments.  stride 1 = the whole bank.  Levels use nested samples (strides 256, 16, 1).
 
 struct TcFilterParams {
   KeySegments segs;
@@ -15,12 +15,22 @@ struct TcFilterParams {
   long long Q;
   long long samp_begin, samp_stride, samp_count;
   int tiles_per_split, nsplit;
-  const float* tau;        // per query: k-th best exact similarity of an earlier (nested) sample; may be null
-  long long tau_stride;    // tau[(b*Q + q) * tau_stride]
-  int* cand;               // [B][nsplit][Q][cap] token indices
-  int* count;              // [B][nsplit][Q]  (-1 = overflow)
+  const float* emax_in;    // [B][Q] upper bound of the k-th smallest exact energy of the previous level; null = +inf
+  int* cand_idx;           // [B][Q][cap] token indices (per-query list, filled with atomics)
+  float* cand_e;           // [B][Q][cap] their TF32 energies
+  int* count;              // [B][Q] number of candidates (may exceed cap = overflow); zeroed by the caller
+  float* dmax;             // [B][Q] largest error bound used (atomicMax on the bit pattern); zeroed by the caller
   int cap;
   float* dbg_energy;       // optional [B][Q][samp_count] tf32 energies (tests)
+};
+
+struct SelectParams {
+  long long Q;
+  const float* cand_e;
+  const int* count;
+  const float* dmax;
+  int cap, top_k;
+  float* emax_out;         // [B][Q]
 };
 
 struct RerankParams {
@@ -28,9 +38,7 @@ struct RerankParams {
   const float* qk;
   const float* qe;
   long long Q, n_total;
-  long long samp_begin, samp_stride, samp_count;
-  int tiles_per_split, nsplit;
-  const int* cand;
+  const int* cand_idx;
   const int* count;
   int cap, top_k, kpad;
   int* out_idx;
@@ -42,6 +50,7 @@ struct RerankParams {
 size_t tc_filter_smem_bytes();
 int tc_split_count(long long B, long long Q, long long samp_count);
 int launch_tc_filter(const TcFilterParams& p, long long B, cudaStream_t st);
+int launch_level_select(const SelectParams& p, long long B, int kpad, cudaStream_t st);
 int launch_rerank(const RerankParams& p, long long B, cudaStream_t st);
 
 }  // namespace cutie

@@ -10,11 +10,12 @@
 //   tile, double buffered) are K-major, 4 x [128 rows x 128 B] SWIZZLE_128B blocks + one [128 x 32 B]
 //   un-swizzled tail block; tcgen05.mma.kind::tf32 accumulates into TMEM (2 x 128 columns).
 //   Epilogue thread == query (TMEM lane): the threshold and the candidate list are thread-private, no atomics:
-//   a token is a candidate iff  E_tf32 < Emax_q + delta,  where Emax_q = -8 * (k-th best EXACT similarity over
-//   a subset scanned earlier) and delta = eps * (P_tile + R_tile * sqrt(b2_q))^2 bounds the TF32 rounding error
-//   (P_tile = max sqrt(shr |k|^2), R_tile = max sqrt(shr) over the tile).  A true top-k member therefore always
-//   survives.  Survivors are re-ranked by the exact fp32 direct form (affinity_rerank_kernel), so the final
-//   selection and weights are bit-identical to the exact scan's.
+//   a token is a candidate iff  E_tf32 < Emax_q + delta,  where Emax_q is an upper bound of the k-th smallest
+//   EXACT energy over a nested subset scanned by the previous level (k-th smallest TF32 energy there + the
+//   largest error bound used there) and delta = eps * (P_tile + R_tile * sqrt(b2_q))^2 bounds the TF32 rounding
+//   error (P_tile = max sqrt(shr |k|^2), R_tile = max sqrt(shr) over the tile).  A true top-k member therefore
+//   always survives every level.  Survivors of the last level are re-ranked by the exact fp32 direct form
+//   (affinity_rerank_kernel), so the final selection and weights are bit-identical to the exact scan's.
 //
 // Warp roles (288 threads): warps 0-3 epilogue (TMEM lane quarters), warps 4-7 producers (global fp32 rows ->
 // scaled/squared/tf32-rounded swizzled smem), warp 8 TMEM allocator + single-thread MMA issuer.
@@ -156,10 +157,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) affinity_tc_filter_kernel(const
     for (int i = 0; i < 8; ++i) *reinterpret_cast<float*>(A + off_tail(tid, i)) = tl[i];
     vq = sqrtf(b2);
     if (q < p.Q) {
-      // Emax = -8 * tau_q  (tau = k-th best exact similarity of an earlier subset; may be -inf => +inf)
-      const float tau = p.tau ? p.tau[((long long)b * p.Q + q) * p.tau_stride] : -CUDART_INF_F;
-      emax = -8.f * tau;
-      emax += fabsf(emax) * 1e-6f;      // the exact re-rank evaluates in fp32: keep boundary ties
+      // Emax: upper bound of the k-th smallest exact energy of the previous (nested) level; null => +inf
+      emax = p.emax_in ? p.emax_in[(long long)b * p.Q + q] : CUDART_INF_F;
     }
     fence_proxy_async();
   }
@@ -171,9 +170,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) affinity_tc_filter_kernel(const
   if (warp < 4) {
     // =========================== epilogue: thread == query ===========================
     const long long q = q0 + tid;
-    int cnt = 0;
-    bool ovf = false;
-    int* my = p.cand + (((long long)b * p.nsplit + split) * p.Q + (q < p.Q ? q : 0)) * p.cap;
+    const long long bq = (long long)b * p.Q + (q < p.Q ? q : 0);
+    int* my_idx = p.cand_idx + bq * p.cap;
+    float* my_e = p.cand_e + bq * p.cap;
+    float dmax = 0.f;
     for (int t = 0; t < ntiles; ++t) {
       const int a = t & 1;
       mbar_wait(smem_u32(&T.tfull[a]), (t >> 1) & 1);
@@ -182,7 +182,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) affinity_tc_filter_kernel(const
 #pragma unroll
       for (int w = 0; w < 4; ++w) { P = fmaxf(P, T.stats[t & 3][w][0]); R = fmaxf(R, T.stats[t & 3][w][1]); }
       const float s_ = P + R * vq;
-      const float thr = (q < p.Q) ? (emax + TF32_EPS * s_ * s_) : -CUDART_INF_F;
+      const float delta = TF32_EPS * s_ * s_;
+      dmax = fmaxf(dmax, delta);
+      const float thr = (q < p.Q) ? (emax + delta) : -CUDART_INF_F;
       const long long ibase = i_begin + (long long)t * KTILE;
 #pragma unroll 1
       for (int cg = 0; cg < 4; ++cg) {
@@ -206,11 +208,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) affinity_tc_filter_kernel(const
             if (i < p.samp_count) p.dbg_energy[((long long)b * p.Q + q) * p.samp_count + i] = e;
           }
           if (e < thr) {
-            if (cnt < p.cap) {
-              my[cnt] = (int)(p.samp_begin + (ibase + cg * 32 + j) * p.samp_stride);
-              ++cnt;
-            } else {
-              ovf = true;
+            const int pos = atomicAdd(&p.count[bq], 1);
+            if (pos < p.cap) {
+              my_idx[pos] = (int)(p.samp_begin + (ibase + cg * 32 + j) * p.samp_stride);
+              my_e[pos] = e;
             }
           }
         }
@@ -218,49 +219,68 @@ __global__ void __launch_bounds__(TC_THREADS, 1) affinity_tc_filter_kernel(const
       tc_fence_before();
       mbar_arrive(smem_u32(&T.tempty[a]));
     }
-    if (q < p.Q) p.count[((long long)b * p.nsplit + split) * p.Q + q] = ovf ? -1 : cnt;
+    if (q < p.Q && ntiles > 0) atomicMax(reinterpret_cast<unsigned int*>(&p.dmax[bq]), __float_as_uint(dmax));
   } else if (warp < 8) {
-    // =========================== producers: thread == token row ===========================
-    const int row = tid - 128;
+    // ============ producers: 16 lanes per token row (coalesced 256-B rows), next tile prefetched ============
+    const int pt = tid - 128;            // 0..127
+    const int c4 = pt & 15;              // which 16-B chunk of the row this lane owns
+    const int r0 = pt >> 4;              // rows r0 + 8*j, j = 0..15
     const int pw = warp - 4;
+    float4 kf[16];
+    float shr[16];
+    auto load_tile = [&](int t) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const long long i = i_begin + (long long)t * KTILE + r0 + 8 * j;
+        if (i < i_end) {
+          const long long g = p.samp_begin + i * p.samp_stride;
+          const int sg = seg_of(p.segs.begin, p.segs.nseg, g);
+          const long long off = g - p.segs.begin[sg];
+          kf[j] = __ldg(reinterpret_cast<const float4*>(p.segs.key[sg] + (long long)b * p.segs.key_bs[sg] + off * CKD) + c4);
+          shr[j] = __ldg(p.segs.shr[sg] + (long long)b * p.segs.shr_bs[sg] + off);
+        } else {
+          kf[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          shr[j] = -1.f;                 // marks an invalid row
+        }
+      }
+    };
+    if (ntiles > 0) load_tile(0);
     for (int t = 0; t < ntiles; ++t) {
       const int s = t & 1;
       mbar_wait(smem_u32(&T.empty[s]), ((t >> 1) & 1) ^ 1);
       unsigned char* Bs = Bst + s * OPER_BYTES;
-      const long long i = i_begin + (long long)t * KTILE + row;
-      const bool valid = i < i_end;
-      float shr = 0.f, n2 = 0.f;
-      float4 kf[16];
-      if (valid) {
-        const long long g = p.samp_begin + i * p.samp_stride;
-        const int sg = seg_of(p.segs.begin, p.segs.nseg, g);
-        const float4* src = reinterpret_cast<const float4*>(p.segs.key[sg] + (long long)b * p.segs.key_bs[sg] +
-                                                            (g - p.segs.begin[sg]) * CKD);
+      float Pm = 0.f, Rm = 0.f;
 #pragma unroll
-        for (int c4 = 0; c4 < 16; ++c4) kf[c4] = __ldg(src + c4);
-        shr = p.segs.shr[sg][(long long)b * p.segs.shr_bs[sg] + (g - p.segs.begin[sg])];
-      } else {
-#pragma unroll
-        for (int c4 = 0; c4 < 16; ++c4) kf[c4] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-#pragma unroll
-      for (int c4 = 0; c4 < 16; ++c4) {
-        const float4 v = kf[c4];
-        n2 += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-        float4 sq = make_float4(to_tf32(shr * v.x * v.x), to_tf32(shr * v.y * v.y), to_tf32(shr * v.z * v.z),
-                                to_tf32(shr * v.w * v.w));
-        float4 ln = make_float4(to_tf32(shr * v.x), to_tf32(shr * v.y), to_tf32(shr * v.z), to_tf32(shr * v.w));
+      for (int j = 0; j < 16; ++j) {
+        const int row = r0 + 8 * j;
+        const bool valid = shr[j] >= 0.f;
+        const float sh = valid ? shr[j] : 0.f;
+        const float4 v = kf[j];
+        float n2 = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        n2 += __shfl_xor_sync(0xffffffffu, n2, 1);
+        n2 += __shfl_xor_sync(0xffffffffu, n2, 2);
+        n2 += __shfl_xor_sync(0xffffffffu, n2, 4);
+        n2 += __shfl_xor_sync(0xffffffffu, n2, 8);
+        Pm = fmaxf(Pm, sh * n2);
+        Rm = fmaxf(Rm, sh);
+        const float4 sq = make_float4(to_tf32(sh * v.x * v.x), to_tf32(sh * v.y * v.y), to_tf32(sh * v.z * v.z),
+                                      to_tf32(sh * v.w * v.w));
+        const float4 ln = make_float4(to_tf32(sh * v.x), to_tf32(sh * v.y), to_tf32(sh * v.z), to_tf32(sh * v.w));
         *reinterpret_cast<float4*>(Bs + off_main(row, 4 * c4)) = sq;
         *reinterpret_cast<float4*>(Bs + off_main(row, 64 + 4 * c4)) = ln;
+        if (c4 == 0) {
+          const float st = to_tf32(sh);
+          // tail: [shr, BIG if invalid, shr, 0 | 0 0 0 0]
+          *reinterpret_cast<float4*>(Bs + off_tail(row, 0)) = make_float4(st, valid ? 0.f : BIG_E, st, 0.f);
+          *reinterpret_cast<float4*>(Bs + off_tail(row, 4)) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
-      const float shr_t = to_tf32(shr);
-      // tail: [shr, BIG if invalid, shr, 0, | 0 0 0 0]
-      *reinterpret_cast<float4*>(Bs + off_tail(row, 0)) = make_float4(shr_t, valid ? 0.f : BIG_E, shr_t, 0.f);
-      *reinterpret_cast<float4*>(Bs + off_tail(row, 4)) = make_float4(0.f, 0.f, 0.f, 0.f);
-      float Pm = warp_max(sqrtf(shr * n2)), Rm = warp_max(sqrtf(shr));
+      Pm = warp_max(sqrtf(Pm));
+      Rm = warp_max(sqrtf(Rm));
       if (lane == 0) { T.stats[t & 3][pw][0] = Pm; T.stats[t & 3][pw][1] = Rm; }
       fence_proxy_async();
       mbar_arrive(smem_u32(&T.full[s]));
+      if (t + 1 < ntiles) load_tile(t + 1);       // in flight while the MMA / epilogue of this tile run
     }
   } else {
     // =========================== MMA issuer ===========================
@@ -296,66 +316,108 @@ __global__ void __launch_bounds__(TC_THREADS, 1) affinity_tc_filter_kernel(const
 }
 
 // ------------------------------------------------------------------------------------------------
-// Exact re-rank: one warp per query.  Candidates of all splits -> exact fp32 similarity -> sorted top-k ->
-// softmax / usage.  A split whose candidate list overflowed is rescanned exhaustively (rare).
+// Threshold hand-over between filter levels: Emax_next[q] = (k-th smallest TF32 energy among this level's
+// candidates) + (largest error bound the level used for q).  One warp per query; no key reads.
 template <int NS>
-__global__ void __launch_bounds__(256) affinity_rerank_kernel(const RerankParams p) {
+__global__ void __launch_bounds__(256) affinity_level_select_kernel(const SelectParams p) {
   __shared__ float lv[8][KPAD_MAX];
   __shared__ int li[8][KPAD_MAX];
-  __shared__ float qa[8][CKD], qb[8][CKD];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int b = blockIdx.y;
-  const long long q = (long long)blockIdx.x * 8 + warp;
-  if (q >= p.Q) return;
+  const long long bq = (long long)blockIdx.y * p.Q + (long long)blockIdx.x * 8 + warp;
+  if ((long long)blockIdx.x * 8 + warp >= p.Q) return;
+  const int n = p.count[bq];
+  if (n > p.cap || n < p.top_k) {            // overflow (or impossible underflow): no usable bound
+    if (lane == 0) p.emax_out[bq] = CUDART_INF_F;
+    return;
+  }
   for (int u = 0; u < NS; ++u) { lv[warp][lane + 32 * u] = -CUDART_INF_F; li[warp][lane + 32 * u] = INT_MAX; }
-  for (int c = lane; c < CKD; c += 32) {
-    const long long off = ((long long)b * CKD + c) * p.Q + q;
-    const float a = sqrtf(p.qe[off]);
-    qa[warp][c] = a;
-    qb[warp][c] = a * p.qk[off];
-  }
   __syncwarp();
-  for (int s = 0; s < p.nsplit; ++s) {
-    const long long lb = ((long long)b * p.nsplit + s) * p.Q + q;
-    int n = p.count[lb];
-    const int* cl = p.cand + lb * p.cap;
-    long long i_begin = 0;
-    const bool exhaustive = n < 0;
-    if (exhaustive) {                        // overflow: walk the split's whole index range
-      i_begin = (long long)s * p.tiles_per_split * KTILE;
-      long long i_end = i_begin + (long long)p.tiles_per_split * KTILE;
-      if (i_end > p.samp_count) i_end = p.samp_count;
-      n = (int)(i_end > i_begin ? i_end - i_begin : 0);
-    }
-    for (int base = 0; base < n; base += 32) {
-      const int j = base + lane;
-      float sv = -CUDART_INF_F;
-      int id = INT_MAX;
-      if (j < n) {
-        id = exhaustive ? (int)(p.samp_begin + (i_begin + j) * p.samp_stride) : cl[j];
-        const int sg = seg_of(p.segs.begin, p.segs.nseg, id);
-        const float* krow = p.segs.key[sg] + (long long)b * p.segs.key_bs[sg] + ((long long)id - p.segs.begin[sg]) * CKD;
-        const float shr = p.segs.shr[sg][(long long)b * p.segs.shr_bs[sg] + ((long long)id - p.segs.begin[sg])];
-        sv = exact_similarity(krow, shr, qa[warp], qb[warp]);
-      }
-      const float kth = lv[warp][p.top_k - 1];
-      const int kthi = li[warp][p.top_k - 1];
-      unsigned bits = __ballot_sync(0xffffffffu, (j < n) && (sv > kth || (sv == kth && id < kthi)));
-      while (bits) {
-        const int src = __ffs(bits) - 1;
-        bits &= bits - 1;
-        const float cs = __shfl_sync(0xffffffffu, sv, src);
-        const int ci = __shfl_sync(0xffffffffu, id, src);
-        const float k2 = lv[warp][p.top_k - 1];
-        if (cs > k2 || (cs == k2 && ci < li[warp][p.top_k - 1]))
-          list_insert<NS>(&lv[warp][0], &li[warp][0], lane, p.top_k, cs, ci);
-      }
+  const float* ce = p.cand_e + bq * p.cap;
+  for (int base = 0; base < n; base += 32) {
+    const int j = base + lane;
+    const float v = j < n ? -ce[j] : -CUDART_INF_F;       // rank by -E, descending
+    const float kth = lv[warp][p.top_k - 1];
+    unsigned bits = __ballot_sync(0xffffffffu, j < n && v > kth);
+    while (bits) {
+      const int src = __ffs(bits) - 1;
+      bits &= bits - 1;
+      const float cv = __shfl_sync(0xffffffffu, v, src);
+      if (cv > lv[warp][p.top_k - 1]) list_insert<NS>(&lv[warp][0], &li[warp][0], lane, p.top_k, cv, base + src);
     }
   }
-  const long long oo = ((long long)b * p.Q + q) * p.kpad;
-  finalize_topk<NS>(&lv[warp][0], &li[warp][0], lane, p.top_k, p.kpad, p.out_idx + oo, p.out_w + oo,
-                    p.out_sim ? p.out_sim + oo : nullptr,
-                    p.usage_acc ? p.usage_acc + (long long)b * p.n_total : nullptr);
+  if (lane == 0) {
+    const float kth_e = -lv[warp][p.top_k - 1];
+    const float bound = kth_e + p.dmax[bq];
+    p.emax_out[bq] = bound + fabsf(bound) * 1e-6f + 1e-30f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Exact re-rank of the last level's candidates: one CTA (4 warps) per query.  Each warp evaluates chunks of 32
+// candidates with the exact fp32 direct form and keeps a sorted top-k; warp 0 merges and finalises (softmax,
+// usage).  A query whose candidate list overflowed is rescanned exhaustively (slow, correct, rare).
+template <int NS>
+__global__ void __launch_bounds__(128) affinity_rerank_kernel(const RerankParams p) {
+  __shared__ float lv[4][KPAD_MAX];
+  __shared__ int li[4][KPAD_MAX];
+  __shared__ float qa[CKD], qb[CKD];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.y;
+  const long long q = blockIdx.x;
+  const long long bq = (long long)b * p.Q + q;
+  for (int u = 0; u < NS; ++u) { lv[warp][lane + 32 * u] = -CUDART_INF_F; li[warp][lane + 32 * u] = INT_MAX; }
+  if (tid < CKD) {
+    const long long off = ((long long)b * CKD + tid) * p.Q + q;
+    const float a = sqrtf(p.qe[off]);
+    qa[tid] = a;
+    qb[tid] = a * p.qk[off];
+  }
+  __syncthreads();
+  int n = p.count[bq];
+  const bool exhaustive = n > p.cap;
+  if (exhaustive) n = (int)p.n_total;
+  const int* cl = p.cand_idx + bq * p.cap;
+  for (int base = warp * 32; base < n; base += 128) {
+    const int j = base + lane;
+    float sv = -CUDART_INF_F;
+    int id = INT_MAX;
+    if (j < n) {
+      id = exhaustive ? j : cl[j];
+      const int sg = seg_of(p.segs.begin, p.segs.nseg, id);
+      const float* krow = p.segs.key[sg] + (long long)b * p.segs.key_bs[sg] + ((long long)id - p.segs.begin[sg]) * CKD;
+      const float shr = p.segs.shr[sg][(long long)b * p.segs.shr_bs[sg] + ((long long)id - p.segs.begin[sg])];
+      sv = exact_similarity(krow, shr, qa, qb);
+    }
+    const float kth = lv[warp][p.top_k - 1];
+    const int kthi = li[warp][p.top_k - 1];
+    unsigned bits = __ballot_sync(0xffffffffu, (j < n) && (sv > kth || (sv == kth && id < kthi)));
+    while (bits) {
+      const int src = __ffs(bits) - 1;
+      bits &= bits - 1;
+      const float cs = __shfl_sync(0xffffffffu, sv, src);
+      const int ci = __shfl_sync(0xffffffffu, id, src);
+      const float k2 = lv[warp][p.top_k - 1];
+      if (cs > k2 || (cs == k2 && ci < li[warp][p.top_k - 1]))
+        list_insert<NS>(&lv[warp][0], &li[warp][0], lane, p.top_k, cs, ci);
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    for (int w = 1; w < 4; ++w) {
+      for (int j = 0; j < p.top_k; ++j) {
+        const float cs = lv[w][j];
+        const int ci = li[w][j];
+        if (ci == INT_MAX) break;
+        const float k2 = lv[0][p.top_k - 1];
+        if (!(cs > k2 || (cs == k2 && ci < li[0][p.top_k - 1]))) break;     // sorted: the rest lose too
+        list_insert<NS>(&lv[0][0], &li[0][0], lane, p.top_k, cs, ci);
+      }
+    }
+    const long long oo = bq * p.kpad;
+    finalize_topk<NS>(&lv[0][0], &li[0][0], lane, p.top_k, p.kpad, p.out_idx + oo, p.out_w + oo,
+                      p.out_sim ? p.out_sim + oo : nullptr,
+                      p.usage_acc ? p.usage_acc + (long long)b * p.n_total : nullptr);
+  }
 }
 
 size_t tc_filter_smem_bytes() { return (size_t)3 * OPER_BYTES + sizeof(TcSmemTail) + 64; }
@@ -374,12 +436,23 @@ int launch_tc_filter(const TcFilterParams& p, long long B, cudaStream_t st) {
   return 0;
 }
 
-int launch_rerank(const RerankParams& p, long long B, cudaStream_t st) {
+int launch_level_select(const SelectParams& p, long long B, int kpad, cudaStream_t st) {
   dim3 grid((unsigned)((p.Q + 7) / 8), (unsigned)B);
-  if (p.kpad == 32)
-    affinity_rerank_kernel<1><<<grid, 256, 0, st>>>(p);
+  if (kpad == 32)
+    affinity_level_select_kernel<1><<<grid, 256, 0, st>>>(p);
   else
-    affinity_rerank_kernel<2><<<grid, 256, 0, st>>>(p);
+    affinity_level_select_kernel<2><<<grid, 256, 0, st>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_cuda_error("affinity_level_select_kernel", e);
+  return 0;
+}
+
+int launch_rerank(const RerankParams& p, long long B, cudaStream_t st) {
+  dim3 grid((unsigned)p.Q, (unsigned)B);
+  if (p.kpad == 32)
+    affinity_rerank_kernel<1><<<grid, 128, 0, st>>>(p);
+  else
+    affinity_rerank_kernel<2><<<grid, 128, 0, st>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error("affinity_rerank_kernel", e);
   return 0;

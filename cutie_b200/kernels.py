@@ -149,7 +149,8 @@ def affinity_topk(segments: Sequence[BankSegment], qk: torch.Tensor, qe: torch.T
     assert qk.is_contiguous() and qe.is_contiguous()
     PA, IA = ctypes.c_void_p * ns, ctypes.c_int64 * ns
     _L = lib()
-    with _call('affinity_topk', 2 * _L.cutie_affinity_plan_levels(_i64(n_total), ctypes.c_int(top_k))):
+    _lv = _L.cutie_affinity_plan_levels(_i64(n_total), ctypes.c_int(top_k))
+    with _call('affinity_topk', 2 * _lv if _lv else 2):
         st = L.cutie_affinity_topk(
             ctypes.c_int(ns), PA(*[s.key.data_ptr() for s in segments]),
             PA(*[s.shrinkage.data_ptr() for s in segments]), IA(*[s.n for s in segments]),
@@ -167,6 +168,7 @@ def set_tc_min_tokens(n: int):
 
 
 def affinity_plan_levels(n_total: int, top_k: int) -> int:
+    """0 = exact fp32 scan only; n >= 1 = n nested tcgen05 filter levels + exact re-rank of the survivors."""
     return int(lib().cutie_affinity_plan_levels(_i64(n_total), ctypes.c_int(top_k)))
 
 
@@ -177,7 +179,7 @@ def debug_tc_energy(segments: Sequence[BankSegment], qk: torch.Tensor, qe: torch
     out = torch.zeros(B, Q, n_total, dtype=torch.float32, device=qk.device)
     ns = len(segments)
     PA, IA = ctypes.c_void_p * ns, ctypes.c_int64 * ns
-    ws_bytes = 148 * 512 * 4 * B * Q + 4 * 148 * B * Q + B * Q * 32 * 12 + (1 << 20)
+    ws_bytes = B * Q * (4096 * 8 + 16 + 32 * 8) + (1 << 20)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=qk.device)
     with _call('debug_tc_energy', 2):
         st = lib().cutie_debug_tc_energy(

@@ -56,10 +56,11 @@ int cutie_affinity_topk(int num_segments, const void* const* seg_key, const void
                         int32_t* out_idx, float* out_w, float* out_sim, unsigned long long* usage_acc,
                         int64_t n_total, void* workspace, size_t workspace_bytes, void* stream);
 
-/* Execution plan of cutie_affinity_topk for a bank of n_total tokens: 1 = exact fp32 scan only; 2 / 3 = exact
- * scan of a strided sample, then tcgen05 (TF32) candidate filter(s) + exact fp32 re-rank.  All plans return the
- * same selection and weights (the filter only discards tokens that provably cannot be in the top-k).
- * cutie_set_tc_min_tokens: banks smaller than n use plan 1 (default 8192; negative restores the default). */
+/* Execution plan of cutie_affinity_topk for a bank of n_total tokens: 0 = exact fp32 scan only; n >= 1 = n nested
+ * tcgen05 (TF32) candidate-filter levels over strided samples (strides ..., 256, 16, 1) followed by an exact fp32
+ * re-rank of the survivors.  All plans return the same selection and weights (a filter level only discards
+ * tokens that provably cannot be in the top-k).
+ * cutie_set_tc_min_tokens: banks smaller than n use plan 0 (default 8192; negative restores the default). */
 int cutie_affinity_plan_levels(int64_t n_total, int top_k);
 void cutie_set_tc_min_tokens(int64_t n);
 /* Test hook: raw TF32 energies E[b,q,n] = -8*S[n,q] computed by the tcgen05 filter over the whole bank
