@@ -30,7 +30,7 @@ constexpr int BLK_BYTES = 128 * 128;    // one SW128 K-block: 128 rows x 128 B
 constexpr int TAIL_BYTES = 128 * 32;    // tail block: 128 rows x 8 tf32
 constexpr int OPER_BYTES = 4 * BLK_BYTES + TAIL_BYTES;   // 69632
 constexpr int TC_THREADS = 288;
-constexpr float TF32_EPS = 1.953125e-3f;   // 2^-9: products of two RN-rounded tf32 operands + fp32 accumulation
+constexpr float TF32_EPS = 1.15e-3f;   // > (1+2^-11)^2-1 + fp32 accumulation over 136 terms + tf32 rounding of the bound's own operands
 constexpr float BIG_E = 1e30f;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -105,7 +105,8 @@ __device__ __forceinline__ int off_tail(int row, int elem) {     // elem in [0,8
 
 struct TcSmemTail {
   unsigned long long full[2], empty[2], tfull[2], tempty[2];
-  float stats[4][4][2];     // [tile % 4][producer warp][P, R]
+  float rowP[4][KTILE];     // [tile % 4][row] sqrt(shr)*|k|
+  float rowR[4][KTILE];     // [tile % 4][row] sqrt(shr)
   uint32_t tmem_base;
 };
 
@@ -152,7 +153,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) affinity_tc_filter_kernel(const
       *reinterpret_cast<float*>(A + off_main(tid, 64 + c)) = to_tf32(-2.f * e * k);
     }
     const float b2_hi = to_tf32(b2), b2_lo = to_tf32(b2 - b2_hi);
-    float tl[8] = {b2_hi, 1.f, b2_lo, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const float vq_ = sqrtf(b2);
+    float tl[8] = {b2_hi, 1.f, b2_lo, 1.f, to_tf32(vq_ * 1.0005f), to_tf32(vq_ * vq_ * 1.001f), 0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < 8; ++i) *reinterpret_cast<float*>(A + off_tail(tid, i)) = tl[i];
     vq = sqrtf(b2);
@@ -173,18 +175,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) affinity_tc_filter_kernel(const
     const long long bq = (long long)b * p.Q + (q < p.Q ? q : 0);
     int* my_idx = p.cand_idx + bq * p.cap;
     float* my_e = p.cand_e + bq * p.cap;
-    float dmax = 0.f;
+    const bool all_pass = (p.emax_in == nullptr);       // coarsest level: every token of the sample is kept
+    if (all_pass && split == 0 && q < p.Q) p.count[bq] = (int)p.samp_count;
     for (int t = 0; t < ntiles; ++t) {
       const int a = t & 1;
       mbar_wait(smem_u32(&T.tfull[a]), (t >> 1) & 1);
       tc_fence_after();
-      float P = 0.f, R = 0.f;
-#pragma unroll
-      for (int w = 0; w < 4; ++w) { P = fmaxf(P, T.stats[t & 3][w][0]); R = fmaxf(R, T.stats[t & 3][w][1]); }
-      const float s_ = P + R * vq;
-      const float delta = TF32_EPS * s_ * s_;
-      dmax = fmaxf(dmax, delta);
-      const float thr = (q < p.Q) ? (emax + delta) : -CUDART_INF_F;
+      const float thr = (q < p.Q) ? emax : -CUDART_INF_F;
       const long long ibase = i_begin + (long long)t * KTILE;
 #pragma unroll 1
       for (int cg = 0; cg < 4; ++cg) {
@@ -202,16 +199,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) affinity_tc_filter_kernel(const
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const float e = __uint_as_float(r[j]);
-          if (p.dbg_energy && q < p.Q) {
-            const long long i = ibase + cg * 32 + j;
-            if (i < p.samp_count) p.dbg_energy[((long long)b * p.Q + q) * p.samp_count + i] = e;
-          }
-          if (e < thr) {
-            const int pos = atomicAdd(&p.count[bq], 1);
+          const float d = __uint_as_float(r[j]);        // E_tf32 - eps (P_n + R_n v_q)^2 : a LOWER bound of E_exact
+          const int col = cg * 32 + j;
+          if (p.dbg_energy && q < p.Q && ibase + col < p.samp_count)
+            p.dbg_energy[((long long)b * p.Q + q) * p.samp_count + ibase + col] = d;
+          if (d < thr && ibase + col < i_end) {
+            const float s_ = T.rowP[t & 3][col] + T.rowR[t & 3][col] * vq;
+            const float e_hi = d + 2.01f * TF32_EPS * s_ * s_;       // an UPPER bound of E_exact
+            int pos;
+            if (all_pass) pos = (int)(ibase + col); else pos = atomicAdd(&p.count[bq], 1);
             if (pos < p.cap) {
-              my_idx[pos] = (int)(p.samp_begin + (ibase + cg * 32 + j) * p.samp_stride);
-              my_e[pos] = e;
+              my_idx[pos] = (int)(p.samp_begin + (ibase + col) * p.samp_stride);
+              my_e[pos] = e_hi;
             }
           }
         }
@@ -219,7 +218,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) affinity_tc_filter_kernel(const
       tc_fence_before();
       mbar_arrive(smem_u32(&T.tempty[a]));
     }
-    if (q < p.Q && ntiles > 0) atomicMax(reinterpret_cast<unsigned int*>(&p.dmax[bq]), __float_as_uint(dmax));
   } else if (warp < 8) {
     // ============ producers: 16 lanes per token row (coalesced 256-B rows), next tile prefetched ============
     const int pt = tid - 128;            // 0..127
@@ -249,7 +247,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) affinity_tc_filter_kernel(const
       const int s = t & 1;
       mbar_wait(smem_u32(&T.empty[s]), ((t >> 1) & 1) ^ 1);
       unsigned char* Bs = Bst + s * OPER_BYTES;
-      float Pm = 0.f, Rm = 0.f;
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const int row = r0 + 8 * j;
@@ -261,8 +258,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) affinity_tc_filter_kernel(const
         n2 += __shfl_xor_sync(0xffffffffu, n2, 2);
         n2 += __shfl_xor_sync(0xffffffffu, n2, 4);
         n2 += __shfl_xor_sync(0xffffffffu, n2, 8);
-        Pm = fmaxf(Pm, sh * n2);
-        Rm = fmaxf(Rm, sh);
         const float4 sq = make_float4(to_tf32(sh * v.x * v.x), to_tf32(sh * v.y * v.y), to_tf32(sh * v.z * v.z),
                                       to_tf32(sh * v.w * v.w));
         const float4 ln = make_float4(to_tf32(sh * v.x), to_tf32(sh * v.y), to_tf32(sh * v.z), to_tf32(sh * v.w));
@@ -270,14 +265,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) affinity_tc_filter_kernel(const
         *reinterpret_cast<float4*>(Bs + off_main(row, 64 + 4 * c4)) = ln;
         if (c4 == 0) {
           const float st = to_tf32(sh);
-          // tail: [shr, BIG if invalid, shr, 0 | 0 0 0 0]
-          *reinterpret_cast<float4*>(Bs + off_tail(row, 0)) = make_float4(st, valid ? 0.f : BIG_E, st, 0.f);
-          *reinterpret_cast<float4*>(Bs + off_tail(row, 4)) = make_float4(0.f, 0.f, 0.f, 0.f);
+          const float Pn = sqrtf(sh * n2) * 1.0005f, Rn = sqrtf(sh) * 1.0005f;   // rounded up a hair
+          T.rowP[t & 3][row] = Pn;
+          T.rowR[t & 3][row] = Rn;
+          // tail: [shr, BIG if invalid, shr, -eps P^2 | -2 eps P R, -eps R^2, 0, 0]   x   [b2_hi, 1, b2_lo, 1 | v, v^2, 0, 0]
+          *reinterpret_cast<float4*>(Bs + off_tail(row, 0)) =
+              make_float4(st, valid ? 0.f : BIG_E, st, to_tf32(-TF32_EPS * Pn * Pn));
+          *reinterpret_cast<float4*>(Bs + off_tail(row, 4)) =
+              make_float4(to_tf32(-2.f * TF32_EPS * Pn * Rn), to_tf32(-TF32_EPS * Rn * Rn), 0.f, 0.f);
         }
       }
-      Pm = warp_max(sqrtf(Pm));
-      Rm = warp_max(sqrtf(Rm));
-      if (lane == 0) { T.stats[t & 3][pw][0] = Pm; T.stats[t & 3][pw][1] = Rm; }
       fence_proxy_async();
       mbar_arrive(smem_u32(&T.full[s]));
       if (t + 1 < ntiles) load_tile(t + 1);       // in flight while the MMA / epilogue of this tile run
@@ -347,7 +344,7 @@ __global__ void __launch_bounds__(256) affinity_level_select_kernel(const Select
   }
   if (lane == 0) {
     const float kth_e = -lv[warp][p.top_k - 1];
-    const float bound = kth_e + p.dmax[bq];
+    const float bound = kth_e;                 // candidates carry upper bounds of their exact energies
     p.emax_out[bq] = bound + fabsf(bound) * 1e-6f + 1e-30f;
   }
 }

@@ -24,16 +24,18 @@ def test_tf32_energy_matches_exact_within_bound(K_, B, N, Q, cuts, scale):
     qk = torch.randn(B, 64, Q, generator=g) * scale
     qe = torch.sigmoid(torch.randn(B, 64, Q, generator=g))
     segs = segments_of(K_, key, shr, vals, cuts)
-    e = K_.debug_tc_energy(segs, qk.cuda(), qe.cuda()).cpu().double()                 # [B,Q,N]
+    d = K_.debug_tc_energy(segs, qk.cuda(), qe.cuda()).cpu().double()                 # [B,Q,N]
     truth = -8.0 * mm.similarity_direct(key.transpose(1, 2), shr.unsqueeze(1), qk, qe).transpose(1, 2)   # [B,Q,N]
-    # rigorous bound used by the kernel: eps * shr_n * (|k_n| + sqrt(b2_q))^2
+    # The MMA output folds the rigorous per-(token, query) error bound in:  d = E_tf32 - eps*shr_n*(|k_n| + sqrt(b2_q))^2
+    # so it must be a LOWER bound of the exact energy, and never further than 2*eps*(...) below it.
     knorm = key.double().norm(dim=2)                                                   # [B,N]
     vq = (qe.double() * qk.double() ** 2).sum(1).sqrt()                                # [B,Q]
-    bound = 2.0 ** -9 * shr.double()[:, None, :] * (knorm[:, None, :] + vq[:, :, None]) ** 2
-    err = (e - truth).abs()
-    assert (err <= bound).all(), f'max err/bound = {float((err / bound).max()):.3f}'
-    # and in practice far below it (random signs): median relative error of a 136-term TF32 dot product
-    assert float((err / truth.abs().clamp_min(1e-6)).median()) < 2e-4
+    s2 = shr.double()[:, None, :] * (knorm[:, None, :] + vq[:, :, None]) ** 2
+    assert (d <= truth + 1e-9).all(), f'filter value above the exact energy by {float((d - truth).max()):.3e}'
+    assert (truth - d <= 2.0 * 1.16e-3 * s2).all(), f'max slack ratio {float(((truth - d) / (1.15e-3 * s2)).max()):.3f}'
+    # the TF32 contraction itself (bound removed) is far more accurate than its worst case
+    e_tf32 = d + 1.15e-3 * s2
+    assert float(((e_tf32 - truth).abs() / truth.abs().clamp_min(1e-6)).median()) < 5e-4
 
 
 @pytest.mark.parametrize('B,N,Q,K,top_k,cuts', [
