@@ -17,8 +17,9 @@
 //   always survives every level.  Survivors of the last level are re-ranked by the exact fp32 direct form
 //   (affinity_rerank_kernel), so the final selection and weights are bit-identical to the exact scan's.
 //
-// Warp roles (288 threads): warps 0-3 epilogue (TMEM lane quarters), warps 4-7 producers (global fp32 rows ->
-// scaled/squared/tf32-rounded swizzled smem), warp 8 TMEM allocator + single-thread MMA issuer.
+// Warp roles (416 threads): warps 0-3 epilogue (TMEM lane quarters); warps 4-7 / 8-11 two producer groups that
+// alternate tiles (global fp32 rows -> scaled/squared/tf32-rounded swizzled smem; a group's next tile is in
+// flight while the other group converts); warp 12 TMEM allocator + single-thread MMA issuer.
 #include "topk_common.cuh"
 #include "affinity_internal.cuh"
 
@@ -29,7 +30,7 @@ constexpr int KTILE = 128;              // memory tokens per tile (MMA N)
 constexpr int BLK_BYTES = 128 * 128;    // one SW128 K-block: 128 rows x 128 B
 constexpr int TAIL_BYTES = 128 * 32;    // tail block: 128 rows x 8 tf32
 constexpr int OPER_BYTES = 4 * BLK_BYTES + TAIL_BYTES;   // 69632
-constexpr int TC_THREADS = 288;
+constexpr int TC_THREADS = 416;   // 4 epilogue + 2 x 4 producer + 1 MMA warps
 constexpr float TF32_EPS = 1.15e-3f;   // > (1+2^-11)^2-1 + fp32 accumulation over 136 terms + tf32 rounding of the bound's own operands
 constexpr float BIG_E = 1e30f;
 
@@ -46,10 +47,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!ok) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(200000u)      // suspend-time hint (ns): sleep in hardware, do not spin
         : "memory");
   }
 }
@@ -67,6 +68,11 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uin
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+__device__ __forceinline__ float fsqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 }
 __device__ __forceinline__ float to_tf32(float x) {
   uint32_t r;
@@ -110,6 +116,7 @@ struct TcSmemTail {
   uint32_t tmem_base;
 };
 
+template <bool DBG>
 __global__ void __launch_bounds__(TC_THREADS, 1) affinity_tc_filter_kernel(const TcFilterParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* A = smem;                              // queries
@@ -132,7 +139,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) affinity_tc_filter_kernel(const
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {
+  if (warp == 12) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&T.tmem_base)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -183,6 +190,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) affinity_tc_filter_kernel(const
       tc_fence_after();
       const float thr = (q < p.Q) ? emax : -CUDART_INF_F;
       const long long ibase = i_begin + (long long)t * KTILE;
+      const int nvalid = (int)((i_end - ibase) < KTILE ? (i_end - ibase) : KTILE);
 #pragma unroll 1
       for (int cg = 0; cg < 4; ++cg) {
         uint32_t r[32];
@@ -197,15 +205,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) affinity_tc_filter_kernel(const
               "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        // r[j] = E_tf32 - eps (P_n + R_n v_q)^2 : a LOWER bound of the exact energy (invalid rows hold ~1e30)
+        if (DBG) {
+          if (q < p.Q)
+            for (int j = 0; j < 32; ++j)
+              if (ibase + cg * 32 + j < p.samp_count)
+                p.dbg_energy[((long long)b * p.Q + q) * p.samp_count + ibase + cg * 32 + j] = __uint_as_float(r[j]);
+        }
+        // branch-free per-lane bitmask of passing columns (2 instructions per element) ...
+        unsigned mask = 0u;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float d = __uint_as_float(r[j]);        // E_tf32 - eps (P_n + R_n v_q)^2 : a LOWER bound of E_exact
-          const int col = cg * 32 + j;
-          if (p.dbg_energy && q < p.Q && ibase + col < p.samp_count)
-            p.dbg_energy[((long long)b * p.Q + q) * p.samp_count + ibase + col] = d;
-          if (d < thr && ibase + col < i_end) {
+        for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(r[j]) < thr) ? (1u << j) : 0u;
+        const int left = nvalid - cg * 32;                       // columns of this group that hold real tokens
+        mask &= left >= 32 ? 0xffffffffu : (left <= 0 ? 0u : ((1u << left) - 1u));
+        // ... and a rare warp-uniform slow path that re-reads just the passing columns from TMEM
+        unsigned wm = __reduce_or_sync(0xffffffffu, mask);
+        while (wm) {
+          const int j = __ffs(wm) - 1;
+          wm &= wm - 1;
+          uint32_t dv;
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(dv) : "r"(taddr + (uint32_t)j));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if ((mask >> j) & 1u) {
+            const float d = __uint_as_float(dv);
+            const int col = cg * 32 + j;
             const float s_ = T.rowP[t & 3][col] + T.rowR[t & 3][col] * vq;
-            const float e_hi = d + 2.01f * TF32_EPS * s_ * s_;       // an UPPER bound of E_exact
+            const float e_hi = d + 2.01f * TF32_EPS * s_ * s_;          // an UPPER bound of the exact energy
             int pos;
             if (all_pass) pos = (int)(ibase + col); else pos = atomicAdd(&p.count[bq], 1);
             if (pos < p.cap) {
@@ -218,32 +243,50 @@ __global__ void __launch_bounds__(TC_THREADS, 1) affinity_tc_filter_kernel(const
       tc_fence_before();
       mbar_arrive(smem_u32(&T.tempty[a]));
     }
-  } else if (warp < 8) {
+  } else if (warp < 12) {
     // ============ producers: 16 lanes per token row (coalesced 256-B rows), next tile prefetched ============
-    const int pt = tid - 128;            // 0..127
+    const int grp = (warp - 4) >> 2;     // producer group 0 handles even tiles (stage 0), group 1 odd tiles
+    const int pt = (tid - 128) & 127;    // 0..127 within the group
     const int c4 = pt & 15;              // which 16-B chunk of the row this lane owns
     const int r0 = pt >> 4;              // rows r0 + 8*j, j = 0..15
-    const int pw = warp - 4;
     float4 kf[16];
     float shr[16];
     auto load_tile = [&](int t) {
+      const long long i0 = i_begin + (long long)t * KTILE;
+      const long long g_first = p.samp_begin + i0 * p.samp_stride;
+      const long long i_last = (i0 + KTILE <= i_end ? i0 + KTILE : i_end) - 1;
+      const long long g_last = p.samp_begin + i_last * p.samp_stride;
+      const int sg = seg_of(p.segs.begin, p.segs.nseg, g_first);
+      if (i0 + KTILE <= i_end && sg == seg_of(p.segs.begin, p.segs.nseg, g_last)) {
+        // whole tile inside one segment: one base pointer, constant row step
+        const long long off0 = g_first - p.segs.begin[sg] + (long long)r0 * p.samp_stride;
+        const float4* kp = reinterpret_cast<const float4*>(p.segs.key[sg] + (long long)b * p.segs.key_bs[sg] + off0 * CKD) + c4;
+        const float* sp = p.segs.shr[sg] + (long long)b * p.segs.shr_bs[sg] + off0;
+        const long long kstep = 8 * p.samp_stride * (CKD / 4), sstep = 8 * p.samp_stride;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const long long i = i_begin + (long long)t * KTILE + r0 + 8 * j;
-        if (i < i_end) {
-          const long long g = p.samp_begin + i * p.samp_stride;
-          const int sg = seg_of(p.segs.begin, p.segs.nseg, g);
-          const long long off = g - p.segs.begin[sg];
-          kf[j] = __ldg(reinterpret_cast<const float4*>(p.segs.key[sg] + (long long)b * p.segs.key_bs[sg] + off * CKD) + c4);
-          shr[j] = __ldg(p.segs.shr[sg] + (long long)b * p.segs.shr_bs[sg] + off);
-        } else {
-          kf[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          shr[j] = -1.f;                 // marks an invalid row
+        for (int j = 0; j < 16; ++j) {
+          kf[j] = __ldg(kp + j * kstep);
+          shr[j] = __ldg(sp + j * sstep);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const long long i = i0 + r0 + 8 * j;
+          if (i < i_end) {
+            const long long g = p.samp_begin + i * p.samp_stride;
+            const int s2 = seg_of(p.segs.begin, p.segs.nseg, g);
+            const long long off = g - p.segs.begin[s2];
+            kf[j] = __ldg(reinterpret_cast<const float4*>(p.segs.key[s2] + (long long)b * p.segs.key_bs[s2] + off * CKD) + c4);
+            shr[j] = __ldg(p.segs.shr[s2] + (long long)b * p.segs.shr_bs[s2] + off);
+          } else {
+            kf[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            shr[j] = -1.f;                 // marks an invalid row
+          }
         }
       }
     };
-    if (ntiles > 0) load_tile(0);
-    for (int t = 0; t < ntiles; ++t) {
+    if (grp < ntiles) load_tile(grp);
+    for (int t = grp; t < ntiles; t += 2) {
       const int s = t & 1;
       mbar_wait(smem_u32(&T.empty[s]), ((t >> 1) & 1) ^ 1);
       unsigned char* Bs = Bst + s * OPER_BYTES;
@@ -253,31 +296,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) affinity_tc_filter_kernel(const
         const bool valid = shr[j] >= 0.f;
         const float sh = valid ? shr[j] : 0.f;
         const float4 v = kf[j];
-        float n2 = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        const float4 ln = make_float4(sh * v.x, sh * v.y, sh * v.z, sh * v.w);
+        float n2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
         n2 += __shfl_xor_sync(0xffffffffu, n2, 1);
         n2 += __shfl_xor_sync(0xffffffffu, n2, 2);
         n2 += __shfl_xor_sync(0xffffffffu, n2, 4);
         n2 += __shfl_xor_sync(0xffffffffu, n2, 8);
-        const float4 sq = make_float4(to_tf32(sh * v.x * v.x), to_tf32(sh * v.y * v.y), to_tf32(sh * v.z * v.z),
-                                      to_tf32(sh * v.w * v.w));
-        const float4 ln = make_float4(to_tf32(sh * v.x), to_tf32(sh * v.y), to_tf32(sh * v.z), to_tf32(sh * v.w));
-        *reinterpret_cast<float4*>(Bs + off_main(row, 4 * c4)) = sq;
-        *reinterpret_cast<float4*>(Bs + off_main(row, 64 + 4 * c4)) = ln;
+        *reinterpret_cast<float4*>(Bs + off_main(row, 4 * c4)) =
+            make_float4(to_tf32(ln.x * v.x), to_tf32(ln.y * v.y), to_tf32(ln.z * v.z), to_tf32(ln.w * v.w));
+        *reinterpret_cast<float4*>(Bs + off_main(row, 64 + 4 * c4)) =
+            make_float4(to_tf32(ln.x), to_tf32(ln.y), to_tf32(ln.z), to_tf32(ln.w));
+        // per-row error-bound factors (rounded up a hair) and the tail block; all 16 lanes of the row hold the
+        // same values, lane c4 == 0 stores them (small predicated body, no divergence region)
+        const float Pn = fsqrt_approx(sh * n2) * 1.002f, Rn = fsqrt_approx(sh) * 1.002f;
+        const float st = to_tf32(sh);
+        const float4 t0 = make_float4(st, valid ? 0.f : BIG_E, st, to_tf32(-TF32_EPS * Pn * Pn));
+        const float4 t1 = make_float4(to_tf32(-2.f * TF32_EPS * Pn * Rn), to_tf32(-TF32_EPS * Rn * Rn), 0.f, 0.f);
         if (c4 == 0) {
-          const float st = to_tf32(sh);
-          const float Pn = sqrtf(sh * n2) * 1.0005f, Rn = sqrtf(sh) * 1.0005f;   // rounded up a hair
           T.rowP[t & 3][row] = Pn;
           T.rowR[t & 3][row] = Rn;
           // tail: [shr, BIG if invalid, shr, -eps P^2 | -2 eps P R, -eps R^2, 0, 0]   x   [b2_hi, 1, b2_lo, 1 | v, v^2, 0, 0]
-          *reinterpret_cast<float4*>(Bs + off_tail(row, 0)) =
-              make_float4(st, valid ? 0.f : BIG_E, st, to_tf32(-TF32_EPS * Pn * Pn));
-          *reinterpret_cast<float4*>(Bs + off_tail(row, 4)) =
-              make_float4(to_tf32(-2.f * TF32_EPS * Pn * Rn), to_tf32(-TF32_EPS * Rn * Rn), 0.f, 0.f);
+          *reinterpret_cast<float4*>(Bs + off_tail(row, 0)) = t0;
+          *reinterpret_cast<float4*>(Bs + off_tail(row, 4)) = t1;
         }
       }
       fence_proxy_async();
       mbar_arrive(smem_u32(&T.full[s]));
-      if (t + 1 < ntiles) load_tile(t + 1);       // in flight while the MMA / epilogue of this tile run
+      if (t + 2 < ntiles) load_tile(t + 2);       // in flight while the other group converts the next tile
     }
   } else {
     // =========================== MMA issuer ===========================
@@ -306,7 +351,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) affinity_tc_filter_kernel(const
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 12) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem));
   }
@@ -423,11 +468,15 @@ int launch_tc_filter(const TcFilterParams& p, long long B, cudaStream_t st) {
   static bool attr_done = false;
   const size_t smem = tc_filter_smem_bytes();
   if (!attr_done) {
-    cudaFuncSetAttribute(affinity_tc_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(affinity_tc_filter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(affinity_tc_filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_done = true;
   }
   dim3 grid((unsigned)((p.Q + QT - 1) / QT), (unsigned)p.nsplit, (unsigned)B);
-  affinity_tc_filter_kernel<<<grid, TC_THREADS, smem, st>>>(p);
+  if (p.dbg_energy)
+    affinity_tc_filter_kernel<true><<<grid, TC_THREADS, smem, st>>>(p);
+  else
+    affinity_tc_filter_kernel<false><<<grid, TC_THREADS, smem, st>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error("affinity_tc_filter_kernel", e);
   return 0;
