@@ -141,7 +141,8 @@ def test_teacher_forced_vs_cpu_oracle(over, H, W, K, T):
         assert torch.allclose(m.work_mem.value[objs[-1]].cpu(), oracle.work.v[objs[-1]], rtol=1e-3, atol=2e-3)
         if cfg.use_long_term:
             assert m.long_mem.size(0) == oracle.long.size(0)
-            assert torch.allclose(m.work_mem.use_cnt[0].cpu(), oracle.work.use[0], atol=1e-4)
+            if 0 in oracle.work.use:            # no temporary tokens (hence no counters) before the second memory frame
+                assert torch.allclose(m.work_mem.use_cnt[0].cpu(), oracle.work.use[0], atol=1e-4)
             if m.long_mem.size(0):       # prototype order may differ where two usages tie to 1e-7
                 assert torch.allclose(m.long_mem.shrinkage[0].cpu().sort(-1)[0], oracle.long.s[0].sort(-1)[0],
                                       rtol=1e-3, atol=1e-3)
