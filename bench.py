@@ -34,6 +34,16 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# Exactly ONE line may reach stdout (the JSON).  Libraries (NCCL prints its version banner) write to fd 1
+# directly, so fd 1 is pointed at stderr for the whole run and the JSON goes to a saved copy of the real stdout.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    os.write(_REAL_STDOUT, (json.dumps(line) + '\n').encode())
+
+
 WORKLOADS = {
     # name: (H, W, objects, memory frames, top_k)
     'cfg2': dict(H=480, W=854, K=3, mem_frames=256, top_k=30,
@@ -250,7 +260,7 @@ def main():
                                            f'{args.steps} requested)'},
                 'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
                 'gpu_launches': 0}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return
 
     if not torch.cuda.is_available():
@@ -289,14 +299,16 @@ def main():
     if scan_ms:
         if tensor_bound:
             ach = flops / (scan_ms * 1e-3) / 1e12
-            roof = {'bound': 'tensor', 'kernel': 'affinity_scan_kernel+topk_merge_kernel (cutie_affinity_topk)',
+            roof = {'bound': 'tensor', 'kernel': 'cutie_affinity_topk = 3 x affinity_tc_filter_kernel (tcgen05 kind::tf32) + 2 x level_select + '
+                              'affinity_rerank_kernel (exact fp32)',
                     'achieved': ach, 'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
                     'frac': ach / peaks['bf16_tflops_sustained'], 'traffic': None,
                     'peak_source': f"{peaks['src']} bf16 sustained (kernel timed inside a long step)",
                     'algorithmic_flops_per_launch': flops, 'avg_launch_ms': scan_ms,
                     'hbm_view': {'algorithmic_bytes': bytes_alg, 'achieved_gbs': bytes_alg / (scan_ms * 1e-3) / 1e9,
                                  'frac': bytes_alg / (scan_ms * 1e-3) / 1e9 / peaks['hbm_gbs']},
-                    'note': 'fp32 CUDA-core direct-form evaluation (exact top-k); tcgen05 path is round-2 work'}
+                    'note': 'algorithmic flops = one K=128 contraction over the whole bank; the TF32 filter levels execute 1.07x '
+                            'that (nested samples) at half the bf16 rate, the exact re-rank touches ~540 tokens/query'}
         else:
             ach = bytes_alg / (scan_ms * 1e-3) / 1e9
             roof = {'bound': 'hbm', 'kernel': 'affinity_scan_kernel+topk_merge_kernel (cutie_affinity_topk)',
@@ -320,7 +332,7 @@ def main():
             'e2e': {'value': fps_e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': res['h2d'],
                     'd2h_bytes_per_step': res['d2h'], 'ms_per_step': res['ms_e2e'] / args.steps},
             'gpu_launches': res['launches'], 'roofline': roof, 'cpu_baseline': cpu, 'kernels': kshare}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 if __name__ == '__main__':

@@ -15,7 +15,6 @@ constexpr int NQ = 16;    // object queries
 
 // ------------------------------------------------------------------------------------------------
 // skinny fused linear: y[M,N] = epi( pro(x)[M,Kd] . W[N,Kd]^T )
-// CTA tile 32 rows x BN cols, 256 threads, K chunks of 32 through smem.
 struct LinearParams {
   const float* x;
   long long M, Kd, ldx;
@@ -32,81 +31,61 @@ struct LinearParams {
   float* y;
 };
 
-template <int BN>
+// CTA tile 32 rows x 8 cols, 256 threads (one output each); the reduction axis is staged through smem in chunks
+// of 256 (the whole axis for embed 256 => one barrier), LayerNorm statistics are taken from the staged tile.
+constexpr int LIN_BM = 32, LIN_BN = 8, LIN_KC = 256;
 __global__ void __launch_bounds__(256) qt_linear_kernel(const LinearParams p) {
-  constexpr int BM = 32, BK = 32;
-  constexpr int OPT = BN / 8;  // outputs per thread
-  __shared__ float xs[BM][BK + 1];
-  __shared__ float wsm[BN][BK + 1];
-  __shared__ float mean_s[BM], rstd_s[BM], den_s[BM];
+  __shared__ float xs[LIN_BM][LIN_KC + 1];
+  __shared__ float wsm[LIN_BN][LIN_KC + 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const long long m0 = (long long)blockIdx.y * BM, n0 = (long long)blockIdx.x * BN;
-  // ---- prologue: per-row statistics ----
-  for (int r = warp; r < BM; r += 8) {
-    const long long m = m0 + r;
-    float den = 1.f, mean = 0.f, rstd = 1.f;
-    if (m < p.M) {
-      if (p.summary_norm) den = 1.f / (p.x[m * p.ldx + p.Kd] + 1e-4f);
-      if (p.ln_w) {
-        float s = 0.f;
-        for (long long k = lane; k < p.Kd; k += 32) s += p.x[m * p.ldx + k] * den;
-        mean = warp_sum(s) / (float)p.Kd;
-        float v = 0.f;
-        for (long long k = lane; k < p.Kd; k += 32) {
-          float d = p.x[m * p.ldx + k] * den - mean;
-          v += d * d;
-        }
-        rstd = rsqrtf(warp_sum(v) / (float)p.Kd + 1e-5f);
-      }
-    }
-    if (lane == 0) { mean_s[r] = mean; rstd_s[r] = rstd; den_s[r] = den; }
-  }
-  __syncthreads();
+  const long long m0 = (long long)blockIdx.y * LIN_BM, n0 = (long long)blockIdx.x * LIN_BN;
   const int r_t = tid >> 3, cg = tid & 7;
-  float acc[OPT];
-#pragma unroll
-  for (int u = 0; u < OPT; ++u) acc[u] = 0.f;
-  for (long long k0 = 0; k0 < p.Kd; k0 += BK) {
-    for (int i = tid; i < BM * BK; i += 256) {
-      const int r = i / BK, kk = i % BK;
-      const long long m = m0 + r, k = k0 + kk;
-      float v = 0.f;
-      if (m < p.M && k < p.Kd) {
-        v = p.x[m * p.ldx + k] * den_s[r];
-        if (p.ln_w) {
-          v = (v - mean_s[r]) * rstd_s[r] * p.ln_w[k] + p.ln_b[k];
-          if (p.xhat_out && blockIdx.x == 0) p.xhat_out[m * p.Kd + k] = v;
+  float acc = 0.f;
+  for (long long k0 = 0; k0 < p.Kd; k0 += LIN_KC) {
+    const int kc = (int)((p.Kd - k0) < LIN_KC ? (p.Kd - k0) : LIN_KC);
+    if (k0) __syncthreads();
+    // ---- stage x rows (4 per warp) and the 8 weight rows (1 per warp) ----
+    for (int r = warp; r < LIN_BM; r += 8) {
+      const long long m = m0 + r;
+      float den = 1.f;
+      if (m < p.M && p.summary_norm) den = 1.f / (p.x[m * p.ldx + p.Kd] + 1e-4f);
+      for (int kk = lane; kk < LIN_KC; kk += 32) {
+        float v = 0.f;
+        if (m < p.M && kk < kc) v = p.x[m * p.ldx + k0 + kk] * den;
+        xs[r][kk] = v;
+      }
+      if (p.ln_w) {                       // Kd == 256: the whole row is staged; two-pass statistics
+        __syncwarp();
+        float sum = 0.f;
+        for (int kk = lane; kk < LIN_KC; kk += 32) sum += xs[r][kk];
+        const float mean = warp_sum(sum) / (float)p.Kd;
+        float var = 0.f;
+        for (int kk = lane; kk < LIN_KC; kk += 32) { const float d = xs[r][kk] - mean; var += d * d; }
+        const float rstd = rsqrtf(warp_sum(var) / (float)p.Kd + 1e-5f);
+        for (int kk = lane; kk < LIN_KC; kk += 32) {
+          float v = (xs[r][kk] - mean) * rstd * p.ln_w[kk] + p.ln_b[kk];
+          if (p.xhat_out && blockIdx.x == 0 && m < p.M) p.xhat_out[m * p.Kd + kk] = v;
+          xs[r][kk] = v;
         }
-        if (p.pe) v += p.pe[m * p.Kd + k];
       }
-      xs[r][kk] = v;
+      if (p.pe && m < p.M)
+        for (int kk = lane; kk < kc; kk += 32) xs[r][kk] += p.pe[m * p.Kd + k0 + kk];
     }
-    for (int i = tid; i < BN * BK; i += 256) {
-      const int c = i / BK, kk = i % BK;
-      const long long n = n0 + c, k = k0 + kk;
-      wsm[c][kk] = (n < p.N && k < p.Kd) ? p.W[n * p.ldw + k] : 0.f;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int kk = 0; kk < BK; ++kk) {
-      const float xv = xs[r_t][kk];
-#pragma unroll
-      for (int u = 0; u < OPT; ++u) acc[u] = fmaf(xv, wsm[cg + 8 * u][kk], acc[u]);
+    {
+      const long long n = n0 + warp;
+      for (int kk = lane; kk < LIN_KC; kk += 32)
+        wsm[warp][kk] = (n < p.N && kk < kc) ? p.W[n * p.ldw + k0 + kk] : 0.f;
     }
     __syncthreads();
+#pragma unroll 8
+    for (int kk = 0; kk < LIN_KC; ++kk) acc = fmaf(xs[r_t][kk], wsm[cg][kk], acc);
   }
-  const long long m = m0 + r_t;
-  if (m < p.M) {
-#pragma unroll
-    for (int u = 0; u < OPT; ++u) {
-      const long long n = n0 + cg + 8 * u;
-      if (n < p.N) {
-        float v = acc[u] + (p.bias ? p.bias[n] : 0.f);
-        if (p.relu) v = fmaxf(v, 0.f);
-        if (p.residual) v += p.residual[(p.residual_mod ? (m % p.residual_mod) : m) * p.N + n];
-        p.y[m * p.N + n] = v;
-      }
-    }
+  const long long m = m0 + r_t, n = n0 + cg;
+  if (m < p.M && n < p.N) {
+    float v = acc + (p.bias ? p.bias[n] : 0.f);
+    if (p.relu) v = fmaxf(v, 0.f);
+    if (p.residual) v += p.residual[(p.residual_mod ? (m % p.residual_mod) : m) * p.N + n];
+    p.y[m * p.N + n] = v;
   }
 }
 
@@ -116,26 +95,23 @@ __global__ void __launch_bounds__(256) qt_head_fold_kernel(const float* __restri
                                                            long long ldw, int transpose_w, float scale,
                                                            const float* __restrict__ bias_vec, float* __restrict__ out,
                                                            float* __restrict__ dots) {
-  __shared__ float as[E_];
+  __shared__ float as[DH];
   const long long m = blockIdx.x;
+  const int h = blockIdx.y;
   const int c = threadIdx.x;
-  as[c] = a[m * E_ + c];
+  if (c < DH) as[c] = a[m * E_ + h * DH + c];
   __syncthreads();
-  for (int h = 0; h < H_; ++h) {
-    float acc = 0.f;
+  float acc = 0.f;
 #pragma unroll 8
-    for (int d = 0; d < DH; ++d) {
-      const int r = h * DH + d;
-      const float w = transpose_w ? W[(long long)c * ldw + r] : W[(long long)r * ldw + c];
-      acc = fmaf(as[r], w, acc);
-    }
-    out[(m * H_ + h) * E_ + c] = acc * scale;
+  for (int d = 0; d < DH; ++d) {
+    const int r = h * DH + d;
+    const float w = transpose_w ? W[(long long)c * ldw + r] : W[(long long)r * ldw + c];
+    acc = fmaf(as[d], w, acc);
   }
-  if (dots) {
-    const int h = c >> 5, d = c & 31;
-    float v = as[h * DH + d] * bias_vec[h * DH + d];
-    v = warp_sum(v);
-    if (d == 0) dots[m * H_ + h] = v * scale;
+  out[(m * H_ + h) * E_ + c] = acc * scale;
+  if (dots && c < DH) {
+    float v = warp_sum(as[c] * bias_vec[h * DH + c]);
+    if (c == 0) dots[m * H_ + h] = v * scale;
   }
 }
 
@@ -490,12 +466,8 @@ extern "C" int cutie_qt_linear(const float* x, int64_t M, int64_t Kd, const floa
   p.summary_norm = summary_norm; p.relu = relu; p.residual = residual; p.residual_mod = residual_mod;
   p.xhat_out = xhat_out; p.y = y;
   cudaStream_t st = (cudaStream_t)stream;
-  const unsigned my = (unsigned)((M + 31) / 32);
-  if (Kd >= 1024 || N <= 256) {
-    qt_linear_kernel<8><<<dim3((unsigned)((N + 7) / 8), my), 256, 0, st>>>(p);
-  } else {
-    qt_linear_kernel<32><<<dim3((unsigned)((N + 31) / 32), my), 256, 0, st>>>(p);
-  }
+  CUTIE_REQUIRE(ln_w == nullptr || Kd == LIN_KC, "fused LayerNorm needs Kd == 256");
+  qt_linear_kernel<<<dim3((unsigned)((N + LIN_BN - 1) / LIN_BN), (unsigned)((M + LIN_BM - 1) / LIN_BM)), 256, 0, st>>>(p);
   CUTIE_CHECK_LAUNCH();
   return 0;
 }
@@ -506,7 +478,8 @@ extern "C" int cutie_qt_head_fold(const float* a, int64_t M, int64_t E, int num_
   CUTIE_REQUIRE(a && W && out && M >= 1, "null/empty argument");
   CUTIE_REQUIRE(E == E_ && num_heads == H_, "embed_dim must be 256 with 8 heads");
   CUTIE_REQUIRE((dots == nullptr) == (bias_vec == nullptr), "dots and bias_vec must be given together");
-  qt_head_fold_kernel<<<(unsigned)M, 256, 0, (cudaStream_t)stream>>>(a, W, ldw, transpose_w, scale, bias_vec, out, dots);
+  qt_head_fold_kernel<<<dim3((unsigned)M, H_), 256, 0, (cudaStream_t)stream>>>(a, W, ldw, transpose_w, scale, bias_vec, out,
+                                                                             dots);
   CUTIE_CHECK_LAUNCH();
   return 0;
 }

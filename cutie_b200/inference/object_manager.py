@@ -78,10 +78,12 @@ class ObjectManager:
         return len(gone) > 0, tmp_keep, [o.id for o in kept]
 
     def tmp_to_obj_cls(self, mask) -> torch.Tensor:
-        out = torch.zeros_like(mask)
+        """tmp-id class map -> object-id class map (object_manager.py:99-104) as one table lookup
+        (boolean-mask assignment per object would force a host sync per object)."""
+        lut = torch.zeros(len(self.tmp_id_to_obj) + 1, dtype=mask.dtype)
         for tmp_id, obj in self.tmp_id_to_obj.items():
-            out[mask == tmp_id] = obj.id
-        return out
+            lut[tmp_id] = obj.id
+        return lut.to(mask.device, non_blocking=True)[mask]
 
     def get_tmp_to_obj_mapping(self) -> Dict[int, ObjectInfo]:
         return {obj.id: tmp_id for obj, tmp_id in self.tmp_id_to_obj.items()}
