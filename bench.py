@@ -118,7 +118,7 @@ def run_ours(args, wl, rank, world, dev):
     n_frames = args.warmup + args.steps + 2
     frames, mask = synthetic_video(n_frames, wl['H'], wl['W'], wl['K'], seed=rank)
     objs = list(range(1, wl['K'] + 1))
-    proc = InferenceCore(net, cfg=cfg)
+    proc = InferenceCore(net, cfg=cfg, use_cuda_graphs=not args.no_graphs)
     with torch.inference_mode():
         proc.step(frames[0].to(dev), mask.to(dev), objects=objs)          # permanent first frame
         for key, shr, vals in synthetic_bank_chunks(wl):                   # steady-state bank
@@ -227,6 +227,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graphs', action='store_true', help='eager launches only (no CUDA-graph frame regions)')
     ap.add_argument('--cpu-seconds', type=float, default=150.0)
     args = ap.parse_args()
     if args.warmup < 3:
@@ -241,7 +242,8 @@ def main():
               'mem_every': 5, 'streams': world, 'parallelism': f'{world} independent streams (1 per GPU)',
               'l2': 'no flush: the bank scanned every frame is larger than the 126 MB L2'
                     if args.workload == 'cfg2' else 'bank fits L2 (north-star size); stated, not flushed',
-              'weights': 'seeded random init (no checkpoint offline)'}
+              'weights': 'seeded random init (no checkpoint offline)',
+              'cuda_graphs': (not args.no_graphs) and args.impl == 'ours'}
 
     if args.impl == 'reference':
         if rank != 0:

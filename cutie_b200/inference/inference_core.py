@@ -22,7 +22,8 @@ log = logging.getLogger()
 
 
 class InferenceCore:
-    def __init__(self, network, cfg, *, image_feature_store: ImageFeatureStore = None):
+    def __init__(self, network, cfg, *, image_feature_store: ImageFeatureStore = None,
+                 use_cuda_graphs: bool = False):
         self.network = network
         self.cfg = cfg
         self.mem_every = cfg.mem_every
@@ -44,6 +45,9 @@ class InferenceCore:
         self.image_feature_store = image_feature_store or ImageFeatureStore(self.network)
         self.last_mask = None
         self.last_logits = None      # network.segment(...)[1] of the latest segmented frame (parity hook)
+        # replay CUDA graphs for the arena-independent parts of a frame (frame_graphs.py); off = reference-like eager
+        self.use_cuda_graphs = use_cuda_graphs
+        self._graphs = None
 
     # -- memory control ------------------------------------------------------------------------
     def _reset_clock(self):
@@ -93,11 +97,23 @@ class InferenceCore:
             log.warning('Trying to segment without any memory!')
             return torch.zeros((1, key.shape[-2] * 16, key.shape[-1] * 16), device=key.device, dtype=key.dtype)
 
-        readout = self.memory.read(pix_feat, key, selection, self.last_mask, self.network)
-        readout = self.object_manager.realize_dict(readout)
         ids = self.object_manager.all_obj_ids
-        sensory, logits, prob = self.network.segment(ms_features, readout, self.memory.get_sensory(ids),
-                                                     chunk_size=self.chunk_size, update_sensory=update_sensory)
+        if self._graph_path_ok(key, ids):
+            # eager memory read (affinity + sparse gather), then one graph replay for fusion + object transformer +
+            # decoder; results live in graph-static buffers, so everything that outlives this frame is cloned
+            visual = self.memory.read_visual(key, selection, ids)
+            sens_in = self.memory.get_sensory(ids)
+            obj_mem = self.memory._get_object_mem_by_ids(ids).unsqueeze(2)
+            sensory, logits, prob = self._graphs.segment(visual, pix_feat, sens_in, self.last_mask, obj_mem,
+                                                         tuple(ms_features), update_sensory)
+            logits, prob = logits.clone(), prob.clone()
+            if update_sensory:
+                sensory = sensory.clone()
+        else:
+            readout = self.memory.read(pix_feat, key, selection, self.last_mask, self.network)
+            readout = self.object_manager.realize_dict(readout)
+            sensory, logits, prob = self.network.segment(ms_features, readout, self.memory.get_sensory(ids),
+                                                         chunk_size=self.chunk_size, update_sensory=update_sensory)
         self.last_logits = logits
         if self.flip_aug:
             prob = (prob[0] + torch.flip(prob[1], dims=[-1])) / 2
@@ -106,6 +122,19 @@ class InferenceCore:
         if update_sensory:
             self.memory.update_sensory(sensory, ids)
         return prob
+
+    def _graph_path_ok(self, key: torch.Tensor, ids) -> bool:
+        if not (self.use_cuda_graphs and key.is_cuda):
+            return False
+        m = self.memory
+        if self.flip_aug or self.chunk_size >= 1 or self.save_aux or len(m.work_mem.buckets) != 1:
+            return False
+        if not getattr(self.network, 'object_transformer_enabled', True) or any(o not in m.obj_v for o in ids):
+            return False
+        if self._graphs is None:
+            from cutie_b200.inference.frame_graphs import FrameGraphs
+            self._graphs = FrameGraphs(self.network)
+        return list(next(iter(m.work_mem.buckets.values()))) == list(ids)
 
     def step(self, image: torch.Tensor, mask: Optional[torch.Tensor] = None,
              objects: Optional[List[int]] = None, *, idx_mask: bool = True, end: bool = False,
@@ -144,8 +173,14 @@ class InferenceCore:
         need_segment = mask is None or (self.object_manager.num_obj > 0 and not self.object_manager.has_all(objects))
         update_sensory = (since_mem in self.stagger_ti) and not end
 
-        ms_feat, pix_feat = self.image_feature_store.get_features(self.curr_ti, image)
-        key, shrinkage, selection = self.image_feature_store.get_key(self.curr_ti, image)
+        if self.use_cuda_graphs and image.is_cuda and not self.flip_aug:
+            if self._graphs is None:
+                from cutie_b200.inference.frame_graphs import FrameGraphs
+                self._graphs = FrameGraphs(self.network)
+            ms_feat, pix_feat, key, shrinkage, selection = self._graphs.encode(image)
+        else:
+            ms_feat, pix_feat = self.image_feature_store.get_features(self.curr_ti, image)
+            key, shrinkage, selection = self.image_feature_store.get_key(self.curr_ti, image)
 
         if need_segment:
             prob_with_bg = self._segment(key, selection, pix_feat, ms_feat, update_sensory=update_sensory)

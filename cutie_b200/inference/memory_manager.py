@@ -138,6 +138,28 @@ class MemoryManager:
                     }
         return out
 
+    def read_visual(self, query_key: torch.Tensor, selection: torch.Tensor, obj_ids: List[int]) -> torch.Tensor:
+        """The memory half of read() for the single-bucket, un-chunked case: fused affinity + sparse value gather
+        (+ usage commits) -> visual readout [B, K, CV, h, w].  Used by the CUDA-graph frame path, which runs the
+        fusion / object-transformer / decoder half as one graph replay."""
+        h, w = query_key.shape[-2:]
+        bs = query_key.shape[0]
+        qk = query_key.flatten(2).contiguous()
+        qe = selection.flatten(2).contiguous()
+        (bucket_id, bucket), = self.work_mem.buckets.items()
+        assert list(bucket) == list(obj_ids)
+        long_n = self.long_mem.size(bucket_id) if (self.use_long_term and self.long_mem.engaged(bucket_id)) else 0
+        segs = self._segments(bucket_id, bucket)
+        usage_acc = None
+        if self.use_long_term:
+            usage_acc = torch.zeros(bs, sum(s.n for s in segs), dtype=torch.int64, device=qk.device)
+        idx, wgt, _ = K_.affinity_topk(segs, qk, qe, self.top_k, usage_acc=usage_acc)
+        if self.use_long_term:
+            self.work_mem.update_bucket_usage(bucket_id, usage_acc, long_n + self.work_mem.perm_size(bucket_id))
+            if long_n and self.count_long_term_usage:
+                self.long_mem.update_bucket_usage(bucket_id, usage_acc, 0)
+        return K_.readout_gather(idx, wgt, segs).view(bs, len(bucket), self.CV, h, w)
+
     # -- insertion -----------------------------------------------------------------------------
     def add_memory(self, key: torch.Tensor, shrinkage: torch.Tensor, msk_value: torch.Tensor,
                    obj_value: Optional[torch.Tensor], objects: List[int],

@@ -158,3 +158,36 @@ def test_teacher_forced_vs_cpu_oracle(over, H, W, K, T):
         K_.affinity_topk = real_topk
     assert worst < 1e-3
     assert rec.flips <= 0.02 * max(rec.queries, 1) + 2
+
+
+def test_cuda_graph_frame_path_matches_eager():
+    """use_cuda_graphs=True replays the encoder and the fusion/transformer/decoder regions as CUDA graphs; the
+    results must equal the eager path (same kernels, same order) over propagated and memory frames."""
+    from cutie_b200.config import default_config
+    from cutie_b200.inference.inference_core import InferenceCore
+    import cutie_b200.kernels as K_
+    from oracle.synth import synthetic_video
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = False
+    cfg = default_config(mem_every=3, max_mem_frames=3)
+    net = _net(cfg)
+    eager, graphed = InferenceCore(net, cfg=cfg), InferenceCore(net, cfg=cfg, use_cuda_graphs=True)
+    frames, mask = synthetic_video(9, 240, 432, 3, seed=7)
+    with torch.inference_mode():
+        for ti in range(9):
+            a = frames[ti].cuda()
+            if ti == 0:
+                pe = eager.step(a, mask.cuda(), objects=[1, 2, 3])
+                pg = graphed.step(a, mask.cuda(), objects=[1, 2, 3])
+            else:
+                n0 = K_.LAUNCH_COUNT
+                pe = eager.step(a)
+                n_eager = K_.LAUNCH_COUNT - n0
+                pg = graphed.step(a)
+                n_graph = K_.LAUNCH_COUNT - n0 - n_eager
+                assert n_graph == n_eager, 'graph replay must account for the same number of cutie_b200 kernels'
+                assert float((eager.last_logits - graphed.last_logits).abs().max()) < 2e-4
+            assert float((pe - pg).abs().max()) < 1e-4
+            assert _sizes(eager) == _sizes(graphed)
+    assert graphed._graphs is not None and len(graphed._graphs._seg) >= 1
