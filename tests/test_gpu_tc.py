@@ -32,10 +32,10 @@ def test_tf32_energy_matches_exact_within_bound(K_, B, N, Q, cuts, scale):
     vq = (qe.double() * qk.double() ** 2).sum(1).sqrt()                                # [B,Q]
     s2 = shr.double()[:, None, :] * (knorm[:, None, :] + vq[:, :, None]) ** 2
     assert (d <= truth + 1e-9).all(), f'filter value above the exact energy by {float((d - truth).max()):.3e}'
-    assert (truth - d <= 2.0 * 1.16e-3 * s2).all(), f'max slack ratio {float(((truth - d) / (1.15e-3 * s2)).max()):.3f}'
+    assert (truth - d <= 2.0 * 1.66e-3 * s2).all(), f'max slack ratio {float(((truth - d) / (1.65e-3 * s2)).max()):.3f}'
     # the TF32 contraction itself (bound removed) is far more accurate than its worst case
-    e_tf32 = d + 1.15e-3 * s2
-    assert float(((e_tf32 - truth).abs() / truth.abs().clamp_min(1e-6)).median()) < 5e-4
+    e_tf32 = d + 1.65e-3 * s2
+    assert float(((e_tf32 - truth).abs() / truth.abs().clamp_min(1e-6)).median()) < 1e-3
 
 
 @pytest.mark.parametrize('B,N,Q,K,top_k,cuts', [
