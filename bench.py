@@ -323,7 +323,8 @@ def main():
                                       'frac': gather_bytes / (gather_ms * 1e-3) / 1e9 / peaks['hbm_gbs']}
     else:
         roof = None
-    kshare = {k: {'avg_ms': sum(v) / len(v), 'calls_per_step': len(v) / args.steps,
+    kshare = {k: {'avg_ms': sum(v) / len(v), 'p50_ms': sorted(v)[len(v) // 2], 'max_ms': max(v),
+                  'calls_per_step': len(v) / args.steps,
                   'share_of_step': sum(v) / res['ms_total']} for k, v in res['kernel_ms'].items()}
     fps = world * args.steps / (res['ms_total'] * 1e-3)
     fps_e2e = world * args.steps / (res['ms_e2e'] * 1e-3)

@@ -390,7 +390,7 @@ static long long tc_min_tokens() {
   static long long v = -1;
   if (v < 0) {
     const char* e = getenv("CUTIE_B200_TC_MIN");
-    v = e ? atoll(e) : 8192;
+    v = e ? atoll(e) : 6144;
     const char* off = getenv("CUTIE_B200_NO_TC");
     if (off && off[0] == '1') v = (1ll << 40);
   }

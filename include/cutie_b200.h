@@ -60,7 +60,7 @@ int cutie_affinity_topk(int num_segments, const void* const* seg_key, const void
  * tcgen05 (TF32) candidate-filter levels over strided samples (strides ..., 256, 16, 1) followed by an exact fp32
  * re-rank of the survivors.  All plans return the same selection and weights (a filter level only discards
  * tokens that provably cannot be in the top-k).
- * cutie_set_tc_min_tokens: banks smaller than n use plan 0 (default 8192; negative restores the default). */
+ * cutie_set_tc_min_tokens: banks smaller than n use plan 0 (default 6144; negative restores the default). */
 int cutie_affinity_plan_levels(int64_t n_total, int top_k);
 void cutie_set_tc_min_tokens(int64_t n);
 /* Test hook: raw TF32 energies E[b,q,n] = -8*S[n,q] computed by the tcgen05 filter over the whole bank

@@ -184,9 +184,11 @@ def test_cuda_graph_frame_path_matches_eager():
                 n0 = K_.LAUNCH_COUNT
                 pe = eager.step(a)
                 n_eager = K_.LAUNCH_COUNT - n0
+                ncap = len(graphed._graphs._seg) + len(graphed._graphs._enc)
                 pg = graphed.step(a)
                 n_graph = K_.LAUNCH_COUNT - n0 - n_eager
-                assert n_graph == n_eager, 'graph replay must account for the same number of cutie_b200 kernels'
+                if len(graphed._graphs._seg) + len(graphed._graphs._enc) == ncap:      # no capture in this step
+                    assert n_graph == n_eager, 'graph replay must account for the same number of cutie_b200 kernels'
                 assert float((eager.last_logits - graphed.last_logits).abs().max()) < 2e-4
             assert float((pe - pg).abs().max()) < 1e-4
             assert _sizes(eager) == _sizes(graphed)
