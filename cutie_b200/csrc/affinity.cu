@@ -381,7 +381,8 @@ struct Plan {
   int levels;             // 0 = exact scan only
   long long stride[8];    // coarsest first, last == 1
 };
-constexpr int TC_CAP = 4096;           // candidate slots per query
+constexpr int TC_CAP = 4096;           // candidate slots per query (also the largest all-pass coarsest sample)
+constexpr int TC_CAP_BIG = 16384;      // slots per query used for the candidate lists (overflow => exhaustive rescan of that query)
 
 static long long g_tc_min_override = -1;
 
@@ -428,8 +429,8 @@ static WsLayout ws_layout(long long B, long long Q, long long n_total, int top_k
   if (pl.levels == 0) {
     w.part = take((size_t)B * pick_splits(B, Q, n_total) * Q * kpad * 8);
   } else {
-    w.cand_idx = take((size_t)B * Q * TC_CAP * 4);
-    w.cand_e = take((size_t)B * Q * TC_CAP * 4);
+    w.cand_idx = take((size_t)B * Q * TC_CAP_BIG * 4);
+    w.cand_e = take((size_t)B * Q * TC_CAP_BIG * 4);
     w.count = take((size_t)B * Q * 4);
     w.dmax = take((size_t)B * Q * 4);
     w.emax0 = take((size_t)B * Q * 4);
@@ -502,7 +503,7 @@ static int run_filter_level(const ScanParams& base, long long B, long long strid
   fp.cand_e = (float*)(ws + wl.cand_e);
   fp.count = (int*)(ws + wl.count);
   fp.dmax = (float*)(ws + wl.dmax);
-  fp.cap = TC_CAP;
+  fp.cap = TC_CAP_BIG;
   fp.dbg_energy = dbg_energy;
   cudaError_t e = cudaMemsetAsync(ws + wl.count, 0, (size_t)(wl.emax0 - wl.count), st);   // count + dmax
   if (e != cudaSuccess) return set_cuda_error("cudaMemsetAsync", e);
@@ -524,7 +525,7 @@ static int run_filtered(const ScanParams& base, long long B, const Plan& pl, cha
       sp.cand_e = (const float*)(ws + wl.cand_e);
       sp.count = (const int*)(ws + wl.count);
       sp.dmax = (const float*)(ws + wl.dmax);
-      sp.cap = TC_CAP;
+      sp.cap = TC_CAP_BIG;
       sp.top_k = base.top_k;
       sp.emax_out = emax[l & 1];
       rc = launch_level_select(sp, B, base.kpad, st);
@@ -541,7 +542,7 @@ static int run_filtered(const ScanParams& base, long long B, const Plan& pl, cha
   rp.n_total = base.n_total;
   rp.cand_idx = (const int*)(ws + wl.cand_idx);
   rp.count = (const int*)(ws + wl.count);
-  rp.cap = TC_CAP;
+  rp.cap = TC_CAP_BIG;
   rp.top_k = base.top_k;
   rp.kpad = base.kpad;
   rp.out_idx = out_idx;
@@ -647,8 +648,8 @@ extern "C" int cutie_debug_tc_energy(int num_segments, const void* const* seg_ke
   memset(&wl, 0, sizeof(wl));
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
-  wl.cand_idx = take((size_t)B * Q * TC_CAP * 4);
-  wl.cand_e = take((size_t)B * Q * TC_CAP * 4);
+  wl.cand_idx = take((size_t)B * Q * TC_CAP_BIG * 4);
+  wl.cand_e = take((size_t)B * Q * TC_CAP_BIG * 4);
   wl.count = take((size_t)B * Q * 4);
   wl.dmax = take((size_t)B * Q * 4);
   wl.emax0 = take((size_t)B * Q * 4);

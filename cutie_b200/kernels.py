@@ -179,7 +179,7 @@ def debug_tc_energy(segments: Sequence[BankSegment], qk: torch.Tensor, qe: torch
     out = torch.zeros(B, Q, n_total, dtype=torch.float32, device=qk.device)
     ns = len(segments)
     PA, IA = ctypes.c_void_p * ns, ctypes.c_int64 * ns
-    ws_bytes = B * Q * (4096 * 8 + 16 + 32 * 8) + (1 << 20)
+    ws_bytes = B * Q * (16384 * 8 + 16 + 32 * 8) + (1 << 20)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=qk.device)
     with _call('debug_tc_energy', 2):
         st = lib().cutie_debug_tc_energy(
