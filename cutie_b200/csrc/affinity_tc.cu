@@ -186,6 +186,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) affinity_tc_filter_kernel(const
     int* my_idx = p.cand_idx + bq * p.cap;
     float* my_e = p.cand_e + bq * p.cap;
     const bool all_pass = (p.emax_in == nullptr);       // coarsest level: every token of the sample is kept
+    int blk_base = 0, blk_used = 32;
     if (all_pass && split == 0 && q < p.Q) p.count[bq] = (int)p.samp_count;
     for (int t = 0; t < ntiles; ++t) {
       const int a = t & 1;
@@ -235,7 +236,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) affinity_tc_filter_kernel(const
             const float s_ = T.rowP[t & 3][col] + T.rowR[t & 3][col] * vq;
             const float e_hi = d + 2.01f * TF32_EPS * s_ * s_;          // an UPPER bound of the exact energy
             int pos;
-            if (all_pass) pos = (int)(ibase + col); else pos = atomicAdd(&p.count[bq], 1);
+            if (all_pass) {
+              pos = (int)(ibase + col);
+            } else {
+              // slots are reserved 32 at a time: one global atomic (latency ~1 us) per 32 candidates of this
+              // (query, CTA) instead of one per candidate; unused slots of the last block are voided at the end
+              if (blk_used == 32) { blk_base = atomicAdd(&p.count[bq], 32); blk_used = 0; }
+              pos = blk_base + blk_used++;
+            }
             if (pos < p.cap) {
               my_idx[pos] = (int)(p.samp_begin + (ibase + col) * p.samp_stride);
               my_e[pos] = e_hi;
@@ -246,6 +254,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) affinity_tc_filter_kernel(const
       tc_fence_before();
       mbar_arrive(smem_u32(&T.tempty[a]));
     }
+    if (!all_pass && blk_used < 32)
+      for (int u = blk_used; u < 32; ++u)
+        if (blk_base + u < p.cap) { my_idx[blk_base + u] = -1; my_e[blk_base + u] = CUDART_INF_F; }
   } else if (warp < 12) {
     // ============ producers: 16 lanes per token row (coalesced 256-B rows), next tile prefetched ============
     const int grp = (warp - 4) >> 2;     // producer group 0 handles even tiles (stage 0), group 1 odd tiles
@@ -425,6 +436,8 @@ __global__ void __launch_bounds__(128) affinity_rerank_kernel(const RerankParams
     int id = INT_MAX;
     if (j < n) {
       id = exhaustive ? j : cl[j];
+    }
+    if (j < n && id >= 0) {
       const int sg = seg_of(p.segs.begin, p.segs.nseg, id);
       const float* krow = p.segs.key[sg] + (long long)b * p.segs.key_bs[sg] + ((long long)id - p.segs.begin[sg]) * CKD;
       const float shr = p.segs.shr[sg][(long long)b * p.segs.shr_bs[sg] + ((long long)id - p.segs.begin[sg])];
@@ -432,7 +445,7 @@ __global__ void __launch_bounds__(128) affinity_rerank_kernel(const RerankParams
     }
     const float kth = lv[warp][p.top_k - 1];
     const int kthi = li[warp][p.top_k - 1];
-    unsigned bits = __ballot_sync(0xffffffffu, (j < n) && (sv > kth || (sv == kth && id < kthi)));
+    unsigned bits = __ballot_sync(0xffffffffu, (j < n) && id >= 0 && (sv > kth || (sv == kth && id < kthi)));
     while (bits) {
       const int src = __ffs(bits) - 1;
       bits &= bits - 1;

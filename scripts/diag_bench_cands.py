@@ -37,3 +37,16 @@ with torch.inference_mode():
     cnt = ws[o_cnt:o_cnt + B*Q*4].view(torch.int32)
     print('final-level candidates/query: mean %.0f median %.0f max %d  frac>4096 %.3f frac>16384 %.3f' % (float(cnt.float().mean()), float(cnt.float().median()), int(cnt.max()), float((cnt > 4096).float().mean()), float((cnt > CAP).float().mean())))
     print('E* (=-8*kth sim) mean %.3f' % float((-8 * sim[0, :, k-1]).mean()), ' winners in newest 20k tokens frac %.3f' % float((idx[0, :, :k] >= N - 20000).float().mean()))
+    segs3 = proc.memory.work_mem.segments(0, [1, 2, 3])
+    flush = torch.empty(64 << 20, dtype=torch.float32, device=dev)
+    for name, tcmin in (('tcgen05 plan', -1), ('exact scan', 1 << 40)):
+        K_.set_tc_min_tokens(tcmin)
+        for _ in range(2): K_.affinity_topk(segs3, qk, qe, 30)
+        ts = []
+        for _ in range(6):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); K_.affinity_topk(segs3, qk, qe, 30); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        print(name, 'isolated on the evolved bank: ms', ['%.3f' % t for t in ts])
+    K_.set_tc_min_tokens(-1)
