@@ -325,44 +325,46 @@ __global__ void __launch_bounds__(256) qt_p2q_partial_kernel(const P2QParams p) 
   if (tid < NQ) { w[NQ * E_ + tid] = rm[tid]; w[NQ * E_ + NQ + tid] = rl[tid]; }
 }
 
-// pass 2: grid (heads, BK): merge splits, normalise, apply the per-head value projection.
+// pass 2: grid (16 query rows, heads, BK): merge the splits of one attention row, normalise, apply the per-head
+// value projection (8 warps x 4 outputs, lanes across the 256 input channels).
 __global__ void __launch_bounds__(256) qt_p2q_combine_kernel(const float* __restrict__ ws, int splits,
                                                              const float* __restrict__ wv, long long ldwv,
                                                              const float* __restrict__ bv, float* __restrict__ attn) {
-  __shared__ float zn[NQ][E_ + 1];
-  __shared__ float coef[64][NQ];   // per split, per row: exp(m_s - M) / L
-  const int tid = threadIdx.x;
-  const int h = blockIdx.x;
-  const long long bk = blockIdx.y;
+  __shared__ float zn[E_];
+  __shared__ float coef[64];   // per split: exp(m_s - M) / L
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int i = blockIdx.x, h = blockIdx.y;
+  const long long bk = blockIdx.z;
   const float* base = ws + ((bk * H_ + h) * splits) * (long long)P2Q_WS;
-  if (tid < NQ) {
+  if (warp == 0) {
     float M = -CUDART_INF_F;
-    for (int s = 0; s < splits; ++s) M = fmaxf(M, base[(long long)s * P2Q_WS + NQ * E_ + tid]);
+    for (int s = lane; s < splits; s += 32) M = fmaxf(M, base[(long long)s * P2Q_WS + NQ * E_ + i]);
+    M = warp_max(M);
     float L = 0.f;
-    for (int s = 0; s < splits; ++s) {
-      const float ms = base[(long long)s * P2Q_WS + NQ * E_ + tid];
+    for (int s = lane; s < splits; s += 32) {
+      const float ms = base[(long long)s * P2Q_WS + NQ * E_ + i];
       const float f = (ms == -CUDART_INF_F) ? 0.f : expf(ms - M);
-      coef[s][tid] = f;
-      L += f * base[(long long)s * P2Q_WS + NQ * E_ + NQ + tid];
+      coef[s] = f;
+      L += f * base[(long long)s * P2Q_WS + NQ * E_ + NQ + i];
     }
+    L = warp_sum(L);
+    __syncwarp();
     const float inv = 1.f / L;
-    for (int s = 0; s < splits; ++s) coef[s][tid] *= inv;
+    for (int s = lane; s < splits; s += 32) coef[s] *= inv;
   }
   __syncthreads();
-  for (int i = 0; i < NQ; ++i) {
-    float acc = 0.f;
-    for (int s = 0; s < splits; ++s) acc = fmaf(coef[s][i], base[(long long)s * P2Q_WS + i * E_ + tid], acc);
-    zn[i][tid] = acc;
-  }
+  float acc = 0.f;
+  for (int s = 0; s < splits; ++s) acc = fmaf(coef[s], base[(long long)s * P2Q_WS + i * E_ + tid], acc);
+  zn[tid] = acc;
   __syncthreads();
-  // attn[(bk*16+i), h*32+e] = zn[i] . wv[h*32+e, :] + bv[h*32+e];  512 outputs, 2 per thread
-  for (int o = tid; o < NQ * DH; o += 256) {
-    const int i = o / DH, e = o % DH;
+  // attn[(bk*16+i), h*32+e] = zn . wv[h*32+e, :] + bv[h*32+e]
+  for (int e = warp; e < DH; e += 8) {
     const float* wr = wv + (long long)(h * DH + e) * ldwv;
-    float acc = 0.f;
-#pragma unroll 8
-    for (int c = 0; c < E_; ++c) acc = fmaf(zn[i][c], wr[c], acc);
-    attn[(bk * NQ + i) * E_ + h * DH + e] = acc + bv[h * DH + e];
+    float d = 0.f;
+#pragma unroll
+    for (int c = lane; c < E_; c += 32) d = fmaf(zn[c], wr[c], d);
+    d = warp_sum(d);
+    if (lane == 0) attn[(bk * NQ + i) * E_ + h * DH + e] = d + bv[h * DH + e];
   }
 }
 
@@ -539,7 +541,7 @@ extern "C" int cutie_qt_pixel_to_query(const float* qfold, const float* pixel, c
   cudaStream_t st = (cudaStream_t)stream;
   qt_p2q_partial_kernel<<<dim3((unsigned)splits, H_, (unsigned)BK), 256, smem, st>>>(p);
   CUTIE_CHECK_LAUNCH();
-  qt_p2q_combine_kernel<<<dim3(H_, (unsigned)BK), 256, 0, st>>>(workspace, splits, wv, ldwv, bv, attn_out);
+  qt_p2q_combine_kernel<<<dim3(NQ, H_, (unsigned)BK), 256, 0, st>>>(workspace, splits, wv, ldwv, bv, attn_out);
   CUTIE_CHECK_LAUNCH();
   return 0;
 }
