@@ -1,0 +1,53 @@
+"""Key-sharded read over NCCL on >= 2 GPUs (skipped on a single-GPU box): sharded == single-GPU result."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from tests.conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, n_total, ret):
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    try:
+        import cutie_b200.kernels as K_
+        from cutie_b200.inference.sharded import shard_bounds, sharded_read
+        g = torch.Generator().manual_seed(0)
+        B, Q, K, top_k = 1, 1620, 3, 30
+        key = torch.randn(B, n_total, 64, generator=g).cuda()
+        shr = (1 + torch.randn(B, n_total, generator=g) ** 2).cuda()
+        vals = [torch.randn(B, n_total, 256, generator=g).cuda() for _ in range(K)]
+        qk = torch.randn(B, 64, Q, generator=g).cuda()
+        qe = torch.sigmoid(torch.randn(B, 64, Q, generator=g)).cuda()
+        lo, hi = shard_bounds(n_total, world, rank)
+        seg = K_.BankSegment(key[:, lo:hi], shr[:, lo:hi], tuple(v[:, lo:hi] for v in vals))
+        usage = torch.zeros(B, hi - lo, dtype=torch.int64, device='cuda')
+        out, idx, w = sharded_read([seg], lo, n_total, qk, qe, top_k, usage_acc_local=usage)
+        full = K_.BankSegment(key, shr, tuple(vals))
+        uref = torch.zeros(B, n_total, dtype=torch.int64, device='cuda')
+        ridx, rw, _ = K_.affinity_topk([full], qk, qe, top_k, usage_acc=uref)
+        rout = K_.readout_gather(ridx, rw, [full])
+        torch.cuda.synchronize()
+        ret[rank] = bool(torch.equal(idx, ridx) and torch.equal(w, rw) and
+                         torch.allclose(out, rout, rtol=1e-5, atol=1e-5) and torch.equal(usage, uref[:, lo:hi]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs >= 2 GPUs')
+@pytest.mark.parametrize('n_total', [5000, 50000])
+def test_sharded_read_nccl(n_total):
+    world = min(torch.cuda.device_count(), 8)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, 29641 + n_total % 97, n_total, ret), nprocs=world, join=True)
+    assert all(ret.get(r) for r in range(world)), dict(ret)
