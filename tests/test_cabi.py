@@ -44,3 +44,23 @@ def test_sass_is_sm100a():
     ge.build()
     out = subprocess.run(['/usr/local/cuda/bin/cuobjdump', '-lelf', ge.LIB], capture_output=True, text=True).stdout
     assert 'sm_100a' in out
+
+
+def test_affinity_plan_is_pure_host_logic():
+    """Which passes cutie_affinity_topk runs for a bank size (no GPU needed): exact scan below the threshold,
+    nested tcgen05 filter levels (strides 16^l) above it, coarsest sample never above 4096 tokens."""
+    import __graft_entry__ as ge
+    ge.build()
+    lib = ctypes.CDLL(ge.LIB)
+    plan = lambda n, k=30: lib.cutie_affinity_plan_levels(ctypes.c_int64(n), k)
+    lib.cutie_set_tc_min_tokens(ctypes.c_int64(-1))
+    assert plan(100) == 0 and plan(1620) == 0 and plan(4860) == 0
+    assert plan(8100) == 2            # 8100/16 = 507-token all-pass sample, then the whole bank
+    assert plan(65536) == 2           # 4096-token sample
+    assert plan(65537) == 3 and plan(413100) == 3 and plan(414720) == 3
+    assert plan(20_000_000) == 5       # strides 65536, 4096, 256, 16, 1
+    lib.cutie_set_tc_min_tokens(ctypes.c_int64(256))
+    assert plan(333) == 1 and plan(59) == 0 and plan(4099) == 2
+    lib.cutie_set_tc_min_tokens(ctypes.c_int64(1 << 40))
+    assert plan(413100) == 0
+    lib.cutie_set_tc_min_tokens(ctypes.c_int64(-1))
