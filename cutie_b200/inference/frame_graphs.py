@@ -9,7 +9,8 @@ frame have static shapes and touch no memory-bank pointers, so each is captured 
             -> pixel_fusion -> object transformer (fused kernels) -> mask decoder -> probabilities, new sensory
 
 The memory read between them (cutie_affinity_topk + cutie_readout_gather) stays eager: its segment pointers move
-whenever the ring advances.  Memory frames (mask encoder + append) also stay eager.  Graphs are keyed by every
+whenever the ring advances.  On memory frames the mask encoder + object summarizer (G3) are a third graph; the
+append into the arena stays eager.  Graphs are keyed by every
 shape/flag they depend on and are bypassed (eager path) for multi-bucket / chunked / flip-augmented reads.
 Enable with `InferenceCore(..., use_cuda_graphs=True)` or `processor.use_cuda_graphs = True`.
 """
@@ -47,6 +48,7 @@ class FrameGraphs:
         self.net = network
         self._enc: Dict[Tuple, _Captured] = {}
         self._seg: Dict[Tuple, _Captured] = {}
+        self._msk: Dict[Tuple, _Captured] = {}
 
     # ---- G1 ------------------------------------------------------------------------------------
     def encode(self, image: torch.Tensor):
@@ -80,5 +82,22 @@ class FrameGraphs:
                 return new_sens, logits, prob
             cap = self._seg[key] = _Captured(fn, st)
         for dst, src in zip(cap.inputs, (visual, sensory, last_mask, obj_mem)):
+            dst.copy_(src)
+        return cap.replay()
+
+    # ---- G3 (memory frames) ----------------------------------------------------------------------
+    def encode_mask(self, image, pix_feat, sensory, masks):
+        """CUTIE.encode_mask (mask encoder + deep sensory update + object summarizer) as one replay.
+        Returns (value [B,K,CV,h,w], new_sensory, summaries [B,K,Q,E+1]) in static buffers."""
+        key = (tuple(image.shape), tuple(masks.shape), image.device, pix_feat.data_ptr())
+        cap = self._msk.get(key)
+        if cap is None:
+            st = (image.clone(), sensory.clone(), masks.clone())
+
+            def fn(img, sens, msk):
+                value, new_sens, summaries, _ = self.net.encode_mask(img, pix_feat, sens, msk)
+                return value, new_sens, summaries
+            cap = self._msk[key] = _Captured(fn, st)
+        for dst, src in zip(cap.inputs, (image, sensory, masks)):
             dst.copy_(src)
         return cap.replay()

@@ -79,9 +79,16 @@ class InferenceCore:
             return
         ids = self.object_manager.all_obj_ids
         self.memory.initialize_sensory_if_needed(key, ids)
-        msk_value, sensory, obj_value, _ = self.network.encode_mask(
-            image, pix_feat, self.memory.get_sensory(ids), prob, deep_update=is_deep_update,
-            chunk_size=self.chunk_size, need_weights=self.save_aux)
+        graphed = (self.use_cuda_graphs and self._graphs is not None and image.is_cuda and is_deep_update and
+                   not self.flip_aug and self.chunk_size < 1 and not self.save_aux and
+                   getattr(self.network, 'object_transformer_enabled', True))
+        if graphed:
+            msk_value, sensory, obj_value = self._graphs.encode_mask(image, pix_feat, self.memory.get_sensory(ids), prob)
+            sensory = sensory.clone()          # outlives this frame; value / summaries are consumed by add_memory below
+        else:
+            msk_value, sensory, obj_value, _ = self.network.encode_mask(
+                image, pix_feat, self.memory.get_sensory(ids), prob, deep_update=is_deep_update,
+                chunk_size=self.chunk_size, need_weights=self.save_aux)
         self.memory.add_memory(key, shrinkage, msk_value, obj_value, ids, selection=selection,
                                as_permanent='all' if force_permanent else 'first')
         self.last_mem_ti = self.curr_ti
