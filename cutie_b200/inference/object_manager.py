@@ -78,12 +78,16 @@ class ObjectManager:
         return len(gone) > 0, tmp_keep, [o.id for o in kept]
 
     def tmp_to_obj_cls(self, mask) -> torch.Tensor:
-        """tmp-id class map -> object-id class map (object_manager.py:99-104) as one table lookup
-        (boolean-mask assignment per object would force a host sync per object)."""
-        lut = torch.zeros(len(self.tmp_id_to_obj) + 1, dtype=mask.dtype)
-        for tmp_id, obj in self.tmp_id_to_obj.items():
-            lut[tmp_id] = obj.id
-        return lut.to(mask.device, non_blocking=True)[mask]
+        """tmp-id class map -> object-id class map (object_manager.py:99-104) as one table lookup.  The table lives
+        on the mask's device and is rebuilt only when the object set changes: boolean-mask assignment per object
+        (or a per-frame pageable H2D copy) would stall the host on the GPU every frame."""
+        sig = (tuple((t, o.id) for t, o in self.tmp_id_to_obj.items()), mask.device, mask.dtype)
+        if getattr(self, '_lut_sig', None) != sig:
+            lut = torch.zeros(len(self.tmp_id_to_obj) + 1, dtype=mask.dtype)
+            for tmp_id, obj in self.tmp_id_to_obj.items():
+                lut[tmp_id] = obj.id
+            self._lut, self._lut_sig = lut.to(mask.device), sig
+        return self._lut[mask]
 
     def get_tmp_to_obj_mapping(self) -> Dict[int, ObjectInfo]:
         return {obj.id: tmp_id for obj, tmp_id in self.tmp_id_to_obj.items()}
