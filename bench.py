@@ -115,6 +115,8 @@ def run_ours(args, wl, rank, world, dev):
     torch.backends.cudnn.benchmark = True
     cfg = make_cfg(wl)
     net = make_net(cfg).to(dev)
+    if not args.no_optimize:
+        net.optimize_for_inference()          # BN folding + channels-last trunks (still PyTorch/cuDNN calls)
     n_frames = args.warmup + args.steps + 2
     frames, mask = synthetic_video(n_frames, wl['H'], wl['W'], wl['K'], seed=rank)
     objs = list(range(1, wl['K'] + 1))
@@ -227,6 +229,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-optimize', action='store_true', help='skip CUTIE.optimize_for_inference()')
     ap.add_argument('--no-graphs', action='store_true', help='eager launches only (no CUDA-graph frame regions)')
     ap.add_argument('--cpu-seconds', type=float, default=150.0)
     args = ap.parse_args()
@@ -243,7 +246,8 @@ def main():
               'l2': 'no flush: the bank scanned every frame is larger than the 126 MB L2'
                     if args.workload == 'cfg2' else 'bank fits L2 (north-star size); stated, not flushed',
               'weights': 'seeded random init (no checkpoint offline)',
-              'cuda_graphs': (not args.no_graphs) and args.impl == 'ours'}
+              'cuda_graphs': (not args.no_graphs) and args.impl == 'ours',
+              'encoder_trunks': 'BN folded, channels_last' if (not args.no_optimize and args.impl == 'ours') else 'as loaded'}
 
     if args.impl == 'reference':
         if rank != 0:

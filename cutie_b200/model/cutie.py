@@ -173,6 +173,21 @@ class CUTIE(nn.Module):
                 log.info(f'Key {k} found in self.state_dict() but not in src_dict!!!')
         self.load_state_dict(src_dict, strict=False)
 
+    def optimize_for_inference(self, channels_last: bool = True) -> 'CUTIE':
+        """Post-load surgery on the PyTorch/cuDNN stages (cutie_b200/model/fuse.py): fold the frozen BatchNorms of
+        both ResNet trunks into their convolutions and run the trunks channels-last.  Numerically equivalent up to
+        fp32 rounding; the module tree (hence state_dict) of the trunks changes, so call it after load_weights."""
+        from cutie_b200.model.fuse import fold_trunk_
+        for enc in (self.pixel_encoder, self.mask_encoder):
+            fold_trunk_(enc)
+            if channels_last:
+                for name in ('conv1', 'res2', 'layer1', 'layer2', 'layer3'):
+                    m = getattr(enc, name, None)
+                    if m is not None:
+                        m.to(memory_format=torch.channels_last)
+                enc.channels_last = True
+        return self
+
     @property
     def device(self) -> torch.device:
         return self.pixel_mean.device

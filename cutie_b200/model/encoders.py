@@ -27,8 +27,11 @@ class PixelEncoder(nn.Module):
         trunk = ResNetTrunk(model_cfg.pixel_encoder.type)
         self.conv1, self.bn1 = trunk.conv1, trunk.bn1
         self.res2, self.layer2, self.layer3 = trunk.layer1, trunk.layer2, trunk.layer3
+        self.channels_last = False
 
     def forward(self, x):
+        if self.channels_last:
+            x = x.contiguous(memory_format=torch.channels_last)
         x = F.max_pool2d(F.relu(self.bn1(self.conv1(x)), inplace=True), 3, stride=2, padding=1)
         f4 = self.res2(x)
         f8 = self.layer2(f4)
@@ -67,6 +70,7 @@ class MaskEncoder(nn.Module):
         self.layer1, self.layer2, self.layer3 = trunk.layer1, trunk.layer2, trunk.layer3
         self.fuser = FeatureFusion(model_cfg.pixel_dim, model_cfg.mask_encoder.final_dim, model_cfg.value_dim)
         self.sensory_update = DeepSensoryUpdater(model_cfg.value_dim, model_cfg.sensory_dim)
+        self.channels_last = False
 
     def forward(self, image, pix_feat, sensory, masks, others, *, deep_update=True, chunk_size=-1):
         B, K = masks.shape[:2]
@@ -77,8 +81,12 @@ class MaskEncoder(nn.Module):
         values = []
         for lo, hi in spans:
             t = fold(g[:, lo:hi])
+            if self.channels_last:
+                t = t.contiguous(memory_format=torch.channels_last)
             t = F.relu(F.max_pool2d(self.bn1(self.conv1(t)), 3, stride=2, padding=1))
             t = self.layer3(self.layer2(self.layer1(t)))
+            if self.channels_last:
+                t = t.contiguous()
             v = self.fuser(pix_feat, unfold(t, B))
             values.append(v)
             if deep_update:

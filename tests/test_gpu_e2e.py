@@ -193,3 +193,25 @@ def test_cuda_graph_frame_path_matches_eager():
             assert float((pe - pg).abs().max()) < 1e-4
             assert _sizes(eager) == _sizes(graphed)
     assert graphed._graphs is not None and len(graphed._graphs._seg) >= 1
+
+
+def test_optimize_for_inference_keeps_parity():
+    """BN folding + channels-last trunks + CUDA graphs (the bench configuration) vs the plain eager model."""
+    from cutie_b200.config import default_config
+    from cutie_b200.inference.inference_core import InferenceCore
+    from oracle.synth import synthetic_video
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg = default_config(mem_every=2, max_mem_frames=3)
+    plain, fast = _net(cfg), _net(cfg).optimize_for_inference()
+    a, b = InferenceCore(plain, cfg=cfg), InferenceCore(fast, cfg=cfg, use_cuda_graphs=True)
+    frames, mask = synthetic_video(5, 96, 160, 3, seed=3)
+    with torch.inference_mode():
+        for ti in range(5):
+            x = frames[ti].cuda()
+            if ti == 0:
+                a.step(x, mask.cuda(), objects=[1, 2, 3]); b.step(x, mask.cuda(), objects=[1, 2, 3])
+            else:
+                pa, pb = a.step(x), b.step(x)
+                assert float((a.last_logits - b.last_logits).abs().max()) < 1e-3
+                assert float((pa - pb).abs().max()) < 1e-3
