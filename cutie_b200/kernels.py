@@ -402,6 +402,7 @@ def qt_aux_mask(pixel: torch.Tensor, w: torch.Tensor, b: torch.Tensor, B: int, K
     """mask_pred + sigmoid + aggregate + foreground test (a15) in one pass over pixel [B*K, E, HW].
     Returns (aux_logits f32 [B,K,HW], fg uint8 [B,K,HW], fg_count int32 [B*K])."""
     BK, E, HW = pixel.shape
+    assert pixel.is_contiguous(), 'pixel must be channel-major contiguous [B*K, E, HW]'
     dev = pixel.device
     logits = torch.empty(B, K, HW, dtype=torch.float32, device=dev)
     fg = torch.empty(B, K, HW, dtype=torch.uint8, device=dev)
@@ -423,6 +424,7 @@ def qt_pixel_to_query(qfold: torch.Tensor, pixel: torch.Tensor, pixel_pe: torch.
     Returns attn [M, E] (to be passed through the output projection by qt_linear)."""
     M, H, E = qfold.shape
     BK, _, HW = pixel.shape
+    assert pixel.is_contiguous() and pixel_pe.is_contiguous() and qfold.is_contiguous() and fg.is_contiguous()
     dev = pixel.device
     out = torch.empty(M, E, dtype=torch.float32, device=dev)
     L = lib()
@@ -448,6 +450,7 @@ def qt_query_to_pixel(kfold: torch.Tensor, kdots: torch.Tensor, vfold: torch.Ten
          out[:, p] = pixel[:, p] + out_bias + sum_{j,h} P[p,(j,h)] * vfold[(bk,j), h, :]
     """
     BK, E, HW = pixel.shape
+    assert pixel.is_contiguous() and pixel_pe.is_contiguous() and kfold.is_contiguous() and vfold.is_contiguous()
     if out is None:
         out = torch.empty_like(pixel)
     with _call('qt_query_to_pixel', 1):

@@ -125,7 +125,7 @@ class QueryTransformerBlock(nn.Module):
         pixel = K_.qt_query_to_pixel(kfold, kdots, vfold, rq.cross_attn.out_proj.bias, pixel, pixel_pe, Q, H)
         # --- PixelFFN (transformer_layers.py:127-136): cuDNN 3x3 convs, already channel-major
         BK = pixel.shape[0]
-        pixel = self.pixel_ffn.conv(pixel.view(BK, E, *hw)).view(BK, E, -1)
+        pixel = self.pixel_ffn.conv(pixel.view(BK, E, *hw)).reshape(BK, E, -1).contiguous()
         return x, pixel
 
 
@@ -168,9 +168,10 @@ class QueryTransformer(nn.Module):
         query_pe = K_.qt_linear(summ, self.summary_to_query_emb.weight, self.summary_to_query_emb.bias,
                                 summary_norm=True, residual=self.query_emb.weight, residual_mod=Q)
         # 1x1 projections (cuDNN) and the positional map; everything stays [BK, E, HW]
-        pix = self.pixel_init_proj(pixel).reshape(B * K, E, h * w)
+        # .contiguous(): upstream convolutions may hand over channels-last strides; the kernels read channel-major
+        pix = self.pixel_init_proj(pixel).reshape(B * K, E, h * w).contiguous()
         pe = self.spatial_pe.grid(h, w).reshape(h * w, E).t()                     # [E, HW]
-        pixel_pe = self.pixel_emb_proj(pixel).reshape(B * K, E, h * w) + pe
+        pixel_pe = (self.pixel_emb_proj(pixel).reshape(B * K, E, h * w) + pe).contiguous()
 
         logits, fg, cnt = self._aux(0, pix, B, K)
         aux_logits = [logits.view(B, K, h, w)]
