@@ -168,10 +168,27 @@ def run_ours(args, wl, rank, world, dev):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         tt = 1 + args.warmup
+        copy_stream = torch.cuda.Stream(dev)
+        cur = torch.cuda.current_stream(dev)
+        bufs = [torch.empty_like(frames_dev[0]) for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        free = [torch.cuda.Event() for _ in range(2)]
+
+        def upload(i):                       # pinned host frame -> device buffer i%2 on the copy stream
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(free[i % 2])
+                bufs[i % 2].copy_(frames_pin[tt + i], non_blocking=True)
+                ready[i % 2].record(copy_stream)
+        for ev in free:
+            ev.record(cur)
         e0.record()
+        upload(0)
         for i in range(args.steps):
-            img = frames_pin[tt + i].to(dev, non_blocking=True)
-            prob = proc2.step(img)
+            if i + 1 < args.steps:
+                upload(i + 1)                # next frame's H2D overlaps this frame's compute
+            cur.wait_event(ready[i % 2])
+            prob = proc2.step(bufs[i % 2])
+            free[i % 2].record(cur)
             host_out.copy_(proc2.output_prob_to_mask(prob).to(torch.uint8), non_blocking=True)
         e1.record()
         barrier()
