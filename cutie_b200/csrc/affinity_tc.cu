@@ -227,18 +227,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) affinity_tc_filter_kernel(const
         while (wm) {
           const int j = __ffs(wm) - 1;
           wm &= wm - 1;
-          // j is warp-uniform: a jump table picks the register, no TMEM re-read and no dynamic register indexing
-          uint32_t dv = r[0];
-          switch (j) {
-#define CUTIE_PICK(n) case n: dv = r[n]; break;
-            CUTIE_PICK(1) CUTIE_PICK(2) CUTIE_PICK(3) CUTIE_PICK(4) CUTIE_PICK(5) CUTIE_PICK(6) CUTIE_PICK(7)
-            CUTIE_PICK(8) CUTIE_PICK(9) CUTIE_PICK(10) CUTIE_PICK(11) CUTIE_PICK(12) CUTIE_PICK(13) CUTIE_PICK(14)
-            CUTIE_PICK(15) CUTIE_PICK(16) CUTIE_PICK(17) CUTIE_PICK(18) CUTIE_PICK(19) CUTIE_PICK(20) CUTIE_PICK(21)
-            CUTIE_PICK(22) CUTIE_PICK(23) CUTIE_PICK(24) CUTIE_PICK(25) CUTIE_PICK(26) CUTIE_PICK(27) CUTIE_PICK(28)
-            CUTIE_PICK(29) CUTIE_PICK(30) CUTIE_PICK(31)
-#undef CUTIE_PICK
-            default: break;
-          }
+          uint32_t dv;
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(dv) : "r"(taddr + (uint32_t)j));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           if ((mask >> j) & 1u) {
             const float d = __uint_as_float(dv);
             const int col = cg * 32 + j;
