@@ -112,6 +112,9 @@ def run_ours(args, wl, rank, world, dev):
     from cutie_b200.inference.inference_core import InferenceCore
     from oracle.synth import synthetic_video
     K_.lib()                                             # fail loudly if the CUDA library is missing
+    if args.no_key_image:
+        import cutie_b200.inference.memory_bank as MB
+        MB.USE_KEY_IMAGE = False
     torch.backends.cudnn.benchmark = True
     cfg = make_cfg(wl)
     net = make_net(cfg).to(dev)
@@ -148,6 +151,8 @@ def run_ours(args, wl, rank, world, dev):
         th.start()
         K_.PROFILE = []
         launches0 = K_.LAUNCH_COUNT
+        if args.phase_timing:
+            K_.phase_timing(True)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         for _ in range(args.steps):
@@ -157,6 +162,17 @@ def run_ours(args, wl, rank, world, dev):
         stop.set(); th.join()
         launches = K_.LAUNCH_COUNT - launches0
         prof, K_.PROFILE = K_.PROFILE, None
+        phases = []
+        if args.phase_timing:
+            K_.phase_timing(False)
+            phases = [K_.phase_times(i) for i in range(min(args.steps, 60))]
+            phases = [p for p in phases if p]
+            if phases:
+                n = min(len(p) for p in phases)
+                avg = [sum(p[i] for p in phases) / len(phases) for i in range(n)]
+                log('[phases] affinity plan, ms per launch (filter, select, ..., re-rank): '
+                    + ' '.join(f'{x:.3f}' for x in avg) + f'  sum {sum(avg):.3f}')
+                phases = avg
         ms_total = ev0.elapsed_time(ev1)
     kernel_ms = {}
     for name, a, b in prof:
@@ -197,7 +213,7 @@ def run_ours(args, wl, rank, world, dev):
     if world > 1:
         torch.distributed.all_reduce(times, op=torch.distributed.ReduceOp.MAX)
     ms_total, ms_e2e = float(times[0]), float(times[1])
-    return dict(ms_total=ms_total, ms_e2e=ms_e2e, kernel_ms=kernel_ms, launches=launches, n_tokens=n_tokens,
+    return dict(phases=phases, image_levels=K_.image_level_launches(), ms_total=ms_total, ms_e2e=ms_e2e, kernel_ms=kernel_ms, launches=launches, n_tokens=n_tokens,
                 clocks=summarize_clocks(samples), h2d=frames_pin[0].numel() * 4, d2h=host_out.numel())
 
 
@@ -247,6 +263,8 @@ def main():
     ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-optimize', action='store_true', help='skip CUTIE.optimize_for_inference()')
+    ap.add_argument('--phase-timing', action='store_true', help='per-launch device times inside cutie_affinity_topk')
+    ap.add_argument('--no-key-image', action='store_true', help='convert memory keys inside the filter (no operand image)')
     ap.add_argument('--no-graphs', action='store_true', help='eager launches only (no CUDA-graph frame regions)')
     ap.add_argument('--cpu-seconds', type=float, default=150.0)
     args = ap.parse_args()
@@ -355,7 +373,8 @@ def main():
             'config': config, 'clocks': res['clocks'],
             'e2e': {'value': fps_e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': res['h2d'],
                     'd2h_bytes_per_step': res['d2h'], 'ms_per_step': res['ms_e2e'] / args.steps},
-            'gpu_launches': res['launches'], 'roofline': roof, 'cpu_baseline': cpu, 'kernels': kshare}
+            'gpu_launches': res['launches'], 'roofline': roof, 'cpu_baseline': cpu, 'kernels': kshare,
+            'affinity_phases_ms': res['phases'] or None, 'key_image_levels': res['image_levels']}
     emit(line)
 
 

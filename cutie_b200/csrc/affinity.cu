@@ -385,6 +385,7 @@ constexpr int TC_CAP = 4096;           // candidate slots per query (also the la
 constexpr int TC_CAP_BIG = 16384;      // slots per query used for the candidate lists (overflow => exhaustive rescan of that query)
 
 static long long g_tc_min_override = -1;
+static long long g_image_level_launches = 0;     // filter levels served from a key image (tests / diagnostics)
 
 static long long tc_min_tokens() {
   if (g_tc_min_override >= 0) return g_tc_min_override;
@@ -483,9 +484,43 @@ static int run_exact(const ScanParams& base, long long B, int nsplit, int* out_i
   return 0;
 }
 
+// Optional per-phase timing of the filtered plan (diagnostics: bench.py --phase-timing).  Events are recorded on
+// the caller's stream, so they measure the kernels in situ; nothing synchronises until the times are read.
+constexpr int PH_RING = 64, PH_MAX = 16;
+static bool g_phase_on = false;
+static cudaEvent_t g_phase_ev[PH_RING][PH_MAX];
+static int g_phase_n[PH_RING];
+static long long g_phase_calls = 0;
+static bool g_phase_init = false;
+
+static void phase_mark(int slot, cudaStream_t st) {
+  if (!g_phase_on || slot < 0) return;
+  if (g_phase_n[slot] < PH_MAX) cudaEventRecord(g_phase_ev[slot][g_phase_n[slot]++], st);
+}
+static int phase_begin(cudaStream_t st) {
+  if (!g_phase_on) return -1;
+  if (!g_phase_init) {
+    for (int i = 0; i < PH_RING; ++i)
+      for (int j = 0; j < PH_MAX; ++j) cudaEventCreate(&g_phase_ev[i][j]);
+    g_phase_init = true;
+  }
+  const int slot = (int)(g_phase_calls++ % PH_RING);
+  g_phase_n[slot] = 0;
+  phase_mark(slot, st);
+  return slot;
+}
+
+// Optional precomputed operand images of the arenas the segments live in (cutie_bank_key_image).
+struct ImageArgs {
+  bool on;
+  const float* img[kMaxSeg];
+  long long bs[kMaxSeg];      // batch stride (floats)
+  long long phys[kMaxSeg];    // physical index of the segment's first token inside its arena
+};
+
 // One filter level: zero the per-query counters, tcgen05 filter over the stride-`stride` sample.
 static int run_filter_level(const ScanParams& base, long long B, long long stride, const float* emax_in, char* ws,
-                            const WsLayout& wl, float* dbg_energy, cudaStream_t st) {
+                            const WsLayout& wl, float* dbg_energy, const ImageArgs& ia, cudaStream_t st) {
   TcFilterParams fp;
   memset(&fp, 0, sizeof(fp));
   fp.segs = base.segs;
@@ -505,6 +540,24 @@ static int run_filter_level(const ScanParams& base, long long B, long long strid
   fp.dmax = (float*)(ws + wl.dmax);
   fp.cap = TC_CAP_BIG;
   fp.dbg_energy = dbg_energy;
+  if (ia.on && stride == 1 && emax_in != nullptr) {
+    // the whole bank, one bulk copy per physical 128-token tile of each segment's arena
+    fp.use_img = 1;
+    long long cum = 0;
+    for (int s = 0; s < base.segs.nseg; ++s) {
+      const long long n = base.segs.begin[s + 1] - base.segs.begin[s];
+      fp.img[s] = ia.img[s];
+      fp.img_bs[s] = ia.bs[s];
+      fp.img_tile0[s] = ia.phys[s] / 128;
+      fp.img_lo0[s] = (int)(ia.phys[s] % 128);
+      fp.img_tcum[s] = cum;
+      cum += n > 0 ? (fp.img_lo0[s] + n + 127) / 128 : 0;
+    }
+    for (int s = base.segs.nseg; s <= kMaxSeg; ++s) fp.img_tcum[s] = cum;
+    fp.nsplit = tc_split_count(B, base.Q, cum * 128);
+    fp.tiles_per_split = (int)((cum + fp.nsplit - 1) / fp.nsplit);
+    ++g_image_level_launches;
+  }
   cudaError_t e = cudaMemsetAsync(ws + wl.count, 0, (size_t)(wl.emax0 - wl.count), st);   // count + dmax
   if (e != cudaSuccess) return set_cuda_error("cudaMemsetAsync", e);
   return launch_tc_filter(fp, B, st);
@@ -512,13 +565,15 @@ static int run_filter_level(const ScanParams& base, long long B, long long strid
 
 static int run_filtered(const ScanParams& base, long long B, const Plan& pl, char* ws, const WsLayout& wl,
                         int* out_idx, float* out_w, float* out_sim, unsigned long long* usage_acc,
-                        float* dbg_energy, cudaStream_t st) {
+                        float* dbg_energy, const ImageArgs& ia, cudaStream_t st) {
   float* emax[2] = {(float*)(ws + wl.emax0), (float*)(ws + wl.emax1)};
   const float* emax_in = nullptr;
+  const int ph = phase_begin(st);
   for (int l = 0; l < pl.levels; ++l) {
     const bool last = (l == pl.levels - 1);
-    int rc = run_filter_level(base, B, pl.stride[l], emax_in, ws, wl, last ? dbg_energy : nullptr, st);
+    int rc = run_filter_level(base, B, pl.stride[l], emax_in, ws, wl, last ? dbg_energy : nullptr, ia, st);
     if (rc) return rc;
+    phase_mark(ph, st);
     if (!last) {
       SelectParams sp;
       sp.Q = base.Q;
@@ -530,6 +585,7 @@ static int run_filtered(const ScanParams& base, long long B, const Plan& pl, cha
       sp.emax_out = emax[l & 1];
       rc = launch_level_select(sp, B, base.kpad, st);
       if (rc) return rc;
+      phase_mark(ph, st);
       emax_in = emax[l & 1];
     }
   }
@@ -549,7 +605,9 @@ static int run_filtered(const ScanParams& base, long long B, const Plan& pl, cha
   rp.out_w = out_w;
   rp.out_sim = out_sim;
   rp.usage_acc = usage_acc;
-  return launch_rerank(rp, B, st);
+  const int rc = launch_rerank(rp, B, st);
+  phase_mark(ph, st);
+  return rc;
 }
 
 }  // namespace cutie
@@ -568,6 +626,25 @@ extern "C" size_t cutie_affinity_workspace_bytes(int64_t B, int64_t Q, int64_t n
 extern "C" void cutie_set_tc_min_tokens(int64_t n) { g_tc_min_override = n; }
 
 // Which plan cutie_affinity_topk will use: 1 = exact scan only, 2/3 = tcgen05 filter levels (see make_plan).
+// Per-phase device times (ms) of a filtered cutie_affinity_topk call: filter level, threshold select, ..., re-rank.
+// cutie_debug_phase_timing(1) starts recording (a ring of the last 64 calls); cutie_debug_phase_times(calls_ago, ...)
+// waits for that call's last event and returns the number of phases written.
+extern "C" void cutie_debug_phase_timing(int enable) { g_phase_on = enable != 0; }
+extern "C" int cutie_debug_phase_times(int64_t calls_ago, float* out_ms, int max_phases) {
+  if (!g_phase_init || calls_ago < 0 || calls_ago >= PH_RING || calls_ago >= g_phase_calls || !out_ms) return 0;
+  const int slot = (int)((g_phase_calls - 1 - calls_ago) % PH_RING);
+  const int n = g_phase_n[slot];
+  if (n < 2) return 0;
+  if (cudaEventSynchronize(g_phase_ev[slot][n - 1]) != cudaSuccess) return 0;
+  int k = 0;
+  for (int i = 1; i < n && k < max_phases; ++i, ++k)
+    if (cudaEventElapsedTime(&out_ms[k], g_phase_ev[slot][i - 1], g_phase_ev[slot][i]) != cudaSuccess) return k;
+  return k;
+}
+
+// How many filter levels have been served from a key image so far in this process (diagnostics / tests).
+extern "C" int64_t cutie_debug_image_level_launches(void) { return g_image_level_launches; }
+
 extern "C" int cutie_affinity_plan_levels(int64_t n_total, int top_k) { return make_plan(n_total, top_k).levels; }
 
 static int fill_scan_params(ScanParams& sp, int num_segments, const void* const* seg_key,
@@ -600,12 +677,14 @@ static int fill_scan_params(ScanParams& sp, int num_segments, const void* const*
   return 0;
 }
 
-extern "C" int cutie_affinity_topk(int num_segments, const void* const* seg_key, const void* const* seg_shrinkage,
-                                   const int64_t* seg_len, const int64_t* seg_key_bstride,
-                                   const int64_t* seg_shr_bstride, const float* qk, const float* qe, int64_t B,
-                                   int64_t CK, int64_t Q, int top_k, int kpad, int32_t* out_idx, float* out_w,
-                                   float* out_sim, unsigned long long* usage_acc, int64_t n_total, void* workspace,
-                                   size_t workspace_bytes, void* stream) {
+extern "C" int cutie_affinity_topk_img(int num_segments, const void* const* seg_key,
+                                       const void* const* seg_shrinkage, const int64_t* seg_len,
+                                       const int64_t* seg_key_bstride, const int64_t* seg_shr_bstride,
+                                       const void* const* seg_key_image, const int64_t* seg_image_bstride,
+                                       const int64_t* seg_phys_begin, const float* qk, const float* qe, int64_t B,
+                                       int64_t CK, int64_t Q, int top_k, int kpad, int32_t* out_idx, float* out_w,
+                                       float* out_sim, unsigned long long* usage_acc, int64_t n_total,
+                                       void* workspace, size_t workspace_bytes, void* stream) {
   CUTIE_REQUIRE(num_segments >= 1 && num_segments <= kMaxSeg, "1..4 segments");
   CUTIE_REQUIRE(CK == CKD, "CK must be 64");
   CUTIE_REQUIRE(kpad == 32 || kpad == 64, "kpad must be 32 or 64");
@@ -628,7 +707,32 @@ extern "C" int cutie_affinity_topk(int num_segments, const void* const* seg_key,
     sp.part_idx = (int*)(ws + wl.part + (size_t)B * ns0 * Q * kpad * 4);
     return run_exact(sp, B, ns0, out_idx, out_w, out_sim, usage_acc, st);
   }
-  return run_filtered(sp, B, pl, ws, wl, out_idx, out_w, out_sim, usage_acc, nullptr, st);
+  ImageArgs ia;
+  memset(&ia, 0, sizeof(ia));
+  if (seg_key_image) {
+    CUTIE_REQUIRE(seg_image_bstride && seg_phys_begin, "image strides / physical offsets missing");
+    ia.on = true;
+    for (int s = 0; s < num_segments; ++s) {
+      if (seg_len[s] > 0 && !seg_key_image[s]) ia.on = false;          // a segment without an image: convert on the fly
+      CUTIE_REQUIRE(seg_phys_begin[s] >= 0, "negative physical offset");
+      CUTIE_REQUIRE(((uintptr_t)seg_key_image[s] & 15) == 0, "key image must be 16-byte aligned");
+      ia.img[s] = (const float*)seg_key_image[s];
+      ia.bs[s] = seg_image_bstride[s];
+      ia.phys[s] = seg_phys_begin[s];
+    }
+  }
+  return run_filtered(sp, B, pl, ws, wl, out_idx, out_w, out_sim, usage_acc, nullptr, ia, st);
+}
+
+extern "C" int cutie_affinity_topk(int num_segments, const void* const* seg_key, const void* const* seg_shrinkage,
+                                   const int64_t* seg_len, const int64_t* seg_key_bstride,
+                                   const int64_t* seg_shr_bstride, const float* qk, const float* qe, int64_t B,
+                                   int64_t CK, int64_t Q, int top_k, int kpad, int32_t* out_idx, float* out_w,
+                                   float* out_sim, unsigned long long* usage_acc, int64_t n_total, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  return cutie_affinity_topk_img(num_segments, seg_key, seg_shrinkage, seg_len, seg_key_bstride, seg_shr_bstride,
+                                 nullptr, nullptr, nullptr, qk, qe, B, CK, Q, top_k, kpad, out_idx, out_w, out_sim,
+                                 usage_acc, n_total, workspace, workspace_bytes, stream);
 }
 
 // Test hook: TF32 energies E[b,q,n] = -8 S of the tcgen05 filter for the whole bank (single level, no
@@ -660,7 +764,9 @@ extern "C" int cutie_debug_tc_energy(int num_segments, const void* const* seg_ke
   pl.levels = 1;
   pl.stride[0] = 1;
   char* ws = (char*)workspace;
-  return run_filtered(sp, B, pl, ws, wl, (int*)(ws + o_idx), (float*)(ws + o_w), nullptr, nullptr, dbg_energy,
+  ImageArgs ia;
+  memset(&ia, 0, sizeof(ia));
+  return run_filtered(sp, B, pl, ws, wl, (int*)(ws + o_idx), (float*)(ws + o_w), nullptr, nullptr, dbg_energy, ia,
                       (cudaStream_t)stream);
 }
 

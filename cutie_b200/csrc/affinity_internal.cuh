@@ -22,6 +22,14 @@ struct TcFilterParams {
   float* dmax;             // [B][Q] largest error bound used (atomicMax on the bit pattern); zeroed by the caller
   int cap;
   float* dbg_energy;       // optional [B][Q][samp_count] tf32 energies (tests)
+  // Image path (stride-1 level only): per segment the precomputed operand image of the arena it lives in
+  // (cutie_bank_key_image), addressed by physical 128-token tile.
+  int use_img;
+  const float* img[kMaxSeg];
+  long long img_bs[kMaxSeg];       // batch stride (floats)
+  long long img_tile0[kMaxSeg];    // first physical tile of the segment
+  int img_lo0[kMaxSeg];            // row of the segment's first token inside that tile
+  long long img_tcum[kMaxSeg + 1]; // prefix sums of the segments' tile counts
 };
 
 struct SelectParams {

@@ -22,20 +22,16 @@
 // flight while the other group converts); warp 12 TMEM allocator + single-thread MMA issuer.
 #include "topk_common.cuh"
 #include "affinity_internal.cuh"
+#include "tc_operand.cuh"
 
 namespace cutie {
 
-constexpr int QT = 128;                 // queries per CTA (MMA M)
-constexpr int KTILE = 128;              // memory tokens per tile (MMA N)
-constexpr int BLK_BYTES = 128 * 128;    // one SW128 K-block: 128 rows x 128 B
-constexpr int TAIL_BYTES = 128 * 32;    // tail block: 128 rows x 8 tf32
-constexpr int OPER_BYTES = 4 * BLK_BYTES + TAIL_BYTES;   // 69632
+constexpr int QT = TC_QT;               // queries per CTA (MMA M)
+constexpr int KTILE = TC_KTILE;         // memory tokens per tile (MMA N)
+constexpr int BLK_BYTES = TC_BLK_BYTES;
+constexpr int OPER_BYTES = TC_OPER_BYTES;
 constexpr int TC_THREADS = 416;   // 4 epilogue + 2 x 4 producer + 1 MMA warps
-// Query operands are rounded to TF32 (RN, 2^-11) once per CTA; memory tokens are fed as raw fp32 and the tensor core
-// ignores their low 13 mantissa bits (<= 2^-10), which saves ~600 conversion instructions per tile.  Product error
-// <= 2^-11 + 2^-10 + 2^-21 = 1.466e-3; + fp32 accumulation over 136 terms + rounding of the bound's own operands.
-constexpr float TF32_EPS = 1.65e-3f;
-constexpr float BIG_E = 1e30f;
+constexpr float TF32_EPS = TC_TF32_EPS;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -72,11 +68,6 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uin
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ float fsqrt_approx(float x) {
-  float r;
-  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
 __device__ __forceinline__ float to_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -103,13 +94,41 @@ __device__ __forceinline__ uint64_t desc_tail(uint32_t addr) {
   d |= (uint64_t)1 << 46;
   return d;                                      // layout type 0 = SWIZZLE_NONE
 }
-// byte offsets inside an operand buffer
-__device__ __forceinline__ int off_main(int row, int elem) {     // elem in [0,128): 4 K-blocks of 32
-  const int blk = elem >> 5, chunk = (elem & 31) >> 2, within = elem & 3;
-  return blk * BLK_BYTES + row * 128 + ((chunk ^ (row & 7)) << 4) + within * 4;
+// Bulk-copy path (IMG): tiles are the bank's precomputed operand image (cutie_bank_key_image), addressed by PHYSICAL
+// 128-token tile of the arena each segment lives in; rows outside the segment are masked in the epilogue.
+struct ImgTile {
+  const unsigned char* src;   // 69632 contiguous bytes: the tile exactly as the MMA wants it in shared memory
+  int lo, hi;                 // rows [lo, hi) of the tile belong to the segment
+  long long lbase;            // bank (logical) index of row 0
+};
+__device__ __forceinline__ ImgTile img_tile(const TcFilterParams& p, int b, long long g) {
+  int s = 0;
+#pragma unroll
+  for (int i = 1; i < kMaxSeg; ++i)
+    if (i < p.segs.nseg && g >= p.img_tcum[i]) s = i;
+  const long long j = g - p.img_tcum[s];
+  const long long n = p.segs.begin[s + 1] - p.segs.begin[s];
+  const long long lo0 = p.img_lo0[s];
+  const long long a = lo0 - j * KTILE, e = lo0 + n - j * KTILE;
+  ImgTile t;
+  t.lo = a < 0 ? 0 : (int)a;
+  t.hi = e > KTILE ? KTILE : (int)e;
+  t.lbase = p.segs.begin[s] - lo0 + j * KTILE;
+  t.src = reinterpret_cast<const unsigned char*>(p.img[s] + (long long)b * p.img_bs[s]) +
+          (p.img_tile0[s] + j) * (long long)OPER_BYTES;
+  return t;
 }
-__device__ __forceinline__ int off_tail(int row, int elem) {     // elem in [0,8)
-  return 4 * BLK_BYTES + (elem >> 2) * 2048 + (row >> 3) * 128 + (row & 7) * 16 + (elem & 3) * 4;
+__device__ __forceinline__ unsigned range_mask32(int a, int b) {      // bits [a, b) of a 32-bit word (any ints)
+  const unsigned hi = b >= 32 ? 0xffffffffu : (b <= 0 ? 0u : ((1u << b) - 1u));
+  const unsigned lo = a <= 0 ? 0xffffffffu : (a >= 32 ? 0u : ~((1u << a) - 1u));
+  return hi & lo;
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
 struct TcSmemTail {
@@ -119,7 +138,7 @@ struct TcSmemTail {
   uint32_t tmem_base;
 };
 
-template <bool DBG>
+template <bool DBG, bool IMG>
 __global__ void __launch_bounds__(TC_THREADS, 1) affinity_tc_filter_kernel(const TcFilterParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* A = smem;                              // queries
@@ -128,14 +147,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) affinity_tc_filter_kernel(const
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.z, split = blockIdx.y;
   const long long q0 = (long long)blockIdx.x * QT;
-  const long long i_begin = (long long)split * p.tiles_per_split * KTILE;
+  // non-IMG: tiles cover sample indices [i_begin, i_end); IMG: physical image tiles [g_begin, g_begin + ntiles)
+  const long long g_begin = (long long)split * p.tiles_per_split;
+  const long long i_begin = g_begin * KTILE;
   long long i_end = i_begin + (long long)p.tiles_per_split * KTILE;
   if (i_end > p.samp_count) i_end = p.samp_count;
-  const int ntiles = i_end > i_begin ? (int)((i_end - i_begin + KTILE - 1) / KTILE) : 0;
+  int ntiles = i_end > i_begin ? (int)((i_end - i_begin + KTILE - 1) / KTILE) : 0;
+  if (IMG) {
+    const long long left = p.img_tcum[p.segs.nseg] - g_begin;
+    ntiles = left <= 0 ? 0 : (left < p.tiles_per_split ? (int)left : p.tiles_per_split);
+  }
 
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
-      mbar_init(smem_u32(&T.full[s]), 128);
+      mbar_init(smem_u32(&T.full[s]), IMG ? 1 : 128);   // IMG: one arrive.expect_tx + the bulk copy's bytes
       mbar_init(smem_u32(&T.empty[s]), 1);
       mbar_init(smem_u32(&T.tfull[s]), 1);
       mbar_init(smem_u32(&T.tempty[s]), 128);
@@ -193,8 +218,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) affinity_tc_filter_kernel(const
       mbar_wait(smem_u32(&T.tfull[a]), (t >> 1) & 1);
       tc_fence_after();
       const float thr = (q < p.Q) ? emax : -CUDART_INF_F;
-      const long long ibase = i_begin + (long long)t * KTILE;
-      const int nvalid = (int)((i_end - ibase) < KTILE ? (i_end - ibase) : KTILE);
+      long long ibase = i_begin + (long long)t * KTILE;      // IMG: bank index of row 0 (may precede the segment)
+      int vlo = 0, nvalid = (int)((i_end - ibase) < KTILE ? (i_end - ibase) : KTILE);   // valid rows [vlo, nvalid)
+      if (IMG) {
+        const ImgTile it = img_tile(p, b, g_begin + t);
+        ibase = it.lbase;
+        vlo = it.lo;
+        nvalid = it.hi;
+      }
 #pragma unroll 1
       for (int cg = 0; cg < 4; ++cg) {
         uint32_t r[32];
@@ -213,15 +244,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) affinity_tc_filter_kernel(const
         if (DBG) {
           if (q < p.Q)
             for (int j = 0; j < 32; ++j)
-              if (ibase + cg * 32 + j < p.samp_count)
+              if (cg * 32 + j >= vlo && cg * 32 + j < nvalid && ibase + cg * 32 + j < p.samp_count)
                 p.dbg_energy[((long long)b * p.Q + q) * p.samp_count + ibase + cg * 32 + j] = __uint_as_float(r[j]);
         }
         // branch-free per-lane bitmask of passing columns (2 instructions per element) ...
         unsigned mask = 0u;
 #pragma unroll
         for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(r[j]) < thr) ? (1u << j) : 0u;
-        const int left = nvalid - cg * 32;                       // columns of this group that hold real tokens
-        mask &= left >= 32 ? 0xffffffffu : (left <= 0 ? 0u : ((1u << left) - 1u));
+        mask &= range_mask32(vlo - cg * 32, nvalid - cg * 32);   // columns of this group that hold real tokens
         // ... and a rare warp-uniform slow path that re-reads just the passing columns from TMEM
         unsigned wm = __reduce_or_sync(0xffffffffu, mask);
         while (wm) {
@@ -233,8 +263,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) affinity_tc_filter_kernel(const
           if ((mask >> j) & 1u) {
             const float d = __uint_as_float(dv);
             const int col = cg * 32 + j;
-            const float s_ = T.rowP[t & 3][col] + T.rowR[t & 3][col] * vq;
-            const float e_hi = d + 2.01f * TF32_EPS * s_ * s_;          // an UPPER bound of the exact energy
+            float e_hi = d;
+            if (!IMG) {      // IMG serves the last level only: its candidates are re-ranked exactly, no bound needed
+              const float s_ = T.rowP[t & 3][col] + T.rowR[t & 3][col] * vq;
+              e_hi = d + 2.01f * TF32_EPS * s_ * s_;                    // an UPPER bound of the exact energy
+            }
             int pos;
             if (all_pass) {
               pos = (int)(ibase + col);
@@ -245,8 +278,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) affinity_tc_filter_kernel(const
               pos = blk_base + blk_used++;
             }
             if (pos < p.cap) {
-              my_idx[pos] = (int)(p.samp_begin + (ibase + col) * p.samp_stride);
-              my_e[pos] = e_hi;
+              my_idx[pos] = IMG ? (int)(ibase + col) : (int)(p.samp_begin + (ibase + col) * p.samp_stride);
+              if (!IMG) my_e[pos] = e_hi;
             }
           }
         }
@@ -256,7 +289,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) affinity_tc_filter_kernel(const
     }
     if (!all_pass && blk_used < 32)
       for (int u = blk_used; u < 32; ++u)
-        if (blk_base + u < p.cap) { my_idx[blk_base + u] = -1; my_e[blk_base + u] = CUDART_INF_F; }
+        if (blk_base + u < p.cap) { my_idx[blk_base + u] = -1; if (!IMG) my_e[blk_base + u] = CUDART_INF_F; }
+  } else if (warp < 12 && IMG) {
+    // ============ producer (image path): one thread, one 68 KB bulk copy per tile ============
+    if (tid == 128) {
+      for (int t = 0; t < ntiles; ++t) {
+        const int s = t & 1;
+        mbar_wait(smem_u32(&T.empty[s]), ((t >> 1) & 1) ^ 1);
+        const ImgTile it = img_tile(p, b, g_begin + t);
+        const uint32_t bar = smem_u32(&T.full[s]);
+        mbar_arrive_expect_tx(bar, (uint32_t)OPER_BYTES);
+        bulk_g2s(smem_u32(Bst + s * OPER_BYTES), it.src, (uint32_t)OPER_BYTES, bar);
+      }
+    }
   } else if (warp < 12) {
     // ============ producers: 16 lanes per token row (coalesced 256-B rows), next tile prefetched ============
     const int grp = (warp - 4) >> 2;     // producer group 0 handles even tiles (stage 0), group 1 odd tiles
@@ -307,28 +352,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) affinity_tc_filter_kernel(const
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const int row = r0 + 8 * j;
-        const bool valid = shr[j] >= 0.f;
-        const float sh = valid ? shr[j] : 0.f;
-        const float4 v = kf[j];
-        const float4 ln = make_float4(sh * v.x, sh * v.y, sh * v.z, sh * v.w);
-        float n2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
-        n2 += __shfl_xor_sync(0xffffffffu, n2, 1);
-        n2 += __shfl_xor_sync(0xffffffffu, n2, 2);
-        n2 += __shfl_xor_sync(0xffffffffu, n2, 4);
-        n2 += __shfl_xor_sync(0xffffffffu, n2, 8);
-        *reinterpret_cast<float4*>(Bs + off_main(row, 4 * c4)) = make_float4(ln.x * v.x, ln.y * v.y, ln.z * v.z, ln.w * v.w);
-        *reinterpret_cast<float4*>(Bs + off_main(row, 64 + 4 * c4)) = ln;
-        // per-row error-bound factors (rounded up a hair) and the tail block; all 16 lanes of the row hold the
-        // same values, lane c4 == 0 stores them (small predicated body, no divergence region)
-        const float Pn = fsqrt_approx(sh * n2) * 1.002f, Rn = fsqrt_approx(sh) * 1.002f;
-        const float4 t0 = make_float4(sh, valid ? 0.f : BIG_E, sh, -TF32_EPS * Pn * Pn);
-        const float4 t1 = make_float4(-2.f * TF32_EPS * Pn * Rn, -TF32_EPS * Rn * Rn, 0.f, 0.f);
+        float Pn, Rn;
+        store_key_row_operand(Bs, row, c4, kf[j], shr[j], Pn, Rn);      // tc_operand.cuh (shared with the image builder)
         if (c4 == 0) {
           T.rowP[t & 3][row] = Pn;
           T.rowR[t & 3][row] = Rn;
-          // tail: [shr, BIG if invalid, shr, -eps P^2 | -2 eps P R, -eps R^2, 0, 0]   x   [b2_hi, 1, b2_lo, 1 | v, v^2, 0, 0]
-          *reinterpret_cast<float4*>(Bs + off_tail(row, 0)) = t0;
-          *reinterpret_cast<float4*>(Bs + off_tail(row, 4)) = t1;
         }
       }
       fence_proxy_async();
@@ -481,15 +509,23 @@ int launch_tc_filter(const TcFilterParams& p, long long B, cudaStream_t st) {
   static bool attr_done = false;
   const size_t smem = tc_filter_smem_bytes();
   if (!attr_done) {
-    cudaFuncSetAttribute(affinity_tc_filter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(affinity_tc_filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(affinity_tc_filter_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(affinity_tc_filter_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(affinity_tc_filter_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(affinity_tc_filter_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_done = true;
   }
   dim3 grid((unsigned)((p.Q + QT - 1) / QT), (unsigned)p.nsplit, (unsigned)B);
-  if (p.dbg_energy)
-    affinity_tc_filter_kernel<true><<<grid, TC_THREADS, smem, st>>>(p);
+  if (p.use_img) {
+    if (!p.emax_in) return fail(-1, "%s: the image path needs a previous level's thresholds", "affinity_tc_filter_kernel");
+    if (p.dbg_energy)
+      affinity_tc_filter_kernel<true, true><<<grid, TC_THREADS, smem, st>>>(p);
+    else
+      affinity_tc_filter_kernel<false, true><<<grid, TC_THREADS, smem, st>>>(p);
+  } else if (p.dbg_energy)
+    affinity_tc_filter_kernel<true, false><<<grid, TC_THREADS, smem, st>>>(p);
   else
-    affinity_tc_filter_kernel<false><<<grid, TC_THREADS, smem, st>>>(p);
+    affinity_tc_filter_kernel<false, false><<<grid, TC_THREADS, smem, st>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error("affinity_tc_filter_kernel", e);
   return 0;

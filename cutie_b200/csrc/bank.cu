@@ -3,8 +3,33 @@
 #include <math_constants.h>
 
 #include "common.cuh"
+#include "tc_operand.cuh"
 
 namespace cutie {
+
+// Operand image of the tcgen05 affinity filter for tokens [phys0, phys0 + n) of an arena: every 128-token physical
+// tile is stored exactly as the filter wants it in shared memory (tc_operand.cuh), so the filter fetches a tile
+// with ONE 68 KB bulk copy instead of converting 128 fp32 rows per tile per query block.
+// 16 lanes per token (coalesced 256-B key rows), 16 tokens per 256-thread CTA.
+__global__ void __launch_bounds__(256) key_image_kernel(const float* __restrict__ key, long long key_bs,
+                                                        const float* __restrict__ shr, long long shr_bs,
+                                                        long long phys0, long long n, unsigned char* __restrict__ img,
+                                                        long long img_bs_bytes) {
+  const int b = blockIdx.y;
+  const int c4 = threadIdx.x & 15;
+  const long long i = (long long)blockIdx.x * 16 + (threadIdx.x >> 4);
+  const bool live = i < n;
+  const long long phys = phys0 + (live ? i : 0);
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  float sh = 0.f;
+  if (live) {
+    v = __ldg(reinterpret_cast<const float4*>(key + (long long)b * key_bs + phys * 64) + c4);
+    sh = __ldg(shr + (long long)b * shr_bs + phys);
+  }
+  unsigned char* tile = img + (long long)b * img_bs_bytes + (phys >> 7) * (long long)TC_OPER_BYTES;
+  float Pn, Rn;
+  store_key_row_operand(tile, (int)(phys & 127), c4, v, sh, Pn, Rn, live);   // dead rows: shuffles only, no stores
+}
 
 // out[b][c][r] = in[b][r][c]   in: [B, R, C] (row stride C), out: [B, C, R]
 __global__ void transpose_kernel(const float* __restrict__ in, long long in_bs, float* __restrict__ out,
@@ -187,6 +212,21 @@ extern "C" int cutie_bank_append(const float* src, int64_t src_bstride, float* d
                                  int64_t B, int64_t C, int64_t n, void* stream) {
   // src [B, C, n] -> dst [B, n, C]
   return launch_transpose(src, src_bstride, dst_rows, dst_bstride, B, C, n, stream, __func__);
+}
+
+extern "C" int cutie_bank_key_image(const float* key_arena, int64_t key_bstride, const float* shr_arena,
+                                    int64_t shr_bstride, int64_t B, int64_t phys_begin, int64_t n, float* image,
+                                    int64_t image_bstride, int64_t image_tiles, void* stream) {
+  CUTIE_REQUIRE(key_arena && shr_arena && image && B >= 1 && phys_begin >= 0 && n >= 0, "null/negative argument");
+  CUTIE_REQUIRE((phys_begin + n + 127) / 128 <= image_tiles, "image too small for the token range");
+  CUTIE_REQUIRE(((uintptr_t)image & 15) == 0 && ((uintptr_t)key_arena & 15) == 0, "16-byte alignment required");
+  if (n == 0) return 0;
+  dim3 grid((unsigned)((n + 15) / 16), (unsigned)B);
+  key_image_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(key_arena, key_bstride, shr_arena, shr_bstride, phys_begin,
+                                                         n, reinterpret_cast<unsigned char*>(image),
+                                                         image_bstride * 4);
+  CUTIE_CHECK_LAUNCH();
+  return 0;
 }
 
 extern "C" int cutie_bank_export(const float* rows, int64_t rows_bstride, float* dst, int64_t dst_bstride, int64_t B,

@@ -26,6 +26,11 @@ from cutie_b200 import kernels as K_
 from cutie_b200.kernels import BankSegment
 
 
+# The arenas keep a tcgen05 operand image of their keys (kernels.bank_key_image); False = the affinity filter
+# converts the fp32 rows inside the kernel instead (A/B switch for bench.py --no-key-image and tests).
+USE_KEY_IMAGE = True
+
+
 class TokenArena:
     """A set of same-length token-major arrays [B, capacity, C_i] with ring semantics."""
 
@@ -39,6 +44,9 @@ class TokenArena:
         self.hint = 0
         self.B = None
         self.device = None
+        # tcgen05 operand image of the 'key'/'shr' arrays (kernels.bank_key_image) + physical runs not yet imaged
+        self.key_image: Optional[torch.Tensor] = None
+        self.dirty: List[Tuple[int, int]] = []
 
     # -- allocation ------------------------------------------------------------------------
     def declare(self, name, width: int, B: int, device):
@@ -73,6 +81,8 @@ class TokenArena:
                     pos += n
             self.arrays[name] = t
         self.cap, self.head = new_cap, 0
+        self.key_image = None                          # re-linearised: rebuild the image of what was kept
+        self.dirty = [(0, self.count)] if self.count else []
 
     def forget(self, name):
         self.arrays.pop(name, None)
@@ -99,6 +109,7 @@ class TokenArena:
         if not self.ring:
             assert self.head == 0
         self.count += n
+        self.dirty += runs                   # the caller fills these rows next; imaged lazily by flush_key_image
         return runs
 
     def drop_oldest(self, n: int):
@@ -117,6 +128,20 @@ class TokenArena:
     def view(self, name, run: Tuple[int, int]) -> torch.Tensor:
         s, n = run
         return self.arrays[name][:, s:s + n]
+
+    def flush_key_image(self) -> Optional[torch.Tensor]:
+        """Bring the operand image up to date with every row written since the last call (new memory frames:
+        one small launch; after a re-allocation or compaction: the whole arena)."""
+        if not USE_KEY_IMAGE or 'key' not in self.arrays or self.widths.get('key') != 64:
+            return None
+        if self.key_image is None:
+            self.key_image = torch.zeros(self.B, K_.key_image_tiles(self.cap), K_.KEY_IMAGE_FLOATS,
+                                         dtype=torch.float32, device=self.device)
+        for s, n in self.dirty:
+            if n > 0:
+                K_.bank_key_image(self.arrays['key'], self.arrays['shr'], s, n, self.key_image)
+        self.dirty = []
+        return self.key_image
 
 
 class _Bucket:
@@ -275,9 +300,10 @@ class KeyValueMemoryStore:
         if bk.temp.count:
             regions.append((bk.temp, bk.temp.pieces(temp_start, temp_len)))
         for arena, runs in regions:
+            image = arena.flush_key_image()
             for r in runs:
                 out.append(BankSegment(arena.view('key', r), arena.view('shr', r),
-                                       tuple(arena.view(('val', o), r) for o in objs)))
+                                       tuple(arena.view(('val', o), r) for o in objs), image, r[0]))
         return out
 
     def temp_runs(self, bucket_id: int, start: int = 0, length: Optional[int] = None):
@@ -341,6 +367,7 @@ class KeyValueMemoryStore:
             fresh[name] = dst
         arena.arrays = fresh
         arena.count = max_size
+        arena.dirty = [(0, max_size)]
 
     # -- object removal (kv:280-307) ---------------------------------------------------------
     def purge_except(self, obj_keep_idx: List[int]) -> None:

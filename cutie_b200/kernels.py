@@ -94,10 +94,18 @@ class BankSegment(NamedTuple):
     key: torch.Tensor
     shrinkage: torch.Tensor
     values: Tuple[torch.Tensor, ...] = ()
+    # optional: the tcgen05 operand image of the ARENA this run lives in ([B, tiles, KEY_IMAGE_FLOATS], built by
+    # bank_key_image) and the run's first physical token index inside that arena
+    key_image: Optional[torch.Tensor] = None
+    phys_begin: int = 0
 
     @property
     def n(self) -> int:
         return self.key.shape[1]
+
+
+KEY_IMAGE_TILE = 128            # tokens per image tile (the filter's MMA N)
+KEY_IMAGE_FLOATS = 17408        # 69632 bytes: 4 swizzled [128 x 128 B] K-blocks + one [128 x 32 B] tail block
 
 
 def _rows_view_ok(t: torch.Tensor):
@@ -150,12 +158,22 @@ def affinity_topk(segments: Sequence[BankSegment], qk: torch.Tensor, qe: torch.T
     PA, IA = ctypes.c_void_p * ns, ctypes.c_int64 * ns
     _L = lib()
     _lv = _L.cutie_affinity_plan_levels(_i64(n_total), ctypes.c_int(top_k))
+    with_img = all(s.key_image is not None for s in segments)
+    if with_img:
+        for s in segments:
+            assert s.key_image.dtype == torch.float32 and s.key_image.shape[2] == KEY_IMAGE_FLOATS
+            assert s.key_image.stride(2) == 1 and s.key_image.stride(1) == KEY_IMAGE_FLOATS
+            assert (s.phys_begin + s.n + KEY_IMAGE_TILE - 1) // KEY_IMAGE_TILE <= s.key_image.shape[1]
+        img_args = (PA(*[s.key_image.data_ptr() for s in segments]), IA(*[s.key_image.stride(0) for s in segments]),
+                    IA(*[s.phys_begin for s in segments]))
+    else:
+        img_args = (None, None, None)
     with _call('affinity_topk', 2 * _lv if _lv else 2):
-        st = L.cutie_affinity_topk(
+        st = L.cutie_affinity_topk_img(
             ctypes.c_int(ns), PA(*[s.key.data_ptr() for s in segments]),
             PA(*[s.shrinkage.data_ptr() for s in segments]), IA(*[s.n for s in segments]),
             IA(*[s.key.stride(0) for s in segments]), IA(*[s.shrinkage.stride(0) for s in segments]),
-            _ptr(qk), _ptr(qe), _i64(B), _i64(CK), _i64(Q), ctypes.c_int(top_k), ctypes.c_int(kpad),
+            *img_args, _ptr(qk), _ptr(qe), _i64(B), _i64(CK), _i64(Q), ctypes.c_int(top_k), ctypes.c_int(kpad),
             _ptr(idx, torch.int32), _ptr(w), _ptr(sim), _ptr(usage_acc, torch.int64), _i64(n_total),
             _ptr(ws, torch.uint8), ctypes.c_size_t(ws_bytes), _stream())
     _check(st, 'cutie_affinity_topk')
@@ -165,6 +183,25 @@ def affinity_topk(segments: Sequence[BankSegment], qk: torch.Tensor, qe: torch.T
 def set_tc_min_tokens(n: int):
     """Banks with fewer tokens than n use the exact fp32 scan only; larger ones add the tcgen05 filter levels."""
     lib().cutie_set_tc_min_tokens(_i64(n))
+
+
+def phase_timing(enable: bool):
+    """Record per-launch device times inside the filtered affinity plan (diagnostics)."""
+    lib().cutie_debug_phase_timing(ctypes.c_int(1 if enable else 0))
+
+
+def phase_times(calls_ago: int = 0):
+    """[ms per phase] of the affinity call `calls_ago` calls back: filter, select, filter, select, ..., re-rank."""
+    buf = (ctypes.c_float * 16)()
+    n = lib().cutie_debug_phase_times(_i64(calls_ago), buf, ctypes.c_int(16))
+    return [float(buf[i]) for i in range(n)]
+
+
+def image_level_launches() -> int:
+    """How many filter levels this process has served from a key image (bulk-copy producer) so far."""
+    f = lib().cutie_debug_image_level_launches
+    f.restype = ctypes.c_int64
+    return int(f())
 
 
 def affinity_plan_levels(n_total: int, top_k: int) -> int:
@@ -261,6 +298,29 @@ def bank_append(src: torch.Tensor, dst_rows: torch.Tensor):
         st = lib().cutie_bank_append(_ptr(src), _i64(src.stride(0)), _ptr(dst_rows), _i64(dst_rows.stride(0)),
                                      _i64(B), _i64(C), _i64(n), _stream())
     _check(st, 'cutie_bank_append')
+
+
+def key_image_tiles(capacity: int) -> int:
+    """Image tiles needed for an arena of `capacity` tokens."""
+    return (int(capacity) + KEY_IMAGE_TILE - 1) // KEY_IMAGE_TILE
+
+
+def bank_key_image(key_arena: torch.Tensor, shr_arena: torch.Tensor, phys_begin: int, n: int, image: torch.Tensor):
+    """(Re)build the tcgen05 operand image for tokens [phys_begin, phys_begin + n) of an arena.
+
+    key_arena [B, cap, 64] and shr_arena [B, cap] token-major, image [B, tiles, KEY_IMAGE_FLOATS]: every
+    128-token physical tile holds [shr k^2 | shr k | error-bound tail] in the swizzled shared-memory layout of
+    the affinity filter (csrc/tc_operand.cuh), so the filter fetches a tile with one bulk copy."""
+    B, cap, CK = key_arena.shape
+    assert CK == 64 and shr_arena.shape == (B, cap) and image.shape[0] == B and image.shape[2] == KEY_IMAGE_FLOATS
+    _rows_view_ok(key_arena), _rows_view_ok(shr_arena)
+    assert image.stride(2) == 1 and image.stride(1) == KEY_IMAGE_FLOATS
+    assert 0 <= phys_begin and phys_begin + n <= cap
+    with _call('bank_key_image', 1):
+        st = lib().cutie_bank_key_image(_ptr(key_arena), _i64(key_arena.stride(0)), _ptr(shr_arena),
+                                        _i64(shr_arena.stride(0)), _i64(B), _i64(phys_begin), _i64(n), _ptr(image),
+                                        _i64(image.stride(0)), _i64(image.shape[1]), _stream())
+    _check(st, 'cutie_bank_key_image')
 
 
 def bank_export(rows: torch.Tensor, dst: torch.Tensor):

@@ -55,6 +55,18 @@ int cutie_affinity_topk(int num_segments, const void* const* seg_key, const void
                         const float* qk, const float* qe, int64_t B, int64_t CK, int64_t Q, int top_k, int kpad,
                         int32_t* out_idx, float* out_w, float* out_sim, unsigned long long* usage_acc,
                         int64_t n_total, void* workspace, size_t workspace_bytes, void* stream);
+/* Same call with the bank's precomputed tcgen05 operand image (cutie_bank_key_image): seg_key_image[s] is the image
+ * of the ARENA segment s lives in ([B, tiles, 17408] floats, batch stride seg_image_bstride[s]), seg_phys_begin[s]
+ * the segment's first token's index inside that arena.  With images the stride-1 filter level fetches every
+ * 128-token tile with one 68 KB bulk copy (cp.async.bulk) instead of converting fp32 rows in the kernel; the
+ * outputs are bit-identical to cutie_affinity_topk.  seg_key_image == NULL (or a NULL entry) = no images. */
+int cutie_affinity_topk_img(int num_segments, const void* const* seg_key, const void* const* seg_shrinkage,
+                            const int64_t* seg_len, const int64_t* seg_key_bstride, const int64_t* seg_shr_bstride,
+                            const void* const* seg_key_image, const int64_t* seg_image_bstride,
+                            const int64_t* seg_phys_begin, const float* qk, const float* qe, int64_t B, int64_t CK,
+                            int64_t Q, int top_k, int kpad, int32_t* out_idx, float* out_w, float* out_sim,
+                            unsigned long long* usage_acc, int64_t n_total, void* workspace,
+                            size_t workspace_bytes, void* stream);
 
 /* Execution plan of cutie_affinity_topk for a bank of n_total tokens: 0 = exact fp32 scan only; n >= 1 = n nested
  * tcgen05 (TF32) candidate-filter levels over strided samples (strides ..., 256, 16, 1) followed by an exact fp32
@@ -63,6 +75,12 @@ int cutie_affinity_topk(int num_segments, const void* const* seg_key, const void
  * cutie_set_tc_min_tokens: banks smaller than n use plan 0 (default 6144; negative restores the default). */
 int cutie_affinity_plan_levels(int64_t n_total, int top_k);
 void cutie_set_tc_min_tokens(int64_t n);
+/* Diagnostics: per-phase device times (ms) of the filtered plan's launches (filter level, threshold select, ...,
+ * exact re-rank) for one of the last 64 calls, measured in situ with events on the caller's stream. */
+void cutie_debug_phase_timing(int enable);
+int cutie_debug_phase_times(int64_t calls_ago, float* out_ms, int max_phases);
+/* Number of filter levels served from a key image so far in this process (diagnostics / tests). */
+int64_t cutie_debug_image_level_launches(void);
 /* Test hook: raw TF32 energies E[b,q,n] = -8*S[n,q] computed by the tcgen05 filter over the whole bank
  * (dbg_energy [B,Q,n_total]); workspace >= cutie_affinity_workspace_bytes(B,Q,n_total,30) + B*Q*n_total*0. */
 int cutie_debug_tc_energy(int num_segments, const void* const* seg_key, const void* const* seg_shrinkage,
@@ -98,6 +116,15 @@ int cutie_usage_commit(float* use_cnt, int64_t use_bstride, float* life_cnt, int
  * Replaces the flatten + torch.cat growth of KeyValueMemoryStore.add (kv_memory_store.py:6-16,:136-149). */
 int cutie_bank_append(const float* src, int64_t src_bstride, float* dst_rows, int64_t dst_bstride, int64_t B,
                       int64_t C, int64_t n, void* stream);
+/* Build / refresh the tcgen05 operand image for tokens [phys_begin, phys_begin + n) of an arena (key_arena
+ * [B, cap, 64], shr_arena [B, cap] token-major; image [B, image_tiles, 17408] floats, image_tiles*128 >= cap).
+ * Tile t of the image holds tokens [128 t, 128 t + 128) as [shr k^2 | shr k | shr, 0, shr, -eps P^2, -2 eps P R,
+ * -eps R^2, 0, 0] in the filter's shared-memory layout (4 SWIZZLE_128B K-blocks + tail; csrc/tc_operand.cuh).
+ * Called once per memory frame for the appended tokens -- the per-token part of get_similarity
+ * (memory_utils.py:28-36: mk^2, shrinkage scaling) hoisted out of the per-frame read; no reference counterpart. */
+int cutie_bank_key_image(const float* key_arena, int64_t key_bstride, const float* shr_arena, int64_t shr_bstride,
+                         int64_t B, int64_t phys_begin, int64_t n, float* image, int64_t image_bstride,
+                         int64_t image_tiles, void* stream);
 /* dst[b,c,i] = rows[b,i,c]  (token-major -> channel-major; reference-shaped views for inspection). */
 int cutie_bank_export(const float* rows, int64_t rows_bstride, float* dst, int64_t dst_bstride, int64_t B,
                       int64_t C, int64_t n, void* stream);

@@ -109,6 +109,10 @@ def bank_export(rows, dst):
     dst.copy_(rows.transpose(1, 2))
 
 
+def bank_key_image(key_arena, shr_arena, phys_begin, n, image):
+    pass        # the operand image only feeds the tcgen05 filter; the CPU emulation reads the fp32 rows
+
+
 def bank_gather(segments_rows, index, dst_rows):
     allr = _cat_rows(segments_rows)
     for b in range(index.shape[0]):
@@ -229,7 +233,7 @@ def qt_query_to_pixel(kfold, kdots, vfold, out_bias, pixel, pixel_pe, num_querie
     return res
 
 
-ALL = ['affinity_topk', 'topk_merge', 'readout_gather', 'usage_commit', 'bank_append', 'bank_export', 'bank_gather',
+ALL = ['affinity_topk', 'topk_merge', 'readout_gather', 'usage_commit', 'bank_append', 'bank_export', 'bank_gather', 'bank_key_image',
        'consolidate', 'obj_summary_accumulate', 'qt_linear', 'qt_head_fold', 'qt_self_attention',
        'qt_aux_mask', 'qt_pixel_to_query', 'qt_query_to_pixel']
 
