@@ -176,16 +176,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) affinity_tc_filter_kernel(const
   if (tid < QT) {
     const long long q = q0 + tid;
     float b2 = 0.f;
-    for (int c = 0; c < CKD; ++c) {
-      float e = 0.f, k = 0.f;
-      if (q < p.Q) {
-        const long long off = ((long long)b * CKD + c) * p.Q + q;
-        e = p.qe[off];
-        k = p.qk[off];
+    const bool qok = q < p.Q;
+    const float* qe_p = p.qe + (long long)b * CKD * p.Q + (qok ? q : 0);
+    const float* qk_p = p.qk + (long long)b * CKD * p.Q + (qok ? q : 0);
+    // 16 channels at a time: all 32 loads of a batch are in flight together (the prologue is on every CTA's
+    // critical path and the filter runs three launches per frame)
+#pragma unroll 1
+    for (int c0 = 0; c0 < CKD; c0 += 16) {
+      float ev[16], kv[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        ev[i] = __ldg(qe_p + (long long)(c0 + i) * p.Q);
+        kv[i] = __ldg(qk_p + (long long)(c0 + i) * p.Q);
       }
-      b2 = fmaf(e * k, k, b2);
-      *reinterpret_cast<float*>(A + off_main(tid, c)) = to_tf32(e);
-      *reinterpret_cast<float*>(A + off_main(tid, 64 + c)) = to_tf32(-2.f * e * k);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float e = qok ? ev[i] : 0.f, k = qok ? kv[i] : 0.f;
+        b2 = fmaf(e * k, k, b2);
+        *reinterpret_cast<float*>(A + off_main(tid, c0 + i)) = to_tf32(e);
+        *reinterpret_cast<float*>(A + off_main(tid, 64 + c0 + i)) = to_tf32(-2.f * e * k);
+      }
     }
     const float b2_hi = to_tf32(b2), b2_lo = to_tf32(b2 - b2_hi);
     const float vq_ = sqrtf(b2);
@@ -252,14 +262,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) affinity_tc_filter_kernel(const
 #pragma unroll
         for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(r[j]) < thr) ? (1u << j) : 0u;
         mask &= range_mask32(vlo - cg * 32, nvalid - cg * 32);   // columns of this group that hold real tokens
-        // ... and a rare warp-uniform slow path that re-reads just the passing columns from TMEM
+        // ... and a warp-uniform slow path over the columns where any lane passes.  The column's value is picked
+        // out of the 32 registers with a 5-level select tree on the (warp-uniform) column bits: 31 SEL, no TMEM
+        // re-read (~150 cycles of latency per candidate column), no dynamic register indexing.
         unsigned wm = __reduce_or_sync(0xffffffffu, mask);
         while (wm) {
           const int j = __ffs(wm) - 1;
           wm &= wm - 1;
-          uint32_t dv;
-          asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(dv) : "r"(taddr + (uint32_t)j));
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          uint32_t s16[16], s8[8], s4[4];
+          const bool b4 = (j & 16) != 0, b3 = (j & 8) != 0, b2 = (j & 4) != 0, b1 = (j & 2) != 0, b0 = (j & 1) != 0;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) s16[i] = b4 ? r[16 + i] : r[i];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) s8[i] = b3 ? s16[8 + i] : s16[i];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) s4[i] = b2 ? s8[4 + i] : s8[i];
+          const uint32_t s2a = b1 ? s4[2] : s4[0], s2b = b1 ? s4[3] : s4[1];
+          const uint32_t dv = b0 ? s2b : s2a;
           if ((mask >> j) & 1u) {
             const float d = __uint_as_float(dv);
             const int col = cg * 32 + j;
