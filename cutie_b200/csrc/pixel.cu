@@ -1,0 +1,79 @@
+// Pixel-side glue on the frame path that ATen parallelises badly at these shapes (sm_100a).
+//
+// upsample2x_add: the mask decoder's UpsampleBlock input  out = bilinear_x2(g) + skip  for every object
+// (cutie/model/modules.py:8-20: F.interpolate(scale_factor=2, mode='bilinear', align_corners=False), then
+// `skip_f + g` broadcast over objects).  ATen's upsample_bilinear2d_out_frame launches one thread per OUTPUT
+// PIXEL and loops over batch x channels inside it: 7 CTAs (337 us) for [3 x 256 x 30 x 54] and 26 CTAs (169 us)
+// for [3 x 256 x 60 x 108] on a 148-SM part.  Here: one thread per four consecutive output pixels of one
+// (object, channel) plane, float4 stores, the add fused -- the kernel is a pure HBM stream.
+#include "common.cuh"
+
+namespace cutie {
+
+// PyTorch's area_pixel_compute_source_index for align_corners=False, scale = 1/2
+__device__ __forceinline__ void src_index(int dst, int in_size, int& i0, int& i1, float& l0, float& l1) {
+  float s = 0.5f * ((float)dst + 0.5f) - 0.5f;
+  s = s < 0.f ? 0.f : s;
+  i0 = (int)s;
+  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  l1 = s - (float)i0;
+  l0 = 1.f - l1;
+}
+
+template <int V>
+__global__ void __launch_bounds__(256) upsample2x_add_kernel(const float* __restrict__ g, const float* __restrict__ skip,
+                                                             float* __restrict__ out, long long planes, int K, int C,
+                                                             int h, int w) {
+  const int W2 = 2 * w, H2 = 2 * h;
+  const int xv = W2 / V;                                   // vectors per output row
+  const long long total = planes * H2 * xv;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int xq = (int)(t % xv);
+  const int Y = (int)((t / xv) % H2);
+  const long long plane = t / ((long long)xv * H2);         // (b*K + k)*C + c
+  const long long c = plane % C, bk = plane / C, b = bk / K;
+  const float* gp = g + plane * (long long)h * w;
+  const float* sp = skip + ((b * C + c) * (long long)H2 + Y) * W2 + (long long)xq * V;
+  int y0, y1;
+  float hy0, hy1;
+  src_index(Y, h, y0, y1, hy0, hy1);
+  const float* r0 = gp + (long long)y0 * w;
+  const float* r1 = gp + (long long)y1 * w;
+  float res[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    int x0, x1;
+    float wx0, wx1;
+    src_index(xq * V + i, w, x0, x1, wx0, wx1);
+    const float v = hy0 * (wx0 * __ldg(r0 + x0) + wx1 * __ldg(r0 + x1)) + hy1 * (wx0 * __ldg(r1 + x0) + wx1 * __ldg(r1 + x1));
+    res[i] = v + __ldg(sp + i);
+  }
+  float* op = out + (plane * (long long)H2 + Y) * W2 + (long long)xq * V;
+  if (V == 4) {
+    *reinterpret_cast<float4*>(op) = make_float4(res[0], res[1], res[2], res[3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < V; ++i) op[i] = res[i];
+  }
+}
+
+}  // namespace cutie
+
+using namespace cutie;
+
+extern "C" int cutie_upsample2x_add(const float* g, const float* skip, float* out, int64_t B, int64_t K, int64_t C,
+                                    int64_t h, int64_t w, void* stream) {
+  CUTIE_REQUIRE(g && skip && out && B >= 1 && K >= 1 && C >= 1 && h >= 1 && w >= 1, "null/empty argument");
+  CUTIE_REQUIRE(h < (1 << 14) && w < (1 << 14), "feature map too large");
+  const long long planes = (long long)B * K * C;
+  const bool vec = ((2 * w) % 4 == 0) && (((uintptr_t)out & 15) == 0);
+  const long long total = planes * 2 * h * (vec ? (2 * w) / 4 : 2 * w);
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  if (vec)
+    upsample2x_add_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(g, skip, out, planes, (int)K, (int)C, (int)h, (int)w);
+  else
+    upsample2x_add_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(g, skip, out, planes, (int)K, (int)C, (int)h, (int)w);
+  CUTIE_CHECK_LAUNCH();
+  return 0;
+}

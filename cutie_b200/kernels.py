@@ -300,6 +300,20 @@ def bank_append(src: torch.Tensor, dst_rows: torch.Tensor):
     _check(st, 'cutie_bank_append')
 
 
+def upsample2x_add(g: torch.Tensor, skip: torch.Tensor) -> torch.Tensor:
+    """bilinear x2 (align_corners=False) of every object's feature map plus the shared skip feature:
+    g [B,K,C,h,w], skip [B,C,2h,2w] -> [B,K,C,2h,2w] (the mask decoder's UpsampleBlock input)."""
+    B, K, C, h, w = g.shape
+    assert skip.shape == (B, C, 2 * h, 2 * w)
+    g, skip = g.contiguous(), skip.contiguous()
+    out = torch.empty(B, K, C, 2 * h, 2 * w, dtype=torch.float32, device=g.device)
+    with _call('upsample2x_add', 1):
+        st = lib().cutie_upsample2x_add(_ptr(g), _ptr(skip), _ptr(out), _i64(B), _i64(K), _i64(C), _i64(h), _i64(w),
+                                        _stream())
+    _check(st, 'cutie_upsample2x_add')
+    return out
+
+
 def key_image_tiles(capacity: int) -> int:
     """Image tiles needed for an arena of `capacity` tokens."""
     return (int(capacity) + KEY_IMAGE_TILE - 1) // KEY_IMAGE_TILE

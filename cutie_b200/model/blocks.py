@@ -11,6 +11,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from cutie_b200 import kernels as K_
+
 
 def fold(g: torch.Tensor) -> torch.Tensor:
     return g.reshape(g.shape[0] * g.shape[1], *g.shape[2:])
@@ -99,6 +101,12 @@ class UpsampleBlock(nn.Module):
         self.out_conv = ObjResBlock(c_in, c_out)
 
     def forward(self, g, skip):
+        if g.is_cuda:
+            # fused sm_100a kernel (raises if the library is missing): ATen's bilinear kernel runs one thread per
+            # output PIXEL and loops over objects x channels inside it -- 7 CTAs at 480p
+            return self.out_conv(K_.upsample2x_add(g, skip))
+        # CPU tensors only reach this block when the oracle harness (oracle/cpu_core.py, tests) borrows the
+        # convolutional modules; InferenceCore itself cannot run on CPU (its kernels reject CPU tensors)
         return self.out_conv(resize_objects(g, 2, 'bilinear') + skip.unsqueeze(1))
 
 

@@ -110,6 +110,14 @@ int cutie_usage_commit(float* use_cnt, int64_t use_bstride, float* life_cnt, int
                        const unsigned long long* usage_acc, int64_t acc_bstride, int64_t acc_offset, int64_t B,
                        int64_t n, void* stream);
 
+/* ---- mask decoder glue ------------------------------------------------------------------------------- */
+
+/* out[b,k,c] = bilinear_x2(g[b,k,c]) + skip[b,c]   (align_corners = False), g [B,K,C,h,w], skip [B,C,2h,2w],
+ * out [B,K,C,2h,2w], all contiguous.  Replaces UpsampleBlock's F.interpolate + broadcast add
+ * (cutie/model/modules.py:15-19, group_modules.py:11-24 upsample_groups) on the frame path. */
+int cutie_upsample2x_add(const float* g, const float* skip, float* out, int64_t B, int64_t K, int64_t C, int64_t h,
+                         int64_t w, void* stream);
+
 /* ---- memory bank maintenance ------------------------------------------------------------------------ */
 
 /* dst[b,i,c] = src[b,c,i]  (channel-major feature map -> token-major arena rows).

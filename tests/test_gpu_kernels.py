@@ -365,3 +365,16 @@ def test_query_transformer_vs_reference_fixture(K_):
     assert err < 5e-4 * max(1.0, float(ref.abs().max())), err
     for i in range(4):
         assert torch.allclose(aux['logits'][i].cpu(), torch.from_numpy(g[f'aux_logits_{i}']), atol=1e-3)
+
+
+@pytest.mark.parametrize('B,K,C,h,w', [(1, 3, 256, 30, 54), (2, 2, 16, 7, 5), (1, 1, 8, 1, 1), (1, 3, 256, 60, 108)])
+def test_upsample2x_add_matches_aten(K_, B, K, C, h, w):
+    """Mask decoder UpsampleBlock input (modules.py:15-19): bilinear x2 (align_corners=False) + skip broadcast."""
+    g_ = torch.Generator().manual_seed(1)
+    g = torch.randn(B, K, C, h, w, generator=g_).cuda()
+    skip = torch.randn(B, C, 2 * h, 2 * w, generator=g_).cuda()
+    out = K_.upsample2x_add(g, skip)
+    up = torch.nn.functional.interpolate(g.flatten(0, 1), scale_factor=2, mode='bilinear', align_corners=False)
+    want = up.reshape(B, K, C, 2 * h, 2 * w) + skip.unsqueeze(1)
+    assert out.shape == want.shape
+    torch.testing.assert_close(out, want, rtol=0, atol=2e-6)
