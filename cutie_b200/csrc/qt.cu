@@ -31,54 +31,93 @@ struct LinearParams {
   float* y;
 };
 
-// CTA tile 32 rows x 8 cols, 256 threads (one output each); the reduction axis is staged through smem in chunks
-// of 256 (the whole axis for embed 256 => one barrier), LayerNorm statistics are taken from the staged tile.
-constexpr int LIN_BM = 32, LIN_BN = 8, LIN_KC = 256;
+// CTA tile 16 rows x 16 cols, 256 threads (one output each).  The reduction axis goes through smem in chunks of
+// 256 (the whole axis for embed 256 => one barrier).  Each warp owns 2 x-rows and 2 W-rows of the tile and issues
+// ALL of their global loads (x, positional term, LayerNorm affine, W) before touching any of them, so the prologue
+// costs one memory latency; LayerNorm statistics are reduced in registers (same summation order as a two-pass
+// row reduction: lane-strided partial sums, then a butterfly).  The next chunk is prefetched into registers while
+// the current one is multiplied (Kd = 2048 in the FFN's second linear).
+constexpr int LIN_BM = 16, LIN_BN = 16, LIN_KC = 256, LIN_LD = LIN_KC + 4;   // +4: 16-B aligned rows, conflict-free LDS.128
 __global__ void __launch_bounds__(256) qt_linear_kernel(const LinearParams p) {
-  __shared__ float xs[LIN_BM][LIN_KC + 1];
-  __shared__ float wsm[LIN_BN][LIN_KC + 1];
+  __shared__ __align__(16) float xs[LIN_BM][LIN_LD];
+  __shared__ __align__(16) float wsm[LIN_BN][LIN_LD];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long m0 = (long long)blockIdx.y * LIN_BM, n0 = (long long)blockIdx.x * LIN_BN;
-  const int r_t = tid >> 3, cg = tid & 7;
+  const int r_t = tid >> 4, cg = tid & 15;
   float acc = 0.f;
+  float xv[2][8], wv[2][8];
+  auto load_chunk = [&](long long k0) {
+    const int kc = (int)((p.Kd - k0) < LIN_KC ? (p.Kd - k0) : LIN_KC);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long long m = m0 + warp + 8 * u, n = n0 + warp + 8 * u;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int kk = lane + 32 * i;
+        xv[u][i] = (m < p.M && kk < kc) ? __ldg(p.x + m * p.ldx + k0 + kk) : 0.f;
+        wv[u][i] = (n < p.N && kk < kc) ? __ldg(p.W + n * p.ldw + k0 + kk) : 0.f;
+      }
+    }
+  };
+  load_chunk(0);
   for (long long k0 = 0; k0 < p.Kd; k0 += LIN_KC) {
     const int kc = (int)((p.Kd - k0) < LIN_KC ? (p.Kd - k0) : LIN_KC);
-    if (k0) __syncthreads();
-    // ---- stage x rows (4 per warp) and the 8 weight rows (1 per warp) ----
-    for (int r = warp; r < LIN_BM; r += 8) {
+    // ---- prologue on this warp's two x rows (registers), then publish the tile ----
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int r = warp + 8 * u;
       const long long m = m0 + r;
+      const bool live = m < p.M;
+      float pev[8], lw[8], lb[8];
       float den = 1.f;
-      if (m < p.M && p.summary_norm) den = 1.f / (p.x[m * p.ldx + p.Kd] + 1e-4f);
-      for (int kk = lane; kk < LIN_KC; kk += 32) {
-        float v = 0.f;
-        if (m < p.M && kk < kc) v = p.x[m * p.ldx + k0 + kk] * den;
-        xs[r][kk] = v;
+      if (live && p.summary_norm) den = __ldg(p.x + m * p.ldx + p.Kd);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int kk = lane + 32 * i;
+        pev[i] = (p.pe && live && kk < kc) ? __ldg(p.pe + m * p.Kd + k0 + kk) : 0.f;
+        lw[i] = p.ln_w ? __ldg(p.ln_w + kk) : 1.f;
+        lb[i] = p.ln_w ? __ldg(p.ln_b + kk) : 0.f;
       }
-      if (p.ln_w) {                       // Kd == 256: the whole row is staged; two-pass statistics
-        __syncwarp();
+      if (p.summary_norm) {
+        den = 1.f / (den + 1e-4f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) xv[u][i] *= den;
+      }
+      if (p.ln_w) {                       // Kd == 256: the whole row is in this warp's registers
         float sum = 0.f;
-        for (int kk = lane; kk < LIN_KC; kk += 32) sum += xs[r][kk];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sum += xv[u][i];
         const float mean = warp_sum(sum) / (float)p.Kd;
         float var = 0.f;
-        for (int kk = lane; kk < LIN_KC; kk += 32) { const float d = xs[r][kk] - mean; var += d * d; }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const float d = xv[u][i] - mean; var += d * d; }
         const float rstd = rsqrtf(warp_sum(var) / (float)p.Kd + 1e-5f);
-        for (int kk = lane; kk < LIN_KC; kk += 32) {
-          float v = (xs[r][kk] - mean) * rstd * p.ln_w[kk] + p.ln_b[kk];
-          if (p.xhat_out && blockIdx.x == 0 && m < p.M) p.xhat_out[m * p.Kd + kk] = v;
-          xs[r][kk] = v;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float v = (xv[u][i] - mean) * rstd * lw[i] + lb[i];
+          if (p.xhat_out && blockIdx.x == 0 && live) p.xhat_out[m * p.Kd + lane + 32 * i] = v;
+          xv[u][i] = v;
         }
       }
-      if (p.pe && m < p.M)
-        for (int kk = lane; kk < kc; kk += 32) xs[r][kk] += p.pe[m * p.Kd + k0 + kk];
-    }
-    {
-      const long long n = n0 + warp;
-      for (int kk = lane; kk < LIN_KC; kk += 32)
-        wsm[warp][kk] = (n < p.N && kk < kc) ? p.W[n * p.ldw + k0 + kk] : 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        xs[r][lane + 32 * i] = xv[u][i] + pev[i];
+        wsm[r][lane + 32 * i] = wv[u][i];
+      }
     }
     __syncthreads();
+    if (k0 + LIN_KC < p.Kd) load_chunk(k0 + LIN_KC);       // in flight during the multiply
+    const float4* xr = reinterpret_cast<const float4*>(&xs[r_t][0]);
+    const float4* wr = reinterpret_cast<const float4*>(&wsm[cg][0]);
 #pragma unroll 8
-    for (int kk = 0; kk < LIN_KC; ++kk) acc = fmaf(xs[r_t][kk], wsm[cg][kk], acc);
+    for (int k4 = 0; k4 < LIN_KC / 4; ++k4) {
+      const float4 a = xr[k4], w = wr[k4];
+      acc = fmaf(a.x, w.x, acc);
+      acc = fmaf(a.y, w.y, acc);
+      acc = fmaf(a.z, w.z, acc);
+      acc = fmaf(a.w, w.w, acc);
+    }
+    if (k0 + LIN_KC < p.Kd) __syncthreads();
   }
   const long long m = m0 + r_t, n = n0 + cg;
   if (m < p.M && n < p.N) {
@@ -243,8 +282,8 @@ __global__ void __launch_bounds__(256) qt_p2q_partial_kernel(const P2QParams p) 
   float(*qf)[E_] = reinterpret_cast<float(*)[E_]>(dsm);                       // [16][256]
   float(*kin)[33] = reinterpret_cast<float(*)[33]>(dsm + NQ * E_);            // [256][33]
   float(*pix)[33] = reinterpret_cast<float(*)[33]>(dsm + NQ * E_ + E_ * 33);  // [256][33]
-  float(*ps)[33] = reinterpret_cast<float(*)[33]>(dsm + NQ * E_ + 2 * E_ * 33);  // [16][33]
-  float* sc = dsm + NQ * E_ + 2 * E_ * 33 + NQ * 33;                          // [16] rescale factors
+  float(*ps)[20] = reinterpret_cast<float(*)[20]>(dsm + NQ * E_ + 2 * E_ * 33);  // [32 pixels][16 rows (+4 pad)]
+  float* sc = dsm + NQ * E_ + 2 * E_ * 33 + 32 * 20;                          // [16] rescale factors
   float* rm = sc + NQ;                                                        // running max
   float* rl = rm + NQ;                                                        // running sum
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -278,11 +317,16 @@ __global__ void __launch_bounds__(256) qt_p2q_partial_kernel(const P2QParams p) 
     __syncthreads();
     // scores for rows (warp, warp+8) x pixel lane
     float s0 = 0.f, s1 = 0.f;
-#pragma unroll 8
-    for (int c = 0; c < E_; ++c) {
-      const float kv = kin[c][lane];
-      s0 = fmaf(qf[warp][c], kv, s0);
-      s1 = fmaf(qf[warp + 8][c], kv, s1);
+    const float4* q0 = reinterpret_cast<const float4*>(&qf[warp][0]);
+    const float4* q1 = reinterpret_cast<const float4*>(&qf[warp + 8][0]);
+#pragma unroll 4
+    for (int c4 = 0; c4 < E_ / 4; ++c4) {
+      const float4 a = q0[c4], b4 = q1[c4];
+      const float k0 = kin[4 * c4][lane], k1 = kin[4 * c4 + 1][lane], k2 = kin[4 * c4 + 2][lane], k3 = kin[4 * c4 + 3][lane];
+      s0 = fmaf(a.x, k0, s0); s1 = fmaf(b4.x, k0, s1);
+      s0 = fmaf(a.y, k1, s0); s1 = fmaf(b4.y, k1, s1);
+      s0 = fmaf(a.z, k2, s0); s1 = fmaf(b4.z, k2, s1);
+      s0 = fmaf(a.w, k3, s0); s1 = fmaf(b4.w, k3, s1);
     }
     const bool f = (px < p.HW) ? (p.fg[bk * p.HW + px] != 0) : false;
     const bool ok0 = (px < p.HW) && (f || open_fg);     // rows 0..7: foreground queries
@@ -295,7 +339,7 @@ __global__ void __launch_bounds__(256) qt_p2q_partial_kernel(const P2QParams p) 
       const float e = (mn == -CUDART_INF_F) ? 0.f : expf(s0 - mn);
       const float scl = (mo == -CUDART_INF_F) ? 0.f : expf(mo - mn);
       const float su = warp_sum(e);
-      ps[warp][lane] = e;
+      ps[lane][warp] = e;
       if (lane == 0) { sc[warp] = scl; rl[warp] = rl[warp] * scl + su; rm[warp] = mn; }
     }
     {
@@ -304,7 +348,7 @@ __global__ void __launch_bounds__(256) qt_p2q_partial_kernel(const P2QParams p) 
       const float e = (mn == -CUDART_INF_F) ? 0.f : expf(s1 - mn);
       const float scl = (mo == -CUDART_INF_F) ? 0.f : expf(mo - mn);
       const float su = warp_sum(e);
-      ps[warp + 8][lane] = e;
+      ps[lane][warp + 8] = e;
       if (lane == 0) { sc[warp + 8] = scl; rl[warp + 8] = rl[warp + 8] * scl + su; rm[warp + 8] = mn; }
     }
     __syncthreads();
@@ -314,8 +358,15 @@ __global__ void __launch_bounds__(256) qt_p2q_partial_kernel(const P2QParams p) 
 #pragma unroll 4
     for (int pp = 0; pp < 32; ++pp) {
       const float v = pix[tid][pp];
+      const float4* pr = reinterpret_cast<const float4*>(&ps[pp][0]);      // broadcast LDS.128: 4 rows per load
 #pragma unroll
-      for (int i = 0; i < NQ; ++i) z[i] = fmaf(ps[i][pp], v, z[i]);
+      for (int i4 = 0; i4 < NQ / 4; ++i4) {
+        const float4 w = pr[i4];
+        z[4 * i4] = fmaf(w.x, v, z[4 * i4]);
+        z[4 * i4 + 1] = fmaf(w.y, v, z[4 * i4 + 1]);
+        z[4 * i4 + 2] = fmaf(w.z, v, z[4 * i4 + 2]);
+        z[4 * i4 + 3] = fmaf(w.w, v, z[4 * i4 + 3]);
+      }
     }
   }
   __syncthreads();
@@ -385,9 +436,9 @@ struct Q2PParams {
 __global__ void __launch_bounds__(256) qt_q2p_kernel(const Q2PParams p) {
   extern __shared__ __align__(16) float dsm[];
   float(*qin)[33] = reinterpret_cast<float(*)[33]>(dsm);                    // [256][33]
-  float(*stage)[33] = reinterpret_cast<float(*)[33]>(dsm + E_ * 33);        // [128][33]: kfold chunk (A)
-  float(*ps)[33] = reinterpret_cast<float(*)[33]>(dsm + E_ * 33 + 128 * 33);  // [128][33] probabilities
-  float* vf = dsm + E_ * 33 + 2 * 128 * 33;                                  // [32][256] vfold chunk (B)
+  float(*stage)[36] = reinterpret_cast<float(*)[36]>(dsm + E_ * 33);        // [128][36]: kfold chunk (A), 16-B rows
+  float(*ps)[33] = reinterpret_cast<float(*)[33]>(dsm + E_ * 33 + 128 * 36);  // [128][33] probabilities
+  float* vf = dsm + E_ * 33 + 128 * 36 + 128 * 33;                           // [32][256] vfold chunk (B)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long bk = blockIdx.y, p0 = (long long)blockIdx.x * 32, px = p0 + lane;
   const float* pbase = p.pixel + bk * E_ * p.HW;
@@ -406,11 +457,19 @@ __global__ void __launch_bounds__(256) qt_q2p_kernel(const Q2PParams p) {
     __syncthreads();
     for (int r = warp; r < 128; r += 8) stage[r][lane] = kf[(long long)r * E_ + c0 + lane];
     __syncthreads();
-#pragma unroll 4
-    for (int cc = 0; cc < 32; ++cc) {
-      const float x = qin[c0 + cc][lane];
+    // broadcast LDS.128 of four reduction steps per query row: 20 shared loads per 64 FMA
+#pragma unroll 2
+    for (int c4 = 0; c4 < 8; ++c4) {
+      const float x0 = qin[c0 + 4 * c4][lane], x1 = qin[c0 + 4 * c4 + 1][lane];
+      const float x2 = qin[c0 + 4 * c4 + 2][lane], x3 = qin[c0 + 4 * c4 + 3][lane];
 #pragma unroll
-      for (int j = 0; j < NQ; ++j) s[j] = fmaf(x, stage[j * 8 + warp][cc], s[j]);
+      for (int j = 0; j < NQ; ++j) {
+        const float4 w = *reinterpret_cast<const float4*>(&stage[j * 8 + warp][4 * c4]);
+        s[j] = fmaf(x0, w.x, s[j]);
+        s[j] = fmaf(x1, w.y, s[j]);
+        s[j] = fmaf(x2, w.z, s[j]);
+        s[j] = fmaf(x3, w.w, s[j]);
+      }
     }
   }
   float mx = -CUDART_INF_F;
@@ -425,7 +484,7 @@ __global__ void __launch_bounds__(256) qt_q2p_kernel(const Q2PParams p) {
   const float inv = 1.f / sum;
 #pragma unroll
   for (int j = 0; j < NQ; ++j) ps[j * 8 + warp][lane] = s[j] * inv;
-  // ---- stage B: out[c][p] = pixel + bias + sum_r P[r][p] * vfold[r][c],  c = warp + 8 v ----
+  // ---- stage B: out[c][p] = pixel + bias + sum_r P[r][p] * vfold[r][c],  c = 32 warp + v ----
   float acc[32];
 #pragma unroll
   for (int v = 0; v < 32; ++v) acc[v] = 0.f;
@@ -437,15 +496,22 @@ __global__ void __launch_bounds__(256) qt_q2p_kernel(const Q2PParams p) {
 #pragma unroll 2
     for (int rr = 0; rr < 32; ++rr) {
       const float pr = ps[r0 + rr][lane];
+      const float4* vr = reinterpret_cast<const float4*>(vf + rr * E_ + warp * 32);
 #pragma unroll
-      for (int v = 0; v < 32; ++v) acc[v] = fmaf(pr, vf[rr * E_ + warp + 8 * v], acc[v]);
+      for (int v4 = 0; v4 < 8; ++v4) {
+        const float4 w = vr[v4];
+        acc[4 * v4] = fmaf(pr, w.x, acc[4 * v4]);
+        acc[4 * v4 + 1] = fmaf(pr, w.y, acc[4 * v4 + 1]);
+        acc[4 * v4 + 2] = fmaf(pr, w.z, acc[4 * v4 + 2]);
+        acc[4 * v4 + 3] = fmaf(pr, w.w, acc[4 * v4 + 3]);
+      }
     }
   }
   if (px < p.HW) {
     float* ob = p.out + bk * E_ * p.HW;
 #pragma unroll
     for (int v = 0; v < 32; ++v) {
-      const int c = warp + 8 * v;
+      const int c = warp * 32 + v;
       ob[(long long)c * p.HW + px] = pbase[(long long)c * p.HW + px] + p.out_bias[c] + acc[v];
     }
   }
@@ -532,7 +598,7 @@ extern "C" int cutie_qt_pixel_to_query(const float* qfold, const float* pixel, c
   const long long chunks = (HW + 31) / 32;
   p.chunks_per_split = (int)((chunks + splits - 1) / splits);
   p.ws = workspace;
-  const size_t smem = (size_t)(NQ * E_ + 2 * E_ * 33 + NQ * 33 + 3 * NQ) * sizeof(float);
+  const size_t smem = (size_t)(NQ * E_ + 2 * E_ * 33 + 32 * 20 + 3 * NQ) * sizeof(float);
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(qt_p2q_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -556,7 +622,7 @@ extern "C" int cutie_qt_query_to_pixel(const float* kfold, const float* kdots, c
   Q2PParams p;
   p.kfold = kfold; p.kdots = kdots; p.vfold = vfold; p.out_bias = out_bias; p.pixel = pixel; p.pe = pixel_pe;
   p.HW = HW; p.out = out;
-  const size_t smem = (size_t)(E_ * 33 + 2 * 128 * 33 + 32 * E_) * sizeof(float);
+  const size_t smem = (size_t)(E_ * 33 + 128 * 36 + 128 * 33 + 32 * E_) * sizeof(float);
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(qt_q2p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

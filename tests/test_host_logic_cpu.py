@@ -194,3 +194,56 @@ def test_kernels_fail_loudly_without_cuda():
     import cutie_b200.kernels as K_
     with pytest.raises(K_.KernelError):
         K_.obj_summary_accumulate(torch.zeros(4), torch.zeros(4))
+
+
+def test_key_image_tracks_every_written_row(cpu_kernels, monkeypatch):
+    """The arena's tcgen05 operand image must be refreshed for exactly the rows written since the last read:
+    appends, ring wrap-around, re-allocation (everything moves) and long-term compaction."""
+    import cutie_b200.kernels as K_
+    from cutie_b200.inference.memory_bank import KeyValueMemoryStore
+    calls = []
+
+    def record(key_arena, shr_arena, phys_begin, n, image):
+        assert image.shape[1] * K_.KEY_IMAGE_TILE >= key_arena.shape[1] and image.shape[2] == K_.KEY_IMAGE_FLOATS
+        calls.append((key_arena.data_ptr(), phys_begin, n))
+    monkeypatch.setattr(K_, 'bank_key_image', record)
+    st = KeyValueMemoryStore(save_selection=False, save_usage=False)
+    st.set_capacity_hint(temp_tokens=30, perm_tokens=10)
+    g = torch.Generator().manual_seed(0)
+
+    def add(n, perm='no'):
+        st.add(torch.randn(1, 64, n, generator=g), {1: torch.randn(1, 256, n, generator=g)}, torch.ones(1, 1, n), None,
+               as_permanent=perm)
+
+    def imaged_rows(arena):
+        """physical rows of `arena` covered by image refreshes since the last reset"""
+        rows = set()
+        for ptr, s, n in calls:
+            if ptr == arena.arrays['key'].data_ptr():
+                rows |= set(range(s, s + n))
+        return rows
+    add(10, 'first')
+    add(10), add(10)
+    segs = st.segments(0)
+    bk = st._b[0]
+    assert all(s.key_image is not None for s in segs)
+    assert imaged_rows(bk.perm) == set(range(10)) and imaged_rows(bk.temp) == set(range(20))
+    assert [s.phys_begin for s in segs] == [0, 0]
+    calls.clear()
+    st.segments(0)
+    assert not calls, 'nothing was written: no refresh'
+    # fill the ring (cap 30), evict the oldest 20, append 15: the new run starts again at physical row 0
+    add(10)
+    st.remove_old_memory(0, 10)
+    add(15)
+    segs = st.segments(0)
+    assert imaged_rows(bk.temp) == set(range(20, 30)) | set(range(0, 15))
+    assert [(s.phys_begin, s.n) for s in segs] == [(0, 10), (20, 10), (0, 15)]
+    # a burst larger than the capacity re-linearises the arena: every kept row is imaged again
+    calls.clear()
+    old_ptr = bk.temp.arrays['key'].data_ptr()
+    add(40)
+    segs = st.segments(0)
+    assert bk.temp.arrays['key'].data_ptr() != old_ptr
+    assert imaged_rows(bk.temp) == set(range(65))
+    assert segs[-1].key_image.shape[1] == K_.key_image_tiles(bk.temp.cap)
