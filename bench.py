@@ -155,8 +155,10 @@ def run_ours(args, wl, rank, world, dev):
             K_.phase_timing(True)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
+        h0 = time.perf_counter()
         for _ in range(args.steps):
             proc.step(frames_dev[t]); t += 1
+        host_ms_dev = (time.perf_counter() - h0) * 1e3 / args.steps     # host time to ENQUEUE a step (no sync inside)
         ev1.record()
         barrier()
         stop.set(); th.join()
@@ -199,21 +201,38 @@ def run_ours(args, wl, rank, world, dev):
             ev.record(cur)
         e0.record()
         upload(0)
+        h0 = time.perf_counter()
+        e2e_marks = []
         for i in range(args.steps):
             if i + 1 < args.steps:
                 upload(i + 1)                # next frame's H2D overlaps this frame's compute
             cur.wait_event(ready[i % 2])
+            if args.phase_timing:
+                marks = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                marks[0].record()
             prob = proc2.step(bufs[i % 2])
             free[i % 2].record(cur)
+            if args.phase_timing:
+                marks[1].record()
             host_out.copy_(proc2.output_prob_to_mask(prob).to(torch.uint8), non_blocking=True)
+            if args.phase_timing:
+                marks[2].record()
+                e2e_marks.append(marks)
+        host_ms_e2e = (time.perf_counter() - h0) * 1e3 / args.steps
         e1.record()
         barrier()
         ms_e2e = e0.elapsed_time(e1)
+        if e2e_marks:
+            st = sum(m[0].elapsed_time(m[1]) for m in e2e_marks) / len(e2e_marks)
+            mk = sum(m[1].elapsed_time(m[2]) for m in e2e_marks) / len(e2e_marks)
+            gap = (ms_e2e - sum(m[0].elapsed_time(m[2]) for m in e2e_marks)) / len(e2e_marks)
+            log(f'[e2e] per step: step() {st:.3f} ms, mask + D2H {mk:.3f} ms, between steps (waiting for the H2D) {gap:.3f} ms')
     times = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         torch.distributed.all_reduce(times, op=torch.distributed.ReduceOp.MAX)
     ms_total, ms_e2e = float(times[0]), float(times[1])
-    return dict(phases=phases, image_levels=K_.image_level_launches(), ms_total=ms_total, ms_e2e=ms_e2e, kernel_ms=kernel_ms, launches=launches, n_tokens=n_tokens,
+    log(f'[rank {rank}] host enqueue time per step: device arm {host_ms_dev:.2f} ms, e2e arm {host_ms_e2e:.2f} ms')
+    return dict(host_ms=[host_ms_dev, host_ms_e2e], phases=phases, image_levels=K_.image_level_launches(), ms_total=ms_total, ms_e2e=ms_e2e, kernel_ms=kernel_ms, launches=launches, n_tokens=n_tokens,
                 clocks=summarize_clocks(samples), h2d=frames_pin[0].numel() * 4, d2h=host_out.numel())
 
 
@@ -374,6 +393,7 @@ def main():
             'e2e': {'value': fps_e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': res['h2d'],
                     'd2h_bytes_per_step': res['d2h'], 'ms_per_step': res['ms_e2e'] / args.steps},
             'gpu_launches': res['launches'], 'roofline': roof, 'cpu_baseline': cpu, 'kernels': kshare,
+            'host_enqueue_ms_per_step': {'device_arm': res['host_ms'][0], 'e2e_arm': res['host_ms'][1]},
             'affinity_phases_ms': res['phases'] or None, 'key_image_levels': res['image_levels']}
     emit(line)
 
