@@ -543,6 +543,17 @@ static int run_filter_level(const ScanParams& base, long long B, long long strid
   if (ia.on && stride == 1 && emax_in != nullptr) {
     // the whole bank, one bulk copy per physical 128-token tile of each segment's arena
     fp.use_img = 1;
+    static int chunks = -1, prefetch = -1;
+    if (chunks < 0) {
+      const char* e = getenv("CUTIE_B200_IMG_CHUNKS");
+      chunks = e ? atoi(e) : 17;
+      if (chunks < 1 || 69632 % chunks != 0 || (69632 / chunks) % 16 != 0) chunks = 1;
+      const char* f = getenv("CUTIE_B200_IMG_PREFETCH");
+      prefetch = f ? atoi(f) : 2;
+      if (prefetch < 0 || prefetch > 64) prefetch = 0;
+    }
+    fp.img_chunks = chunks;
+    fp.img_prefetch = prefetch;
     long long cum = 0;
     for (int s = 0; s < base.segs.nseg; ++s) {
       const long long n = base.segs.begin[s + 1] - base.segs.begin[s];

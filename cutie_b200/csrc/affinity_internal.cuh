@@ -25,6 +25,8 @@ struct TcFilterParams {
   // Image path (stride-1 level only): per segment the precomputed operand image of the arena it lives in
   // (cutie_bank_key_image), addressed by physical 128-token tile.
   int use_img;
+  int img_chunks;                  // bulk copies per 68 KB tile (69632 / chunks must be a multiple of 16)
+  int img_prefetch;                // L2 prefetch distance in tiles (0 = off)
   const float* img[kMaxSeg];
   long long img_bs[kMaxSeg];       // batch stride (floats)
   long long img_tile0[kMaxSeg];    // first physical tile of the segment

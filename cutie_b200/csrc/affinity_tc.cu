@@ -30,7 +30,12 @@ constexpr int QT = TC_QT;               // queries per CTA (MMA M)
 constexpr int KTILE = TC_KTILE;         // memory tokens per tile (MMA N)
 constexpr int BLK_BYTES = TC_BLK_BYTES;
 constexpr int OPER_BYTES = TC_OPER_BYTES;
-constexpr int TC_THREADS = 416;   // 4 epilogue + 2 x 4 producer + 1 MMA warps
+// Warp roles.  On-the-fly producers (strided levels): warps 0-3 epilogue, 4-11 two producer groups, 12 MMA = 416
+// threads.  Image path: the producer is ONE thread issuing bulk copies, so the freed warps become epilogue warps --
+// warps 0-15 epilogue (TMEM lane quarter = warp & 3, 32-column group = warp >> 2: four warps per scheduler hide
+// each other's TMEM-load / select latency), warp 16 bulk-copy producer, warp 17 MMA = 576 threads.
+constexpr int TC_THREADS = 416;
+constexpr int TC_THREADS_IMG = 576;
 constexpr float TF32_EPS = TC_TF32_EPS;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -139,7 +144,10 @@ struct TcSmemTail {
 };
 
 template <bool DBG, bool IMG>
-__global__ void __launch_bounds__(TC_THREADS, 1) affinity_tc_filter_kernel(const TcFilterParams p) {
+__global__ void __launch_bounds__(IMG ? TC_THREADS_IMG : TC_THREADS, 1) affinity_tc_filter_kernel(const TcFilterParams p) {
+  constexpr int EPI_WARPS = IMG ? 16 : 4;
+  constexpr int MMA_WARP = IMG ? 17 : 12;
+  constexpr int RESERVE = IMG ? 16 : 32;     // candidate slots reserved per global atomic (per thread)
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* A = smem;                              // queries
   unsigned char* Bst = smem + OPER_BYTES;               // 2 stages of keys
@@ -147,27 +155,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) affinity_tc_filter_kernel(const
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.z, split = blockIdx.y;
   const long long q0 = (long long)blockIdx.x * QT;
-  // non-IMG: tiles cover sample indices [i_begin, i_end); IMG: physical image tiles [g_begin, g_begin + ntiles)
-  const long long g_begin = (long long)split * p.tiles_per_split;
-  const long long i_begin = g_begin * KTILE;
-  long long i_end = i_begin + (long long)p.tiles_per_split * KTILE;
-  if (i_end > p.samp_count) i_end = p.samp_count;
-  int ntiles = i_end > i_begin ? (int)((i_end - i_begin + KTILE - 1) / KTILE) : 0;
-  if (IMG) {
-    const long long left = p.img_tcum[p.segs.nseg] - g_begin;
-    ntiles = left <= 0 ? 0 : (left < p.tiles_per_split ? (int)left : p.tiles_per_split);
-  }
+  // Tiles are dealt to the key splits round-robin (split s takes tiles s, s + nsplit, ...): candidates cluster in
+  // the part of the bank that resembles the current frame (recent memory frames), and contiguous ranges would
+  // leave the CTAs owning that part with nearly all of the candidate work.
+  // non-IMG: tile g covers sample indices [128 g, 128 g + 128); IMG: g enumerates the segments' physical image tiles
+  const long long total_tiles = IMG ? p.img_tcum[p.segs.nseg] : (p.samp_count + KTILE - 1) / KTILE;
+  const long long tile_step = p.nsplit;
+  const long long i_end = p.samp_count;
+  const int ntiles = split < total_tiles ? (int)((total_tiles - split + tile_step - 1) / tile_step) : 0;
+  auto tile_of = [&](int t) { return (long long)split + (long long)t * tile_step; };
 
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&T.full[s]), IMG ? 1 : 128);   // IMG: one arrive.expect_tx + the bulk copy's bytes
       mbar_init(smem_u32(&T.empty[s]), 1);
       mbar_init(smem_u32(&T.tfull[s]), 1);
-      mbar_init(smem_u32(&T.tempty[s]), 128);
+      mbar_init(smem_u32(&T.tempty[s]), 32 * EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 12) {
+  if (warp == MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&T.tmem_base)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -214,32 +221,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) affinity_tc_filter_kernel(const
   tc_fence_after();
   const uint32_t tmem = T.tmem_base;
 
-  if (warp < 4) {
-    // =========================== epilogue: thread == query ===========================
-    const long long q = q0 + tid;
+  if (warp < EPI_WARPS) {
+    // =========================== epilogue: thread == query (x column group on the image path) ===========================
+    const long long q = q0 + (tid & 127);
+    if (IMG) emax = (q < p.Q) ? p.emax_in[(long long)b * p.Q + q] : -CUDART_INF_F;
     const long long bq = (long long)b * p.Q + (q < p.Q ? q : 0);
     int* my_idx = p.cand_idx + bq * p.cap;
     float* my_e = p.cand_e + bq * p.cap;
     const bool all_pass = (p.emax_in == nullptr);       // coarsest level: every token of the sample is kept
-    int blk_base = 0, blk_used = 32;
+    int blk_base = 0, blk_used = RESERVE;
     if (all_pass && split == 0 && q < p.Q) p.count[bq] = (int)p.samp_count;
     for (int t = 0; t < ntiles; ++t) {
       const int a = t & 1;
       mbar_wait(smem_u32(&T.tfull[a]), (t >> 1) & 1);
       tc_fence_after();
       const float thr = (q < p.Q) ? emax : -CUDART_INF_F;
-      long long ibase = i_begin + (long long)t * KTILE;      // IMG: bank index of row 0 (may precede the segment)
+      long long ibase = tile_of(t) * KTILE;                  // IMG: bank index of row 0 (may precede the segment)
       int vlo = 0, nvalid = (int)((i_end - ibase) < KTILE ? (i_end - ibase) : KTILE);   // valid rows [vlo, nvalid)
       if (IMG) {
-        const ImgTile it = img_tile(p, b, g_begin + t);
+        const ImgTile it = img_tile(p, b, tile_of(t));
         ibase = it.lbase;
         vlo = it.lo;
         nvalid = it.hi;
       }
 #pragma unroll 1
-      for (int cg = 0; cg < 4; ++cg) {
+      for (int cg = IMG ? (warp >> 2) : 0; cg < (IMG ? (warp >> 2) + 1 : 4); ++cg) {
         uint32_t r[32];
-        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * KTILE + cg * 32);
+        const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(a * KTILE + cg * 32);
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -262,66 +270,72 @@ __global__ void __launch_bounds__(TC_THREADS, 1) affinity_tc_filter_kernel(const
 #pragma unroll
         for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(r[j]) < thr) ? (1u << j) : 0u;
         mask &= range_mask32(vlo - cg * 32, nvalid - cg * 32);   // columns of this group that hold real tokens
-        // ... and a warp-uniform slow path over the columns where any lane passes.  The column's value is picked
-        // out of the 32 registers with a 5-level select tree on the (warp-uniform) column bits: 31 SEL, no TMEM
-        // re-read (~150 cycles of latency per candidate column), no dynamic register indexing.
-        unsigned wm = __reduce_or_sync(0xffffffffu, mask);
-        while (wm) {
-          const int j = __ffs(wm) - 1;
-          wm &= wm - 1;
-          uint32_t s16[16], s8[8], s4[4];
-          const bool b4 = (j & 16) != 0, b3 = (j & 8) != 0, b2 = (j & 4) != 0, b1 = (j & 2) != 0, b0 = (j & 1) != 0;
+        // ... and a per-lane walk over the lane's own passing columns (iterations per group = the largest popcount
+        // among the 32 queries, not the number of distinct passing columns).  Strided levels also need the value: it
+        // is picked out of the 32 registers with a 5-level select tree on the column bits (31 SEL; no TMEM re-read,
+        // no dynamic register indexing).  The image path keeps only the index -- its survivors are re-ranked exactly.
+        unsigned m = mask;
+        while (m) {
+          const int j = __ffs(m) - 1;
+          m &= m - 1;
+          const int col = cg * 32 + j;
+          float e_hi = 0.f;
+          if (!IMG) {
+            uint32_t s16[16], s8[8], s4[4];
+            const bool b4 = (j & 16) != 0, b3 = (j & 8) != 0, b2 = (j & 4) != 0, b1 = (j & 2) != 0, b0 = (j & 1) != 0;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) s16[i] = b4 ? r[16 + i] : r[i];
+            for (int i = 0; i < 16; ++i) s16[i] = b4 ? r[16 + i] : r[i];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) s8[i] = b3 ? s16[8 + i] : s16[i];
+            for (int i = 0; i < 8; ++i) s8[i] = b3 ? s16[8 + i] : s16[i];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) s4[i] = b2 ? s8[4 + i] : s8[i];
-          const uint32_t s2a = b1 ? s4[2] : s4[0], s2b = b1 ? s4[3] : s4[1];
-          const uint32_t dv = b0 ? s2b : s2a;
-          if ((mask >> j) & 1u) {
-            const float d = __uint_as_float(dv);
-            const int col = cg * 32 + j;
-            float e_hi = d;
-            if (!IMG) {      // IMG serves the last level only: its candidates are re-ranked exactly, no bound needed
-              const float s_ = T.rowP[t & 3][col] + T.rowR[t & 3][col] * vq;
-              e_hi = d + 2.01f * TF32_EPS * s_ * s_;                    // an UPPER bound of the exact energy
-            }
-            int pos;
-            if (all_pass) {
-              pos = (int)(ibase + col);
-            } else {
-              // slots are reserved 32 at a time: one global atomic (latency ~1 us) per 32 candidates of this
-              // (query, CTA) instead of one per candidate; unused slots of the last block are voided at the end
-              if (blk_used == 32) { blk_base = atomicAdd(&p.count[bq], 32); blk_used = 0; }
-              pos = blk_base + blk_used++;
-            }
-            if (pos < p.cap) {
-              my_idx[pos] = IMG ? (int)(ibase + col) : (int)(p.samp_begin + (ibase + col) * p.samp_stride);
-              if (!IMG) my_e[pos] = e_hi;
-            }
+            for (int i = 0; i < 4; ++i) s4[i] = b2 ? s8[4 + i] : s8[i];
+            const uint32_t s2a = b1 ? s4[2] : s4[0], s2b = b1 ? s4[3] : s4[1];
+            const float d = __uint_as_float(b0 ? s2b : s2a);
+            const float s_ = T.rowP[t & 3][col] + T.rowR[t & 3][col] * vq;
+            e_hi = d + 2.01f * TF32_EPS * s_ * s_;                      // an UPPER bound of the exact energy
+          }
+          int pos;
+          if (all_pass) {
+            pos = (int)(ibase + col);
+          } else {
+            // slots are reserved in blocks: one global atomic (latency ~1 us) per block of candidates of this
+            // (query, CTA) instead of one per candidate; unused slots of the last block are voided at the end
+            if (blk_used == RESERVE) { blk_base = atomicAdd(&p.count[bq], RESERVE); blk_used = 0; }
+            pos = blk_base + blk_used++;
+          }
+          if (pos < p.cap) {
+            my_idx[pos] = IMG ? (int)(ibase + col) : (int)(p.samp_begin + (ibase + col) * p.samp_stride);
+            if (!IMG) my_e[pos] = e_hi;
           }
         }
+        __syncwarp();      // reconverge before the next aligned tcgen05.ld / the barrier arrive
       }
       tc_fence_before();
       mbar_arrive(smem_u32(&T.tempty[a]));
     }
-    if (!all_pass && blk_used < 32)
-      for (int u = blk_used; u < 32; ++u)
+    if (!all_pass && blk_used < RESERVE)
+      for (int u = blk_used; u < RESERVE; ++u)
         if (blk_base + u < p.cap) { my_idx[blk_base + u] = -1; if (!IMG) my_e[blk_base + u] = CUDART_INF_F; }
-  } else if (warp < 12 && IMG) {
+  } else if (IMG && warp == 16) {
     // ============ producer (image path): one thread, one 68 KB bulk copy per tile ============
-    if (tid == 128) {
+    if (lane == 0) {
       for (int t = 0; t < ntiles; ++t) {
         const int s = t & 1;
         mbar_wait(smem_u32(&T.empty[s]), ((t >> 1) & 1) ^ 1);
-        const ImgTile it = img_tile(p, b, g_begin + t);
+        const ImgTile it = img_tile(p, b, tile_of(t));
         const uint32_t bar = smem_u32(&T.full[s]);
         mbar_arrive_expect_tx(bar, (uint32_t)OPER_BYTES);
-        bulk_g2s(smem_u32(Bst + s * OPER_BYTES), it.src, (uint32_t)OPER_BYTES, bar);
+        // several independent bulk copies per tile: one 68 KB copy is serviced with little memory-level parallelism
+        const uint32_t cb = (uint32_t)OPER_BYTES / (uint32_t)p.img_chunks;
+        const uint32_t dst = smem_u32(Bst + s * OPER_BYTES);
+        for (int c = 0; c < p.img_chunks; ++c) bulk_g2s(dst + c * cb, it.src + (size_t)c * cb, cb, bar);
+        if (p.img_prefetch > 0 && t + p.img_prefetch < ntiles) {       // pull a later tile into L2 ahead of its copy
+          const ImgTile nx = img_tile(p, b, tile_of(t + p.img_prefetch));
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nx.src), "r"((uint32_t)OPER_BYTES) : "memory");
+        }
       }
     }
-  } else if (warp < 12) {
+  } else if (!IMG && warp < 12) {
     // ============ producers: 16 lanes per token row (coalesced 256-B rows), next tile prefetched ============
     const int grp = (warp - 4) >> 2;     // producer group 0 handles even tiles (stage 0), group 1 odd tiles
     const int pt = (tid - 128) & 127;    // 0..127 within the group
@@ -330,7 +344,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) affinity_tc_filter_kernel(const
     float4 kf[16];
     float shr[16];
     auto load_tile = [&](int t) {
-      const long long i0 = i_begin + (long long)t * KTILE;
+      const long long i0 = tile_of(t) * KTILE;
       const long long g_first = p.samp_begin + i0 * p.samp_stride;
       const long long i_last = (i0 + KTILE <= i_end ? i0 + KTILE : i_end) - 1;
       const long long g_last = p.samp_begin + i_last * p.samp_stride;
@@ -382,7 +396,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) affinity_tc_filter_kernel(const
       mbar_arrive(smem_u32(&T.full[s]));
       if (t + 2 < ntiles) load_tile(t + 2);       // in flight while the other group converts the next tile
     }
-  } else {
+  } else if (warp == MMA_WARP) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       // instruction descriptor: D=F32, A=B=TF32, K-major both, N=128, M=128
@@ -409,7 +423,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) affinity_tc_filter_kernel(const
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 12) {
+  if (warp == MMA_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem));
   }
@@ -538,9 +552,9 @@ int launch_tc_filter(const TcFilterParams& p, long long B, cudaStream_t st) {
   if (p.use_img) {
     if (!p.emax_in) return fail(-1, "%s: the image path needs a previous level's thresholds", "affinity_tc_filter_kernel");
     if (p.dbg_energy)
-      affinity_tc_filter_kernel<true, true><<<grid, TC_THREADS, smem, st>>>(p);
+      affinity_tc_filter_kernel<true, true><<<grid, TC_THREADS_IMG, smem, st>>>(p);
     else
-      affinity_tc_filter_kernel<false, true><<<grid, TC_THREADS, smem, st>>>(p);
+      affinity_tc_filter_kernel<false, true><<<grid, TC_THREADS_IMG, smem, st>>>(p);
   } else if (p.dbg_energy)
     affinity_tc_filter_kernel<true, false><<<grid, TC_THREADS, smem, st>>>(p);
   else

@@ -58,9 +58,38 @@ __global__ void __launch_bounds__(256) upsample2x_add_kernel(const float* __rest
   }
 }
 
+// out[y,x] = lut[argmax_c prob[c,y,x]] (first maximum wins, like torch.argmax): InferenceCore.output_prob_to_mask
+// (inference_core.py:377-385 + object_manager.py:99-104) as one pass instead of a strided reduce, a gather and a cast.
+__global__ void __launch_bounds__(256) prob_to_mask_kernel(const float* __restrict__ prob, long long plane_stride,
+                                                           long long row_stride, int C, int H, int W,
+                                                           const long long* __restrict__ lut,
+                                                           long long* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)H * W) return;
+  const int y = (int)(i / W), x = (int)(i % W);
+  const float* p = prob + (long long)y * row_stride + x;
+  float best = __ldg(p);
+  int arg = 0;
+  for (int c = 1; c < C; ++c) {
+    const float v = __ldg(p + (long long)c * plane_stride);
+    if (v > best) { best = v; arg = c; }
+  }
+  out[i] = lut[arg];
+}
+
 }  // namespace cutie
 
 using namespace cutie;
+
+extern "C" int cutie_prob_to_mask(const float* prob, int64_t plane_stride, int64_t row_stride, int64_t C, int64_t H,
+                                  int64_t W, const int64_t* lut, int64_t* out, void* stream) {
+  CUTIE_REQUIRE(prob && lut && out && C >= 1 && H >= 1 && W >= 1, "null/empty argument");
+  const long long n = (long long)H * W;
+  prob_to_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      prob, plane_stride, row_stride, (int)C, (int)H, (int)W, (const long long*)lut, (long long*)out);
+  CUTIE_CHECK_LAUNCH();
+  return 0;
+}
 
 extern "C" int cutie_upsample2x_add(const float* g, const float* skip, float* out, int64_t B, int64_t K, int64_t C,
                                     int64_t h, int64_t w, void* stream) {

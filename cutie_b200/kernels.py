@@ -314,6 +314,18 @@ def upsample2x_add(g: torch.Tensor, skip: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def prob_to_mask(prob: torch.Tensor, lut: torch.Tensor) -> torch.Tensor:
+    """lut[argmax over channels] of a [C,H,W] probability map (any plane/row strides, unit pixel stride) -> int64 [H,W]."""
+    C, H, W = prob.shape
+    assert prob.stride(2) == 1 and lut.dtype == torch.int64 and lut.numel() >= C and lut.is_contiguous()
+    out = torch.empty(H, W, dtype=torch.int64, device=prob.device)
+    with _call('prob_to_mask', 1):
+        st = lib().cutie_prob_to_mask(_ptr(prob), _i64(prob.stride(0)), _i64(prob.stride(1)), _i64(C), _i64(H), _i64(W),
+                                      _ptr(lut, torch.int64), _ptr(out, torch.int64), _stream())
+    _check(st, 'cutie_prob_to_mask')
+    return out
+
+
 def key_image_tiles(capacity: int) -> int:
     """Image tiles needed for an arena of `capacity` tokens."""
     return (int(capacity) + KEY_IMAGE_TILE - 1) // KEY_IMAGE_TILE

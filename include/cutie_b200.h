@@ -118,6 +118,13 @@ int cutie_usage_commit(float* use_cnt, int64_t use_bstride, float* life_cnt, int
 int cutie_upsample2x_add(const float* g, const float* skip, float* out, int64_t B, int64_t K, int64_t C, int64_t h,
                          int64_t w, void* stream);
 
+/* out[y,x] = lut[argmax_c prob[c,y,x]]: InferenceCore.output_prob_to_mask (inference_core.py:377-385: argmax over
+ * the 1+K channels, then ObjectManager.tmp_to_obj_cls object_manager.py:99-104) in one pass.  prob may be a strided
+ * view (plane_stride / row_stride in elements, unit pixel stride); lut int64 [C]; out int64 [H,W] contiguous.
+ * Ties: the first maximum wins (torch.argmax); NaN is not treated specially. */
+int cutie_prob_to_mask(const float* prob, int64_t plane_stride, int64_t row_stride, int64_t C, int64_t H, int64_t W,
+                       const int64_t* lut, int64_t* out, void* stream);
+
 /* ---- memory bank maintenance ------------------------------------------------------------------------ */
 
 /* dst[b,i,c] = src[b,c,i]  (channel-major feature map -> token-major arena rows).

@@ -115,6 +115,10 @@ def upsample2x_add(g, skip):
     return up.reshape(B, K, *up.shape[1:]) + skip.unsqueeze(1)
 
 
+def prob_to_mask(prob, lut):
+    return lut[torch.argmax(prob, dim=0)]
+
+
 def bank_key_image(key_arena, shr_arena, phys_begin, n, image):
     pass        # the operand image only feeds the tcgen05 filter; the CPU emulation reads the fp32 rows
 
@@ -239,7 +243,7 @@ def qt_query_to_pixel(kfold, kdots, vfold, out_bias, pixel, pixel_pe, num_querie
     return res
 
 
-ALL = ['affinity_topk', 'topk_merge', 'readout_gather', 'usage_commit', 'bank_append', 'bank_export', 'bank_gather', 'bank_key_image', 'upsample2x_add',
+ALL = ['affinity_topk', 'topk_merge', 'readout_gather', 'usage_commit', 'bank_append', 'bank_export', 'bank_gather', 'bank_key_image', 'upsample2x_add', 'prob_to_mask',
        'consolidate', 'obj_summary_accumulate', 'qt_linear', 'qt_head_fold', 'qt_self_attention',
        'qt_aux_mask', 'qt_pixel_to_query', 'qt_query_to_pixel']
 
