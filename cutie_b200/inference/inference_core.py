@@ -13,6 +13,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
+from cutie_b200 import kernels as K_
 from cutie_b200.inference.image_feature_store import ImageFeatureStore
 from cutie_b200.inference.memory_manager import MemoryManager
 from cutie_b200.inference.object_manager import ObjectManager
@@ -241,5 +242,8 @@ class InferenceCore:
         self.memory.purge_except(self.object_manager.all_obj_ids)
 
     def output_prob_to_mask(self, output_prob: torch.Tensor) -> torch.Tensor:
-        """argmax over channels, then tmp-id -> object-id remap."""
-        return self.object_manager.tmp_to_obj_cls(torch.argmax(output_prob, dim=0))
+        """argmax over channels, then tmp-id -> object-id remap (one fused kernel on the GPU)."""
+        prob = output_prob.float()
+        if prob.stride(-1) != 1:
+            prob = prob.contiguous()
+        return K_.prob_to_mask(prob, self.object_manager.tmp_to_obj_lut(prob.device))

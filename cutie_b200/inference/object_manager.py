@@ -81,13 +81,17 @@ class ObjectManager:
         """tmp-id class map -> object-id class map (object_manager.py:99-104) as one table lookup.  The table lives
         on the mask's device and is rebuilt only when the object set changes: boolean-mask assignment per object
         (or a per-frame pageable H2D copy) would stall the host on the GPU every frame."""
-        sig = (tuple((t, o.id) for t, o in self.tmp_id_to_obj.items()), mask.device, mask.dtype)
+        return self.tmp_to_obj_lut(mask.device, mask.dtype)[mask]
+
+    def tmp_to_obj_lut(self, device, dtype=torch.int64) -> torch.Tensor:
+        """[1 + num_obj] table tmp id -> object id (0 -> 0), cached on `device` until the object set changes."""
+        sig = (tuple((t, o.id) for t, o in self.tmp_id_to_obj.items()), device, dtype)
         if getattr(self, '_lut_sig', None) != sig:
-            lut = torch.zeros(len(self.tmp_id_to_obj) + 1, dtype=mask.dtype)
+            lut = torch.zeros(len(self.tmp_id_to_obj) + 1, dtype=dtype)
             for tmp_id, obj in self.tmp_id_to_obj.items():
                 lut[tmp_id] = obj.id
-            self._lut, self._lut_sig = lut.to(mask.device), sig
-        return self._lut[mask]
+            self._lut, self._lut_sig = lut.to(device), sig
+        return self._lut
 
     def get_tmp_to_obj_mapping(self) -> Dict[int, ObjectInfo]:
         return {obj.id: tmp_id for obj, tmp_id in self.tmp_id_to_obj.items()}

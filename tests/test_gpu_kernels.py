@@ -378,3 +378,18 @@ def test_upsample2x_add_matches_aten(K_, B, K, C, h, w):
     want = up.reshape(B, K, C, 2 * h, 2 * w) + skip.unsqueeze(1)
     assert out.shape == want.shape
     torch.testing.assert_close(out, want, rtol=0, atol=2e-6)
+
+
+def test_prob_to_mask_matches_argmax_and_lut(K_):
+    """InferenceCore.output_prob_to_mask (inference_core.py:377-385, object_manager.py:99-104) as one kernel,
+    on a strided (un-padded) view, with exact ties (first maximum wins like torch.argmax)."""
+    g_ = torch.Generator().manual_seed(3)
+    full = torch.rand(4, 480, 864, generator=g_).cuda()
+    full[1, 10:20] = full[2, 10:20]                       # exact ties between channels 1 and 2
+    full[0, 30:40] = 2.0
+    full[3, 30:40] = 2.0                                  # tie between first and last channel
+    prob = full[:, :, 5:859]                              # [4, 480, 854] view: row stride 864
+    lut = torch.tensor([0, 7, 3, 11], dtype=torch.int64).cuda()
+    out = K_.prob_to_mask(prob, lut)
+    want = lut[torch.argmax(prob, dim=0)]
+    assert out.dtype == torch.int64 and torch.equal(out, want)
