@@ -356,13 +356,19 @@ def main():
     gather_ms = sum(gather) / len(gather) if gather else None
     gather_bytes = min(N, HW * wl['top_k']) * wl['K'] * 256 * 4 + HW * wl['K'] * 256 * 4 + HW * 32 * 8
     tensor_bound = flops / (peaks['bf16_tflops_sustained'] * 1e12) > bytes_alg / (peaks['hbm_gbs'] * 1e9)
+    # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of this workload
+    traffic, traffic_note = None, None
+    tj = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    if os.path.exists(tj) and args.workload == 'cfg2':
+        t = json.load(open(tj))
+        traffic, traffic_note = t.get('affinity_topk_dram_bytes'), t.get('note')
     if scan_ms:
         if tensor_bound:
             ach = flops / (scan_ms * 1e-3) / 1e12
-            roof = {'bound': 'tensor', 'kernel': 'cutie_affinity_topk = 3 x affinity_tc_filter_kernel (tcgen05 kind::tf32) + 2 x level_select + '
-                              'affinity_rerank_kernel (exact fp32)',
+            roof = {'bound': 'tensor', 'kernel': 'cutie_affinity_topk = 3 x affinity_tc_filter_kernel (tcgen05 kind::tf32; the stride-1 level '
+                              'fed by bulk copies of the key operand image) + 2 x level_select + affinity_rerank_kernel (exact fp32)',
                     'achieved': ach, 'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
-                    'frac': ach / peaks['bf16_tflops_sustained'], 'traffic': None,
+                    'frac': ach / peaks['bf16_tflops_sustained'], 'traffic': traffic, 'traffic_note': traffic_note,
                     'peak_source': f"{peaks['src']} bf16 sustained (kernel timed inside a long step)",
                     'algorithmic_flops_per_launch': flops, 'avg_launch_ms': scan_ms,
                     'hbm_view': {'algorithmic_bytes': bytes_alg, 'achieved_gbs': bytes_alg / (scan_ms * 1e-3) / 1e9,

@@ -546,10 +546,10 @@ static int run_filter_level(const ScanParams& base, long long B, long long strid
     static int chunks = -1, prefetch = -1;
     if (chunks < 0) {
       const char* e = getenv("CUTIE_B200_IMG_CHUNKS");
-      chunks = e ? atoi(e) : 17;
+      chunks = e ? atoi(e) : 1;        // measured at cfg 2: 1 x 68 KB and 17 x 4 KB copies per tile are within noise
       if (chunks < 1 || 69632 % chunks != 0 || (69632 / chunks) % 16 != 0) chunks = 1;
       const char* f = getenv("CUTIE_B200_IMG_PREFETCH");
-      prefetch = f ? atoi(f) : 2;
+      prefetch = f ? atoi(f) : 0;      // ... and so is an explicit L2 prefetch two tiles ahead
       if (prefetch < 0 || prefetch > 64) prefetch = 0;
     }
     fp.img_chunks = chunks;
