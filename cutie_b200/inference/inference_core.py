@@ -24,7 +24,7 @@ log = logging.getLogger()
 
 class InferenceCore:
     def __init__(self, network, cfg, *, image_feature_store: ImageFeatureStore = None,
-                 use_cuda_graphs: bool = False):
+                 use_cuda_graphs: bool = False, memory_shard_group=None):
         self.network = network
         self.cfg = cfg
         self.mem_every = cfg.mem_every
@@ -42,7 +42,8 @@ class InferenceCore:
         else:
             self.stagger_ti = set(np.round(np.linspace(1, self.mem_every, stagger)).astype(int))
         self.object_manager = ObjectManager()
-        self.memory = MemoryManager(cfg=cfg, object_manager=self.object_manager)
+        self.memory_shard_group = memory_shard_group
+        self.memory = MemoryManager(cfg=cfg, object_manager=self.object_manager, shard_group=memory_shard_group)
         self.image_feature_store = image_feature_store or ImageFeatureStore(self.network)
         self.last_mask = None
         self.last_logits = None      # network.segment(...)[1] of the latest segmented frame (parity hook)
@@ -57,7 +58,8 @@ class InferenceCore:
 
     def clear_memory(self):
         self._reset_clock()
-        self.memory = MemoryManager(cfg=self.cfg, object_manager=self.object_manager)
+        self.memory = MemoryManager(cfg=self.cfg, object_manager=self.object_manager,
+                                    shard_group=self.memory_shard_group)
 
     def clear_non_permanent_memory(self):
         self._reset_clock()

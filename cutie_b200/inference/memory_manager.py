@@ -24,8 +24,20 @@ log = logging.getLogger()
 
 
 class MemoryManager:
-    def __init__(self, cfg, object_manager: ObjectManager):
+    def __init__(self, cfg, object_manager: ObjectManager, *, shard_group=None):
+        """shard_group (a torch.distributed process group, or None): key-shard THIS stream's working memory over the
+        group's ranks.  Every rank runs the same frames through the same model; each stores the
+        slice shard_bounds(HW, world, rank) of every memory frame's tokens and the read exchanges top-k candidates
+        (all_gather) and partial readouts (all_reduce) -- cutie_b200/inference/sharded.py."""
         self.object_manager = object_manager
+        self.shard_group = shard_group
+        self.shard_world, self.shard_rank = 1, 0
+        if shard_group is not None:
+            import torch.distributed as dist
+            self.shard_world, self.shard_rank = dist.get_world_size(shard_group), dist.get_rank(shard_group)
+            if cfg.use_long_term:
+                raise NotImplementedError('key-sharded memory covers the FIFO working memory; long-term prototype '
+                                          'selection ranks usage globally and is not sharded yet')
         self.sensory_dim = cfg.model.sensory_dim
         self.top_k = cfg.top_k
         self.chunk_size = cfg.chunk_size
@@ -77,6 +89,32 @@ class MemoryManager:
             return None
         return torch.stack([self.obj_v[o] for o in obj_ids], dim=1)
 
+    def _topk(self, bucket_id: int, qk: torch.Tensor, qe: torch.Tensor):
+        """Affinity -> top-k -> softmax (+ usage commits) for one bucket.  Returns gather(objects) -> [B,K,CV,Q]."""
+        bs = qk.shape[0]
+        if self.shard_group is not None:
+            from cutie_b200.inference.sharded import sharded_gather, sharded_topk
+            key_segs = self._segments(bucket_id, [])
+            n_local = sum(s.n for s in key_segs)
+            frames, rem = divmod(n_local, self.HW)             # self.HW is the LOCAL tokens per frame here
+            assert rem == 0 and frames >= 1
+            n_total = frames * self.HW_global
+            idx_l, w_l, _, _ = sharded_topk(key_segs, frames * self.shard_begin, n_total, qk, qe, self.top_k,
+                                            self.shard_group)
+            return lambda objects: sharded_gather(idx_l, w_l, self._segments(bucket_id, objects), self.shard_group)
+        long_n = self.long_mem.size(bucket_id) if (self.use_long_term and self.long_mem.engaged(bucket_id)) else 0
+        key_segs = self._segments(bucket_id, [])
+        usage_acc = None
+        if self.use_long_term:
+            usage_acc = torch.zeros(bs, sum(s.n for s in key_segs), dtype=torch.int64, device=qk.device)
+        idx, wgt, _ = K_.affinity_topk(key_segs, qk, qe, self.top_k, usage_acc=usage_acc)
+        if self.use_long_term:
+            # usage of the temporary working tokens; permanent tokens are skipped (kv:157)
+            self.work_mem.update_bucket_usage(bucket_id, usage_acc, long_n + self.work_mem.perm_size(bucket_id))
+            if long_n and self.count_long_term_usage:
+                self.long_mem.update_bucket_usage(bucket_id, usage_acc, 0)
+        return lambda objects: K_.readout_gather(idx, wgt, self._segments(bucket_id, objects))
+
     def _segments(self, bucket_id: int, obj_ids: List[int]):
         segs = []
         if self.use_long_term and self.long_mem.engaged(bucket_id):
@@ -97,19 +135,7 @@ class MemoryManager:
 
         out: Dict[int, torch.Tensor] = {}
         for bucket_id, bucket in self.work_mem.buckets.items():
-            long_n = self.long_mem.size(bucket_id) if (self.use_long_term and self.long_mem.engaged(bucket_id)) else 0
-            key_segs = self._segments(bucket_id, [])
-            n_total = sum(s.n for s in key_segs)
-            usage_acc = None
-            if self.use_long_term:
-                usage_acc = torch.zeros(bs, n_total, dtype=torch.int64, device=qk.device)
-            idx, wgt, _ = K_.affinity_topk(key_segs, qk, qe, self.top_k, usage_acc=usage_acc)
-            if self.use_long_term:
-                # usage of the temporary working tokens; permanent tokens are skipped (kv:157)
-                self.work_mem.update_bucket_usage(bucket_id, usage_acc,
-                                                  long_n + self.work_mem.perm_size(bucket_id))
-                if long_n and self.count_long_term_usage:
-                    self.long_mem.update_bucket_usage(bucket_id, usage_acc, 0)
+            gather = self._topk(bucket_id, qk, qe)
 
             if self.chunk_size < 1:
                 chunks = [bucket]
@@ -118,8 +144,7 @@ class MemoryManager:
             for objects in chunks:
                 this_sensory = self._get_sensory_by_ids(objects)
                 this_last_mask = self._get_mask_by_ids(last_mask, objects)
-                visual = K_.readout_gather(idx, wgt, self._segments(bucket_id, objects))
-                visual = visual.view(bs, len(objects), self.CV, h, w)
+                visual = gather(objects).view(bs, len(objects), self.CV, h, w)
                 pixel_readout = network.pixel_fusion(pix_feat, visual, this_sensory, this_last_mask)
                 obj_mem = self._get_object_mem_by_ids(objects)
                 obj_mem = obj_mem.unsqueeze(2) if obj_mem is not None else None
@@ -148,17 +173,7 @@ class MemoryManager:
         qe = selection.flatten(2).contiguous()
         (bucket_id, bucket), = self.work_mem.buckets.items()
         assert list(bucket) == list(obj_ids)
-        long_n = self.long_mem.size(bucket_id) if (self.use_long_term and self.long_mem.engaged(bucket_id)) else 0
-        segs = self._segments(bucket_id, bucket)
-        usage_acc = None
-        if self.use_long_term:
-            usage_acc = torch.zeros(bs, sum(s.n for s in segs), dtype=torch.int64, device=qk.device)
-        idx, wgt, _ = K_.affinity_topk(segs, qk, qe, self.top_k, usage_acc=usage_acc)
-        if self.use_long_term:
-            self.work_mem.update_bucket_usage(bucket_id, usage_acc, long_n + self.work_mem.perm_size(bucket_id))
-            if long_n and self.count_long_term_usage:
-                self.long_mem.update_bucket_usage(bucket_id, usage_acc, 0)
-        return K_.readout_gather(idx, wgt, segs).view(bs, len(bucket), self.CV, h, w)
+        return self._topk(bucket_id, qk, qe)(bucket).view(bs, len(bucket), self.CV, h, w)
 
     # -- insertion -----------------------------------------------------------------------------
     def add_memory(self, key: torch.Tensor, shrinkage: torch.Tensor, msk_value: torch.Tensor,
@@ -174,7 +189,13 @@ class MemoryManager:
         if self.H is None or self.config_stale:
             self.config_stale = False
             self.H, self.W = msk_value.shape[-2:]
-            self.HW = self.H * self.W
+            self.HW = self.HW_global = self.H * self.W
+            if self.shard_group is not None:              # sizes below are in LOCAL tokens (this rank's slice)
+                from cutie_b200.inference.sharded import shard_bounds
+                self.shard_begin, self.shard_end = shard_bounds(self.HW_global, self.shard_world, self.shard_rank)
+                self.HW = self.shard_end - self.shard_begin
+                if self.HW < 1:
+                    raise ValueError(f'{self.HW_global} tokens per frame cannot be sharded over {self.shard_world} ranks')
             self.max_work_tokens = self.max_mem_frames * self.HW
             if self.use_long_term:
                 self.min_work_tokens = self.min_mem_frames * self.HW
@@ -188,6 +209,10 @@ class MemoryManager:
         self.CV = msk_value.shape[2]
         if selection is not None:
             selection = selection.flatten(2)
+        if self.shard_group is not None:                  # keep this rank's slice of the frame's tokens
+            sl = slice(self.shard_begin, self.shard_end)
+            key, shrinkage, msk_value = key[:, :, sl], shrinkage[:, :, sl], msk_value[:, :, :, sl]
+            selection = selection[:, :, sl] if selection is not None else None
 
         if obj_value is not None:                       # streaming sums (memory_manager.py:252-271)
             for i, obj in enumerate(objects):

@@ -29,10 +29,12 @@ def shard_bounds(n_total: int, world: int, rank: int):
     return begin, begin + base + (1 if rank < rem else 0)
 
 
-def sharded_read(local_segments: Sequence[BankSegment], index_offset: int, n_total: int, qk: torch.Tensor,
+def sharded_topk(local_segments: Sequence[BankSegment], index_offset: int, n_total: int, qk: torch.Tensor,
                  qe: torch.Tensor, top_k: int, group=None, usage_acc_local: Optional[torch.Tensor] = None):
-    """local_segments: this rank's tokens (global indices index_offset .. index_offset + n_local).
-    Returns (readout [B,K,CV,Q] identical on every rank, idx [B,Q,kpad] global, weights [B,Q,kpad])."""
+    """The exchange step: local top-k -> all_gather of candidates -> merge.  local_segments: this rank's tokens
+    (global indices index_offset .. index_offset + n_local; only keys/shrinkage are read).
+    Returns (idx_local, w_local, idx, w): the global winners [B,Q,kpad] (identical on every rank) and the same lists
+    restricted to the tokens this rank owns (local indices, -1 / weight 0 elsewhere) for sharded_gather."""
     world = dist.get_world_size(group)
     n_local = sum(s.n for s in local_segments)
     B, CK, Q = qk.shape
@@ -64,10 +66,22 @@ def sharded_read(local_segments: Sequence[BankSegment], index_offset: int, n_tot
     mine = (idx >= index_offset) & (idx < index_offset + n_local)
     idx_local = torch.where(mine, idx - index_offset, torch.full_like(idx, -1))
     w_local = torch.where(mine, w, torch.zeros_like(w))
-    K = len(local_segments[0].values) if local_segments else 0
-    if n_local > 0 and K > 0:
-        out = K_.readout_gather(idx_local, w_local, local_segments)
-    else:
+    return idx_local, w_local, idx, w
+
+
+def sharded_gather(idx_local: torch.Tensor, w_local: torch.Tensor, local_segments: Sequence[BankSegment], group=None):
+    """Partial readout of the winners this rank owns, summed over the ranks: [B,K,CV,Q], identical everywhere."""
+    if not local_segments or sum(s.n for s in local_segments) == 0 or len(local_segments[0].values) == 0:
         raise ValueError('every rank needs at least one token and one object value array')
+    out = K_.readout_gather(idx_local, w_local, local_segments)
     dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
-    return out, idx, w
+    return out
+
+
+def sharded_read(local_segments: Sequence[BankSegment], index_offset: int, n_total: int, qk: torch.Tensor,
+                 qe: torch.Tensor, top_k: int, group=None, usage_acc_local: Optional[torch.Tensor] = None):
+    """local_segments: this rank's tokens (global indices index_offset .. index_offset + n_local).
+    Returns (readout [B,K,CV,Q] identical on every rank, idx [B,Q,kpad] global, weights [B,Q,kpad])."""
+    idx_local, w_local, idx, w = sharded_topk(local_segments, index_offset, n_total, qk, qe, top_k, group,
+                                              usage_acc_local)
+    return sharded_gather(idx_local, w_local, local_segments, group), idx, w

@@ -51,3 +51,50 @@ def test_sharded_read_nccl(n_total):
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, 29641 + n_total % 97, n_total, ret), nprocs=world, join=True)
     assert all(ret.get(r) for r in range(world)), dict(ret)
+
+
+def _stream_worker(rank, world, port, ret):
+    """One stream with its working memory key-sharded over the ranks (MemoryManager(shard_group=...)) against the
+    un-sharded run on the same GPU: same logits up to the summation order of the all-reduced readout."""
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    try:
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        from cutie_b200.config import default_config
+        from cutie_b200.inference.inference_core import InferenceCore
+        from cutie_b200.model.cutie import CUTIE
+        from oracle.synth import synthetic_state_dict, synthetic_video
+        cfg = default_config(mem_every=2, max_mem_frames=4)
+        net = CUTIE(cfg).eval()
+        net.load_state_dict(synthetic_state_dict(net.state_dict(), 0))
+        net = net.cuda()
+        T, K = 10, 3
+        frames, mask = synthetic_video(T, 240, 432, K, seed=3)
+        sharded = InferenceCore(net, cfg=cfg, memory_shard_group=dist.group.WORLD)
+        plain = InferenceCore(net, cfg=cfg)
+        worst = 0.0
+        with torch.inference_mode():
+            for ti in range(T):
+                args = (frames[ti].cuda(), mask.cuda()) if ti == 0 else (frames[ti].cuda(),)
+                kw = dict(objects=[1, 2, 3]) if ti == 0 else {}
+                sharded.step(*args, **kw)
+                plain.step(*args, **kw)
+                if ti > 0:
+                    worst = max(worst, float((sharded.last_logits - plain.last_logits).abs().max()))
+        torch.cuda.synchronize()
+        ret[rank] = worst
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs >= 2 GPUs')
+def test_key_sharded_stream_nccl():
+    world = min(torch.cuda.device_count(), 8)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_stream_worker, args=(world, 29877, ret), nprocs=world, join=True)
+    assert all(ret.get(r, 1e9) < 1e-3 for r in range(world)), dict(ret)

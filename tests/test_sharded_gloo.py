@@ -63,3 +63,77 @@ def test_shard_bounds_partition():
             assert segs[0][0] == 0 and segs[-1][1] == n
             assert all(segs[i][1] == segs[i + 1][0] for i in range(w - 1))
             assert max(e - b for b, e in segs) - min(e - b for b, e in segs) <= 1
+
+
+def _stream_worker(rank, world, port, ret):
+    """One video stream, working memory key-sharded over `world` ranks: every rank must produce the logits of the
+    un-sharded run (up to the fp32 summation order of the all-reduced readout) while holding 1/world of the bank."""
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from tests import cpu_kernels as ck
+        ck.install()
+        from cutie_b200.config import default_config
+        from cutie_b200.inference.inference_core import InferenceCore
+        from cutie_b200.inference.sharded import shard_bounds
+        from cutie_b200.model.cutie import CUTIE
+        from oracle.synth import synthetic_state_dict, synthetic_video
+        torch.set_num_threads(2)
+        cfg = default_config(mem_every=2, max_mem_frames=3, chunk_size=2)      # 3 objects in chunks of 2
+        net = CUTIE(cfg).eval()
+        net.load_state_dict(synthetic_state_dict(net.state_dict(), 0))
+        T, K = 8, 3
+        frames, mask = synthetic_video(T, 96, 160, K, seed=3)                   # 6 x 10 = 60 tokens per frame
+        sharded = InferenceCore(net, cfg=cfg, memory_shard_group=dist.group.WORLD)
+        plain = InferenceCore(net, cfg=cfg)
+        lo, hi = shard_bounds(60, world, rank)
+        worst = 0.0
+        ok = True
+        with torch.inference_mode():
+            for ti in range(T):
+                args = (frames[ti], mask) if ti == 0 else (frames[ti],)
+                kw = dict(objects=[1, 2, 3]) if ti == 0 else {}
+                ps = sharded.step(*args, **kw)
+                pp = plain.step(*args, **kw)
+                worst = max(worst, float((ps - pp).abs().max()))
+                if ti > 0:
+                    worst = max(worst, float((sharded.last_logits - plain.last_logits).abs().max()))
+                # same frames in memory, 1/world of their tokens here; the FIFO evicts whole frames on every rank
+                frames_in_mem = plain.memory.work_mem.size(0) // 60
+                ok = ok and sharded.memory.work_mem.size(0) == frames_in_mem * (hi - lo)
+                ok = ok and sharded.memory.work_mem.perm_size(0) == (hi - lo)
+        ret[rank] = (ok, worst)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_key_sharded_stream_matches_unsharded(world):
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 31500 + (os.getpid() + world * 13) % 2000
+    mp.spawn(_stream_worker, args=(world, port, ret), nprocs=world, join=True)
+    for r in range(world):
+        ok, worst = ret.get(r, (False, 1e9))
+        assert ok, f'rank {r}: shard sizes wrong'
+        assert worst < 2e-4, f'rank {r}: sharded stream deviates by {worst}'
+
+
+def test_key_sharding_rejects_long_term():
+    from cutie_b200.config import default_config
+    from cutie_b200.inference.memory_manager import MemoryManager
+    from cutie_b200.inference.object_manager import ObjectManager
+
+    class _Group:          # never touched: the constructor must refuse before any collective
+        pass
+    import torch.distributed as dist_
+    cfg = default_config(use_long_term=True)
+    orig = (dist_.get_world_size, dist_.get_rank)
+    dist_.get_world_size, dist_.get_rank = (lambda g=None: 2), (lambda g=None: 0)
+    try:
+        with pytest.raises(NotImplementedError):
+            MemoryManager(cfg, ObjectManager(), shard_group=_Group())
+    finally:
+        dist_.get_world_size, dist_.get_rank = orig
