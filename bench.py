@@ -79,7 +79,44 @@ def synthetic_bank_chunks(wl, chunk_frames=16, seed=1234):
         done += n
 
 
+def _nvml_handle(idx):
+    """NVML handle of torch device `idx` (honours CUDA_VISIBLE_DEVICES through the device's UUID), or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(idx).uuid)
+        for cand in (f'GPU-{uuid}', uuid):
+            try:
+                return pynvml, pynvml.nvmlDeviceGetHandleByUUID(cand.encode())
+            except Exception:
+                pass
+        return pynvml, pynvml.nvmlDeviceGetHandleByIndex(idx)
+    except Exception:
+        return None
+
+
 def nvsmi_sampler(stop, out, idx):
+    """Samples SM clock, power and throttle reasons DURING the timed region: NVML in-process every ~5 ms (the
+    timed region of a default run is a fraction of a second), `nvidia-smi` every 0.2 s if NVML is unavailable.
+    Rows: [sm_mhz, sm_max_mhz, power_w, hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap]."""
+    nv = _nvml_handle(idx)
+    if nv is not None:
+        pynvml, h = nv
+        try:
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            bits = (('hw_slowdown', pynvml.nvmlClocksThrottleReasonHwSlowdown),
+                    ('hw_thermal_slowdown', pynvml.nvmlClocksThrottleReasonHwThermalSlowdown),
+                    ('sw_thermal_slowdown', pynvml.nvmlClocksThrottleReasonSwThermalSlowdown),
+                    ('sw_power_cap', pynvml.nvmlClocksThrottleReasonSwPowerCap))
+            while not stop.is_set():
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                out.append([str(sm), str(mx), f'{pw:.2f}'] + ['Active' if r & b else 'Not Active' for _, b in bits])
+                stop.wait(0.005)
+            return
+        except Exception as e:                       # noqa: BLE001 -- fall through to nvidia-smi
+            log(f'[clocks] NVML sampling failed ({type(e).__name__}: {e}); using nvidia-smi')
     q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
     while not stop.is_set():
@@ -119,7 +156,8 @@ def run_ours(args, wl, rank, world, dev):
     cfg = make_cfg(wl)
     net = make_net(cfg).to(dev)
     if not args.no_optimize:
-        net.optimize_for_inference()          # BN folding + channels-last trunks (still PyTorch/cuDNN calls)
+        # BN folding + channels-last trunks + conv/bias/ReLU epilogues in one cuDNN call (still PyTorch/cuDNN calls)
+        net.optimize_for_inference(fuse_epilogues=not args.no_fuse_epilogues)
     n_frames = args.warmup + args.steps + 2
     frames, mask = synthetic_video(n_frames, wl['H'], wl['W'], wl['K'], seed=rank)
     objs = list(range(1, wl['K'] + 1))
@@ -232,7 +270,10 @@ def run_ours(args, wl, rank, world, dev):
         torch.distributed.all_reduce(times, op=torch.distributed.ReduceOp.MAX)
     ms_total, ms_e2e = float(times[0]), float(times[1])
     log(f'[rank {rank}] host enqueue time per step: device arm {host_ms_dev:.2f} ms, e2e arm {host_ms_e2e:.2f} ms')
-    return dict(host_ms=[host_ms_dev, host_ms_e2e], phases=phases, image_levels=K_.image_level_launches(), ms_total=ms_total, ms_e2e=ms_e2e, kernel_ms=kernel_ms, launches=launches, n_tokens=n_tokens,
+    epi = net.conv_epilogues.report() if hasattr(net, 'conv_epilogues') else None
+    if epi:
+        log(f'[rank {rank}] conv epilogues: {epi}')
+    return dict(epilogues=epi, host_ms=[host_ms_dev, host_ms_e2e], phases=phases, image_levels=K_.image_level_launches(), ms_total=ms_total, ms_e2e=ms_e2e, kernel_ms=kernel_ms, launches=launches, n_tokens=n_tokens,
                 clocks=summarize_clocks(samples), h2d=frames_pin[0].numel() * 4, d2h=host_out.numel())
 
 
@@ -285,6 +326,8 @@ def main():
     ap.add_argument('--phase-timing', action='store_true', help='per-launch device times inside cutie_affinity_topk')
     ap.add_argument('--no-key-image', action='store_true', help='convert memory keys inside the filter (no operand image)')
     ap.add_argument('--no-graphs', action='store_true', help='eager launches only (no CUDA-graph frame regions)')
+    ap.add_argument('--no-fuse-epilogues', action='store_true',
+                    help='keep convolution, bias add and ReLU as three launches (no cuDNN fused conv-bias-activation)')
     ap.add_argument('--cpu-seconds', type=float, default=150.0)
     args = ap.parse_args()
     if args.warmup < 3:
@@ -401,6 +444,7 @@ def main():
             'gpu_launches': res['launches'], 'roofline': roof, 'cpu_baseline': cpu, 'kernels': kshare,
             'host_enqueue_ms_per_step': {'device_arm': res['host_ms'][0], 'e2e_arm': res['host_ms'][1]},
             'affinity_phases_ms': res['phases'] or None, 'key_image_levels': res['image_levels']}
+    line['config']['conv_epilogues'] = res['epilogues']     # which conv+bias(+add)+ReLU calls won their on-device trial
     emit(line)
 
 

@@ -11,6 +11,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from cutie_b200.model.fuse import conv_add_relu, conv_relu
+
 
 class _Residual(nn.Module):
     """One residual unit; `widths` lists the conv output widths, `ksizes` their kernel sizes."""
@@ -31,6 +33,14 @@ class _Residual(nn.Module):
             self.downsample = None
 
     def forward(self, x):
+        if getattr(self, 'bn_folded', False):
+            # BatchNorms folded into the convolutions (fuse.fold_trunk_): every ReLU and the residual add ride in
+            # the convolution's epilogue where cuDNN's fused graph wins its on-device trial (fuse.ConvEpilogueFuser)
+            y = x
+            for i in range(1, self.n):
+                y = conv_relu(getattr(self, f'conv{i}'), y)
+            skip = x if self.downsample is None else self.downsample(x)
+            return conv_add_relu(getattr(self, f'conv{self.n}'), y, skip)
         y = x
         for i in range(1, self.n + 1):
             y = getattr(self, f'bn{i}')(getattr(self, f'conv{i}')(y))

@@ -12,6 +12,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from cutie_b200 import kernels as K_
+from cutie_b200.model.fuse import conv_relu
 
 
 def fold(g: torch.Tensor) -> torch.Tensor:
@@ -48,7 +49,7 @@ class ChannelAttnResBlock(nn.Module):
         self.downsample = nn.Identity() if c_in == c_out else nn.Conv2d(c_in, c_out, 1)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        y = self.conv2(F.relu(self.conv1(F.relu(x))))
+        y = self.conv2(conv_relu(self.conv1, F.relu(x)))
         gate = self.conv(y.mean(dim=(2, 3)).unsqueeze(1)).sigmoid().transpose(1, 2).unsqueeze(-1)
         return y * gate + self.downsample(x)
 
@@ -63,7 +64,8 @@ class ObjResBlock(nn.Module):
         self.conv2 = ObjConv2d(c_out, c_out, 3, padding=1)
 
     def forward(self, g):
-        y = self.conv2(F.relu(self.conv1(F.relu(g))))
+        B = g.shape[0]
+        y = self.conv2(unfold(conv_relu(self.conv1, fold(F.relu(g))), B))
         return y + self.downsample(g)
 
 

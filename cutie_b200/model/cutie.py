@@ -173,11 +173,13 @@ class CUTIE(nn.Module):
                 log.info(f'Key {k} found in self.state_dict() but not in src_dict!!!')
         self.load_state_dict(src_dict, strict=False)
 
-    def optimize_for_inference(self, channels_last: bool = True) -> 'CUTIE':
+    def optimize_for_inference(self, channels_last: bool = True, fuse_epilogues: bool = True) -> 'CUTIE':
         """Post-load surgery on the PyTorch/cuDNN stages (cutie_b200/model/fuse.py): fold the frozen BatchNorms of
-        both ResNet trunks into their convolutions and run the trunks channels-last.  Numerically equivalent up to
-        fp32 rounding; the module tree (hence state_dict) of the trunks changes, so call it after load_weights."""
-        from cutie_b200.model.fuse import fold_trunk_
+        both ResNet trunks into their convolutions, run the trunks channels-last, and let conv+bias(+residual)+ReLU
+        go through cuDNN's fused graph wherever its on-device trial matches and beats the three-launch form
+        (`fuse.ConvEpilogueFuser`, kept as `self.conv_epilogues`).  Numerically equivalent up to fp32 rounding; the module
+        tree (hence state_dict) of the trunks changes, so call it after load_weights."""
+        from cutie_b200.model.fuse import ConvEpilogueFuser, attach_epilogue_fuser, fold_trunk_
         for enc in (self.pixel_encoder, self.mask_encoder):
             fold_trunk_(enc)
             if channels_last:
@@ -186,6 +188,9 @@ class CUTIE(nn.Module):
                     if m is not None:
                         m.to(memory_format=torch.channels_last)
                 enc.channels_last = True
+        # after the folding: fold_trunk_ replaces the trunk convolutions by new modules
+        object.__setattr__(self, 'conv_epilogues', ConvEpilogueFuser(enabled=bool(fuse_epilogues)))
+        attach_epilogue_fuser(self, self.conv_epilogues)
         return self
 
     @property

@@ -9,6 +9,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from cutie_b200.model.backbone import ResNetTrunk
+from cutie_b200.model.fuse import conv_relu
 from cutie_b200.model.blocks import (DeepSensoryUpdater, FeatureFusion, MultiScaleSensoryUpdater, ObjConv2d,
                                      UpsampleBlock, fold, unfold)
 
@@ -32,7 +33,10 @@ class PixelEncoder(nn.Module):
     def forward(self, x):
         if self.channels_last:
             x = x.contiguous(memory_format=torch.channels_last)
-        x = F.max_pool2d(F.relu(self.bn1(self.conv1(x)), inplace=True), 3, stride=2, padding=1)
+        if getattr(self, 'bn_folded', False):
+            x = F.max_pool2d(conv_relu(self.conv1, x), 3, stride=2, padding=1)
+        else:
+            x = F.max_pool2d(F.relu(self.bn1(self.conv1(x)), inplace=True), 3, stride=2, padding=1)
         f4 = self.res2(x)
         f8 = self.layer2(f4)
         return self.layer3(f8), f8, f4
@@ -83,7 +87,11 @@ class MaskEncoder(nn.Module):
             t = fold(g[:, lo:hi])
             if self.channels_last:
                 t = t.contiguous(memory_format=torch.channels_last)
-            t = F.relu(F.max_pool2d(self.bn1(self.conv1(t)), 3, stride=2, padding=1))
+            if getattr(self, 'bn_folded', False):
+                # relu and max-pool commute (both monotone): relu(maxpool(y)) == maxpool(relu(y)), bit for bit
+                t = F.max_pool2d(conv_relu(self.conv1, t), 3, stride=2, padding=1)
+            else:
+                t = F.relu(F.max_pool2d(self.bn1(self.conv1(t)), 3, stride=2, padding=1))
             t = self.layer3(self.layer2(self.layer1(t)))
             if self.channels_last:
                 t = t.contiguous()

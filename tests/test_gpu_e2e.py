@@ -196,14 +196,15 @@ def test_cuda_graph_frame_path_matches_eager():
 
 
 def test_optimize_for_inference_keeps_parity():
-    """BN folding + channels-last trunks + CUDA graphs (the bench configuration) vs the plain eager model."""
+    """BN folding + channels-last trunks + CUDA graphs vs the plain eager model (the fused conv epilogues the
+    bench adds on top are compared with this configuration in tests/test_gpu_zz_conv_epilogues.py)."""
     from cutie_b200.config import default_config
     from cutie_b200.inference.inference_core import InferenceCore
     from oracle.synth import synthetic_video
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     cfg = default_config(mem_every=2, max_mem_frames=3)
-    plain, fast = _net(cfg), _net(cfg).optimize_for_inference()
+    plain, fast = _net(cfg), _net(cfg).optimize_for_inference(fuse_epilogues=False)
     a, b = InferenceCore(plain, cfg=cfg), InferenceCore(fast, cfg=cfg, use_cuda_graphs=True)
     frames, mask = synthetic_video(5, 96, 160, 3, seed=3)
     with torch.inference_mode():
