@@ -77,9 +77,72 @@ __global__ void __launch_bounds__(256) prob_to_mask_kernel(const float* __restri
   out[i] = lut[arg];
 }
 
+// y = act(y + bias[c] (+ z)) in place -- the epilogue of a cuDNN convolution that was called WITHOUT its bias.
+// PyTorch's cudnn_convolution adds the bias with a broadcast TensorIterator kernel (elementwise_kernel<128,2>, offset
+// calculator per element, no vector accesses: 6.5 us for a 5 MB map, 29 us for 40 MB) and the ReLU / residual add with
+// further launches; this is one float4 grid-stride stream.  Same association as ATen: (y + bias) + z, then the clamp;
+// NaN propagates like clamp_min.  CL = channels-last storage [N, HW, C]; otherwise [N, C, HW].
+template <bool CL, bool VEC>
+__global__ void __launch_bounds__(256) bias_act_kernel(float* __restrict__ y, const float* __restrict__ bias,
+                                                       const float* __restrict__ z, long long total, int C,
+                                                       long long HW, int relu) {
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
+    if (VEC) {
+      const long long e = i * 4;
+      float4 v = reinterpret_cast<const float4*>(y)[i];
+      float4 b;
+      if (CL) {
+        b = __ldg(reinterpret_cast<const float4*>(bias + (int)(e % C)));
+      } else {
+        const float bb = __ldg(bias + (int)((e / HW) % C));
+        b = make_float4(bb, bb, bb, bb);
+      }
+      v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+      if (z) {
+        const float4 r = __ldg(reinterpret_cast<const float4*>(z) + i);
+        v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+      }
+      if (relu) {
+        v.x = v.x < 0.f ? 0.f : v.x; v.y = v.y < 0.f ? 0.f : v.y;
+        v.z = v.z < 0.f ? 0.f : v.z; v.w = v.w < 0.f ? 0.f : v.w;
+      }
+      reinterpret_cast<float4*>(y)[i] = v;
+    } else {
+      float v = y[i] + __ldg(bias + (CL ? (int)(i % C) : (int)((i / HW) % C)));
+      if (z) v += __ldg(z + i);
+      if (relu) v = v < 0.f ? 0.f : v;
+      y[i] = v;
+    }
+  }
+}
+
 }  // namespace cutie
 
 using namespace cutie;
+
+extern "C" int cutie_bias_act(float* y, const float* bias, const float* z, int64_t N, int64_t C, int64_t HW,
+                              int channels_last, int relu, void* stream) {
+  CUTIE_REQUIRE(y && bias && N >= 1 && C >= 1 && HW >= 1, "null/empty argument");
+  CUTIE_REQUIRE(C < (1LL << 31) && N * C * HW < (1LL << 60), "tensor too large");
+  const long long n = (long long)N * C * HW;
+  const bool aligned = (((uintptr_t)y | (uintptr_t)(z ? z : y)) & 15) == 0;
+  const bool vec = aligned && (channels_last ? (C % 4 == 0 && ((uintptr_t)bias & 15) == 0) : (HW % 4 == 0));
+  const long long total = vec ? n / 4 : n;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (channels_last) {
+    if (vec) bias_act_kernel<true, true><<<(unsigned)blocks, 256, 0, st>>>(y, bias, z, total, (int)C, HW, relu);
+    else bias_act_kernel<true, false><<<(unsigned)blocks, 256, 0, st>>>(y, bias, z, total, (int)C, HW, relu);
+  } else {
+    if (vec) bias_act_kernel<false, true><<<(unsigned)blocks, 256, 0, st>>>(y, bias, z, total, (int)C, HW, relu);
+    else bias_act_kernel<false, false><<<(unsigned)blocks, 256, 0, st>>>(y, bias, z, total, (int)C, HW, relu);
+  }
+  CUTIE_CHECK_LAUNCH();
+  return 0;
+}
 
 extern "C" int cutie_prob_to_mask(const float* prob, int64_t plane_stride, int64_t row_stride, int64_t C, int64_t H,
                                   int64_t W, const int64_t* lut, int64_t* out, void* stream) {

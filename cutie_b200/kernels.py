@@ -314,6 +314,30 @@ def upsample2x_add(g: torch.Tensor, skip: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def bias_act_(y: torch.Tensor, bias: torch.Tensor, z: Optional[torch.Tensor] = None, relu: bool = False) -> torch.Tensor:
+    """In place y = act(y + bias[c] (+ z)) for a dense [N,C,H,W] tensor in NCHW or channels-last storage: the epilogue
+    of a cuDNN convolution called without its bias (one float4 stream instead of ATen's broadcast add + add + clamp)."""
+    assert y.dim() == 4 and y.dtype == torch.float32
+    N, C, H, W = y.shape
+    if y.is_contiguous():
+        cl = False
+    elif y.is_contiguous(memory_format=torch.channels_last):
+        cl = True
+    else:
+        raise KernelError('bias_act_: y must be dense NCHW or channels-last')
+    if z is not None:
+        assert z.shape == y.shape
+        if z.stride() != y.stride():            # other storage order: one copy into y's layout
+            z = torch.empty_like(y).copy_(z)
+    bias = bias.detach()
+    assert bias.shape == (C,) and bias.is_contiguous()
+    with _call('bias_act', 1):
+        st = lib().cutie_bias_act(_ptr(y), _ptr(bias), _ptr(z), _i64(N), _i64(C), _i64(H * W), int(cl), int(bool(relu)),
+                                  _stream())
+    _check(st, 'cutie_bias_act')
+    return y
+
+
 def prob_to_mask(prob: torch.Tensor, lut: torch.Tensor) -> torch.Tensor:
     """lut[argmax over channels] of a [C,H,W] probability map (any plane/row strides, unit pixel stride) -> int64 [H,W]."""
     C, H, W = prob.shape

@@ -40,44 +40,59 @@ def fold_trunk_(module: nn.Module) -> int:
 
 
 # ---------------------------------------------------------------------------------------------------
-# conv + bias (+ residual) + ReLU as ONE cuDNN call
+# convolution epilogues: bias (+ residual) (+ ReLU) without ATen's extra launches
 # ---------------------------------------------------------------------------------------------------
 class ConvEpilogueFuser:
-    """`relu(conv(x) + bias [+ z])` through cuDNN's fused conv-bias-add-activation graph
-    (`torch.cudnn_convolution_relu` / `torch.cudnn_convolution_add_relu`, the ops PyTorch's own frozen-graph
-    pass emits) instead of three launches (convolution, broadcast bias add, clamp).
+    """`act(conv(x) + bias [+ z])` in fewer launches than PyTorch's convolution + broadcast bias add [+ add] [+ clamp].
 
-    On the round-1 launch list the trunks' bias adds and ReLUs were ~150 launches and ~1 ms of a 4.35 ms frame
-    (`profiles/r01_ncu_summary.md`: `elementwise_kernel<add>` 85/step at 8 us, `clamp_scalar` 62/step at 4.8 us,
-    residual adds 26/step at 6.7 us).  These stay PyTorch/cuDNN calls -- only the call changes.
+    On the round-1 launch list those epilogue launches were ~180 per 4.35 ms frame and ~1.3 ms of it
+    (`profiles/r01_ncu_summary.md`: `elementwise_kernel<add>` 85/step at 8 us -- the bias adds, which ATen runs through
+    a broadcast TensorIterator with no vector accesses --, `clamp_scalar` 62/step at 4.8 us, residual adds 26/step at
+    6.7 us).  The convolutions themselves stay cuDNN calls (BASELINE.json north_star); three forms of the epilogue:
 
-    Nothing is assumed about how the fused engines behave on a given GPU / cuDNN build: the first time a
-    (layer, input geometry) pair is seen OUTSIDE a stream capture, both forms run on the live tensors, the fused
-    result must match the three-launch result, both are timed with CUDA events, and the faster one is kept
-    for that pair (`decisions`).  Any exception from the fused op keeps the three-launch form and is recorded in
-    `errors`.  CPU tensors (the oracle harness borrowing these modules) always take the three-launch form.
+      'aten'    F.conv2d(x, w, b) [+ y.add_(z)] [+ relu_]                -- what PyTorch does; the reference form
+      'cudnn'   torch.cudnn_convolution_add_relu(x, w, z, alpha, b, ..)  -- cuDNN's fused conv-bias-add-ReLU graph (the
+                op PyTorch's own frozen-graph pass emits); ReLU epilogues only
+      'kernel'  F.conv2d(x, w, None) + cutie_bias_act(y, b, z, relu)     -- the bias-less convolution followed by ONE
+                float4 stream of ours (csrc/pixel.cu), same association as 'aten' => bit-identical results
+
+    Nothing is assumed about how any form behaves on a given GPU / cuDNN build: the first time a (layer, input geometry,
+    epilogue) triple is seen OUTSIDE a stream capture, every applicable form runs on the live tensors, a candidate must
+    match 'aten', all are timed with CUDA events, and the fastest is kept for that triple (`decisions`, `timings`).
+    A form that raises is dropped for that triple and recorded in `errors`.  CPU tensors (the oracle harness borrowing
+    these modules) always take 'aten'.
 
     `cudnn_convolution_relu` hands the *uninitialised* output to cuDNN as the residual operand with alpha = 0;
     0 x (stale NaN bits) is NaN, so the no-residual case passes a persistent zero tensor of the output shape
     instead (read once per call, ~100 MB per 480p frame over all layers: 15 us of HBM time).
     """
+    FORMS = ('aten', 'cudnn', 'kernel')
 
-    def __init__(self, enabled: bool = True, trial_iters: int = 6):
+    def __init__(self, enabled: bool = True, trial_iters: int = 6, forms=FORMS):
         self.enabled = enabled
         self.trial_iters = trial_iters
-        self.decisions = {}          # key -> True (fused) / False (three launches)
-        self.timings = {}            # key -> (fused_ms, unfused_ms)
+        self.forms = tuple(forms)
+        self.decisions = {}          # key -> form name
+        self.timings = {}            # key -> {form: ms}
         self.errors = []
         self._zeros = {}
 
-    # -- the two forms --------------------------------------------------------------------------------
+    # -- the forms ------------------------------------------------------------------------------------
     @staticmethod
-    def unfused(conv: nn.Conv2d, x: torch.Tensor, z=None) -> torch.Tensor:
-        # nn.Conv2d's own convolution (not conv(x): ObjConv2d overrides forward for 5-D object tensors)
-        y = conv._conv_forward(x, conv.weight, conv.bias)
+    def _conv(conv: nn.Conv2d, x: torch.Tensor, with_bias: bool) -> torch.Tensor:
+        # nn.Conv2d's own convolution (class method: instances may carry a patched _conv_forward, and ObjConv2d
+        # overrides forward for 5-D object tensors)
+        return nn.Conv2d._conv_forward(conv, x, conv.weight, conv.bias if with_bias else None)
+
+    @classmethod
+    def unfused(cls, conv: nn.Conv2d, x: torch.Tensor, z=None, relu: bool = True) -> torch.Tensor:
+        """The 'aten' form."""
+        y = cls._conv(conv, x, True)
         if z is not None:
             y = y.add_(z) if not y.requires_grad else y + z
-        return torch.relu_(y) if not y.requires_grad else torch.relu(y)
+        if relu:
+            y = torch.relu_(y) if not y.requires_grad else torch.relu(y)
+        return y
 
     def _zero_like_output(self, conv: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
         n, _, h, w = x.shape
@@ -94,16 +109,29 @@ class ConvEpilogueFuser:
         return buf
 
     def fused(self, conv: nn.Conv2d, x: torch.Tensor, z=None) -> torch.Tensor:
+        """The 'cudnn' form (always with ReLU)."""
         if z is None:
             return torch.cudnn_convolution_add_relu(x, conv.weight, self._zero_like_output(conv, x), 0.0, conv.bias,
                                                     conv.stride, conv.padding, conv.dilation, conv.groups)
         return torch.cudnn_convolution_add_relu(x, conv.weight, z, 1.0, conv.bias,
                                                 conv.stride, conv.padding, conv.dilation, conv.groups)
 
-    # -- one-off trial per (layer, geometry) -------------------------------------------------------------
+    def kernel(self, conv: nn.Conv2d, x: torch.Tensor, z=None, relu: bool = True) -> torch.Tensor:
+        """The 'kernel' form: bias-less convolution + cutie_bias_act."""
+        from cutie_b200 import kernels as K_
+        return K_.bias_act_(self._conv(conv, x, False), conv.bias, z, relu)
+
+    def run(self, form: str, conv: nn.Conv2d, x: torch.Tensor, z=None, relu: bool = True) -> torch.Tensor:
+        if form == 'cudnn':
+            return self.fused(conv, x, z)
+        if form == 'kernel':
+            return self.kernel(conv, x, z, relu)
+        return self.unfused(conv, x, z, relu)
+
+    # -- one-off trial per (layer, geometry, epilogue) -------------------------------------------------------
     @staticmethod
-    def _key(conv, x, z):
-        return (id(conv), tuple(x.shape), tuple(x.stride()), x.dtype, z is not None,
+    def _key(conv, x, z, relu):
+        return (id(conv), tuple(x.shape), tuple(x.stride()), x.dtype, z is not None, bool(relu),
                 torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark)
 
     def _time(self, fn) -> float:
@@ -117,66 +145,94 @@ class ConvEpilogueFuser:
         b.synchronize()
         return a.elapsed_time(b) / self.trial_iters
 
-    def _trial(self, key, conv, x, z) -> bool:
-        try:
-            # the three-launch form adds z in place into a fresh tensor, never into z itself
-            ref = self.unfused(conv, x, z)
-            out = self.fused(conv, x, z)
-            scale = float(ref.abs().max()) + 1e-6
-            err = float((out - ref).abs().max())
-            tol = (2e-2 if torch.backends.cudnn.allow_tf32 else 2e-4) * scale
-            if not (err <= tol):                   # also catches NaN
-                self.errors.append(f'conv {tuple(conv.weight.shape)} on {tuple(x.shape)}: fused differs by {err:.3e} '
-                                   f'(scale {scale:.3e})')
-                return False
-            t_f = self._time(lambda: self.fused(conv, x, z))
-            t_u = self._time(lambda: self.unfused(conv, x, z))
-            self.timings[key] = (t_f, t_u)
-            return t_f <= t_u
-        except Exception as e:                     # noqa: BLE001 -- any cuDNN / dispatcher failure: keep three launches
-            self.errors.append(f'conv {tuple(conv.weight.shape)} on {tuple(x.shape)}: {type(e).__name__}: {e}')
-            return False
+    def _candidates(self, relu: bool):
+        return [f for f in self.forms if f != 'aten' and (relu or f != 'cudnn')]
+
+    def _trial(self, key, conv, x, z, relu) -> str:
+        what = f'conv {tuple(conv.weight.shape)} on {tuple(x.shape)}'
+        ref = self.unfused(conv, x, z, relu)
+        scale = float(ref.abs().max()) + 1e-6
+        times = {'aten': self._time(lambda: self.unfused(conv, x, z, relu))}
+        for form in self._candidates(relu):
+            try:
+                out = self.run(form, conv, x, z, relu)
+                err = float((out - ref).abs().max())
+                # 'kernel' repeats ATen's arithmetic on the same cuDNN call; 'cudnn' may pick another engine (another
+                # summation order / TF32 path) -- the check is against gross errors (layout, operand order), not rounding
+                tol = (2e-2 if torch.backends.cudnn.allow_tf32 else 2e-4) * scale
+                if not (err <= tol):               # also catches NaN
+                    self.errors.append(f'{what}: {form} differs by {err:.3e} (scale {scale:.3e})')
+                    continue
+                times[form] = self._time(lambda: self.run(form, conv, x, z, relu))
+            except Exception as e:                 # noqa: BLE001 -- any cuDNN / dispatcher / launch failure: drop the form
+                self.errors.append(f'{what}: {form}: {type(e).__name__}: {e}')
+        self.timings[key] = times
+        return min(times, key=times.get)
 
     def _eligible(self, conv: nn.Conv2d, x: torch.Tensor) -> bool:
         return (self.enabled and x.is_cuda and conv.bias is not None and conv.padding_mode == 'zeros'
-                and x.dim() == 4 and not torch.is_grad_enabled())
+                and x.dim() == 4 and x.dtype == torch.float32 and not torch.is_grad_enabled())
 
     @staticmethod
     def _capturing() -> bool:
         return torch.cuda.is_current_stream_capturing()
 
-    def __call__(self, conv: nn.Conv2d, x: torch.Tensor, z=None) -> torch.Tensor:
+    def __call__(self, conv: nn.Conv2d, x: torch.Tensor, z=None, relu: bool = True) -> torch.Tensor:
         if not self._eligible(conv, x):
-            return self.unfused(conv, x, z)
-        key = self._key(conv, x, z)
-        use = self.decisions.get(key)
-        if use is None:
+            return self.unfused(conv, x, z, relu)
+        key = self._key(conv, x, z, relu)
+        form = self.decisions.get(key)
+        if form is None:
             if self._capturing():
-                return self.unfused(conv, x, z)    # no timing inside a capture; _Captured warms up outside one first
-            use = self.decisions[key] = self._trial(key, conv, x, z)
-        return self.fused(conv, x, z) if use else self.unfused(conv, x, z)
+                return self.unfused(conv, x, z, relu)   # no timing inside a capture; _Captured warms up outside one first
+            form = self.decisions[key] = self._trial(key, conv, x, z, relu)
+        return self.run(form, conv, x, z, relu)
+
+    def __deepcopy__(self, memo):          # a copied model gets its own (empty) fuser with the same settings
+        new = ConvEpilogueFuser(self.enabled, self.trial_iters, self.forms)
+        memo[id(self)] = new
+        return new
 
     def report(self) -> dict:
-        n_f = sum(1 for v in self.decisions.values() if v)
-        saved = sum(u - f for k, (f, u) in self.timings.items() if self.decisions.get(k))
-        return {'enabled': self.enabled, 'fused': n_f, 'three_launch': len(self.decisions) - n_f,
-                'errors': len(self.errors), 'first_error': self.errors[0] if self.errors else None,
-                'trial_ms_saved_per_pass': saved}
+        counts = {f: sum(1 for v in self.decisions.values() if v == f) for f in self.FORMS}
+        saved = sum(t['aten'] - t[self.decisions[k]] for k, t in self.timings.items() if k in self.decisions)
+        return {'enabled': self.enabled, **counts, 'errors': len(self.errors),
+                'first_error': self.errors[0] if self.errors else None, 'trial_ms_saved_per_pass': saved}
 
 
 def attach_epilogue_fuser(module: nn.Module, fuser: 'ConvEpilogueFuser') -> int:
-    """Hands `fuser` to every nn.Conv2d under `module` (plain attribute, not a parameter / buffer / sub-module, so
-    state_dict and .to() are unaffected).  Per model, not process-wide: an un-optimised model keeps three launches."""
+    """Hands `fuser` to every nn.Conv2d under `module` (plain attributes, not parameters / buffers / sub-modules, so
+    state_dict and .to() are unaffected).  Per model, not process-wide: an un-optimised model keeps PyTorch's launches.
+    Besides `epilogue_fuser` (read by conv_relu / conv_add_relu) each convolution's `_conv_forward` is pointed at the
+    fuser, so plain `conv(x)` calls -- no ReLU behind them -- get their bias from the fuser's choice as well."""
     n = 0
     for m in module.modules():
         if isinstance(m, nn.Conv2d):
             object.__setattr__(m, 'epilogue_fuser', fuser)
+            object.__setattr__(m, '_conv_forward', _BiasOnlyForward(m, fuser))
             n += 1
     return n
 
 
+class _BiasOnlyForward:
+    """Instance-level replacement of nn.Conv2d._conv_forward(input, weight, bias) (called by Conv2d.forward)."""
+
+    def __init__(self, conv: nn.Conv2d, fuser: ConvEpilogueFuser):
+        self.conv, self.fuser = conv, fuser
+
+    def __call__(self, x, weight, bias):
+        conv = self.conv
+        if bias is None or weight is not conv.weight or bias is not conv.bias:
+            return nn.Conv2d._conv_forward(conv, x, weight, bias)
+        return self.fuser(conv, x, None, relu=False)
+
+    def __deepcopy__(self, memo):          # a copied module must point at ITS convolution (already in memo) and fuser
+        import copy
+        return _BiasOnlyForward(copy.deepcopy(self.conv, memo), copy.deepcopy(self.fuser, memo))
+
+
 def conv_relu(conv: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
-    """relu(conv(x)) -- one cuDNN call where the model's fuser says so, else convolution + bias add + clamp."""
+    """relu(conv(x)) -- in the form the model's fuser chose for this layer, else convolution + bias add + clamp."""
     f = getattr(conv, 'epilogue_fuser', None)
     return ConvEpilogueFuser.unfused(conv, x) if f is None else f(conv, x)
 

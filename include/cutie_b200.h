@@ -118,6 +118,15 @@ int cutie_usage_commit(float* use_cnt, int64_t use_bstride, float* life_cnt, int
 int cutie_upsample2x_add(const float* g, const float* skip, float* out, int64_t B, int64_t K, int64_t C, int64_t h,
                          int64_t w, void* stream);
 
+/* y = act(y + bias[c] (+ z)) in place, act = ReLU if `relu` else identity: the epilogue of a convolution called
+ * without its bias.  Replaces the broadcast bias add inside every `nn.Conv2d` call on the frame path plus the
+ * `F.relu` / residual `+` that follow it in the reference's blocks (cutie/model/group_modules.py:46-64 GroupResBlock,
+ * cutie/model/channel_attn.py:27-38 CAResBlock, cutie/model/utils/resnet.py:77-131 BasicBlock/Bottleneck,
+ * cutie/model/big_modules.py:64-87 KeyProjection ...).  y (and z, if not null) dense fp32 [N,C,HW] when
+ * channels_last == 0, [N,HW,C] when 1; bias [C].  Association as in ATen: (y + bias) + z, then the clamp. */
+int cutie_bias_act(float* y, const float* bias, const float* z, int64_t N, int64_t C, int64_t HW, int channels_last,
+                   int relu, void* stream);
+
 /* out[y,x] = lut[argmax_c prob[c,y,x]]: InferenceCore.output_prob_to_mask (inference_core.py:377-385: argmax over
  * the 1+K channels, then ObjectManager.tmp_to_obj_cls object_manager.py:99-104) in one pass.  prob may be a strided
  * view (plane_stride / row_stride in elements, unit pixel stride); lut int64 [C]; out int64 [H,W] contiguous.

@@ -243,7 +243,15 @@ def qt_query_to_pixel(kfold, kdots, vfold, out_bias, pixel, pixel_pe, num_querie
     return res
 
 
-ALL = ['affinity_topk', 'topk_merge', 'readout_gather', 'usage_commit', 'bank_append', 'bank_export', 'bank_gather', 'bank_key_image', 'upsample2x_add', 'prob_to_mask',
+def bias_act_(y, bias, z=None, relu=False):
+    assert y.dim() == 4 and (y.is_contiguous() or y.is_contiguous(memory_format=torch.channels_last))
+    y.add_(bias.detach().view(1, -1, 1, 1))
+    if z is not None:
+        y.add_(z)
+    return torch.relu_(y) if relu else y
+
+
+ALL = ['bias_act_', 'affinity_topk', 'topk_merge', 'readout_gather', 'usage_commit', 'bank_append', 'bank_export', 'bank_gather', 'bank_key_image', 'upsample2x_add', 'prob_to_mask',
        'consolidate', 'obj_summary_accumulate', 'qt_linear', 'qt_head_fold', 'qt_self_attention',
        'qt_aux_mask', 'qt_pixel_to_query', 'qt_query_to_pixel']
 

@@ -1,22 +1,28 @@
-"""Host logic of fuse.ConvEpilogueFuser (conv + bias [+ residual] + ReLU as one cuDNN call, chosen per layer by
-an on-device trial).  No GPU here: the fused op is emulated and the trial clock is scripted, so what is tested
-is the wiring -- folded trunks route every ReLU / residual add through the fuser, the trial accepts, rejects and
-survives exceptions, and all forms agree with the un-folded modules."""
+"""Host logic of fuse.ConvEpilogueFuser: act(conv(x) + bias [+ z]) in the cheapest of three forms ('aten' = PyTorch's
+launches, 'cudnn' = cuDNN's fused conv-bias-add-ReLU graph, 'kernel' = bias-less convolution + cutie_bias_act), chosen
+per layer by an on-device trial.  No GPU here: the fused op is emulated, cutie_bias_act runs as its CPU emulation
+(tests/cpu_kernels.py) and the trial clock is scripted, so what is tested is the wiring -- folded trunks route every
+ReLU / residual add / bias through the fuser, the trial accepts, rejects and survives exceptions, and all forms agree
+with the un-folded modules."""
+import copy
+
 import pytest
 import torch
 import torch.nn.functional as F
 
 from cutie_b200.model import fuse
 from cutie_b200.model.backbone import ResNetTrunk
-from cutie_b200.model.blocks import ChannelAttnResBlock, ObjResBlock
+from cutie_b200.model.blocks import ChannelAttnResBlock, ObjConv2d, ObjResBlock
 
 
 class _FakeDeviceFuser(fuse.ConvEpilogueFuser):
-    def __init__(self, fused_ms=1.0, unfused_ms=3.0, broken=None):
-        super().__init__(enabled=True)
-        self.ms = {'fused': fused_ms, 'unfused': unfused_ms}
+    """Runs on CPU tensors; `ms` scripts the trial clock per form; `broken` makes the cuDNN form misbehave."""
+
+    def __init__(self, ms=None, broken=None, forms=fuse.ConvEpilogueFuser.FORMS):
+        super().__init__(enabled=True, forms=forms)
+        self.ms = {**dict(aten=3.0, cudnn=1.0, kernel=2.0), **(ms or {})}
         self.broken = broken
-        self.calls = {'fused': 0, 'unfused': 0}
+        self.calls = {'aten': 0, 'cudnn': 0, 'kernel': 0}
         self._which = None
 
     def _eligible(self, conv, x):
@@ -27,8 +33,8 @@ class _FakeDeviceFuser(fuse.ConvEpilogueFuser):
         return False
 
     def fused(self, conv, x, z=None):
-        self.calls['fused'] += 1
-        self._which = 'fused'
+        self.calls['cudnn'] += 1
+        self._which = 'cudnn'
         if self.broken == 'raise':
             raise RuntimeError('CUDNN_STATUS_NOT_SUPPORTED')
         y = F.conv2d(x, conv.weight, conv.bias, conv.stride, conv.padding, conv.dilation, conv.groups)
@@ -42,14 +48,19 @@ class _FakeDeviceFuser(fuse.ConvEpilogueFuser):
             y = y * float('nan')
         return torch.relu(y)
 
+    def kernel(self, conv, x, z=None, relu=True):
+        self.calls['kernel'] += 1
+        self._which = 'kernel'
+        return super().kernel(conv, x, z, relu)
+
     def _time(self, fn):
         fn()
         return self.ms[self._which]
 
-    def unfused(self, conv, x, z=None):
-        self.calls['unfused'] += 1
-        self._which = 'unfused'
-        return fuse.ConvEpilogueFuser.unfused(conv, x, z)
+    def unfused(self, conv, x, z=None, relu=True):
+        self.calls['aten'] += 1
+        self._which = 'aten'
+        return fuse.ConvEpilogueFuser.unfused(conv, x, z, relu)
 
 
 def _randomise_bn(m):
@@ -77,7 +88,7 @@ class _Trunk(torch.nn.Module):
 
 
 @pytest.mark.parametrize('arch', ['resnet18', 'resnet50'])
-def test_folded_trunk_routes_through_fuser_and_matches(arch):
+def test_folded_trunk_routes_through_fuser_and_matches(arch, cpu_kernels):
     torch.manual_seed(0)
     net = _Trunk(arch).eval()
     _randomise_bn(net)
@@ -86,8 +97,7 @@ def test_folded_trunk_routes_through_fuser_and_matches(arch):
         ref = net(x)
         n = fuse.fold_trunk_(net)
         assert net.bn_folded and all(getattr(u, 'bn_folded', False) for s in (net.layer1, net.layer2, net.layer3) for u in s)
-        # no fuser attached: the folded forward is convolution + add + clamp, as before
-        off = net(x)
+        off = net(x)                      # no fuser attached: convolution + add + clamp, as before
         f = _FakeDeviceFuser()
         assert fuse.attach_epilogue_fuser(net, f) == n
         on = net(x)
@@ -98,16 +108,18 @@ def test_folded_trunk_routes_through_fuser_and_matches(arch):
     assert float((on - ref).abs().max()) < 2e-5 * scale
     assert torch.equal(on, on2)
     rep = f.report()
-    downsamples = 3 if arch == 'resnet50' else 2         # projection shortcuts keep a plain convolution
-    assert rep['fused'] == n - downsamples and rep['three_launch'] == 0 and rep['errors'] == 0
-    # after the trials only the fused form runs: one call per decided layer, none of the three-launch form
-    assert f.calls['fused'] - calls_first['fused'] == rep['fused']
-    assert f.calls['unfused'] == calls_first['unfused']
-    assert rep['trial_ms_saved_per_pass'] == pytest.approx(2.0 * rep['fused'])
+    downsamples = 3 if arch == 'resnet50' else 2
+    # every conv with a ReLU behind it took the (scripted-fastest) cuDNN form, the projection shortcuts -- bias only,
+    # no ReLU, so no cuDNN form -- took ours
+    assert rep['cudnn'] == n - downsamples and rep['kernel'] == downsamples and rep['aten'] == 0 and rep['errors'] == 0
+    assert f.calls['cudnn'] - calls_first['cudnn'] == rep['cudnn']       # after the trials: one call per layer
+    assert f.calls['kernel'] - calls_first['kernel'] == rep['kernel']
+    assert f.calls['aten'] == calls_first['aten']
+    assert rep['trial_ms_saved_per_pass'] == pytest.approx(2.0 * rep['cudnn'] + 1.0 * rep['kernel'])
 
 
 @pytest.mark.parametrize('broken', ['raise', 'wrong', 'nan'])
-def test_trial_rejects_a_bad_fused_engine(broken):
+def test_trial_drops_a_bad_form_and_keeps_the_next_best(broken, cpu_kernels):
     torch.manual_seed(1)
     blk = ChannelAttnResBlock(8, 8).eval()
     x = torch.randn(2, 8, 12, 10)
@@ -117,29 +129,53 @@ def test_trial_rejects_a_bad_fused_engine(broken):
         fuse.attach_epilogue_fuser(blk, f)
         out = blk(x)
         out2 = blk(x)
-    assert torch.equal(out, ref) and torch.equal(out2, ref)
+    assert torch.equal(out, ref) and torch.equal(out2, ref)          # 'kernel' repeats ATen's arithmetic exactly
     rep = f.report()
-    assert rep['fused'] == 0 and rep['three_launch'] == 1 and rep['errors'] == 1 and rep['first_error']
+    # conv1 (+ReLU): cuDNN form rejected -> ours; conv2 (bias only): ours
+    assert rep['cudnn'] == 0 and rep['kernel'] == 2 and rep['aten'] == 0 and rep['errors'] == 1 and rep['first_error']
 
 
-def test_trial_keeps_three_launches_when_they_are_faster():
+def test_trial_keeps_pytorch_launches_when_they_are_fastest(cpu_kernels):
     torch.manual_seed(2)
     blk = ObjResBlock(6, 4).eval()
     g = torch.randn(1, 3, 6, 9, 7)
     with torch.inference_mode():
         ref = blk(g)
-        f = _FakeDeviceFuser(fused_ms=5.0, unfused_ms=3.0)
+        f = _FakeDeviceFuser(ms=dict(aten=1.0, cudnn=5.0, kernel=4.0))
         fuse.attach_epilogue_fuser(blk, f)
         out = blk(g)
-        n_fused = f.calls['fused']
+        n_other = f.calls['cudnn'] + f.calls['kernel']
         out = blk(g)
-    assert torch.allclose(out, ref, atol=1e-6)
-    assert f.report()['fused'] == 0 and f.calls['fused'] == n_fused      # never called again after losing the trial
+    assert torch.equal(out, ref)
+    rep = f.report()
+    assert rep['aten'] == 3 and rep['cudnn'] == 0 and rep['kernel'] == 0     # conv1, conv2, 1x1 downsample
+    assert f.calls['cudnn'] + f.calls['kernel'] == n_other                     # losers are never called again
 
 
-def test_cpu_tensors_never_reach_the_fused_op():
-    """The real fuser (enabled) must leave CPU tensors on the three-launch form: the oracle harness borrows these
-    modules on CPU, and torch.cudnn_convolution_add_relu does not exist there."""
+def test_kernel_form_handles_object_convs_residuals_and_layouts(cpu_kernels):
+    """ObjConv2d (5-D tensors through fold/unfold), residual operand, channels-last storage: 'kernel' == 'aten'."""
+    torch.manual_seed(4)
+    conv = ObjConv2d(5, 7, 3, padding=1).eval()
+    g = torch.randn(2, 3, 5, 6, 8)
+    f = _FakeDeviceFuser(forms=('aten', 'kernel'))
+    with torch.inference_mode():
+        ref = conv(g)
+        fuse.attach_epilogue_fuser(conv, f)
+        assert torch.equal(conv(g), ref) and f.report()['kernel'] == 1
+        plain = torch.nn.Conv2d(5, 7, 3, padding=1).eval()
+        x, z = torch.randn(2, 5, 6, 8), torch.randn(2, 7, 6, 8)
+        want = torch.relu(plain(x) + z)
+        fuse.attach_epilogue_fuser(plain, f)
+        assert torch.equal(fuse.conv_add_relu(plain, x, z), want)
+        xcl = x.contiguous(memory_format=torch.channels_last)
+        got = fuse.conv_add_relu(plain, xcl, z)                     # z in the other storage order
+        assert torch.allclose(got, want, atol=1e-6)
+    assert f.report()['errors'] == 0
+
+
+def test_cpu_tensors_never_reach_the_device_forms():
+    """The real fuser (enabled) must leave CPU tensors on PyTorch's launches: the oracle harness borrows these modules
+    on CPU, and neither torch.cudnn_convolution_add_relu nor cutie_bias_act exists there."""
     torch.manual_seed(3)
     blk = ChannelAttnResBlock(8, 8).eval()
     x = torch.randn(1, 8, 9, 9)
@@ -170,7 +206,6 @@ def test_optimize_for_inference_attaches_one_fuser_per_model():
     torch.manual_seed(0)
     net = CUTIE(cfg).eval()
     _randomise_bn(net)
-    keys_before = set(net.state_dict().keys())
     x = torch.randn(1, 3, 64, 96)
     with torch.inference_mode():
         ref = net.pixel_encoder(x)
@@ -178,11 +213,21 @@ def test_optimize_for_inference_attaches_one_fuser_per_model():
         out = net.pixel_encoder(x)
     convs = [m for m in net.modules() if isinstance(m, torch.nn.Conv2d)]
     assert convs and all(m.epilogue_fuser is net.conv_epilogues for m in convs)
-    assert net.conv_epilogues.enabled and not net.conv_epilogues.decisions      # CPU tensors: three launches
-    assert 'conv_epilogues' not in net.state_dict() and not any('epilogue' in k for k in net.state_dict())
+    assert net.conv_epilogues.enabled and not net.conv_epilogues.decisions      # CPU tensors: PyTorch's launches
+    assert not any('epilogue' in k or '_conv_forward' in k for k in net.state_dict())
     for a, b in zip(out, ref):
         assert float((a - b).abs().max()) <= 2e-5 * float(b.abs().max())
     other = CUTIE(cfg).eval()                                                    # an un-optimised model is untouched
     assert not hasattr(other, 'conv_epilogues')
-    assert all(not hasattr(m, 'epilogue_fuser') for m in other.modules())
-    assert keys_before  # (state_dict of the trunks changes by design: bn.* keys fold into conv bias)
+    assert all('epilogue_fuser' not in m.__dict__ and '_conv_forward' not in m.__dict__ for m in other.modules())
+    # a deep copy points at its own convolutions and its own (empty) fuser
+    dup = copy.deepcopy(net.key_proj)
+    for m in dup.modules():
+        if isinstance(m, torch.nn.Conv2d):
+            assert m._conv_forward.conv is m and m._conv_forward.fuser is m.epilogue_fuser
+            assert m.epilogue_fuser is not net.conv_epilogues
+    with torch.inference_mode():
+        f16 = torch.randn(1, 1024, 4, 6)
+        a = net.key_proj(f16, need_s=True, need_e=True)
+        b = dup(f16, need_s=True, need_e=True)
+    assert all(torch.equal(p, q) for p, q in zip(a, b))

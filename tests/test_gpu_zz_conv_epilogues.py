@@ -1,7 +1,8 @@
-"""conv + bias (+ residual) + ReLU through cuDNN's fused graph (cutie_b200/model/fuse.ConvEpilogueFuser) against the
-three-launch form, on the GPU.  These are PyTorch/cuDNN stages either side of the hot path (kept as library calls);
-what is asserted is that switching the call form changes nothing beyond fp32 rounding, whatever each layer's
-on-device trial decided.  (File name sorts last on purpose: it exercises cuDNN engines, not cutie_b200 kernels.)"""
+"""Convolution epilogues (cutie_b200/model/fuse.ConvEpilogueFuser): bias (+ residual) (+ ReLU) through cuDNN's fused
+graph or through cutie_bias_act after a bias-less convolution, against PyTorch's own launches, on the GPU.  The
+convolutions are PyTorch/cuDNN stages either side of the hot path (kept as library calls); what is asserted is that
+switching the epilogue form changes nothing beyond fp32 rounding, whatever each layer's on-device trial decided, and that
+cutie_bias_act itself is bit-identical to the ATen ops it replaces.  (The file name sorts last on purpose.)"""
 import pytest
 import torch
 
@@ -33,7 +34,7 @@ def test_trunks_fused_epilogues_match_three_launches():
         fz.enabled = True
     rep = fz.report()
     print('conv epilogues (pixel encoder, 240p, fp32):', rep)
-    assert rep['fused'] + rep['three_launch'] >= 40        # ResNet-50 stages 1-3: 1 stem + 39 convs with a ReLU
+    assert rep['aten'] + rep['cudnn'] + rep['kernel'] >= 43   # ResNet-50 stages 1-3: stem + 39 convs + 3 projection shortcuts
     for a, b, c in zip(out_f, out_f2, out_u):
         scale = float(c.abs().max())
         assert torch.isfinite(a).all()
@@ -64,3 +65,39 @@ def test_stream_with_fused_epilogues_matches_three_launches():
                 assert float((pa - pb).abs().max()) < 1e-3
     print('conv epilogues (stream, 96x160):', on.conv_epilogues.report())
     assert not off.conv_epilogues.decisions
+
+
+@pytest.mark.parametrize('shape', [(3, 256, 30, 54), (1, 1, 30, 54), (2, 7, 5, 3), (3, 128, 120, 216), (1, 64, 9, 11)])
+@pytest.mark.parametrize('cl', [False, True])
+@pytest.mark.parametrize('relu', [False, True])
+@pytest.mark.parametrize('with_z', [False, True])
+def test_bias_act_kernel_is_bit_identical_to_aten(shape, cl, relu, with_z):
+    """cutie_bias_act (vector and scalar paths, NCHW and channels-last, odd sizes) vs y.add_(bias).add_(z).relu_()."""
+    import cutie_b200.kernels as K_
+    g = torch.Generator().manual_seed(sum(shape) + 2 * cl + relu)
+    fmt = torch.channels_last if cl else torch.contiguous_format
+    y = torch.randn(*shape, generator=g).cuda().contiguous(memory_format=fmt)
+    z = torch.randn(*shape, generator=g).cuda() if with_z else None          # NCHW: exercises the layout copy when cl
+    bias = torch.randn(shape[1], generator=g).cuda()
+    want = y.clone() + bias.view(1, -1, 1, 1)
+    if z is not None:
+        want = want + z
+    if relu:
+        want = torch.relu(want)
+    got = K_.bias_act_(y.clone(memory_format=torch.preserve_format), bias, z, relu)
+    torch.cuda.synchronize()
+    assert got.stride() == y.stride()
+    assert torch.equal(got, want)
+
+
+def test_bias_act_misaligned_views_take_the_scalar_path():
+    import cutie_b200.kernels as K_
+    base = torch.randn(1 + 2 * 8 * 6 * 4).cuda()
+    y = base[1:].view(2, 8, 6, 4)                       # 4-byte aligned only
+    bias = torch.randn(8).cuda()
+    want = torch.relu(y + bias.view(1, -1, 1, 1))
+    got = K_.bias_act_(y.clone()[:], bias, None, True)  # clone is aligned: vector path
+    assert torch.equal(got, want)
+    got2 = K_.bias_act_(y, bias, None, True)            # in place on the misaligned view
+    torch.cuda.synchronize()
+    assert torch.equal(got2, want) and got2.data_ptr() == y.data_ptr()
