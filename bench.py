@@ -157,7 +157,7 @@ def run_ours(args, wl, rank, world, dev):
     net = make_net(cfg).to(dev)
     if not args.no_optimize:
         # BN folding + channels-last trunks + conv/bias/ReLU epilogues in one cuDNN call (still PyTorch/cuDNN calls)
-        net.optimize_for_inference(fuse_epilogues=not args.no_fuse_epilogues)
+        net.optimize_for_inference(fuse_epilogues=not args.no_fuse_epilogues, fuse_glue=not args.no_fuse_glue)
     n_frames = args.warmup + args.steps + 2
     frames, mask = synthetic_video(n_frames, wl['H'], wl['W'], wl['K'], seed=rank)
     objs = list(range(1, wl['K'] + 1))
@@ -273,7 +273,10 @@ def run_ours(args, wl, rank, world, dev):
     epi = net.conv_epilogues.report() if hasattr(net, 'conv_epilogues') else None
     if epi:
         log(f'[rank {rank}] conv epilogues: {epi}')
-    return dict(epilogues=epi, host_ms=[host_ms_dev, host_ms_e2e], phases=phases, image_levels=K_.image_level_launches(), ms_total=ms_total, ms_e2e=ms_e2e, kernel_ms=kernel_ms, launches=launches, n_tokens=n_tokens,
+    glue = net.op_trials.report() if hasattr(net, 'op_trials') else None
+    if glue:
+        log(f'[rank {rank}] glue ops: {glue}')
+    return dict(glue=glue, epilogues=epi, host_ms=[host_ms_dev, host_ms_e2e], phases=phases, image_levels=K_.image_level_launches(), ms_total=ms_total, ms_e2e=ms_e2e, kernel_ms=kernel_ms, launches=launches, n_tokens=n_tokens,
                 clocks=summarize_clocks(samples), h2d=frames_pin[0].numel() * 4, d2h=host_out.numel())
 
 
@@ -326,6 +329,8 @@ def main():
     ap.add_argument('--phase-timing', action='store_true', help='per-launch device times inside cutie_affinity_topk')
     ap.add_argument('--no-key-image', action='store_true', help='convert memory keys inside the filter (no operand image)')
     ap.add_argument('--no-graphs', action='store_true', help='eager launches only (no CUDA-graph frame regions)')
+    ap.add_argument('--no-fuse-glue', action='store_true',
+                    help='keep area down-sampling / CAResBlock tail / sensory gates as ATen launches')
     ap.add_argument('--no-fuse-epilogues', action='store_true',
                     help='keep convolution, bias add and ReLU as three launches (no cuDNN fused conv-bias-activation)')
     ap.add_argument('--cpu-seconds', type=float, default=150.0)
@@ -445,6 +450,7 @@ def main():
             'host_enqueue_ms_per_step': {'device_arm': res['host_ms'][0], 'e2e_arm': res['host_ms'][1]},
             'affinity_phases_ms': res['phases'] or None, 'key_image_levels': res['image_levels']}
     line['config']['conv_epilogues'] = res['epilogues']     # which conv+bias(+add)+ReLU calls won their on-device trial
+    line['config']['glue_ops'] = res['glue']                 # which ATen chains were replaced by cutie_b200 kernels
     emit(line)
 
 

@@ -117,6 +117,126 @@ __global__ void __launch_bounds__(256) bias_act_kernel(float* __restrict__ y, co
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Integer-factor area down-sampling (F.interpolate(mode='area') == adaptive_avg_pool2d when the sizes divide):
+// out[p, Y, X] = mean of the f x f window.  ATen's adaptive_average_pool kernel assigns whole planes to a handful of
+// CTAs: 15 CTAs / 46 us for the [3, 480, 864] -> [3, 30, 54] mask of cutie.py:149, ~33 us for the decoder's
+// [3, 256, 60, 108] / [3, 257, 120, 216] feature maps (modules.py:58-60).  One thread per output pixel here, rows
+// of the window read as float4 when the geometry allows; accumulation row-major in fp32, then one division.
+template <int F, bool VEC>
+__global__ void __launch_bounds__(128) area_pool_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                        long long total, int Ho, int Wo, int f_rt) {
+  const int f = F > 0 ? F : f_rt;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int X = (int)(t % Wo);
+  const int Y = (int)((t / Wo) % Ho);
+  const long long p = t / ((long long)Wo * Ho);
+  const long long W = (long long)Wo * f;
+  const float* src = in + (p * Ho * f + (long long)Y * f) * W + (long long)X * f;
+  float s = 0.f;
+  if (VEC) {                                               // f % 4 == 0, rows 16-byte aligned
+#pragma unroll
+    for (int r = 0; r < (F > 0 ? F : 1); ++r) {
+#pragma unroll
+      for (int c4 = 0; c4 < (F > 0 ? F / 4 : 1); ++c4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src + r * W) + c4);
+        s += v.x; s += v.y; s += v.z; s += v.w;
+      }
+    }
+  } else {
+    for (int r = 0; r < f; ++r)
+      for (int c = 0; c < f; ++c) s += __ldg(src + r * W + c);
+  }
+  out[t] = s / (float)(f * f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tail of the channel-attention residual block (cutie/model/channel_attn.py:27-38, CAResBlock):
+//   gate[n, c] = sigmoid( sum_j w[j] * mean[n, c + j - (k-1)/2] )      (Conv1d over channels, zero padded, no bias)
+//   out        = y * gate + x                                           (in place into y)
+// ATen: conv1d + sigmoid + mul + add = 4 launches and 5 passes over the feature map; here a (tiny) gate kernel and one
+// stream.  y * gate is rounded before the add, as in ATen (no FMA contraction).
+__global__ void __launch_bounds__(256) eca_gate_kernel(const float* __restrict__ mean, const float* __restrict__ w,
+                                                       float* __restrict__ gate, long long total, int C, int k) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int c = (int)(t % C);
+  const int pad = (k - 1) / 2;
+  float a = 0.f;
+  for (int j = 0; j < k; ++j) {
+    const int cc = c + j - pad;
+    if (cc >= 0 && cc < C) a = fmaf(__ldg(w + j), __ldg(mean + t + (j - pad)), a);
+  }
+  gate[t] = 1.f / (1.f + expf(-a));
+}
+
+template <bool CL, bool VEC>
+__global__ void __launch_bounds__(256) scale_add_kernel(float* __restrict__ y, const float* __restrict__ gate,
+                                                        const float* __restrict__ x, long long total, int C,
+                                                        long long HW) {
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
+    if (VEC) {
+      const long long e = i * 4;
+      float4 v = reinterpret_cast<const float4*>(y)[i];
+      const float4 r = __ldg(reinterpret_cast<const float4*>(x) + i);
+      float4 g;
+      if (CL) {
+        g = __ldg(reinterpret_cast<const float4*>(gate + (e / (HW * C)) * C + (e % C)));
+      } else {
+        const float gg = __ldg(gate + e / HW);
+        g = make_float4(gg, gg, gg, gg);
+      }
+      v.x = __fadd_rn(__fmul_rn(v.x, g.x), r.x); v.y = __fadd_rn(__fmul_rn(v.y, g.y), r.y);
+      v.z = __fadd_rn(__fmul_rn(v.z, g.z), r.z); v.w = __fadd_rn(__fmul_rn(v.w, g.w), r.w);
+      reinterpret_cast<float4*>(y)[i] = v;
+    } else {
+      const float g = __ldg(gate + (CL ? (i / (HW * C)) * C + (i % C) : i / HW));
+      y[i] = __fadd_rn(__fmul_rn(y[i], g), __ldg(x + i));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GRU-like sensory update (cutie/model/modules.py:37-45 _recurrent_update): v [P, 3d, HW] = [forget | update | candidate],
+//   out = sigmoid(vf) * h * (1 - sigmoid(vu)) + sigmoid(vu) * tanh(vn)
+// ATen: 2 sigmoid + tanh + mul + rsub + mul + mul + add = 8 launches; every product / sum is rounded as ATen rounds it.
+template <bool VEC>
+__global__ void __launch_bounds__(256) gated_update_kernel(const float* __restrict__ v, const float* __restrict__ h,
+                                                           float* __restrict__ out, long long total, int d,
+                                                           long long HW) {
+  const long long step = (long long)gridDim.x * blockDim.x;
+  const long long plane = (long long)d * HW;                   // elements of h per object
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
+    const long long e = VEC ? i * 4 : i;
+    const long long p = e / plane, r = e % plane;
+    const float* vf = v + p * 3 * plane + r;
+    float a[4], b[4], c[4], hh[4], o[4];
+    if (VEC) {
+      const float4 A = __ldg(reinterpret_cast<const float4*>(vf));
+      const float4 B = __ldg(reinterpret_cast<const float4*>(vf + plane));
+      const float4 Cc = __ldg(reinterpret_cast<const float4*>(vf + 2 * plane));
+      const float4 Hh = __ldg(reinterpret_cast<const float4*>(h) + i);
+      a[0] = A.x; a[1] = A.y; a[2] = A.z; a[3] = A.w;
+      b[0] = B.x; b[1] = B.y; b[2] = B.z; b[3] = B.w;
+      c[0] = Cc.x; c[1] = Cc.y; c[2] = Cc.z; c[3] = Cc.w;
+      hh[0] = Hh.x; hh[1] = Hh.y; hh[2] = Hh.z; hh[3] = Hh.w;
+    } else {
+      a[0] = __ldg(vf); b[0] = __ldg(vf + plane); c[0] = __ldg(vf + 2 * plane); hh[0] = __ldg(h + i);
+    }
+#pragma unroll
+    for (int q = 0; q < (VEC ? 4 : 1); ++q) {
+      const float f = 1.f / (1.f + expf(-a[q]));
+      const float u = 1.f / (1.f + expf(-b[q]));
+      const float n = tanhf(c[q]);
+      o[q] = __fadd_rn(__fmul_rn(__fmul_rn(f, hh[q]), __fsub_rn(1.f, u)), __fmul_rn(u, n));
+    }
+    if (VEC) reinterpret_cast<float4*>(out)[i] = make_float4(o[0], o[1], o[2], o[3]);
+    else out[i] = o[0];
+  }
+}
+
 }  // namespace cutie
 
 using namespace cutie;
@@ -166,6 +286,67 @@ extern "C" int cutie_upsample2x_add(const float* g, const float* skip, float* ou
     upsample2x_add_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(g, skip, out, planes, (int)K, (int)C, (int)h, (int)w);
   else
     upsample2x_add_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(g, skip, out, planes, (int)K, (int)C, (int)h, (int)w);
+  CUTIE_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int cutie_area_pool(const float* in, float* out, int64_t planes, int64_t H, int64_t W, int64_t f, void* stream) {
+  CUTIE_REQUIRE(in && out && planes >= 1 && H >= 1 && W >= 1 && f >= 1, "null/empty argument");
+  CUTIE_REQUIRE(H % f == 0 && W % f == 0, "sizes must be multiples of the factor");
+  CUTIE_REQUIRE(H < (1 << 20) && W < (1 << 20) && f <= 64, "feature map / factor too large");
+  const int Ho = (int)(H / f), Wo = (int)(W / f);
+  const long long total = (long long)planes * Ho * Wo;
+  const unsigned blocks = (unsigned)((total + 127) / 128);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool vec = (f % 4 == 0) && (W % 4 == 0) && (((uintptr_t)in & 15) == 0);
+  if (f == 16 && vec) area_pool_kernel<16, true><<<blocks, 128, 0, st>>>(in, out, total, Ho, Wo, (int)f);
+  else if (f == 4 && vec) area_pool_kernel<4, true><<<blocks, 128, 0, st>>>(in, out, total, Ho, Wo, (int)f);
+  else if (f == 2) area_pool_kernel<2, false><<<blocks, 128, 0, st>>>(in, out, total, Ho, Wo, (int)f);
+  else area_pool_kernel<0, false><<<blocks, 128, 0, st>>>(in, out, total, Ho, Wo, (int)f);
+  CUTIE_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int cutie_eca_scale_add(float* y, const float* x, const float* mean, const float* w, float* gate, int64_t N,
+                                   int64_t C, int64_t HW, int64_t k, int channels_last, void* stream) {
+  CUTIE_REQUIRE(y && x && mean && w && gate && N >= 1 && C >= 1 && HW >= 1, "null/empty argument");
+  CUTIE_REQUIRE(k >= 1 && k <= 15 && (k & 1), "kernel size must be odd and <= 15");
+  CUTIE_REQUIRE(C < (1LL << 31) && N * C * HW < (1LL << 60), "tensor too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long nc = (long long)N * C;
+  eca_gate_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(mean, w, gate, nc, (int)C, (int)k);
+  CUTIE_CHECK_LAUNCH();
+  const long long n = nc * HW;
+  const bool aligned = (((uintptr_t)y | (uintptr_t)x) & 15) == 0;
+  const bool vec = aligned && (channels_last ? (C % 4 == 0 && ((uintptr_t)gate & 15) == 0) : (HW % 4 == 0));
+  const long long total = vec ? n / 4 : n;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (channels_last) {
+    if (vec) scale_add_kernel<true, true><<<(unsigned)blocks, 256, 0, st>>>(y, gate, x, total, (int)C, HW);
+    else scale_add_kernel<true, false><<<(unsigned)blocks, 256, 0, st>>>(y, gate, x, total, (int)C, HW);
+  } else {
+    if (vec) scale_add_kernel<false, true><<<(unsigned)blocks, 256, 0, st>>>(y, gate, x, total, (int)C, HW);
+    else scale_add_kernel<false, false><<<(unsigned)blocks, 256, 0, st>>>(y, gate, x, total, (int)C, HW);
+  }
+  CUTIE_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int cutie_gated_update(const float* v, const float* h, float* out, int64_t P, int64_t d, int64_t HW,
+                                  void* stream) {
+  CUTIE_REQUIRE(v && h && out && P >= 1 && d >= 1 && HW >= 1, "null/empty argument");
+  CUTIE_REQUIRE(d < (1LL << 31) && P * d * HW < (1LL << 59), "tensor too large");
+  const long long n = (long long)P * d * HW;
+  const bool vec = (HW % 4 == 0) && ((((uintptr_t)v | (uintptr_t)h | (uintptr_t)out) & 15) == 0);
+  const long long total = vec ? n / 4 : n;
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (vec) gated_update_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(v, h, out, total, (int)d, HW);
+  else gated_update_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(v, h, out, total, (int)d, HW);
   CUTIE_CHECK_LAUNCH();
   return 0;
 }

@@ -338,6 +338,54 @@ def bias_act_(y: torch.Tensor, bias: torch.Tensor, z: Optional[torch.Tensor] = N
     return y
 
 
+def area_pool(x: torch.Tensor, f: int) -> torch.Tensor:
+    """F.interpolate(x, scale_factor=1/f, mode='area') for [..., H, W] with H % f == W % f == 0."""
+    H, W = x.shape[-2:]
+    assert x.dtype == torch.float32 and H % f == 0 and W % f == 0
+    x = x.contiguous()
+    out = torch.empty(*x.shape[:-2], H // f, W // f, dtype=torch.float32, device=x.device)
+    planes = x.numel() // (H * W)
+    with _call('area_pool', 1):
+        st = lib().cutie_area_pool(_ptr(x), _ptr(out), _i64(planes), _i64(H), _i64(W), _i64(f), _stream())
+    _check(st, 'cutie_area_pool')
+    return out
+
+
+def eca_scale_add_(y: torch.Tensor, x: torch.Tensor, conv1d_weight: torch.Tensor) -> torch.Tensor:
+    """In place y = y * sigmoid(conv1d(mean_hw(y))) + x -- the tail of ChannelAttnResBlock (the spatial mean stays an
+    ATen reduction).  y [N,C,H,W] dense NCHW or channels-last; x same shape; conv1d_weight [1,1,k]."""
+    assert y.dim() == 4 and y.dtype == torch.float32 and x.shape == y.shape
+    N, C, H, W = y.shape
+    if y.is_contiguous():
+        cl = False
+    elif y.is_contiguous(memory_format=torch.channels_last):
+        cl = True
+    else:
+        raise KernelError('eca_scale_add_: y must be dense NCHW or channels-last')
+    if x.stride() != y.stride():
+        x = torch.empty_like(y).copy_(x)
+    w = conv1d_weight.detach().reshape(-1)
+    mean = y.mean(dim=(2, 3)).contiguous()
+    gate = torch.empty_like(mean)
+    with _call('eca_scale_add', 2):
+        st = lib().cutie_eca_scale_add(_ptr(y), _ptr(x), _ptr(mean), _ptr(w), _ptr(gate), _i64(N), _i64(C), _i64(H * W),
+                                       _i64(w.numel()), int(cl), _stream())
+    _check(st, 'cutie_eca_scale_add')
+    return y
+
+
+def gated_update(h: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
+    """GRU-like sensory update: h [B,K,d,H,W], v [B,K,3d,H,W] = [forget | update | candidate] -> [B,K,d,H,W]."""
+    B, K, d, H, W = h.shape
+    assert v.shape == (B, K, 3 * d, H, W) and h.dtype == torch.float32 and v.dtype == torch.float32
+    h, v = h.contiguous(), v.contiguous()
+    out = torch.empty_like(h)
+    with _call('gated_update', 1):
+        st = lib().cutie_gated_update(_ptr(v), _ptr(h), _ptr(out), _i64(B * K), _i64(d), _i64(H * W), _stream())
+    _check(st, 'cutie_gated_update')
+    return out
+
+
 def prob_to_mask(prob: torch.Tensor, lut: torch.Tensor) -> torch.Tensor:
     """lut[argmax over channels] of a [C,H,W] probability map (any plane/row strides, unit pixel stride) -> int64 [H,W]."""
     C, H, W = prob.shape

@@ -29,6 +29,22 @@ def resize_objects(g: torch.Tensor, ratio: float, mode: str) -> torch.Tensor:
     return unfold(F.interpolate(fold(g), scale_factor=ratio, mode=mode, **kw), B)
 
 
+def area_resize(owner: nn.Module, x: torch.Tensor, size) -> torch.Tensor:
+    """F.interpolate(x, size=size, mode='area') for [..., H, W]; an integer-factor reduction goes through
+    cutie_area_pool where `owner.op_trials` (attached by CUTIE.optimize_for_inference) found it faster."""
+    H, W = x.shape[-2:]
+    h, w = int(size[0]), int(size[1])
+    lead = x.shape[:-2]
+
+    def aten():
+        return F.interpolate(x.reshape(-1, 1, H, W), size=(h, w), mode='area').reshape(*lead, h, w)
+    t = getattr(owner, 'op_trials', None)
+    if t is None or h == 0 or w == 0 or H % h or W % w or H // h != W // w or H // h < 2 or H // h > 64:
+        return aten()
+    f = H // h
+    return t('area_pool', (tuple(x.shape), f), aten, lambda trial: K_.area_pool(x, f), x)
+
+
 class ObjConv2d(nn.Conv2d):
     """nn.Conv2d applied independently to every object (group_modules.py:39-43)."""
 
@@ -50,8 +66,18 @@ class ChannelAttnResBlock(nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         y = self.conv2(conv_relu(self.conv1, F.relu(x)))
-        gate = self.conv(y.mean(dim=(2, 3)).unsqueeze(1)).sigmoid().transpose(1, 2).unsqueeze(-1)
-        return y * gate + self.downsample(x)
+        skip = self.downsample(x)
+
+        def aten():
+            gate = self.conv(y.mean(dim=(2, 3)).unsqueeze(1)).sigmoid().transpose(1, 2).unsqueeze(-1)
+            return y * gate + skip
+        t = getattr(self, 'op_trials', None)
+        if t is None:
+            return aten()
+        # conv1d + sigmoid + mul + add as cutie_eca_scale_add (in place into the fresh convolution output)
+        return t('eca_scale_add', (tuple(y.shape), tuple(y.stride()), tuple(skip.stride())), aten,
+                 lambda trial: K_.eca_scale_add_(y.clone(memory_format=torch.preserve_format) if trial else y, skip,
+                                                 self.conv.weight), y)
 
 
 class ObjResBlock(nn.Module):
@@ -112,13 +138,21 @@ class UpsampleBlock(nn.Module):
         return self.out_conv(resize_objects(g, 2, 'bilinear') + skip.unsqueeze(1))
 
 
-def gated_update(h: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
-    """modules.py:37-45: GRU-like update; v carries [forget | update | candidate] along channels."""
+def gated_update(h: torch.Tensor, v: torch.Tensor, owner: nn.Module = None) -> torch.Tensor:
+    """modules.py:37-45: GRU-like update; v carries [forget | update | candidate] along channels.  With
+    `owner.op_trials` attached the eight ATen launches may run as cutie_gated_update."""
     d = v.shape[2] // 3
-    f = torch.sigmoid(v[:, :, :d])
-    u = torch.sigmoid(v[:, :, d:2 * d])
-    n = torch.tanh(v[:, :, 2 * d:])
-    return f * h * (1 - u) + u * n
+
+    def aten():
+        f = torch.sigmoid(v[:, :, :d])
+        u = torch.sigmoid(v[:, :, d:2 * d])
+        n = torch.tanh(v[:, :, 2 * d:])
+        return f * h * (1 - u) + u * n
+    t = getattr(owner, 'op_trials', None) if owner is not None else None
+    if t is None or h.dim() != 5 or v.shape[2] != 3 * h.shape[2]:
+        return aten()
+    return t('gated_update', (tuple(h.shape), tuple(h.stride()), tuple(v.stride())), aten,
+             lambda trial: K_.gated_update(h, v), h)
 
 
 class MultiScaleSensoryUpdater(nn.Module):
@@ -132,9 +166,9 @@ class MultiScaleSensoryUpdater(nn.Module):
         self.transform = ObjConv2d(mid_dim + sensory_dim, sensory_dim * 3, 3, padding=1)
 
     def forward(self, g16, g8, g4, h):
-        g = self.g16_conv(g16) + self.g8_conv(resize_objects(g8, 1 / 2, 'area')) + \
-            self.g4_conv(resize_objects(g4, 1 / 4, 'area'))
-        return gated_update(h.float(), self.transform(torch.cat([g.float(), h.float()], 2)))
+        g = self.g16_conv(g16) + self.g8_conv(area_resize(self, g8, (g8.shape[-2] // 2, g8.shape[-1] // 2))) + \
+            self.g4_conv(area_resize(self, g4, (g4.shape[-2] // 4, g4.shape[-1] // 4)))
+        return gated_update(h.float(), self.transform(torch.cat([g.float(), h.float()], 2)), self)
 
 
 class DeepSensoryUpdater(nn.Module):
@@ -145,4 +179,4 @@ class DeepSensoryUpdater(nn.Module):
         self.transform = ObjConv2d(f_dim + sensory_dim, sensory_dim * 3, 3, padding=1)
 
     def forward(self, g, h):
-        return gated_update(h.float(), self.transform(torch.cat([g.float(), h.float()], 2)))
+        return gated_update(h.float(), self.transform(torch.cat([g.float(), h.float()], 2)), self)

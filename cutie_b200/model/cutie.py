@@ -12,7 +12,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from cutie_b200.model.blocks import ObjConv2d
+from cutie_b200.model.blocks import ObjConv2d, area_resize
 from cutie_b200.model.encoders import KeyProjection, MaskDecoder, MaskEncoder, PixelEncoder, PixelFeatureFuser
 from cutie_b200.model.object_summarizer import ObjectSummarizer
 from cutie_b200.model.object_transformer import QueryTransformer
@@ -111,7 +111,7 @@ class CUTIE(nn.Module):
     # -- hot path, model side --------------------------------------------------------------
     def pixel_fusion(self, pix_feat, pixel, sensory, last_mask, *, chunk_size: int = -1):
         """cutie.py:142-157 (a8)."""
-        last_mask = F.interpolate(last_mask, size=sensory.shape[-2:], mode='area')
+        last_mask = area_resize(self, last_mask, sensory.shape[-2:])
         return self.pixel_fuser(pix_feat, pixel, sensory, last_mask, self._others(last_mask),
                                 chunk_size=chunk_size)
 
@@ -173,11 +173,14 @@ class CUTIE(nn.Module):
                 log.info(f'Key {k} found in self.state_dict() but not in src_dict!!!')
         self.load_state_dict(src_dict, strict=False)
 
-    def optimize_for_inference(self, channels_last: bool = True, fuse_epilogues: bool = True) -> 'CUTIE':
+    def optimize_for_inference(self, channels_last: bool = True, fuse_epilogues: bool = True,
+                               fuse_glue: bool = True) -> 'CUTIE':
         """Post-load surgery on the PyTorch/cuDNN stages (cutie_b200/model/fuse.py): fold the frozen BatchNorms of
         both ResNet trunks into their convolutions, run the trunks channels-last, and let conv+bias(+residual)+ReLU
         go through cuDNN's fused graph wherever its on-device trial matches and beats the three-launch form
-        (`fuse.ConvEpilogueFuser`, kept as `self.conv_epilogues`).  Numerically equivalent up to fp32 rounding; the module
+        (`fuse.ConvEpilogueFuser`, kept as `self.conv_epilogues`); `fuse_glue` lets short ATen chains around the
+        convolutions (area down-sampling, CAResBlock tail, sensory GRU gates) run as single cutie_b200 kernels where
+        their on-device trial matches and wins (`utils.op_trials.OpTrials`, kept as `self.op_trials`).  Numerically equivalent up to fp32 rounding; the module
         tree (hence state_dict) of the trunks changes, so call it after load_weights."""
         from cutie_b200.model.fuse import ConvEpilogueFuser, attach_epilogue_fuser, fold_trunk_
         for enc in (self.pixel_encoder, self.mask_encoder):
@@ -191,6 +194,9 @@ class CUTIE(nn.Module):
         # after the folding: fold_trunk_ replaces the trunk convolutions by new modules
         object.__setattr__(self, 'conv_epilogues', ConvEpilogueFuser(enabled=bool(fuse_epilogues)))
         attach_epilogue_fuser(self, self.conv_epilogues)
+        # pixel-side glue (area down-sampling, channel-attention tail, sensory GRU gates): ATen chains vs our kernels
+        from cutie_b200.utils.op_trials import OpTrials, attach_op_trials
+        attach_op_trials(self, OpTrials(enabled=bool(fuse_glue)))
         return self
 
     @property

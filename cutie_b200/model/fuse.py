@@ -149,6 +149,7 @@ class ConvEpilogueFuser:
         return [f for f in self.forms if f != 'aten' and (relu or f != 'cudnn')]
 
     def _trial(self, key, conv, x, z, relu) -> str:
+        from cutie_b200.kernels import KernelError
         what = f'conv {tuple(conv.weight.shape)} on {tuple(x.shape)}'
         ref = self.unfused(conv, x, z, relu)
         scale = float(ref.abs().max()) + 1e-6
@@ -164,7 +165,9 @@ class ConvEpilogueFuser:
                     self.errors.append(f'{what}: {form} differs by {err:.3e} (scale {scale:.3e})')
                     continue
                 times[form] = self._time(lambda: self.run(form, conv, x, z, relu))
-            except Exception as e:                 # noqa: BLE001 -- any cuDNN / dispatcher / launch failure: drop the form
+            except KernelError:                    # our library missing / a failed launch is never absorbed
+                raise
+            except Exception as e:                 # noqa: BLE001 -- any cuDNN / dispatcher failure: drop the form
                 self.errors.append(f'{what}: {form}: {type(e).__name__}: {e}')
         self.timings[key] = times
         return min(times, key=times.get)

@@ -6,6 +6,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from cutie_b200.model.blocks import area_resize
 from cutie_b200.model.positional import SinusoidPE
 
 
@@ -25,7 +26,7 @@ class ObjectSummarizer(nn.Module):
     def forward(self, masks, value, need_weights: bool = False):
         """masks [B,K,H,W] in [0,1]; value [B,K,CV,h,w] -> summaries [B,K,Q,E+1] (sums | area), logits or None."""
         h, w = value.shape[-2:]
-        m = F.interpolate(masks, size=(h, w), mode='area').unsqueeze(-1)           # [B,K,h,w,1]
+        m = area_resize(self, masks, (h, w)).unsqueeze(-1)                         # [B,K,h,w,1]
         half = self.num_summaries // 2
         allow = torch.cat([m.expand(-1, -1, -1, -1, half), (1 - m).expand(-1, -1, -1, -1, half)], -1)
         tok = self.input_proj(value.permute(0, 1, 3, 4, 2))

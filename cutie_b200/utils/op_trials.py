@@ -1,0 +1,92 @@
+"""First-use A/B of an ATen composition against one of our kernels (per op and geometry).
+
+The pixel-side glue kernels in csrc/pixel.cu replace short chains of ATen launches inside the PyTorch stages around
+the hot path.  Which form is faster depends on the GPU, the driver and the shapes, so nothing is assumed: the first
+time an (op, geometry) pair is seen OUTSIDE a stream capture both forms run on the live tensors, the kernel's result
+must match the ATen composition, both are timed with CUDA events, and the faster one is kept (`decisions`).  A
+mismatch keeps the ATen form and is recorded in `errors` (bench.py prints the report).  A missing library or a failed
+launch (`KernelError`) is NOT absorbed -- it propagates like everywhere else in cutie_b200.  CPU tensors (the oracle
+harness borrowing the modules) always take the ATen form.
+
+Attached per model by `CUTIE.optimize_for_inference()` (attribute `op_trials` on every sub-module); modules without
+it run PyTorch's launches unchanged.
+"""
+from typing import Callable, Dict
+
+import torch
+import torch.nn as nn
+
+
+class OpTrials:
+    def __init__(self, enabled: bool = True, trial_iters: int = 6):
+        self.enabled = enabled
+        self.trial_iters = trial_iters
+        self.decisions: Dict[tuple, bool] = {}       # (op, key) -> True: our kernel
+        self.timings: Dict[tuple, tuple] = {}        # (op, key) -> (kernel_ms, aten_ms)
+        self.errors = []
+
+    def _eligible(self, probe: torch.Tensor) -> bool:
+        return self.enabled and probe.is_cuda and probe.dtype == torch.float32 and not torch.is_grad_enabled()
+
+    @staticmethod
+    def _capturing() -> bool:
+        return torch.cuda.is_current_stream_capturing()
+
+    def _time(self, fn) -> float:
+        for _ in range(2):
+            fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(self.trial_iters):
+            fn()
+        b.record()
+        b.synchronize()
+        return a.elapsed_time(b) / self.trial_iters
+
+    def _trial(self, op, key, aten: Callable, kernel: Callable, rtol: float) -> bool:
+        ref = aten()
+        out = kernel(True)                           # trial=True: in-place kernels work on a copy
+        scale = float(ref.abs().max()) + 1e-6
+        err = float((out - ref).abs().max())
+        if not (out.shape == ref.shape and err <= rtol * scale):       # also catches NaN
+            self.errors.append(f'{op} {key}: kernel differs from ATen by {err:.3e} (scale {scale:.3e})')
+            return False
+        t_k = self._time(lambda: kernel(True))
+        t_a = self._time(aten)
+        self.timings[(op, key)] = (t_k, t_a)
+        return t_k <= t_a
+
+    def __call__(self, op: str, key: tuple, aten: Callable, kernel: Callable, probe: torch.Tensor,
+                 rtol: float = 1e-5) -> torch.Tensor:
+        """aten(): the PyTorch composition.  kernel(trial: bool): our kernel; with trial=True it must not modify its
+        inputs (in-place kernels clone their destination)."""
+        if not self._eligible(probe):
+            return aten()
+        use = self.decisions.get((op, key))
+        if use is None:
+            if self._capturing():
+                return aten()
+            use = self.decisions[(op, key)] = self._trial(op, key, aten, kernel, rtol)
+        return kernel(False) if use else aten()
+
+    def __deepcopy__(self, memo):
+        new = OpTrials(self.enabled, self.trial_iters)
+        memo[id(self)] = new
+        return new
+
+    def report(self) -> dict:
+        ops = {}
+        for (op, _), use in self.decisions.items():
+            d = ops.setdefault(op, {'kernel': 0, 'aten': 0})
+            d['kernel' if use else 'aten'] += 1
+        saved = sum(a - k for key, (k, a) in self.timings.items() if self.decisions.get(key))
+        return {'enabled': self.enabled, 'ops': ops, 'errors': len(self.errors),
+                'first_error': self.errors[0] if self.errors else None, 'trial_ms_saved_per_pass': saved}
+
+
+def attach_op_trials(module: nn.Module, trials: OpTrials) -> int:
+    n = 0
+    for m in module.modules():
+        object.__setattr__(m, 'op_trials', trials)
+        n += 1
+    return n

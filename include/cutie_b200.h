@@ -127,6 +127,23 @@ int cutie_upsample2x_add(const float* g, const float* skip, float* out, int64_t 
 int cutie_bias_act(float* y, const float* bias, const float* z, int64_t N, int64_t C, int64_t HW, int channels_last,
                    int relu, void* stream);
 
+/* out[p,Y,X] = mean of the f x f window of in[p]: F.interpolate(mode='area') / adaptive_avg_pool2d for sizes that
+ * divide (H % f == 0, W % f == 0).  Replaces the 16x mask down-sampling of CUTIE.pixel_fusion (cutie/model/cutie.py:149),
+ * the 2x / 4x feature down-sampling of SensoryUpdater (cutie/model/modules.py:58-60, group_modules.py:27-36
+ * downsample_groups) and ObjectSummarizer's mask resize (object_summarizer.py:60).  in [planes,H,W], out
+ * [planes,H/f,W/f], dense fp32; row-major fp32 accumulation, one division. */
+int cutie_area_pool(const float* in, float* out, int64_t planes, int64_t H, int64_t W, int64_t f, void* stream);
+
+/* CAResBlock tail (cutie/model/channel_attn.py:27-38): gate[n,c] = sigmoid(conv1d_k(mean[n,:])[c]) (zero padded, no
+ * bias), then y = y * gate + x in place.  y, x dense fp32 [N,C,HW] (channels_last == 0) or [N,HW,C] (1); mean [N,C] =
+ * spatial mean of y (caller supplied); w [k], k odd; gate [N,C] scratch. */
+int cutie_eca_scale_add(float* y, const float* x, const float* mean, const float* w, float* gate, int64_t N, int64_t C,
+                        int64_t HW, int64_t k, int channels_last, void* stream);
+
+/* Sensory GRU update (cutie/model/modules.py:37-45 _recurrent_update): v [P,3d,HW] = [forget | update | candidate],
+ * h [P,d,HW] -> out [P,d,HW] = sigmoid(vf) * h * (1 - sigmoid(vu)) + sigmoid(vu) * tanh(vn).  Dense fp32. */
+int cutie_gated_update(const float* v, const float* h, float* out, int64_t P, int64_t d, int64_t HW, void* stream);
+
 /* out[y,x] = lut[argmax_c prob[c,y,x]]: InferenceCore.output_prob_to_mask (inference_core.py:377-385: argmax over
  * the 1+K channels, then ObjectManager.tmp_to_obj_cls object_manager.py:99-104) in one pass.  prob may be a strided
  * view (plane_stride / row_stride in elements, unit pixel stride); lut int64 [C]; out int64 [H,W] contiguous.

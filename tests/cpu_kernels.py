@@ -251,7 +251,27 @@ def bias_act_(y, bias, z=None, relu=False):
     return torch.relu_(y) if relu else y
 
 
-ALL = ['bias_act_', 'affinity_topk', 'topk_merge', 'readout_gather', 'usage_commit', 'bank_append', 'bank_export', 'bank_gather', 'bank_key_image', 'upsample2x_add', 'prob_to_mask',
+def area_pool(x, f):
+    import torch.nn.functional as F
+    lead = x.shape[:-2]
+    y = F.avg_pool2d(x.reshape(-1, 1, *x.shape[-2:]), f)
+    return y.reshape(*lead, *y.shape[-2:])
+
+
+def eca_scale_add_(y, x, conv1d_weight):
+    import torch.nn.functional as F
+    k = conv1d_weight.shape[-1]
+    gate = torch.sigmoid(F.conv1d(y.mean(dim=(2, 3)).unsqueeze(1), conv1d_weight, padding=(k - 1) // 2))
+    return y.mul_(gate.transpose(1, 2).unsqueeze(-1)).add_(x)
+
+
+def gated_update(h, v):
+    d = h.shape[2]
+    f, u, n = torch.sigmoid(v[:, :, :d]), torch.sigmoid(v[:, :, d:2 * d]), torch.tanh(v[:, :, 2 * d:])
+    return f * h * (1 - u) + u * n
+
+
+ALL = ['bias_act_', 'area_pool', 'eca_scale_add_', 'gated_update', 'affinity_topk', 'topk_merge', 'readout_gather', 'usage_commit', 'bank_append', 'bank_export', 'bank_gather', 'bank_key_image', 'upsample2x_add', 'prob_to_mask',
        'consolidate', 'obj_summary_accumulate', 'qt_linear', 'qt_head_fold', 'qt_self_attention',
        'qt_aux_mask', 'qt_pixel_to_query', 'qt_query_to_pixel']
 

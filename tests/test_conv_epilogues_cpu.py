@@ -231,3 +231,85 @@ def test_optimize_for_inference_attaches_one_fuser_per_model():
         a = net.key_proj(f16, need_s=True, need_e=True)
         b = dup(f16, need_s=True, need_e=True)
     assert all(torch.equal(p, q) for p, q in zip(a, b))
+
+
+# ---- pixel-side glue: ATen chains vs cutie kernels (utils/op_trials.OpTrials) ------------------------------------
+class _FakeDeviceTrials:
+    """OpTrials on CPU tensors with a scripted clock (kernel_ms, aten_ms per op)."""
+
+    def __new__(cls, ms=None, **kw):
+        from cutie_b200.utils.op_trials import OpTrials
+
+        class T(OpTrials):
+            def _eligible(self, probe):
+                return self.enabled and not torch.is_grad_enabled()
+
+            @staticmethod
+            def _capturing():
+                return False
+
+            def _time(self, fn):
+                fn()
+                self._n = getattr(self, '_n', 0) + 1
+                return (ms or (1.0, 2.0))[(self._n - 1) % 2]        # kernel first, then ATen (order in _trial)
+        return T(**kw)
+
+
+def test_glue_ops_route_through_trials_and_match(cpu_kernels):
+    from cutie_b200.config import default_config
+    from cutie_b200.model.cutie import CUTIE
+    from cutie_b200.utils.op_trials import attach_op_trials
+    cfg = default_config()
+    torch.manual_seed(0)
+    net = CUTIE(cfg).eval()
+    g = torch.Generator().manual_seed(1)
+    B, K, h, w = 1, 2, 4, 6
+    pix_feat = torch.randn(B, 256, h, w, generator=g)
+    pixel = torch.randn(B, K, 256, h, w, generator=g)
+    sensory = torch.randn(B, K, 256, h, w, generator=g)
+    last_mask = torch.rand(B, K, 16 * h, 16 * w, generator=g)
+    ms = [torch.randn(B, 1024, h, w, generator=g), torch.randn(B, 512, 2 * h, 2 * w, generator=g),
+          torch.randn(B, 256, 4 * h, 4 * w, generator=g)]
+    with torch.inference_mode():
+        ref_fused = net.pixel_fusion(pix_feat, pixel, sensory, last_mask)
+        # the decoder's UpsampleBlock needs the CUDA kernel for CUDA tensors only; on CPU it is plain PyTorch
+        ref_sens, ref_logits = net.mask_decoder(ms, ref_fused, sensory)
+        ref_summ, _ = net.object_summarizer(last_mask, pixel)
+        t = _FakeDeviceTrials()
+        attach_op_trials(net, t)
+        fused = net.pixel_fusion(pix_feat, pixel, sensory, last_mask)
+        sens, logits = net.mask_decoder(ms, fused, sensory)
+        summ, _ = net.object_summarizer(last_mask, pixel)
+    rep = t.report()
+    assert rep['errors'] == 0, rep
+    assert rep['ops']['area_pool']['kernel'] >= 3            # mask /16 (fusion + summarizer share a shape), g8 /2, g4 /4
+    assert rep['ops']['eca_scale_add']['kernel'] >= 1 and rep['ops']['gated_update']['kernel'] >= 1
+    for a, b in ((fused, ref_fused), (sens, ref_sens), (logits, ref_logits), (summ, ref_summ)):
+        assert float((a - b).abs().max()) <= 2e-5 * (float(b.abs().max()) + 1e-6)
+
+
+def test_glue_trial_rejects_a_wrong_kernel_and_propagates_kernel_errors(cpu_kernels, monkeypatch):
+    import cutie_b200.kernels as K_
+    from cutie_b200.model.blocks import area_resize
+    from cutie_b200.utils.op_trials import attach_op_trials
+    owner = torch.nn.Identity()
+    t = _FakeDeviceTrials()
+    attach_op_trials(owner, t)
+    x = torch.rand(2, 3, 8, 12)
+    with torch.inference_mode():
+        want = F.interpolate(x.reshape(-1, 1, 8, 12), size=(2, 3), mode='area').reshape(2, 3, 2, 3)
+        monkeypatch.setattr(K_, 'area_pool', lambda x_, f: K_.__dict__['area_pool__orig'](x_, f) + 1.0, raising=False)
+        K_.__dict__['area_pool__orig'] = cpu_kernels.area_pool
+        got = area_resize(owner, x, (2, 3))
+        assert torch.equal(got, want) and t.report()['errors'] == 1 and t.report()['ops']['area_pool'] == {'kernel': 0, 'aten': 1}
+        assert torch.equal(area_resize(owner, x, (2, 3)), want)            # decision is sticky
+
+        def boom(x_, f):
+            raise K_.KernelError('libcutie_b200.so not found')
+        monkeypatch.setattr(K_, 'area_pool', boom)
+        with pytest.raises(K_.KernelError):                               # never absorbed into an ATen fallback
+            area_resize(owner, torch.rand(1, 8, 8), (2, 2))
+        # non-integer ratios stay with PyTorch
+        y = torch.rand(1, 9, 10)
+        assert torch.equal(area_resize(owner, y, (4, 4)), F.interpolate(y[None], size=(4, 4), mode='area')[0])
+    del K_.__dict__['area_pool__orig']

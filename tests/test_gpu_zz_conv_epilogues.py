@@ -101,3 +101,69 @@ def test_bias_act_misaligned_views_take_the_scalar_path():
     got2 = K_.bias_act_(y, bias, None, True)            # in place on the misaligned view
     torch.cuda.synchronize()
     assert torch.equal(got2, want) and got2.data_ptr() == y.data_ptr()
+
+
+@pytest.mark.parametrize('shape,f', [((1, 3, 480, 864), 16), ((3, 256, 60, 108), 2), ((3, 257, 120, 216), 4), ((2, 5, 9, 12), 3),
+                                     ((1, 2, 96, 160), 16)])
+def test_area_pool_kernel_matches_interpolate_area(shape, f):
+    import torch.nn.functional as F
+    import cutie_b200.kernels as K_
+    x = torch.rand(*shape, generator=torch.Generator().manual_seed(f)).cuda()
+    got = K_.area_pool(x, f)
+    want = F.interpolate(x, scale_factor=1.0 / f, mode='area')
+    assert got.shape == want.shape and float((got - want).abs().max()) <= 1e-6
+
+
+@pytest.mark.parametrize('shape', [(3, 256, 30, 54), (2, 8, 5, 3), (1, 64, 9, 11)])
+@pytest.mark.parametrize('cl', [False, True])
+def test_eca_scale_add_kernel_matches_aten(shape, cl):
+    import cutie_b200.kernels as K_
+    g = torch.Generator().manual_seed(shape[1])
+    fmt = torch.channels_last if cl else torch.contiguous_format
+    y = torch.randn(*shape, generator=g).cuda().contiguous(memory_format=fmt)
+    x = torch.randn(*shape, generator=g).cuda()                     # NCHW: exercises the layout copy when cl
+    conv = torch.nn.Conv1d(1, 1, 5, padding=2, bias=False).cuda()
+    with torch.inference_mode():
+        gate = conv(y.mean(dim=(2, 3)).unsqueeze(1)).sigmoid().transpose(1, 2).unsqueeze(-1)
+        want = y * gate + x
+        got = K_.eca_scale_add_(y.clone(memory_format=torch.preserve_format), x, conv.weight)
+    assert float((got - want).abs().max()) <= 1e-5 * float(want.abs().max())
+
+
+@pytest.mark.parametrize('shape', [(1, 3, 256, 30, 54), (2, 2, 4, 5, 3)])
+def test_gated_update_kernel_matches_aten(shape):
+    import cutie_b200.kernels as K_
+    from cutie_b200.model.blocks import gated_update
+    B, K, d, H, W = shape
+    g = torch.Generator().manual_seed(d)
+    h = torch.randn(*shape, generator=g).cuda()
+    v = (2 * torch.randn(B, K, 3 * d, H, W, generator=g)).cuda()
+    want = gated_update(h, v)                                        # no owner: the ATen composition
+    got = K_.gated_update(h, v)
+    assert float((got - want).abs().max()) <= 2e-6
+
+
+def test_stream_with_glue_kernels_matches_aten_chains():
+    """Same as the epilogue stream test, for the glue ops: optimised model with fuse_glue on vs off."""
+    from cutie_b200.config import default_config
+    from cutie_b200.inference.inference_core import InferenceCore
+    from oracle.synth import synthetic_video
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg = default_config(mem_every=2, max_mem_frames=3)
+    on, off = _net(cfg, fuse_epilogues=False, fuse_glue=True), _net(cfg, fuse_epilogues=False, fuse_glue=False)
+    a, b = InferenceCore(on, cfg=cfg, use_cuda_graphs=True), InferenceCore(off, cfg=cfg, use_cuda_graphs=True)
+    frames, mask = synthetic_video(3, 96, 160, 3, seed=3)
+    with torch.inference_mode():
+        for ti in range(3):
+            x = frames[ti].cuda()
+            if ti == 0:
+                a.step(x, mask.cuda(), objects=[1, 2, 3]); b.step(x, mask.cuda(), objects=[1, 2, 3])
+            else:
+                pa, pb = a.step(x), b.step(x)
+                assert float((a.last_logits - b.last_logits).abs().max()) < 1e-3
+                assert float((pa - pb).abs().max()) < 1e-3
+    rep = on.op_trials.report()
+    print('glue ops (stream, 96x160):', rep)
+    assert rep['errors'] == 0, rep
+    assert not off.op_trials.decisions
