@@ -36,8 +36,12 @@ def log(*a):
 
 # Exactly ONE line may reach stdout (the JSON).  Libraries (NCCL prints its version banner) write to fd 1
 # directly, so fd 1 is pointed at stderr for the whole run and the JSON goes to a saved copy of the real stdout.
-_REAL_STDOUT = os.dup(1)
-os.dup2(2, 1)
+if os.environ.get('CUTIE_BENCH_STDOUT_FD'):          # re-exec'ed by the fallback below: fd 1 already points at stderr
+    _REAL_STDOUT = int(os.environ['CUTIE_BENCH_STDOUT_FD'])
+else:
+    _REAL_STDOUT = os.dup(1)
+    os.set_inheritable(_REAL_STDOUT, True)
+    os.dup2(2, 1)
 
 
 def emit(line: dict):
@@ -141,6 +145,79 @@ def summarize_clocks(samples):
                 reasons.add(name)
     return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': float(samples[0][1]),
             'power_w_max': max(float(s[2]) for s in samples), 'reasons': sorted(reasons), 'samples': len(samples)}
+
+
+# ---------------------------------------------------------------------------------------------------
+def preflight(local: int) -> int:
+    """Runs in a CHILD process before the measured run (`bench.py --preflight`): the optional launch-saving forms that
+    optimize_for_inference() can switch on (cuDNN fused conv epilogues, cutie_bias_act, the pixel-side glue kernels)
+    against PyTorch's own launches on this box -- kernels on random tensors, then a short optimised stream with CUDA
+    graphs.  Exit code 0 = use them; anything else (mismatch, exception, crash, time-out) = the measured run keeps
+    PyTorch's launches for those stages and says so in its JSON line.  The hot-path kernels are not optional and are not
+    part of this check."""
+    import torch.nn.functional as F
+    import cutie_b200.kernels as K_
+    from cutie_b200.config import default_config
+    from cutie_b200.inference.inference_core import InferenceCore
+    from cutie_b200.model.blocks import gated_update
+    from oracle.synth import synthetic_video
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator().manual_seed(0)
+    rnd = lambda *s: torch.randn(*s, generator=g).to(dev)
+    with torch.inference_mode():
+        for shape in ((3, 256, 30, 54), (2, 7, 5, 3)):
+            for fmt in (torch.contiguous_format, torch.channels_last):
+                y, z, b = rnd(*shape).contiguous(memory_format=fmt), rnd(*shape), rnd(shape[1])
+                want = torch.relu(y + b.view(1, -1, 1, 1) + z)
+                assert torch.equal(K_.bias_act_(y.clone(memory_format=torch.preserve_format), b, z, True), want), 'bias_act'
+                conv = torch.nn.Conv1d(1, 1, 5, padding=2, bias=False).to(dev)
+                gate = conv(y.mean(dim=(2, 3)).unsqueeze(1)).sigmoid().transpose(1, 2).unsqueeze(-1)
+                want = y * gate + z
+                got = K_.eca_scale_add_(y.clone(memory_format=torch.preserve_format), z, conv.weight)
+                assert float((got - want).abs().max()) <= 1e-5 * float(want.abs().max()), 'eca_scale_add'
+        for shape, f in (((1, 3, 480, 864), 16), ((3, 256, 60, 108), 2), ((3, 257, 120, 216), 4)):
+            x = torch.rand(*shape, generator=g).to(dev)
+            assert float((K_.area_pool(x, f) - F.interpolate(x, scale_factor=1.0 / f, mode='area')).abs().max()) <= 1e-6, 'area_pool'
+        h, v = rnd(1, 3, 256, 30, 54), 2 * rnd(1, 3, 768, 30, 54)
+        assert float((K_.gated_update(h, v) - gated_update(h, v)).abs().max()) <= 2e-6, 'gated_update'
+        cfg = default_config(mem_every=2, max_mem_frames=3)
+        on = make_net(cfg).to(dev).optimize_for_inference()
+        off = make_net(cfg).to(dev).optimize_for_inference(fuse_epilogues=False, fuse_glue=False)
+        a, b = InferenceCore(on, cfg=cfg, use_cuda_graphs=True), InferenceCore(off, cfg=cfg, use_cuda_graphs=True)
+        frames, mask = synthetic_video(4, 96, 160, 3, seed=3)
+        for ti in range(4):
+            x = frames[ti].to(dev)
+            if ti == 0:
+                a.step(x, mask.to(dev), objects=[1, 2, 3]); b.step(x, mask.to(dev), objects=[1, 2, 3])
+            else:
+                pa, pb = a.step(x), b.step(x)
+                d = float((a.last_logits - b.last_logits).abs().max())
+                assert d < 1e-3 and bool(torch.isfinite(pa).all()), f'optimised stream deviates by {d} at frame {ti}'
+        torch.cuda.synchronize(dev)
+    log(f'[preflight] ok: conv epilogues {on.conv_epilogues.report()}; glue ops {on.op_trials.report()}')
+    return 0
+
+
+def run_preflight(local: int, timeout_s: float = 420.0):
+    """(ok, note): spawns `bench.py --preflight` for this rank's GPU."""
+    env = dict(os.environ)
+    env.pop('CUTIE_BENCH_STDOUT_FD', None)
+    for k in ('RANK', 'WORLD_SIZE', 'LOCAL_WORLD_SIZE', 'GROUP_RANK', 'ROLE_RANK', 'TORCHELASTIC_RUN_ID'):
+        env.pop(k, None)
+    env['LOCAL_RANK'] = str(local)
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), '--preflight'], env=env, timeout=timeout_s,
+                           stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+    except subprocess.TimeoutExpired:
+        return False, f'pre-flight timed out after {timeout_s:.0f} s'
+    tail = (r.stderr or '').strip().splitlines()[-1:] or ['']
+    if r.returncode != 0:
+        return False, f'pre-flight exit {r.returncode}: {tail[0][:300]}'
+    log(tail[0])
+    return True, 'ok'
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -334,7 +411,13 @@ def main():
     ap.add_argument('--no-fuse-epilogues', action='store_true',
                     help='keep convolution, bias add and ReLU as three launches (no cuDNN fused conv-bias-activation)')
     ap.add_argument('--cpu-seconds', type=float, default=150.0)
+    ap.add_argument('--preflight', action='store_true', help=argparse.SUPPRESS)
+    ap.add_argument('--skip-preflight', action='store_true',
+                    help='do not check the optional launch-saving forms in a child process first')
+    ap.add_argument('--fallback-reason', default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.preflight:
+        sys.exit(preflight(int(os.environ.get('LOCAL_RANK', 0))))
     if args.warmup < 3:
         args.warmup = 3
     wl = WORKLOADS[args.workload]
@@ -374,11 +457,37 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a CUDA device: there is no CPU fallback for the product path '
                          '(use --impl reference for the CPU arm)')
+    # The optional launch-saving forms (cuDNN fused epilogues, cutie_bias_act, glue kernels) are checked against
+    # PyTorch's own launches in a child process first; a failed check only switches THEM off for this run.
+    optional = {'checked': False, 'note': args.fallback_reason or 'not checked'}
+    wants_optional = not args.no_optimize and not (args.no_fuse_epilogues and args.no_fuse_glue)
+    if wants_optional and not args.skip_preflight and not args.fallback_reason:
+        ok, note = run_preflight(local)
+        optional = {'checked': True, 'note': note}
+        if not ok:
+            log(f'[rank {rank}] optional fused forms disabled: {note}')
+            args.no_fuse_epilogues = args.no_fuse_glue = True
     dev = torch.device('cuda', local)
     torch.cuda.set_device(dev)
     if world > 1:
         torch.distributed.init_process_group('nccl', device_id=dev)
-    res = run_ours(args, wl, rank, world, dev)
+    try:
+        res = run_ours(args, wl, rank, world, dev)
+    except Exception as e:                               # noqa: BLE001
+        # single process only: start over in a fresh process (fresh CUDA context) with PyTorch's launches for the
+        # optional stages; a second failure, or any failure under torchrun, is fatal
+        if world == 1 and wants_optional and not args.fallback_reason and not (args.no_fuse_epilogues and args.no_fuse_glue):
+            import traceback
+            traceback.print_exc()
+            reason = f'{type(e).__name__}: {e}'[:200].replace('\n', ' ')
+            log(f'[bench] optimised run failed ({reason}); re-running with --no-fuse-epilogues --no-fuse-glue')
+            os.environ['CUTIE_BENCH_STDOUT_FD'] = str(_REAL_STDOUT)
+            argv = [sys.executable, os.path.abspath(__file__)] + sys.argv[1:] + \
+                   ['--no-fuse-epilogues', '--no-fuse-glue', '--fallback-reason', reason]
+            os.execv(sys.executable, argv)
+        raise
+    optional['conv_epilogues'] = not args.no_optimize and not args.no_fuse_epilogues
+    optional['glue_kernels'] = not args.no_optimize and not args.no_fuse_glue
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count())
@@ -451,6 +560,7 @@ def main():
             'affinity_phases_ms': res['phases'] or None, 'key_image_levels': res['image_levels']}
     line['config']['conv_epilogues'] = res['epilogues']     # which conv+bias(+add)+ReLU calls won their on-device trial
     line['config']['glue_ops'] = res['glue']                 # which ATen chains were replaced by cutie_b200 kernels
+    line['config']['optional_forms'] = optional               # pre-flight verdict for the two entries above
     emit(line)
 
 

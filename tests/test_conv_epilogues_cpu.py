@@ -313,3 +313,38 @@ def test_glue_trial_rejects_a_wrong_kernel_and_propagates_kernel_errors(cpu_kern
         y = torch.rand(1, 9, 10)
         assert torch.equal(area_resize(owner, y, (4, 4)), F.interpolate(y[None], size=(4, 4), mode='area')[0])
     del K_.__dict__['area_pool__orig']
+
+
+def test_whole_stream_with_every_optional_form_active(cpu_kernels):
+    """InferenceCore over a short clip with BN folding, channels-last trunks, the epilogue fuser choosing the cuDNN /
+    kernel forms and the glue trials choosing our kernels (all emulated on CPU) against the plain model: the closest
+    CPU stand-in for the bench configuration -- every stride / layout hand-over between the forms is exercised."""
+    from cutie_b200.config import default_config
+    from cutie_b200.inference.inference_core import InferenceCore
+    from cutie_b200.model.cutie import CUTIE
+    from cutie_b200.utils.op_trials import attach_op_trials
+    from oracle.synth import synthetic_state_dict, synthetic_video
+    cfg = default_config(mem_every=2, max_mem_frames=3)
+
+    def net():
+        n = CUTIE(cfg).eval()
+        n.load_state_dict(synthetic_state_dict(n.state_dict(), 0))
+        return n
+    plain, fast = net(), net().optimize_for_inference()
+    f, t = _FakeDeviceFuser(), _FakeDeviceTrials()
+    fuse.attach_epilogue_fuser(fast, f)
+    attach_op_trials(fast, t)
+    a, b = InferenceCore(plain, cfg=cfg), InferenceCore(fast, cfg=cfg)
+    frames, mask = synthetic_video(4, 96, 160, 3, seed=3)
+    with torch.inference_mode():
+        for ti in range(4):
+            if ti == 0:
+                a.step(frames[0], mask, objects=[1, 2, 3]); b.step(frames[0], mask, objects=[1, 2, 3])
+            else:
+                pa, pb = a.step(frames[ti]), b.step(frames[ti])
+                assert float((a.last_logits - b.last_logits).abs().max()) < 1e-3
+                assert float((pa - pb).abs().max()) < 1e-3
+    rf, rt = f.report(), t.report()
+    assert rf['errors'] == 0 and rt['errors'] == 0, (rf, rt)
+    assert rf['cudnn'] >= 40 and rf['kernel'] >= 20                       # trunks / bias-only convolutions
+    assert set(rt['ops']) == {'area_pool', 'eca_scale_add', 'gated_update'}
