@@ -69,6 +69,22 @@ class OpTrials:
             use = self.decisions[(op, key)] = self._trial(op, key, aten, kernel, rtol)
         return kernel(False) if use else aten()
 
+    def pick(self, op: str, key: tuple, candidates, run: Callable, probe: torch.Tensor):
+        """Launch-parameter A/B: `run(c)` performs the op with parameter c (all candidates are valid; results may differ
+        in summation order only).  Returns the fastest candidate for (op, key); candidates[0] -- the library default --
+        for CPU tensors, inside a capture before a decision exists, or when there is nothing to choose."""
+        if len(candidates) < 2 or not self._eligible(probe):
+            return candidates[0]
+        got = self.decisions.get((op, key))
+        if got is None:
+            if self._capturing():
+                return candidates[0]
+            times = [self._time(lambda c=c: run(c)) for c in candidates]
+            best = min(range(len(candidates)), key=times.__getitem__)
+            got = self.decisions[(op, key)] = candidates[best]
+            self.timings[(op, key)] = (times[best], times[0])
+        return got
+
     def __deepcopy__(self, memo):
         new = OpTrials(self.enabled, self.trial_iters)
         memo[id(self)] = new
@@ -77,9 +93,12 @@ class OpTrials:
     def report(self) -> dict:
         ops = {}
         for (op, _), use in self.decisions.items():
-            d = ops.setdefault(op, {'kernel': 0, 'aten': 0})
-            d['kernel' if use else 'aten'] += 1
-        saved = sum(a - k for key, (k, a) in self.timings.items() if self.decisions.get(key))
+            if isinstance(use, bool):
+                d = ops.setdefault(op, {'kernel': 0, 'aten': 0})
+                d['kernel' if use else 'aten'] += 1
+            else:                                             # a picked launch parameter
+                ops.setdefault(op, {'picked': []})['picked'].append(use)
+        saved = sum(a - k for key, (k, a) in self.timings.items() if self.decisions.get(key) not in (None, False))
         return {'enabled': self.enabled, 'ops': ops, 'errors': len(self.errors),
                 'first_error': self.errors[0] if self.errors else None, 'trial_ms_saved_per_pass': saved}
 

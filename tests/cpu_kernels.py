@@ -207,7 +207,7 @@ def qt_aux_mask(pixel, w, b, B, K):
     return logits, fg.to(torch.uint8), fg.reshape(BK, HW).sum(1).int()
 
 
-def qt_pixel_to_query(qfold, pixel, pixel_pe, fg, fg_count, wv, bv, num_queries, num_heads=8):
+def qt_pixel_to_query(qfold, pixel, pixel_pe, fg, fg_count, wv, bv, num_queries, num_heads=8, splits=None):
     M, H, E = qfold.shape
     BK, _, HW = pixel.shape
     Q = num_queries

@@ -347,4 +347,24 @@ def test_whole_stream_with_every_optional_form_active(cpu_kernels):
     rf, rt = f.report(), t.report()
     assert rf['errors'] == 0 and rt['errors'] == 0, (rf, rt)
     assert rf['cudnn'] >= 40 and rf['kernel'] >= 20                       # trunks / bias-only convolutions
-    assert set(rt['ops']) == {'area_pool', 'eca_scale_add', 'gated_update'}
+    assert set(rt['ops']) == {'area_pool', 'eca_scale_add', 'gated_update', 'qt_p2q_splits'}
+    assert len(rt['ops']['qt_p2q_splits']['picked']) == 1                  # one decision per (objects, pixels)
+
+
+def test_pick_times_every_candidate_once_and_sticks():
+    t = _FakeDeviceTrials(ms=(5.0, 1.0, 3.0, 4.0))      # scripted clock cycles through these per timed call
+    # the fake clock alternates by call count: candidate order [a, b, c] -> 5, 1, 3 => b
+    class Clock:
+        n = 0
+    ran = []
+
+    def run(c):
+        ran.append(c)
+    t._time = lambda fn: (fn(), (5.0, 1.0, 3.0)[len(ran) - 1])[1]
+    probe = torch.zeros(1)
+    with torch.inference_mode():
+        assert t.pick('op', (1,), ['a', 'b', 'c'], run, probe) == 'b'
+        assert ran == ['a', 'b', 'c']
+        assert t.pick('op', (1,), ['a', 'b', 'c'], run, probe) == 'b' and ran == ['a', 'b', 'c']
+        assert t.pick('op', (2,), ['only'], run, probe) == 'only'
+    assert t.report()['ops']['op'] == {'picked': ['b']}

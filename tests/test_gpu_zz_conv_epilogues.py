@@ -167,3 +167,24 @@ def test_stream_with_glue_kernels_matches_aten_chains():
     print('glue ops (stream, 96x160):', rep)
     assert rep['errors'] == 0, rep
     assert not off.op_trials.decisions
+
+
+@pytest.mark.parametrize('BK,HW', [(3, 1620), (2, 77)])
+def test_p2q_every_split_candidate_gives_the_same_attention(BK, HW):
+    """qt_pixel_to_query with each split count offered to the on-device A/B: same result up to the summation order."""
+    import cutie_b200.kernels as K_
+    g = torch.Generator().manual_seed(8)
+    M = BK * 16
+    qfold = (torch.randn(M, 8, 256, generator=g) / 8).cuda()
+    pix = (torch.randn(BK, 256, HW, generator=g) * 2).cuda()
+    pe = torch.randn(BK, 256, HW, generator=g).cuda()
+    fg = (torch.rand(BK, HW, generator=g) < 0.3).to(torch.uint8).cuda()
+    cnt = fg.sum(1).int()
+    W = (torch.randn(256, 256, generator=g) / 16).cuda()
+    b = torch.randn(256, generator=g).cuda()
+    cands = K_.qt_p2q_split_candidates(BK, HW, 8)
+    ref = K_.qt_pixel_to_query(qfold, pix, pe, fg.view(1, BK, HW), cnt, W, b, 16)
+    assert len(cands) >= 2 or HW <= 32
+    for s in cands:
+        got = K_.qt_pixel_to_query(qfold, pix, pe, fg.view(1, BK, HW), cnt, W, b, 16, splits=s)
+        assert torch.allclose(got, ref, rtol=1e-5, atol=1e-5), s
