@@ -56,6 +56,11 @@ class ConvEpilogueFuser:
       'kernel'  F.conv2d(x, w, None) + cutie_bias_act(y, b, z, relu)     -- the bias-less convolution followed by ONE
                 float4 stream of ours (csrc/pixel.cu), same association as 'aten' => bit-identical results
 
+    Convolutions with a handful of input channels (the two ResNet stems: 3 and 5) get every form a second time as
+    `<form>+pad`: the input is zero-padded to a multiple of 4 channels and the weight likewise (cached twin), which is
+    what cuDNN's NHWC tensor-core kernels need for 16-byte channel vectors -- with C = 3 the round-1 profile shows the
+    generic `convolve_common_engine_float_NHWC` at 141 us per stem call.  The zero channel contributes exact zeros.
+
     Nothing is assumed about how any form behaves on a given GPU / cuDNN build: the first time a (layer, input geometry,
     epilogue) triple is seen OUTSIDE a stream capture, every applicable form runs on the live tensors, a candidate must
     match 'aten', all are timed with CUDA events, and the fastest is kept for that triple (`decisions`, `timings`).
@@ -76,6 +81,7 @@ class ConvEpilogueFuser:
         self.timings = {}            # key -> {form: ms}
         self.errors = []
         self._zeros = {}
+        self._twins = {}             # id(conv) -> (conv, twin with zero-padded input channels)
 
     # -- the forms ------------------------------------------------------------------------------------
     @staticmethod
@@ -121,7 +127,36 @@ class ConvEpilogueFuser:
         from cutie_b200 import kernels as K_
         return K_.bias_act_(self._conv(conv, x, False), conv.bias, z, relu)
 
+    @staticmethod
+    def _padded_channels(conv: nn.Conv2d) -> int:
+        """Input channels after zero padding, or 0 if this convolution does not get '+pad' forms."""
+        c = conv.in_channels
+        if conv.groups != 1 or c % 4 == 0 or c > 12:
+            return 0
+        return (c + 3) // 4 * 4
+
+    def _twin(self, conv: nn.Conv2d) -> nn.Conv2d:
+        got = self._twins.get(id(conv))
+        if got is not None and got[0] is conv and got[1].weight.device == conv.weight.device:
+            return got[1]
+        cp = self._padded_channels(conv)
+        tw = nn.Conv2d(cp, conv.out_channels, conv.kernel_size, conv.stride, conv.padding, conv.dilation, conv.groups,
+                       bias=conv.bias is not None)
+        w = torch.zeros(conv.out_channels, cp, *conv.kernel_size, dtype=conv.weight.dtype, device=conv.weight.device)
+        w[:, :conv.in_channels] = conv.weight.detach()
+        if conv.weight.is_contiguous(memory_format=torch.channels_last) and not conv.weight.is_contiguous():
+            w = w.contiguous(memory_format=torch.channels_last)
+        tw.weight = nn.Parameter(w, requires_grad=False)
+        tw.bias = conv.bias                       # the same Parameter object
+        tw.eval()
+        self._twins[id(conv)] = (conv, tw)
+        return tw
+
     def run(self, form: str, conv: nn.Conv2d, x: torch.Tensor, z=None, relu: bool = True) -> torch.Tensor:
+        if form.endswith('+pad'):
+            tw = self._twin(conv)
+            x = F.pad(x, (0, 0, 0, 0, 0, tw.in_channels - x.shape[1]))        # keeps x's memory format
+            conv, form = tw, form[:-4]
         if form == 'cudnn':
             return self.fused(conv, x, z)
         if form == 'kernel':
@@ -145,8 +180,11 @@ class ConvEpilogueFuser:
         b.synchronize()
         return a.elapsed_time(b) / self.trial_iters
 
-    def _candidates(self, relu: bool):
-        return [f for f in self.forms if f != 'aten' and (relu or f != 'cudnn')]
+    def _candidates(self, relu: bool, conv: nn.Conv2d = None):
+        base = [f for f in self.forms if f != 'aten' and (relu or f != 'cudnn')]
+        if conv is not None and self._padded_channels(conv):
+            base += [f + '+pad' for f in self.forms if relu or f != 'cudnn']
+        return base
 
     def _trial(self, key, conv, x, z, relu) -> str:
         from cutie_b200.kernels import KernelError
@@ -154,7 +192,7 @@ class ConvEpilogueFuser:
         ref = self.unfused(conv, x, z, relu)
         scale = float(ref.abs().max()) + 1e-6
         times = {'aten': self._time(lambda: self.unfused(conv, x, z, relu))}
-        for form in self._candidates(relu):
+        for form in self._candidates(relu, conv):
             try:
                 out = self.run(form, conv, x, z, relu)
                 err = float((out - ref).abs().max())
@@ -198,6 +236,7 @@ class ConvEpilogueFuser:
 
     def report(self) -> dict:
         counts = {f: sum(1 for v in self.decisions.values() if v == f) for f in self.FORMS}
+        counts['padded_input'] = sum(1 for v in self.decisions.values() if v.endswith('+pad'))
         saved = sum(t['aten'] - t[self.decisions[k]] for k, t in self.timings.items() if k in self.decisions)
         return {'enabled': self.enabled, **counts, 'errors': len(self.errors),
                 'first_error': self.errors[0] if self.errors else None, 'trial_ms_saved_per_pass': saved}

@@ -53,9 +53,14 @@ class _FakeDeviceFuser(fuse.ConvEpilogueFuser):
         self._which = 'kernel'
         return super().kernel(conv, x, z, relu)
 
+    def run(self, form, conv, x, z=None, relu=True):
+        self._form = form
+        return super().run(form, conv, x, z, relu)
+
     def _time(self, fn):
+        self._form = 'aten'                 # the reference form is timed through unfused(), not run()
         fn()
-        return self.ms[self._which]
+        return self.ms.get(self._form, self.ms[self._which])
 
     def unfused(self, conv, x, z=None, relu=True):
         self.calls['aten'] += 1
@@ -368,3 +373,38 @@ def test_pick_times_every_candidate_once_and_sticks():
         assert t.pick('op', (1,), ['a', 'b', 'c'], run, probe) == 'b' and ran == ['a', 'b', 'c']
         assert t.pick('op', (2,), ['only'], run, probe) == 'only'
     assert t.report()['ops']['op'] == {'picked': ['b']}
+
+
+def test_stem_gets_padded_input_forms(cpu_kernels):
+    """3- and 5-channel stems: every form is also offered on a zero-padded (4 / 8 channel) input with a zero-padded
+    weight twin; the results agree with the plain convolution and the twin shares the bias Parameter."""
+    torch.manual_seed(5)
+    for cin, cp in ((3, 4), (5, 8)):
+        conv = torch.nn.Conv2d(cin, 16, 7, stride=2, padding=3).eval()
+        x = torch.randn(2, cin, 20, 28).contiguous(memory_format=torch.channels_last)
+        conv = conv.to(memory_format=torch.channels_last)
+        f = _FakeDeviceFuser(ms={'aten': 9.0, 'cudnn': 8.0, 'kernel': 7.0, 'aten+pad': 6.0, 'cudnn+pad': 1.0,
+                                 'kernel+pad': 5.0})           # scripted clock: the padded cuDNN form is the fastest
+        seen = []
+        orig_run = f.run
+
+        def run(form, *a, **k):
+            seen.append(form)
+            return orig_run(form, *a, **k)
+        f.run = run
+        with torch.inference_mode():
+            want = torch.relu(conv(x))
+            fuse.attach_epilogue_fuser(conv, f)
+            got = fuse.conv_relu(conv, x)
+            again = fuse.conv_relu(conv, x)
+        assert {'cudnn+pad', 'kernel+pad', 'aten+pad'} <= set(seen)
+        assert list(f.decisions.values()) == ['cudnn+pad'] and f.report()['padded_input'] == 1
+        tw = f._twins[id(conv)][1]
+        assert tw.in_channels == cp and tw.bias is conv.bias and float(tw.weight[:, cin:].abs().sum()) == 0
+        assert torch.equal(tw.weight[:, :cin], conv.weight)
+        assert tw.weight.is_contiguous(memory_format=torch.channels_last)
+        assert torch.allclose(got, want, atol=1e-5) and torch.allclose(again, want, atol=1e-5)
+        assert f.report()['errors'] == 0
+    # wide convolutions never get padded forms
+    assert fuse.ConvEpilogueFuser._padded_channels(torch.nn.Conv2d(64, 64, 3)) == 0
+    assert fuse.ConvEpilogueFuser._padded_channels(torch.nn.Conv2d(258, 64, 1)) == 0
