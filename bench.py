@@ -181,6 +181,11 @@ def preflight(local: int) -> int:
         for shape, f in (((1, 3, 480, 864), 16), ((3, 256, 60, 108), 2), ((3, 257, 120, 216), 4)):
             x = torch.rand(*shape, generator=g).to(dev)
             assert float((K_.area_pool(x, f) - F.interpolate(x, scale_factor=1.0 / f, mode='area')).abs().max()) <= 1e-6, 'area_pool'
+        for shape in ((1, 64, 240, 432), (3, 64, 48, 80)):
+            for fmt in (torch.contiguous_format, torch.channels_last):
+                y, b = rnd(*shape).contiguous(memory_format=fmt), rnd(shape[1])
+                want = F.max_pool2d(torch.relu(y + b.view(1, -1, 1, 1)), 3, stride=2, padding=1)
+                assert torch.equal(K_.bias_relu_maxpool(y, b), want), 'bias_relu_maxpool'
         h, v = rnd(1, 3, 256, 30, 54), 2 * rnd(1, 3, 768, 30, 54)
         assert float((K_.gated_update(h, v) - gated_update(h, v)).abs().max()) <= 2e-6, 'gated_update'
         cfg = default_config(mem_every=2, max_mem_frames=3)

@@ -6,6 +6,8 @@
 // PIXEL and loops over batch x channels inside it: 7 CTAs (337 us) for [3 x 256 x 30 x 54] and 26 CTAs (169 us)
 // for [3 x 256 x 60 x 108] on a 148-SM part.  Here: one thread per four consecutive output pixels of one
 // (object, channel) plane, float4 stores, the add fused -- the kernel is a pure HBM stream.
+#include <math_constants.h>
+
 #include "common.cuh"
 
 namespace cutie {
@@ -237,6 +239,64 @@ __global__ void __launch_bounds__(256) gated_update_kernel(const float* __restri
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// ResNet stem tail: out = relu(maxpool3x3/s2/p1(y) + bias[c]) for a bias-less convolution output y.  Equal, bit for bit,
+// to maxpool(relu(y + bias)) (adding a constant and clamping are monotone, so they commute with max) -- i.e. to
+// utils/resnet.py:139-142 `relu(bn1(conv1(x)))` -> `maxpool` with the BatchNorm folded into the convolution.  ATen
+// spends three launches here (broadcast bias add 18.5 us, clamp, max_pool_forward_nhwc 41 us for [1,64,240,432] at
+// 480p); this is one pass: 26.5 MB in, 6.6 MB out.  CL: storage [N,H,W,C], one thread per 4 channels of an output
+// pixel; otherwise [N,C,H,W], one thread per output pixel.
+template <bool CL>
+__global__ void __launch_bounds__(256) bias_relu_maxpool_kernel(const float* __restrict__ y, const float* __restrict__ bias,
+                                                                float* __restrict__ out, long long total, int C, int H,
+                                                                int W, int Ho, int Wo) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  if (CL) {
+    const int C4 = C >> 2;
+    const int c4 = (int)(t % C4);
+    const int X = (int)((t / C4) % Wo);
+    const int Y = (int)((t / ((long long)C4 * Wo)) % Ho);
+    const long long n = t / ((long long)C4 * Wo * Ho);
+    float4 m = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int yy = 2 * Y - 1 + dy;
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int xx = 2 * X - 1 + dx;
+        if (xx < 0 || xx >= W) continue;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(y + ((n * H + yy) * W + xx) * C) + c4);
+        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+      }
+    }
+    const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + c4);
+    m.x += b.x; m.y += b.y; m.z += b.z; m.w += b.w;
+    m.x = m.x < 0.f ? 0.f : m.x; m.y = m.y < 0.f ? 0.f : m.y; m.z = m.z < 0.f ? 0.f : m.z; m.w = m.w < 0.f ? 0.f : m.w;
+    reinterpret_cast<float4*>(out)[t] = m;
+  } else {
+    const int X = (int)(t % Wo);
+    const int Y = (int)((t / Wo) % Ho);
+    const long long plane = t / ((long long)Wo * Ho);              // n * C + c
+    const float* src = y + plane * (long long)H * W;
+    float m = -CUDART_INF_F;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int yy = 2 * Y - 1 + dy;
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int xx = 2 * X - 1 + dx;
+        if (xx < 0 || xx >= W) continue;
+        m = fmaxf(m, __ldg(src + (long long)yy * W + xx));
+      }
+    }
+    m += __ldg(bias + (int)(plane % C));
+    out[t] = m < 0.f ? 0.f : m;
+  }
+}
+
 }  // namespace cutie
 
 using namespace cutie;
@@ -347,6 +407,27 @@ extern "C" int cutie_gated_update(const float* v, const float* h, float* out, in
   cudaStream_t st = (cudaStream_t)stream;
   if (vec) gated_update_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(v, h, out, total, (int)d, HW);
   else gated_update_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(v, h, out, total, (int)d, HW);
+  CUTIE_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int cutie_bias_relu_maxpool(const float* y, const float* bias, float* out, int64_t N, int64_t C, int64_t H,
+                                       int64_t W, int channels_last, void* stream) {
+  CUTIE_REQUIRE(y && bias && out && N >= 1 && C >= 1 && H >= 1 && W >= 1, "null/empty argument");
+  CUTIE_REQUIRE(H < (1 << 20) && W < (1 << 20) && C < (1 << 20), "feature map too large");
+  const int Ho = (int)((H - 1) / 2 + 1), Wo = (int)((W - 1) / 2 + 1);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (channels_last) {
+    CUTIE_REQUIRE(C % 4 == 0 && ((((uintptr_t)y | (uintptr_t)out | (uintptr_t)bias) & 15) == 0),
+                  "channels-last path needs C % 4 == 0 and 16-byte aligned pointers");
+    const long long total = (long long)N * Ho * Wo * (C / 4);
+    bias_relu_maxpool_kernel<true><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(y, bias, out, total, (int)C, (int)H,
+                                                                                   (int)W, Ho, Wo);
+  } else {
+    const long long total = (long long)N * C * Ho * Wo;
+    bias_relu_maxpool_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(y, bias, out, total, (int)C, (int)H,
+                                                                                    (int)W, Ho, Wo);
+  }
   CUTIE_CHECK_LAUNCH();
   return 0;
 }

@@ -338,6 +338,29 @@ def bias_act_(y: torch.Tensor, bias: torch.Tensor, z: Optional[torch.Tensor] = N
     return y
 
 
+def bias_relu_maxpool(y: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """relu(max_pool2d(y, 3, stride=2, padding=1) + bias[c]) == max_pool2d(relu(y + bias), 3, 2, 1) for a bias-less
+    convolution output y [N,C,H,W] (dense NCHW, or channels-last with C % 4 == 0); the result keeps y's storage order."""
+    assert y.dim() == 4 and y.dtype == torch.float32
+    N, C, H, W = y.shape
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    if y.is_contiguous():
+        cl = False
+    elif y.is_contiguous(memory_format=torch.channels_last) and C % 4 == 0:
+        cl = True
+    else:
+        y, cl = y.contiguous(), False
+    out = torch.empty(N, C, Ho, Wo, dtype=torch.float32, device=y.device,
+                      memory_format=torch.channels_last if cl else torch.contiguous_format)
+    bias = bias.detach()
+    assert bias.shape == (C,) and bias.is_contiguous()
+    with _call('bias_relu_maxpool', 1):
+        st = lib().cutie_bias_relu_maxpool(_ptr(y), _ptr(bias), _ptr(out), _i64(N), _i64(C), _i64(H), _i64(W), int(cl),
+                                           _stream())
+    _check(st, 'cutie_bias_relu_maxpool')
+    return out
+
+
 def area_pool(x: torch.Tensor, f: int) -> torch.Tensor:
     """F.interpolate(x, scale_factor=1/f, mode='area') for [..., H, W] with H % f == W % f == 0."""
     H, W = x.shape[-2:]

@@ -9,7 +9,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from cutie_b200.model.backbone import ResNetTrunk
-from cutie_b200.model.fuse import conv_relu
+from cutie_b200.model.fuse import conv_relu_maxpool
 from cutie_b200.model.blocks import (DeepSensoryUpdater, FeatureFusion, MultiScaleSensoryUpdater, ObjConv2d,
                                      UpsampleBlock, fold, unfold)
 
@@ -34,7 +34,7 @@ class PixelEncoder(nn.Module):
         if self.channels_last:
             x = x.contiguous(memory_format=torch.channels_last)
         if getattr(self, 'bn_folded', False):
-            x = F.max_pool2d(conv_relu(self.conv1, x), 3, stride=2, padding=1)
+            x = conv_relu_maxpool(self.conv1, x)
         else:
             x = F.max_pool2d(F.relu(self.bn1(self.conv1(x)), inplace=True), 3, stride=2, padding=1)
         f4 = self.res2(x)
@@ -89,7 +89,7 @@ class MaskEncoder(nn.Module):
                 t = t.contiguous(memory_format=torch.channels_last)
             if getattr(self, 'bn_folded', False):
                 # relu and max-pool commute (both monotone): relu(maxpool(y)) == maxpool(relu(y)), bit for bit
-                t = F.max_pool2d(conv_relu(self.conv1, t), 3, stride=2, padding=1)
+                t = conv_relu_maxpool(self.conv1, t)
             else:
                 t = F.relu(F.max_pool2d(self.bn1(self.conv1(t)), 3, stride=2, padding=1))
             t = self.layer3(self.layer2(self.layer1(t)))

@@ -229,6 +229,55 @@ class ConvEpilogueFuser:
             form = self.decisions[key] = self._trial(key, conv, x, z, relu)
         return self.run(form, conv, x, z, relu)
 
+    # -- ResNet stem: relu(conv(x) + bias) -> max_pool2d(3, 2, 1) ---------------------------------------------
+    def stem(self, conv: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
+        """max_pool2d(relu(conv(x)), 3, stride=2, padding=1): either the chosen conv+ReLU form followed by ATen's pooling
+        ('aten'), or the bias-less convolution followed by cutie_bias_relu_maxpool ('pool', 'pool+pad'): bias, clamp and
+        pooling in one pass over the convolution output (they commute with max, so the result is the same)."""
+        def aten():
+            return F.max_pool2d(self(conv, x, None, True), 3, stride=2, padding=1)
+        if not self._eligible(conv, x):
+            return F.max_pool2d(self.unfused(conv, x), 3, stride=2, padding=1)
+        key = ('stem',) + self._key(conv, x, None, True)
+        form = self.decisions.get(key)
+        if form is None:
+            if self._capturing():
+                return aten()
+            form = self.decisions[key] = self._stem_trial(key, conv, x, aten)
+        return self._stem_run(form, conv, x, aten)
+
+    def _stem_run(self, form: str, conv: nn.Conv2d, x: torch.Tensor, aten) -> torch.Tensor:
+        if form == 'aten':
+            return aten()
+        from cutie_b200 import kernels as K_
+        if form.endswith('+pad'):
+            tw = self._twin(conv)
+            x = F.pad(x, (0, 0, 0, 0, 0, tw.in_channels - x.shape[1]))
+            conv = tw
+        return K_.bias_relu_maxpool(self._conv(conv, x, False), conv.bias)
+
+    def _stem_trial(self, key, conv, x, aten) -> str:
+        from cutie_b200.kernels import KernelError
+        what = f'stem conv {tuple(conv.weight.shape)} on {tuple(x.shape)}'
+        ref = aten()                                   # also settles the conv+ReLU decision it is built on
+        scale = float(ref.abs().max()) + 1e-6
+        times = {'aten': self._time(aten)}
+        for form in ['pool'] + (['pool+pad'] if self._padded_channels(conv) else []):
+            try:
+                out = self._stem_run(form, conv, x, aten)
+                err = float((out - ref).abs().max())
+                tol = (2e-2 if torch.backends.cudnn.allow_tf32 else 2e-4) * scale
+                if not (out.shape == ref.shape and err <= tol):
+                    self.errors.append(f'{what}: {form} differs by {err:.3e} (scale {scale:.3e})')
+                    continue
+                times[form] = self._time(lambda: self._stem_run(form, conv, x, aten))
+            except KernelError:
+                raise
+            except Exception as e:                     # noqa: BLE001 -- cuDNN / dispatcher failure of the bias-less call
+                self.errors.append(f'{what}: {form}: {type(e).__name__}: {e}')
+        self.timings[key] = times
+        return min(times, key=times.get)
+
     def __deepcopy__(self, memo):          # a copied model gets its own (empty) fuser with the same settings
         new = ConvEpilogueFuser(self.enabled, self.trial_iters, self.forms)
         memo[id(self)] = new
@@ -237,6 +286,7 @@ class ConvEpilogueFuser:
     def report(self) -> dict:
         counts = {f: sum(1 for v in self.decisions.values() if v == f) for f in self.FORMS}
         counts['padded_input'] = sum(1 for v in self.decisions.values() if v.endswith('+pad'))
+        counts['stem_pool'] = sum(1 for v in self.decisions.values() if v.startswith('pool'))
         saved = sum(t['aten'] - t[self.decisions[k]] for k, t in self.timings.items() if k in self.decisions)
         return {'enabled': self.enabled, **counts, 'errors': len(self.errors),
                 'first_error': self.errors[0] if self.errors else None, 'trial_ms_saved_per_pass': saved}
@@ -277,6 +327,14 @@ def conv_relu(conv: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
     """relu(conv(x)) -- in the form the model's fuser chose for this layer, else convolution + bias add + clamp."""
     f = getattr(conv, 'epilogue_fuser', None)
     return ConvEpilogueFuser.unfused(conv, x) if f is None else f(conv, x)
+
+
+def conv_relu_maxpool(conv: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
+    """max_pool2d(relu(conv(x)), 3, stride=2, padding=1) -- the ResNet stem."""
+    f = getattr(conv, 'epilogue_fuser', None)
+    if f is None:
+        return F.max_pool2d(ConvEpilogueFuser.unfused(conv, x), 3, stride=2, padding=1)
+    return f.stem(conv, x)
 
 
 def conv_add_relu(conv: nn.Conv2d, x: torch.Tensor, z: torch.Tensor) -> torch.Tensor:

@@ -144,6 +144,13 @@ int cutie_eca_scale_add(float* y, const float* x, const float* mean, const float
  * h [P,d,HW] -> out [P,d,HW] = sigmoid(vf) * h * (1 - sigmoid(vu)) + sigmoid(vu) * tanh(vn).  Dense fp32. */
 int cutie_gated_update(const float* v, const float* h, float* out, int64_t P, int64_t d, int64_t HW, void* stream);
 
+/* out = relu(maxpool3x3/stride2/pad1(y) + bias[c]) == maxpool(relu(y + bias)): the tail of both ResNet stems
+ * (cutie/model/utils/resnet.py:139-142; cutie/model/big_modules.py:42-46, 150-154) applied to the BIAS-LESS
+ * convolution output (BatchNorm folded).  y [N,C,H,W] dense fp32 (channels_last == 0) or [N,H,W,C] (1, needs
+ * C % 4 == 0), out the same layout with Ho = (H-1)/2 + 1, Wo = (W-1)/2 + 1. */
+int cutie_bias_relu_maxpool(const float* y, const float* bias, float* out, int64_t N, int64_t C, int64_t H, int64_t W,
+                            int channels_last, void* stream);
+
 /* out[y,x] = lut[argmax_c prob[c,y,x]]: InferenceCore.output_prob_to_mask (inference_core.py:377-385: argmax over
  * the 1+K channels, then ObjectManager.tmp_to_obj_cls object_manager.py:99-104) in one pass.  prob may be a strided
  * view (plane_stride / row_stride in elements, unit pixel stride); lut int64 [C]; out int64 [H,W] contiguous.

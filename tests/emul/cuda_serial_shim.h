@@ -17,6 +17,7 @@ static dim3 blockIdx, threadIdx, gridDim, blockDim;
 #define __restrict__
 #define __launch_bounds__(...)
 template <typename T> static inline T __ldg(const T* p) { return *p; }
+#define CUDART_INF_F (__builtin_huge_valf())
 // round-to-nearest single operations (the host compiler must not contract them either: built with -ffp-contract=off)
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }

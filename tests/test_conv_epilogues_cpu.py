@@ -20,7 +20,7 @@ class _FakeDeviceFuser(fuse.ConvEpilogueFuser):
 
     def __init__(self, ms=None, broken=None, forms=fuse.ConvEpilogueFuser.FORMS):
         super().__init__(enabled=True, forms=forms)
-        self.ms = {**dict(aten=3.0, cudnn=1.0, kernel=2.0), **(ms or {})}
+        self.ms = {**{'aten': 3.0, 'cudnn': 1.0, 'kernel': 2.0, 'stem-aten': 3.0, 'pool': 0.5, 'pool+pad': 0.7}, **(ms or {})}
         self.broken = broken
         self.calls = {'aten': 0, 'cudnn': 0, 'kernel': 0}
         self._which = None
@@ -56,6 +56,11 @@ class _FakeDeviceFuser(fuse.ConvEpilogueFuser):
     def run(self, form, conv, x, z=None, relu=True):
         self._form = form
         return super().run(form, conv, x, z, relu)
+
+    def _stem_run(self, form, conv, x, aten):
+        out = super()._stem_run(form, conv, x, aten)
+        self._form = form if form != 'aten' else 'stem-aten'
+        return out
 
     def _time(self, fn):
         self._form = 'aten'                 # the reference form is timed through unfused(), not run()
@@ -352,6 +357,7 @@ def test_whole_stream_with_every_optional_form_active(cpu_kernels):
     rf, rt = f.report(), t.report()
     assert rf['errors'] == 0 and rt['errors'] == 0, (rf, rt)
     assert rf['cudnn'] >= 40 and rf['kernel'] >= 20                       # trunks / bias-only convolutions
+    assert rf['stem_pool'] == 2                                           # pixel- and mask-encoder stems
     assert set(rt['ops']) == {'area_pool', 'eca_scale_add', 'gated_update', 'qt_p2q_splits'}
     assert len(rt['ops']['qt_p2q_splits']['picked']) == 1                  # one decision per (objects, pixels)
 

@@ -188,3 +188,20 @@ def test_p2q_every_split_candidate_gives_the_same_attention(BK, HW):
     for s in cands:
         got = K_.qt_pixel_to_query(qfold, pix, pe, fg.view(1, BK, HW), cnt, W, b, 16, splits=s)
         assert torch.allclose(got, ref, rtol=1e-5, atol=1e-5), s
+
+
+@pytest.mark.parametrize('shape', [(1, 64, 240, 432), (3, 64, 48, 80), (2, 8, 9, 12), (1, 6, 7, 7), (1, 4, 1, 1)])
+@pytest.mark.parametrize('cl', [False, True])
+def test_bias_relu_maxpool_kernel_is_bit_identical(shape, cl):
+    """cutie_bias_relu_maxpool(y, b) == max_pool2d(relu(y + b), 3, 2, 1), NCHW and channels-last (C % 4 != 0 falls back
+    to an NCHW copy inside the wrapper)."""
+    import torch.nn.functional as F
+    import cutie_b200.kernels as K_
+    g = torch.Generator().manual_seed(shape[2])
+    y = torch.randn(*shape, generator=g).cuda()
+    if cl:
+        y = y.contiguous(memory_format=torch.channels_last)
+    bias = torch.randn(shape[1], generator=g).cuda()
+    want = F.max_pool2d(torch.relu(y + bias.view(1, -1, 1, 1)), 3, stride=2, padding=1)
+    got = K_.bias_relu_maxpool(y, bias)
+    assert got.shape == want.shape and torch.equal(got, want)

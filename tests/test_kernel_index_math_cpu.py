@@ -41,6 +41,13 @@ extern "C" void emu_eca(float* y, const float* x, const float* mean, const float
     else EMU_LAUNCH((cutie::scale_add_kernel<false, false>), blocks, 256, y, gate, x, total, (int)C, HW);
   }
 }
+extern "C" void emu_stem_pool(const float* y, const float* bias, float* out, long long N, int C, int H, int W, int cl) {
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const long long total = cl ? N * Ho * Wo * (C / 4) : N * C * Ho * Wo;
+  const int blocks = (int)((total + 255) / 256);
+  if (cl) EMU_LAUNCH((cutie::bias_relu_maxpool_kernel<true>), blocks, 256, y, bias, out, total, C, H, W, Ho, Wo);
+  else EMU_LAUNCH((cutie::bias_relu_maxpool_kernel<false>), blocks, 256, y, bias, out, total, C, H, W, Ho, Wo);
+}
 extern "C" void emu_gated(const float* v, const float* h, float* out, long long P, long long d, long long HW, int vec,
                           int blocks) {
   const long long n = P * d * HW, total = vec ? n / 4 : n;
@@ -71,7 +78,8 @@ def emu(tmp_path_factory):
     for head in (r'template <int F, bool VEC>\n__global__ void [^\n]*area_pool_kernel\(',
                  r'__global__ void [^\n]*eca_gate_kernel\(',
                  r'template <bool CL, bool VEC>\n__global__ void [^\n]*scale_add_kernel\(',
-                 r'template <bool VEC>\n__global__ void [^\n]*gated_update_kernel\('):
+                 r'template <bool VEC>\n__global__ void [^\n]*gated_update_kernel\(',
+                 r'template <bool CL>\n__global__ void [^\n]*bias_relu_maxpool_kernel\('):
         mm = re.search('(' + head + r'.*?\n}\n)', src, re.S)
         assert mm, head
         more.append(mm.group(1))
@@ -173,3 +181,26 @@ def test_gated_update_index_math(emu, P_, d, HW, vec, blocks):
     emu.emu_gated(P(v.data_ptr()), P(h.data_ptr()), P(out.data_ptr()), ctypes.c_longlong(P_), ctypes.c_longlong(d),
                   ctypes.c_longlong(HW), int(vec), blocks)
     assert torch.allclose(out, want, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize('shape', [(2, 8, 9, 12), (1, 4, 6, 5), (3, 12, 7, 7), (1, 64, 30, 54), (2, 4, 1, 1), (1, 8, 2, 3)])
+@pytest.mark.parametrize('cl', [False, True])
+def test_bias_relu_maxpool_index_math(emu, shape, cl):
+    import torch.nn.functional as F
+    N, C, H, W = shape
+    g = torch.Generator().manual_seed(H * 31 + W)
+    y = torch.randn(*shape, generator=g)
+    bias = torch.randn(C, generator=g)
+    want = F.max_pool2d(torch.relu(y + bias.view(1, -1, 1, 1)), 3, stride=2, padding=1)
+    Ho, Wo = want.shape[-2:]
+    assert (Ho, Wo) == ((H - 1) // 2 + 1, (W - 1) // 2 + 1)
+    P = ctypes.c_void_p
+    if cl:
+        ybuf = y.permute(0, 2, 3, 1).contiguous()
+        out = torch.full((N, Ho, Wo, C), float('nan'))
+    else:
+        ybuf = y.contiguous()
+        out = torch.full((N, C, Ho, Wo), float('nan'))
+    emu.emu_stem_pool(P(ybuf.data_ptr()), P(bias.data_ptr()), P(out.data_ptr()), ctypes.c_longlong(N), C, H, W, int(cl))
+    got = out.permute(0, 3, 1, 2) if cl else out
+    assert torch.equal(got, want)               # max, one add, clamp: bit-identical to maxpool(relu(y + b))
