@@ -65,7 +65,34 @@ class ChannelAttnResBlock(nn.Module):
         self.downsample = nn.Identity() if c_in == c_out else nn.Conv2d(c_in, c_out, 1)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        y = self.conv2(conv_relu(self.conv1, F.relu(x)))
+        t = getattr(self, 'op_trials', None)
+        twins = getattr(self, 'cl_twins', None)
+        if t is None or twins is None or x.dim() != 4 or not x.is_contiguous() or x.shape[1] % 4:
+            return self._forward(x, self.conv1, self.conv2)
+        # NCHW input (our transformer kernels emit channel-major pixels): cuDNN then re-lays-out input, weight AND output
+        # around each 3x3 convolution (6 + 7 + 6 us around a 19 us kernel at 480p).  Alternative, A/B-ed on the device: one
+        # copy to channels-last on entry, channels-last weight twins, everything in between channels-last.
+        tol = 2e-2 if torch.backends.cudnn.allow_tf32 else 2e-4
+        return t('caresblock_channels_last', (tuple(x.shape),), lambda: self._forward(x, self.conv1, self.conv2),
+                 lambda trial: self._forward(x.contiguous(memory_format=torch.channels_last), *twins), x, rtol=tol)
+
+    def make_channels_last_twins(self):
+        """conv1 / conv2 copies with channels-last weights (sharing the bias Parameters), for the channels-last variant of
+        forward(); plain attributes, so state_dict is unchanged.  Needs c_in == c_out (no projection shortcut)."""
+        if not isinstance(self.downsample, nn.Identity):
+            return None
+        twins = []
+        for conv in (self.conv1, self.conv2):
+            tw = nn.Conv2d(conv.in_channels, conv.out_channels, conv.kernel_size, conv.stride, conv.padding)
+            tw.weight = nn.Parameter(conv.weight.detach().clone().contiguous(memory_format=torch.channels_last),
+                                     requires_grad=False)
+            tw.bias = conv.bias
+            twins.append(tw.eval())
+        object.__setattr__(self, 'cl_twins', tuple(twins))
+        return self.cl_twins
+
+    def _forward(self, x: torch.Tensor, conv1: nn.Conv2d, conv2: nn.Conv2d) -> torch.Tensor:
+        y = conv2(conv_relu(conv1, F.relu(x)))
         skip = self.downsample(x)
 
         def aten():

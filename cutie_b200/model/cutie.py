@@ -194,6 +194,17 @@ class CUTIE(nn.Module):
         # after the folding: fold_trunk_ replaces the trunk convolutions by new modules
         object.__setattr__(self, 'conv_epilogues', ConvEpilogueFuser(enabled=bool(fuse_epilogues)))
         attach_epilogue_fuser(self, self.conv_epilogues)
+        if channels_last and fuse_glue and self.object_transformer_enabled:
+            # PixelFFN blocks sit between two of our channel-major kernels: offer a channels-last variant to the trial
+            for blk in self.object_transformer.blocks:
+                for tw in blk.pixel_ffn.conv.make_channels_last_twins() or ():
+                    attach_epilogue_fuser(tw, self.conv_epilogues)
+            # the two fuser blocks already receive channels-last tensors (their input descends from the channels-last
+            # trunk): keep their weights channels-last too instead of re-laying them out on every call
+            for fz in (self.pixel_fuser.fuser, self.mask_encoder.fuser):
+                for blk in (fz.block1, fz.block2):
+                    blk.conv1.to(memory_format=torch.channels_last)
+                    blk.conv2.to(memory_format=torch.channels_last)
         # pixel-side glue (area down-sampling, channel-attention tail, sensory GRU gates): ATen chains vs our kernels
         from cutie_b200.utils.op_trials import OpTrials, attach_op_trials
         attach_op_trials(self, OpTrials(enabled=bool(fuse_glue)))
