@@ -205,3 +205,30 @@ def test_bias_relu_maxpool_kernel_is_bit_identical(shape, cl):
     want = F.max_pool2d(torch.relu(y + bias.view(1, -1, 1, 1)), 3, stride=2, padding=1)
     got = K_.bias_relu_maxpool(y, bias)
     assert got.shape == want.shape and torch.equal(got, want)
+
+
+def test_pixel_ffn_channels_last_variant_matches_nchw():
+    """ChannelAttnResBlock with channels-last weight twins (one layout copy in, channels-last in between) vs the NCHW
+    form, both with every trial switched off (pure PyTorch/cuDNN) and with the trials on."""
+    from cutie_b200.model.blocks import ChannelAttnResBlock
+    from cutie_b200.model.fuse import ConvEpilogueFuser, attach_epilogue_fuser
+    from cutie_b200.utils.op_trials import OpTrials, attach_op_trials
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(0)
+    blk = ChannelAttnResBlock(256, 256).cuda().eval()
+    x = torch.randn(3, 256, 30, 54, device='cuda')
+    with torch.inference_mode():
+        ref = blk(x)
+        twins = blk.make_channels_last_twins()
+        got = blk._forward(x.contiguous(memory_format=torch.channels_last), *twins)
+        assert float((got - ref).abs().max()) <= 2e-4 * float(ref.abs().max())
+        fz, tr = ConvEpilogueFuser(), OpTrials()
+        attach_epilogue_fuser(blk, fz)
+        for tw in twins:
+            attach_epilogue_fuser(tw, fz)
+        attach_op_trials(blk, tr)
+        out1, out2 = blk(x), blk(x)
+    assert float((out1 - ref).abs().max()) <= 2e-4 * float(ref.abs().max())
+    assert float((out2 - ref).abs().max()) <= 2e-4 * float(ref.abs().max())
+    print('PixelFFN block trials:', tr.report(), fz.report())
+    assert tr.report()['errors'] == 0
