@@ -170,15 +170,8 @@ class ConvEpilogueFuser:
                 torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark)
 
     def _time(self, fn) -> float:
-        for _ in range(2):
-            fn()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(self.trial_iters):
-            fn()
-        b.record()
-        b.synchronize()
-        return a.elapsed_time(b) / self.trial_iters
+        from cutie_b200.utils.op_trials import gpu_time_ms
+        return gpu_time_ms(fn, self.trial_iters)       # launches queued back to back (device time, as in a graph replay)
 
     def _candidates(self, relu: bool, conv: nn.Conv2d = None):
         base = [f for f in self.forms if f != 'aten' and (relu or f != 'cudnn')]

@@ -17,6 +17,27 @@ import torch
 import torch.nn as nn
 
 
+def gpu_time_ms(fn: Callable, iters: int) -> float:
+    """Device time of one fn() with its launches queued back to back.  Measured eagerly, a chain of small kernels is
+    bounded by the host's launch rate (the GPU idles between them), which would favour whichever form has fewer
+    launches even when its kernels are slower -- but the frame path replays these launches from CUDA graphs, where only
+    device time counts.  So the GPU is parked on a ~1.5 ms spin kernel first, the host runs ahead and queues all
+    iterations behind it, and the events bracket a gap-free execution."""
+    for _ in range(2):
+        fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    try:
+        torch.cuda._sleep(3_000_000)
+    except Exception:              # noqa: BLE001 -- private helper missing: plain eager timing
+        pass
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    b.synchronize()
+    return a.elapsed_time(b) / iters
+
+
 class OpTrials:
     def __init__(self, enabled: bool = True, trial_iters: int = 6):
         self.enabled = enabled
@@ -33,15 +54,7 @@ class OpTrials:
         return torch.cuda.is_current_stream_capturing()
 
     def _time(self, fn) -> float:
-        for _ in range(2):
-            fn()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(self.trial_iters):
-            fn()
-        b.record()
-        b.synchronize()
-        return a.elapsed_time(b) / self.trial_iters
+        return gpu_time_ms(fn, self.trial_iters)
 
     def _trial(self, op, key, aten: Callable, kernel: Callable, rtol: float) -> bool:
         ref = aten()
