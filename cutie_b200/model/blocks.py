@@ -193,8 +193,15 @@ class MultiScaleSensoryUpdater(nn.Module):
         self.transform = ObjConv2d(mid_dim + sensory_dim, sensory_dim * 3, 3, padding=1)
 
     def forward(self, g16, g8, g4, h):
+        if isinstance(g4, (tuple, list)):
+            # channel groups handed over separately (decoder features | logits): area pooling is per channel, so pooling
+            # the pieces and concatenating at 1/16 of the size equals pooling their concatenation -- without the
+            # full-resolution torch.cat (a 40 MB copy per frame at 480p)
+            g4s = torch.cat([area_resize(self, t, (t.shape[-2] // 4, t.shape[-1] // 4)) for t in g4], 2)
+        else:
+            g4s = area_resize(self, g4, (g4.shape[-2] // 4, g4.shape[-1] // 4))
         g = self.g16_conv(g16) + self.g8_conv(area_resize(self, g8, (g8.shape[-2] // 2, g8.shape[-1] // 2))) + \
-            self.g4_conv(area_resize(self, g4, (g4.shape[-2] // 4, g4.shape[-1] // 4)))
+            self.g4_conv(g4s)
         return gated_update(h.float(), self.transform(torch.cat([g.float(), h.float()], 2)), self)
 
 

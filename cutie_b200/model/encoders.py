@@ -164,7 +164,7 @@ class MaskDecoder(nn.Module):
             p4 = self.up_8_4(p8, f4)
             lg = unfold(self.pred(F.relu(fold(p4).float())), B)             # [B,k,1,4h,4w]
             if update_sensory:
-                upd = self.sensory_update(p16, p8, torch.cat([p4, lg], 2), sensory[:, lo:hi])
+                upd = self.sensory_update(p16, p8, (p4, lg), sensory[:, lo:hi])
                 if len(spans) == 1:
                     new_sensory = upd
                 else:
