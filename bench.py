@@ -186,6 +186,12 @@ def preflight(local: int) -> int:
                 y, b = rnd(*shape).contiguous(memory_format=fmt), rnd(shape[1])
                 want = F.max_pool2d(torch.relu(y + b.view(1, -1, 1, 1)), 3, stride=2, padding=1)
                 assert torch.equal(K_.bias_relu_maxpool(y, b), want), 'bias_relu_maxpool'
+        from cutie_b200.utils.tensor_utils import aggregate
+        x = 4 * rnd(1, 3, 120, 216)
+        lg_want = F.interpolate(aggregate(torch.sigmoid(x), dim=1), scale_factor=4, mode='bilinear', align_corners=False)
+        lg, pr = K_.segment_tail(x)
+        assert float((lg - lg_want).abs().max()) <= 1e-4 and float((pr - F.softmax(lg_want, dim=1)).abs().max()) <= 1e-5, \
+            'segment_tail'
         h, v = rnd(1, 3, 256, 30, 54), 2 * rnd(1, 3, 768, 30, 54)
         assert float((K_.gated_update(h, v) - gated_update(h, v)).abs().max()) <= 2e-6, 'gated_update'
         cfg = default_config(mem_every=2, max_mem_frames=3)

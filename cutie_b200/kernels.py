@@ -361,6 +361,25 @@ def bias_relu_maxpool(y: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
     return out
 
 
+SEGMENT_TAIL_MAX_CHANNELS = 16
+
+
+def segment_tail(x: torch.Tensor):
+    """Decoder logits x [B,K,h,w] (stride 4) -> (logits [B,1+K,4h,4w], prob [B,1+K,4h,4w]): sigmoid, soft aggregation
+    (background = prod(1-p), clamp, log-odds), bilinear x4, softmax over channels."""
+    B, K, h, w = x.shape
+    assert x.dtype == torch.float32 and K + 1 <= SEGMENT_TAIL_MAX_CHANNELS
+    x = x.contiguous()
+    agg = torch.empty(B, K + 1, h, w, dtype=torch.float32, device=x.device)
+    logits = torch.empty(B, K + 1, 4 * h, 4 * w, dtype=torch.float32, device=x.device)
+    prob = torch.empty_like(logits)
+    with _call('segment_tail', 2):
+        st = lib().cutie_segment_tail(_ptr(x), _ptr(agg), _ptr(logits), _ptr(prob), _i64(B), _i64(K), _i64(h), _i64(w),
+                                      _stream())
+    _check(st, 'cutie_segment_tail')
+    return logits, prob
+
+
 def area_pool(x: torch.Tensor, f: int) -> torch.Tensor:
     """F.interpolate(x, scale_factor=1/f, mode='area') for [..., H, W] with H % f == W % f == 0."""
     H, W = x.shape[-2:]

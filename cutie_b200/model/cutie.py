@@ -12,6 +12,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from cutie_b200 import kernels as K_
 from cutie_b200.model.blocks import ObjConv2d, area_resize
 from cutie_b200.model.encoders import KeyProjection, MaskDecoder, MaskEncoder, PixelEncoder, PixelFeatureFuser
 from cutie_b200.model.object_summarizer import ObjectSummarizer
@@ -131,11 +132,20 @@ class CUTIE(nn.Module):
         """cutie.py:172-203 -> (sensory, logits [B,1+K,16h,16w], prob)."""
         sensory, logits = self.mask_decoder(ms_image_feat, memory_readout, sensory, chunk_size=chunk_size,
                                             update_sensory=update_sensory)
-        prob = torch.sigmoid(logits)
-        if selector is not None:
-            prob = prob * selector
-        logits = F.interpolate(aggregate(prob, dim=1), scale_factor=4, mode='bilinear', align_corners=False)
-        return sensory, logits, F.softmax(logits, dim=1)
+        raw = logits
+
+        def aten():
+            prob = torch.sigmoid(raw)
+            if selector is not None:
+                prob = prob * selector
+            lg = F.interpolate(aggregate(prob, dim=1), scale_factor=4, mode='bilinear', align_corners=False)
+            return lg, F.softmax(lg, dim=1)
+        t = getattr(self, 'op_trials', None)
+        if t is None or selector is not None or raw.dim() != 4 or raw.shape[1] + 1 > K_.SEGMENT_TAIL_MAX_CHANNELS:
+            lg, prob = aten()
+        else:           # sigmoid + aggregate + bilinear x4 + softmax (11 launches) as cutie_segment_tail (2)
+            lg, prob = t('segment_tail', (tuple(raw.shape),), aten, lambda trial: K_.segment_tail(raw), raw, rtol=1e-4)
+        return sensory, lg, prob
 
     def compute_aux(self, pix_feat, aux_inputs, selector):
         return self.aux_computer(pix_feat, aux_inputs, selector)

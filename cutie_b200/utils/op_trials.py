@@ -59,10 +59,17 @@ class OpTrials:
     def _trial(self, op, key, aten: Callable, kernel: Callable, rtol: float) -> bool:
         ref = aten()
         out = kernel(True)                           # trial=True: in-place kernels work on a copy
-        scale = float(ref.abs().max()) + 1e-6
-        err = float((out - ref).abs().max())
-        if not (out.shape == ref.shape and err <= rtol * scale):       # also catches NaN
-            self.errors.append(f'{op} {key}: kernel differs from ATen by {err:.3e} (scale {scale:.3e})')
+        refs = list(ref) if isinstance(ref, (tuple, list)) else [ref]
+        outs = list(out) if isinstance(out, (tuple, list)) else [out]
+        ok = len(refs) == len(outs)
+        worst = 0.0
+        for r, o in zip(refs, outs):
+            scale = float(r.abs().max()) + 1e-6
+            err = float((o - r).abs().max()) if o.shape == r.shape else float('nan')
+            worst = max(worst, err / scale) if err == err else float('nan')
+            ok = ok and o.shape == r.shape and err <= rtol * scale            # also catches NaN
+        if not ok:
+            self.errors.append(f'{op} {key}: kernel differs from ATen (relative error {worst:.3e}, allowed {rtol:.1e})')
             return False
         t_k = self._time(lambda: kernel(True))
         t_a = self._time(aten)
@@ -70,9 +77,9 @@ class OpTrials:
         return t_k <= t_a
 
     def __call__(self, op: str, key: tuple, aten: Callable, kernel: Callable, probe: torch.Tensor,
-                 rtol: float = 1e-5) -> torch.Tensor:
-        """aten(): the PyTorch composition.  kernel(trial: bool): our kernel; with trial=True it must not modify its
-        inputs (in-place kernels clone their destination)."""
+                 rtol: float = 1e-5):
+        """aten(): the PyTorch composition (a tensor or a tuple of tensors).  kernel(trial: bool): our kernel, same
+        outputs; with trial=True it must not modify its inputs (in-place kernels clone their destination)."""
         if not self._eligible(probe):
             return aten()
         use = self.decisions.get((op, key))

@@ -151,6 +151,13 @@ int cutie_gated_update(const float* v, const float* h, float* out, int64_t P, in
 int cutie_bias_relu_maxpool(const float* y, const float* bias, float* out, int64_t N, int64_t C, int64_t H, int64_t W,
                             int channels_last, void* stream);
 
+/* CUTIE.segment tail (cutie/model/cutie.py:196-203; aggregate cutie/utils/tensor_utils.py:47-54): x [B,K,h,w] decoder
+ * logits at stride 4 -> agg [B,1+K,h,w] = log-odds of clamp([prod(1-sigmoid x) | sigmoid x], 1e-7, 1-1e-7) (scratch /
+ * by-product), logits [B,1+K,4h,4w] = bilinear x4 (align_corners = False) of agg, prob = softmax over the 1+K channels.
+ * K <= 15; all dense fp32. */
+int cutie_segment_tail(const float* x, float* agg, float* logits, float* prob, int64_t B, int64_t K, int64_t h, int64_t w,
+                       void* stream);
+
 /* out[y,x] = lut[argmax_c prob[c,y,x]]: InferenceCore.output_prob_to_mask (inference_core.py:377-385: argmax over
  * the 1+K channels, then ObjectManager.tmp_to_obj_cls object_manager.py:99-104) in one pass.  prob may be a strided
  * view (plane_stride / row_stride in elements, unit pixel stride); lut int64 [C]; out int64 [H,W] contiguous.

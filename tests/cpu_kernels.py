@@ -256,6 +256,13 @@ def bias_relu_maxpool(y, bias):
     return F.max_pool2d(torch.relu(y + bias.detach().view(1, -1, 1, 1)), 3, stride=2, padding=1)
 
 
+def segment_tail(x):
+    import torch.nn.functional as F
+    from cutie_b200.utils.tensor_utils import aggregate
+    logits = F.interpolate(aggregate(torch.sigmoid(x), dim=1), scale_factor=4, mode='bilinear', align_corners=False)
+    return logits, F.softmax(logits, dim=1)
+
+
 def area_pool(x, f):
     import torch.nn.functional as F
     lead = x.shape[:-2]
@@ -276,7 +283,7 @@ def gated_update(h, v):
     return f * h * (1 - u) + u * n
 
 
-ALL = ['bias_act_', 'bias_relu_maxpool', 'area_pool', 'eca_scale_add_', 'gated_update', 'affinity_topk', 'topk_merge', 'readout_gather', 'usage_commit', 'bank_append', 'bank_export', 'bank_gather', 'bank_key_image', 'upsample2x_add', 'prob_to_mask',
+ALL = ['bias_act_', 'bias_relu_maxpool', 'segment_tail', 'area_pool', 'eca_scale_add_', 'gated_update', 'affinity_topk', 'topk_merge', 'readout_gather', 'usage_commit', 'bank_append', 'bank_export', 'bank_gather', 'bank_key_image', 'upsample2x_add', 'prob_to_mask',
        'consolidate', 'obj_summary_accumulate', 'qt_linear', 'qt_head_fold', 'qt_self_attention',
        'qt_aux_mask', 'qt_pixel_to_query', 'qt_query_to_pixel']
 

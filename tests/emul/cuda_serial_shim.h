@@ -22,6 +22,7 @@ template <typename T> static inline T __ldg(const T* p) { return *p; }
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
+static inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
 
 // serial launch: EMU_LAUNCH(kernel<...>, grid, block, args...)
 #define EMU_LAUNCH(kern, grid, block, ...)                                   \

@@ -358,7 +358,8 @@ def test_whole_stream_with_every_optional_form_active(cpu_kernels):
     assert rf['errors'] == 0 and rt['errors'] == 0, (rf, rt)
     assert rf['cudnn'] >= 40 and rf['kernel'] >= 20                       # trunks / bias-only convolutions
     assert rf['stem_pool'] == 2                                           # pixel- and mask-encoder stems
-    assert set(rt['ops']) == {'area_pool', 'eca_scale_add', 'gated_update', 'qt_p2q_splits', 'caresblock_channels_last'}
+    assert set(rt['ops']) == {'area_pool', 'eca_scale_add', 'gated_update', 'qt_p2q_splits', 'caresblock_channels_last',
+                              'segment_tail'}
     assert rt['ops']['caresblock_channels_last'] == {'kernel': 1, 'aten': 0}       # one geometry, three blocks
     assert len(rt['ops']['qt_p2q_splits']['picked']) == 1                  # one decision per (objects, pixels)
 

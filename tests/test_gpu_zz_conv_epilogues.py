@@ -232,3 +232,16 @@ def test_pixel_ffn_channels_last_variant_matches_nchw():
     assert float((out2 - ref).abs().max()) <= 2e-4 * float(ref.abs().max())
     print('PixelFFN block trials:', tr.report(), fz.report())
     assert tr.report()['errors'] == 0
+
+
+@pytest.mark.parametrize('B,K,h,w', [(1, 3, 120, 216), (2, 1, 24, 40), (1, 15, 6, 10)])
+def test_segment_tail_kernel_matches_aten(B, K, h, w):
+    import torch.nn.functional as F
+    import cutie_b200.kernels as K_
+    from cutie_b200.utils.tensor_utils import aggregate
+    x = (4 * torch.randn(B, K, h, w, generator=torch.Generator().manual_seed(K))).cuda()
+    x[0, 0, 0, 0], x[0, K - 1, -1, -1] = 40.0, -40.0
+    lg_want = F.interpolate(aggregate(torch.sigmoid(x), dim=1), scale_factor=4, mode='bilinear', align_corners=False)
+    pr_want = F.softmax(lg_want, dim=1)
+    lg, pr = K_.segment_tail(x)
+    assert float((lg - lg_want).abs().max()) <= 1e-4 and float((pr - pr_want).abs().max()) <= 1e-5

@@ -48,6 +48,12 @@ extern "C" void emu_stem_pool(const float* y, const float* bias, float* out, lon
   if (cl) EMU_LAUNCH((cutie::bias_relu_maxpool_kernel<true>), blocks, 256, y, bias, out, total, C, H, W, Ho, Wo);
   else EMU_LAUNCH((cutie::bias_relu_maxpool_kernel<false>), blocks, 256, y, bias, out, total, C, H, W, Ho, Wo);
 }
+extern "C" void emu_segment_tail(const float* x, float* agg, float* logits, float* prob, long long B, int K, int h, int w) {
+  const long long lo = B * h * w;
+  EMU_LAUNCH(cutie::aggregate_logits_kernel, (int)((lo + 255) / 256), 256, x, agg, lo, K, (long long)h * w);
+  const long long hi = lo * 16;
+  EMU_LAUNCH(cutie::upsample4_softmax_kernel, (int)((hi + 255) / 256), 256, agg, logits, prob, hi, K + 1, h, w);
+}
 extern "C" void emu_gated(const float* v, const float* h, float* out, long long P, long long d, long long HW, int vec,
                           int blocks) {
   const long long n = P * d * HW, total = vec ? n / 4 : n;
@@ -79,7 +85,10 @@ def emu(tmp_path_factory):
                  r'__global__ void [^\n]*eca_gate_kernel\(',
                  r'template <bool CL, bool VEC>\n__global__ void [^\n]*scale_add_kernel\(',
                  r'template <bool VEC>\n__global__ void [^\n]*gated_update_kernel\(',
-                 r'template <bool CL>\n__global__ void [^\n]*bias_relu_maxpool_kernel\('):
+                 r'template <bool CL>\n__global__ void [^\n]*bias_relu_maxpool_kernel\(',
+                 r'constexpr int SEG_MAXC = 16;\n\n__global__ void [^\n]*aggregate_logits_kernel\(',
+                 r'__device__ __forceinline__ void src_index4\(',
+                 r'__global__ void [^\n]*upsample4_softmax_kernel\('):
         mm = re.search('(' + head + r'.*?\n}\n)', src, re.S)
         assert mm, head
         more.append(mm.group(1))
@@ -204,3 +213,24 @@ def test_bias_relu_maxpool_index_math(emu, shape, cl):
     emu.emu_stem_pool(P(ybuf.data_ptr()), P(bias.data_ptr()), P(out.data_ptr()), ctypes.c_longlong(N), C, H, W, int(cl))
     got = out.permute(0, 3, 1, 2) if cl else out
     assert torch.equal(got, want)               # max, one add, clamp: bit-identical to maxpool(relu(y + b))
+
+
+@pytest.mark.parametrize('B,K,h,w', [(1, 3, 6, 9), (2, 1, 3, 4), (1, 15, 2, 2), (1, 5, 1, 7)])
+def test_segment_tail_index_math(emu, B, K, h, w):
+    import torch.nn.functional as F
+    from cutie_b200.utils.tensor_utils import aggregate
+    g = torch.Generator().manual_seed(K * 10 + h)
+    x = 4 * torch.randn(B, K, h, w, generator=g)
+    x[0, 0, 0, 0] = 40.0                                   # saturates the clamp at 1 - 1e-7
+    x[0, K - 1, -1, -1] = -40.0                            # and at 1e-7
+    agg_want = aggregate(torch.sigmoid(x), dim=1)
+    lg_want = F.interpolate(agg_want, scale_factor=4, mode='bilinear', align_corners=False)
+    pr_want = F.softmax(lg_want, dim=1)
+    agg = torch.full((B, K + 1, h, w), float('nan'))
+    lg = torch.full((B, K + 1, 4 * h, 4 * w), float('nan'))
+    pr = torch.full_like(lg, float('nan'))
+    P = ctypes.c_void_p
+    emu.emu_segment_tail(P(x.data_ptr()), P(agg.data_ptr()), P(lg.data_ptr()), P(pr.data_ptr()), ctypes.c_longlong(B), K, h, w)
+    assert torch.allclose(agg, agg_want, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(lg, lg_want, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(pr, pr_want, rtol=1e-5, atol=1e-6)
