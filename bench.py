@@ -57,6 +57,26 @@ WORKLOADS = {
 }
 
 
+def usable_cpus() -> int:
+    """Host threads this process can actually run: the affinity mask, capped by the cgroup CPU quota if there is one
+    (os.cpu_count() reports the machine, not the container; oversubscribing a quota-limited container makes the CPU arm
+    slower, which would flatter the GPU arm)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    try:
+        quota, period = open('/sys/fs/cgroup/cpu.max').read().split()[:2]
+        if quota != 'max':
+            n = min(n, max(1, -(-int(quota) // int(period))))
+    except Exception:
+        try:
+            q = int(open('/sys/fs/cgroup/cpu/cpu.cfs_quota_us').read())
+            p_ = int(open('/sys/fs/cgroup/cpu/cpu.cfs_period_us').read())
+            if q > 0:
+                n = min(n, max(1, -(-q // p_)))
+        except Exception:
+            pass
+    return max(1, n)
+
+
 def make_cfg(wl):
     from cutie_b200.config import default_config
     return default_config(mem_every=5, max_mem_frames=wl['mem_frames'], use_long_term=False, top_k=wl['top_k'])
@@ -448,7 +468,7 @@ def main():
     if args.impl == 'reference':
         if rank != 0:
             return
-        cores = os.cpu_count()
+        cores = usable_cpus()
         torch.set_num_threads(cores)
         per = run_cpu_reference(args, wl, max_seconds=max(args.cpu_seconds, 60.0), steps=args.steps,
                                 warmup=min(args.warmup, 1))
@@ -501,11 +521,11 @@ def main():
     optional['glue_kernels'] = not args.no_optimize and not args.no_fuse_glue
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        torch.set_num_threads(os.cpu_count())
-        per = run_cpu_reference(args, wl, max_seconds=40.0, steps=1, warmup=0)
+        torch.set_num_threads(usable_cpus())
+        per = run_cpu_reference(args, wl, max_seconds=40.0, steps=1, warmup=1)
         cpu = {'value': len(per) / sum(per), 'unit': 'frames/s', 'cores': torch.get_num_threads(), 'kind': 'port',
                'sample': f'{len(per)} full frame of the same workload (same weights, same pre-filled bank) '
-                         f'through oracle/cpu_core.py'}
+                         f'through oracle/cpu_core.py, after one untimed warm-up frame'}
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
