@@ -86,7 +86,9 @@ class InferenceCore:
                    not self.flip_aug and self.chunk_size < 1 and not self.save_aux and
                    getattr(self.network, 'object_transformer_enabled', True))
         if graphed:
-            msk_value, sensory, obj_value = self._graphs.encode_mask(image, pix_feat, self.memory.get_sensory(ids), prob)
+            with K_._call('region:encode_mask_graph', 0):          # bench.py: device time of the whole replay
+                msk_value, sensory, obj_value = self._graphs.encode_mask(image, pix_feat, self.memory.get_sensory(ids),
+                                                                         prob)
             sensory = sensory.clone()          # outlives this frame; value / summaries are consumed by add_memory below
         else:
             msk_value, sensory, obj_value, _ = self.network.encode_mask(
@@ -111,11 +113,13 @@ class InferenceCore:
         if self._graph_path_ok(key, ids):
             # eager memory read (affinity + sparse gather), then one graph replay for fusion + object transformer +
             # decoder; results live in graph-static buffers, so everything that outlives this frame is cloned
-            visual = self.memory.read_visual(key, selection, ids)
+            with K_._call('region:memory_read', 0):
+                visual = self.memory.read_visual(key, selection, ids)
             sens_in = self.memory.get_sensory(ids)
             obj_mem = self.memory._get_object_mem_by_ids(ids).unsqueeze(2)
-            sensory, logits, prob = self._graphs.segment(visual, pix_feat, sens_in, self.last_mask, obj_mem,
-                                                         tuple(ms_features), update_sensory)
+            with K_._call('region:segment_graph', 0):
+                sensory, logits, prob = self._graphs.segment(visual, pix_feat, sens_in, self.last_mask, obj_mem,
+                                                             tuple(ms_features), update_sensory)
             logits, prob = logits.clone(), prob.clone()
             if update_sensory:
                 sensory = sensory.clone()
@@ -187,7 +191,8 @@ class InferenceCore:
             if self._graphs is None:
                 from cutie_b200.inference.frame_graphs import FrameGraphs
                 self._graphs = FrameGraphs(self.network)
-            ms_feat, pix_feat, key, shrinkage, selection = self._graphs.encode(image)
+            with K_._call('region:encode_graph', 0):
+                ms_feat, pix_feat, key, shrinkage, selection = self._graphs.encode(image)
         else:
             ms_feat, pix_feat = self.image_feature_store.get_features(self.curr_ti, image)
             key, shrinkage, selection = self.image_feature_store.get_key(self.curr_ti, image)
