@@ -67,7 +67,8 @@ class ChannelAttnResBlock(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         t = getattr(self, 'op_trials', None)
         twins = getattr(self, 'cl_twins', None)
-        if t is None or twins is None or x.dim() != 4 or not x.is_contiguous() or x.shape[1] % 4:
+        if (t is None or twins is None or x.dim() != 4 or not x.is_contiguous() or x.shape[1] % 4
+                or twins[0].weight.device != x.device):
             return self._forward(x, self.conv1, self.conv2)
         # NCHW input (our transformer kernels emit channel-major pixels): cuDNN then re-lays-out input, weight AND output
         # around each 3x3 convolution (6 + 7 + 6 us around a 19 us kernel at 480p).  Alternative, A/B-ed on the device: one

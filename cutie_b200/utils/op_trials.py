@@ -57,8 +57,15 @@ class OpTrials:
         return gpu_time_ms(fn, self.trial_iters)
 
     def _trial(self, op, key, aten: Callable, kernel: Callable, rtol: float) -> bool:
+        from cutie_b200.kernels import KernelError
         ref = aten()
-        out = kernel(True)                           # trial=True: in-place kernels work on a copy
+        try:
+            out = kernel(True)                       # trial=True: in-place kernels work on a copy
+        except KernelError:                          # our library missing / a failed launch is never absorbed
+            raise
+        except Exception as e:                       # noqa: BLE001 -- a PyTorch / cuDNN variant that does not run here
+            self.errors.append(f'{op} {key}: {type(e).__name__}: {e}')
+            return False
         refs = list(ref) if isinstance(ref, (tuple, list)) else [ref]
         outs = list(out) if isinstance(out, (tuple, list)) else [out]
         ok = len(refs) == len(outs)
