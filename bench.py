@@ -227,6 +227,18 @@ def preflight(local: int) -> int:
                 pa, pb = a.step(x), b.step(x)
                 d = float((a.last_logits - b.last_logits).abs().max())
                 assert d < 1e-3 and bool(torch.isfinite(pa).all()), f'optimised stream deviates by {d} at frame {ti}'
+        # encoder look-ahead: same results with and without it (same kernels, another stream schedule)
+        c, d = InferenceCore(on, cfg=cfg, use_cuda_graphs=True), InferenceCore(on, cfg=cfg, use_cuda_graphs=True)
+        frames, mask = synthetic_video(14, 96, 160, 3, seed=5)
+        fd = frames.to(dev)
+        for ti in range(13):
+            kw = dict(objects=[1, 2, 3]) if ti == 0 else {}
+            args_ = (fd[ti], mask.to(dev)) if ti == 0 else (fd[ti],)
+            pc = c.step(*args_, next_image=fd[ti + 1], **kw)
+            pd_ = d.step(*args_, **kw)
+            # a mis-ordered stream would hand the decoder another frame's features (gross error); run-to-run rounding of
+            # library kernels is tolerated
+            assert float((pc - pd_).abs().max()) < 2e-2, f'look-ahead changes the result at frame {ti}'
         torch.cuda.synchronize(dev)
     log(f'[preflight] ok: conv epilogues {on.conv_epilogues.report()}; glue ops {on.op_trials.report()}')
     return 0
@@ -289,8 +301,10 @@ def run_ours(args, wl, rank, world, dev):
     # ---- device-resident arm: inputs already in HBM ----
     with torch.inference_mode():
         t = 1
+        look = (not args.no_lookahead) and (not args.no_graphs)
+        nxt = (lambda i: frames_dev[i + 1]) if look else (lambda i: None)
         for _ in range(args.warmup):
-            proc.step(frames_dev[t]); t += 1
+            proc.step(frames_dev[t], next_image=nxt(t)); t += 1
         barrier()
         stop, samples = threading.Event(), []
         th = threading.Thread(target=nvsmi_sampler, args=(stop, samples, dev.index or 0), daemon=True)
@@ -303,7 +317,7 @@ def run_ours(args, wl, rank, world, dev):
         ev0.record()
         h0 = time.perf_counter()
         for _ in range(args.steps):
-            proc.step(frames_dev[t]); t += 1
+            proc.step(frames_dev[t], next_image=nxt(t)); t += 1
         host_ms_dev = (time.perf_counter() - h0) * 1e3 / args.steps     # host time to ENQUEUE a step (no sync inside)
         ev1.record()
         barrier()
@@ -334,30 +348,37 @@ def run_ours(args, wl, rank, world, dev):
         tt = 1 + args.warmup
         copy_stream = torch.cuda.Stream(dev)
         cur = torch.cuda.current_stream(dev)
-        bufs = [torch.empty_like(frames_dev[0]) for _ in range(2)]
-        ready = [torch.cuda.Event() for _ in range(2)]
-        free = [torch.cuda.Event() for _ in range(2)]
+        NB = 3 if look else 2                # look-ahead hands frame i+1 to step i, so uploads run two frames ahead
+        ahead = NB - 1
+        bufs = [torch.empty_like(frames_dev[0]) for _ in range(NB)]
+        ready = [torch.cuda.Event() for _ in range(NB)]
+        free = [torch.cuda.Event() for _ in range(NB)]
 
-        def upload(i):                       # pinned host frame -> device buffer i%2 on the copy stream
+        def upload(i):                       # pinned host frame -> device buffer i%NB on the copy stream
             with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(free[i % 2])
-                bufs[i % 2].copy_(frames_pin[tt + i], non_blocking=True)
-                ready[i % 2].record(copy_stream)
+                copy_stream.wait_event(free[i % NB])
+                bufs[i % NB].copy_(frames_pin[tt + i], non_blocking=True)
+                ready[i % NB].record(copy_stream)
         for ev in free:
             ev.record(cur)
         e0.record()
-        upload(0)
+        for j in range(min(ahead, args.steps)):
+            upload(j)
         h0 = time.perf_counter()
         e2e_marks = []
         for i in range(args.steps):
-            if i + 1 < args.steps:
-                upload(i + 1)                # next frame's H2D overlaps this frame's compute
-            cur.wait_event(ready[i % 2])
+            if i + ahead < args.steps:
+                upload(i + ahead)            # H2D of a later frame overlaps this frame's compute
+            cur.wait_event(ready[i % NB])
+            ahead_img = None
+            if look and i + 1 < args.steps:  # exactly K uploads and K encoder passes for K steps
+                cur.wait_event(ready[(i + 1) % NB])
+                ahead_img = bufs[(i + 1) % NB]
             if args.phase_timing:
                 marks = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
                 marks[0].record()
-            prob = proc2.step(bufs[i % 2])
-            free[i % 2].record(cur)
+            prob = proc2.step(bufs[i % NB], next_image=ahead_img)
+            free[i % NB].record(cur)
             if args.phase_timing:
                 marks[1].record()
             host_out.copy_(proc2.output_prob_to_mask(prob).to(torch.uint8), non_blocking=True)
@@ -384,7 +405,7 @@ def run_ours(args, wl, rank, world, dev):
     glue = net.op_trials.report() if hasattr(net, 'op_trials') else None
     if glue:
         log(f'[rank {rank}] glue ops: {glue}')
-    return dict(glue=glue, epilogues=epi, host_ms=[host_ms_dev, host_ms_e2e], phases=phases, image_levels=K_.image_level_launches(), ms_total=ms_total, ms_e2e=ms_e2e, kernel_ms=kernel_ms, launches=launches, n_tokens=n_tokens,
+    return dict(lookahead=look, glue=glue, epilogues=epi, host_ms=[host_ms_dev, host_ms_e2e], phases=phases, image_levels=K_.image_level_launches(), ms_total=ms_total, ms_e2e=ms_e2e, kernel_ms=kernel_ms, launches=launches, n_tokens=n_tokens,
                 clocks=summarize_clocks(samples), h2d=frames_pin[0].numel() * 4, d2h=host_out.numel())
 
 
@@ -437,6 +458,8 @@ def main():
     ap.add_argument('--phase-timing', action='store_true', help='per-launch device times inside cutie_affinity_topk')
     ap.add_argument('--no-key-image', action='store_true', help='convert memory keys inside the filter (no operand image)')
     ap.add_argument('--no-graphs', action='store_true', help='eager launches only (no CUDA-graph frame regions)')
+    ap.add_argument('--no-lookahead', action='store_true',
+                    help='do not run the next frame\'s image encoder on a side stream (step(..., next_image=...))')
     ap.add_argument('--no-fuse-glue', action='store_true',
                     help='keep area down-sampling / CAResBlock tail / sensory gates as ATen launches')
     ap.add_argument('--no-fuse-epilogues', action='store_true',
@@ -451,6 +474,10 @@ def main():
         sys.exit(preflight(int(os.environ.get('LOCAL_RANK', 0))))
     if args.warmup < 3:
         args.warmup = 3
+    if args.impl == 'ours' and not args.no_graphs:
+        # every CUDA-graph variant must exist before the timed region: two capture slots (the encoder look-ahead
+        # alternates them) x {encoder, segment, mask encoder}; memory frames come every 5th step
+        args.warmup = max(args.warmup, 11)
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
@@ -491,13 +518,14 @@ def main():
     # The optional launch-saving forms (cuDNN fused epilogues, cutie_bias_act, glue kernels) are checked against
     # PyTorch's own launches in a child process first; a failed check only switches THEM off for this run.
     optional = {'checked': False, 'note': args.fallback_reason or 'not checked'}
-    wants_optional = not args.no_optimize and not (args.no_fuse_epilogues and args.no_fuse_glue)
+    wants_optional = (not args.no_optimize and not (args.no_fuse_epilogues and args.no_fuse_glue)) or \
+                     not (args.no_lookahead or args.no_graphs)
     if wants_optional and not args.skip_preflight and not args.fallback_reason:
         ok, note = run_preflight(local)
         optional = {'checked': True, 'note': note}
         if not ok:
             log(f'[rank {rank}] optional fused forms disabled: {note}')
-            args.no_fuse_epilogues = args.no_fuse_glue = True
+            args.no_fuse_epilogues = args.no_fuse_glue = args.no_lookahead = True
     dev = torch.device('cuda', local)
     torch.cuda.set_device(dev)
     if world > 1:
@@ -507,14 +535,14 @@ def main():
     except Exception as e:                               # noqa: BLE001
         # single process only: start over in a fresh process (fresh CUDA context) with PyTorch's launches for the
         # optional stages; a second failure, or any failure under torchrun, is fatal
-        if world == 1 and wants_optional and not args.fallback_reason and not (args.no_fuse_epilogues and args.no_fuse_glue):
+        if world == 1 and wants_optional and not args.fallback_reason:
             import traceback
             traceback.print_exc()
             reason = f'{type(e).__name__}: {e}'[:200].replace('\n', ' ')
             log(f'[bench] optimised run failed ({reason}); re-running with --no-fuse-epilogues --no-fuse-glue')
             os.environ['CUTIE_BENCH_STDOUT_FD'] = str(_REAL_STDOUT)
             argv = [sys.executable, os.path.abspath(__file__)] + sys.argv[1:] + \
-                   ['--no-fuse-epilogues', '--no-fuse-glue', '--fallback-reason', reason]
+                   ['--no-fuse-epilogues', '--no-fuse-glue', '--no-lookahead', '--fallback-reason', reason]
             os.execv(sys.executable, argv)
         raise
     optional['conv_epilogues'] = not args.no_optimize and not args.no_fuse_epilogues
@@ -592,6 +620,7 @@ def main():
     line['config']['conv_epilogues'] = res['epilogues']     # which conv+bias(+add)+ReLU calls won their on-device trial
     line['config']['glue_ops'] = res['glue']                 # which ATen chains were replaced by cutie_b200 kernels
     line['config']['optional_forms'] = optional               # pre-flight verdict for the two entries above
+    line['config']['encoder_lookahead'] = res['lookahead']    # next frame's encoder graph on a side stream (step(next_image=))
     emit(line)
 
 

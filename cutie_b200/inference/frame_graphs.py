@@ -51,8 +51,10 @@ class FrameGraphs:
         self._msk: Dict[Tuple, _Captured] = {}
 
     # ---- G1 ------------------------------------------------------------------------------------
-    def encode(self, image: torch.Tensor):
-        key = (tuple(image.shape), image.device)
+    def encode(self, image: torch.Tensor, slot: int = 0):
+        """`slot` selects one of several independent captures (own static input and outputs): InferenceCore alternates
+        two of them so that the next frame's encoder can run on a side stream while this frame's outputs are in use."""
+        key = (tuple(image.shape), image.device, int(slot))
         cap = self._enc.get(key)
         if cap is None:
             static_img = image.clone()

@@ -50,6 +50,10 @@ class InferenceCore:
         # replay CUDA graphs for the arena-independent parts of a frame (frame_graphs.py); off = reference-like eager
         self.use_cuda_graphs = use_cuda_graphs
         self._graphs = None
+        # encoder look-ahead (step(..., next_image=...)): the next frame's image-encoder graph on a side stream
+        self._lookahead = None
+        self._side_stream = None
+        self._enc_slot = 0           # encoder capture slot holding the CURRENT frame's features (look-ahead writes the other)
 
     # -- memory control ------------------------------------------------------------------------
     def _reset_clock(self):
@@ -152,10 +156,17 @@ class InferenceCore:
 
     def step(self, image: torch.Tensor, mask: Optional[torch.Tensor] = None,
              objects: Optional[List[int]] = None, *, idx_mask: bool = True, end: bool = False,
-             delete_buffer: bool = True, force_permanent: bool = False) -> torch.Tensor:
+             delete_buffer: bool = True, force_permanent: bool = False,
+             next_image: Optional[torch.Tensor] = None) -> torch.Tensor:
         """One frame.  image [3,H,W] in [0,1]; mask [H,W] ids (idx_mask) or [K,H,W] soft masks or None;
         objects: ids present in `mask`.  With a mask the listed objects are memorised (and any others
-        are propagated first); without, the frame is segmented from memory.  Returns [1+K,H,W]."""
+        are propagated first); without, the frame is segmented from memory.  Returns [1+K,H,W].
+
+        next_image (extension; CUDA-graph path only): the frame the NEXT call will be given.  Its image encoder -- which
+        depends on nothing but the image -- is enqueued on a side stream now and overlaps this frame's memory read,
+        object transformer and decoder; the next call picks the result up if it is handed the same tensor.  Results
+        are identical with or without it."""
+        src_id = (image.data_ptr(), tuple(image.shape))
         if objects is None and mask is not None:
             assert not idx_mask
             objects = list(range(1, mask.shape[0] + 1))
@@ -191,8 +202,18 @@ class InferenceCore:
             if self._graphs is None:
                 from cutie_b200.inference.frame_graphs import FrameGraphs
                 self._graphs = FrameGraphs(self.network)
-            with K_._call('region:encode_graph', 0):
-                ms_feat, pix_feat, key, shrinkage, selection = self._graphs.encode(image)
+            la, self._lookahead = self._lookahead, None
+            if la is not None:
+                torch.cuda.current_stream().wait_event(la['done'])       # also drains a stale look-ahead before slot reuse
+            if la is not None and la['ti'] == self.curr_ti and la['src'] == src_id and la['shape'] == tuple(image.shape):
+                ms_feat, pix_feat, key, shrinkage, selection = la['out']
+                self._enc_slot = la['slot']
+            else:
+                # same slot as the previous frame: its readers were enqueued on this stream before this replay
+                with K_._call('region:encode_graph', 0):
+                    ms_feat, pix_feat, key, shrinkage, selection = self._graphs.encode(image, self._enc_slot)
+            if next_image is not None and next_image.is_cuda and not resize_needed:
+                self._encode_ahead(next_image)
         else:
             ms_feat, pix_feat = self.image_feature_store.get_features(self.curr_ti, image)
             key, shrinkage, selection = self.image_feature_store.get_key(self.curr_ti, image)
@@ -243,6 +264,32 @@ class InferenceCore:
         if resize_needed:
             out = F.interpolate(out[None], size=(h, w), mode='bilinear', align_corners=False)[0]
         return out
+
+    def _encode_ahead(self, next_image: torch.Tensor) -> None:
+        """Enqueue G1 (image encoder + key projection) of the next frame on the side stream.
+
+        Ordering: the side stream first waits for everything enqueued on the current stream so far -- i.e. the end of the
+        PREVIOUS step, whose consumers were the last readers of the capture slot written here (the slot the current frame
+        does NOT use), and whatever made `next_image` valid (an upload the caller synchronised this stream with) -- and the next step
+        waits on `done` before touching the outputs.  This frame's own work is enqueued on the current stream after this
+        call and therefore runs concurrently with it."""
+        if self.max_internal_size > 0 and min(next_image.shape[-2:]) > self.max_internal_size:
+            return                                    # the internal down-scaling path recomputes on the main stream
+        main = torch.cuda.current_stream()
+        if self._side_stream is None or self._side_stream.device != next_image.device:
+            self._side_stream = torch.cuda.Stream(device=next_image.device)
+        side = self._side_stream
+        side.wait_stream(main)
+        next_image.record_stream(side)
+        with torch.cuda.stream(side):
+            img, _ = pad_divide_by(next_image, 16)
+            img = img.unsqueeze(0)
+            with K_._call('region:encode_graph_ahead', 0):
+                out = self._graphs.encode(img, 1 - self._enc_slot)
+            done = torch.cuda.Event()
+            done.record(side)
+        self._lookahead = dict(ti=self.curr_ti + 1, slot=1 - self._enc_slot, src=(next_image.data_ptr(), tuple(next_image.shape)),
+                               shape=tuple(img.shape), out=out, done=done)
 
     def delete_objects(self, objects: List[int]) -> None:
         self.object_manager.delete_objects(objects)

@@ -245,3 +245,41 @@ def test_segment_tail_kernel_matches_aten(B, K, h, w):
     pr_want = F.softmax(lg_want, dim=1)
     lg, pr = K_.segment_tail(x)
     assert float((lg - lg_want).abs().max()) <= 1e-4 and float((pr - pr_want).abs().max()) <= 1e-5
+
+
+@pytest.mark.parametrize('optimised', [False, True])
+def test_encoder_lookahead_gives_the_same_stream(optimised):
+    """step(image, next_image=...) runs the next frame's encoder graph on a side stream (two alternating capture slots);
+    masks, logits and memory sizes must equal the plain graph path frame by frame -- a mis-ordered stream would hand the
+    decoder another frame's features."""
+    from cutie_b200.config import default_config
+    from cutie_b200.inference.inference_core import InferenceCore
+    from cutie_b200.model.cutie import CUTIE
+    from oracle.synth import synthetic_state_dict, synthetic_video
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg = default_config(mem_every=3, max_mem_frames=3)
+    net = CUTIE(cfg).eval()
+    net.load_state_dict(synthetic_state_dict(net.state_dict(), 0))
+    net = net.cuda()
+    if optimised:
+        net.optimize_for_inference()
+    a, b = InferenceCore(net, cfg=cfg, use_cuda_graphs=True), InferenceCore(net, cfg=cfg, use_cuda_graphs=True)
+    T = 16
+    frames, mask = synthetic_video(T + 1, 240, 432, 3, seed=9)
+    fd = frames.cuda()
+    worst = 0.0
+    with torch.inference_mode():
+        for ti in range(T):
+            kw = dict(objects=[1, 2, 3]) if ti == 0 else {}
+            args = (fd[ti], mask.cuda()) if ti == 0 else (fd[ti],)
+            # every third call hands over a DIFFERENT tensor than announced: the look-ahead must be discarded, not used
+            announced = fd[ti + 1] if ti % 5 != 4 else fd[ti + 1].clone()
+            pa = a.step(*args, next_image=announced, **kw)
+            pb = b.step(*args, **kw)
+            worst = max(worst, float((pa - pb).abs().max()))
+            assert worst < 2e-2, (ti, worst)
+            assert a.memory.work_mem.size(0) == b.memory.work_mem.size(0)
+            assert (a.output_prob_to_mask(pa) != b.output_prob_to_mask(pb)).float().mean() < 1e-3
+    print('look-ahead vs plain: max |prob diff| =', worst)
+    assert len(a._graphs._enc) == 2 and len(b._graphs._enc) == 1      # the second capture slot exists only with look-ahead
