@@ -22,6 +22,74 @@ from cutie_b200.utils.tensor_utils import aggregate, pad_divide_by, unpad
 log = logging.getLogger()
 
 
+class _CudaStreamOps:
+    """The torch.cuda calls EncoderLookahead needs (tests substitute a recording fake)."""
+
+    def __init__(self):
+        self.side = None
+
+    def _side(self, device):
+        if self.side is None or self.side.device != device:
+            self.side = torch.cuda.Stream(device=device)
+        return self.side
+
+    def side_wait_main(self, device):
+        self._side(device).wait_stream(torch.cuda.current_stream())
+
+    def keep_alive_on_side(self, tensor):
+        tensor.record_stream(self._side(tensor.device))
+
+    def on_side(self, device):
+        return torch.cuda.stream(self._side(device))
+
+    def record_on_side(self, device):
+        ev = torch.cuda.Event()
+        ev.record(self._side(device))
+        return ev
+
+    def main_wait_event(self, ev):
+        torch.cuda.current_stream().wait_event(ev)
+
+
+class EncoderLookahead:
+    """Which encoder capture slot holds the current frame's features, and the pending look-ahead (if any).
+
+    encode(image, slot) replays the image-encoder graph of `slot` on the CURRENT stream and returns its (graph-static)
+    outputs.  Protocol (checked as a happens-before model in tests/test_lookahead_protocol_cpu.py):
+      * a look-ahead always writes the slot the current frame does NOT use;
+      * before it, the side stream waits for everything enqueued on the main stream so far -- the end of the previous
+        step, whose consumers were the last readers of that slot, and whatever made the announced image valid;
+      * the main stream waits for the look-ahead's event before it touches either the outputs (hit) or re-encodes
+        (miss: wrong frame / tensor announced -- the result is discarded, never used)."""
+
+    def __init__(self, encode, ops=None):
+        self.encode = encode
+        self.ops = ops or _CudaStreamOps()
+        self.slot = 0
+        self.pending = None
+
+    def current(self, ti: int, image: torch.Tensor, src_id):
+        la, self.pending = self.pending, None
+        if la is not None:
+            self.ops.main_wait_event(la['done'])
+            if la['ti'] == ti and la['src'] == src_id and la['shape'] == tuple(image.shape):
+                self.slot = la['slot']
+                return la['out'], True
+        return self.encode(image, self.slot), False
+
+    def ahead(self, ti: int, next_image: torch.Tensor, prepare):
+        dev = next_image.device
+        self.ops.side_wait_main(dev)
+        self.ops.keep_alive_on_side(next_image)
+        slot = 1 - self.slot
+        with self.ops.on_side(dev):
+            img = prepare(next_image)
+            out = self.encode(img, slot)
+            done = self.ops.record_on_side(dev)
+        self.pending = dict(ti=ti + 1, slot=slot, src=(next_image.data_ptr(), tuple(next_image.shape)),
+                            shape=tuple(img.shape), out=out, done=done)
+
+
 class InferenceCore:
     def __init__(self, network, cfg, *, image_feature_store: ImageFeatureStore = None,
                  use_cuda_graphs: bool = False, memory_shard_group=None):
@@ -51,9 +119,7 @@ class InferenceCore:
         self.use_cuda_graphs = use_cuda_graphs
         self._graphs = None
         # encoder look-ahead (step(..., next_image=...)): the next frame's image-encoder graph on a side stream
-        self._lookahead = None
-        self._side_stream = None
-        self._enc_slot = 0           # encoder capture slot holding the CURRENT frame's features (look-ahead writes the other)
+        self._lookahead = None       # EncoderLookahead, created with the graphs
 
     # -- memory control ------------------------------------------------------------------------
     def _reset_clock(self):
@@ -202,16 +268,9 @@ class InferenceCore:
             if self._graphs is None:
                 from cutie_b200.inference.frame_graphs import FrameGraphs
                 self._graphs = FrameGraphs(self.network)
-            la, self._lookahead = self._lookahead, None
-            if la is not None:
-                torch.cuda.current_stream().wait_event(la['done'])       # also drains a stale look-ahead before slot reuse
-            if la is not None and la['ti'] == self.curr_ti and la['src'] == src_id and la['shape'] == tuple(image.shape):
-                ms_feat, pix_feat, key, shrinkage, selection = la['out']
-                self._enc_slot = la['slot']
-            else:
-                # same slot as the previous frame: its readers were enqueued on this stream before this replay
-                with K_._call('region:encode_graph', 0):
-                    ms_feat, pix_feat, key, shrinkage, selection = self._graphs.encode(image, self._enc_slot)
+            if self._lookahead is None:
+                self._lookahead = EncoderLookahead(self._encode_graph)
+            (ms_feat, pix_feat, key, shrinkage, selection), _hit = self._lookahead.current(self.curr_ti, image, src_id)
             if next_image is not None and next_image.is_cuda and not resize_needed:
                 self._encode_ahead(next_image)
         else:
@@ -265,31 +324,16 @@ class InferenceCore:
             out = F.interpolate(out[None], size=(h, w), mode='bilinear', align_corners=False)[0]
         return out
 
-    def _encode_ahead(self, next_image: torch.Tensor) -> None:
-        """Enqueue G1 (image encoder + key projection) of the next frame on the side stream.
+    def _encode_graph(self, image: torch.Tensor, slot: int):
+        with K_._call('region:encode_graph', 0):
+            return self._graphs.encode(image, slot)
 
-        Ordering: the side stream first waits for everything enqueued on the current stream so far -- i.e. the end of the
-        PREVIOUS step, whose consumers were the last readers of the capture slot written here (the slot the current frame
-        does NOT use), and whatever made `next_image` valid (an upload the caller synchronised this stream with) -- and the next step
-        waits on `done` before touching the outputs.  This frame's own work is enqueued on the current stream after this
-        call and therefore runs concurrently with it."""
+    def _encode_ahead(self, next_image: torch.Tensor) -> None:
+        """Enqueue G1 (image encoder + key projection) of the next frame on the side stream (EncoderLookahead.ahead);
+        this frame's own work is enqueued on the current stream after this call and runs concurrently with it."""
         if self.max_internal_size > 0 and min(next_image.shape[-2:]) > self.max_internal_size:
             return                                    # the internal down-scaling path recomputes on the main stream
-        main = torch.cuda.current_stream()
-        if self._side_stream is None or self._side_stream.device != next_image.device:
-            self._side_stream = torch.cuda.Stream(device=next_image.device)
-        side = self._side_stream
-        side.wait_stream(main)
-        next_image.record_stream(side)
-        with torch.cuda.stream(side):
-            img, _ = pad_divide_by(next_image, 16)
-            img = img.unsqueeze(0)
-            with K_._call('region:encode_graph_ahead', 0):
-                out = self._graphs.encode(img, 1 - self._enc_slot)
-            done = torch.cuda.Event()
-            done.record(side)
-        self._lookahead = dict(ti=self.curr_ti + 1, slot=1 - self._enc_slot, src=(next_image.data_ptr(), tuple(next_image.shape)),
-                               shape=tuple(img.shape), out=out, done=done)
+        self._lookahead.ahead(self.curr_ti, next_image, lambda t: pad_divide_by(t, 16)[0].unsqueeze(0))
 
     def delete_objects(self, objects: List[int]) -> None:
         self.object_manager.delete_objects(objects)
