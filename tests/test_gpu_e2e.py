@@ -204,7 +204,7 @@ def test_optimize_for_inference_keeps_parity():
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     cfg = default_config(mem_every=2, max_mem_frames=3)
-    plain, fast = _net(cfg), _net(cfg).optimize_for_inference(fuse_epilogues=False)
+    plain, fast = _net(cfg), _net(cfg).optimize_for_inference(fuse_epilogues=False, fuse_glue=False)
     a, b = InferenceCore(plain, cfg=cfg), InferenceCore(fast, cfg=cfg, use_cuda_graphs=True)
     frames, mask = synthetic_video(5, 96, 160, 3, seed=3)
     with torch.inference_mode():
