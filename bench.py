@@ -278,7 +278,8 @@ def run_ours(args, wl, rank, world, dev):
     if not args.no_optimize:
         # BN folding + channels-last trunks + conv/bias/ReLU epilogues in one cuDNN call (still PyTorch/cuDNN calls)
         net.optimize_for_inference(fuse_epilogues=not args.no_fuse_epilogues, fuse_glue=not args.no_fuse_glue)
-    n_frames = args.warmup + args.steps + 2
+    AB = 10                                    # steps per arm of the look-ahead A/B (untimed, after the warm-up)
+    n_frames = args.warmup + 2 * AB + args.steps + 2
     frames, mask = synthetic_video(n_frames, wl['H'], wl['W'], wl['K'], seed=rank)
     objs = list(range(1, wl['K'] + 1))
     proc = InferenceCore(net, cfg=cfg, use_cuda_graphs=not args.no_graphs)
@@ -305,6 +306,27 @@ def run_ours(args, wl, rank, world, dev):
         nxt = (lambda i: frames_dev[i + 1]) if look else (lambda i: None)
         for _ in range(args.warmup):
             proc.step(frames_dev[t], next_image=nxt(t)); t += 1
+        # look-ahead A/B on this GPU (every graph variant exists by now): keep it only if the step gets shorter
+        ab = None
+        if look:
+            ab = {}
+            for mode in (True, False):
+                torch.cuda.synchronize(dev)
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                for _ in range(AB):
+                    proc.step(frames_dev[t], next_image=frames_dev[t + 1] if mode else None); t += 1
+                a1.record()
+                torch.cuda.synchronize(dev)
+                ab['with' if mode else 'without'] = a0.elapsed_time(a1) / AB
+            look = ab['with'] <= ab['without']
+            ab['kept'] = look
+            log(f'[rank {rank}] encoder look-ahead A/B (ms/step over {AB} steps each): {ab}')
+            nxt = (lambda i: frames_dev[i + 1]) if look else (lambda i: None)
+        else:
+            t += 2 * AB                           # same frames in the timed region either way
+        untimed = t - 1                           # index offset of the timed frames
+        untimed_steps = args.warmup + (2 * AB if ab else 0)
         barrier()
         stop, samples = threading.Event(), []
         th = threading.Thread(target=nvsmi_sampler, args=(stop, samples, dev.index or 0), daemon=True)
@@ -345,7 +367,7 @@ def run_ours(args, wl, rank, world, dev):
     with torch.inference_mode():
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        tt = 1 + args.warmup
+        tt = 1 + untimed
         copy_stream = torch.cuda.Stream(dev)
         cur = torch.cuda.current_stream(dev)
         NB = 3 if look else 2                # look-ahead hands frame i+1 to step i, so uploads run two frames ahead
@@ -401,7 +423,7 @@ def run_ours(args, wl, rank, world, dev):
             torch.cuda.synchronize(dev)
             K_.PROFILE = []
             for j in range(min(args.steps, 10)):
-                proc.step(frames_dev[1 + args.warmup + (j % args.steps)])
+                proc.step(frames_dev[1 + untimed + (j % args.steps)])
             torch.cuda.synchronize(dev)
             prof2, K_.PROFILE = K_.PROFILE, None
         for name, a, b in prof2:
@@ -417,7 +439,7 @@ def run_ours(args, wl, rank, world, dev):
     glue = net.op_trials.report() if hasattr(net, 'op_trials') else None
     if glue:
         log(f'[rank {rank}] glue ops: {glue}')
-    return dict(solo_ms=solo_ms, lookahead=look, glue=glue, epilogues=epi, host_ms=[host_ms_dev, host_ms_e2e], phases=phases, image_levels=K_.image_level_launches(), ms_total=ms_total, ms_e2e=ms_e2e, kernel_ms=kernel_ms, launches=launches, n_tokens=n_tokens,
+    return dict(untimed=untimed_steps, lookahead_ab=ab, solo_ms=solo_ms, lookahead=look, glue=glue, epilogues=epi, host_ms=[host_ms_dev, host_ms_e2e], phases=phases, image_levels=K_.image_level_launches(), ms_total=ms_total, ms_e2e=ms_e2e, kernel_ms=kernel_ms, launches=launches, n_tokens=n_tokens,
                 clocks=summarize_clocks(samples), h2d=frames_pin[0].numel() * 4, d2h=host_out.numel())
 
 
@@ -641,6 +663,8 @@ def main():
     line['config']['glue_ops'] = res['glue']                 # which ATen chains were replaced by cutie_b200 kernels
     line['config']['optional_forms'] = optional               # pre-flight verdict for the two entries above
     line['config']['encoder_lookahead'] = res['lookahead']    # next frame's encoder graph on a side stream (step(next_image=))
+    line['config']['encoder_lookahead_ab_ms'] = res['lookahead_ab']
+    line['warmup'] = res['untimed']                            # every untimed step before the timed region (warm-up + A/B)
     emit(line)
 
 
