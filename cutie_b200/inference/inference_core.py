@@ -22,6 +22,12 @@ from cutie_b200.utils.tensor_utils import aggregate, pad_divide_by, unpad
 log = logging.getLogger()
 
 
+def _graphable(t: torch.Tensor) -> bool:
+    """CUDA graphs (and the encoder look-ahead) need CUDA tensors.  A function so that the CPU suite can drive the graph
+    path with stand-in graphs (tests/test_graph_path_cpu.py); the product never changes it."""
+    return t.is_cuda
+
+
 class _CudaStreamOps:
     """The torch.cuda calls EncoderLookahead needs (tests substitute a recording fake)."""
 
@@ -152,7 +158,7 @@ class InferenceCore:
             return
         ids = self.object_manager.all_obj_ids
         self.memory.initialize_sensory_if_needed(key, ids)
-        graphed = (self.use_cuda_graphs and self._graphs is not None and image.is_cuda and is_deep_update and
+        graphed = (self.use_cuda_graphs and self._graphs is not None and _graphable(image) and is_deep_update and
                    not self.flip_aug and self.chunk_size < 1 and not self.save_aux and
                    getattr(self.network, 'object_transformer_enabled', True))
         if graphed:
@@ -208,7 +214,7 @@ class InferenceCore:
         return prob
 
     def _graph_path_ok(self, key: torch.Tensor, ids) -> bool:
-        if not (self.use_cuda_graphs and key.is_cuda):
+        if not (self.use_cuda_graphs and _graphable(key)):
             return False
         m = self.memory
         if self.flip_aug or self.chunk_size >= 1 or self.save_aux or len(m.work_mem.buckets) != 1:
@@ -264,14 +270,14 @@ class InferenceCore:
         need_segment = mask is None or (self.object_manager.num_obj > 0 and not self.object_manager.has_all(objects))
         update_sensory = (since_mem in self.stagger_ti) and not end
 
-        if self.use_cuda_graphs and image.is_cuda and not self.flip_aug:
+        if self.use_cuda_graphs and _graphable(image) and not self.flip_aug:
             if self._graphs is None:
                 from cutie_b200.inference.frame_graphs import FrameGraphs
                 self._graphs = FrameGraphs(self.network)
             if self._lookahead is None:
                 self._lookahead = EncoderLookahead(self._encode_graph)
             (ms_feat, pix_feat, key, shrinkage, selection), _hit = self._lookahead.current(self.curr_ti, image, src_id)
-            if next_image is not None and next_image.is_cuda and not resize_needed:
+            if next_image is not None and _graphable(next_image) and not resize_needed:
                 self._encode_ahead(next_image)
         else:
             ms_feat, pix_feat = self.image_feature_store.get_features(self.curr_ti, image)
