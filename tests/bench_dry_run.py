@@ -78,6 +78,14 @@ def _timed(name, fn, launches):
 K_.affinity_topk = _timed('affinity_topk', K_.affinity_topk, 2)
 K_.readout_gather = _timed('readout_gather', K_.readout_gather, 1)
 
+# the CUDA-graph frame path and the encoder look-ahead with stand-in graphs / streams (tests/test_graph_path_cpu.py)
+import cutie_b200.inference.frame_graphs as _fg  # noqa: E402
+import cutie_b200.inference.inference_core as _ic  # noqa: E402
+from tests.test_graph_path_cpu import _FakeCaptured, _NoStreams  # noqa: E402
+_fg._Captured = _FakeCaptured
+_ic._graphable = lambda t: True
+_ic._CudaStreamOps = _NoStreams
+
 sys.argv = ['bench.py'] + sys.argv[1:]
 import bench  # noqa: E402  (points fd 1 at stderr; the JSON goes to the real stdout)
 
