@@ -365,15 +365,12 @@ def test_whole_stream_with_every_optional_form_active(cpu_kernels):
 
 
 def test_pick_times_every_candidate_once_and_sticks():
-    t = _FakeDeviceTrials(ms=(5.0, 1.0, 3.0, 4.0))      # scripted clock cycles through these per timed call
-    # the fake clock alternates by call count: candidate order [a, b, c] -> 5, 1, 3 => b
-    class Clock:
-        n = 0
+    t = _FakeDeviceTrials()
     ran = []
 
     def run(c):
         ran.append(c)
-    t._time = lambda fn: (fn(), (5.0, 1.0, 3.0)[len(ran) - 1])[1]
+    t._time = lambda fn: (fn(), (5.0, 1.0, 3.0)[len(ran) - 1])[1]      # scripted clock: a -> 5 ms, b -> 1 ms, c -> 3 ms
     probe = torch.zeros(1)
     with torch.inference_mode():
         assert t.pick('op', (1,), ['a', 'b', 'c'], run, probe) == 'b'
