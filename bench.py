@@ -8,7 +8,7 @@ Workload (config.workload = "cfg2", BASELINE.json configs[1]): synthetic 480p (8
 padded, 30x54 = 1620 tokens/frame) video, 3 objects, 256-frame working memory (max_mem_frames=256,
 use_long_term=False, mem_every=5, top_k=30): a steady-state bank of 414 720 tokens (1.38 GB), pre-filled
 with seeded N(0,1) keys/values and 1+N(0,1)^2 shrinkage; random-init weights of
-the cutie-base architecture (oracle/synth.py).  A *step* is one InferenceCore.step on one frame; every
+the cutie-base architecture (cutie_b200/utils/synth.py).  A *step* is one InferenceCore.step on one frame; every
 5th step is a memory frame (mask encoder + append + FIFO eviction).  N>1: one independent video stream per
 GPU (weak scaling, no data-path collective -- SURVEY.md section 8(e).1).
 
@@ -84,7 +84,7 @@ def make_cfg(wl):
 
 def make_net(cfg):
     from cutie_b200.model.cutie import CUTIE
-    from oracle.synth import synthetic_state_dict      # synthetic weights only (no oracle math)
+    from cutie_b200.utils.synth import synthetic_state_dict      # synthetic weights (data generation, no oracle code)
     net = CUTIE(cfg).eval()
     net.load_state_dict(synthetic_state_dict(net.state_dict(), 0))
     return net
@@ -180,7 +180,7 @@ def preflight(local: int) -> int:
     from cutie_b200.config import default_config
     from cutie_b200.inference.inference_core import InferenceCore
     from cutie_b200.model.blocks import gated_update
-    from oracle.synth import synthetic_video
+    from cutie_b200.utils.synth import synthetic_video
     dev = torch.device('cuda', local)
     torch.cuda.set_device(dev)
     torch.backends.cudnn.allow_tf32 = False
@@ -267,7 +267,7 @@ def run_preflight(local: int, timeout_s: float = 420.0):
 def run_ours(args, wl, rank, world, dev):
     import cutie_b200.kernels as K_
     from cutie_b200.inference.inference_core import InferenceCore
-    from oracle.synth import synthetic_video
+    from cutie_b200.utils.synth import synthetic_video
     K_.lib()                                             # fail loudly if the CUDA library is missing
     if args.no_key_image:
         import cutie_b200.inference.memory_bank as MB
