@@ -9,7 +9,8 @@ CUDA path on the GPU box at sizes beyond the committed fixtures, (b) as the time
   cutie/inference/kv_memory_store.py:55-149   (add), :151-162, :164-242 (usage / sieve / obsolete removal)
 with the same data layout the reference uses (channel-major tensors grown by torch.cat, dense
 [N,HW] affinity, dense readout GEMM).  The convolutional stages are the product's PyTorch modules run
-on CPU (they are verified bit-identical to the reference's, tests/test_model_parity.py); the memory
+on CPU (pinned to the reference's by the free-running fixtures of tests/test_oracle_golden.py: full-frame
+logits of the unmodified reference within 2e-4); the memory
 math and the object transformer are oracle/memory_math.py and oracle/transformer.py.
 It is pinned by the committed reference fixtures (tests/test_oracle_golden.py).
 """
