@@ -93,7 +93,12 @@ def load_reference():
         if name == 'cutie' or name.startswith('cutie.'):
             raise RuntimeError('a different `cutie` package is already imported; load the reference in a '
                                'fresh process (tests run it through a subprocess)')
-    sys.path.insert(0, REF_ROOT)
+    # this repo ships a `cutie/` drop-in shim (a regular package, which would shadow -- and, composed with the reference,
+    # override -- the reference's namespace package): keep every path entry that holds it out of sight while the
+    # reference's modules are imported; they stay cached in sys.modules afterwards
+    saved_path = list(sys.path)
+    sys.path[:] = [REF_ROOT] + [q for q in sys.path
+                                if not os.path.isfile(os.path.join(q or os.getcwd(), 'cutie', '__init__.py'))]
     try:
         import cutie.model.utils.resnet as R
         r18, r50 = R.resnet18, R.resnet50
@@ -110,7 +115,7 @@ def load_reference():
         import cutie.model.transformer.object_summarizer as object_summarizer
         import cutie.utils.tensor_utils as tensor_utils
     finally:
-        sys.path.remove(REF_ROOT)
+        sys.path[:] = saved_path
     ns = types.SimpleNamespace(memory_utils=memory_utils, kv_memory_store=kv_memory_store,
                                memory_manager=memory_manager, inference_core=inference_core,
                                cutie_model=cutie_model, object_transformer=object_transformer,
