@@ -12,7 +12,7 @@ from tests.conftest import ROOT
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, n_total, ret):
+def _worker(rank, world, port, n_total, Q, K, ret):
     sys.path.insert(0, ROOT)
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
@@ -22,7 +22,7 @@ def _worker(rank, world, port, n_total, ret):
         import cutie_b200.kernels as K_
         from cutie_b200.inference.sharded import shard_bounds, sharded_read
         g = torch.Generator().manual_seed(0)
-        B, Q, K, top_k = 1, 1620, 3, 30
+        B, top_k = 1, 30
         key = torch.randn(B, n_total, 64, generator=g).cuda()
         shr = (1 + torch.randn(B, n_total, generator=g) ** 2).cuda()
         vals = [torch.randn(B, n_total, 256, generator=g).cuda() for _ in range(K)]
@@ -44,12 +44,13 @@ def _worker(rank, world, port, n_total, ret):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs >= 2 GPUs')
-@pytest.mark.parametrize('n_total', [5000, 50000])
-def test_sharded_read_nccl(n_total):
+@pytest.mark.parametrize('n_total,Q,K', [(5000, 1620, 3), (50000, 1620, 3),
+                                         (50000, 8160, 10)])      # cfg 5: 1080p queries, 10 objects, 50k keys
+def test_sharded_read_nccl(n_total, Q, K):
     world = min(torch.cuda.device_count(), 8)
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, 29641 + n_total % 97, n_total, ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, 29641 + (n_total + Q) % 97, n_total, Q, K, ret), nprocs=world, join=True)
     assert all(ret.get(r) for r in range(world)), dict(ret)
 
 
