@@ -70,6 +70,7 @@ def test_oracle_matches_the_reference_on_the_bike_example():
 
 
 @pytest.mark.gpu
+@pytest.mark.timeout(900, method='thread')
 @pytest.mark.parametrize('graphs', [False, True])
 def test_cuda_path_matches_the_reference_on_the_bike_example(graphs):
     from cutie_b200.inference.inference_core import InferenceCore

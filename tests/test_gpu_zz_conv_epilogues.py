@@ -6,7 +6,8 @@ cutie_bias_act itself is bit-identical to the ATen ops it replaces.  (The file n
 import pytest
 import torch
 
-pytestmark = pytest.mark.gpu
+# first run of these cases is at round end: never let one of them wedge the suite (thread method: the process exits)
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900, method='thread')]
 
 
 def _net(cfg, **opt):
