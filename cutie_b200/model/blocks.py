@@ -118,9 +118,46 @@ class ObjResBlock(nn.Module):
         self.conv2 = ObjConv2d(c_out, c_out, 3, padding=1)
 
     def forward(self, g):
+        t = getattr(self, 'op_trials', None)
+        twins = getattr(self, 'cl_twins', None)
+        if (t is None or twins is None or g.dim() != 5 or not g.is_contiguous() or g.shape[2] % 4
+                or twins[0].weight.device != g.device):
+            return self._forward(g, self.conv1, self.conv2, self.downsample)
+        # The decoder feeds this block NCHW tensors (cutie_upsample2x_add), so cuDNN transposes input and weight around
+        # each 3x3 convolution and falls back to legacy NCHW-output engines (82 / 49 / 2 x 70 us at 480p, 3 objects).
+        # Alternative, A/B-ed on the device: one copy to channels-last on entry, channels-last weight twins throughout.
+        tol = 2e-2 if torch.backends.cudnn.allow_tf32 else 2e-4
+
+        def channels_last(trial):
+            B, K = g.shape[:2]
+            x = fold(g).contiguous(memory_format=torch.channels_last)
+            return unfold(self._forward4(x, *twins), B)
+        return t('objresblock_channels_last', (tuple(g.shape),),
+                 lambda: self._forward(g, self.conv1, self.conv2, self.downsample), channels_last, g, rtol=tol)
+
+    def make_channels_last_twins(self):
+        """Plain nn.Conv2d copies of conv1 / conv2 / the 1x1 projection shortcut with channels-last weights (sharing the
+        bias Parameters), for the channels-last variant of forward(); plain attributes, state_dict unchanged."""
+        def twin(conv):
+            tw = nn.Conv2d(conv.in_channels, conv.out_channels, conv.kernel_size, conv.stride, conv.padding)
+            tw.weight = nn.Parameter(conv.weight.detach().clone().contiguous(memory_format=torch.channels_last),
+                                     requires_grad=False)
+            tw.bias = conv.bias
+            return tw.eval()
+        ds = None if isinstance(self.downsample, nn.Identity) else twin(self.downsample)
+        object.__setattr__(self, 'cl_twins', (twin(self.conv1), twin(self.conv2), ds))
+        return tuple(tw for tw in self.cl_twins if tw is not None)
+
+    def _forward(self, g, conv1, conv2, downsample):
         B = g.shape[0]
-        y = self.conv2(unfold(conv_relu(self.conv1, fold(F.relu(g))), B))
-        return y + self.downsample(g)
+        y = conv2(unfold(conv_relu(conv1, fold(F.relu(g))), B))
+        return y + downsample(g)
+
+    @staticmethod
+    def _forward4(x, conv1, conv2, downsample):
+        """The same block on a folded [B*K, C, H, W] tensor with plain convolutions (channels-last variant)."""
+        y = conv2(conv_relu(conv1, F.relu(x)))
+        return y + (x if downsample is None else downsample(x))
 
 
 class _AddDistributor(nn.Module):

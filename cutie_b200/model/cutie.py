@@ -204,10 +204,14 @@ class CUTIE(nn.Module):
         # after the folding: fold_trunk_ replaces the trunk convolutions by new modules
         object.__setattr__(self, 'conv_epilogues', ConvEpilogueFuser(enabled=bool(fuse_epilogues)))
         attach_epilogue_fuser(self, self.conv_epilogues)
-        if channels_last and fuse_glue and self.object_transformer_enabled:
+        if channels_last and fuse_glue and self.object_transformer_enabled:   # (transformer-less variants: no twins)
             # PixelFFN blocks sit between two of our channel-major kernels: offer a channels-last variant to the trial
             for blk in self.object_transformer.blocks:
                 for tw in blk.pixel_ffn.conv.make_channels_last_twins() or ():
+                    attach_epilogue_fuser(tw, self.conv_epilogues)
+            # so do the decoder's two residual blocks (between cutie_upsample2x_add calls)
+            for up in (self.mask_decoder.up_16_8, self.mask_decoder.up_8_4):
+                for tw in up.out_conv.make_channels_last_twins():
                     attach_epilogue_fuser(tw, self.conv_epilogues)
             # the two fuser blocks already receive channels-last tensors (their input descends from the channels-last
             # trunk): keep their weights channels-last too instead of re-laying them out on every call

@@ -300,3 +300,20 @@ def test_bench_preflight_child_passes_here():
                        text=True, timeout=800)
     print(r.stderr[-3000:])
     assert r.returncode == 0, r.stderr[-3000:]
+
+
+@pytest.mark.parametrize('cin,cout,hw', [(256, 128, (60, 108)), (128, 128, (120, 216))])
+def test_decoder_resblock_channels_last_variant_matches_nchw(cin, cout, hw):
+    """ObjResBlock (the decoder's residual blocks) with channels-last weight twins vs the NCHW form, at the 480p shapes."""
+    from cutie_b200.model.blocks import ObjResBlock, fold, unfold
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(0)
+    blk = ObjResBlock(cin, cout).cuda().eval()
+    g = torch.randn(1, 3, cin, *hw, device='cuda')
+    with torch.inference_mode():
+        ref = blk(g)
+        blk.make_channels_last_twins()
+        x = fold(g).contiguous(memory_format=torch.channels_last)
+        got = unfold(blk._forward4(x, *blk.cl_twins), 1)
+    assert got.shape == ref.shape
+    assert float((got - ref).abs().max()) <= 2e-4 * float(ref.abs().max())
