@@ -75,7 +75,8 @@ class ChannelAttnResBlock(nn.Module):
         # copy to channels-last on entry, channels-last weight twins, everything in between channels-last.
         tol = 2e-2 if torch.backends.cudnn.allow_tf32 else 2e-4
         return t('caresblock_channels_last', (tuple(x.shape),), lambda: self._forward(x, self.conv1, self.conv2),
-                 lambda trial: self._forward(x.contiguous(memory_format=torch.channels_last), *twins), x, rtol=tol)
+                 lambda trial: self._forward(x.contiguous(memory_format=torch.channels_last), *twins).contiguous(), x,
+                 rtol=tol)                         # .contiguous(): the copy back to NCHW is part of what is timed
 
     def make_channels_last_twins(self):
         """conv1 / conv2 copies with channels-last weights (sharing the bias Parameters), for the channels-last variant of
@@ -131,7 +132,7 @@ class ObjResBlock(nn.Module):
         def channels_last(trial):
             B, K = g.shape[:2]
             x = fold(g).contiguous(memory_format=torch.channels_last)
-            return unfold(self._forward4(x, *twins), B)
+            return unfold(self._forward4(x, *twins).contiguous(), B)      # back to NCHW inside the timed variant
         return t('objresblock_channels_last', (tuple(g.shape),),
                  lambda: self._forward(g, self.conv1, self.conv2, self.downsample), channels_last, g, rtol=tol)
 
