@@ -212,6 +212,11 @@ def preflight(local: int) -> int:
         lg, pr = K_.segment_tail(x)
         assert float((lg - lg_want).abs().max()) <= 1e-4 and float((pr - F.softmax(lg_want, dim=1)).abs().max()) <= 1e-5, \
             'segment_tail'
+        conv = torch.nn.Conv2d(128, 1, 3, padding=1).to(dev)
+        x = rnd(3, 128, 120, 216)
+        want = conv(torch.relu(x))
+        got = K_.conv3x3_c1(x, conv.weight, conv.bias, relu_input=True)
+        assert float((got - want).abs().max()) <= 2e-5 * max(1.0, float(want.abs().max())), 'conv3x3_c1'
         h, v = rnd(1, 3, 256, 30, 54), 2 * rnd(1, 3, 768, 30, 54)
         assert float((K_.gated_update(h, v) - gated_update(h, v)).abs().max()) <= 2e-6, 'gated_update'
         cfg = default_config(mem_every=2, max_mem_frames=3)

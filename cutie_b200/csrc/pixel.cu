@@ -374,6 +374,41 @@ __global__ void __launch_bounds__(256) upsample4_softmax_kernel(const float* __r
     if (c < C) prob[(b * C + c) * HW4 + (long long)Y * W4 + X] = v[c] / sum;
 }
 
+// ------------------------------------------------------------------------------------------------
+// The mask decoder's prediction head (cutie/model/big_modules.py:264,300: `self.pred(F.relu(p4))`, Conv2d(C, 1, 3, padding=1)):
+// a 3x3 convolution with ONE output channel over [planes, C, H, W].  cuDNN treats it as a GEMM with N = 1 and wraps
+// it in NCHW<->NHWC transposes of the 40 MB input and of the weight (18.5 + 10.2 + 39.9 + 6.2 us at 480p, after an
+// 11.4 us clamp and before a 3.7 us bias add); it is really a 9-tap weighted sum over channels -- one pass over the
+// input.  One thread per output pixel, channels outermost, taps row-major, fp32 FMA chain; the ReLU of the input is
+// applied on the fly (zero padding is applied to the rectified input, as F.relu -> Conv2d(padding=1) does).
+__global__ void __launch_bounds__(256) conv3x3_c1_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, float* __restrict__ out,
+                                                         long long total, int C, int H, int W, int relu_input) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // (plane, Y, X)
+  if (t >= total) return;
+  const int X = (int)(t % W);
+  const int Y = (int)((t / W) % H);
+  const long long p = t / ((long long)W * H);
+  const long long hw = (long long)H * W;
+  const float* xp = x + p * C * hw;
+  const bool y0 = Y > 0, y2 = Y < H - 1, x0 = X > 0, x2 = X < W - 1;
+  float acc = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float* r = xp + (long long)c * hw + (long long)Y * W + X;
+    const float* k = w + c * 9;
+    float v[9];
+    v[0] = (y0 && x0) ? __ldg(r - W - 1) : 0.f; v[1] = y0 ? __ldg(r - W) : 0.f; v[2] = (y0 && x2) ? __ldg(r - W + 1) : 0.f;
+    v[3] = x0 ? __ldg(r - 1) : 0.f;             v[4] = __ldg(r);                v[5] = x2 ? __ldg(r + 1) : 0.f;
+    v[6] = (y2 && x0) ? __ldg(r + W - 1) : 0.f; v[7] = y2 ? __ldg(r + W) : 0.f; v[8] = (y2 && x2) ? __ldg(r + W + 1) : 0.f;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const float a = relu_input ? (v[i] < 0.f ? 0.f : v[i]) : v[i];
+      acc = fmaf(__ldg(k + i), a, acc);
+    }
+  }
+  out[t] = acc + __ldg(bias);
+}
+
 }  // namespace cutie
 
 using namespace cutie;
@@ -520,6 +555,17 @@ extern "C" int cutie_segment_tail(const float* x, float* agg, float* logits, flo
   CUTIE_CHECK_LAUNCH();
   const long long hi = lo * 16;
   upsample4_softmax_kernel<<<(unsigned)((hi + 255) / 256), 256, 0, st>>>(agg, logits, prob, hi, (int)(K + 1), (int)h, (int)w);
+  CUTIE_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int cutie_conv3x3_c1(const float* x, const float* w, const float* bias, float* out, int64_t planes, int64_t C,
+                                int64_t H, int64_t W, int relu_input, void* stream) {
+  CUTIE_REQUIRE(x && w && bias && out && planes >= 1 && C >= 1 && H >= 1 && W >= 1, "null/empty argument");
+  CUTIE_REQUIRE(H < (1 << 20) && W < (1 << 20) && C < (1 << 20), "feature map too large");
+  const long long total = (long long)planes * H * W;
+  conv3x3_c1_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, w, bias, out, total, (int)C, (int)H,
+                                                                                       (int)W, relu_input);
   CUTIE_CHECK_LAUNCH();
   return 0;
 }

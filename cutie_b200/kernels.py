@@ -380,6 +380,20 @@ def segment_tail(x: torch.Tensor):
     return logits, prob
 
 
+def conv3x3_c1(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, relu_input: bool = False) -> torch.Tensor:
+    """F.conv2d(relu(x) if relu_input else x, weight, bias, padding=1) for weight [1,C,3,3]: x [N,C,H,W] -> [N,1,H,W]."""
+    N, C, H, W = x.shape
+    assert x.dtype == torch.float32 and tuple(weight.shape) == (1, C, 3, 3) and bias.numel() == 1
+    x = x.contiguous()
+    w = weight.detach().contiguous()
+    out = torch.empty(N, 1, H, W, dtype=torch.float32, device=x.device)
+    with _call('conv3x3_c1', 1):
+        st = lib().cutie_conv3x3_c1(_ptr(x), _ptr(w), _ptr(bias.detach()), _ptr(out), _i64(N), _i64(C), _i64(H), _i64(W),
+                                    int(bool(relu_input)), _stream())
+    _check(st, 'cutie_conv3x3_c1')
+    return out
+
+
 def area_pool(x: torch.Tensor, f: int) -> torch.Tensor:
     """F.interpolate(x, scale_factor=1/f, mode='area') for [..., H, W] with H % f == W % f == 0."""
     H, W = x.shape[-2:]

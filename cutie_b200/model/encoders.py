@@ -8,6 +8,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from cutie_b200 import kernels as K_
 from cutie_b200.model.backbone import ResNetTrunk
 from cutie_b200.model.fuse import conv_relu_maxpool
 from cutie_b200.model.blocks import (DeepSensoryUpdater, FeatureFusion, MultiScaleSensoryUpdater, ObjConv2d,
@@ -162,7 +163,18 @@ class MaskDecoder(nn.Module):
             p16 = memory_readout[:, lo:hi]
             p8 = self.up_16_8(p16, f8)
             p4 = self.up_8_4(p8, f4)
-            lg = unfold(self.pred(F.relu(fold(p4).float())), B)             # [B,k,1,4h,4w]
+            x4 = fold(p4).float()
+
+            def aten():
+                return self.pred(F.relu(x4))
+            t = getattr(self, 'op_trials', None)
+            if t is None:
+                lg = aten()
+            else:   # single-output-channel 3x3 convolution: cutie_conv3x3_c1 (ReLU on the fly, no cuDNN transposes)
+                tol = 2e-2 if torch.backends.cudnn.allow_tf32 else 2e-4
+                lg = t('pred_conv3x3', (tuple(x4.shape),), aten,
+                       lambda trial: K_.conv3x3_c1(x4, self.pred.weight, self.pred.bias, relu_input=True), x4, rtol=tol)
+            lg = unfold(lg, B)                                              # [B,k,1,4h,4w]
             if update_sensory:
                 upd = self.sensory_update(p16, p8, (p4, lg), sensory[:, lo:hi])
                 if len(spans) == 1:

@@ -158,6 +158,12 @@ int cutie_bias_relu_maxpool(const float* y, const float* bias, float* out, int64
 int cutie_segment_tail(const float* x, float* agg, float* logits, float* prob, int64_t B, int64_t K, int64_t h, int64_t w,
                        void* stream);
 
+/* 3x3 convolution with a single output channel, optionally of the rectified input: the mask decoder's prediction head
+ * `pred(F.relu(p4))` (cutie/model/big_modules.py:264,300; Conv2d(C, 1, 3, padding=1)).  x [planes,C,H,W] dense fp32
+ * (planes = B*K objects), w [C,3,3] (= weight[0]), bias [1], out [planes,H,W]; zero padding of the (rectified) input. */
+int cutie_conv3x3_c1(const float* x, const float* w, const float* bias, float* out, int64_t planes, int64_t C, int64_t H,
+                     int64_t W, int relu_input, void* stream);
+
 /* out[y,x] = lut[argmax_c prob[c,y,x]]: InferenceCore.output_prob_to_mask (inference_core.py:377-385: argmax over
  * the 1+K channels, then ObjectManager.tmp_to_obj_cls object_manager.py:99-104) in one pass.  prob may be a strided
  * view (plane_stride / row_stride in elements, unit pixel stride); lut int64 [C]; out int64 [H,W] contiguous.

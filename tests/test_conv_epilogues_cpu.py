@@ -359,7 +359,7 @@ def test_whole_stream_with_every_optional_form_active(cpu_kernels):
     assert rf['cudnn'] >= 40 and rf['kernel'] >= 20                       # trunks / bias-only convolutions
     assert rf['stem_pool'] == 2                                           # pixel- and mask-encoder stems
     assert set(rt['ops']) == {'area_pool', 'eca_scale_add', 'gated_update', 'qt_p2q_splits', 'caresblock_channels_last',
-                              'segment_tail', 'objresblock_channels_last'}
+                              'segment_tail', 'objresblock_channels_last', 'pred_conv3x3'}
     # (on the CPU the bilinear + skip add can hand the second block a non-contiguous tensor, which keeps the NCHW form)
     assert rt['ops']['objresblock_channels_last']['kernel'] >= 1 and rt['ops']['objresblock_channels_last']['aten'] == 0
     assert rt['ops']['caresblock_channels_last'] == {'kernel': 1, 'aten': 0}       # one geometry, three blocks

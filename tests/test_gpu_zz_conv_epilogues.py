@@ -317,3 +317,16 @@ def test_decoder_resblock_channels_last_variant_matches_nchw(cin, cout, hw):
         got = unfold(blk._forward4(x, *blk.cl_twins), 1)
     assert got.shape == ref.shape
     assert float((got - ref).abs().max()) <= 2e-4 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize('shape', [(3, 128, 120, 216), (2, 16, 9, 7), (1, 5, 1, 1)])
+def test_conv3x3_c1_kernel_matches_cudnn(shape):
+    import cutie_b200.kernels as K_
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator().manual_seed(shape[1])
+    x = torch.randn(*shape, generator=g).cuda()
+    conv = torch.nn.Conv2d(shape[1], 1, 3, padding=1).cuda()
+    with torch.inference_mode():
+        want = conv(torch.relu(x))
+        got = K_.conv3x3_c1(x, conv.weight, conv.bias, relu_input=True)
+    assert got.shape == want.shape and float((got - want).abs().max()) <= 2e-5 * max(1.0, float(want.abs().max()))

@@ -145,3 +145,18 @@ def test_prob_to_mask_wrapper(K_):
     assert torch.equal(K_.prob_to_mask(prob, lut), want)
     strided = torch.rand(4, 9, 26, generator=g)[:, :, :13]             # row stride != width
     assert torch.equal(K_.prob_to_mask(strided, lut), lut[strided.argmax(0)])
+
+
+@pytest.mark.parametrize('shape', [(3, 16, 9, 12), (1, 128, 6, 7), (2, 5, 1, 1), (1, 3, 2, 5)])
+@pytest.mark.parametrize('relu', [False, True])
+def test_conv3x3_c1_wrapper(K_, shape, relu):
+    g = torch.Generator().manual_seed(shape[1] + relu)
+    x = torch.randn(*shape, generator=g)
+    conv = torch.nn.Conv2d(shape[1], 1, 3, padding=1)
+    with torch.no_grad():
+        want = conv(torch.relu(x) if relu else x)
+        got = K_.conv3x3_c1(x, conv.weight, conv.bias, relu_input=relu)
+    assert got.shape == want.shape and torch.allclose(got, want, rtol=1e-5, atol=1e-5)
+    xs = x.transpose(-1, -2).contiguous().transpose(-1, -2)                 # strided input: the wrapper copies
+    with torch.no_grad():
+        assert torch.allclose(K_.conv3x3_c1(xs, conv.weight, conv.bias, relu_input=relu), want, rtol=1e-5, atol=1e-5)
