@@ -12,7 +12,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from cutie_b200 import kernels as K_
-from cutie_b200.model.fuse import conv_relu
+from cutie_b200.model.fuse import conv_add, conv_plain, conv_relu
 
 
 def fold(g: torch.Tensor) -> torch.Tensor:
@@ -150,15 +150,15 @@ class ObjResBlock(nn.Module):
         return tuple(tw for tw in self.cl_twins if tw is not None)
 
     def _forward(self, g, conv1, conv2, downsample):
-        B = g.shape[0]
-        y = conv2(unfold(conv_relu(conv1, fold(F.relu(g))), B))
-        return y + downsample(g)
+        ds = None if isinstance(downsample, nn.Identity) else downsample
+        return unfold(self._forward4(fold(g), conv1, conv2, ds), g.shape[0])
 
     @staticmethod
     def _forward4(x, conv1, conv2, downsample):
-        """The same block on a folded [B*K, C, H, W] tensor with plain convolutions (channels-last variant)."""
-        y = conv2(conv_relu(conv1, F.relu(x)))
-        return y + (x if downsample is None else downsample(x))
+        """The block on a folded [B*K, C, H, W] tensor: relu - conv1 - relu - conv2, plus the (projected) input; the
+        residual add rides in conv2's epilogue where the model's fuser chose a form that can carry it."""
+        skip = x if downsample is None else conv_plain(downsample, x)
+        return conv_add(conv2, conv_relu(conv1, F.relu(x)), skip)
 
 
 class _AddDistributor(nn.Module):

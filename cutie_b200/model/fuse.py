@@ -330,6 +330,18 @@ def conv_relu_maxpool(conv: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
     return f.stem(conv, x)
 
 
+def conv_add(conv: nn.Conv2d, x: torch.Tensor, z: torch.Tensor) -> torch.Tensor:
+    """conv(x) + z (bias included, no activation): the closing convolution of a pre-activation residual block."""
+    f = getattr(conv, 'epilogue_fuser', None)
+    return ConvEpilogueFuser.unfused(conv, x, z, relu=False) if f is None else f(conv, x, z, relu=False)
+
+
+def conv_plain(conv: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
+    """conv(x) on a 4-D tensor for any nn.Conv2d subclass (ObjConv2d's own forward expects 5-D object tensors)."""
+    f = getattr(conv, 'epilogue_fuser', None)
+    return ConvEpilogueFuser._conv(conv, x, True) if f is None else f(conv, x, None, relu=False)
+
+
 def conv_add_relu(conv: nn.Conv2d, x: torch.Tensor, z: torch.Tensor) -> torch.Tensor:
     """relu(conv(x) + z)."""
     f = getattr(conv, 'epilogue_fuser', None)
