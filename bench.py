@@ -1,16 +1,22 @@
-"""bench.py -- frames/sec of the Cutie per-frame path on B200 (BASELINE.json metric), with the
-roofline of the dominant kernel and the reference's CPU path timed beside it.
+"""bench.py -- frames/sec of the Cutie per-frame path on B200 (BASELINE.json metric), with the roofline of the
+dominant kernel and the reference's CPU path timed beside it.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|northstar]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (config.workload = "cfg2", BASELINE.json configs[1]): synthetic 480p (854x480 -> 864x480
-padded, 30x54 = 1620 tokens/frame) video, 3 objects, 256-frame working memory (max_mem_frames=256,
-use_long_term=False, mem_every=5, top_k=30): a steady-state bank of 414 720 tokens (1.38 GB), pre-filled
-with seeded N(0,1) keys/values and 1+N(0,1)^2 shrinkage; random-init weights of
-the cutie-base architecture (cutie_b200/utils/synth.py).  A *step* is one InferenceCore.step on one frame; every
-5th step is a memory frame (mask encoder + append + FIFO eviction).  N>1: one independent video stream per
-GPU (weak scaling, no data-path collective -- SURVEY.md section 8(e).1).
+Workload (config.workload = "cfg2", BASELINE.json configs[1]): synthetic 480p (854x480 -> 864x480 padded, 30x54 = 1620
+tokens/frame) video, 3 objects, 256-frame working memory (max_mem_frames=256, use_long_term=False, mem_every=5,
+top_k=30): a steady-state bank of 413 100 tokens, pre-filled with seeded N(0,1) keys/values and 1+N(0,1)^2 shrinkage
+(SURVEY.md section 8(d)); random-init weights of the cutie-base architecture (cutie_b200/utils/synth.py).  A *step* is
+one InferenceCore.step on one frame through the reference's own call signature (no extension arguments); every 5th step
+is a memory frame (mask encoder + append + FIFO eviction).  N>1: one independent video stream per GPU (weak scaling, no
+data-path collective -- SURVEY.md section 8(e).1); after the stream benchmark the N ranks also run the key-sharded
+memory read of BASELINE.json configs[4] (`sharded_read`).
+
+Numerics of the timed region = numerics of the parity tests: fp32, cuDNN / cuBLAS TF32 OFF (`amp=False`); every
+optional launch form is chosen by a committed table (cutie_b200/utils/dispatch.py, model/fuse.py), nothing is timed to
+choose an arithmetic.  After the timed region one frame is re-computed by the CPU oracle from the live state
+(`parity_check`).
 
 One JSON line on stdout (rank 0); everything else goes to stderr.
 """
@@ -34,14 +40,10 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-# Exactly ONE line may reach stdout (the JSON).  Libraries (NCCL prints its version banner) write to fd 1
-# directly, so fd 1 is pointed at stderr for the whole run and the JSON goes to a saved copy of the real stdout.
-if os.environ.get('CUTIE_BENCH_STDOUT_FD'):          # re-exec'ed by the fallback below: fd 1 already points at stderr
-    _REAL_STDOUT = int(os.environ['CUTIE_BENCH_STDOUT_FD'])
-else:
-    _REAL_STDOUT = os.dup(1)
-    os.set_inheritable(_REAL_STDOUT, True)
-    os.dup2(2, 1)
+# Exactly ONE line may reach stdout (the JSON).  Libraries (NCCL prints its version banner) write to fd 1 directly, so
+# fd 1 is pointed at stderr for the whole run and the JSON goes to a saved copy of the real stdout.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
 
 
 def emit(line: dict):
@@ -55,6 +57,7 @@ WORKLOADS = {
     'northstar': dict(H=480, W=854, K=3, mem_frames=6, top_k=30,
                       desc='synthetic 480p video, 3 objects, ~10k-key working memory (9720 tokens)'),
 }
+METRIC = 'frames/sec @480p 3-obj'
 
 
 def usable_cpus() -> int:
@@ -90,9 +93,13 @@ def make_net(cfg):
     return net
 
 
+def tokens_per_frame(wl) -> int:
+    return (wl['H'] // 16) * (-(-wl['W'] // 16))
+
+
 def synthetic_bank_chunks(wl, chunk_frames=16, seed=1234):
     """Yields (key [1,64,n], shrinkage [1,1,n], values [1,K,256,n]) CPU chunks of the steady-state bank."""
-    HW = (wl['H'] // 16) * (-(-wl['W'] // 16))
+    HW = tokens_per_frame(wl)
     total = (wl['mem_frames'] - 2) * HW          # perm frame + this many temp frames = one short of the FIFO limit
     g = torch.Generator().manual_seed(seed)
     done = 0
@@ -103,6 +110,19 @@ def synthetic_bank_chunks(wl, chunk_frames=16, seed=1234):
         done += n
 
 
+def base_config(args, wl, world):
+    """The `config` object: identical for both arms (--impl ours / reference) so the driver can compare them."""
+    HW = tokens_per_frame(wl)
+    return {'workload': f"{args.workload}: {wl['desc']}", 'resolution': [wl['H'], wl['W']], 'objects': wl['K'],
+            'tokens_per_frame': HW, 'memory_tokens': (wl['mem_frames'] - 1) * HW, 'top_k': wl['top_k'], 'mem_every': 5,
+            'streams': world, 'parallelism': f'{world} independent streams (1 per GPU)',
+            'l2': 'no flush: the bank scanned every frame is larger than the 126 MB L2'
+                  if args.workload == 'cfg2' else 'bank fits L2 (north-star size); stated, not flushed',
+            'weights': 'seeded random init (no checkpoint offline)', 'precision': 'fp32, TF32 off (amp=False)'}
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks
 def _nvml_handle(idx):
     """NVML handle of torch device `idx` (honours CUDA_VISIBLE_DEVICES through the device's UUID), or None."""
     try:
@@ -120,9 +140,9 @@ def _nvml_handle(idx):
 
 
 def nvsmi_sampler(stop, out, idx):
-    """Samples SM clock, power and throttle reasons DURING the timed region: NVML in-process every ~5 ms (the
-    timed region of a default run is a fraction of a second), `nvidia-smi` every 0.2 s if NVML is unavailable.
-    Rows: [sm_mhz, sm_max_mhz, power_w, hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap]."""
+    """Samples SM clock, power and throttle reasons DURING the timed region: NVML in-process every ~5 ms, `nvidia-smi`
+    every 0.2 s if NVML is unavailable.  Rows: [sm_mhz, sm_max_mhz, power_w, hw_slowdown, hw_thermal_slowdown,
+    sw_thermal_slowdown, sw_power_cap]."""
     nv = _nvml_handle(idx)
     if nv is not None:
         pynvml, h = nv
@@ -167,105 +187,10 @@ def summarize_clocks(samples):
             'power_w_max': max(float(s[2]) for s in samples), 'reasons': sorted(reasons), 'samples': len(samples)}
 
 
-# ---------------------------------------------------------------------------------------------------
-def preflight(local: int) -> int:
-    """Runs in a CHILD process before the measured run (`bench.py --preflight`): the optional launch-saving forms that
-    optimize_for_inference() can switch on (cuDNN fused conv epilogues, cutie_bias_act, the pixel-side glue kernels)
-    against PyTorch's own launches on this box -- kernels on random tensors, then a short optimised stream with CUDA
-    graphs.  Exit code 0 = use them; anything else (mismatch, exception, crash, time-out) = the measured run keeps
-    PyTorch's launches for those stages and says so in its JSON line.  The hot-path kernels are not optional and are not
-    part of this check."""
-    import torch.nn.functional as F
-    import cutie_b200.kernels as K_
-    from cutie_b200.config import default_config
-    from cutie_b200.inference.inference_core import InferenceCore
-    from cutie_b200.model.blocks import gated_update
-    from cutie_b200.utils.synth import synthetic_video
-    dev = torch.device('cuda', local)
-    torch.cuda.set_device(dev)
-    torch.backends.cudnn.allow_tf32 = False
-    torch.backends.cuda.matmul.allow_tf32 = False
-    g = torch.Generator().manual_seed(0)
-    rnd = lambda *s: torch.randn(*s, generator=g).to(dev)
-    with torch.inference_mode():
-        for shape in ((3, 256, 30, 54), (2, 7, 5, 3)):
-            for fmt in (torch.contiguous_format, torch.channels_last):
-                y, z, b = rnd(*shape).contiguous(memory_format=fmt), rnd(*shape), rnd(shape[1])
-                want = torch.relu(y + b.view(1, -1, 1, 1) + z)
-                assert torch.equal(K_.bias_act_(y.clone(memory_format=torch.preserve_format), b, z, True), want), 'bias_act'
-                conv = torch.nn.Conv1d(1, 1, 5, padding=2, bias=False).to(dev)
-                gate = conv(y.mean(dim=(2, 3)).unsqueeze(1)).sigmoid().transpose(1, 2).unsqueeze(-1)
-                want = y * gate + z
-                got = K_.eca_scale_add_(y.clone(memory_format=torch.preserve_format), z, conv.weight)
-                assert float((got - want).abs().max()) <= 1e-5 * float(want.abs().max()), 'eca_scale_add'
-        for shape, f in (((1, 3, 480, 864), 16), ((3, 256, 60, 108), 2), ((3, 257, 120, 216), 4)):
-            x = torch.rand(*shape, generator=g).to(dev)
-            assert float((K_.area_pool(x, f) - F.interpolate(x, scale_factor=1.0 / f, mode='area')).abs().max()) <= 1e-6, 'area_pool'
-        for shape in ((1, 64, 240, 432), (3, 64, 48, 80)):
-            for fmt in (torch.contiguous_format, torch.channels_last):
-                y, b = rnd(*shape).contiguous(memory_format=fmt), rnd(shape[1])
-                want = F.max_pool2d(torch.relu(y + b.view(1, -1, 1, 1)), 3, stride=2, padding=1)
-                assert torch.equal(K_.bias_relu_maxpool(y, b), want), 'bias_relu_maxpool'
-        from cutie_b200.utils.tensor_utils import aggregate
-        x = 4 * rnd(1, 3, 120, 216)
-        lg_want = F.interpolate(aggregate(torch.sigmoid(x), dim=1), scale_factor=4, mode='bilinear', align_corners=False)
-        lg, pr = K_.segment_tail(x)
-        assert float((lg - lg_want).abs().max()) <= 1e-4 and float((pr - F.softmax(lg_want, dim=1)).abs().max()) <= 1e-5, \
-            'segment_tail'
-        conv = torch.nn.Conv2d(128, 1, 3, padding=1).to(dev)
-        x = rnd(3, 128, 120, 216)
-        want = conv(torch.relu(x))
-        got = K_.conv3x3_c1(x, conv.weight, conv.bias, relu_input=True)
-        assert float((got - want).abs().max()) <= 2e-5 * max(1.0, float(want.abs().max())), 'conv3x3_c1'
-        h, v = rnd(1, 3, 256, 30, 54), 2 * rnd(1, 3, 768, 30, 54)
-        assert float((K_.gated_update(h, v) - gated_update(h, v)).abs().max()) <= 2e-6, 'gated_update'
-        cfg = default_config(mem_every=2, max_mem_frames=3)
-        on = make_net(cfg).to(dev).optimize_for_inference()
-        off = make_net(cfg).to(dev).optimize_for_inference(fuse_epilogues=False, fuse_glue=False)
-        a, b = InferenceCore(on, cfg=cfg, use_cuda_graphs=True), InferenceCore(off, cfg=cfg, use_cuda_graphs=True)
-        frames, mask = synthetic_video(4, 96, 160, 3, seed=3)
-        for ti in range(4):
-            x = frames[ti].to(dev)
-            if ti == 0:
-                a.step(x, mask.to(dev), objects=[1, 2, 3]); b.step(x, mask.to(dev), objects=[1, 2, 3])
-            else:
-                pa, pb = a.step(x), b.step(x)
-                d = float((a.last_logits - b.last_logits).abs().max())
-                assert d < 1e-3 and bool(torch.isfinite(pa).all()), f'optimised stream deviates by {d} at frame {ti}'
-        # encoder look-ahead: same results with and without it (same kernels, another stream schedule)
-        c, d = InferenceCore(on, cfg=cfg, use_cuda_graphs=True), InferenceCore(on, cfg=cfg, use_cuda_graphs=True)
-        frames, mask = synthetic_video(14, 96, 160, 3, seed=5)
-        fd = frames.to(dev)
-        for ti in range(13):
-            kw = dict(objects=[1, 2, 3]) if ti == 0 else {}
-            args_ = (fd[ti], mask.to(dev)) if ti == 0 else (fd[ti],)
-            pc = c.step(*args_, next_image=fd[ti + 1], **kw)
-            pd_ = d.step(*args_, **kw)
-            # a mis-ordered stream would hand the decoder another frame's features (gross error); run-to-run rounding of
-            # library kernels is tolerated
-            assert float((pc - pd_).abs().max()) < 2e-2, f'look-ahead changes the result at frame {ti}'
-        torch.cuda.synchronize(dev)
-    log(f'[preflight] ok: conv epilogues {on.conv_epilogues.report()}; glue ops {on.op_trials.report()}')
-    return 0
-
-
-def run_preflight(local: int, timeout_s: float = 420.0):
-    """(ok, note): spawns `bench.py --preflight` for this rank's GPU."""
-    env = dict(os.environ)
-    env.pop('CUTIE_BENCH_STDOUT_FD', None)
-    for k in ('RANK', 'WORLD_SIZE', 'LOCAL_WORLD_SIZE', 'GROUP_RANK', 'ROLE_RANK', 'TORCHELASTIC_RUN_ID'):
-        env.pop(k, None)
-    env['LOCAL_RANK'] = str(local)
-    try:
-        r = subprocess.run([sys.executable, os.path.abspath(__file__), '--preflight'], env=env, timeout=timeout_s,
-                           stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
-    except subprocess.TimeoutExpired:
-        return False, f'pre-flight timed out after {timeout_s:.0f} s'
-    tail = (r.stderr or '').strip().splitlines()[-1:] or ['']
-    if r.returncode != 0:
-        return False, f'pre-flight exit {r.returncode}: {tail[0][:300]}'
-    log(tail[0])
-    return True, 'ok'
+def percentiles(ms):
+    s = sorted(ms)
+    pick = lambda q: s[min(len(s) - 1, int(q * len(s)))]
+    return {'frames': len(s), 'mean': sum(s) / len(s), 'p50': pick(0.50), 'p90': pick(0.90), 'p99': pick(0.99), 'max': s[-1]}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -274,185 +199,216 @@ def run_ours(args, wl, rank, world, dev):
     from cutie_b200.inference.inference_core import InferenceCore
     from cutie_b200.utils.synth import synthetic_video
     K_.lib()                                             # fail loudly if the CUDA library is missing
-    if args.no_key_image:
-        import cutie_b200.inference.memory_bank as MB
-        MB.USE_KEY_IMAGE = False
-    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.allow_tf32 = False              # the validated configuration: fp32 convolutions (amp=False)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = not args.no_cudnn_benchmark
     cfg = make_cfg(wl)
     net = make_net(cfg).to(dev)
     if not args.no_optimize:
-        # BN folding + channels-last trunks + conv/bias/ReLU epilogues in one cuDNN call (still PyTorch/cuDNN calls)
-        net.optimize_for_inference(fuse_epilogues=not args.no_fuse_epilogues, fuse_glue=not args.no_fuse_glue)
-    AB = 10                                    # steps per arm of the look-ahead A/B (untimed, after the warm-up)
-    n_frames = args.warmup + 2 * AB + args.steps + 2
+        # BN folding + channels-last trunks + conv/bias/ReLU epilogues in the form the committed rule names
+        net.optimize_for_inference()
+    use_graphs = not args.no_graphs
+    warm = max(args.warmup, 11) if use_graphs else args.warmup       # every CUDA-graph variant exists after 11 steps
+    K = args.steps
+    n_frames = warm + 4 * K + 16
     frames, mask = synthetic_video(n_frames, wl['H'], wl['W'], wl['K'], seed=rank)
     objs = list(range(1, wl['K'] + 1))
-    proc = InferenceCore(net, cfg=cfg, use_cuda_graphs=not args.no_graphs)
+    proc = InferenceCore(net, cfg=cfg, use_cuda_graphs=use_graphs)
     with torch.inference_mode():
         proc.step(frames[0].to(dev), mask.to(dev), objects=objs)          # permanent first frame
         for key, shr, vals in synthetic_bank_chunks(wl):                   # steady-state bank
             proc.memory.work_mem.add(key.to(dev), {o: vals[:, i].to(dev) for i, o in enumerate(objs)},
                                      shr.to(dev), None, as_permanent='no')
     n_tokens = proc.memory.work_mem.size(0)
-    log(f'[rank {rank}] bank prefilled: {n_tokens} tokens, '
-        f'{torch.cuda.memory_allocated(dev) / 2**30:.2f} GiB allocated')
+    log(f'[rank {rank}] bank prefilled: {n_tokens} tokens, {torch.cuda.memory_allocated(dev) / 2**30:.2f} GiB allocated')
     frames_dev = frames.to(dev)
     frames_pin = frames.pin_memory()
+    host_out = torch.empty(wl['H'], wl['W'], dtype=torch.uint8).pin_memory()
 
     def barrier():
         if world > 1:
             torch.distributed.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---- device-resident arm: inputs already in HBM ----
-    with torch.inference_mode():
-        t = 1
-        look = (not args.no_lookahead) and (not args.no_graphs)
-        nxt = (lambda i: frames_dev[i + 1]) if look else (lambda i: None)
-        for _ in range(args.warmup):
-            proc.step(frames_dev[t], next_image=nxt(t)); t += 1
-        # look-ahead A/B on this GPU (every graph variant exists by now): keep it only if the step gets shorter
-        ab = None
-        if look:
-            ab = {}
-            for mode in (True, False):
-                torch.cuda.synchronize(dev)
-                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a0.record()
-                for _ in range(AB):
-                    proc.step(frames_dev[t], next_image=frames_dev[t + 1] if mode else None); t += 1
-                a1.record()
-                torch.cuda.synchronize(dev)
-                ab['with' if mode else 'without'] = a0.elapsed_time(a1) / AB
-            look = ab['with'] <= ab['without']
-            ab['kept'] = look
-            log(f'[rank {rank}] encoder look-ahead A/B (ms/step over {AB} steps each): {ab}')
-            nxt = (lambda i: frames_dev[i + 1]) if look else (lambda i: None)
-        else:
-            t += 2 * AB                           # same frames in the timed region either way
-        untimed = t - 1                           # index offset of the timed frames
-        untimed_steps = args.warmup + (2 * AB if ab else 0)
-        barrier()
-        stop, samples = threading.Event(), []
-        th = threading.Thread(target=nvsmi_sampler, args=(stop, samples, dev.index or 0), daemon=True)
-        th.start()
-        K_.PROFILE = []
-        launches0 = K_.LAUNCH_COUNT
-        if args.phase_timing:
-            K_.phase_timing(True)
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
+    state = {'t': 1}
+
+    def device_arm(steps, lookahead, profile):
+        """`steps` frames with inputs resident in HBM; returns (per-step event marks, host enqueue ms/step)."""
+        t = state['t']
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        if profile:
+            K_.PROFILE = []
+        marks[0].record()
         h0 = time.perf_counter()
-        for j in range(args.steps):
-            # exactly K encoder passes inside the timed region: the first step encodes on the main stream (nothing was
-            # announced before the region), steps 2..K pick up their look-ahead, the last step announces nothing
-            proc.step(frames_dev[t], next_image=nxt(t) if j + 1 < args.steps else None); t += 1
-        host_ms_dev = (time.perf_counter() - h0) * 1e3 / args.steps     # host time to ENQUEUE a step (no sync inside)
-        ev1.record()
-        barrier()
-        stop.set(); th.join()
-        launches = K_.LAUNCH_COUNT - launches0
-        prof, K_.PROFILE = K_.PROFILE, None
-        phases = []
-        if args.phase_timing:
-            K_.phase_timing(False)
-            phases = [K_.phase_times(i) for i in range(min(args.steps, 60))]
-            phases = [p for p in phases if p]
-            if phases:
-                n = min(len(p) for p in phases)
-                avg = [sum(p[i] for p in phases) / len(phases) for i in range(n)]
-                log('[phases] affinity plan, ms per launch (filter, select, ..., re-rank): '
-                    + ' '.join(f'{x:.3f}' for x in avg) + f'  sum {sum(avg):.3f}')
-                phases = avg
-        ms_total = ev0.elapsed_time(ev1)
-    kernel_ms = {}
-    for name, a, b in prof:
-        kernel_ms.setdefault(name, []).append(a.elapsed_time(b))
-    # ---- end-to-end arm: pinned host frame in, uint8 mask out, copies inside the timed region ----
-    proc2 = proc                                          # same stream state continues (steady state)
-    host_out = torch.empty(wl['H'], wl['W'], dtype=torch.uint8).pin_memory()
-    with torch.inference_mode():
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        tt = 1 + untimed
+        for j in range(steps):
+            if lookahead:
+                proc.step(frames_dev[t], next_image=frames_dev[t + 1] if j + 1 < steps else None)
+            else:
+                proc.step(frames_dev[t])
+            marks[j + 1].record()
+            t += 1
+        host_ms = (time.perf_counter() - h0) * 1e3 / steps
+        state['t'] = t
+        return marks, host_ms
+
+    def e2e_arm(steps, lookahead):
+        """Pinned host frame in, uint8 mask on the host out, copies inside the timed region (H2D double-buffered on a
+        copy stream so that the upload of a later frame overlaps this frame's compute)."""
+        t0 = state['t']
         copy_stream = torch.cuda.Stream(dev)
         cur = torch.cuda.current_stream(dev)
-        NB = 3 if look else 2                # look-ahead hands frame i+1 to step i, so uploads run two frames ahead
+        NB = 3 if lookahead else 2
         ahead = NB - 1
         bufs = [torch.empty_like(frames_dev[0]) for _ in range(NB)]
         ready = [torch.cuda.Event() for _ in range(NB)]
         free = [torch.cuda.Event() for _ in range(NB)]
 
-        def upload(i):                       # pinned host frame -> device buffer i%NB on the copy stream
+        def upload(i):
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(free[i % NB])
-                bufs[i % NB].copy_(frames_pin[tt + i], non_blocking=True)
+                bufs[i % NB].copy_(frames_pin[t0 + i], non_blocking=True)
                 ready[i % NB].record(copy_stream)
         for ev in free:
             ev.record(cur)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for j in range(min(ahead, args.steps)):
+        for j in range(min(ahead, steps)):
             upload(j)
         h0 = time.perf_counter()
-        e2e_marks = []
-        for i in range(args.steps):
-            if i + ahead < args.steps:
-                upload(i + ahead)            # H2D of a later frame overlaps this frame's compute
+        for i in range(steps):
+            if i + ahead < steps:
+                upload(i + ahead)
             cur.wait_event(ready[i % NB])
-            ahead_img = None
-            if look and i + 1 < args.steps:  # exactly K uploads and K encoder passes for K steps
-                cur.wait_event(ready[(i + 1) % NB])
-                ahead_img = bufs[(i + 1) % NB]
-            if args.phase_timing:
-                marks = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-                marks[0].record()
-            prob = proc2.step(bufs[i % NB], next_image=ahead_img)
+            if lookahead:
+                nxt = None
+                if i + 1 < steps:
+                    cur.wait_event(ready[(i + 1) % NB])
+                    nxt = bufs[(i + 1) % NB]
+                prob = proc.step(bufs[i % NB], next_image=nxt)
+            else:
+                prob = proc.step(bufs[i % NB])
             free[i % NB].record(cur)
-            if args.phase_timing:
-                marks[1].record()
-            host_out.copy_(proc2.output_prob_to_mask(prob).to(torch.uint8), non_blocking=True)
-            if args.phase_timing:
-                marks[2].record()
-                e2e_marks.append(marks)
-        host_ms_e2e = (time.perf_counter() - h0) * 1e3 / args.steps
+            host_out.copy_(proc.output_prob_to_mask(prob).to(torch.uint8), non_blocking=True)
+        host_ms = (time.perf_counter() - h0) * 1e3 / steps
         e1.record()
+        state['t'] = t0 + steps
+        return e0, e1, host_ms
+
+    res = {}
+    with torch.inference_mode():
+        for _ in range(warm):
+            proc.step(frames_dev[state['t']])
+            state['t'] += 1
+        # ---- timed region 1: device-resident inputs, the reference's call signature ----
+        barrier()
+        stop, samples = threading.Event(), []
+        th = threading.Thread(target=nvsmi_sampler, args=(stop, samples, dev.index or 0), daemon=True)
+        th.start()
+        launches0 = K_.LAUNCH_COUNT
+        if args.phase_timing:
+            K_.phase_timing(True)
+        marks, host_dev = device_arm(K, False, True)
+        barrier()
+        stop.set(); th.join()
+        launches = K_.LAUNCH_COUNT - launches0
+        prof, K_.PROFILE = K_.PROFILE, None
+        if args.phase_timing:
+            K_.phase_timing(False)
+            ph = [p for p in (K_.phase_times(i) for i in range(min(K, 60))) if p]
+            if ph:
+                n = min(len(p) for p in ph)
+                res['phases'] = [sum(p[i] for p in ph) / len(ph) for i in range(n)]
+                log('[phases] affinity plan, ms per launch: ' + ' '.join(f'{x:.3f}' for x in res['phases']))
+        ms_total = marks[0].elapsed_time(marks[-1])
+        per_step = [marks[i].elapsed_time(marks[i + 1]) for i in range(K)]
+        kernel_ms = {}
+        for name, a, b in prof:
+            kernel_ms.setdefault(name, []).append(a.elapsed_time(b))
+        # ---- timed region 2: end to end through the public API with host buffers ----
+        barrier()
+        e0, e1, host_e2e = e2e_arm(K, False)
         barrier()
         ms_e2e = e0.elapsed_time(e1)
-        if e2e_marks:
-            st = sum(m[0].elapsed_time(m[1]) for m in e2e_marks) / len(e2e_marks)
-            mk = sum(m[1].elapsed_time(m[2]) for m in e2e_marks) / len(e2e_marks)
-            gap = (ms_e2e - sum(m[0].elapsed_time(m[2]) for m in e2e_marks)) / len(e2e_marks)
-            log(f'[e2e] per step: step() {st:.3f} ms, mask + D2H {mk:.3f} ms, between steps (waiting for the H2D) {gap:.3f} ms')
-    # ---- the dominant kernel without the look-ahead's concurrent encoder (explains `roofline`; not a bench value) ----
-    solo_ms = {}
-    if look and rank == 0:
-        with torch.inference_mode():
-            torch.cuda.synchronize(dev)
-            K_.PROFILE = []
-            for j in range(min(args.steps, 10)):
-                proc.step(frames_dev[1 + untimed + (j % args.steps)])
-            torch.cuda.synchronize(dev)
-            prof2, K_.PROFILE = K_.PROFILE, None
-        for name, a, b in prof2:
-            solo_ms.setdefault(name, []).append(a.elapsed_time(b))
-    times = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+        # ---- extension (not the reference signature): step(..., next_image=...) = encoder look-ahead ----
+        look = None
+        if use_graphs and not args.no_lookahead:
+            for _ in range(4):                                  # the second encoder capture slot
+                proc.step(frames_dev[state['t']], next_image=frames_dev[state['t'] + 1])
+                state['t'] += 1
+            barrier()
+            lm, _ = device_arm(K, True, False)
+            barrier()
+            le0, le1, _ = e2e_arm(K, True)
+            barrier()
+            look = {'ms_total': lm[0].elapsed_time(lm[-1]), 'ms_e2e': le0.elapsed_time(le1)}
+    times = torch.tensor([ms_total, ms_e2e] + ([look['ms_total'], look['ms_e2e']] if look else [0.0, 0.0]),
+                         dtype=torch.float64, device=dev)
     if world > 1:
         torch.distributed.all_reduce(times, op=torch.distributed.ReduceOp.MAX)
     ms_total, ms_e2e = float(times[0]), float(times[1])
-    log(f'[rank {rank}] host enqueue time per step: device arm {host_ms_dev:.2f} ms, e2e arm {host_ms_e2e:.2f} ms')
-    epi = net.conv_epilogues.report() if hasattr(net, 'conv_epilogues') else None
-    if epi:
-        log(f'[rank {rank}] conv epilogues: {epi}')
-    glue = net.op_trials.report() if hasattr(net, 'op_trials') else None
-    if glue:
-        log(f'[rank {rank}] glue ops: {glue}')
-    return dict(untimed=untimed_steps, lookahead_ab=ab, solo_ms=solo_ms, lookahead=look, glue=glue, epilogues=epi, host_ms=[host_ms_dev, host_ms_e2e], phases=phases, image_levels=K_.image_level_launches(), ms_total=ms_total, ms_e2e=ms_e2e, kernel_ms=kernel_ms, launches=launches, n_tokens=n_tokens,
-                clocks=summarize_clocks(samples), h2d=frames_pin[0].numel() * 4, d2h=host_out.numel())
+    if look:
+        look = {'ms_total': float(times[2]), 'ms_e2e': float(times[3])}
+    log(f'[rank {rank}] host enqueue time per step: device arm {host_dev:.2f} ms, e2e arm {host_e2e:.2f} ms')
+    res.update(ms_total=ms_total, ms_e2e=ms_e2e, per_step=per_step, kernel_ms=kernel_ms, launches=launches,
+               n_tokens=n_tokens, clocks=summarize_clocks(samples), h2d=frames_pin[0].numel() * 4, d2h=host_out.numel(),
+               host_ms=[host_dev, host_e2e], lookahead=look, untimed=warm, image_levels=K_.image_level_launches(),
+               epilogues=net.conv_epilogues.report() if hasattr(net, 'conv_epilogues') else None,
+               glue=net.glue_dispatch.report() if hasattr(net, 'glue_dispatch') else None)
+    # ---- in-run parity check: ONE frame re-computed by the CPU oracle from the live state ----
+    if rank == 0 and world == 1 and not args.no_parity_check:
+        try:
+            res['parity'] = parity_check(proc, cfg, frames[state['t']], dev)
+        except Exception as e:                                 # noqa: BLE001 -- reported, never hidden
+            import traceback
+            traceback.print_exc()
+            res['parity'] = {'error': f'{type(e).__name__}: {e}'[:300]}
+    return res
 
 
-def run_cpu_reference(args, wl, max_seconds, steps, warmup):
-    """The reference's algorithm on the host cores: oracle/cpu_core.py (pinned to the reference by
-    tests/test_oracle_golden.py), same weights, same synthetic video, same pre-filled bank."""
+def parity_check(proc, cfg, frame, dev):
+    """The oracle (CPU restatement of the reference, dense [N,HW] affinity) re-computes the next frame from the state the
+    CUDA path is in after the timed region -- the 413 100-token bank, i.e. the tcgen05 filter plan, the key-image path and
+    the ring arena as the bench ran them -- and the segment() logits are compared.  The top-k sets are compared per
+    query; where they differ, the CUDA choice is checked against the float64 direct-form ground truth (a near-tie the
+    reference's fp32 three-term expansion cannot resolve) and adopted by the oracle, as in the teacher-forced tests."""
+    import cutie_b200.kernels as K_
+    from oracle.cpu_core import OracleCore
+    from oracle.state_sync import SelectionReconciler, export_state_to_oracle
+    t0 = time.perf_counter()
+    oc = export_state_to_oracle(proc, OracleCore(make_net(cfg), cfg))     # un-optimised CPU copy of the same weights
+    rec = SelectionReconciler(cfg.top_k, max_frac=0.05)
+    oc.selection_hook = rec
+    orig = K_.affinity_topk
+
+    def spy(*a, **k):
+        out = orig(*a, **k)
+        rec.gpu_idx = out[0].clone()
+        return out
+    K_.affinity_topk = spy
+    try:
+        with torch.inference_mode():
+            proc.step(frame.to(dev))
+            torch.cuda.synchronize(dev)
+            threads = torch.get_num_threads()
+            torch.set_num_threads(usable_cpus())
+            oc.step(frame)
+            torch.set_num_threads(threads)
+    finally:
+        K_.affinity_topk = orig
+    diff = float((proc.last_logits.cpu() - oc.last_logits).abs().max())
+    out = {'max_abs_logit_diff': diff, 'within_1e-3': diff < 1e-3, 'queries': rec.queries,
+           'topk_set_equal': rec.flips == 0, 'topk_sets_differing': rec.flips,
+           'differing_sets_valid_vs_float64': True,            # SelectionReconciler raises if one is not
+           'memory_tokens': proc.memory.work_mem.size(0), 'seconds': time.perf_counter() - t0,
+           'what': 'one teacher-forced frame after the timed region: CUDA path vs oracle/cpu_core.py from the same live state'}
+    log(f'[parity] {out}')
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_cpu_port(args, wl, max_seconds, steps, warmup):
+    """The reference's algorithm on the host cores as restated by oracle/cpu_core.py (pinned to the reference by
+    tests/test_oracle_golden.py): same weights, same synthetic video, same pre-filled bank.  kind = "port"."""
     from oracle.cpu_core import OracleCore
     from oracle.synth import synthetic_video
     cfg = make_cfg(wl)
@@ -487,114 +443,178 @@ def run_cpu_reference(args, wl, max_seconds, steps, warmup):
     return per_frame
 
 
+def run_cpu_reference(args, wl, max_seconds, steps, warmup, threads):
+    """The UNMODIFIED reference (baseline/_ref) on the host cores, in a child process (baseline/ref_bench_child.py).
+    Returns (per-frame seconds, info) or (None, why) when no reference tree travelled with the repo."""
+    from oracle import ref_harness as rh
+    if not rh.available():
+        return None, 'no reference tree (baseline/_ref is created by __graft_entry__.build() where /root/reference exists)'
+    job = dict(H=wl['H'], W=wl['W'], K=wl['K'], mem_frames=wl['mem_frames'], top_k=wl['top_k'], steps=steps, warmup=warmup,
+               max_seconds=max_seconds, threads=threads)
+    env = dict(os.environ, CUTIE_REFERENCE_ROOT=rh.REF_ROOT)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'baseline', 'ref_bench_child.py'), json.dumps(job)], env=env,
+                       stdout=subprocess.PIPE, stderr=None, text=True, timeout=max_seconds * 4 + 900)
+    if r.returncode != 0:
+        return None, f'reference child exited {r.returncode}'
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    return out['per_frame_s'], out
+
+
+def reference_arm(args, wl, config):
+    """bench.py --impl reference: the reference's own implementation of the path on the box's host cores."""
+    cores = usable_cpus()
+    torch.set_num_threads(cores)
+    budget = max(args.cpu_seconds, 60.0)
+    per, info = run_cpu_reference(args, wl, budget, args.steps, min(args.warmup, 1), cores)
+    kind, note = 'reference', None
+    calib = None
+    if not per:
+        log(f'[reference arm] {info}; timing the oracle port instead')
+        kind, note = 'port', str(info)
+        per = run_cpu_port(args, wl, budget, args.steps, min(args.warmup, 1))
+    elif not args.no_port_calibration:
+        # how the oracle port (the in-run cpu_baseline of the other arm) compares with the real thing on this box
+        pp = run_cpu_port(args, wl, 60.0, 2, 1)
+        calib = {'port_frames_per_s': len(pp) / sum(pp), 'reference_frames_per_s': len(per) / sum(per), 'port_frames': len(pp)}
+    fps = len(per) / sum(per)
+    line = {'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': args.gpus,
+            'steps': len(per), 'warmup': min(args.warmup, 1), 'ms_per_step': 1000 * sum(per) / len(per),
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': config,
+            'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': kind,
+                             'sample': f'{len(per)} full frame(s) of the same workload (time-bounded; {args.steps} requested) '
+                                       + ('through the unmodified reference (baseline/_ref) InferenceCore.step'
+                                          if kind == 'reference' else 'through oracle/cpu_core.py'),
+                             'note': note, 'port_calibration': calib},
+            'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    emit(line)
+
+
+# ---------------------------------------------------------------------------------------------------
+def sharded_read_bench(rank, world, dev):
+    """BASELINE.json configs[4] on the N ranks of the scaling run: 1080p queries (8160), 10 objects (rounded up to a
+    multiple of N), a 50 000-key bank sharded 50 000/N keys per rank; local top-k -> NCCL all-gather of (similarity, global
+    index) candidates -> merge -> local partial readout -> NCCL all-reduce (replicated result) or reduce-scatter over
+    objects (object-sharded continuation).  Asserts bit-identity of the selection and weights with rank 0's unsharded read."""
+    import torch.distributed as dist
+    import cutie_b200.kernels as K_
+    from cutie_b200.inference.sharded import shard_bounds, sharded_topk
+    n_total, Q, K, top_k, B = 50000, 8160, 10, 30, 1
+    K = -(-K // world) * world                                   # reduce-scatter over objects needs K % N == 0
+    g = torch.Generator().manual_seed(7)
+    key = torch.randn(B, n_total, 64, generator=g)
+    shr = 1 + torch.randn(B, n_total, generator=g) ** 2
+    qk = torch.randn(B, 64, Q, generator=g).to(dev)
+    qe = torch.sigmoid(torch.randn(B, 64, Q, generator=g)).to(dev)
+    lo, hi = shard_bounds(n_total, world, rank)
+    gl = torch.Generator().manual_seed(100 + rank)
+    vals_local = [torch.randn(B, hi - lo, 256, generator=gl).to(dev) for _ in range(K)]
+    seg = K_.BankSegment(key[:, lo:hi].to(dev), shr[:, lo:hi].to(dev), tuple(vals_local))
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    res = {'keys': n_total, 'keys_per_rank': hi - lo, 'queries': Q, 'objects': K, 'ranks': world}
+    with torch.inference_mode():
+        def one(mode):
+            e = [ev() for _ in range(4)]
+            e[0].record()
+            idx_l, w_l, idx, w = sharded_topk([seg], lo, n_total, qk, qe, top_k)
+            e[1].record()
+            part = K_.readout_gather(idx_l, w_l, [seg])          # [B, K, 256, Q] partial sums over this rank's winners
+            e[2].record()
+            if mode == 'all_reduce':
+                dist.all_reduce(part, op=dist.ReduceOp.SUM)
+                out = part
+            else:
+                out = torch.empty(K // world * 256 * Q, device=dev)     # this rank's K/N objects of the summed readout
+                dist.reduce_scatter_tensor(out, part[0].contiguous().view(-1), op=dist.ReduceOp.SUM)
+            e[3].record()
+            return e, idx, w, out
+        for mode in ('all_reduce', 'reduce_scatter'):
+            for _ in range(3):
+                one(mode)
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+            t = [[], [], []]
+            for _ in range(10):
+                e, idx, w, out = one(mode)
+                torch.cuda.synchronize(dev)
+                for i in range(3):
+                    t[i].append(e[i].elapsed_time(e[i + 1]))
+            tm = torch.tensor([sum(x) / len(x) for x in t], dtype=torch.float64, device=dev)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            res[mode] = {'topk_allgather_merge_ms': float(tm[0]), 'local_gather_ms': float(tm[1]),
+                         'collective_ms': float(tm[2]), 'total_ms': float(tm.sum())}
+        res['allgather_bytes_per_rank'] = int(idx.numel() * 8)
+        res['readout_bytes'] = int(B * K * 256 * Q * 4)
+        # bit-identity with the unsharded read (rank 0 holds the whole key bank for the check)
+        ok = torch.ones(1, device=dev)
+        if rank == 0:
+            full = K_.BankSegment(key.to(dev), shr.to(dev), ())
+            ridx, rw, _ = K_.affinity_topk([full], qk, qe, top_k)
+            ok[0] = float(torch.equal(idx, ridx) and torch.equal(w, rw))
+        dist.broadcast(ok, 0)
+        res['bit_identical_to_unsharded'] = bool(ok.item())
+    res['limiting'] = max(('topk_allgather_merge_ms', 'local_gather_ms', 'collective_ms'),
+                          key=lambda k: res['reduce_scatter'][k])
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=40)
+    ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-parity-check', action='store_true')
+    ap.add_argument('--no-port-calibration', action='store_true')
     ap.add_argument('--no-optimize', action='store_true', help='skip CUTIE.optimize_for_inference()')
+    ap.add_argument('--no-cudnn-benchmark', action='store_true', help='cuDNN heuristics instead of its autotuner')
     ap.add_argument('--phase-timing', action='store_true', help='per-launch device times inside cutie_affinity_topk')
-    ap.add_argument('--no-key-image', action='store_true', help='convert memory keys inside the filter (no operand image)')
     ap.add_argument('--no-graphs', action='store_true', help='eager launches only (no CUDA-graph frame regions)')
-    ap.add_argument('--no-lookahead', action='store_true',
-                    help='do not run the next frame\'s image encoder on a side stream (step(..., next_image=...))')
-    ap.add_argument('--no-fuse-glue', action='store_true',
-                    help='keep area down-sampling / CAResBlock tail / sensory gates as ATen launches')
-    ap.add_argument('--no-fuse-epilogues', action='store_true',
-                    help='keep convolution, bias add and ReLU as three launches (no cuDNN fused conv-bias-activation)')
+    ap.add_argument('--no-lookahead', action='store_true', help='skip the extension arm step(..., next_image=...)')
+    ap.add_argument('--no-sharded-read', action='store_true', help='skip the key-sharded read benchmark at N > 1')
     ap.add_argument('--cpu-seconds', type=float, default=150.0)
-    ap.add_argument('--preflight', action='store_true', help=argparse.SUPPRESS)
-    ap.add_argument('--skip-preflight', action='store_true',
-                    help='do not check the optional launch-saving forms in a child process first')
-    ap.add_argument('--fallback-reason', default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
-    if args.preflight:
-        sys.exit(preflight(int(os.environ.get('LOCAL_RANK', 0))))
     if args.warmup < 3:
         args.warmup = 3
-    if args.impl == 'ours' and not args.no_graphs:
-        # every CUDA-graph variant must exist before the timed region: two capture slots (the encoder look-ahead
-        # alternates them) x {encoder, segment, mask encoder}; memory frames come every 5th step
-        args.warmup = max(args.warmup, 11)
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))
-    HW = (wl['H'] // 16) * (-(-wl['W'] // 16))
-    config = {'workload': f"{args.workload}: {wl['desc']}", 'resolution': [wl['H'], wl['W']], 'objects': wl['K'],
-              'tokens_per_frame': HW, 'memory_tokens': (wl['mem_frames'] - 1) * HW, 'top_k': wl['top_k'],
-              'mem_every': 5, 'streams': world, 'parallelism': f'{world} independent streams (1 per GPU)',
-              'l2': 'no flush: the bank scanned every frame is larger than the 126 MB L2'
-                    if args.workload == 'cfg2' else 'bank fits L2 (north-star size); stated, not flushed',
-              'weights': 'seeded random init (no checkpoint offline)',
-              'cuda_graphs': (not args.no_graphs) and args.impl == 'ours',
-              'encoder_trunks': 'BN folded, channels_last' if (not args.no_optimize and args.impl == 'ours') else 'as loaded'}
+    HW = tokens_per_frame(wl)
+    config = base_config(args, wl, world)
 
     if args.impl == 'reference':
-        if rank != 0:
-            return
-        cores = usable_cpus()
-        torch.set_num_threads(cores)
-        per = run_cpu_reference(args, wl, max_seconds=max(args.cpu_seconds, 60.0), steps=args.steps,
-                                warmup=min(args.warmup, 1))
-        fps = len(per) / sum(per)
-        line = {'impl': 'reference', 'metric': 'frames/sec @480p 3-obj', 'value': fps, 'unit': 'frames/s',
-                'n_gpus': args.gpus, 'steps': len(per), 'warmup': min(args.warmup, 1),
-                'ms_per_step': 1000 * sum(per) / len(per), 'higher_is_better': True, 'scaling': 'weak',
-                'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': config,
-                'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': torch.get_num_threads(), 'kind': 'port',
-                                 'sample': f'{len(per)} full frame(s) of the same workload (time-bounded; '
-                                           f'{args.steps} requested)'},
-                'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-                'gpu_launches': 0}
-        emit(line)
+        if rank == 0:
+            reference_arm(args, wl, config)
         return
 
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a CUDA device: there is no CPU fallback for the product path '
                          '(use --impl reference for the CPU arm)')
-    # The optional launch-saving forms (cuDNN fused epilogues, cutie_bias_act, glue kernels) are checked against
-    # PyTorch's own launches in a child process first; a failed check only switches THEM off for this run.
-    optional = {'checked': False, 'note': args.fallback_reason or 'not checked'}
-    wants_optional = (not args.no_optimize and not (args.no_fuse_epilogues and args.no_fuse_glue)) or \
-                     not (args.no_lookahead or args.no_graphs)
-    if wants_optional and not args.skip_preflight and not args.fallback_reason:
-        ok, note = run_preflight(local)
-        optional = {'checked': True, 'note': note}
-        if not ok:
-            log(f'[rank {rank}] optional fused forms disabled: {note}')
-            args.no_fuse_epilogues = args.no_fuse_glue = args.no_lookahead = True
     dev = torch.device('cuda', local)
     torch.cuda.set_device(dev)
     if world > 1:
         torch.distributed.init_process_group('nccl', device_id=dev)
-    try:
-        res = run_ours(args, wl, rank, world, dev)
-    except Exception as e:                               # noqa: BLE001
-        # single process only: start over in a fresh process (fresh CUDA context) with PyTorch's launches for the
-        # optional stages; a second failure, or any failure under torchrun, is fatal
-        if world == 1 and wants_optional and not args.fallback_reason:
+    res = run_ours(args, wl, rank, world, dev)
+    sharded = None
+    if world > 1 and not args.no_sharded_read:
+        try:
+            sharded = sharded_read_bench(rank, world, dev)
+        except Exception as e:                                   # noqa: BLE001 -- reported in the line, never hidden
             import traceback
             traceback.print_exc()
-            reason = f'{type(e).__name__}: {e}'[:200].replace('\n', ' ')
-            log(f'[bench] optimised run failed ({reason}); re-running with --no-fuse-epilogues --no-fuse-glue')
-            os.environ['CUTIE_BENCH_STDOUT_FD'] = str(_REAL_STDOUT)
-            argv = [sys.executable, os.path.abspath(__file__)] + sys.argv[1:] + \
-                   ['--no-fuse-epilogues', '--no-fuse-glue', '--no-lookahead', '--fallback-reason', reason]
-            os.execv(sys.executable, argv)
-        raise
-    optional['conv_epilogues'] = not args.no_optimize and not args.no_fuse_epilogues
-    optional['glue_kernels'] = not args.no_optimize and not args.no_fuse_glue
+            sharded = {'error': f'{type(e).__name__}: {e}'[:300]}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         torch.set_num_threads(usable_cpus())
-        per = run_cpu_reference(args, wl, max_seconds=40.0, steps=1, warmup=1)
+        per = run_cpu_port(args, wl, max_seconds=40.0, steps=1, warmup=1)
         cpu = {'value': len(per) / sum(per), 'unit': 'frames/s', 'cores': torch.get_num_threads(), 'kind': 'port',
-               'sample': f'{len(per)} full frame of the same workload (same weights, same pre-filled bank) '
-                         f'through oracle/cpu_core.py, after one untimed warm-up frame'}
+               'sample': f'{len(per)} full frame of the same workload (same weights, same pre-filled bank) through '
+                         f'oracle/cpu_core.py, after one untimed warm-up frame; `bench.py --impl reference` times the '
+                         f'unmodified reference (baseline/_ref) and calibrates this port against it'}
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
@@ -605,73 +625,68 @@ def main():
     if os.path.exists(pk):
         peaks = dict(json.load(open(pk)), src='measured')
     N = res['n_tokens']
+    K = args.steps
     scan = res['kernel_ms'].get('affinity_topk', [])
     scan_ms = sum(scan) / len(scan) if scan else None
-    flops = 2.0 * N * 128 * HW                       # one K=128 contraction [mk^2|mk].[−qe;2qk.qe]
+    flops = 2.0 * N * 128 * HW                       # one K=128 contraction [mk^2|mk].[-qe;2qk.qe]
     bytes_alg = N * 65 * 4 + HW * 128 * 4 + HW * 32 * 8
     gather = res['kernel_ms'].get('readout_gather', [])
     gather_ms = sum(gather) / len(gather) if gather else None
     gather_bytes = min(N, HW * wl['top_k']) * wl['K'] * 256 * 4 + HW * wl['K'] * 256 * 4 + HW * 32 * 8
     tensor_bound = flops / (peaks['bf16_tflops_sustained'] * 1e12) > bytes_alg / (peaks['hbm_gbs'] * 1e9)
-    # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of this workload
     traffic, traffic_note = None, None
-    tj = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    tj = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')       # dram bytes of one `ncu --set full` capture (per launch)
     if os.path.exists(tj) and args.workload == 'cfg2':
         t = json.load(open(tj))
         traffic, traffic_note = t.get('affinity_topk_dram_bytes'), t.get('note')
+    roof = None
     if scan_ms:
         if tensor_bound:
             ach = flops / (scan_ms * 1e-3) / 1e12
-            roof = {'bound': 'tensor', 'kernel': 'cutie_affinity_topk = 3 x affinity_tc_filter_kernel (tcgen05 kind::tf32; the stride-1 level '
-                              'fed by bulk copies of the key operand image) + 2 x level_select + affinity_rerank_kernel (exact fp32)',
+            roof = {'bound': 'tensor', 'kernel': 'cutie_affinity_topk (tcgen05 candidate filter over the key operand image + '
+                                                 'exact fp32 re-rank; csrc/affinity*.cu)',
                     'achieved': ach, 'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
                     'frac': ach / peaks['bf16_tflops_sustained'], 'traffic': traffic, 'traffic_note': traffic_note,
                     'peak_source': f"{peaks['src']} bf16 sustained (kernel timed inside a long step)",
                     'algorithmic_flops_per_launch': flops, 'avg_launch_ms': scan_ms,
                     'hbm_view': {'algorithmic_bytes': bytes_alg, 'achieved_gbs': bytes_alg / (scan_ms * 1e-3) / 1e9,
-                                 'frac': bytes_alg / (scan_ms * 1e-3) / 1e9 / peaks['hbm_gbs']},
-                    'note': 'algorithmic flops = one K=128 contraction over the whole bank; the TF32 filter levels execute 1.07x '
-                            'that (nested samples) at half the bf16 rate, the exact re-rank touches ~540 tokens/query'}
+                                 'frac': bytes_alg / (scan_ms * 1e-3) / 1e9 / peaks['hbm_gbs']}}
         else:
             ach = bytes_alg / (scan_ms * 1e-3) / 1e9
-            roof = {'bound': 'hbm', 'kernel': 'affinity_scan_kernel+topk_merge_kernel (cutie_affinity_topk)',
-                    'achieved': ach, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': ach / peaks['hbm_gbs'],
-                    'traffic': None, 'peak_source': f"{peaks['src']} copy bandwidth",
-                    'algorithmic_bytes_per_launch': bytes_alg, 'avg_launch_ms': scan_ms}
-        solo = res.get('solo_ms', {}).get('affinity_topk')
-        if solo:
-            s_ms = sum(solo) / len(solo)
-            roof['no_overlap'] = {'avg_launch_ms': s_ms,
-                                  'achieved': (flops / (s_ms * 1e-3) / 1e12) if tensor_bound else bytes_alg / (s_ms * 1e-3) / 1e9,
-                                  'note': 'same kernel over 10 extra steps WITHOUT the encoder look-ahead: `achieved` above is '
-                                          'measured in the timed region, where the next frame\'s encoder graph shares the GPU'}
-            roof['no_overlap']['frac'] = roof['no_overlap']['achieved'] / roof['peak']
+            roof = {'bound': 'hbm', 'kernel': 'cutie_affinity_topk', 'achieved': ach, 'peak': peaks['hbm_gbs'],
+                    'unit': 'GB/s', 'frac': ach / peaks['hbm_gbs'], 'traffic': None,
+                    'peak_source': f"{peaks['src']} copy bandwidth", 'algorithmic_bytes_per_launch': bytes_alg,
+                    'avg_launch_ms': scan_ms}
         if gather_ms:
             roof['readout_gather'] = {'bound': 'hbm', 'algorithmic_bytes': gather_bytes, 'avg_launch_ms': gather_ms,
                                       'achieved_gbs': gather_bytes / (gather_ms * 1e-3) / 1e9,
                                       'frac': gather_bytes / (gather_ms * 1e-3) / 1e9 / peaks['hbm_gbs']}
-    else:
-        roof = None
     kshare = {k: {'avg_ms': sum(v) / len(v), 'p50_ms': sorted(v)[len(v) // 2], 'max_ms': max(v),
-                  'calls_per_step': len(v) / args.steps,
-                  'share_of_step': sum(v) / res['ms_total']} for k, v in res['kernel_ms'].items()}
-    fps = world * args.steps / (res['ms_total'] * 1e-3)
-    fps_e2e = world * args.steps / (res['ms_e2e'] * 1e-3)
-    line = {'metric': 'frames/sec @480p 3-obj', 'value': fps, 'unit': 'frames/s', 'n_gpus': world,
-            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': res['ms_total'] / args.steps,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': config, 'clocks': res['clocks'],
+                  'calls_per_step': len(v) / K, 'share_of_step': sum(v) / res['ms_total']}
+              for k, v in res['kernel_ms'].items()}
+    fps = world * K / (res['ms_total'] * 1e-3)
+    fps_e2e = world * K / (res['ms_e2e'] * 1e-3)
+    line = {'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': world, 'steps': K, 'warmup': args.warmup,
+            'ms_per_step': res['ms_total'] / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic', 'config': config, 'clocks': res['clocks'],
             'e2e': {'value': fps_e2e, 'unit': 'frames/s', 'h2d_bytes_per_step': res['h2d'],
-                    'd2h_bytes_per_step': res['d2h'], 'ms_per_step': res['ms_e2e'] / args.steps},
-            'gpu_launches': res['launches'], 'roofline': roof, 'cpu_baseline': cpu, 'kernels': kshare,
+                    'd2h_bytes_per_step': res['d2h'], 'ms_per_step': res['ms_e2e'] / K},
+            'gpu_launches': res['launches'], 'roofline': roof, 'cpu_baseline': cpu,
+            'parity_check': res.get('parity'), 'latency_ms': percentiles(res['per_step']),
+            'untimed_steps_before_timed_region': res['untimed'],
+            'api': 'InferenceCore.step(image) -- the reference signature (scripting_demo.py / eval_vos.py unchanged)',
+            'with_encoder_lookahead': None if not res['lookahead'] else {
+                'what': 'extension step(image, next_image=...): the next frame\'s encoder graph on a side stream; NOT the '
+                        'reference signature, reported beside the headline',
+                'value': world * K / (res['lookahead']['ms_total'] * 1e-3),
+                'e2e': world * K / (res['lookahead']['ms_e2e'] * 1e-3), 'unit': 'frames/s'},
+            'kernels': kshare,
             'host_enqueue_ms_per_step': {'device_arm': res['host_ms'][0], 'e2e_arm': res['host_ms'][1]},
-            'affinity_phases_ms': res['phases'] or None, 'key_image_levels': res['image_levels']}
-    line['config']['conv_epilogues'] = res['epilogues']     # which conv+bias(+add)+ReLU calls won their on-device trial
-    line['config']['glue_ops'] = res['glue']                 # which ATen chains were replaced by cutie_b200 kernels
-    line['config']['optional_forms'] = optional               # pre-flight verdict for the two entries above
-    line['config']['encoder_lookahead'] = res['lookahead']    # next frame's encoder graph on a side stream (step(next_image=))
-    line['config']['encoder_lookahead_ab_ms'] = res['lookahead_ab']
-    line['warmup'] = res['untimed']                            # every untimed step before the timed region (warm-up + A/B)
+            'affinity_phases_ms': res.get('phases'), 'key_image_levels': res['image_levels'],
+            'build': {'cuda_graphs': not args.no_graphs, 'optimize_for_inference': not args.no_optimize,
+                      'cudnn_benchmark': not args.no_cudnn_benchmark, 'cudnn_allow_tf32': False, 'matmul_allow_tf32': False,
+                      'conv_epilogues': res['epilogues'], 'glue_dispatch': res['glue']},
+            'sharded_read': sharded}
     emit(line)
 
 

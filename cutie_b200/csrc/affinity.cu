@@ -450,11 +450,10 @@ static int run_exact(const ScanParams& base, long long B, int nsplit, int* out_i
   if ((long long)sp.tiles_per_split * TK >= (1ll << 24)) return fail(-1, "%s: split too long", "run_exact");
   dim3 grid((unsigned)((sp.Q + TQ - 1) / TQ), (unsigned)nsplit, (unsigned)B);
   const size_t smem = sizeof(ScanSmem);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[64] = {};
+  if (first_use_on_device(attr_done)) {
     cudaFuncSetAttribute(affinity_scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(affinity_scan_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_done = true;
   }
   if (sp.kpad == 32)
     affinity_scan_kernel<1><<<grid, NT, smem, st>>>(sp);

@@ -539,14 +539,13 @@ __global__ void __launch_bounds__(128) affinity_rerank_kernel(const RerankParams
 size_t tc_filter_smem_bytes() { return (size_t)3 * OPER_BYTES + sizeof(TcSmemTail) + 64; }
 
 int launch_tc_filter(const TcFilterParams& p, long long B, cudaStream_t st) {
-  static bool attr_done = false;
   const size_t smem = tc_filter_smem_bytes();
-  if (!attr_done) {
+  static bool attr_done[64] = {};
+  if (first_use_on_device(attr_done)) {
     cudaFuncSetAttribute(affinity_tc_filter_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(affinity_tc_filter_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(affinity_tc_filter_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(affinity_tc_filter_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_done = true;
   }
   dim3 grid((unsigned)((p.Q + QT - 1) / QT), (unsigned)p.nsplit, (unsigned)B);
   if (p.use_img) {

@@ -2,6 +2,8 @@
 // of 32, 16 object queries; the pixel axis (HW) and the number of objects are free.
 // All pixel-side tensors are channel-major [B*K, 256, HW] (what the cuDNN convolutions around these
 // kernels produce and consume), so lanes run along the contiguous pixel axis.
+// This file: the query-side kernels (skinny linears, head folds, 16x16 self attention) and the aux-mask pass; the two
+// cross attentions run on the tensor cores (qt_tc.cu).
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -261,262 +263,6 @@ __global__ void __launch_bounds__(256) qt_aux_mask_kernel(const float* __restric
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// read_from_pixel core, pass 1: grid (splits, heads, BK); each CTA streams its pixel range in chunks of
-// 32, online softmax for the 16 rows of one head, Z[16][256] accumulators (thread == channel).
-struct P2QParams {
-  const float* qfold;   // [BK*16, 8, 256]
-  const float* pixel;   // [BK, 256, HW]
-  const float* pe;
-  const uint8_t* fg;    // [BK, HW]
-  const int* fg_count;  // [BK]
-  long long HW;
-  int splits, chunks_per_split;
-  float* ws;            // [BK][H][splits][16*(256+2)]
-};
-
-constexpr int P2Q_WS = NQ * (E_ + 2);
-
-__global__ void __launch_bounds__(256) qt_p2q_partial_kernel(const P2QParams p) {
-  extern __shared__ __align__(16) float dsm[];
-  float(*qf)[E_] = reinterpret_cast<float(*)[E_]>(dsm);                       // [16][256]
-  float(*kin)[33] = reinterpret_cast<float(*)[33]>(dsm + NQ * E_);            // [256][33]
-  float(*pix)[33] = reinterpret_cast<float(*)[33]>(dsm + NQ * E_ + E_ * 33);  // [256][33]
-  float(*ps)[20] = reinterpret_cast<float(*)[20]>(dsm + NQ * E_ + 2 * E_ * 33);  // [32 pixels][16 rows (+4 pad)]
-  float* sc = dsm + NQ * E_ + 2 * E_ * 33 + 32 * 20;                          // [16] rescale factors
-  float* rm = sc + NQ;                                                        // running max
-  float* rl = rm + NQ;                                                        // running sum
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int split = blockIdx.x, h = blockIdx.y;
-  const long long bk = blockIdx.z;
-  for (int i = tid; i < NQ * E_; i += 256) {
-    const int r = i / E_, c = i % E_;
-    qf[r][c] = p.qfold[((bk * NQ + r) * H_ + h) * E_ + c];
-  }
-  if (tid < NQ) { rm[tid] = -CUDART_INF_F; rl[tid] = 0.f; }
-  const int cnt = p.fg_count[bk];
-  const bool open_fg = (cnt == 0);           // no foreground pixel at all: foreground queries see everything
-  const bool open_bg = (cnt == (int)p.HW);   // everything foreground: background queries see everything
-  float z[NQ];
-#pragma unroll
-  for (int i = 0; i < NQ; ++i) z[i] = 0.f;
-  const float* pbase = p.pixel + bk * E_ * p.HW;
-  const float* ebase = p.pe + bk * E_ * p.HW;
-  const long long p_begin = (long long)split * p.chunks_per_split * 32;
-  for (int ch = 0; ch < p.chunks_per_split; ++ch) {
-    const long long p0 = p_begin + (long long)ch * 32;
-    if (p0 >= p.HW) break;
-    __syncthreads();
-    const long long px = p0 + lane;
-    for (int c = warp; c < E_; c += 8) {
-      float a = 0.f, e = 0.f;
-      if (px < p.HW) { a = pbase[(long long)c * p.HW + px]; e = ebase[(long long)c * p.HW + px]; }
-      pix[c][lane] = a;
-      kin[c][lane] = a + e;
-    }
-    __syncthreads();
-    // scores for rows (warp, warp+8) x pixel lane
-    float s0 = 0.f, s1 = 0.f;
-    const float4* q0 = reinterpret_cast<const float4*>(&qf[warp][0]);
-    const float4* q1 = reinterpret_cast<const float4*>(&qf[warp + 8][0]);
-#pragma unroll 4
-    for (int c4 = 0; c4 < E_ / 4; ++c4) {
-      const float4 a = q0[c4], b4 = q1[c4];
-      const float k0 = kin[4 * c4][lane], k1 = kin[4 * c4 + 1][lane], k2 = kin[4 * c4 + 2][lane], k3 = kin[4 * c4 + 3][lane];
-      s0 = fmaf(a.x, k0, s0); s1 = fmaf(b4.x, k0, s1);
-      s0 = fmaf(a.y, k1, s0); s1 = fmaf(b4.y, k1, s1);
-      s0 = fmaf(a.z, k2, s0); s1 = fmaf(b4.z, k2, s1);
-      s0 = fmaf(a.w, k3, s0); s1 = fmaf(b4.w, k3, s1);
-    }
-    const bool f = (px < p.HW) ? (p.fg[bk * p.HW + px] != 0) : false;
-    const bool ok0 = (px < p.HW) && (f || open_fg);     // rows 0..7: foreground queries
-    const bool ok1 = (px < p.HW) && (!f || open_bg);    // rows 8..15: background queries
-    s0 = ok0 ? s0 : -CUDART_INF_F;
-    s1 = ok1 ? s1 : -CUDART_INF_F;
-    {
-      const float cm = warp_max(s0);
-      const float mo = rm[warp], mn = fmaxf(mo, cm);
-      const float e = (mn == -CUDART_INF_F) ? 0.f : expf(s0 - mn);
-      const float scl = (mo == -CUDART_INF_F) ? 0.f : expf(mo - mn);
-      const float su = warp_sum(e);
-      ps[lane][warp] = e;
-      if (lane == 0) { sc[warp] = scl; rl[warp] = rl[warp] * scl + su; rm[warp] = mn; }
-    }
-    {
-      const float cm = warp_max(s1);
-      const float mo = rm[warp + 8], mn = fmaxf(mo, cm);
-      const float e = (mn == -CUDART_INF_F) ? 0.f : expf(s1 - mn);
-      const float scl = (mo == -CUDART_INF_F) ? 0.f : expf(mo - mn);
-      const float su = warp_sum(e);
-      ps[lane][warp + 8] = e;
-      if (lane == 0) { sc[warp + 8] = scl; rl[warp + 8] = rl[warp + 8] * scl + su; rm[warp + 8] = mn; }
-    }
-    __syncthreads();
-    // Z[i][c=tid] = Z*scale + sum_p P[i][p] * pix[c][p]
-#pragma unroll
-    for (int i = 0; i < NQ; ++i) z[i] *= sc[i];
-#pragma unroll 4
-    for (int pp = 0; pp < 32; ++pp) {
-      const float v = pix[tid][pp];
-      const float4* pr = reinterpret_cast<const float4*>(&ps[pp][0]);      // broadcast LDS.128: 4 rows per load
-#pragma unroll
-      for (int i4 = 0; i4 < NQ / 4; ++i4) {
-        const float4 w = pr[i4];
-        z[4 * i4] = fmaf(w.x, v, z[4 * i4]);
-        z[4 * i4 + 1] = fmaf(w.y, v, z[4 * i4 + 1]);
-        z[4 * i4 + 2] = fmaf(w.z, v, z[4 * i4 + 2]);
-        z[4 * i4 + 3] = fmaf(w.w, v, z[4 * i4 + 3]);
-      }
-    }
-  }
-  __syncthreads();
-  float* w = p.ws + (((bk * H_ + h) * p.splits) + split) * P2Q_WS;
-#pragma unroll
-  for (int i = 0; i < NQ; ++i) w[i * E_ + tid] = z[i];
-  if (tid < NQ) { w[NQ * E_ + tid] = rm[tid]; w[NQ * E_ + NQ + tid] = rl[tid]; }
-}
-
-// pass 2: grid (16 query rows, heads, BK): merge the splits of one attention row, normalise, apply the per-head
-// value projection (8 warps x 4 outputs, lanes across the 256 input channels).
-__global__ void __launch_bounds__(256) qt_p2q_combine_kernel(const float* __restrict__ ws, int splits,
-                                                             const float* __restrict__ wv, long long ldwv,
-                                                             const float* __restrict__ bv, float* __restrict__ attn) {
-  __shared__ float zn[E_];
-  __shared__ float coef[64];   // per split: exp(m_s - M) / L
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int i = blockIdx.x, h = blockIdx.y;
-  const long long bk = blockIdx.z;
-  const float* base = ws + ((bk * H_ + h) * splits) * (long long)P2Q_WS;
-  if (warp == 0) {
-    float M = -CUDART_INF_F;
-    for (int s = lane; s < splits; s += 32) M = fmaxf(M, base[(long long)s * P2Q_WS + NQ * E_ + i]);
-    M = warp_max(M);
-    float L = 0.f;
-    for (int s = lane; s < splits; s += 32) {
-      const float ms = base[(long long)s * P2Q_WS + NQ * E_ + i];
-      const float f = (ms == -CUDART_INF_F) ? 0.f : expf(ms - M);
-      coef[s] = f;
-      L += f * base[(long long)s * P2Q_WS + NQ * E_ + NQ + i];
-    }
-    L = warp_sum(L);
-    __syncwarp();
-    const float inv = 1.f / L;
-    for (int s = lane; s < splits; s += 32) coef[s] *= inv;
-  }
-  __syncthreads();
-  float acc = 0.f;
-  for (int s = 0; s < splits; ++s) acc = fmaf(coef[s], base[(long long)s * P2Q_WS + i * E_ + tid], acc);
-  zn[tid] = acc;
-  __syncthreads();
-  // attn[(bk*16+i), h*32+e] = zn . wv[h*32+e, :] + bv[h*32+e]
-  for (int e = warp; e < DH; e += 8) {
-    const float* wr = wv + (long long)(h * DH + e) * ldwv;
-    float d = 0.f;
-#pragma unroll
-    for (int c = lane; c < E_; c += 32) d = fmaf(zn[c], wr[c], d);
-    d = warp_sum(d);
-    if (lane == 0) attn[(bk * NQ + i) * E_ + h * DH + e] = d + bv[h * DH + e];
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// read_from_query fused: grid (ceil(HW/32), BK), block 256 (lane == pixel, warp == head in stage A,
-// warp == channel phase in stage B).
-struct Q2PParams {
-  const float* kfold;   // [BK*16, 8, 256]  row r = j*8 + h
-  const float* kdots;   // [BK*16, 8]
-  const float* vfold;   // [BK*16, 8, 256]
-  const float* out_bias;
-  const float* pixel;
-  const float* pe;
-  long long HW;
-  float* out;
-};
-
-__global__ void __launch_bounds__(256) qt_q2p_kernel(const Q2PParams p) {
-  extern __shared__ __align__(16) float dsm[];
-  float(*qin)[33] = reinterpret_cast<float(*)[33]>(dsm);                    // [256][33]
-  float(*stage)[36] = reinterpret_cast<float(*)[36]>(dsm + E_ * 33);        // [128][36]: kfold chunk (A), 16-B rows
-  float(*ps)[33] = reinterpret_cast<float(*)[33]>(dsm + E_ * 33 + 128 * 36);  // [128][33] probabilities
-  float* vf = dsm + E_ * 33 + 128 * 36 + 128 * 33;                           // [32][256] vfold chunk (B)
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const long long bk = blockIdx.y, p0 = (long long)blockIdx.x * 32, px = p0 + lane;
-  const float* pbase = p.pixel + bk * E_ * p.HW;
-  const float* ebase = p.pe + bk * E_ * p.HW;
-  for (int c = warp; c < E_; c += 8) {
-    float v = 0.f;
-    if (px < p.HW) v = pbase[(long long)c * p.HW + px] + ebase[(long long)c * p.HW + px];
-    qin[c][lane] = v;
-  }
-  // ---- stage A: scores for head `warp`, queries j = 0..15 (row r = j*8 + warp) ----
-  float s[NQ];
-#pragma unroll
-  for (int j = 0; j < NQ; ++j) s[j] = 0.f;
-  const float* kf = p.kfold + bk * NQ * H_ * E_;
-  for (int c0 = 0; c0 < E_; c0 += 32) {
-    __syncthreads();
-    for (int r = warp; r < 128; r += 8) stage[r][lane] = kf[(long long)r * E_ + c0 + lane];
-    __syncthreads();
-    // broadcast LDS.128 of four reduction steps per query row: 20 shared loads per 64 FMA
-#pragma unroll 2
-    for (int c4 = 0; c4 < 8; ++c4) {
-      const float x0 = qin[c0 + 4 * c4][lane], x1 = qin[c0 + 4 * c4 + 1][lane];
-      const float x2 = qin[c0 + 4 * c4 + 2][lane], x3 = qin[c0 + 4 * c4 + 3][lane];
-#pragma unroll
-      for (int j = 0; j < NQ; ++j) {
-        const float4 w = *reinterpret_cast<const float4*>(&stage[j * 8 + warp][4 * c4]);
-        s[j] = fmaf(x0, w.x, s[j]);
-        s[j] = fmaf(x1, w.y, s[j]);
-        s[j] = fmaf(x2, w.z, s[j]);
-        s[j] = fmaf(x3, w.w, s[j]);
-      }
-    }
-  }
-  float mx = -CUDART_INF_F;
-#pragma unroll
-  for (int j = 0; j < NQ; ++j) {
-    s[j] += p.kdots[(bk * NQ + j) * H_ + warp];
-    mx = fmaxf(mx, s[j]);
-  }
-  float sum = 0.f;
-#pragma unroll
-  for (int j = 0; j < NQ; ++j) { s[j] = expf(s[j] - mx); sum += s[j]; }
-  const float inv = 1.f / sum;
-#pragma unroll
-  for (int j = 0; j < NQ; ++j) ps[j * 8 + warp][lane] = s[j] * inv;
-  // ---- stage B: out[c][p] = pixel + bias + sum_r P[r][p] * vfold[r][c],  c = 32 warp + v ----
-  float acc[32];
-#pragma unroll
-  for (int v = 0; v < 32; ++v) acc[v] = 0.f;
-  const float* vfg = p.vfold + bk * NQ * H_ * E_;
-  for (int r0 = 0; r0 < 128; r0 += 32) {
-    __syncthreads();
-    for (int i = tid; i < 32 * E_; i += 256) vf[i] = vfg[(long long)r0 * E_ + i];
-    __syncthreads();
-#pragma unroll 2
-    for (int rr = 0; rr < 32; ++rr) {
-      const float pr = ps[r0 + rr][lane];
-      const float4* vr = reinterpret_cast<const float4*>(vf + rr * E_ + warp * 32);
-#pragma unroll
-      for (int v4 = 0; v4 < 8; ++v4) {
-        const float4 w = vr[v4];
-        acc[4 * v4] = fmaf(pr, w.x, acc[4 * v4]);
-        acc[4 * v4 + 1] = fmaf(pr, w.y, acc[4 * v4 + 1]);
-        acc[4 * v4 + 2] = fmaf(pr, w.z, acc[4 * v4 + 2]);
-        acc[4 * v4 + 3] = fmaf(pr, w.w, acc[4 * v4 + 3]);
-      }
-    }
-  }
-  if (px < p.HW) {
-    float* ob = p.out + bk * E_ * p.HW;
-#pragma unroll
-    for (int v = 0; v < 32; ++v) {
-      const int c = warp * 32 + v;
-      ob[(long long)c * p.HW + px] = pbase[(long long)c * p.HW + px] + p.out_bias[c] + acc[v];
-    }
-  }
-}
-
 }  // namespace cutie
 
 using namespace cutie;
@@ -569,66 +315,6 @@ extern "C" int cutie_qt_aux_mask(const float* pixel, const float* w, const float
   CUTIE_REQUIRE(K >= 1 && K <= AUX_MAX_K && B >= 1 && HW >= 1, "1..32 objects");
   dim3 grid((unsigned)((HW + 31) / 32), (unsigned)B);
   qt_aux_mask_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pixel, w, b, K, HW, logits, fg, fg_count);
-  CUTIE_CHECK_LAUNCH();
-  return 0;
-}
-
-extern "C" int cutie_qt_pixel_to_query_splits(int64_t BK, int64_t HW, int num_heads) {
-  const long long chunks = (HW + 31) / 32;
-  long long s = (2 * num_sms() + BK * num_heads - 1) / (BK * num_heads);
-  if (s < 1) s = 1;
-  if (s > chunks) s = chunks;
-  if (s > 64) s = 64;
-  // make every split non-empty
-  const long long cps = (chunks + s - 1) / s;
-  s = (chunks + cps - 1) / cps;
-  return (int)s;
-}
-
-extern "C" int cutie_qt_pixel_to_query(const float* qfold, const float* pixel, const float* pixel_pe,
-                                       const uint8_t* fg, const int32_t* fg_count, const float* wv, int64_t ldwv,
-                                       const float* bv, int64_t BK, int64_t E, int64_t HW, int num_queries,
-                                       int num_heads, int splits, float* workspace, float* attn_out, void* stream) {
-  CUTIE_REQUIRE(qfold && pixel && pixel_pe && fg && fg_count && wv && bv && workspace && attn_out, "null argument");
-  CUTIE_REQUIRE(E == E_ && num_heads == H_ && num_queries == NQ, "embed_dim 256, 8 heads, 16 queries");
-  CUTIE_REQUIRE(splits >= 1 && splits <= 64 && BK >= 1 && HW >= 1, "1..64 splits");
-  P2QParams p;
-  p.qfold = qfold; p.pixel = pixel; p.pe = pixel_pe; p.fg = fg; p.fg_count = fg_count; p.HW = HW;
-  p.splits = splits;
-  const long long chunks = (HW + 31) / 32;
-  p.chunks_per_split = (int)((chunks + splits - 1) / splits);
-  p.ws = workspace;
-  const size_t smem = (size_t)(NQ * E_ + 2 * E_ * 33 + 32 * 20 + 3 * NQ) * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(qt_p2q_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_done = true;
-  }
-  cudaStream_t st = (cudaStream_t)stream;
-  qt_p2q_partial_kernel<<<dim3((unsigned)splits, H_, (unsigned)BK), 256, smem, st>>>(p);
-  CUTIE_CHECK_LAUNCH();
-  qt_p2q_combine_kernel<<<dim3(NQ, H_, (unsigned)BK), 256, 0, st>>>(workspace, splits, wv, ldwv, bv, attn_out);
-  CUTIE_CHECK_LAUNCH();
-  return 0;
-}
-
-extern "C" int cutie_qt_query_to_pixel(const float* kfold, const float* kdots, const float* vfold,
-                                       const float* out_bias, const float* pixel, const float* pixel_pe, int64_t BK,
-                                       int64_t E, int64_t HW, int num_queries, int num_heads, float* out,
-                                       void* stream) {
-  CUTIE_REQUIRE(kfold && kdots && vfold && out_bias && pixel && pixel_pe && out, "null argument");
-  CUTIE_REQUIRE(E == E_ && num_heads == H_ && num_queries == NQ, "embed_dim 256, 8 heads, 16 queries");
-  CUTIE_REQUIRE(BK >= 1 && HW >= 1, "empty");
-  Q2PParams p;
-  p.kfold = kfold; p.kdots = kdots; p.vfold = vfold; p.out_bias = out_bias; p.pixel = pixel; p.pe = pixel_pe;
-  p.HW = HW; p.out = out;
-  const size_t smem = (size_t)(E_ * 33 + 128 * 36 + 128 * 33 + 32 * E_) * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(qt_q2p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_done = true;
-  }
-  qt_q2p_kernel<<<dim3((unsigned)((HW + 31) / 32), (unsigned)BK), 256, smem, (cudaStream_t)stream>>>(p);
   CUTIE_CHECK_LAUNCH();
   return 0;
 }

@@ -57,6 +57,16 @@ class _CudaStreamOps:
         torch.cuda.current_stream().wait_event(ev)
 
 
+def _version_of(t: torch.Tensor):
+    """In-place modification counter of a tensor, or None for inference tensors (created under torch.inference_mode():
+    they carry no counter, so for them a look-ahead hit rests on object identity alone and overwriting an announced
+    inference tensor in place before the next step is outside the contract of step(next_image=...))."""
+    try:
+        return t._version
+    except RuntimeError:
+        return None
+
+
 class EncoderLookahead:
     """Which encoder capture slot holds the current frame's features, and the pending look-ahead (if any).
 
@@ -78,7 +88,13 @@ class EncoderLookahead:
         la, self.pending = self.pending, None
         if la is not None:
             self.ops.main_wait_event(la['done'])
-            if la['ti'] == ti and la['src'] == src_id and la['shape'] == tuple(image.shape):
+            # a hit needs the very memory that was announced, unmodified since: same address / shape / strides, same
+            # in-place version counter (views share their base's), and `pending` holds a reference to the announced
+            # tensor, so its address cannot have been recycled for another frame in between
+            t = la['tensor']
+            if (la['ti'] == ti and src_id.data_ptr() == t.data_ptr() and tuple(src_id.shape) == tuple(t.shape)
+                    and src_id.stride() == t.stride() and la['version'] == _version_of(src_id)
+                    and la['shape'] == tuple(image.shape)):
                 self.slot = la['slot']
                 return la['out'], True
         return self.encode(image, self.slot), False
@@ -92,7 +108,7 @@ class EncoderLookahead:
             img = prepare(next_image)
             out = self.encode(img, slot)
             done = self.ops.record_on_side(dev)
-        self.pending = dict(ti=ti + 1, slot=slot, src=(next_image.data_ptr(), tuple(next_image.shape)),
+        self.pending = dict(ti=ti + 1, slot=slot, tensor=next_image, version=_version_of(next_image),
                             shape=tuple(img.shape), out=out, done=done)
 
 
@@ -194,7 +210,8 @@ class InferenceCore:
             sens_in = self.memory.get_sensory(ids)
             obj_mem = self.memory._get_object_mem_by_ids(ids).unsqueeze(2)
             with K_._call('region:segment_graph', 0):
-                sensory, logits, prob = self._graphs.segment(visual, pix_feat, sens_in, self.last_mask, obj_mem,
+                last_mask = self.memory._get_mask_by_ids(self.last_mask, ids)     # after delete_objects: live channels only
+                sensory, logits, prob = self._graphs.segment(visual, pix_feat, sens_in, last_mask, obj_mem,
                                                              tuple(ms_features), update_sensory)
             logits, prob = logits.clone(), prob.clone()
             if update_sensory:
@@ -238,7 +255,7 @@ class InferenceCore:
         depends on nothing but the image -- is enqueued on a side stream now and overlaps this frame's memory read,
         object transformer and decoder; the next call picks the result up if it is handed the same tensor.  Results
         are identical with or without it."""
-        src_id = (image.data_ptr(), tuple(image.shape))
+        src_id = image               # the caller's tensor itself: a look-ahead hit is decided on its memory + version
         if objects is None and mask is not None:
             assert not idx_mask
             objects = list(range(1, mask.shape[0] + 1))

@@ -76,6 +76,11 @@ def _ptr(t: Optional[torch.Tensor], dtype=torch.float32) -> ctypes.c_void_p:
         return ctypes.c_void_p(0)
     if not t.is_cuda:
         raise KernelError('cutie_b200 kernels need CUDA tensors (no CPU path exists)')
+    if t.device.index != torch.cuda.current_device():
+        # launches go to torch.cuda.current_stream() of the CURRENT device: a tensor living elsewhere would be
+        # dereferenced by a kernel running on the wrong GPU
+        raise KernelError(f'tensor on cuda:{t.device.index} but the current device is cuda:{torch.cuda.current_device()} '
+                          '(wrap the call in torch.cuda.device(tensor.device))')
     if t.dtype != dtype:
         raise KernelError(f'expected {dtype}, got {t.dtype}')
     return ctypes.c_void_p(t.data_ptr())
@@ -630,54 +635,29 @@ def qt_aux_mask(pixel: torch.Tensor, w: torch.Tensor, b: torch.Tensor, B: int, K
 
 def qt_pixel_to_query(qfold: torch.Tensor, pixel: torch.Tensor, pixel_pe: torch.Tensor, fg: torch.Tensor,
                       fg_count: torch.Tensor, wv: torch.Tensor, bv: torch.Tensor, num_queries: int,
-                      num_heads: int = 8, splits: Optional[int] = None) -> torch.Tensor:
-    """read_from_pixel attention core (a11) for all objects/heads:
+                      num_heads: int = 8) -> torch.Tensor:
+    """read_from_pixel attention core (a11) for all objects/heads, on the tensor cores (csrc/qt_tc.cu):
          scores[(i,h), p] = qfold[m=(bk,i), h, :] . (pixel+pixel_pe)[bk, :, p]  (scale pre-folded)
          foreground queries (i < Q/2) see only fg pixels, background queries only non-fg (a15 rules),
          P = softmax_p(scores), Z = P . pixel^T, attn[m, h*d+e] = Z[(i,h), :] . wv[h*d+e, :] + bv[h*d+e]
-    Returns attn [M, E] (to be passed through the output projection by qt_linear).
-    `splits`: how many CTAs share the pixel axis of one (object, head) (flash-style partial softmax + combine);
-    None = the library's heuristic; qt_p2q_split_candidates lists alternatives worth timing."""
+    Returns attn [M, E] (to be passed through the output projection by qt_linear).  One CTA per 64-pixel tile and
+    object (tile-local softmax), then a combine kernel; the tile count is fixed by HW (deterministic)."""
     M, H, E = qfold.shape
     BK, _, HW = pixel.shape
     assert pixel.is_contiguous() and pixel_pe.is_contiguous() and qfold.is_contiguous() and fg.is_contiguous()
     dev = pixel.device
     out = torch.empty(M, E, dtype=torch.float32, device=dev)
     L = lib()
-    if splits is None:
-        L.cutie_qt_pixel_to_query_splits.restype = ctypes.c_int
-        splits = L.cutie_qt_pixel_to_query_splits(_i64(BK), _i64(HW), ctypes.c_int(num_heads))
-    ws = torch.empty(BK * num_heads * splits * num_queries * (E + 2), dtype=torch.float32, device=dev)
-    _L = lib()
+    L.cutie_qt_pixel_to_query_splits.restype = ctypes.c_int
+    L.cutie_qt_pixel_to_query_workspace_floats.restype = ctypes.c_int64
+    splits = L.cutie_qt_pixel_to_query_splits(_i64(BK), _i64(HW), ctypes.c_int(num_heads))
+    ws = torch.empty(int(L.cutie_qt_pixel_to_query_workspace_floats(_i64(BK), _i64(HW))), dtype=torch.float32, device=dev)
     with _call('qt_pixel_to_query', 2):
         st = L.cutie_qt_pixel_to_query(_ptr(qfold), _ptr(pixel), _ptr(pixel_pe), _ptr(fg, torch.uint8),
                                        _ptr(fg_count, torch.int32), _ptr(wv), _i64(wv.stride(0)), _ptr(bv),
                                        _i64(BK), _i64(E), _i64(HW), ctypes.c_int(num_queries), ctypes.c_int(num_heads),
                                        ctypes.c_int(splits), _ptr(ws), _ptr(out), _stream())
     _check(st, 'cutie_qt_pixel_to_query')
-    return out
-
-
-def qt_p2q_split_candidates(BK: int, HW: int, num_heads: int = 8) -> List[int]:
-    """Split counts for qt_pixel_to_query worth an on-device A/B, the library's heuristic first.  The partial kernel
-    runs grid (splits, heads, BK) with ~2 CTAs resident per SM and 32-pixel chunks; the heuristic's
-    ceil(2*SMs / (BK*heads)) can land just above one full wave (480p, 3 objects: 13 x 8 x 3 = 312 CTAs for 296 slots),
-    so the neighbours with one chunk more / fewer per CTA are offered too."""
-    L = lib()
-    L.cutie_qt_pixel_to_query_splits.restype = ctypes.c_int
-    s0 = int(L.cutie_qt_pixel_to_query_splits(_i64(BK), _i64(HW), ctypes.c_int(num_heads)))
-    return split_neighbours(s0, HW)
-
-
-def split_neighbours(s0: int, HW: int) -> List[int]:
-    chunks = (int(HW) + 31) // 32
-    cps0 = -(-chunks // max(s0, 1))
-    out = [s0]
-    for cps in (cps0 + 1, cps0 - 1, cps0 + 2):
-        if cps >= 1:
-            s = min(64, max(1, -(-chunks // cps)))
-            if s not in out:
-                out.append(s)
     return out
 
 

@@ -31,14 +31,14 @@ def resize_objects(g: torch.Tensor, ratio: float, mode: str) -> torch.Tensor:
 
 def area_resize(owner: nn.Module, x: torch.Tensor, size) -> torch.Tensor:
     """F.interpolate(x, size=size, mode='area') for [..., H, W]; an integer-factor reduction goes through
-    cutie_area_pool where `owner.op_trials` (attached by CUTIE.optimize_for_inference) found it faster."""
+    cutie_area_pool where `owner.glue_dispatch` (attached by CUTIE.optimize_for_inference) found it faster."""
     H, W = x.shape[-2:]
     h, w = int(size[0]), int(size[1])
     lead = x.shape[:-2]
 
     def aten():
         return F.interpolate(x.reshape(-1, 1, H, W), size=(h, w), mode='area').reshape(*lead, h, w)
-    t = getattr(owner, 'op_trials', None)
+    t = getattr(owner, 'glue_dispatch', None)
     if t is None or h == 0 or w == 0 or H % h or W % w or H // h != W // w or H // h < 2 or H // h > 64:
         return aten()
     f = H // h
@@ -65,7 +65,7 @@ class ChannelAttnResBlock(nn.Module):
         self.downsample = nn.Identity() if c_in == c_out else nn.Conv2d(c_in, c_out, 1)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        t = getattr(self, 'op_trials', None)
+        t = getattr(self, 'glue_dispatch', None)
         twins = getattr(self, 'cl_twins', None)
         if (t is None or twins is None or x.dim() != 4 or not x.is_contiguous() or x.shape[1] % 4
                 or twins[0].weight.device != x.device):
@@ -100,7 +100,7 @@ class ChannelAttnResBlock(nn.Module):
         def aten():
             gate = self.conv(y.mean(dim=(2, 3)).unsqueeze(1)).sigmoid().transpose(1, 2).unsqueeze(-1)
             return y * gate + skip
-        t = getattr(self, 'op_trials', None)
+        t = getattr(self, 'glue_dispatch', None)
         if t is None:
             return aten()
         # conv1d + sigmoid + mul + add as cutie_eca_scale_add (in place into the fresh convolution output)
@@ -119,7 +119,7 @@ class ObjResBlock(nn.Module):
         self.conv2 = ObjConv2d(c_out, c_out, 3, padding=1)
 
     def forward(self, g):
-        t = getattr(self, 'op_trials', None)
+        t = getattr(self, 'glue_dispatch', None)
         twins = getattr(self, 'cl_twins', None)
         if (t is None or twins is None or g.dim() != 5 or not g.is_contiguous() or g.shape[2] % 4
                 or twins[0].weight.device != g.device):
@@ -206,7 +206,7 @@ class UpsampleBlock(nn.Module):
 
 def gated_update(h: torch.Tensor, v: torch.Tensor, owner: nn.Module = None) -> torch.Tensor:
     """modules.py:37-45: GRU-like update; v carries [forget | update | candidate] along channels.  With
-    `owner.op_trials` attached the eight ATen launches may run as cutie_gated_update."""
+    `owner.glue_dispatch` attached the eight ATen launches may run as cutie_gated_update."""
     d = v.shape[2] // 3
 
     def aten():
@@ -214,7 +214,7 @@ def gated_update(h: torch.Tensor, v: torch.Tensor, owner: nn.Module = None) -> t
         u = torch.sigmoid(v[:, :, d:2 * d])
         n = torch.tanh(v[:, :, 2 * d:])
         return f * h * (1 - u) + u * n
-    t = getattr(owner, 'op_trials', None) if owner is not None else None
+    t = getattr(owner, 'glue_dispatch', None) if owner is not None else None
     if t is None or h.dim() != 5 or v.shape[2] != 3 * h.shape[2]:
         return aten()
     return t('gated_update', (tuple(h.shape), tuple(h.stride()), tuple(v.stride())), aten,

@@ -140,7 +140,7 @@ class CUTIE(nn.Module):
                 prob = prob * selector
             lg = F.interpolate(aggregate(prob, dim=1), scale_factor=4, mode='bilinear', align_corners=False)
             return lg, F.softmax(lg, dim=1)
-        t = getattr(self, 'op_trials', None)
+        t = getattr(self, 'glue_dispatch', None)
         if t is None or selector is not None or raw.dim() != 4 or raw.shape[1] + 1 > K_.SEGMENT_TAIL_MAX_CHANNELS:
             lg, prob = aten()
         else:           # sigmoid + aggregate + bilinear x4 + softmax (11 launches) as cutie_segment_tail (2)
@@ -186,12 +186,12 @@ class CUTIE(nn.Module):
     def optimize_for_inference(self, channels_last: bool = True, fuse_epilogues: bool = True,
                                fuse_glue: bool = True) -> 'CUTIE':
         """Post-load surgery on the PyTorch/cuDNN stages (cutie_b200/model/fuse.py): fold the frozen BatchNorms of
-        both ResNet trunks into their convolutions, run the trunks channels-last, and let conv+bias(+residual)+ReLU
-        go through cuDNN's fused graph wherever its on-device trial matches and beats the three-launch form
-        (`fuse.ConvEpilogueFuser`, kept as `self.conv_epilogues`); `fuse_glue` lets short ATen chains around the
-        convolutions (area down-sampling, CAResBlock tail, sensory GRU gates) run as single cutie_b200 kernels where
-        their on-device trial matches and wins (`utils.op_trials.OpTrials`, kept as `self.op_trials`).  Numerically equivalent up to fp32 rounding; the module
-        tree (hence state_dict) of the trunks changes, so call it after load_weights."""
+        both ResNet trunks into their convolutions, run the trunks channels-last, and run conv+bias(+residual)(+ReLU)
+        epilogues in the form a committed rule names (`fuse.ConvEpilogueFuser`, kept as `self.conv_epilogues`);
+        `fuse_glue` lets short ATen chains around the convolutions (area down-sampling, CAResBlock tail, sensory GRU
+        gates, ...) run as single cutie_b200 kernels per the committed table of `utils.dispatch` (kept as
+        `self.glue_dispatch`).  Deterministic: no run-time timing decides anything.  Numerically equivalent up to fp32
+        rounding; the module tree (hence state_dict) of the trunks changes, so call it after load_weights."""
         from cutie_b200.model.fuse import ConvEpilogueFuser, attach_epilogue_fuser, fold_trunk_
         for enc in (self.pixel_encoder, self.mask_encoder):
             fold_trunk_(enc)
@@ -220,8 +220,8 @@ class CUTIE(nn.Module):
                     blk.conv1.to(memory_format=torch.channels_last)
                     blk.conv2.to(memory_format=torch.channels_last)
         # pixel-side glue (area down-sampling, channel-attention tail, sensory GRU gates): ATen chains vs our kernels
-        from cutie_b200.utils.op_trials import OpTrials, attach_op_trials
-        attach_op_trials(self, OpTrials(enabled=bool(fuse_glue)))
+        from cutie_b200.utils.dispatch import GlueDispatch, attach_glue_dispatch
+        attach_glue_dispatch(self, GlueDispatch(enabled=bool(fuse_glue)))
         return self
 
     @property

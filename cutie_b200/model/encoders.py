@@ -167,7 +167,7 @@ class MaskDecoder(nn.Module):
 
             def aten():
                 return self.pred(F.relu(x4))
-            t = getattr(self, 'op_trials', None)
+            t = getattr(self, 'glue_dispatch', None)
             if t is None:
                 lg = aten()
             else:   # single-output-channel 3x3 convolution: cutie_conv3x3_c1 (ReLU on the fly, no cuDNN transposes)

@@ -55,33 +55,26 @@ class ConvEpilogueFuser:
                 op PyTorch's own frozen-graph pass emits); ReLU epilogues only
       'kernel'  F.conv2d(x, w, None) + cutie_bias_act(y, b, z, relu)     -- the bias-less convolution followed by ONE
                 float4 stream of ours (csrc/pixel.cu), same association as 'aten' => bit-identical results
+      'pool'    (ResNet stems) bias-less convolution + cutie_bias_relu_maxpool: bias, clamp and 3x3/s2 pooling in one pass
 
-    Convolutions with a handful of input channels (the two ResNet stems: 3 and 5) get every form a second time as
-    `<form>+pad`: the input is zero-padded to a multiple of 4 channels and the weight likewise (cached twin), which is
-    what cuDNN's NHWC tensor-core kernels need for 16-byte channel vectors -- with C = 3 the round-1 profile shows the
-    generic `convolve_common_engine_float_NHWC` at 141 us per stem call.  The zero channel contributes exact zeros.
-
-    Nothing is assumed about how any form behaves on a given GPU / cuDNN build: the first time a (layer, input geometry,
-    epilogue) triple is seen OUTSIDE a stream capture, every applicable form runs on the live tensors, a candidate must
-    match 'aten', all are timed with CUDA events, and the fastest is kept for that triple (`decisions`, `timings`).
-    A form that raises is dropped for that triple and recorded in `errors`.  CPU tensors (the oracle harness borrowing
-    these modules) always take 'aten'.
+    DETERMINISTIC: the form is a function of the epilogue alone -- `RULE`: ReLU epilogues take 'cudnn', bias-only and
+    bias+residual epilogues take 'kernel', stems take 'pool' -- which is what the round-1 on-device A/B chose for 101 of
+    104 layers on B200 with fp32 convolutions (BENCH/profiles r02); nothing is timed at run time, so two runs of the
+    same video execute the same arithmetic.  CPU tensors (the oracle harness borrowing these modules) always take 'aten'.
 
     `cudnn_convolution_relu` hands the *uninitialised* output to cuDNN as the residual operand with alpha = 0;
     0 x (stale NaN bits) is NaN, so the no-residual case passes a persistent zero tensor of the output shape
     instead (read once per call, ~100 MB per 480p frame over all layers: 15 us of HBM time).
     """
     FORMS = ('aten', 'cudnn', 'kernel')
+    RULE = {'relu': 'cudnn', 'linear': 'kernel', 'stem': 'pool'}
 
-    def __init__(self, enabled: bool = True, trial_iters: int = 6, forms=FORMS):
+    def __init__(self, enabled: bool = True, rule=None):
         self.enabled = enabled
-        self.trial_iters = trial_iters
-        self.forms = tuple(forms)
-        self.decisions = {}          # key -> form name
-        self.timings = {}            # key -> {form: ms}
-        self.errors = []
+        self.rule = dict(self.RULE if rule is None else rule)
+        self.counts = {}             # form -> number of distinct (layer, geometry, epilogue) triples routed to it
+        self._seen = set()
         self._zeros = {}
-        self._twins = {}             # id(conv) -> (conv, twin with zero-padded input channels)
 
     # -- the forms ------------------------------------------------------------------------------------
     @staticmethod
@@ -127,162 +120,50 @@ class ConvEpilogueFuser:
         from cutie_b200 import kernels as K_
         return K_.bias_act_(self._conv(conv, x, False), conv.bias, z, relu)
 
-    @staticmethod
-    def _padded_channels(conv: nn.Conv2d) -> int:
-        """Input channels after zero padding, or 0 if this convolution does not get '+pad' forms."""
-        c = conv.in_channels
-        if conv.groups != 1 or c % 4 == 0 or c > 12:
-            return 0
-        return (c + 3) // 4 * 4
-
-    def _twin(self, conv: nn.Conv2d) -> nn.Conv2d:
-        got = self._twins.get(id(conv))
-        if got is not None and got[0] is conv and got[1].weight.device == conv.weight.device:
-            return got[1]
-        cp = self._padded_channels(conv)
-        tw = nn.Conv2d(cp, conv.out_channels, conv.kernel_size, conv.stride, conv.padding, conv.dilation, conv.groups,
-                       bias=conv.bias is not None)
-        w = torch.zeros(conv.out_channels, cp, *conv.kernel_size, dtype=conv.weight.dtype, device=conv.weight.device)
-        w[:, :conv.in_channels] = conv.weight.detach()
-        if conv.weight.is_contiguous(memory_format=torch.channels_last) and not conv.weight.is_contiguous():
-            w = w.contiguous(memory_format=torch.channels_last)
-        tw.weight = nn.Parameter(w, requires_grad=False)
-        tw.bias = conv.bias                       # the same Parameter object
-        tw.eval()
-        self._twins[id(conv)] = (conv, tw)
-        return tw
-
     def run(self, form: str, conv: nn.Conv2d, x: torch.Tensor, z=None, relu: bool = True) -> torch.Tensor:
-        if form.endswith('+pad'):
-            tw = self._twin(conv)
-            x = F.pad(x, (0, 0, 0, 0, 0, tw.in_channels - x.shape[1]))        # keeps x's memory format
-            conv, form = tw, form[:-4]
         if form == 'cudnn':
             return self.fused(conv, x, z)
         if form == 'kernel':
             return self.kernel(conv, x, z, relu)
         return self.unfused(conv, x, z, relu)
 
-    # -- one-off trial per (layer, geometry, epilogue) -------------------------------------------------------
-    @staticmethod
-    def _key(conv, x, z, relu):
-        return (id(conv), tuple(x.shape), tuple(x.stride()), x.dtype, z is not None, bool(relu),
-                torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark)
-
-    def _time(self, fn) -> float:
-        from cutie_b200.utils.op_trials import gpu_time_ms
-        return gpu_time_ms(fn, self.trial_iters)       # launches queued back to back (device time, as in a graph replay)
-
-    def _candidates(self, relu: bool, conv: nn.Conv2d = None):
-        base = [f for f in self.forms if f != 'aten' and (relu or f != 'cudnn')]
-        if conv is not None and self._padded_channels(conv):
-            base += [f + '+pad' for f in self.forms if relu or f != 'cudnn']
-        return base
-
-    def _trial(self, key, conv, x, z, relu) -> str:
-        from cutie_b200.kernels import KernelError
-        what = f'conv {tuple(conv.weight.shape)} on {tuple(x.shape)}'
-        ref = self.unfused(conv, x, z, relu)
-        scale = float(ref.abs().max()) + 1e-6
-        times = {'aten': self._time(lambda: self.unfused(conv, x, z, relu))}
-        for form in self._candidates(relu, conv):
-            try:
-                out = self.run(form, conv, x, z, relu)
-                err = float((out - ref).abs().max())
-                # 'kernel' repeats ATen's arithmetic on the same cuDNN call; 'cudnn' may pick another engine (another
-                # summation order / TF32 path) -- the check is against gross errors (layout, operand order), not rounding
-                tol = (2e-2 if torch.backends.cudnn.allow_tf32 else 2e-4) * scale
-                if not (err <= tol):               # also catches NaN
-                    self.errors.append(f'{what}: {form} differs by {err:.3e} (scale {scale:.3e})')
-                    continue
-                times[form] = self._time(lambda: self.run(form, conv, x, z, relu))
-            except KernelError:                    # our library missing / a failed launch is never absorbed
-                raise
-            except Exception as e:                 # noqa: BLE001 -- any cuDNN / dispatcher failure: drop the form
-                self.errors.append(f'{what}: {form}: {type(e).__name__}: {e}')
-        self.timings[key] = times
-        return min(times, key=times.get)
-
     def _eligible(self, conv: nn.Conv2d, x: torch.Tensor) -> bool:
         return (self.enabled and x.is_cuda and conv.bias is not None and conv.padding_mode == 'zeros'
                 and x.dim() == 4 and x.dtype == torch.float32 and not torch.is_grad_enabled())
 
-    @staticmethod
-    def _capturing() -> bool:
-        return torch.cuda.is_current_stream_capturing()
+    def _note(self, form: str, conv, x, z, relu):
+        key = (id(conv), tuple(x.shape), z is not None, bool(relu), form)
+        if key not in self._seen:
+            self._seen.add(key)
+            self.counts[form] = self.counts.get(form, 0) + 1
 
     def __call__(self, conv: nn.Conv2d, x: torch.Tensor, z=None, relu: bool = True) -> torch.Tensor:
         if not self._eligible(conv, x):
             return self.unfused(conv, x, z, relu)
-        key = self._key(conv, x, z, relu)
-        form = self.decisions.get(key)
-        if form is None:
-            if self._capturing():
-                return self.unfused(conv, x, z, relu)   # no timing inside a capture; _Captured warms up outside one first
-            form = self.decisions[key] = self._trial(key, conv, x, z, relu)
+        form = self.rule['relu'] if relu else self.rule['linear']
+        self._note(form, conv, x, z, relu)
         return self.run(form, conv, x, z, relu)
 
     # -- ResNet stem: relu(conv(x) + bias) -> max_pool2d(3, 2, 1) ---------------------------------------------
     def stem(self, conv: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
-        """max_pool2d(relu(conv(x)), 3, stride=2, padding=1): either the chosen conv+ReLU form followed by ATen's pooling
-        ('aten'), or the bias-less convolution followed by cutie_bias_relu_maxpool ('pool', 'pool+pad'): bias, clamp and
-        pooling in one pass over the convolution output (they commute with max, so the result is the same)."""
-        def aten():
-            return F.max_pool2d(self(conv, x, None, True), 3, stride=2, padding=1)
+        """max_pool2d(relu(conv(x)), 3, stride=2, padding=1): the bias-less convolution followed by
+        cutie_bias_relu_maxpool ('pool': bias, clamp and pooling in one pass over the convolution output; they commute
+        with max, so the result is bit-identical), or the conv+ReLU rule followed by ATen's pooling."""
         if not self._eligible(conv, x):
             return F.max_pool2d(self.unfused(conv, x), 3, stride=2, padding=1)
-        key = ('stem',) + self._key(conv, x, None, True)
-        form = self.decisions.get(key)
-        if form is None:
-            if self._capturing():
-                return aten()
-            form = self.decisions[key] = self._stem_trial(key, conv, x, aten)
-        return self._stem_run(form, conv, x, aten)
+        if self.rule['stem'] == 'pool':
+            from cutie_b200 import kernels as K_
+            self._note('pool', conv, x, None, True)
+            return K_.bias_relu_maxpool(self._conv(conv, x, False), conv.bias)
+        return F.max_pool2d(self(conv, x, None, True), 3, stride=2, padding=1)
 
-    def _stem_run(self, form: str, conv: nn.Conv2d, x: torch.Tensor, aten) -> torch.Tensor:
-        if form == 'aten':
-            return aten()
-        from cutie_b200 import kernels as K_
-        if form.endswith('+pad'):
-            tw = self._twin(conv)
-            x = F.pad(x, (0, 0, 0, 0, 0, tw.in_channels - x.shape[1]))
-            conv = tw
-        return K_.bias_relu_maxpool(self._conv(conv, x, False), conv.bias)
-
-    def _stem_trial(self, key, conv, x, aten) -> str:
-        from cutie_b200.kernels import KernelError
-        what = f'stem conv {tuple(conv.weight.shape)} on {tuple(x.shape)}'
-        ref = aten()                                   # also settles the conv+ReLU decision it is built on
-        scale = float(ref.abs().max()) + 1e-6
-        times = {'aten': self._time(aten)}
-        for form in ['pool'] + (['pool+pad'] if self._padded_channels(conv) else []):
-            try:
-                out = self._stem_run(form, conv, x, aten)
-                err = float((out - ref).abs().max())
-                tol = (2e-2 if torch.backends.cudnn.allow_tf32 else 2e-4) * scale
-                if not (out.shape == ref.shape and err <= tol):
-                    self.errors.append(f'{what}: {form} differs by {err:.3e} (scale {scale:.3e})')
-                    continue
-                times[form] = self._time(lambda: self._stem_run(form, conv, x, aten))
-            except KernelError:
-                raise
-            except Exception as e:                     # noqa: BLE001 -- cuDNN / dispatcher failure of the bias-less call
-                self.errors.append(f'{what}: {form}: {type(e).__name__}: {e}')
-        self.timings[key] = times
-        return min(times, key=times.get)
-
-    def __deepcopy__(self, memo):          # a copied model gets its own (empty) fuser with the same settings
-        new = ConvEpilogueFuser(self.enabled, self.trial_iters, self.forms)
+    def __deepcopy__(self, memo):          # a copied model gets its own fuser with the same settings
+        new = ConvEpilogueFuser(self.enabled, self.rule)
         memo[id(self)] = new
         return new
 
     def report(self) -> dict:
-        counts = {f: sum(1 for v in self.decisions.values() if v == f) for f in self.FORMS}
-        counts['padded_input'] = sum(1 for v in self.decisions.values() if v.endswith('+pad'))
-        counts['stem_pool'] = sum(1 for v in self.decisions.values() if v.startswith('pool'))
-        saved = sum(t['aten'] - t[self.decisions[k]] for k, t in self.timings.items() if k in self.decisions)
-        return {'enabled': self.enabled, **counts, 'errors': len(self.errors),
-                'first_error': self.errors[0] if self.errors else None, 'trial_ms_saved_per_pass': saved}
+        return {'enabled': self.enabled, 'rule': dict(self.rule), 'layers': dict(self.counts)}
 
 
 def attach_epilogue_fuser(module: nn.Module, fuser: 'ConvEpilogueFuser') -> int:

@@ -101,14 +101,7 @@ class QueryTransformerBlock(nn.Module):
         xhat = torch.empty_like(x)
         qp = K_.qt_linear(x, wq, bq, ln=(rp.norm.weight, rp.norm.bias), pe=query_pe, xhat_out=xhat)
         qfold, _ = K_.qt_head_fold(qp, wk, transpose_w=False, scale=scale, num_heads=H)
-        t = getattr(self, 'op_trials', None)
-        splits = None
-        if t is not None:        # optimised models A/B the pixel-axis split count on the device (utils/op_trials.py)
-            BK, _, HW = pixel.shape
-            splits = t.pick('qt_p2q_splits', (BK, HW), K_.qt_p2q_split_candidates(BK, HW, H),
-                            lambda s_: K_.qt_pixel_to_query(qfold, pixel, pixel_pe, fg, fg_count, wv, bv, Q, H,
-                                                             splits=s_), pixel)
-        attn = K_.qt_pixel_to_query(qfold, pixel, pixel_pe, fg, fg_count, wv, bv, Q, H, splits=splits)
+        attn = K_.qt_pixel_to_query(qfold, pixel, pixel_pe, fg, fg_count, wv, bv, Q, H)
         x = K_.qt_linear(attn, rp.cross_attn.out_proj.weight, rp.cross_attn.out_proj.bias, residual=xhat)
         # --- query self attention (transformer_layers.py:27-41)
         sa = self.self_attn

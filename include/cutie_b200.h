@@ -232,16 +232,19 @@ int cutie_qt_self_attention(const float* qk, const float* v, int64_t M, int64_t 
  * cutie/utils/tensor_utils.py:47-54).  The [(B*K*heads),Q,HW] bool mask is represented by fg + fg_count. */
 int cutie_qt_aux_mask(const float* pixel, const float* w, const float* b, int64_t B, int64_t K, int64_t E,
                       int64_t HW, float* logits, uint8_t* fg, int32_t* fg_count, void* stream);
-/* read_from_pixel attention core (masked, queries <- pixels), channel-major pixels, flash-style split over
- * pixels + combine + V projection.  Replaces CrossAttention.cross_attn for read_from_pixel
- * (transformer_layers.py:88-93 via object_transformer.py:51-56).  workspace: BK*H*splits*Q*(E+2) floats. */
+/* read_from_pixel attention core (masked, queries <- pixels) on tcgen05 tensor cores (3xTF32, fp32-class accuracy):
+ * one CTA per 64-pixel tile and object computes S = Qfold.(pixel+pe), the masked tile-local softmax and Z = P.pixel^T
+ * (csrc/qt_tc.cu); a combine kernel merges the tiles and applies the per-head value projection.  Replaces
+ * CrossAttention.cross_attn for read_from_pixel (transformer_layers.py:88-93 via object_transformer.py:51-56).
+ * `splits` must be cutie_qt_pixel_to_query_splits() = ceil(HW/64); workspace: cutie_qt_pixel_to_query_workspace_floats(). */
 int cutie_qt_pixel_to_query_splits(int64_t BK, int64_t HW, int num_heads);
+int64_t cutie_qt_pixel_to_query_workspace_floats(int64_t BK, int64_t HW);
 int cutie_qt_pixel_to_query(const float* qfold, const float* pixel, const float* pixel_pe, const uint8_t* fg,
                             const int32_t* fg_count, const float* wv, int64_t ldwv, const float* bv, int64_t BK,
                             int64_t E, int64_t HW, int num_queries, int num_heads, int splits, float* workspace,
                             float* attn_out, void* stream);
-/* read_from_query (pixels <- queries) fused through softmax, value fold, output bias and residual,
- * channel-major in/out.  Replaces CrossAttention for read_from_query (object_transformer.py:61-65) and the
+/* read_from_query (pixels <- queries) on tcgen05 tensor cores (3xTF32): one CTA per 128-pixel tile and object, fused
+ * through the per-head softmax over the 16 queries, value fold, output bias and residual, channel-major in/out.  Replaces CrossAttention for read_from_query (object_transformer.py:61-65) and the
  * NLC<->NCHW permutes around it (:50, transformer_layers.py:131-132). */
 int cutie_qt_query_to_pixel(const float* kfold, const float* kdots, const float* vfold, const float* out_bias,
                             const float* pixel, const float* pixel_pe, int64_t BK, int64_t E, int64_t HW,

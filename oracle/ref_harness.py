@@ -1,8 +1,8 @@
 """Loads the UNMODIFIED reference (hkchengrex/Cutie, read-only at /root/reference) on CPU.
 
-TEST INFRASTRUCTURE, usable only in the build container (the GPU box has no /root/reference): used by
-tests/golden/make_golden.py to emit the committed fixtures that pin oracle/ and the CUDA path, and by
-tests that re-validate the oracle against the live reference when it is present.
+TEST / BASELINE INFRASTRUCTURE: used by tests/golden/make_golden.py to emit the committed fixtures that pin oracle/
+and the CUDA path, by tests that re-validate the oracle against the live reference, by tests/ref_runner.py (the
+reference run in eager fp32 on the GPU box, from baseline/_ref/) and by bench.py --impl reference.
 
 Accommodations:
   * `omegaconf` is not installed: a stand-in module with DictConfig/OmegaConf/open_dict is injected
@@ -19,7 +19,22 @@ import types
 
 import yaml
 
-REF_ROOT = os.environ.get('CUTIE_REFERENCE_ROOT', '/root/reference')
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root() -> str:
+    """CUTIE_REFERENCE_ROOT, else the read-only mount of the build container, else the install under baseline/_ref/
+    (git-ignored, shipped to the GPU box by gpurun; baseline/install_reference.py)."""
+    env = os.environ.get('CUTIE_REFERENCE_ROOT')
+    if env:
+        return env
+    for cand in ('/root/reference', os.path.join(os.path.dirname(_HERE), 'baseline', '_ref')):
+        if os.path.isdir(os.path.join(cand, 'cutie', 'inference')):
+            return cand
+    return '/root/reference'
+
+
+REF_ROOT = _find_root()
 
 
 def available() -> bool:

@@ -2,7 +2,7 @@
 
 torch.cuda's stream / event / graph entry points are replaced by inert stand-ins, bench's `torch.device('cuda', i)`
 resolves to the CPU, the kernel wrappers are the CPU emulations of tests/cpu_kernels.py and the workload is a tiny clip.
-Nothing measured here means anything; the point is that every line of bench.py (arms, A/B, pre-flight fallback, JSON
+Nothing measured here means anything; the point is that every line of bench.py (arms, extension arm, parity check, JSON
 assembly) executes before it first runs on a B200.  Usage: python tests/bench_dry_run.py [bench args]"""
 import contextlib
 import os

@@ -315,7 +315,8 @@ def test_qt_aux_mask(K_, B, K, HW):
     assert (cg.cpu() == fg.cpu().reshape(B * K, HW).sum(1).int()).all()
 
 
-@pytest.mark.parametrize('BK,HW,case', [(3, 1620, 'mixed'), (2, 60, 'mixed'), (2, 77, 'nofg'), (1, 40, 'allfg')])
+@pytest.mark.parametrize('BK,HW,case', [(3, 1620, 'mixed'), (2, 60, 'mixed'), (2, 77, 'nofg'), (1, 40, 'allfg'), (2, 77, 'mixed'),
+                                        (5, 3600, 'mixed'), (1, 129, 'mixed'), (1, 64, 'allfg')])
 def test_qt_cross_attention_kernels(K_, BK, HW, case):
     from tests import cpu_kernels as ck
     g = torch.Generator().manual_seed(8)

@@ -84,7 +84,7 @@ def _run(seed: int, steps: int = 40):
     prep = lambda t: t.unsqueeze(0)
     for t in range(steps):
         img = frames[t].unsqueeze(0)
-        out, hit = la.current(t, img, (frames[t].data_ptr(), tuple(frames[t].shape)))
+        out, hit = la.current(t, img, frames[t])
         assert out['frame'] == t, f'step {t} got the features of frame {out["frame"]}'
         mode = rng.choice(['announce', 'announce', 'announce', 'none', 'wrong_tensor', 'wrong_frame'])
         if mode == 'announce':
@@ -127,7 +127,7 @@ def test_hit_and_miss_bookkeeping():
         return ('features', slot)
     la = EncoderLookahead(encode, ops=rec)
     a, b, c = torch.zeros(3, 2, 2), torch.ones(3, 2, 2), torch.ones(3, 2, 2) * 2
-    sid = lambda t: (t.data_ptr(), tuple(t.shape))
+    sid = lambda t: t                    # a hit is decided on the announced tensor's memory and version counter
     out, hit = la.current(0, a.unsqueeze(0), sid(a))
     assert not hit and log == [('main', 0)]
     la.ahead(0, b, lambda t: t.unsqueeze(0))
@@ -140,3 +140,12 @@ def test_hit_and_miss_bookkeeping():
     assert not hit and log[-1] == ('main', 1) and la.slot == 1                          # re-encoded into the current slot
     out, hit = la.current(3, c.unsqueeze(0), sid(c))                                   # nothing pending
     assert not hit and log[-1] == ('main', 1)
+    # the announced buffer is overwritten in place before the next step (a reused staging buffer): never a hit
+    la.ahead(3, a, lambda t: t.unsqueeze(0))
+    a.add_(1.0)
+    out, hit = la.current(4, a.unsqueeze(0), sid(a))
+    assert not hit and log[-1][0] == 'main'
+    # a different tensor of the same shape is never a hit either (the announced one is kept alive: no recycled address)
+    la.ahead(4, b, lambda t: t.unsqueeze(0))
+    out, hit = la.current(5, b.clone().unsqueeze(0), sid(b.clone()))
+    assert not hit
