@@ -373,18 +373,25 @@ def parity_check(proc, cfg, frame, dev):
     reference's fp32 three-term expansion cannot resolve) and adopted by the oracle, as in the teacher-forced tests."""
     import cutie_b200.kernels as K_
     from oracle.cpu_core import OracleCore
-    from oracle.state_sync import SelectionReconciler, export_state_to_oracle
+    from oracle.state_sync import ForegroundReconciler, SelectionReconciler, export_state_to_oracle
     t0 = time.perf_counter()
     oc = export_state_to_oracle(proc, OracleCore(make_net(cfg), cfg))     # un-optimised CPU copy of the same weights
-    rec = SelectionReconciler(cfg.top_k, max_frac=0.05)
-    oc.selection_hook = rec
-    orig = K_.affinity_topk
+    rec, fgr = SelectionReconciler(cfg.top_k, max_frac=0.05), ForegroundReconciler()
+    oc.selection_hook, oc.fg_hook = rec, fgr
+    orig, orig_aux = K_.affinity_topk, K_.qt_aux_mask
 
     def spy(*a, **k):
         out = orig(*a, **k)
         rec.gpu_idx = out[0].clone()
         return out
-    K_.affinity_topk = spy
+
+    def spy_aux(*a, **k):
+        out = orig_aux(*a, **k)
+        fgr.gpu_fg.append(out[1].clone())
+        return out
+    K_.affinity_topk, K_.qt_aux_mask = spy, spy_aux
+    graphs = proc.use_cuda_graphs
+    proc.use_cuda_graphs = False          # this one frame runs the same kernels eagerly so that the foreground maps can be read
     try:
         with torch.inference_mode():
             proc.step(frame.to(dev))
@@ -394,11 +401,13 @@ def parity_check(proc, cfg, frame, dev):
             oc.step(frame)
             torch.set_num_threads(threads)
     finally:
-        K_.affinity_topk = orig
+        K_.affinity_topk, K_.qt_aux_mask = orig, orig_aux
+        proc.use_cuda_graphs = graphs
     diff = float((proc.last_logits.cpu() - oc.last_logits).abs().max())
     out = {'max_abs_logit_diff': diff, 'within_1e-3': diff < 1e-3, 'queries': rec.queries,
            'topk_set_equal': rec.flips == 0, 'topk_sets_differing': rec.flips,
            'differing_sets_valid_vs_float64': True,            # SelectionReconciler raises if one is not
+           'foreground_pixels_near_tied_and_adopted': fgr.flips, 'foreground_pixels': fgr.pixels,
            'memory_tokens': proc.memory.work_mem.size(0), 'seconds': time.perf_counter() - t0,
            'what': 'one teacher-forced frame after the timed region: CUDA path vs oracle/cpu_core.py from the same live state'}
     log(f'[parity] {out}')

@@ -174,6 +174,7 @@ class OracleCore:
         self.HW = None
         self.read_trace = None                 # filled with (idx, weights, usage) of the last read when set to {}
         self.selection_hook = None
+        self.fg_hook = None                    # test-only, see oracle/transformer.query_transformer
         self.chunk_size = cfg.chunk_size
 
     # -- memory read (memory_manager.py:112-208) -----------------------------------------------
@@ -215,7 +216,7 @@ class OracleCore:
                 lm = self.last_mask[:, [self.objects.index(o) for o in chunk]]
                 fused = self.net.pixel_fusion(pix_feat, visual, sens, lm)
                 obj_mem = torch.stack([self.obj_v[o] for o in chunk], 1).unsqueeze(2)
-                pix, _ = query_transformer(fused, obj_mem, self.sd)
+                pix, _ = query_transformer(fused, obj_mem, self.sd, fg_hook=self.fg_hook)
                 for i, o in enumerate(chunk):
                     out[o] = pix[:, i]
         return out

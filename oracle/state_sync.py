@@ -75,7 +75,9 @@ def export_state_to_oracle(proc, oc):
     exactly the state the CUDA path is in (bench.py's `parity_check` after the timed region).  FIFO mode only."""
     m = proc.memory
     assert not m.use_long_term, 'export_state_to_oracle covers FIFO working memory (the bench workloads)'
-    cpu = lambda t: t.detach().float().cpu()
+    def cpu(t):
+        c = t.detach().float().cpu()
+        return c.clone() if c.data_ptr() == t.data_ptr() else c      # never alias the product's state (CPU dry runs)
     oc.objects = [int(o) for o in proc.object_manager.all_obj_ids]
     oc.curr_ti, oc.last_mem_ti = proc.curr_ti, proc.last_mem_ti
     oc.last_mask = cpu(proc.last_mask) if proc.last_mask is not None else None
@@ -132,3 +134,38 @@ class SelectionReconciler:
             self.flips += 1
         assert self.flips <= self.max_frac * self.queries + 2, 'too many near-tie disagreements'
         return out
+
+
+class ForegroundReconciler:
+    """Near-tie arbitration for the foreground test of _get_aux_mask (object_transformer.py:185-192), the network's other
+    discrete decision: fg[k,p] = (logit_k >= max over {bg, 1..K}).  On a pixel whose two largest log-odds differ by less
+    than fp32 rounding of the mask_pred accumulation, the CUDA kernel and the oracle can legitimately disagree, and with
+    random-init weights ONE flipped pixel moves the next logits by 4e-2 (measured on the bike clip).  For every pixel
+    where the two maps differ this hook checks that the margin is below `tol` (in log-odds, from the ORACLE's own aux
+    logits) and, if so, lets the oracle adopt the CUDA map; a disagreement on a pixel with a real margin raises.
+
+    `gpu_fg`: list (one per aux stage, in call order) of uint8/bool [B,K,HW] maps captured from kernels.qt_aux_mask."""
+
+    def __init__(self, tol=2e-4):
+        self.tol = tol
+        self.gpu_fg = []
+        self.flips = 0
+        self.pixels = 0
+
+    def __call__(self, stage, aux_logits, fg):
+        from oracle.transformer import aggregate_logits
+        if stage >= len(self.gpu_fg):
+            return fg
+        g = self.gpu_fg[stage].to(torch.bool).cpu().reshape(fg.shape)
+        diff = g != fg
+        self.pixels += fg.numel()
+        if not diff.any():
+            return fg
+        lo = aggregate_logits(aux_logits.sigmoid(), dim=1).flatten(2)            # [B, 1+K, HW]
+        top2 = lo.topk(2, dim=1)[0]
+        margin = (top2[:, 0] - top2[:, 1]).abs()                                  # [B, HW]
+        bad = diff.any(1) & (margin > self.tol)
+        assert not bad.any(), (f'foreground maps differ on {int(bad.sum())} pixel(s) with a margin up to '
+                               f'{float(margin[bad].max()):.3e} (> {self.tol:.0e}) at aux stage {stage}')
+        self.flips += int(diff.sum())
+        return g

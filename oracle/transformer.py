@@ -103,11 +103,14 @@ def ca_res_block(x: torch.Tensor, sd: Dict[str, torch.Tensor], pre: str) -> torc
 def query_transformer(pixel: torch.Tensor, obj_summaries: torch.Tensor, sd: Dict[str, torch.Tensor],
                       prefix: str = 'object_transformer.', num_heads: int = 8, num_blocks: int = 3,
                       pe_scale: float = 32.0, pe_temperature: float = 128.0,
-                      trace: Optional[dict] = None):
+                      trace: Optional[dict] = None, fg_hook=None):
     """QueryTransformer.forward (object_transformer.py:114-177), inference mode, selector=None.
 
     pixel [B,K,E,h,w]; obj_summaries [B,K,T,Q,E+1].  Returns (pixel_out [B,K,E,h,w], aux_logits list).
     If `trace` is a dict it receives intermediate tensors (used by the module-level parity tests).
+    `fg_hook(stage, aux_logits [B,K,h,w], fg bool [B,K,HW]) -> fg` (test-only) lets a checker substitute an equally valid
+    foreground map on near-tied pixels (oracle/state_sync.ForegroundReconciler), like OracleCore.selection_hook does
+    for near-tied top-k members.
     """
     g = lambda n: sd[prefix + n]
     B, K, E, h, w = pixel.shape
@@ -129,8 +132,12 @@ def query_transformer(pixel: torch.Tensor, obj_summaries: torch.Tensor, sd: Dict
     def mask_pred(i, t):
         return F.conv2d(F.relu(t), g(f'mask_pred.{i}.1.weight'), g(f'mask_pred.{i}.1.bias')).reshape(B, K, h, w)
 
+    def fg_of(stage, lg):
+        fg = foreground_map(lg)
+        return fg if fg_hook is None else fg_hook(stage, lg, fg)
+
     logits: List[torch.Tensor] = [mask_pred(0, pix)]
-    blocked = attention_block_mask(foreground_map(logits[0]), Q)
+    blocked = attention_block_mask(fg_of(0, logits[0]), Q)
     if trace is not None:
         trace.update(query0=x.clone(), query_pe=qpe.clone(), pixel_pe=pixel_pe.clone(), pixel0=pix.clone(),
                      blocked0=blocked.clone())
@@ -169,7 +176,7 @@ def query_transformer(pixel: torch.Tensor, obj_summaries: torch.Tensor, sd: Dict
         # pixel_ffn: transformer_layers.py:127-136
         pix = ca_res_block(pf.transpose(1, 2).reshape(B * K, E, h, w), sd, prefix + bp + 'pixel_ffn.conv.')
         logits.append(mask_pred(i + 1, pix))                                            # :164-167
-        blocked = attention_block_mask(foreground_map(logits[-1]), Q)
+        blocked = attention_block_mask(fg_of(i + 1, logits[-1]), Q)
         if trace is not None:
             trace[f'b{i}_pixel'] = pix.clone()
     return pix.reshape(B, K, E, h, w), logits
