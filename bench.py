@@ -354,6 +354,20 @@ def run_ours(args, wl, rank, world, dev):
                host_ms=[host_dev, host_e2e], lookahead=look, untimed=warm, image_levels=K_.image_level_launches(),
                epilogues=net.conv_epilogues.report() if hasattr(net, 'conv_epilogues') else None,
                glue=net.glue_dispatch.report() if hasattr(net, 'glue_dispatch') else None)
+    # ---- how selective the candidate filter is on this bank (one extra untimed frame; explains `roofline`) ----
+    try:
+        K_.KEEP_LAST_WORKSPACE = True
+        with torch.inference_mode():
+            proc.step(frames_dev[state['t']])
+            state['t'] += 1
+        torch.cuda.synchronize(dev)
+        cnt = K_.last_candidate_counts()
+        if cnt is not None:
+            c = cnt.float().flatten()
+            res['candidates'] = {'per_query_mean': float(c.mean()), 'per_query_p50': float(c.median()),
+                                 'per_query_max': float(c.max()), 'of_tokens': n_tokens, 'top_k': wl['top_k']}
+    finally:
+        K_.KEEP_LAST_WORKSPACE = False
     # ---- in-run parity check: ONE frame re-computed by the CPU oracle from the live state ----
     if rank == 0 and world == 1 and not args.no_parity_check:
         try:
@@ -691,7 +705,8 @@ def main():
                 'e2e': world * K / (res['lookahead']['ms_e2e'] * 1e-3), 'unit': 'frames/s'},
             'kernels': kshare,
             'host_enqueue_ms_per_step': {'device_arm': res['host_ms'][0], 'e2e_arm': res['host_ms'][1]},
-            'affinity_phases_ms': res.get('phases'), 'key_image_levels': res['image_levels'],
+            'affinity_phases_ms': res.get('phases'), 'affinity_candidates': res.get('candidates'),
+            'key_image_levels': res['image_levels'],
             'build': {'cuda_graphs': not args.no_graphs, 'optimize_for_inference': not args.no_optimize,
                       'cudnn_benchmark': not args.no_cudnn_benchmark, 'cudnn_allow_tf32': False, 'matmul_allow_tf32': False,
                       'conv_epilogues': res['epilogues'], 'glue_dispatch': res['glue']},

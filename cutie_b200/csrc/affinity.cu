@@ -573,6 +573,82 @@ static int run_filter_level(const ScanParams& base, long long B, long long strid
   return launch_tc_filter(fp, B, st);
 }
 
+// FP16 plan over the key operand image: tile-sampled threshold pass -> k-th smallest slot minimum -> candidate filter
+// over the whole image -> exact re-rank.  Two memsets + four launches per call, whatever the bank size.
+static int run_filtered_f16(const ScanParams& base, long long B, char* ws, const WsLayout& wl, int* out_idx, float* out_w,
+                            float* out_sim, unsigned long long* usage_acc, const ImageArgs& ia, cudaStream_t st) {
+  F16FilterParams fp;
+  memset(&fp, 0, sizeof(fp));
+  fp.segs = base.segs;
+  fp.qk = base.qk;
+  fp.qe = base.qe;
+  fp.Q = base.Q;
+  long long cum = 0;
+  for (int s = 0; s < base.segs.nseg; ++s) {
+    const long long n = base.segs.begin[s + 1] - base.segs.begin[s];
+    fp.img[s] = reinterpret_cast<const unsigned char*>(ia.img[s]);
+    fp.img_bs[s] = ia.bs[s] * 4;
+    fp.img_tile0[s] = ia.phys[s] / 128;
+    fp.img_lo0[s] = (int)(ia.phys[s] % 128);
+    fp.img_tcum[s] = cum;
+    cum += n > 0 ? (fp.img_lo0[s] + n + 127) / 128 : 0;
+  }
+  for (int s = base.segs.nseg; s <= kMaxSeg; ++s) fp.img_tcum[s] = cum;
+  const int grid_x = f16_schedule(fp, B);
+  const int groups = (fp.full_groups > 0 ? fp.splits_full : fp.splits_half) * 64;    // threshold slots per query
+  if (groups > TC_CAP_BIG) return fail(-1, "%s: too many key splits for the threshold workspace", "run_filtered_f16");
+  // sample every `stride`-th tile: every split of a query group should still see >= 8 tiles (its 64 slots then hold
+  // minima over >= 16 tokens each); small banks are sampled whole
+  const long long max_splits = fp.full_groups > 0 ? fp.splits_full : fp.splits_half;
+  long long stride = cum / (8ll * max_splits);
+  if (stride > 16) stride = 16;
+  if (stride < 1) stride = 1;
+  const int ph = phase_begin(st);
+  float* group_min = (float*)(ws + wl.cand_e);
+  float* emax = (float*)(ws + wl.emax0);
+  cudaError_t e = cudaMemsetAsync(group_min, 0x7f, (size_t)B * base.Q * groups * 4, st);      // 0x7f7f7f7f = 3.4e38: "empty slot"
+  if (e != cudaSuccess) return set_cuda_error("cudaMemsetAsync", e);
+  fp.tile_stride = (int)stride;
+  fp.tile_phase = 0;
+  fp.group_min = group_min;
+  fp.groups_per_query = groups;
+  int rc = launch_f16_filter(fp, B, grid_x, true, st);
+  if (rc) return rc;
+  phase_mark(ph, st);
+  rc = launch_f16_threshold(group_min, groups, B, base.Q, base.top_k, base.kpad, emax, st);
+  if (rc) return rc;
+  phase_mark(ph, st);
+  e = cudaMemsetAsync(ws + wl.count, 0, (size_t)B * base.Q * 4, st);
+  if (e != cudaSuccess) return set_cuda_error("cudaMemsetAsync", e);
+  fp.emax_in = emax;
+  fp.cand_idx = (int*)(ws + wl.cand_idx);
+  fp.count = (int*)(ws + wl.count);
+  fp.cap = TC_CAP_BIG;
+  rc = launch_f16_filter(fp, B, grid_x, false, st);
+  if (rc) return rc;
+  ++g_image_level_launches;
+  phase_mark(ph, st);
+  RerankParams rp;
+  memset(&rp, 0, sizeof(rp));
+  rp.segs = base.segs;
+  rp.qk = base.qk;
+  rp.qe = base.qe;
+  rp.Q = base.Q;
+  rp.n_total = base.n_total;
+  rp.cand_idx = (const int*)(ws + wl.cand_idx);
+  rp.count = (const int*)(ws + wl.count);
+  rp.cap = TC_CAP_BIG;
+  rp.top_k = base.top_k;
+  rp.kpad = base.kpad;
+  rp.out_idx = out_idx;
+  rp.out_w = out_w;
+  rp.out_sim = out_sim;
+  rp.usage_acc = usage_acc;
+  rc = launch_rerank(rp, B, st);
+  phase_mark(ph, st);
+  return rc;
+}
+
 static int run_filtered(const ScanParams& base, long long B, const Plan& pl, char* ws, const WsLayout& wl,
                         int* out_idx, float* out_w, float* out_sim, unsigned long long* usage_acc,
                         float* dbg_energy, const ImageArgs& ia, cudaStream_t st) {
@@ -657,6 +733,12 @@ extern "C" int64_t cutie_debug_image_level_launches(void) { return g_image_level
 
 extern "C" int cutie_affinity_plan_levels(int64_t n_total, int top_k) { return make_plan(n_total, top_k).levels; }
 
+// Diagnostics: byte offset of the per-query candidate counters [B][Q] int32 inside the workspace (-1: exact-scan plan).
+extern "C" int64_t cutie_debug_ws_count_offset(int64_t B, int64_t Q, int64_t n_total, int top_k) {
+  if (make_plan(n_total, top_k).levels == 0) return -1;
+  return (int64_t)ws_layout(B, Q, n_total, top_k).count;
+}
+
 static int fill_scan_params(ScanParams& sp, int num_segments, const void* const* seg_key,
                             const void* const* seg_shrinkage, const int64_t* seg_len,
                             const int64_t* seg_key_bstride, const int64_t* seg_shr_bstride, const float* qk,
@@ -731,6 +813,7 @@ extern "C" int cutie_affinity_topk_img(int num_segments, const void* const* seg_
       ia.phys[s] = seg_phys_begin[s];
     }
   }
+  if (ia.on) return run_filtered_f16(sp, B, ws, wl, out_idx, out_w, out_sim, usage_acc, ia, st);
   return run_filtered(sp, B, pl, ws, wl, out_idx, out_w, out_sim, usage_acc, nullptr, ia, st);
 }
 

@@ -57,6 +57,37 @@ struct RerankParams {
   unsigned long long* usage_acc;
 };
 
+// FP16 filter over the key operand image (affinity_f16.cu): threshold sampling pass + candidate filter pass.
+constexpr int F16_RESERVE = 16;            // candidate slots reserved per global atomic (per thread)
+struct F16FilterParams {
+  KeySegments segs;
+  const float* qk;
+  const float* qe;
+  long long Q;
+  // sample pass: tiles g = tile_phase + j * tile_stride of the image; output group_min [B][Q][groups_per_query]
+  int tile_stride, tile_phase;
+  float* group_min;
+  int groups_per_query;
+  // filter pass: thresholds in, per-query candidate lists out
+  const float* emax_in;
+  int* cand_idx;
+  int* count;
+  int cap;
+  // CTA schedule (f16_schedule)
+  int full_groups, splits_full, splits_half;
+  // per segment: the FP16 operand image of the arena it lives in (cutie_bank_key_image), by physical 128-token tile
+  const unsigned char* img[kMaxSeg];
+  long long img_bs[kMaxSeg];       // batch stride (bytes)
+  long long img_tile0[kMaxSeg];    // first physical tile of the segment
+  int img_lo0[kMaxSeg];            // row of the segment's first token inside that tile
+  long long img_tcum[kMaxSeg + 1]; // prefix sums of the segments' tile counts
+};
+size_t f16_filter_smem_bytes();
+int f16_schedule(F16FilterParams& p, long long B);
+int launch_f16_filter(const F16FilterParams& p, long long B, int grid_x, bool sample, cudaStream_t st);
+int launch_f16_threshold(const float* group_min, int groups, long long B, long long Q, int top_k, int kpad, float* emax_out,
+                         cudaStream_t st);
+
 size_t tc_filter_smem_bytes();
 int tc_split_count(long long B, long long Q, long long samp_count);
 int launch_tc_filter(const TcFilterParams& p, long long B, cudaStream_t st);

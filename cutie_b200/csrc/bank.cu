@@ -3,13 +3,13 @@
 #include <math_constants.h>
 
 #include "common.cuh"
-#include "tc_operand.cuh"
+#include "tc_operand_f16.cuh"
 
 namespace cutie {
 
 // Operand image of the tcgen05 affinity filter for tokens [phys0, phys0 + n) of an arena: every 128-token physical
-// tile is stored exactly as the filter wants it in shared memory (tc_operand.cuh), so the filter fetches a tile
-// with ONE 68 KB bulk copy instead of converting 128 fp32 rows per tile per query block.
+// tile is stored exactly as the FP16 filter wants it in shared memory (tc_operand_f16.cuh), so the filter fetches a
+// tile with ONE 36 KB bulk copy instead of converting 128 fp32 rows per tile per query block.
 // 16 lanes per token (coalesced 256-B key rows), 16 tokens per 256-thread CTA.
 __global__ void __launch_bounds__(256) key_image_kernel(const float* __restrict__ key, long long key_bs,
                                                         const float* __restrict__ shr, long long shr_bs,
@@ -26,9 +26,8 @@ __global__ void __launch_bounds__(256) key_image_kernel(const float* __restrict_
     v = __ldg(reinterpret_cast<const float4*>(key + (long long)b * key_bs + phys * 64) + c4);
     sh = __ldg(shr + (long long)b * shr_bs + phys);
   }
-  unsigned char* tile = img + (long long)b * img_bs_bytes + (phys >> 7) * (long long)TC_OPER_BYTES;
-  float Pn, Rn;
-  store_key_row_operand(tile, (int)(phys & 127), c4, v, sh, Pn, Rn, live);   // dead rows: shuffles only, no stores
+  unsigned char* tile = img + (long long)b * img_bs_bytes + (phys >> 7) * (long long)F16_OPER_BYTES;
+  store_key_row_operand_f16(tile, (int)(phys & 127), c4, v, sh, live);   // dead rows: shuffles only, no stores
 }
 
 // out[b][c][r] = in[b][r][c]   in: [B, R, C] (row stride C), out: [B, C, R]

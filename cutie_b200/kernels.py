@@ -110,7 +110,7 @@ class BankSegment(NamedTuple):
 
 
 KEY_IMAGE_TILE = 128            # tokens per image tile (the filter's MMA N)
-KEY_IMAGE_FLOATS = 17408        # 69632 bytes: 4 swizzled [128 x 128 B] K-blocks + one [128 x 32 B] tail block
+KEY_IMAGE_FLOATS = 9216         # 36864 bytes of FP16 operands: 2 swizzled [128 x 128 B] K-blocks + one [128 x 32 B] tail block
 
 
 def _rows_view_ok(t: torch.Tensor):
@@ -173,7 +173,9 @@ def affinity_topk(segments: Sequence[BankSegment], qk: torch.Tensor, qe: torch.T
                     IA(*[s.phys_begin for s in segments]))
     else:
         img_args = (None, None, None)
-    with _call('affinity_topk', 2 * _lv if _lv else 2):
+    # launches: exact scan = scan + merge; FP16 image plan = sample pass, threshold, filter pass, re-rank; TF32 levels
+    # (no image) = one filter per level, a select between levels, re-rank
+    with _call('affinity_topk', (4 if with_img else 2 * _lv) if _lv else 2):
         st = L.cutie_affinity_topk_img(
             ctypes.c_int(ns), PA(*[s.key.data_ptr() for s in segments]),
             PA(*[s.shrinkage.data_ptr() for s in segments]), IA(*[s.n for s in segments]),
@@ -182,7 +184,28 @@ def affinity_topk(segments: Sequence[BankSegment], qk: torch.Tensor, qe: torch.T
             _ptr(idx, torch.int32), _ptr(w), _ptr(sim), _ptr(usage_acc, torch.int64), _i64(n_total),
             _ptr(ws, torch.uint8), ctypes.c_size_t(ws_bytes), _stream())
     _check(st, 'cutie_affinity_topk')
+    if KEEP_LAST_WORKSPACE:
+        global _LAST_WS
+        _LAST_WS = (ws, B, Q, n_total, top_k)
     return idx, w, sim
+
+
+KEEP_LAST_WORKSPACE = False     # diagnostics: keep the workspace of the last affinity_topk call alive
+_LAST_WS = None
+
+
+def last_candidate_counts() -> Optional[torch.Tensor]:
+    """Diagnostics (KEEP_LAST_WORKSPACE = True): per-query number of candidates the last filtered affinity_topk call
+    handed to the exact re-rank, int32 [B, Q]; None if the last call was an exact scan."""
+    if _LAST_WS is None:
+        return None
+    ws, B, Q, n_total, top_k = _LAST_WS
+    f = lib().cutie_debug_ws_count_offset
+    f.restype = ctypes.c_int64
+    off = int(f(_i64(B), _i64(Q), _i64(n_total), ctypes.c_int(top_k)))
+    if off < 0:
+        return None
+    return ws[off:off + 4 * B * Q].view(torch.int32).view(B, Q).clone()
 
 
 def set_tc_min_tokens(n: int):
@@ -469,7 +492,8 @@ def bank_key_image(key_arena: torch.Tensor, shr_arena: torch.Tensor, phys_begin:
 
     key_arena [B, cap, 64] and shr_arena [B, cap] token-major, image [B, tiles, KEY_IMAGE_FLOATS]: every
     128-token physical tile holds [shr k^2 | shr k | error-bound tail] in the swizzled shared-memory layout of
-    the affinity filter (csrc/tc_operand.cuh), so the filter fetches a tile with one bulk copy."""
+    the FP16 affinity filter (csrc/tc_operand_f16.cuh), so the filter fetches a tile with one 36 KB bulk copy.
+    (The tensor's dtype is float32 only as a container: 9216 floats = 36864 bytes of f16 operands per tile.)"""
     B, cap, CK = key_arena.shape
     assert CK == 64 and shr_arena.shape == (B, cap) and image.shape[0] == B and image.shape[2] == KEY_IMAGE_FLOATS
     _rows_view_ok(key_arena), _rows_view_ok(shr_arena)

@@ -74,6 +74,8 @@ int cutie_affinity_topk_img(int num_segments, const void* const* seg_key, const 
  * tokens that provably cannot be in the top-k).
  * cutie_set_tc_min_tokens: banks smaller than n use plan 0 (default 6144; negative restores the default). */
 int cutie_affinity_plan_levels(int64_t n_total, int top_k);
+/* Diagnostics: byte offset of the per-query candidate counters inside the workspace of a filtered call (-1: exact scan). */
+int64_t cutie_debug_ws_count_offset(int64_t B, int64_t Q, int64_t n_total, int top_k);
 void cutie_set_tc_min_tokens(int64_t n);
 /* Diagnostics: per-phase device times (ms) of the filtered plan's launches (filter level, threshold select, ...,
  * exact re-rank) for one of the last 64 calls, measured in situ with events on the caller's stream. */

@@ -288,9 +288,13 @@ def gated_update(h, v):
     return f * h * (1 - u) + u * n
 
 
-ALL = ['bias_act_', 'bias_relu_maxpool', 'segment_tail', 'conv3x3_c1', 'area_pool', 'eca_scale_add_', 'gated_update', 'affinity_topk', 'topk_merge', 'readout_gather', 'usage_commit', 'bank_append', 'bank_export', 'bank_gather', 'bank_key_image', 'upsample2x_add', 'prob_to_mask',
+ALL = ['last_candidate_counts', 'bias_act_', 'bias_relu_maxpool', 'segment_tail', 'conv3x3_c1', 'area_pool', 'eca_scale_add_', 'gated_update', 'affinity_topk', 'topk_merge', 'readout_gather', 'usage_commit', 'bank_append', 'bank_export', 'bank_gather', 'bank_key_image', 'upsample2x_add', 'prob_to_mask',
        'consolidate', 'obj_summary_accumulate', 'qt_linear', 'qt_head_fold', 'qt_self_attention',
        'qt_aux_mask', 'qt_pixel_to_query', 'qt_query_to_pixel']
+
+
+def last_candidate_counts():
+    return None
 
 
 def install(monkeypatch=None):

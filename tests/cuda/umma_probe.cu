@@ -174,7 +174,65 @@ static int run_case(const char* name, int M, int N, int K, bool a_mn, bool b_mn,
   return bad == 0;
 }
 
+// ---- TMEM -> register bandwidth: W warps each issue R x tcgen05.ld.32x32b.x32 (4 KB per warp instruction) ----
+__global__ void __launch_bounds__(512, 1) tmem_read_kernel(int iters, long long* cycles, float* sink) {
+  __shared__ uint32_t tmem_base;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base;
+  float acc = 0.f;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    uint32_t r[32];
+    const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(((warp >> 2) * 32 + it * 128) & 511);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc += __uint_as_float(r[j] & 1u);
+  }
+  __syncthreads();
+  const long long t1 = clock64();
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+  if (acc == 12345.f) sink[0] = acc;
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+}
+
+static void tmem_bandwidth() {
+  long long* dc;
+  float* ds;
+  CK(cudaMalloc(&dc, 8 * 148));
+  CK(cudaMalloc(&ds, 4));
+  for (int warps : {4, 8, 16}) {
+    const int iters = 2000;
+    tmem_read_kernel<<<1, warps * 32, 0>>>(iters, dc, ds);
+    CK(cudaDeviceSynchronize());
+    long long c;
+    CK(cudaMemcpy(&c, dc, 8, cudaMemcpyDeviceToHost));
+    printf("TMEM read: %2d warps x %d x tcgen05.ld.32x32b.x32 (4 KB each): %lld cycles => %.1f B/clk/SM\n", warps, iters, c,
+           (double)warps * iters * 4096.0 / (double)c);
+  }
+  cudaFree(dc); cudaFree(ds);
+}
+
 int main() {
+  tmem_bandwidth();
   int ok = 0, n = 0;
   ok += run_case("A K-major, B K-major (control)", 128, 128, 64, false, false, 0); ++n;
   ok += run_case("A K-major, B K-major N=64", 128, 64, 64, false, false, 0); ++n;

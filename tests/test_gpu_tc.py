@@ -1,5 +1,5 @@
-"""tcgen05 (TF32) candidate filter + exact re-rank: numerics of the tensor-core contraction itself, and
-bit-identity of the filtered path with the exact fp32 scan."""
+"""tcgen05 candidate filters (TF32 with in-kernel producers; FP16 over the bank's key operand image) + exact re-rank:
+numerics of the tensor-core contraction itself, and bit-identity of the filtered paths with the exact fp32 scan."""
 import pytest
 import torch
 
@@ -75,13 +75,13 @@ def test_filter_keeps_duplicates_and_near_duplicates(K_, tc_everywhere):
 # key image (bulk-copy producer of the stride-1 filter level)
 # ---------------------------------------------------------------------------------------------------------
 def _image_offsets(row, elem):
-    """Byte offset of operand element `elem` (0..135) of token row `row` inside a 69632-byte tile
-    (csrc/tc_operand.cuh: 4 SWIZZLE_128B K-blocks of 32 tf32 + one un-swizzled 8-element tail block)."""
+    """Byte offset of FP16 operand element `elem` (0..143) of token row `row` inside a 36864-byte tile
+    (csrc/tc_operand_f16.cuh: 2 SWIZZLE_128B K-blocks of 64 f16 + one un-swizzled 16-element tail block)."""
     if elem < 128:
-        blk, chunk, within = elem >> 5, (elem & 31) >> 2, elem & 3
-        return blk * 16384 + row * 128 + ((chunk ^ (row & 7)) << 4) + within * 4
+        blk, w = elem >> 6, elem & 63
+        return blk * 16384 + row * 128 + (((w >> 3) ^ (row & 7)) << 4) + (w & 7) * 2
     e = elem - 128
-    return 4 * 16384 + (e >> 2) * 2048 + (row >> 3) * 128 + (row & 7) * 16 + (e & 3) * 4
+    return 2 * 16384 + (e >> 3) * 2048 + (row >> 3) * 128 + (row & 7) * 16 + (e & 7) * 2
 
 
 def test_key_image_layout_and_values(K_):
@@ -89,36 +89,52 @@ def test_key_image_layout_and_values(K_):
     B, cap = 2, 1000
     key = (torch.randn(B, cap, 64, generator=g) * 2).cuda()
     shr = (1 + torch.randn(B, cap, generator=g) ** 2).cuda()
+    key[0, 100] *= 200.0                               # shr k^2 beyond the f16 range: a flagged ("always candidate") row
     tiles = K_.key_image_tiles(cap)
     img = torch.full((B, tiles, K_.KEY_IMAGE_FLOATS), 7.0, device='cuda')
     p0, n = 77, 600                                   # unaligned range: rows outside it must stay untouched
     K_.bank_key_image(key, shr, p0, n, img)
-    img, key, shr = img.cpu(), key.cpu(), shr.cpu()
-    flat = img.reshape(B, tiles, -1)
+    untouched = torch.full((1,), 7.0).view(torch.float16)            # the two f16 halves of the fill pattern
+    key, shr = key.cpu(), shr.cpu()
+    flat = img.cpu().view(torch.float16).reshape(B, tiles, -1)       # [B, tiles, 18432] f16 elements
     rows = torch.arange(cap)
     t, r = rows // 128, rows % 128
-    eps = 1.65e-3
+    eps = 1.05e-3
     for b in range(B):
         inside = (rows >= p0) & (rows < p0 + n)
         ln = shr[b][:, None] * key[b]                                         # shr k    (fp32, same op order)
         sq = ln * key[b]                                                      # shr k^2
-        for c in (0, 1, 31, 32, 63):
+        sat = (torch.maximum(sq.abs().amax(1), ln.abs().amax(1)) > 60000.0)
+        assert bool(sat[100]) == (b == 0)
+        live = inside & ~sat
+        for c in (0, 1, 7, 8, 31, 32, 63):
             for which, want in ((0, sq[:, c]), (64, ln[:, c])):
-                off = torch.tensor([_image_offsets(int(x), which + c) // 4 for x in r])
+                off = torch.tensor([_image_offsets(int(x), which + c) // 2 for x in r])
                 got = flat[b, t, off]
-                assert torch.equal(got[inside], want[inside]), f'element {which + c}'
-                assert (got[~inside] == 7.0).all(), 'rows outside the range were written'
-        P = (shr[b] * key[b].pow(2).sum(1)).sqrt() * 1.002
-        R = shr[b].sqrt() * 1.002
-        tail = [shr[b], torch.zeros(cap), shr[b], -eps * P * P, -2 * eps * P * R, -eps * R * R, torch.zeros(cap), torch.zeros(cap)]
-        for e, want in enumerate(tail):
-            off = torch.tensor([_image_offsets(int(x), 128 + e) // 4 for x in r])
-            got = flat[b, t, off]
-            torch.testing.assert_close(got[inside], want[inside], rtol=2e-5, atol=1e-9)
-            # the bound factors must never be smaller than the exact ones (they are rounded UP by 1.002)
-        offP = torch.tensor([_image_offsets(int(x), 128 + 3) // 4 for x in r])
-        exactP2 = eps * (shr[b].double() * key[b].double().pow(2).sum(1))
-        assert (-(flat[b, t, offP][inside]).double() >= exactP2[inside]).all()
+                assert torch.equal(got[live], want[live].half()), f'element {which + c}'          # round to nearest f16
+                assert (got[inside & sat] == 0).all()
+                assert (got[~inside] == untouched[off[~inside] % 2]).all(), 'rows outside the range were written'
+        n2, n1 = key[b].double().pow(2).sum(1), key[b].double().abs().sum(1)
+        P2 = shr[b].double() * n2
+        tail = {0: shr[b].half().float(), 1: shr[b].half().float(), 6: torch.ones(cap), 7: torch.zeros(cap)}
+        for e, want in tail.items():
+            off = torch.tensor([_image_offsets(int(x), 128 + e) // 2 for x in r])
+            assert torch.equal(flat[b, t, off][live].float(), want[live]), e
+        for e in range(8, 16):
+            off = torch.tensor([_image_offsets(int(x), 128 + e) // 2 for x in r])
+            assert (flat[b, t, off][inside] == 0).all()
+        # the error-bound factors are rounded AWAY from zero: never smaller than the exact ones, never more than 1 % larger
+        bounds = {2: eps * P2, 3: 2 * eps * (P2 * shr[b].double()).sqrt(), 4: eps * shr[b].double(),
+                  5: 2.0 ** -25 * (P2 + shr[b].double() * n1)}
+        for e, exact in bounds.items():
+            off = torch.tensor([_image_offsets(int(x), 128 + e) // 2 for x in r])
+            got = -flat[b, t, off].double()
+            assert (got[live] >= exact[live]).all(), e
+            if e != 5:
+                assert (got[live] <= exact[live] * 1.012 + 1e-7).all(), e
+        # a flagged row: no energy terms, flag = -60000 (the filter sees D < any threshold; the sampler sees +60000)
+        offF = torch.tensor([_image_offsets(int(x), 128 + 7) // 2 for x in r])
+        assert (flat[b, t, offF][inside & sat].float() == -60000.0).all()
 
 
 def _arena_bank(K_, B, layout, seed):
@@ -140,6 +156,7 @@ def _arena_bank(K_, B, layout, seed):
     (1, 260, 30, [(3000, 1, 2999), (20000, 12345, 7000), (20000, 0, 5001)]),    # ring wrap: tail run + head run
     (2, 130, 30, [(700, 130, 500), (8000, 127, 7000), (8000, 7999, 1), (6000, 128, 3000)]),   # 4 runs, batch 2
     (1, 96, 64, [(80000, 3, 70001)]),                                       # 3 levels, kpad 64
+    (1, 1620, 30, [(420000, 1000, 413100)]),                                # BASELINE cfg 2 bank size
 ])
 def test_image_path_is_bit_identical_to_exact_scan(K_, tc_everywhere, B, Q, top_k, layout):
     segs, key, shr = _arena_bank(K_, B, layout, seed=11)
@@ -151,7 +168,7 @@ def test_image_path_is_bit_identical_to_exact_scan(K_, tc_everywhere, B, Q, top_
     before = K_.image_level_launches()
     acc = torch.zeros(B, N, dtype=torch.int64, device='cuda')
     idx, w, sim = K_.affinity_topk(segs, qk, qe, top_k, usage_acc=acc, want_sim=True)
-    assert K_.image_level_launches() == before + 1, 'the stride-1 level did not use the key image'
+    assert K_.image_level_launches() == before + 1, 'the FP16 image plan did not run'
     plain = [K_.BankSegment(s.key, s.shrinkage, ()) for s in segs]          # same bank, in-kernel producers
     idx_p, w_p, sim_p = K_.affinity_topk(plain, qk, qe, top_k, want_sim=True)
     assert K_.image_level_launches() == before + 1
@@ -161,7 +178,35 @@ def test_image_path_is_bit_identical_to_exact_scan(K_, tc_everywhere, B, Q, top_
     for a, b_ in ((idx, idx_x), (w, w_x), (sim, sim_x), (idx_p, idx_x), (w_p, w_x), (acc, acc_x)):
         assert torch.equal(a, b_)
     # and against float64 truth: the selected set is the true top-k up to fp32 near-ties
-    truth = mm.similarity_direct(key.cpu().transpose(1, 2), shr.cpu().unsqueeze(1), qk.cpu(), qe.cpu(), dtype=torch.float64)
-    n_dec, n_dec_eq, _, _ = mm.topk_set_agreement(idx[:, :, :top_k].cpu().long().transpose(1, 2), truth, top_k,
-                                                  rel_noise=1e-5)
-    assert n_dec > 0 and n_dec_eq == n_dec
+    truth = None if N * Q > 3e8 else mm.similarity_direct(key.cpu().transpose(1, 2), shr.cpu().unsqueeze(1), qk.cpu(), qe.cpu(),
+                                                         dtype=torch.float64)
+    if N * Q <= 3e8:
+        n_dec, n_dec_eq, _, _ = mm.topk_set_agreement(idx[:, :, :top_k].cpu().long().transpose(1, 2), truth, top_k,
+                                                      rel_noise=1e-5)
+        assert n_dec > 0 and n_dec_eq == n_dec
+
+
+@pytest.mark.parametrize('key_scale,q_scale,note', [
+    (1e-3, 1.0, 'tiny keys: shr k^2 ~ 1e-6 is an f16 subnormal (absolute error term)'),
+    (40.0, 1.0, 'huge keys: some rows exceed the f16 range and are flagged always-candidate'),
+    (1.0, 40.0, 'huge queries: b^2 > 3e4 does not fit f16 => those queries are re-ranked exhaustively'),
+    (300.0, 1.0, 'every row flagged: the filter passes everything, the exact re-rank decides'),
+])
+def test_image_path_outside_the_f16_range(K_, tc_everywhere, key_scale, q_scale, note):
+    g = torch.Generator().manual_seed(21)
+    B, cap, Q, top_k = 1, 6000, 200, 30
+    key = (torch.randn(B, cap, 64, generator=g) * key_scale).cuda()
+    if key_scale == 40.0:
+        key[:, ::3] /= 40.0                               # a mix of representable and flagged rows
+    shr = (1 + torch.randn(B, cap, generator=g) ** 2).cuda()
+    img = torch.zeros(B, K_.key_image_tiles(cap), K_.KEY_IMAGE_FLOATS, device='cuda')
+    K_.bank_key_image(key, shr, 0, cap, img)
+    qk = (torch.randn(B, 64, Q, generator=g) * q_scale).cuda()
+    if q_scale == 40.0:
+        qk[:, :, ::2] /= 40.0                             # half of the queries stay filterable
+    qe = torch.sigmoid(torch.randn(B, 64, Q, generator=g)).cuda()
+    seg = [K_.BankSegment(key, shr, (), img, 0)]
+    idx, w, sim = K_.affinity_topk(seg, qk, qe, top_k, want_sim=True)
+    K_.set_tc_min_tokens(1 << 40)
+    idx_x, w_x, sim_x = K_.affinity_topk([K_.BankSegment(key, shr, ())], qk, qe, top_k, want_sim=True)
+    assert torch.equal(idx, idx_x) and torch.equal(w, w_x) and torch.equal(sim, sim_x), note
