@@ -336,11 +336,13 @@ def run_ours(args, wl, rank, world, dev):
                 proc.step(frames_dev[state['t']], next_image=frames_dev[state['t'] + 1])
                 state['t'] += 1
             barrier()
-            lm, _ = device_arm(K, True, False)
+            lm, lh = device_arm(K, True, False)
             barrier()
-            le0, le1, _ = e2e_arm(K, True)
+            le0, le1, leh = e2e_arm(K, True)
             barrier()
             look = {'ms_total': lm[0].elapsed_time(lm[-1]), 'ms_e2e': le0.elapsed_time(le1)}
+            log(f'[rank {rank}] look-ahead arms: device {look["ms_total"] / K:.2f} ms/step (host enqueue {lh:.2f}), '
+                f'e2e {look["ms_e2e"] / K:.2f} ms/step (host enqueue {leh:.2f})')
     times = torch.tensor([ms_total, ms_e2e] + ([look['ms_total'], look['ms_e2e']] if look else [0.0, 0.0]),
                          dtype=torch.float64, device=dev)
     if world > 1:
@@ -426,6 +428,55 @@ def parity_check(proc, cfg, frame, dev):
            'what': 'one teacher-forced frame after the timed region: CUDA path vs oracle/cpu_core.py from the same live state'}
     log(f'[parity] {out}')
     return out
+
+
+def northstar_read_bench(dev, iters=50):
+    """BASELINE.json north_star size of the fused memory read: 480p queries (1620), 3 objects, 10 000 keys -- SURVEY.md
+    section 8(d): 39.1 MB algorithmic, HBM-bound (6.0 us at the measured copy bandwidth).  The read = cutie_affinity_topk
+    (FP16 image plan: sample, threshold, filter, re-rank) + cutie_readout_gather, timed with CUDA events over `iters`
+    back-to-back reads of a seeded synthetic bank.  The bank (2.6 MB of keys + 30.7 MB of values) fits the 126 MB L2 and
+    is NOT flushed between reads: the denominator stays the HBM roofline of the algorithmic bytes, as the north star
+    states it, and the line says so."""
+    import cutie_b200.kernels as K_
+    N, Q, K, top_k = 10000, 1620, 3, 30
+    g = torch.Generator().manual_seed(3)
+    key = torch.randn(1, N, 64, generator=g).to(dev)
+    shr = (1 + torch.randn(1, N, generator=g) ** 2).to(dev)
+    vals = tuple(torch.randn(1, N, 256, generator=g).to(dev) for _ in range(K))
+    qk = torch.randn(1, 64, Q, generator=g).to(dev)
+    qe = torch.sigmoid(torch.randn(1, 64, Q, generator=g)).to(dev)
+    img = torch.zeros(1, K_.key_image_tiles(N), K_.KEY_IMAGE_FLOATS, device=dev)
+    K_.bank_key_image(key, shr, 0, N, img)
+    seg = [K_.BankSegment(key, shr, vals, img, 0)]
+    with torch.inference_mode():
+        for _ in range(5):
+            idx, w, _ = K_.affinity_topk(seg, qk, qe, top_k)
+            out = K_.readout_gather(idx, w, seg)
+        torch.cuda.synchronize(dev)
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        l0 = K_.LAUNCH_COUNT
+        e0.record()
+        for _ in range(iters):
+            idx, w, _ = K_.affinity_topk(seg, qk, qe, top_k)
+        e1.record()
+        for _ in range(iters):
+            out = K_.readout_gather(idx, w, seg)
+        e2.record()
+        torch.cuda.synchronize(dev)
+    launches = (K_.LAUNCH_COUNT - l0) / iters
+    t_topk, t_gather = e0.elapsed_time(e1) / iters, e1.elapsed_time(e2) / iters
+    bytes_alg = N * 65 * 4 + min(N, Q * top_k) * K * 256 * 4 + Q * 128 * 4 + Q * K * 256 * 4
+    peaks = {'hbm_gbs': 6650.0}
+    pk = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    ms = t_topk + t_gather
+    ach = bytes_alg / (ms * 1e-3) / 1e9
+    return {'what': '480p queries, 3 objects, 10 000 keys: cutie_affinity_topk + cutie_readout_gather', 'bound': 'hbm',
+            'algorithmic_bytes': bytes_alg, 'ms': ms, 'affinity_topk_ms': t_topk, 'readout_gather_ms': t_gather,
+            'launches_per_read': launches, 'achieved': ach, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+            'frac': ach / peaks['hbm_gbs'], 'l2': 'bank fits L2 and is not flushed between reads (stated)',
+            'roofline_time_us': bytes_alg / (peaks['hbm_gbs'] * 1e9) * 1e6}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -598,6 +649,7 @@ def main():
     ap.add_argument('--no-graphs', action='store_true', help='eager launches only (no CUDA-graph frame regions)')
     ap.add_argument('--no-lookahead', action='store_true', help='skip the extension arm step(..., next_image=...)')
     ap.add_argument('--no-sharded-read', action='store_true', help='skip the key-sharded read benchmark at N > 1')
+    ap.add_argument('--no-northstar', action='store_true', help='skip the north-star-size memory-read micro-benchmark')
     ap.add_argument('--cpu-seconds', type=float, default=150.0)
     args = ap.parse_args()
     if args.warmup < 3:
@@ -622,6 +674,15 @@ def main():
     if world > 1:
         torch.distributed.init_process_group('nccl', device_id=dev)
     res = run_ours(args, wl, rank, world, dev)
+    northstar = None
+    if rank == 0 and not args.no_northstar:
+        try:
+            northstar = northstar_read_bench(dev)
+            log(f'[northstar] {northstar}')
+        except Exception as e:                                   # noqa: BLE001 -- reported in the line, never hidden
+            import traceback
+            traceback.print_exc()
+            northstar = {'error': f'{type(e).__name__}: {e}'[:300]}
     sharded = None
     if world > 1 and not args.no_sharded_read:
         try:
@@ -710,7 +771,7 @@ def main():
             'build': {'cuda_graphs': not args.no_graphs, 'optimize_for_inference': not args.no_optimize,
                       'cudnn_benchmark': not args.no_cudnn_benchmark, 'cudnn_allow_tf32': False, 'matmul_allow_tf32': False,
                       'conv_epilogues': res['epilogues'], 'glue_dispatch': res['glue']},
-            'sharded_read': sharded}
+            'roofline_northstar': northstar, 'sharded_read': sharded}
     emit(line)
 
 

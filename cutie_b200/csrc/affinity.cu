@@ -512,6 +512,7 @@ static int phase_begin(cudaStream_t st) {
 // Optional precomputed operand images of the arenas the segments live in (cutie_bank_key_image).
 struct ImageArgs {
   bool on;
+  const float* mu;            // [B][64] key centre of the images (null = 0)
   const float* img[kMaxSeg];
   long long bs[kMaxSeg];      // batch stride (floats)
   long long phys[kMaxSeg];    // physical index of the segment's first token inside its arena
@@ -582,6 +583,7 @@ static int run_filtered_f16(const ScanParams& base, long long B, char* ws, const
   fp.segs = base.segs;
   fp.qk = base.qk;
   fp.qe = base.qe;
+  fp.key_mu = ia.mu;
   fp.Q = base.Q;
   long long cum = 0;
   for (int s = 0; s < base.segs.nseg; ++s) {
@@ -595,13 +597,13 @@ static int run_filtered_f16(const ScanParams& base, long long B, char* ws, const
   }
   for (int s = base.segs.nseg; s <= kMaxSeg; ++s) fp.img_tcum[s] = cum;
   const int grid_x = f16_schedule(fp, B);
-  const int groups = (fp.full_groups > 0 ? fp.splits_full : fp.splits_half) * 64;    // threshold slots per query
+  const int groups = (fp.full_groups > 0 ? fp.splits_full : fp.splits_half) * 2 * F16_SLOTS;    // threshold slots per query
   if (groups > TC_CAP_BIG) return fail(-1, "%s: too many key splits for the threshold workspace", "run_filtered_f16");
   // sample every `stride`-th tile: every split of a query group should still see >= 8 tiles (its 64 slots then hold
   // minima over >= 16 tokens each); small banks are sampled whole
   const long long max_splits = fp.full_groups > 0 ? fp.splits_full : fp.splits_half;
   long long stride = cum / (8ll * max_splits);
-  if (stride > 16) stride = 16;
+  if (stride > 8) stride = 8;
   if (stride < 1) stride = 1;
   const int ph = phase_begin(st);
   float* group_min = (float*)(ws + wl.cand_e);
@@ -773,7 +775,8 @@ extern "C" int cutie_affinity_topk_img(int num_segments, const void* const* seg_
                                        const void* const* seg_shrinkage, const int64_t* seg_len,
                                        const int64_t* seg_key_bstride, const int64_t* seg_shr_bstride,
                                        const void* const* seg_key_image, const int64_t* seg_image_bstride,
-                                       const int64_t* seg_phys_begin, const float* qk, const float* qe, int64_t B,
+                                       const int64_t* seg_phys_begin, const float* key_mu, const float* qk,
+                                       const float* qe, int64_t B,
                                        int64_t CK, int64_t Q, int top_k, int kpad, int32_t* out_idx, float* out_w,
                                        float* out_sim, unsigned long long* usage_acc, int64_t n_total,
                                        void* workspace, size_t workspace_bytes, void* stream) {
@@ -804,6 +807,7 @@ extern "C" int cutie_affinity_topk_img(int num_segments, const void* const* seg_
   if (seg_key_image) {
     CUTIE_REQUIRE(seg_image_bstride && seg_phys_begin, "image strides / physical offsets missing");
     ia.on = true;
+    ia.mu = key_mu;
     for (int s = 0; s < num_segments; ++s) {
       if (seg_len[s] > 0 && !seg_key_image[s]) ia.on = false;          // a segment without an image: convert on the fly
       CUTIE_REQUIRE(seg_phys_begin[s] >= 0, "negative physical offset");
@@ -824,7 +828,7 @@ extern "C" int cutie_affinity_topk(int num_segments, const void* const* seg_key,
                                    float* out_sim, unsigned long long* usage_acc, int64_t n_total, void* workspace,
                                    size_t workspace_bytes, void* stream) {
   return cutie_affinity_topk_img(num_segments, seg_key, seg_shrinkage, seg_len, seg_key_bstride, seg_shr_bstride,
-                                 nullptr, nullptr, nullptr, qk, qe, B, CK, Q, top_k, kpad, out_idx, out_w, out_sim,
+                                 nullptr, nullptr, nullptr, nullptr, qk, qe, B, CK, Q, top_k, kpad, out_idx, out_w, out_sim,
                                  usage_acc, n_total, workspace, workspace_bytes, stream);
 }
 

@@ -18,7 +18,9 @@
 // every epilogue thread (= one query x one 64-column group of one CTA) keeps 32 running minima of U, one per register
 // of its tcgen05.ld -- 1 FMNMX per element, no memory traffic.  The minima of different (CTA, column group, register)
 // slots belong to DISJOINT token sets, so the k-th smallest of a query's slot minima is an upper bound of its k-th
-// smallest exact energy (f16_threshold_kernel).
+// smallest exact energy (f16_threshold_kernel).  8 slots per thread (register j folds into slot j % 8): with 22 key
+// splits a query owns 352 disjoint groups -- ~1.3 expected collisions among its 30 best, i.e. the bound lands on the
+// ~31st smallest instead of the 30th -- and the threshold kernel handles 11 values per lane instead of 44.
 //
 // Warp roles (576 threads): warps 0-15 epilogue (TMEM lane quarter = w & 3, query half = (w >> 2) & 1, 64-column group
 // = w >> 3), warp 16 bulk-copy producer (one thread), warp 17 TMEM allocator + single-thread MMA issuer.
@@ -66,6 +68,22 @@ __device__ __forceinline__ unsigned range_mask32(int a, int b) {      // bits [a
   const unsigned hi = b >= 32 ? 0xffffffffu : (b <= 0 ? 0u : ((1u << b) - 1u));
   const unsigned lo = a <= 0 ? 0xffffffffu : (a >= 32 ? 0u : ~((1u << a) - 1u));
   return hi & lo;
+}
+// three-input minimum (sm_100+): one ALU-pipe instruction per two new elements.  The epilogue is bound by the ALU pipe
+// (one warp instruction per 2 cycles per scheduler: ncu "math pipe throttle" was the top stall of the compare-and-mask
+// formulation, 2+ instructions per accumulator element), so everything per-element goes through min3 trees.
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+  float d;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float min32(const uint32_t (&r)[32]) {
+  float m[11];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) m[i] = fmin3(__uint_as_float(r[3 * i]), __uint_as_float(r[3 * i + 1]), __uint_as_float(r[3 * i + 2]));
+  m[10] = fminf(__uint_as_float(r[30]), __uint_as_float(r[31]));
+  const float a = fmin3(m[0], m[1], m[2]), b = fmin3(m[3], m[4], m[5]), c = fmin3(m[6], m[7], m[8]);
+  return fmin3(fmin3(a, b, c), m[9], m[10]);
 }
 // K-major un-swizzled (interleaved 8 x 16 B core matrices) descriptor of the [128 x 32 B] tail block
 __device__ __forceinline__ uint64_t desc_tail16(uint32_t addr) {
@@ -128,7 +146,7 @@ __global__ void __launch_bounds__(F16_THREADS, 1) affinity_f16_filter_kernel(con
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         ev[i] = qok ? __ldg(qe_p + (long long)(c0 + i) * p.Q) : 0.f;
-        kv[i] = qok ? __ldg(qk_p + (long long)(c0 + i) * p.Q) : 0.f;
+        kv[i] = qok ? __ldg(qk_p + (long long)(c0 + i) * p.Q) - (p.key_mu ? __ldg(p.key_mu + b * CKD + c0 + i) : 0.f) : 0.f;
       }
       uint32_t w0[4], w1[4];
 #pragma unroll
@@ -178,10 +196,10 @@ __global__ void __launch_bounds__(F16_THREADS, 1) affinity_f16_filter_kernel(con
       const long long bq = (long long)b * p.Q + (qok ? q : 0);
       int* my_idx = SAMPLE ? nullptr : p.cand_idx + bq * p.cap;
       int blk_base = 0, blk_used = F16_RESERVE;
-      float mn[32];
+      float mn[F16_SLOTS];
       if (SAMPLE) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) mn[j] = CUDART_INF_F;
+        for (int j = 0; j < F16_SLOTS; ++j) mn[j] = CUDART_INF_F;
       }
       const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(half * 128 + cg64 * 64);
       for (int t = 0; t < ntiles; ++t) {
@@ -197,19 +215,25 @@ __global__ void __launch_bounds__(F16_THREADS, 1) affinity_f16_filter_kernel(con
           if (SAMPLE) {
             if (it.lo <= c0 && it.hi >= c0 + 32) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) mn[j] = fminf(mn[j], __uint_as_float(r[j]));
+              for (int j = 0; j < F16_SLOTS; ++j) {             // 4 new values per slot: two min3
+                mn[j] = fmin3(mn[j], __uint_as_float(r[j]), __uint_as_float(r[j + F16_SLOTS]));
+                mn[j] = fmin3(mn[j], __uint_as_float(r[j + 2 * F16_SLOTS]), __uint_as_float(r[j + 3 * F16_SLOTS]));
+              }
             } else {
               const unsigned ok = range_mask32(it.lo - c0, it.hi - c0);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) mn[j] = ((ok >> j) & 1u) ? fminf(mn[j], __uint_as_float(r[j])) : mn[j];
+              for (int j = 0; j < 32; ++j)
+                mn[j % F16_SLOTS] = ((ok >> j) & 1u) ? fminf(mn[j % F16_SLOTS], __uint_as_float(r[j])) : mn[j % F16_SLOTS];
             }
           } else {
-            // branch-free per-lane bitmask of passing columns, then a per-lane walk over the lane's own passing columns
-            unsigned mask = 0u;
+            // candidates are rare (~0.1 % of the columns): a min3 tree decides "none here" in 16 instructions; only a
+            // lane that saw something builds its bitmask of passing columns and walks it
+            unsigned m = 0u;
+            if (min32(r) < thr) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(r[j]) < thr) ? (1u << j) : 0u;
-            mask &= range_mask32(it.lo - c0, it.hi - c0);
-            unsigned m = mask;
+              for (int j = 0; j < 32; ++j) m |= (__uint_as_float(r[j]) < thr) ? (1u << j) : 0u;
+              m &= range_mask32(it.lo - c0, it.hi - c0);
+            }
             while (m) {
               const int j = __ffs(m) - 1;
               m &= m - 1;
@@ -226,9 +250,9 @@ __global__ void __launch_bounds__(F16_THREADS, 1) affinity_f16_filter_kernel(con
       }
       if (SAMPLE) {
         if (qok) {
-          float* g = p.group_min + bq * (long long)p.groups_per_query + (long long)(split * 2 + cg64) * 32;
+          float* g = p.group_min + bq * (long long)p.groups_per_query + (long long)(split * 2 + cg64) * F16_SLOTS;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)      // thr = +inf marks a query whose operand row carries no valid bound
+          for (int j = 0; j < F16_SLOTS; j += 4)      // thr = +inf marks a query whose operand row carries no valid bound
             *reinterpret_cast<float4*>(g + j) = make_float4(mn[j] + thr, mn[j + 1] + thr, mn[j + 2] + thr, mn[j + 3] + thr);
         }
       } else if (blk_used < F16_RESERVE) {
@@ -289,7 +313,7 @@ __global__ void __launch_bounds__(F16_THREADS, 1) affinity_f16_filter_kernel(con
 // on the float bit patterns (energies are >= 0, so the unsigned order is the numeric order): 31 rounds of "how many values
 // are <= candidate", no sorting, no shared memory, deterministic.  Fewer than k finite slots (tiny sample) => +inf: every
 // token of that query is re-ranked.
-constexpr int THR_PER_LANE = 64;
+constexpr int THR_PER_LANE = 16;
 __global__ void __launch_bounds__(256) f16_threshold_kernel(const float* __restrict__ group_min, int groups, long long Q,
                                                             int top_k, float* __restrict__ emax_out) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -338,7 +362,7 @@ int f16_schedule(F16FilterParams& p, long long B) {
   const long long units = 2ll * p.full_groups + half_groups;             // half-tile work units per key tile
   long long u = sms / (units * B);
   if (u < 1) u = 1;
-  if (u > 16) u = 16;                              // 2u splits x 64 threshold slots <= 2048 (f16_threshold_kernel)
+  if (u > 16) u = 16;                              // 2u splits x 16 threshold slots <= 512 (f16_threshold_kernel)
   const long long tiles = p.img_tcum[p.segs.nseg];
   if (2 * u > tiles) u = (tiles + 1) / 2 > 0 ? (tiles + 1) / 2 : 1;
   p.splits_full = (int)(2 * u);

@@ -59,10 +59,12 @@ struct RerankParams {
 
 // FP16 filter over the key operand image (affinity_f16.cu): threshold sampling pass + candidate filter pass.
 constexpr int F16_RESERVE = 16;            // candidate slots reserved per global atomic (per thread)
+constexpr int F16_SLOTS = 8;               // running minima per sampling thread (threshold slots = splits x 2 x F16_SLOTS)
 struct F16FilterParams {
   KeySegments segs;
   const float* qk;
   const float* qe;
+  const float* key_mu;             // [B][64] centre the image was built with (null = 0): the operand uses qk - mu
   long long Q;
   // sample pass: tiles g = tile_phase + j * tile_stride of the image; output group_min [B][Q][groups_per_query]
   int tile_stride, tile_phase;

@@ -470,11 +470,35 @@ __global__ void __launch_bounds__(256) affinity_level_select_kernel(const Select
 // Exact re-rank of the last level's candidates: one CTA (4 warps) per query.  Each warp evaluates chunks of 32
 // candidates with the exact fp32 direct form and keeps a sorted top-k; warp 0 merges and finalises (softmax,
 // usage).  A query whose candidate list overflowed is rescanned exhaustively (slow, correct, rare).
+//
+// Candidate key rows (256 B each) are fetched COALESCED -- a half-warp per row, 16 independent LDG.128 per lane in flight
+// -- and staged in shared memory; each lane then evaluates its own candidate from shared memory with the same
+// channel-sequential fp32 arithmetic as the exact scan (`exact_similarity_smem`), so results stay bit-identical.  (A lane
+// reading its own row straight from global memory touches 32 different 128-byte lines per instruction: 512 L1 wavefronts
+// per 32 candidates against 64 here, and the re-rank was bound by exactly that.)
+constexpr int RR_LD = 68;                 // floats per staged row: 272 B, 16-byte aligned, conflict-free LDS.128 per quarter-warp
+
+__device__ __forceinline__ float exact_similarity_smem(const float* __restrict__ krow, float shr, const float* __restrict__ a,
+                                                       const float* __restrict__ b) {
+  float acc = 0.f;
+#pragma unroll
+  for (int c4 = 0; c4 < CKD / 4; ++c4) {
+    const float4 kf = *reinterpret_cast<const float4*>(krow + 4 * c4);
+    float d;
+    d = fmaf(a[4 * c4 + 0], kf.x, -b[4 * c4 + 0]); acc = fmaf(d, d, acc);
+    d = fmaf(a[4 * c4 + 1], kf.y, -b[4 * c4 + 1]); acc = fmaf(d, d, acc);
+    d = fmaf(a[4 * c4 + 2], kf.z, -b[4 * c4 + 2]); acc = fmaf(d, d, acc);
+    d = fmaf(a[4 * c4 + 3], kf.w, -b[4 * c4 + 3]); acc = fmaf(d, d, acc);
+  }
+  return acc * (-shr * rsqrtf((float)CKD));
+}
+
 template <int NS>
 __global__ void __launch_bounds__(128) affinity_rerank_kernel(const RerankParams p) {
   __shared__ float lv[4][KPAD_MAX];
   __shared__ int li[4][KPAD_MAX];
   __shared__ float qa[CKD], qb[CKD];
+  __shared__ __align__(16) float rows[4][32][RR_LD];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.y;
   const long long q = blockIdx.x;
@@ -491,22 +515,35 @@ __global__ void __launch_bounds__(128) affinity_rerank_kernel(const RerankParams
   const bool exhaustive = n > p.cap;
   if (exhaustive) n = (int)p.n_total;
   const int* cl = p.cand_idx + bq * p.cap;
+  const int h = lane >> 4, c4 = lane & 15;
   for (int base = warp * 32; base < n; base += 128) {
     const int j = base + lane;
-    float sv = -CUDART_INF_F;
-    int id = INT_MAX;
-    if (j < n) {
-      id = exhaustive ? j : cl[j];
-    }
-    if (j < n && id >= 0) {
+    int id = -1;
+    if (j < n) id = exhaustive ? j : cl[j];
+    const bool live = id >= 0;
+    float shr = 0.f;
+    const float* krow = nullptr;
+    if (live) {
       const int sg = seg_of(p.segs.begin, p.segs.nseg, id);
-      const float* krow = p.segs.key[sg] + (long long)b * p.segs.key_bs[sg] + ((long long)id - p.segs.begin[sg]) * CKD;
-      const float shr = p.segs.shr[sg][(long long)b * p.segs.shr_bs[sg] + ((long long)id - p.segs.begin[sg])];
-      sv = exact_similarity(krow, shr, qa, qb);
+      const long long off = (long long)id - p.segs.begin[sg];
+      krow = p.segs.key[sg] + (long long)b * p.segs.key_bs[sg] + off * CKD;
+      shr = __ldg(p.segs.shr[sg] + (long long)b * p.segs.shr_bs[sg] + off);
     }
+    // cooperative, coalesced fetch: at step it the two half-warps fetch rows 2 it and 2 it + 1 (16 lanes x 16 B each)
+    float4 piece[16];
+#pragma unroll
+    for (int it = 0; it < 16; ++it) {
+      const unsigned long long rp = __shfl_sync(0xffffffffu, (unsigned long long)krow, 2 * it + h);
+      piece[it] = rp ? __ldg(reinterpret_cast<const float4*>(rp) + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int it = 0; it < 16; ++it) *reinterpret_cast<float4*>(&rows[warp][2 * it + h][4 * c4]) = piece[it];
+    __syncwarp();
+    const float sv = live ? exact_similarity_smem(&rows[warp][lane][0], shr, qa, qb) : -CUDART_INF_F;
+    if (!live) id = INT_MAX;
     const float kth = lv[warp][p.top_k - 1];
     const int kthi = li[warp][p.top_k - 1];
-    unsigned bits = __ballot_sync(0xffffffffu, (j < n) && id >= 0 && (sv > kth || (sv == kth && id < kthi)));
+    unsigned bits = __ballot_sync(0xffffffffu, live && (sv > kth || (sv == kth && id < kthi)));
     while (bits) {
       const int src = __ffs(bits) - 1;
       bits &= bits - 1;
@@ -516,6 +553,7 @@ __global__ void __launch_bounds__(128) affinity_rerank_kernel(const RerankParams
       if (cs > k2 || (cs == k2 && ci < li[warp][p.top_k - 1]))
         list_insert<NS>(&lv[warp][0], &li[warp][0], lane, p.top_k, cs, ci);
     }
+    __syncwarp();      // the staging rows are overwritten by the next chunk
   }
   __syncthreads();
   if (warp == 0) {

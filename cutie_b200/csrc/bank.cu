@@ -11,10 +11,13 @@ namespace cutie {
 // tile is stored exactly as the FP16 filter wants it in shared memory (tc_operand_f16.cuh), so the filter fetches a
 // tile with ONE 36 KB bulk copy instead of converting 128 fp32 rows per tile per query block.
 // 16 lanes per token (coalesced 256-B key rows), 16 tokens per 256-thread CTA.
+// `mu` ([B][64] or null): the bank's key centre.  The image holds k - mu (and the filter's query operand qk - mu): the
+// energy sum_c qe (k - qk)^2 does not change, but the error bound eps shr (|k - mu| + v')^2 shrinks with |k - mu| --
+// network-derived keys sit on a large common mean (|mu| = 9.0 of |k| = 9.7 with the bench weights: an 8.5x smaller band).
 __global__ void __launch_bounds__(256) key_image_kernel(const float* __restrict__ key, long long key_bs,
                                                         const float* __restrict__ shr, long long shr_bs,
-                                                        long long phys0, long long n, unsigned char* __restrict__ img,
-                                                        long long img_bs_bytes) {
+                                                        const float* __restrict__ mu, long long phys0, long long n,
+                                                        unsigned char* __restrict__ img, long long img_bs_bytes) {
   const int b = blockIdx.y;
   const int c4 = threadIdx.x & 15;
   const long long i = (long long)blockIdx.x * 16 + (threadIdx.x >> 4);
@@ -25,6 +28,10 @@ __global__ void __launch_bounds__(256) key_image_kernel(const float* __restrict_
   if (live) {
     v = __ldg(reinterpret_cast<const float4*>(key + (long long)b * key_bs + phys * 64) + c4);
     sh = __ldg(shr + (long long)b * shr_bs + phys);
+    if (mu) {
+      const float4 m = __ldg(reinterpret_cast<const float4*>(mu + (long long)b * 64) + c4);
+      v = make_float4(v.x - m.x, v.y - m.y, v.z - m.z, v.w - m.w);
+    }
   }
   unsigned char* tile = img + (long long)b * img_bs_bytes + (phys >> 7) * (long long)F16_OPER_BYTES;
   store_key_row_operand_f16(tile, (int)(phys & 127), c4, v, sh, live);   // dead rows: shuffles only, no stores
@@ -215,14 +222,15 @@ extern "C" int cutie_bank_append(const float* src, int64_t src_bstride, float* d
 
 extern "C" int cutie_bank_key_image(const float* key_arena, int64_t key_bstride, const float* shr_arena,
                                     int64_t shr_bstride, int64_t B, int64_t phys_begin, int64_t n, float* image,
-                                    int64_t image_bstride, int64_t image_tiles, void* stream) {
+                                    int64_t image_bstride, int64_t image_tiles, const float* key_mu, void* stream) {
   CUTIE_REQUIRE(key_arena && shr_arena && image && B >= 1 && phys_begin >= 0 && n >= 0, "null/negative argument");
   CUTIE_REQUIRE((phys_begin + n + 127) / 128 <= image_tiles, "image too small for the token range");
   CUTIE_REQUIRE(((uintptr_t)image & 15) == 0 && ((uintptr_t)key_arena & 15) == 0, "16-byte alignment required");
   if (n == 0) return 0;
   dim3 grid((unsigned)((n + 15) / 16), (unsigned)B);
-  key_image_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(key_arena, key_bstride, shr_arena, shr_bstride, phys_begin,
-                                                         n, reinterpret_cast<unsigned char*>(image),
+  CUTIE_REQUIRE(key_mu == nullptr || ((uintptr_t)key_mu & 15) == 0, "key_mu must be 16-byte aligned");
+  key_image_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(key_arena, key_bstride, shr_arena, shr_bstride, key_mu,
+                                                         phys_begin, n, reinterpret_cast<unsigned char*>(image),
                                                          image_bstride * 4);
   CUTIE_CHECK_LAUNCH();
   return 0;

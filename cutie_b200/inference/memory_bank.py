@@ -46,6 +46,7 @@ class TokenArena:
         self.device = None
         # tcgen05 operand image of the 'key'/'shr' arrays (kernels.bank_key_image) + physical runs not yet imaged
         self.key_image: Optional[torch.Tensor] = None
+        self.image_mu: Optional[torch.Tensor] = None
         self.dirty: List[Tuple[int, int]] = []
 
     # -- allocation ------------------------------------------------------------------------
@@ -129,17 +130,21 @@ class TokenArena:
         s, n = run
         return self.arrays[name][:, s:s + n]
 
-    def flush_key_image(self) -> Optional[torch.Tensor]:
+    def flush_key_image(self, mu: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
         """Bring the operand image up to date with every row written since the last call (new memory frames:
-        one small launch; after a re-allocation or compaction: the whole arena)."""
+        one small launch; after a re-allocation or compaction: the whole arena).  `mu` [B, 64]: the bucket's key centre
+        (the image holds k - mu); one image is only ever built with one centre."""
         if not USE_KEY_IMAGE or 'key' not in self.arrays or self.widths.get('key') != 64:
             return None
         if self.key_image is None:
             self.key_image = torch.zeros(self.B, K_.key_image_tiles(self.cap), K_.KEY_IMAGE_FLOATS,
                                          dtype=torch.float32, device=self.device)
+            self.image_mu = mu
+        assert (mu is None) == (self.image_mu is None) and (mu is None or mu.data_ptr() == self.image_mu.data_ptr()), \
+            'a key image is tied to the centre it was first built with'
         for s, n in self.dirty:
             if n > 0:
-                K_.bank_key_image(self.arrays['key'], self.arrays['shr'], s, n, self.key_image)
+                K_.bank_key_image(self.arrays['key'], self.arrays['shr'], s, n, self.key_image, mu)
         self.dirty = []
         return self.key_image
 
@@ -155,10 +160,14 @@ class _Bucket:
 class KeyValueMemoryStore:
     """Arena-backed equivalent of cutie/inference/kv_memory_store.py:19-352."""
 
-    def __init__(self, save_selection: bool = False, save_usage: bool = False, ring: bool = True):
+    def __init__(self, save_selection: bool = False, save_usage: bool = False, ring: bool = True,
+                 key_centres: Optional[Dict[int, torch.Tensor]] = None):
         self.save_selection = save_selection
         self.save_usage = save_usage
         self.ring = ring
+        # bucket id -> key centre [B, 64] of the tcgen05 operand images (shared between the working and the long-term
+        # store of one MemoryManager: their segments are read in ONE affinity call and must agree on it)
+        self.key_centres: Dict[int, torch.Tensor] = {} if key_centres is None else key_centres
         self.global_bucket_id = 0
         self._b: Dict[int, _Bucket] = {}
         self.perm_end_pt: Dict[int, int] = defaultdict(int)
@@ -299,12 +308,28 @@ class KeyValueMemoryStore:
             regions.append((bk.perm, bk.perm.pieces()))
         if bk.temp.count:
             regions.append((bk.temp, bk.temp.pieces(temp_start, temp_len)))
+        mu = self.key_centre(bucket_id, regions)
         for arena, runs in regions:
-            image = arena.flush_key_image()
+            image = arena.flush_key_image(mu)
             for r in runs:
                 out.append(BankSegment(arena.view('key', r), arena.view('shr', r),
-                                       tuple(arena.view(('val', o), r) for o in objs), image, r[0]))
+                                       tuple(arena.view(('val', o), r) for o in objs), image, r[0],
+                                       mu if image is not None else None))
         return out
+
+    def key_centre(self, bucket_id: int, regions=None) -> Optional[torch.Tensor]:
+        """The bucket's key centre: the mean key of the first tokens it ever served (the permanent first frame), fixed
+        for the bucket's life.  Any vector is valid -- the energies do not depend on it -- it only tightens the FP16
+        filter's error bound (network-derived keys sit on a large common mean)."""
+        if not USE_KEY_IMAGE:
+            return None
+        mu = self.key_centres.get(bucket_id)
+        if mu is None and regions:
+            arena, runs = regions[0]
+            if runs and runs[0][1] > 0 and arena.widths.get('key') == 64:
+                mu = arena.view('key', runs[0]).mean(dim=1).contiguous()
+                self.key_centres[bucket_id] = mu
+        return mu
 
     def temp_runs(self, bucket_id: int, start: int = 0, length: Optional[int] = None):
         bk = self._b[bucket_id]
@@ -381,6 +406,7 @@ class KeyValueMemoryStore:
             bk.objects = [o for o in bk.objects if o in keep]
             if not bk.objects:
                 del self._b[b]
+                self.key_centres.pop(b, None)
 
     # -- channel-major materialisation (inspection / parity tests; never on the frame path) ----
     def _export(self, bucket_id: int, name, perm: bool, temp: bool = True) -> torch.Tensor:

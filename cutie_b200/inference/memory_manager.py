@@ -53,7 +53,8 @@ class MemoryManager:
         self.work_mem = KeyValueMemoryStore(save_selection=self.use_long_term, save_usage=self.use_long_term,
                                             ring=True)
         if self.use_long_term:
-            self.long_mem = KeyValueMemoryStore(save_usage=self.count_long_term_usage, ring=False)
+            self.long_mem = KeyValueMemoryStore(save_usage=self.count_long_term_usage, ring=False,
+                                                key_centres=self.work_mem.key_centres)
         self.config_stale = True
         self.engaged = False
         self.aux = None

@@ -103,6 +103,8 @@ class BankSegment(NamedTuple):
     # bank_key_image) and the run's first physical token index inside that arena
     key_image: Optional[torch.Tensor] = None
     phys_begin: int = 0
+    # the key centre [B, 64] the image was built with (bank_key_image(..., mu)); all segments of a call share it
+    key_mu: Optional[torch.Tensor] = None
 
     @property
     def n(self) -> int:
@@ -169,10 +171,16 @@ def affinity_topk(segments: Sequence[BankSegment], qk: torch.Tensor, qe: torch.T
             assert s.key_image.dtype == torch.float32 and s.key_image.shape[2] == KEY_IMAGE_FLOATS
             assert s.key_image.stride(2) == 1 and s.key_image.stride(1) == KEY_IMAGE_FLOATS
             assert (s.phys_begin + s.n + KEY_IMAGE_TILE - 1) // KEY_IMAGE_TILE <= s.key_image.shape[1]
+        mu = segments[0].key_mu
+        for s in segments:
+            assert (s.key_mu is None) == (mu is None) and (mu is None or s.key_mu.data_ptr() == mu.data_ptr()), \
+                'all key images of one read must have been built with the same key centre'
+        if mu is not None:
+            assert mu.shape == (B, CK) and mu.is_contiguous()
         img_args = (PA(*[s.key_image.data_ptr() for s in segments]), IA(*[s.key_image.stride(0) for s in segments]),
-                    IA(*[s.phys_begin for s in segments]))
+                    IA(*[s.phys_begin for s in segments]), _ptr(mu))
     else:
-        img_args = (None, None, None)
+        img_args = (None, None, None, None)
     # launches: exact scan = scan + merge; FP16 image plan = sample pass, threshold, filter pass, re-rank; TF32 levels
     # (no image) = one filter per level, a select between levels, re-rank
     with _call('affinity_topk', (4 if with_img else 2 * _lv) if _lv else 2):
@@ -487,11 +495,13 @@ def key_image_tiles(capacity: int) -> int:
     return (int(capacity) + KEY_IMAGE_TILE - 1) // KEY_IMAGE_TILE
 
 
-def bank_key_image(key_arena: torch.Tensor, shr_arena: torch.Tensor, phys_begin: int, n: int, image: torch.Tensor):
+def bank_key_image(key_arena: torch.Tensor, shr_arena: torch.Tensor, phys_begin: int, n: int, image: torch.Tensor,
+                   mu: Optional[torch.Tensor] = None):
     """(Re)build the tcgen05 operand image for tokens [phys_begin, phys_begin + n) of an arena.
 
     key_arena [B, cap, 64] and shr_arena [B, cap] token-major, image [B, tiles, KEY_IMAGE_FLOATS]: every
-    128-token physical tile holds [shr k^2 | shr k | error-bound tail] in the swizzled shared-memory layout of
+    128-token physical tile holds [shr k'^2 | shr k' | error-bound tail], k' = k - mu (mu [B, 64]: the bank's key centre,
+    None = 0; the filter subtracts the same mu from the query keys), in the swizzled shared-memory layout of
     the FP16 affinity filter (csrc/tc_operand_f16.cuh), so the filter fetches a tile with one 36 KB bulk copy.
     (The tensor's dtype is float32 only as a container: 9216 floats = 36864 bytes of f16 operands per tile.)"""
     B, cap, CK = key_arena.shape
@@ -499,10 +509,11 @@ def bank_key_image(key_arena: torch.Tensor, shr_arena: torch.Tensor, phys_begin:
     _rows_view_ok(key_arena), _rows_view_ok(shr_arena)
     assert image.stride(2) == 1 and image.stride(1) == KEY_IMAGE_FLOATS
     assert 0 <= phys_begin and phys_begin + n <= cap
+    assert mu is None or (mu.shape == (B, CK) and mu.is_contiguous())
     with _call('bank_key_image', 1):
         st = lib().cutie_bank_key_image(_ptr(key_arena), _i64(key_arena.stride(0)), _ptr(shr_arena),
                                         _i64(shr_arena.stride(0)), _i64(B), _i64(phys_begin), _i64(n), _ptr(image),
-                                        _i64(image.stride(0)), _i64(image.shape[1]), _stream())
+                                        _i64(image.stride(0)), _i64(image.shape[1]), _ptr(mu), _stream())
     _check(st, 'cutie_bank_key_image')
 
 

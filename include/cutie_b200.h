@@ -55,15 +55,18 @@ int cutie_affinity_topk(int num_segments, const void* const* seg_key, const void
                         const float* qk, const float* qe, int64_t B, int64_t CK, int64_t Q, int top_k, int kpad,
                         int32_t* out_idx, float* out_w, float* out_sim, unsigned long long* usage_acc,
                         int64_t n_total, void* workspace, size_t workspace_bytes, void* stream);
-/* Same call with the bank's precomputed tcgen05 operand image (cutie_bank_key_image): seg_key_image[s] is the image
- * of the ARENA segment s lives in ([B, tiles, 17408] floats, batch stride seg_image_bstride[s]), seg_phys_begin[s]
- * the segment's first token's index inside that arena.  With images the stride-1 filter level fetches every
- * 128-token tile with one 68 KB bulk copy (cp.async.bulk) instead of converting fp32 rows in the kernel; the
- * outputs are bit-identical to cutie_affinity_topk.  seg_key_image == NULL (or a NULL entry) = no images. */
+/* Same call with the bank's precomputed FP16 tcgen05 operand image (cutie_bank_key_image): seg_key_image[s] is the
+ * image of the ARENA segment s lives in ([B, tiles, 9216] floats = 36864 bytes of f16 operands per 128-token tile,
+ * batch stride seg_image_bstride[s]), seg_phys_begin[s] the segment's first token's index inside that arena, key_mu
+ * ([B, 64] or NULL) the key centre every one of those images was built with.  With images the call runs the FP16 plan
+ * (csrc/affinity_f16.cu): tile-sampled threshold pass, threshold select, candidate filter over the whole image (one
+ * 36 KB cp.async.bulk per tile), exact fp32 re-rank; the outputs are bit-identical to cutie_affinity_topk.
+ * seg_key_image == NULL (or a NULL entry) = no images (TF32 levels with in-kernel producers). */
 int cutie_affinity_topk_img(int num_segments, const void* const* seg_key, const void* const* seg_shrinkage,
                             const int64_t* seg_len, const int64_t* seg_key_bstride, const int64_t* seg_shr_bstride,
                             const void* const* seg_key_image, const int64_t* seg_image_bstride,
-                            const int64_t* seg_phys_begin, const float* qk, const float* qe, int64_t B, int64_t CK,
+                            const int64_t* seg_phys_begin, const float* key_mu, const float* qk, const float* qe,
+                            int64_t B, int64_t CK,
                             int64_t Q, int top_k, int kpad, int32_t* out_idx, float* out_w, float* out_sim,
                             unsigned long long* usage_acc, int64_t n_total, void* workspace,
                             size_t workspace_bytes, void* stream);
@@ -180,14 +183,14 @@ int cutie_prob_to_mask(const float* prob, int64_t plane_stride, int64_t row_stri
 int cutie_bank_append(const float* src, int64_t src_bstride, float* dst_rows, int64_t dst_bstride, int64_t B,
                       int64_t C, int64_t n, void* stream);
 /* Build / refresh the tcgen05 operand image for tokens [phys_begin, phys_begin + n) of an arena (key_arena
- * [B, cap, 64], shr_arena [B, cap] token-major; image [B, image_tiles, 17408] floats, image_tiles*128 >= cap).
+ * [B, cap, 64], shr_arena [B, cap] token-major; image [B, image_tiles, 9216] floats, image_tiles*128 >= cap; key_mu [B, 64] or NULL: the image holds k - mu.
  * Tile t of the image holds tokens [128 t, 128 t + 128) as [shr k^2 | shr k | shr, 0, shr, -eps P^2, -2 eps P R,
  * -eps R^2, 0, 0] in the filter's shared-memory layout (4 SWIZZLE_128B K-blocks + tail; csrc/tc_operand.cuh).
  * Called once per memory frame for the appended tokens -- the per-token part of get_similarity
  * (memory_utils.py:28-36: mk^2, shrinkage scaling) hoisted out of the per-frame read; no reference counterpart. */
 int cutie_bank_key_image(const float* key_arena, int64_t key_bstride, const float* shr_arena, int64_t shr_bstride,
                          int64_t B, int64_t phys_begin, int64_t n, float* image, int64_t image_bstride,
-                         int64_t image_tiles, void* stream);
+                         int64_t image_tiles, const float* key_mu, void* stream);
 /* dst[b,c,i] = rows[b,i,c]  (token-major -> channel-major; reference-shaped views for inspection). */
 int cutie_bank_export(const float* rows, int64_t rows_bstride, float* dst, int64_t dst_bstride, int64_t B,
                       int64_t C, int64_t n, void* stream);

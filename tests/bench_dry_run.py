@@ -103,4 +103,6 @@ bench.torch = _TorchProxy('torch')
 bench.WORKLOADS['tiny'] = dict(H=96, W=160, K=2, mem_frames=4, top_k=30, desc='dry run (CPU, emulated kernels)')
 if '--workload' not in sys.argv:
     sys.argv += ['--workload', 'tiny']
+if '--no-northstar' not in sys.argv:
+    sys.argv += ['--no-northstar']          # a 10 000-key read through the CPU emulation would take minutes
 bench.main()

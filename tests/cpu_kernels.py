@@ -119,7 +119,7 @@ def prob_to_mask(prob, lut):
     return lut[torch.argmax(prob, dim=0)]
 
 
-def bank_key_image(key_arena, shr_arena, phys_begin, n, image):
+def bank_key_image(key_arena, shr_arena, phys_begin, n, image, mu=None):
     pass        # the operand image only feeds the tcgen05 filter; the CPU emulation reads the fp32 rows
 
 

@@ -137,16 +137,19 @@ def test_key_image_layout_and_values(K_):
         assert (flat[b, t, offF][inside & sat].float() == -60000.0).all()
 
 
-def _arena_bank(K_, B, layout, seed):
-    """layout: list of (capacity, phys_begin, n) -- one arena per entry, the segment is rows [phys, phys+n)."""
+def _arena_bank(K_, B, layout, seed, centred=False):
+    """layout: list of (capacity, phys_begin, n) -- one arena per entry, the segment is rows [phys, phys+n).
+    centred: keys sit on a large common mean and the images are built around a key centre (as the runtime does)."""
     g = torch.Generator().manual_seed(seed)
     segs, keys, shrs = [], [], []
+    offset = (torch.randn(B, 1, 64, generator=g) * 4).cuda() if centred else 0.0
+    mu = (offset[:, 0] + 0.1).contiguous() if centred else None          # any vector is valid; a good one is near the mean
     for cap, p0, n in layout:
-        key = (torch.randn(B, cap, 64, generator=g) * 1.5).cuda()
+        key = (torch.randn(B, cap, 64, generator=g) * 1.5).cuda() + offset
         shr = (1 + torch.randn(B, cap, generator=g) ** 2).cuda()
         img = torch.full((B, K_.key_image_tiles(cap), K_.KEY_IMAGE_FLOATS), float('nan'), device='cuda')
-        K_.bank_key_image(key, shr, p0, n, img)        # everything outside the segment stays NaN on purpose
-        segs.append(K_.BankSegment(key[:, p0:p0 + n], shr[:, p0:p0 + n], (), img, p0))
+        K_.bank_key_image(key, shr, p0, n, img, mu)    # everything outside the segment stays NaN on purpose
+        segs.append(K_.BankSegment(key[:, p0:p0 + n], shr[:, p0:p0 + n], (), img, p0, mu))
         keys.append(key[:, p0:p0 + n]), shrs.append(shr[:, p0:p0 + n])
     return segs, torch.cat(keys, 1), torch.cat(shrs, 1)
 
@@ -158,12 +161,13 @@ def _arena_bank(K_, B, layout, seed):
     (1, 96, 64, [(80000, 3, 70001)]),                                       # 3 levels, kpad 64
     (1, 1620, 30, [(420000, 1000, 413100)]),                                # BASELINE cfg 2 bank size
 ])
-def test_image_path_is_bit_identical_to_exact_scan(K_, tc_everywhere, B, Q, top_k, layout):
-    segs, key, shr = _arena_bank(K_, B, layout, seed=11)
+@pytest.mark.parametrize('centred', [False, True])
+def test_image_path_is_bit_identical_to_exact_scan(K_, tc_everywhere, B, Q, top_k, layout, centred):
+    segs, key, shr = _arena_bank(K_, B, layout, seed=11, centred=centred)
     N = key.shape[1]
     assert K_.affinity_plan_levels(N, top_k) >= 2
     g = torch.Generator().manual_seed(5)
-    qk = (torch.randn(B, 64, Q, generator=g) * 1.5).cuda()
+    qk = (torch.randn(B, 64, Q, generator=g) * 1.5).cuda() + (segs[0].key_mu[:, :, None] if centred else 0.0)
     qe = torch.sigmoid(torch.randn(B, 64, Q, generator=g)).cuda()
     before = K_.image_level_launches()
     acc = torch.zeros(B, N, dtype=torch.int64, device='cuda')

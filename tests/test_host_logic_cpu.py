@@ -203,8 +203,12 @@ def test_key_image_tracks_every_written_row(cpu_kernels, monkeypatch):
     from cutie_b200.inference.memory_bank import KeyValueMemoryStore
     calls = []
 
-    def record(key_arena, shr_arena, phys_begin, n, image):
+    centres = set()
+
+    def record(key_arena, shr_arena, phys_begin, n, image, mu=None):
         assert image.shape[1] * K_.KEY_IMAGE_TILE >= key_arena.shape[1] and image.shape[2] == K_.KEY_IMAGE_FLOATS
+        assert mu is not None and mu.shape == (1, 64)
+        centres.add(mu.data_ptr())
         calls.append((key_arena.data_ptr(), phys_begin, n))
     monkeypatch.setattr(K_, 'bank_key_image', record)
     st = KeyValueMemoryStore(save_selection=False, save_usage=False)
@@ -227,6 +231,9 @@ def test_key_image_tracks_every_written_row(cpu_kernels, monkeypatch):
     segs = st.segments(0)
     bk = st._b[0]
     assert all(s.key_image is not None for s in segs)
+    # one key centre per bucket (the mean key of the permanent first frame), shared by every image and every segment
+    assert len(centres) == 1 and all(s.key_mu.data_ptr() in centres for s in segs)
+    assert torch.allclose(segs[0].key_mu, bk.perm.view('key', (0, 10)).mean(1))
     assert imaged_rows(bk.perm) == set(range(10)) and imaged_rows(bk.temp) == set(range(20))
     assert [s.phys_begin for s in segs] == [0, 0]
     calls.clear()
@@ -247,3 +254,5 @@ def test_key_image_tracks_every_written_row(cpu_kernels, monkeypatch):
     assert bk.temp.arrays['key'].data_ptr() != old_ptr
     assert imaged_rows(bk.temp) == set(range(65))
     assert segs[-1].key_image.shape[1] == K_.key_image_tiles(bk.temp.cap)
+    assert len(centres) == 1, 'the centre is fixed for the life of the bucket'
+
