@@ -513,6 +513,7 @@ static int phase_begin(cudaStream_t st) {
 struct ImageArgs {
   bool on;
   const float* mu;            // [B][64] key centre of the images (null = 0)
+  const int* seed_idx;        // [B][Q][kpad] threshold seeds (null = none)
   const float* img[kMaxSeg];
   long long bs[kMaxSeg];      // batch stride (floats)
   long long phys[kMaxSeg];    // physical index of the segment's first token inside its arena
@@ -617,7 +618,20 @@ static int run_filtered_f16(const ScanParams& base, long long B, char* ws, const
   int rc = launch_f16_filter(fp, B, grid_x, true, st);
   if (rc) return rc;
   phase_mark(ph, st);
-  rc = launch_f16_threshold(group_min, groups, B, base.Q, base.top_k, base.kpad, emax, st);
+  F16ThresholdParams tp;
+  memset(&tp, 0, sizeof(tp));
+  tp.group_min = group_min;
+  tp.groups = groups;
+  tp.top_k = base.top_k;
+  tp.kpad = base.kpad;
+  tp.Q = base.Q;
+  tp.n_total = base.n_total;
+  tp.emax_out = emax;
+  tp.seed_idx = ia.seed_idx;
+  tp.segs = base.segs;
+  tp.qk = base.qk;
+  tp.qe = base.qe;
+  rc = launch_f16_threshold(tp, B, st);
   if (rc) return rc;
   phase_mark(ph, st);
   e = cudaMemsetAsync(ws + wl.count, 0, (size_t)B * base.Q * 4, st);
@@ -775,8 +789,8 @@ extern "C" int cutie_affinity_topk_img(int num_segments, const void* const* seg_
                                        const void* const* seg_shrinkage, const int64_t* seg_len,
                                        const int64_t* seg_key_bstride, const int64_t* seg_shr_bstride,
                                        const void* const* seg_key_image, const int64_t* seg_image_bstride,
-                                       const int64_t* seg_phys_begin, const float* key_mu, const float* qk,
-                                       const float* qe, int64_t B,
+                                       const int64_t* seg_phys_begin, const float* key_mu, const int32_t* seed_idx,
+                                       const float* qk, const float* qe, int64_t B,
                                        int64_t CK, int64_t Q, int top_k, int kpad, int32_t* out_idx, float* out_w,
                                        float* out_sim, unsigned long long* usage_acc, int64_t n_total,
                                        void* workspace, size_t workspace_bytes, void* stream) {
@@ -808,6 +822,7 @@ extern "C" int cutie_affinity_topk_img(int num_segments, const void* const* seg_
     CUTIE_REQUIRE(seg_image_bstride && seg_phys_begin, "image strides / physical offsets missing");
     ia.on = true;
     ia.mu = key_mu;
+    ia.seed_idx = seed_idx;
     for (int s = 0; s < num_segments; ++s) {
       if (seg_len[s] > 0 && !seg_key_image[s]) ia.on = false;          // a segment without an image: convert on the fly
       CUTIE_REQUIRE(seg_phys_begin[s] >= 0, "negative physical offset");
@@ -828,7 +843,8 @@ extern "C" int cutie_affinity_topk(int num_segments, const void* const* seg_key,
                                    float* out_sim, unsigned long long* usage_acc, int64_t n_total, void* workspace,
                                    size_t workspace_bytes, void* stream) {
   return cutie_affinity_topk_img(num_segments, seg_key, seg_shrinkage, seg_len, seg_key_bstride, seg_shr_bstride,
-                                 nullptr, nullptr, nullptr, nullptr, qk, qe, B, CK, Q, top_k, kpad, out_idx, out_w, out_sim,
+                                 nullptr, nullptr, nullptr, nullptr, nullptr, qk, qe, B, CK, Q, top_k, kpad, out_idx, out_w,
+                                 out_sim,
                                  usage_acc, n_total, workspace, workspace_bytes, stream);
 }
 

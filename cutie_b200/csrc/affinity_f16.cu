@@ -314,39 +314,73 @@ __global__ void __launch_bounds__(F16_THREADS, 1) affinity_f16_filter_kernel(con
 // are <= candidate", no sorting, no shared memory, deterministic.  Fewer than k finite slots (tiny sample) => +inf: every
 // token of that query is re-ranked.
 constexpr int THR_PER_LANE = 16;
-__global__ void __launch_bounds__(256) f16_threshold_kernel(const float* __restrict__ group_min, int groups, long long Q,
-                                                            int top_k, float* __restrict__ emax_out) {
+__global__ void __launch_bounds__(256) f16_threshold_kernel(const F16ThresholdParams p) {
+  __shared__ float qab[8][2 * CKD];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long q = (long long)blockIdx.x * 8 + warp;
-  if (q >= Q) return;
-  const long long bq = (long long)blockIdx.y * Q + q;
-  const float* g = group_min + bq * (long long)groups;
+  if (q >= p.Q) return;
+  const int b = blockIdx.y;
+  const long long bq = (long long)b * p.Q + q;
+  const float* g = p.group_min + bq * (long long)p.groups;
   uint32_t v[THR_PER_LANE];
   int finite = 0;
 #pragma unroll
   for (int i = 0; i < THR_PER_LANE; ++i) {
     const int j = i * 32 + lane;
-    float e = j < groups ? __ldg(g + j) : CUDART_INF_F;
+    float e = j < p.groups ? __ldg(g + j) : CUDART_INF_F;
     e = (e >= 0.f) ? e : 0.f;                                  // a bound can round a hair below zero: still an upper bound at 0+
     const bool ok = e < 1e30f;                                 // empty (memset pattern) / flagged slots never count
     v[i] = ok ? __float_as_uint(e) : 0x7f800000u;
     finite += ok ? 1 : 0;
   }
   finite = __reduce_add_sync(0xffffffffu, finite);
-  if (finite < top_k) {
-    if (lane == 0) emax_out[bq] = CUDART_INF_F;
-    return;
-  }
-  uint32_t prefix = 0u;                                        // bits decided so far of the k-th smallest pattern
-  for (int bit = 30; bit >= 0; --bit) {
-    const uint32_t cand = prefix | ((1u << bit) - 1u);         // largest pattern with this bit clear
-    int c = 0;
+  float emax = CUDART_INF_F;
+  if (finite >= p.top_k) {
+    uint32_t prefix = 0u;                                      // bits decided so far of the k-th smallest pattern
+    for (int bit = 30; bit >= 0; --bit) {
+      const uint32_t cand = prefix | ((1u << bit) - 1u);       // largest pattern with this bit clear
+      int c = 0;
 #pragma unroll
-    for (int i = 0; i < THR_PER_LANE; ++i) c += (v[i] <= cand) ? 1 : 0;
-    c = __reduce_add_sync(0xffffffffu, c);
-    if (c < top_k) prefix |= (1u << bit);                      // fewer than k values at or below: the answer has the bit set
+      for (int i = 0; i < THR_PER_LANE; ++i) c += (v[i] <= cand) ? 1 : 0;
+      c = __reduce_add_sync(0xffffffffu, c);
+      if (c < p.top_k) prefix |= (1u << bit);                  // fewer than k values at or below: the answer has the bit set
+    }
+    emax = __uint_as_float(prefix) * (1.f + 1e-6f) + 1e-30f;
   }
-  if (lane == 0) emax_out[bq] = __uint_as_float(prefix) * (1.f + 1e-6f) + 1e-30f;
+  // Seeds: top_k DISTINCT tokens proposed by the caller (the previous frame's winners for this query position, re-indexed
+  // for what the ring dropped since).  The largest of their exact energies under THIS query bounds the k-th smallest
+  // exact energy -- in a temporally coherent video it is nearly the k-th smallest itself, far below what a 1/8 sample
+  // can offer.  A query with an invalid seed keeps the sampled bound.
+  if (p.seed_idx) {
+    for (int c = lane; c < CKD; c += 32) {
+      const long long off = ((long long)b * CKD + c) * p.Q + q;
+      const float a = sqrtf(__ldg(p.qe + off));
+      qab[warp][c] = a;
+      qab[warp][CKD + c] = a * __ldg(p.qk + off);
+    }
+    __syncwarp();
+    const bool mine = lane < p.top_k || (lane + 32 < p.top_k);
+    float worst = 0.f;
+    bool ok = true;
+    for (int j = lane; j < p.top_k; j += 32) {
+      const int id = __ldg(p.seed_idx + bq * p.kpad + j);
+      const bool valid = id >= 0 && id < p.n_total;
+      ok = ok && valid;
+      if (valid) {
+        const int sg = seg_of(p.segs.begin, p.segs.nseg, id);
+        const long long off = (long long)id - p.segs.begin[sg];
+        const float sv = exact_similarity(p.segs.key[sg] + (long long)b * p.segs.key_bs[sg] + off * CKD,
+                                          __ldg(p.segs.shr[sg] + (long long)b * p.segs.shr_bs[sg] + off), &qab[warp][0],
+                                          &qab[warp][CKD]);
+        worst = fmaxf(worst, -8.f * sv);
+      }
+    }
+    (void)mine;
+    ok = __all_sync(0xffffffffu, ok);
+    worst = warp_max(worst);
+    if (ok) emax = fminf(emax, worst * (1.f + 1e-5f) + 1e-30f);
+  }
+  if (lane == 0) p.emax_out[bq] = emax;
 }
 
 size_t f16_filter_smem_bytes() { return (size_t)(2 + F16_STAGES) * F16_OPER_BYTES + sizeof(F16Tail) + 64; }
@@ -387,12 +421,10 @@ int launch_f16_filter(const F16FilterParams& p, long long B, int grid_x, bool sa
   return 0;
 }
 
-int launch_f16_threshold(const float* group_min, int groups, long long B, long long Q, int top_k, int kpad, float* emax_out,
-                         cudaStream_t st) {
-  (void)kpad;
-  if (groups > THR_PER_LANE * 32) return fail(-1, "%s: too many threshold slots", "f16_threshold_kernel");
-  dim3 grid((unsigned)((Q + 7) / 8), (unsigned)B);
-  f16_threshold_kernel<<<grid, 256, 0, st>>>(group_min, groups, Q, top_k, emax_out);
+int launch_f16_threshold(const F16ThresholdParams& p, long long B, cudaStream_t st) {
+  if (p.groups > THR_PER_LANE * 32) return fail(-1, "%s: too many threshold slots", "f16_threshold_kernel");
+  dim3 grid((unsigned)((p.Q + 7) / 8), (unsigned)B);
+  f16_threshold_kernel<<<grid, 256, 0, st>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_cuda_error("f16_threshold_kernel", e);
   return 0;

@@ -87,8 +87,18 @@ struct F16FilterParams {
 size_t f16_filter_smem_bytes();
 int f16_schedule(F16FilterParams& p, long long B);
 int launch_f16_filter(const F16FilterParams& p, long long B, int grid_x, bool sample, cudaStream_t st);
-int launch_f16_threshold(const float* group_min, int groups, long long B, long long Q, int top_k, int kpad, float* emax_out,
-                         cudaStream_t st);
+struct F16ThresholdParams {
+  const float* group_min;      // [B][Q][groups] slot minima of the sample pass
+  int groups, top_k, kpad;
+  long long Q, n_total;
+  float* emax_out;             // [B][Q]
+  // optional seeds: [B][Q][kpad] token indices (first top_k entries; -1 = none), evaluated exactly against this query
+  const int* seed_idx;
+  KeySegments segs;
+  const float* qk;
+  const float* qe;
+};
+int launch_f16_threshold(const F16ThresholdParams& p, long long B, cudaStream_t st);
 
 size_t tc_filter_smem_bytes();
 int tc_split_count(long long B, long long Q, long long samp_count);

@@ -48,6 +48,11 @@ class TokenArena:
         self.key_image: Optional[torch.Tensor] = None
         self.image_mu: Optional[torch.Tensor] = None
         self.dirty: List[Tuple[int, int]] = []
+        # logical-order bookkeeping for readers that remember token indices across frames (threshold seeds): tokens ever
+        # pushed / dropped from the front, and a generation that changes whenever the order changes any other way
+        self.total_pushed = 0
+        self.total_dropped = 0
+        self.generation = 0
 
     # -- allocation ------------------------------------------------------------------------
     def declare(self, name, width: int, B: int, device):
@@ -110,6 +115,7 @@ class TokenArena:
         if not self.ring:
             assert self.head == 0
         self.count += n
+        self.total_pushed += n
         self.dirty += runs                   # the caller fills these rows next; imaged lazily by flush_key_image
         return runs
 
@@ -117,6 +123,7 @@ class TokenArena:
         n = min(n, self.count)
         if n <= 0:
             return
+        self.total_dropped += n
         if self.ring:
             self.head = (self.head + n) % self.cap
             self.count -= n
@@ -392,6 +399,7 @@ class KeyValueMemoryStore:
             fresh[name] = dst
         arena.arrays = fresh
         arena.count = max_size
+        arena.generation += 1                # tokens re-ordered by usage: remembered indices are void
         arena.dirty = [(0, max_size)]
 
     # -- object removal (kv:280-307) ---------------------------------------------------------

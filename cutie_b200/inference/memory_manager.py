@@ -58,6 +58,7 @@ class MemoryManager:
         self.config_stale = True
         self.engaged = False
         self.aux = None
+        self._prev_topk = {}           # bucket -> (idx of the last read, layout tag): threshold seeds of the next read
 
     def _read_sizes(self, cfg):
         # the first frame lives in permanent memory and is not counted (memory_manager.py:27-38)
@@ -108,13 +109,38 @@ class MemoryManager:
         usage_acc = None
         if self.use_long_term:
             usage_acc = torch.zeros(bs, sum(s.n for s in key_segs), dtype=torch.int64, device=qk.device)
-        idx, wgt, _ = K_.affinity_topk(key_segs, qk, qe, self.top_k, usage_acc=usage_acc)
+        seed, tag = self._threshold_seeds(bucket_id, qk)
+        idx, wgt, _ = K_.affinity_topk(key_segs, qk, qe, self.top_k, usage_acc=usage_acc, seed_idx=seed)
+        if tag is not None:
+            self._prev_topk[bucket_id] = (idx,) + tag
         if self.use_long_term:
             # usage of the temporary working tokens; permanent tokens are skipped (kv:157)
             self.work_mem.update_bucket_usage(bucket_id, usage_acc, long_n + self.work_mem.perm_size(bucket_id))
             if long_n and self.count_long_term_usage:
                 self.long_mem.update_bucket_usage(bucket_id, usage_acc, 0)
         return lambda objects: K_.readout_gather(idx, wgt, self._segments(bucket_id, objects))
+
+    def _threshold_seeds(self, bucket_id: int, qk: torch.Tensor):
+        """The previous read's winners of this bucket, re-indexed for what the ring dropped since, as threshold seeds for
+        the candidate filter (kernels.affinity_topk(seed_idx=...)): in a temporally coherent video the k tokens that won
+        for a pixel on the last frame are still (nearly) the k best, so the largest of their exact energies is a far
+        tighter bound than a sampled one.  Exactness never depends on them.  FIFO working memory only (long-term
+        consolidation re-orders tokens): returns (seed or None, tag to store with this read's result or None)."""
+        if self.use_long_term:
+            return None, None
+        bk = self.work_mem._b[bucket_id]
+        tag = (bk.perm.count, bk.perm.generation, bk.temp.generation, bk.temp.total_dropped, tuple(qk.shape))
+        prev = self._prev_topk.get(bucket_id)
+        if prev is None:
+            return None, tag
+        idx, P, gp, gt, dropped0, shape = prev
+        if (P, gp, gt, shape) != (tag[0], tag[1], tag[2], tag[4]):
+            return None, tag
+        d = bk.temp.total_dropped - dropped0
+        if d == 0:
+            return idx, tag
+        moved = idx - d                                  # temporary tokens slid towards the permanent prefix by d
+        return torch.where(idx < P, idx, torch.where(moved >= P, moved, torch.full_like(idx, -1))), tag
 
     def _segments(self, bucket_id: int, obj_ids: List[int]):
         segs = []
@@ -238,6 +264,7 @@ class MemoryManager:
 
     def purge_except(self, obj_keep_idx: List[int]) -> None:
         """memory_manager.py:298-307 -- including its quirk: obj_v entries of purged objects are kept."""
+        self._prev_topk.clear()
         self.work_mem.purge_except(obj_keep_idx)
         if self.use_long_term and self.long_mem.engaged():
             self.long_mem.purge_except(obj_keep_idx)

@@ -134,7 +134,8 @@ def kpad_for(top_k: int) -> int:
 
 
 def affinity_topk(segments: Sequence[BankSegment], qk: torch.Tensor, qe: torch.Tensor, top_k: int,
-                  usage_acc: Optional[torch.Tensor] = None, want_sim: bool = False):
+                  usage_acc: Optional[torch.Tensor] = None, want_sim: bool = False,
+                  seed_idx: Optional[torch.Tensor] = None):
     """Anisotropic-L2 similarity of every query against every memory token of `segments`, exact
     top-k per query, softmax over the k winners.
 
@@ -143,6 +144,9 @@ def affinity_topk(segments: Sequence[BankSegment], qk: torch.Tensor, qe: torch.T
     (-1, 0).  idx counts tokens across `segments` in order.  Winners are ordered by descending
     similarity, ties toward the lower index.  If usage_acc (int64 [B, N_total], zeroed by the caller) is
     given, w * 2^40 is accumulated per token (deterministic integer adds).
+    seed_idx (int32 [B, Q, kpad], image plan only): per query top_k distinct token indices of THIS bank (-1 = none) --
+    typically the previous frame's winners; their exact energies tighten the candidate filter's threshold.  The
+    result never depends on them (any k distinct tokens bound the k-th smallest energy from above).
     """
     B, CK, Q = qk.shape
     n_total = sum(s.n for s in segments)
@@ -177,10 +181,12 @@ def affinity_topk(segments: Sequence[BankSegment], qk: torch.Tensor, qe: torch.T
                 'all key images of one read must have been built with the same key centre'
         if mu is not None:
             assert mu.shape == (B, CK) and mu.is_contiguous()
+        if seed_idx is not None:
+            assert seed_idx.shape == (B, Q, kpad) and seed_idx.is_contiguous()
         img_args = (PA(*[s.key_image.data_ptr() for s in segments]), IA(*[s.key_image.stride(0) for s in segments]),
-                    IA(*[s.phys_begin for s in segments]), _ptr(mu))
+                    IA(*[s.phys_begin for s in segments]), _ptr(mu), _ptr(seed_idx, torch.int32))
     else:
-        img_args = (None, None, None, None)
+        img_args = (None, None, None, None, None)
     # launches: exact scan = scan + merge; FP16 image plan = sample pass, threshold, filter pass, re-rank; TF32 levels
     # (no image) = one filter per level, a select between levels, re-rank
     with _call('affinity_topk', (4 if with_img else 2 * _lv) if _lv else 2):

@@ -61,12 +61,14 @@ int cutie_affinity_topk(int num_segments, const void* const* seg_key, const void
  * ([B, 64] or NULL) the key centre every one of those images was built with.  With images the call runs the FP16 plan
  * (csrc/affinity_f16.cu): tile-sampled threshold pass, threshold select, candidate filter over the whole image (one
  * 36 KB cp.async.bulk per tile), exact fp32 re-rank; the outputs are bit-identical to cutie_affinity_topk.
+ * seed_idx ([B, Q, kpad] or NULL): per query top_k DISTINCT token indices (e.g. the previous frame's winners) whose
+ * exact energies tighten the filter threshold; they never change the result, only how many candidates are re-ranked.
  * seg_key_image == NULL (or a NULL entry) = no images (TF32 levels with in-kernel producers). */
 int cutie_affinity_topk_img(int num_segments, const void* const* seg_key, const void* const* seg_shrinkage,
                             const int64_t* seg_len, const int64_t* seg_key_bstride, const int64_t* seg_shr_bstride,
                             const void* const* seg_key_image, const int64_t* seg_image_bstride,
-                            const int64_t* seg_phys_begin, const float* key_mu, const float* qk, const float* qe,
-                            int64_t B, int64_t CK,
+                            const int64_t* seg_phys_begin, const float* key_mu, const int32_t* seed_idx, const float* qk,
+                            const float* qe, int64_t B, int64_t CK,
                             int64_t Q, int top_k, int kpad, int32_t* out_idx, float* out_w, float* out_sim,
                             unsigned long long* usage_acc, int64_t n_total, void* workspace,
                             size_t workspace_bytes, void* stream);

@@ -17,7 +17,7 @@ def _cat_rows(rows):
     return torch.cat(list(rows), dim=1)
 
 
-def affinity_topk(segments, qk, qe, top_k, usage_acc=None, want_sim=False):
+def affinity_topk(segments, qk, qe, top_k, usage_acc=None, want_sim=False, seed_idx=None):
     from cutie_b200.kernels import kpad_for, KernelError
     keys = _cat_rows([s.key for s in segments])                 # [B,N,CK]
     shr = _cat_rows([s.shrinkage for s in segments])            # [B,N]

@@ -214,3 +214,32 @@ def test_image_path_outside_the_f16_range(K_, tc_everywhere, key_scale, q_scale,
     K_.set_tc_min_tokens(1 << 40)
     idx_x, w_x, sim_x = K_.affinity_topk([K_.BankSegment(key, shr, ())], qk, qe, top_k, want_sim=True)
     assert torch.equal(idx, idx_x) and torch.equal(w, w_x) and torch.equal(sim, sim_x), note
+
+
+def test_threshold_seeds_never_change_the_result(K_, tc_everywhere):
+    """seed_idx only tightens the filter threshold: the previous winners (the runtime's use), random distinct tokens,
+    partly invalid lists and the true answer itself all give the bit-identical selection."""
+    segs, key, shr = _arena_bank(K_, 1, [(20000, 12345, 7000), (20000, 0, 5001)], seed=4, centred=True)
+    N, Q, top_k = key.shape[1], 260, 30
+    g = torch.Generator().manual_seed(6)
+    qk = (torch.randn(1, 64, Q, generator=g) * 1.5).cuda() + segs[0].key_mu[:, :, None]
+    qe = torch.sigmoid(torch.randn(1, 64, Q, generator=g)).cuda()
+    idx0, w0, s0 = K_.affinity_topk(segs, qk, qe, top_k, want_sim=True)
+    K_.KEEP_LAST_WORKSPACE = True
+    try:
+        rand = torch.stack([torch.randperm(N, generator=g)[:32] for _ in range(Q)])[None].int().cuda()
+        rand[:, :, 30:] = -1
+        partly = rand.clone()
+        partly[:, ::3, 5] = -1                                            # every third query has an invalid seed
+        partly[:, 1::3, 7] = N + 5
+        counts = {}
+        for name, seed in (('true winners', idx0), ('random distinct', rand), ('partly invalid', partly)):
+            idx, w, s = K_.affinity_topk(segs, qk, qe, top_k, want_sim=True, seed_idx=seed.contiguous())
+            assert torch.equal(idx, idx0) and torch.equal(w, w0) and torch.equal(s, s0), name
+            counts[name] = float(K_.last_candidate_counts().float().mean())
+        idx, _, _ = K_.affinity_topk(segs, qk, qe, top_k)
+        counts['no seeds'] = float(K_.last_candidate_counts().float().mean())
+    finally:
+        K_.KEEP_LAST_WORKSPACE = False
+    print('candidates per query:', counts)
+    assert counts['true winners'] <= counts['no seeds'] and counts['true winners'] < 4 * top_k
