@@ -457,12 +457,19 @@ def northstar_read_bench(dev, iters=50):
         l0 = K_.LAUNCH_COUNT
         e0.record()
         for _ in range(iters):
-            idx, w, _ = K_.affinity_topk(seg, qk, qe, top_k)
+            idx, w, _ = K_.affinity_topk(seg, qk, qe, top_k, seed_idx=idx)       # steady state: last read's winners seed this one
         e1.record()
         for _ in range(iters):
             out = K_.readout_gather(idx, w, seg)
         e2.record()
         torch.cuda.synchronize(dev)
+        K_.phase_timing(True)                                                    # per-launch breakdown (separate, untimed reads)
+        for _ in range(8):
+            K_.affinity_topk(seg, qk, qe, top_k, seed_idx=idx)
+        torch.cuda.synchronize(dev)
+        ph = [p for p in (K_.phase_times(i) for i in range(8)) if p]
+        K_.phase_timing(False)
+        phases = [sum(p[i] for p in ph) / len(ph) for i in range(min(len(p) for p in ph))] if ph else None
     launches = (K_.LAUNCH_COUNT - l0) / iters
     t_topk, t_gather = e0.elapsed_time(e1) / iters, e1.elapsed_time(e2) / iters
     bytes_alg = N * 65 * 4 + min(N, Q * top_k) * K * 256 * 4 + Q * 128 * 4 + Q * K * 256 * 4
@@ -474,7 +481,7 @@ def northstar_read_bench(dev, iters=50):
     ach = bytes_alg / (ms * 1e-3) / 1e9
     return {'what': '480p queries, 3 objects, 10 000 keys: cutie_affinity_topk + cutie_readout_gather', 'bound': 'hbm',
             'algorithmic_bytes': bytes_alg, 'ms': ms, 'affinity_topk_ms': t_topk, 'readout_gather_ms': t_gather,
-            'launches_per_read': launches, 'achieved': ach, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+            'launches_per_read': launches, 'affinity_phases_ms': phases, 'achieved': ach, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
             'frac': ach / peaks['hbm_gbs'], 'l2': 'bank fits L2 and is not flushed between reads (stated)',
             'roofline_time_us': bytes_alg / (peaks['hbm_gbs'] * 1e9) * 1e6}
 
@@ -584,15 +591,20 @@ def sharded_read_bench(rank, world, dev):
     lo, hi = shard_bounds(n_total, world, rank)
     gl = torch.Generator().manual_seed(100 + rank)
     vals_local = [torch.randn(B, hi - lo, 256, generator=gl).to(dev) for _ in range(K)]
-    seg = K_.BankSegment(key[:, lo:hi].to(dev), shr[:, lo:hi].to(dev), tuple(vals_local))
+    key_l, shr_l = key[:, lo:hi].to(dev).contiguous(), shr[:, lo:hi].to(dev).contiguous()
+    img = torch.zeros(B, K_.key_image_tiles(hi - lo), K_.KEY_IMAGE_FLOATS, device=dev)      # as the runtime's arenas keep it
+    K_.bank_key_image(key_l, shr_l, 0, hi - lo, img)
+    seg = K_.BankSegment(key_l, shr_l, tuple(vals_local), img, 0)
     ev = lambda: torch.cuda.Event(enable_timing=True)
     res = {'keys': n_total, 'keys_per_rank': hi - lo, 'queries': Q, 'objects': K, 'ranks': world}
     with torch.inference_mode():
         def one(mode):
             e = [ev() for _ in range(4)]
+            marks = []
             e[0].record()
-            idx_l, w_l, idx, w = sharded_topk([seg], lo, n_total, qk, qe, top_k)
+            idx_l, w_l, idx, w = sharded_topk([seg], lo, n_total, qk, qe, top_k, marks=marks)
             e[1].record()
+            e += [e[0]] + marks + [e[1]]           # [4..7]: begin, after local top-k, after all-gather, after merge
             part = K_.readout_gather(idx_l, w_l, [seg])          # [B, K, 256, Q] partial sums over this rank's winners
             e[2].record()
             if mode == 'all_reduce':
@@ -608,16 +620,19 @@ def sharded_read_bench(rank, world, dev):
                 one(mode)
             dist.barrier()
             torch.cuda.synchronize(dev)
-            t = [[], [], []]
+            t = [[] for _ in range(6)]
             for _ in range(10):
                 e, idx, w, out = one(mode)
                 torch.cuda.synchronize(dev)
                 for i in range(3):
                     t[i].append(e[i].elapsed_time(e[i + 1]))
+                for i in range(3):
+                    t[3 + i].append(e[4 + i].elapsed_time(e[5 + i]))
             tm = torch.tensor([sum(x) / len(x) for x in t], dtype=torch.float64, device=dev)
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
             res[mode] = {'topk_allgather_merge_ms': float(tm[0]), 'local_gather_ms': float(tm[1]),
-                         'collective_ms': float(tm[2]), 'total_ms': float(tm.sum())}
+                         'collective_ms': float(tm[2]), 'total_ms': float(tm[:3].sum()),
+                         'local_topk_ms': float(tm[3]), 'candidate_allgather_ms': float(tm[4]), 'merge_ms': float(tm[5])}
         res['allgather_bytes_per_rank'] = int(idx.numel() * 8)
         res['readout_bytes'] = int(B * K * 256 * Q * 4)
         # bit-identity with the unsharded read (rank 0 holds the whole key bank for the check)
@@ -628,7 +643,7 @@ def sharded_read_bench(rank, world, dev):
             ok[0] = float(torch.equal(idx, ridx) and torch.equal(w, rw))
         dist.broadcast(ok, 0)
         res['bit_identical_to_unsharded'] = bool(ok.item())
-    res['limiting'] = max(('topk_allgather_merge_ms', 'local_gather_ms', 'collective_ms'),
+    res['limiting'] = max(('local_topk_ms', 'candidate_allgather_ms', 'merge_ms', 'local_gather_ms', 'collective_ms'),
                           key=lambda k: res['reduce_scatter'][k])
     return res
 

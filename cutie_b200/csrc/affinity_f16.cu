@@ -38,7 +38,7 @@ constexpr int F16_STAGES = 3;
 constexpr int F16_QT = 256;                 // queries per CTA (two MMA M = 128 halves)
 
 struct F16Tail {
-  unsigned long long full[F16_STAGES], empty[F16_STAGES], tfull[2], tempty[2];
+  unsigned long long full[F16_STAGES], empty[F16_STAGES], tfull[2], tempty[2], aready;
   uint32_t tmem_base;
   float thr[F16_QT];          // per query row: filter threshold (filter pass) / +inf for a query that cannot be bounded (sample pass)
 };
@@ -128,9 +128,14 @@ __global__ void __launch_bounds__(F16_THREADS, 1) affinity_f16_filter_kernel(con
   if (tid == 0) {
     for (int s = 0; s < F16_STAGES; ++s) { mbar_init(smem_u32(&T.full[s]), 1); mbar_init(smem_u32(&T.empty[s]), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&T.tfull[a]), 1); mbar_init(smem_u32(&T.tempty[a]), 32 * 8 * halves); }
+    mbar_init(smem_u32(&T.aready), F16_QT);
     mbar_init_fence();
   }
   if (warp == 17) tmem_alloc<512>(smem_u32(&T.tmem_base));
+  tc_fence_before();
+  __syncthreads();          // barriers + TMEM exist; from here the roles run free: the key tiles are already being copied
+  tc_fence_after();         // while warps 0-7 build the query operand (the MMA issuer waits for `aready`)
+  const uint32_t tmem = T.tmem_base;
   // ---- query operand: thread == query row (tid < 256): [qe | -2 qe qk] + tail ----
   if (tid < F16_QT) {
     const int half = tid >> 7, row = tid & 127;
@@ -140,26 +145,30 @@ __global__ void __launch_bounds__(F16_THREADS, 1) affinity_f16_filter_kernel(con
     const float* qe_p = p.qe + (long long)b * CKD * p.Q + (qok ? q : 0);
     const float* qk_p = p.qk + (long long)b * CKD * p.Q + (qok ? q : 0);
     float b2 = 0.f, a1 = 0.f;
+    // 32 channels per batch: 64 independent loads in flight (the prologue is latency-bound and sits on every CTA's path)
 #pragma unroll 1
-    for (int c0 = 0; c0 < CKD; c0 += 8) {
-      float ev[8], kv[8];
+    for (int cb = 0; cb < CKD; cb += 32) {
+      float ev[32], kv[32];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        ev[i] = qok ? __ldg(qe_p + (long long)(c0 + i) * p.Q) : 0.f;
-        kv[i] = qok ? __ldg(qk_p + (long long)(c0 + i) * p.Q) - (p.key_mu ? __ldg(p.key_mu + b * CKD + c0 + i) : 0.f) : 0.f;
+      for (int i = 0; i < 32; ++i) {
+        ev[i] = qok ? __ldg(qe_p + (long long)(cb + i) * p.Q) : 0.f;
+        kv[i] = qok ? __ldg(qk_p + (long long)(cb + i) * p.Q) - (p.key_mu ? __ldg(p.key_mu + b * CKD + cb + i) : 0.f) : 0.f;
       }
-      uint32_t w0[4], w1[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float e0 = ev[2 * i], e1 = ev[2 * i + 1], k0 = kv[2 * i], k1 = kv[2 * i + 1];
-        b2 = fmaf(e0 * k0, k0, b2);
-        b2 = fmaf(e1 * k1, k1, b2);
-        a1 += e0 + 2.f * e0 * fabsf(k0) + e1 + 2.f * e1 * fabsf(k1);
-        w0[i] = pack_rn(e0, e1);
-        w1[i] = pack_rn(-2.f * e0 * k0, -2.f * e1 * k1);
+      for (int g8 = 0; g8 < 4; ++g8) {
+        uint32_t w0[4], w1[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float e0 = ev[8 * g8 + 2 * i], e1 = ev[8 * g8 + 2 * i + 1], k0 = kv[8 * g8 + 2 * i], k1 = kv[8 * g8 + 2 * i + 1];
+          b2 = fmaf(e0 * k0, k0, b2);
+          b2 = fmaf(e1 * k1, k1, b2);
+          a1 += e0 + 2.f * e0 * fabsf(k0) + e1 + 2.f * e1 * fabsf(k1);
+          w0[i] = pack_rn(e0, e1);
+          w1[i] = pack_rn(-2.f * e0 * k0, -2.f * e1 * k1);
+        }
+        *reinterpret_cast<uint4*>(Ah + f16_off_main(row, cb + 8 * g8)) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
+        *reinterpret_cast<uint4*>(Ah + f16_off_main(row, 64 + cb + 8 * g8)) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
       }
-      *reinterpret_cast<uint4*>(Ah + f16_off_main(row, c0)) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
-      *reinterpret_cast<uint4*>(Ah + f16_off_main(row, 64 + c0)) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
     }
     // tail: [b2_hi, b2_lo, s, s v, s v^2, s, -s absA, s | 0 x 8] with s = +1 (filter: lower bound) / -1 (sample: upper)
     const bool fits = qok && b2 <= 3.0e4f;            // v^2 must fit f16; otherwise the query is not filtered at all
@@ -180,11 +189,8 @@ __global__ void __launch_bounds__(F16_THREADS, 1) affinity_f16_filter_kernel(con
     else
       T.thr[tid] = !qok ? -CUDART_INF_F : (fits ? p.emax_in[(long long)b * p.Q + q] : CUDART_INF_F);
     fence_proxy_async();
+    mbar_arrive(smem_u32(&T.aready));
   }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = T.tmem_base;
 
   if (warp < 16) {
     // =========================== epilogue: thread == (query, 64-column group) ===========================
@@ -192,6 +198,7 @@ __global__ void __launch_bounds__(F16_THREADS, 1) affinity_f16_filter_kernel(con
     if (half < halves) {
       const long long q = q0 + half * 128 + (warp & 3) * 32 + lane;
       const bool qok = q < p.Q;
+      mbar_wait(smem_u32(&T.aready), 0);                                 // the query rows (and their thresholds) exist
       const float thr = T.thr[half * 128 + (warp & 3) * 32 + lane];     // written by the thread that built this query's row
       const long long bq = (long long)b * p.Q + (qok ? q : 0);
       int* my_idx = SAMPLE ? nullptr : p.cand_idx + bq * p.cap;
@@ -278,6 +285,7 @@ __global__ void __launch_bounds__(F16_THREADS, 1) affinity_f16_filter_kernel(con
       // instruction descriptor: D = F32, A = B = F16, K-major both, N = 128, M = 128
       const uint32_t idesc = (1u << 4) | ((uint32_t)(F16_KTILE >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint32_t a_base = smem_u32(A);
+      mbar_wait(smem_u32(&T.aready), 0);                       // all 256 query rows written (and proxy-fenced)
       for (int t = 0; t < ntiles; ++t) {
         const int s = t % F16_STAGES, a = t & 1;
         mbar_wait(smem_u32(&T.full[s]), (t / F16_STAGES) & 1);

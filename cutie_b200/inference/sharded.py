@@ -30,11 +30,13 @@ def shard_bounds(n_total: int, world: int, rank: int):
 
 
 def sharded_topk(local_segments: Sequence[BankSegment], index_offset: int, n_total: int, qk: torch.Tensor,
-                 qe: torch.Tensor, top_k: int, group=None, usage_acc_local: Optional[torch.Tensor] = None):
+                 qe: torch.Tensor, top_k: int, group=None, usage_acc_local: Optional[torch.Tensor] = None,
+                 marks: Optional[list] = None):
     """The exchange step: local top-k -> all_gather of candidates -> merge.  local_segments: this rank's tokens
     (global indices index_offset .. index_offset + n_local; only keys/shrinkage are read).
     Returns (idx_local, w_local, idx, w): the global winners [B,Q,kpad] (identical on every rank) and the same lists
-    restricted to the tokens this rank owns (local indices, -1 / weight 0 elsewhere) for sharded_gather."""
+    restricted to the tokens this rank owns (local indices, -1 / weight 0 elsewhere) for sharded_gather.
+    `marks` (bench only): a list that receives CUDA events after the local top-k and after the all-gather."""
     world = dist.get_world_size(group)
     n_local = sum(s.n for s in local_segments)
     B, CK, Q = qk.shape
@@ -51,10 +53,14 @@ def sharded_topk(local_segments: Sequence[BankSegment], index_offset: int, n_tot
     else:
         gidx = torch.full((B, Q, kpad), -1, dtype=torch.int32, device=dev)
         sim_l = torch.zeros(B, Q, kpad, device=dev)
+    if marks is not None:
+        marks.append(torch.cuda.Event(enable_timing=True)); marks[-1].record()
     all_sim = torch.empty(world * B, Q, kpad, device=dev)
     all_idx = torch.empty(world * B, Q, kpad, dtype=torch.int32, device=dev)
     dist.all_gather_into_tensor(all_sim, sim_l.contiguous(), group=group)
     dist.all_gather_into_tensor(all_idx, gidx.contiguous(), group=group)
+    if marks is not None:
+        marks.append(torch.cuda.Event(enable_timing=True)); marks[-1].record()
     part_val = all_sim.view(world, B, Q, kpad).permute(1, 0, 2, 3).contiguous()
     part_idx = all_idx.view(world, B, Q, kpad).permute(1, 0, 2, 3).contiguous()
     usage_global = None

