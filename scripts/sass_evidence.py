@@ -12,7 +12,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, 'cutie_b200', 'lib', 'libcutie_b200.so')
 WATCH = ('UTCHMMA', 'UTCBAR', 'LDTM', 'UBLKCP', 'SYNCS', 'LDGSTS', 'HMMA', 'FFMA', 'LDG', 'STG', 'ATOMG', 'RED', 'LDS', 'STS',
-         'SHFL', 'BAR')
+         'SHFL', 'BAR', 'FMNMX3')
 
 
 def demangle(s):
