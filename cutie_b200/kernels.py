@@ -436,6 +436,46 @@ def conv3x3_c1(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, relu_i
     return out
 
 
+def conv3x3_tc_eligible(weight: torch.Tensor, stride=(1, 1), padding=(1, 1), dilation=(1, 1), groups: int = 1) -> bool:
+    """Geometry cutie_conv3x3_tc implements: 3x3, stride 1, zero pad 1, Cin % 32 == 0, Cout % 128 == 0."""
+    return (weight.dim() == 4 and tuple(weight.shape[2:]) == (3, 3) and tuple(stride) == (1, 1) and tuple(padding) == (1, 1)
+            and tuple(dilation) == (1, 1) and groups == 1 and weight.shape[0] % 128 == 0 and weight.shape[1] % 32 == 0)
+
+
+def conv3x3_weight_image(weight: torch.Tensor) -> torch.Tensor:
+    """The layer's tcgen05 operand image (tf32 hi | lo planes per (128-channel tile, 32-channel chunk, tap), swizzled):
+    built once per weight version, 2x the weight bytes."""
+    Cout, Cin = weight.shape[:2]
+    assert conv3x3_tc_eligible(weight) and weight.dtype == torch.float32
+    lib().cutie_conv3x3_weight_image_bytes.restype = ctypes.c_int64
+    nbytes = lib().cutie_conv3x3_weight_image_bytes(_i64(Cout), _i64(Cin))
+    img = torch.empty(nbytes // 4, dtype=torch.float32, device=weight.device)
+    w = weight.detach().contiguous()
+    with _call('conv3x3_weight_image', 1):
+        st = lib().cutie_conv3x3_weight_image(_ptr(w), _i64(Cout), _i64(Cin), _ptr(img), _stream())
+    _check(st, 'cutie_conv3x3_weight_image')
+    return img
+
+
+def conv3x3_tc(x: torch.Tensor, weight_image: torch.Tensor, bias: Optional[torch.Tensor], cout: int,
+               residual: Optional[torch.Tensor] = None, relu_in: bool = False, relu_out: bool = False) -> torch.Tensor:
+    """act(bias + conv3x3(pre(x)) [+ residual]) on the tensor cores with 3xTF32 splitting (fp32-class accuracy):
+    x [N, Cin, H, W] dense NCHW -> [N, cout, H, W]."""
+    N, Cin, H, W = x.shape
+    assert x.dtype == torch.float32
+    x = x.contiguous()
+    if residual is not None:
+        assert tuple(residual.shape) == (N, cout, H, W)
+        residual = residual.contiguous()
+    out = torch.empty(N, cout, H, W, dtype=torch.float32, device=x.device)
+    with _call('conv3x3_tc', 1):
+        st = lib().cutie_conv3x3_tc(_ptr(x), _ptr(weight_image), _ptr(bias.detach() if bias is not None else None),
+                                    _ptr(residual), _i64(N), _i64(Cin), _i64(cout), _i64(H), _i64(W), int(bool(relu_in)),
+                                    int(bool(relu_out)), _ptr(out), _stream())
+    _check(st, 'cutie_conv3x3_tc')
+    return out
+
+
 def area_pool(x: torch.Tensor, f: int) -> torch.Tensor:
     """F.interpolate(x, scale_factor=1/f, mode='area') for [..., H, W] with H % f == W % f == 0."""
     H, W = x.shape[-2:]

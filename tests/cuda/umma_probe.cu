@@ -174,6 +174,63 @@ static int run_case(const char* name, int M, int N, int K, bool a_mn, bool b_mn,
   return bad == 0;
 }
 
+
+// ---- K-major SWIZZLE_128B operand whose start is shifted by `shift` ROWS (shift * 128 bytes) inside a larger row-major
+// buffer swizzled by the ABSOLUTE row index: the implicit-GEMM convolution reads every filter tap as a row-shifted window
+// of one shared-memory activation tile.  base_offset_mode 0: descriptor base-offset field 0; 1: (shift & 7) in bits 49..51.
+static int run_shift_case(int shift, int base_offset_mode, int N) {
+  const int M = 128, K = 64, R = N + 64;
+  std::vector<float> A((size_t)M * K), B((size_t)R * K);
+  srand(99 + shift);
+  for (auto& v : A) v = (float)((rand() % 9) - 4);
+  for (auto& v : B) v = (float)((rand() % 9) - 4);
+  std::vector<unsigned char> ai((size_t)M * K * 4, 0), bi((size_t)R * K * 4, 0);
+  for (int m = 0; m < M; ++m)
+    for (int k = 0; k < K; ++k) memcpy(&ai[off_kmajor(M, m, k)], &A[(size_t)m * K + k], 4);
+  for (int n = 0; n < R; ++n)
+    for (int k = 0; k < K; ++k) memcpy(&bi[off_kmajor(R, n, k)], &B[(size_t)n * K + k], 4);
+  Job job;
+  memset(&job, 0, sizeof(job));
+  job.N = N;
+  job.a_bytes = (int)ai.size();
+  job.b_bytes = (int)bi.size();
+  job.nk = K / 8;
+  job.adesc = desc(16, 1024);
+  job.bdesc = desc(16, 1024) | ((uint64_t)(base_offset_mode ? (shift & 7) : 0) << 49);
+  job.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+  for (int i = 0; i < job.nk; ++i) {
+    const int k0 = i * 8;
+    job.a_step[i] = (k0 / 32) * M * 128 + (k0 % 32) * 4;
+    job.b_step[i] = (k0 / 32) * R * 128 + (k0 % 32) * 4 + shift * 128;
+  }
+  unsigned char *da, *db;
+  float* dout;
+  CK(cudaMalloc(&da, ai.size()));
+  CK(cudaMalloc(&db, bi.size()));
+  CK(cudaMalloc(&dout, (size_t)M * N * 4));
+  CK(cudaMemcpy(da, ai.data(), ai.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(db, bi.data(), bi.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemset(dout, 0xff, (size_t)M * N * 4));
+  const size_t smem = ((ai.size() + 1023) / 1024) * 1024 + bi.size() + 1024;
+  CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  probe_kernel<<<1, 128, smem>>>(da, db, job, dout);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("row-shifted start: CUDA error: %s\n", cudaGetErrorString(e)); exit(3); }
+  std::vector<float> out((size_t)M * N);
+  CK(cudaMemcpy(out.data(), dout, out.size() * 4, cudaMemcpyDeviceToHost));
+  int bad = 0;
+  for (int m = 0; m < M; ++m)
+    for (int n = 0; n < N; ++n) {
+      float ref = 0;
+      for (int k = 0; k < K; ++k) ref += A[(size_t)m * K + k] * B[(size_t)(n + shift) * K + k];
+      if (!(fabs((double)ref - out[(size_t)m * N + n]) <= 1e-3)) ++bad;
+    }
+  printf("B K-major SW128, start shifted by %3d rows, base-offset field %s, N=%d : %s (%d wrong)\n", shift,
+         base_offset_mode ? "(shift&7)" : "0        ", N, bad ? "FAIL" : "PASS", bad);
+  cudaFree(da); cudaFree(db); cudaFree(dout);
+  return bad == 0;
+}
+
 // ---- TMEM -> register bandwidth: W warps each issue R x tcgen05.ld.32x32b.x32 (4 KB per warp instruction) ----
 __global__ void __launch_bounds__(512, 1) tmem_read_kernel(int iters, long long* cycles, float* sink) {
   __shared__ uint32_t tmem_base;
@@ -244,5 +301,8 @@ int main() {
     ok += run_case("A MN-major, B MN-major N=128", 128, 128, 32, true, true, v); ++n;
   }
   printf("%d / %d cases passed\n", ok, n);
+  for (int mode = 0; mode < 2; ++mode)
+    for (int shift : {0, 8, 1, 3, 7, 13, 55, 57})
+      for (int N : {128, 256}) run_shift_case(shift, mode, N);
   return 0;
 }

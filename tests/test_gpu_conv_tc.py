@@ -1,0 +1,70 @@
+"""cutie_conv3x3_tc (csrc/conv_tc.cu): the tcgen05 3xTF32 implicit-GEMM 3x3 convolution against F.conv2d evaluated in
+float64 (the ground truth) and against cuDNN's fp32 result (the library call it replaces): its error vs float64 must be of
+the same class as cuDNN's own fp32 error -- never a TF32-class (1e-3 relative) one."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600, method='thread')]
+
+
+def _ref64(x, w, b, z, relu_in, relu_out):
+    xx = x.double()
+    if relu_in:
+        xx = xx.relu()
+    y = F.conv2d(xx, w.double(), b.double() if b is not None else None, padding=1)
+    if z is not None:
+        y = y + z.double()
+    return y.relu() if relu_out else y
+
+
+CASES = [
+    # NB, Cin, Cout, H, W
+    (3, 256, 256, 30, 54),        # PixelFFN / CAResBlock at 480p, 3 objects (cfg 2)
+    (1, 256, 256, 30, 54),
+    (2, 32, 128, 5, 7),           # one chunk, tiny image: every position near a border
+    (1, 64, 128, 1, 1),
+    (1, 96, 256, 17, 130),        # wider than one tile row: column tiles with halos
+    (2, 128, 128, 60, 108),       # decoder shapes
+    (1, 128, 128, 120, 216),
+    (1, 512, 256, 23, 40),        # 16 chunks
+]
+
+
+@pytest.mark.parametrize('NB,Cin,Cout,H,W', CASES)
+@pytest.mark.parametrize('epi', ['plain', 'relu_in+residual', 'relu_out'])
+def test_conv3x3_tc_is_fp32_class_accurate(NB, Cin, Cout, H, W, epi):
+    import os
+    import cutie_b200.kernels as K_
+    torch.backends.cudnn.allow_tf32 = False
+    if os.environ.get('CUTIE_CONV_BASE_OFFSET'):             # hardware probe aid (tests/cuda/umma_probe.cu decides the default)
+        K_.lib().cutie_debug_conv_base_offset_mode(int(os.environ['CUTIE_CONV_BASE_OFFSET']))
+    g = torch.Generator(device='cuda').manual_seed(NB * 1000 + Cin + H)
+    x = torch.randn(NB, Cin, H, W, device='cuda', generator=g) * 1.5
+    w = torch.randn(Cout, Cin, 3, 3, device='cuda', generator=g) * (2.0 / (9 * Cin)) ** 0.5
+    b = torch.randn(Cout, device='cuda', generator=g)
+    z = torch.randn(NB, Cout, H, W, device='cuda', generator=g) if 'residual' in epi else None
+    relu_in, relu_out = 'relu_in' in epi, 'relu_out' in epi
+    img = K_.conv3x3_weight_image(w)
+    got = K_.conv3x3_tc(x, img, b, Cout, residual=z, relu_in=relu_in, relu_out=relu_out)
+    ref = _ref64(x, w, b, z, relu_in, relu_out)
+    lib32 = F.conv2d(x.relu() if relu_in else x, w, b, padding=1)
+    if z is not None:
+        lib32 = lib32 + z
+    if relu_out:
+        lib32 = lib32.relu()
+    scale = float(ref.abs().max())
+    err = float((got.double() - ref).abs().max()) / scale
+    err_lib = float((lib32.double() - ref).abs().max()) / scale
+    print(f'[{NB},{Cin}->{Cout},{H}x{W}] {epi}: tcgen05 3xTF32 err {err:.2e}, cuDNN fp32 err {err_lib:.2e} (relative to max |y|)')
+    assert err < 2e-6, (err, err_lib)          # 1xTF32 would sit at ~3e-4
+
+
+def test_conv3x3_tc_rejects_unsupported_geometry():
+    import cutie_b200.kernels as K_
+    w = torch.randn(64, 32, 3, 3, device='cuda')
+    assert not K_.conv3x3_tc_eligible(w)
+    assert K_.conv3x3_tc_eligible(torch.empty(128, 32, 3, 3)) and not K_.conv3x3_tc_eligible(torch.empty(128, 32, 3, 3), stride=(2, 2))
+    img = K_.conv3x3_weight_image(torch.randn(128, 32, 3, 3, device='cuda'))
+    with pytest.raises(K_.KernelError):
+        K_.conv3x3_tc(torch.randn(1, 33, 4, 4, device='cuda'), img, None, 128)

@@ -264,22 +264,6 @@ def test_encoder_lookahead_gives_the_same_stream(optimised):
     assert len(a._graphs._enc) == 2 and len(b._graphs._enc) == 1      # the second capture slot exists only with look-ahead
 
 
-def test_bench_preflight_child_passes_here():
-    """bench.py's own pre-flight (the check that decides whether the measured run may use the optional forms), run the
-    way bench.py runs it; on failure its stderr names the form that misbehaved."""
-    import os
-    import subprocess
-    import sys
-    from tests.conftest import ROOT
-    env = dict(os.environ, LOCAL_RANK='0')
-    for k in ('RANK', 'WORLD_SIZE'):
-        env.pop(k, None)
-    r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--preflight'], env=env, capture_output=True,
-                       text=True, timeout=800)
-    print(r.stderr[-3000:])
-    assert r.returncode == 0, r.stderr[-3000:]
-
-
 @pytest.mark.parametrize('cin,cout,hw', [(256, 128, (60, 108)), (128, 128, (120, 216))])
 def test_decoder_resblock_channels_last_variant_matches_nchw(cin, cout, hw):
     """ObjResBlock (the decoder's residual blocks) with channels-last weight twins vs the NCHW form, at the 480p shapes."""
