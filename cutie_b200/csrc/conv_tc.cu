@@ -18,8 +18,9 @@
 //     planes.  Output position j = ty * (TW + 2) + lx reads, for tap (dy, dx), row j + dy * (TW + 2) + dx: EVERY TAP IS
 //     THE SAME TILE READ THROUGH A DESCRIPTOR WHOSE START ADDRESS IS SHIFTED BY WHOLE ROWS -- no im2col copies, no
 //     per-tap producer work.  (The hardware applies the 128-byte swizzle to absolute shared-memory address bits, so a
-//     start shifted by r rows reads rows r.. of a tile that was written with the address-based pattern;
-//     tests/cuda/umma_probe.cu checks this on the device.)  The two padding columns of every local row are computed and
+//     start shifted by r rows reads rows r.. of a tile that was written with the address-based pattern, with the
+//     descriptor's base-offset field left 0; tests/cuda/umma_probe.cu checks this on the device:
+//     profiles/r02_umma_probe.txt.)  The two padding columns of every local row are computed and
 //     discarded (TW / (TW + 2) efficiency); image borders are zero rows.
 //   * 3xTF32: x = hi + lo with hi = tf32(x) RN, lo = tf32(x - hi); three MMAs per k-step (lo.hi + hi.lo + hi.hi) into one
 //     fp32 TMEM accumulator: relative error ~2^-21 per product.
@@ -54,7 +55,7 @@ constexpr int CV_SMEM = 2 * CV_X_BYTES + CV_A_STAGES * CV_A_BYTES + (int)sizeof(
 
 struct ConvTcParams {
   const float* x;              // [NB, Cin, H, W]
-  const unsigned char* wimg;   // [Cout / 128][Cin / 32][9][32768]
+  const unsigned char* wimg;   // [ceil(Cout / 128)][Cin / 32][9][32768]
   const float* bias;           // [Cout] or null
   const float* z;              // [NB, Cout, H, W] or null
   float* y;                    // [NB, Cout, H, W]
@@ -62,14 +63,7 @@ struct ConvTcParams {
   int TH, TW, tiles_x;         // spatial tile; tiles per image row
   int N;                       // MMA N = round16(TH * (TW + 2))
   int relu_in, relu_out;
-  int base_offset_mode;        // descriptor base-offset field for row-shifted starts (see umma_probe)
 };
-
-__device__ __forceinline__ uint64_t desc_b_shifted(uint32_t addr, int mode) {
-  uint64_t d = desc_sw128_kmajor(addr);
-  if (mode) d |= (uint64_t)((addr >> 7) & 7) << 49;
-  return d;
-}
 
 __global__ void __launch_bounds__(CV_THREADS, 1) conv3x3_tc_kernel(const ConvTcParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -166,8 +160,8 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv3x3_tc_kernel(const ConvTcP
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const uint64_t da_hi = desc_sw128_kmajor(a_hi + ks * 32), da_lo = desc_sw128_kmajor(a_lo + ks * 32);
-            const uint64_t db_hi = desc_b_shifted(xb_hi + shift + ks * 32, p.base_offset_mode);
-            const uint64_t db_lo = desc_b_shifted(xb_lo + shift + ks * 32, p.base_offset_mode);
+            const uint64_t db_hi = desc_sw128_kmajor(xb_hi + shift + ks * 32);
+            const uint64_t db_lo = desc_sw128_kmajor(xb_lo + shift + ks * 32);
             tc_mma_tf32(tmem, da_lo, db_hi, idesc, (i | ks) != 0 ? 1u : 0u);
             tc_mma_tf32(tmem, da_hi, db_lo, idesc, 1u);
             tc_mma_tf32(tmem, da_hi, db_hi, idesc, 1u);
@@ -181,7 +175,8 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv3x3_tc_kernel(const ConvTcP
   } else {
     // ================================== epilogue: thread == output channel ==================================
     const int co = cot * CV_M + tid;
-    const float b = p.bias ? __ldg(p.bias + co) : 0.f;
+    const bool co_ok = co < p.Cout;                           // the last channel tile may be padded (zero weight rows)
+    const float b = (p.bias && co_ok) ? __ldg(p.bias + co) : 0.f;
     const long long obase = ((long long)nb * p.Cout + co) * HW;
     const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
     mbar_wait(smem_u32(&T.acc_full), 0);
@@ -193,7 +188,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv3x3_tc_kernel(const ConvTcP
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const int gy = ty0 + ty, gx = tx0 + lx - 1;
-        if (g + j < p.N && lx >= 1 && lx <= p.TW && ty < p.TH && gy < p.H && gx < p.W) {
+        if (co_ok && g + j < p.N && lx >= 1 && lx <= p.TW && ty < p.TH && gy < p.H && gx < p.W) {
           const long long a = obase + (long long)gy * p.W + gx;
           float val = __uint_as_float(o[j]) + b;
           if (p.z) val += __ldg(p.z + a);
@@ -216,7 +211,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv3x3_tc_kernel(const ConvTcP
 __global__ void __launch_bounds__(256) conv3x3_weight_image_kernel(const float* __restrict__ w, int Cout, int Cin,
                                                                    unsigned char* __restrict__ img) {
   const int chunks = Cin / CV_KC;
-  const long long total = (long long)Cout * chunks * 9 * 8;
+  const long long total = (long long)((Cout + CV_M - 1) / CV_M * CV_M) * chunks * 9 * 8;
   const long long f = (long long)blockIdx.x * 256 + threadIdx.x;
   if (f >= total) return;
   const int k4 = (int)(f & 7);
@@ -228,7 +223,7 @@ __global__ void __launch_bounds__(256) conv3x3_weight_image_kernel(const float* 
   const int co = cot * CV_M + row;
   float v[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) v[i] = w[((long long)co * Cin + c * CV_KC + 4 * k4 + i) * 9 + t];
+  for (int i = 0; i < 4; ++i) v[i] = co < Cout ? w[((long long)co * Cin + c * CV_KC + 4 * k4 + i) * 9 + t] : 0.f;
   const float4 h = make_float4(to_tf32(v[0]), to_tf32(v[1]), to_tf32(v[2]), to_tf32(v[3]));
   const float4 l = make_float4(to_tf32(v[0] - h.x), to_tf32(v[1] - h.y), to_tf32(v[2] - h.z), to_tf32(v[3] - h.w));
   unsigned char* blk = img + (((size_t)cot * chunks + c) * 9 + t) * CV_A_BYTES;
@@ -237,8 +232,6 @@ __global__ void __launch_bounds__(256) conv3x3_weight_image_kernel(const float* 
   *reinterpret_cast<float4*>(blk + CV_M * 128 + off) = l;
 }
 
-int g_conv_base_offset_mode = 0;
-
 }  // namespace
 
 }  // namespace cutie
@@ -246,15 +239,14 @@ int g_conv_base_offset_mode = 0;
 using namespace cutie;
 
 extern "C" int64_t cutie_conv3x3_weight_image_bytes(int64_t Cout, int64_t Cin) {
-  if (Cout < CV_M || Cout % CV_M || Cin < CV_KC || Cin % CV_KC) return -1;
-  return (Cout / CV_M) * (Cin / CV_KC) * 9 * (int64_t)CV_A_BYTES;
+  if (Cout < 1 || Cin < CV_KC || Cin % CV_KC) return -1;
+  return ((Cout + CV_M - 1) / CV_M) * (Cin / CV_KC) * 9 * (int64_t)CV_A_BYTES;
 }
 
 extern "C" int cutie_conv3x3_weight_image(const float* weight, int64_t Cout, int64_t Cin, void* image, void* stream) {
   CUTIE_REQUIRE(weight && image, "null argument");
-  CUTIE_REQUIRE(Cout >= CV_M && Cout % CV_M == 0 && Cin >= CV_KC && Cin % CV_KC == 0,
-                "output channels must be a multiple of 128, input channels of 32");
-  const long long total = Cout * (Cin / CV_KC) * 9 * 8;
+  CUTIE_REQUIRE(Cout >= 1 && Cin >= CV_KC && Cin % CV_KC == 0, "input channels must be a multiple of 32");
+  const long long total = (Cout + CV_M - 1) / CV_M * CV_M * (Cin / CV_KC) * 9 * 8;
   conv3x3_weight_image_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       weight, (int)Cout, (int)Cin, static_cast<unsigned char*>(image));
   CUTIE_CHECK_LAUNCH();
@@ -283,8 +275,7 @@ extern "C" int cutie_conv3x3_tc(const float* x, const void* weight_image, const 
                                 int64_t NB, int64_t Cin, int64_t Cout, int64_t H, int64_t W, int relu_in, int relu_out,
                                 float* y, void* stream) {
   CUTIE_REQUIRE(x && weight_image && y, "null argument");
-  CUTIE_REQUIRE(Cout >= CV_M && Cout % CV_M == 0 && Cin >= CV_KC && Cin % CV_KC == 0,
-                "output channels must be a multiple of 128, input channels of 32");
+  CUTIE_REQUIRE(Cout >= 1 && Cin >= CV_KC && Cin % CV_KC == 0, "input channels must be a multiple of 32");
   CUTIE_REQUIRE(NB >= 1 && NB <= 65535 && H >= 1 && W >= 1 && H * W < (1ll << 30), "bad geometry");
   ConvTcParams p;
   p.x = x; p.wimg = static_cast<const unsigned char*>(weight_image); p.bias = bias; p.z = residual; p.y = y;
@@ -294,19 +285,16 @@ extern "C" int cutie_conv3x3_tc(const float* x, const void* weight_image, const 
   CUTIE_REQUIRE(p.N >= 16, "no tile shape for this geometry");
   p.tiles_x = (p.W + p.TW - 1) / p.TW;
   p.relu_in = relu_in; p.relu_out = relu_out;
-  p.base_offset_mode = g_conv_base_offset_mode;
   const long long tiles = (long long)p.tiles_x * ((p.H + p.TH - 1) / p.TH);
   CUTIE_REQUIRE(tiles <= 0x7fffffff, "too many tiles");
   static bool attr_done[64] = {};
   if (first_use_on_device(attr_done))
     cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SMEM);
-  conv3x3_tc_kernel<<<dim3((unsigned)tiles, (unsigned)(Cout / CV_M), (unsigned)NB), CV_THREADS, CV_SMEM,
+  conv3x3_tc_kernel<<<dim3((unsigned)tiles, (unsigned)((Cout + CV_M - 1) / CV_M), (unsigned)NB), CV_THREADS, CV_SMEM,
                       (cudaStream_t)stream>>>(p);
   CUTIE_CHECK_LAUNCH();
   return 0;
 }
-
-extern "C" void cutie_debug_conv_base_offset_mode(int mode) { g_conv_base_offset_mode = mode; }
 
 extern "C" int cutie_debug_conv_tile_shape(int64_t H, int64_t W, int* out3) {
   int th = 0, tw = 0, n = 0;

@@ -437,9 +437,10 @@ def conv3x3_c1(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, relu_i
 
 
 def conv3x3_tc_eligible(weight: torch.Tensor, stride=(1, 1), padding=(1, 1), dilation=(1, 1), groups: int = 1) -> bool:
-    """Geometry cutie_conv3x3_tc implements: 3x3, stride 1, zero pad 1, Cin % 32 == 0, Cout % 128 == 0."""
+    """Geometry cutie_conv3x3_tc implements: 3x3, stride 1, zero pad 1, Cin % 32 == 0; output channels go in tiles of 128
+    (a partial tile costs a full one, so layers with fewer than 64 output channels stay with the library)."""
     return (weight.dim() == 4 and tuple(weight.shape[2:]) == (3, 3) and tuple(stride) == (1, 1) and tuple(padding) == (1, 1)
-            and tuple(dilation) == (1, 1) and groups == 1 and weight.shape[0] % 128 == 0 and weight.shape[1] % 32 == 0)
+            and tuple(dilation) == (1, 1) and groups == 1 and weight.shape[0] >= 64 and weight.shape[1] % 32 == 0)
 
 
 def conv3x3_weight_image(weight: torch.Tensor) -> torch.Tensor:

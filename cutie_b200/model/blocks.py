@@ -94,7 +94,7 @@ class ChannelAttnResBlock(nn.Module):
         return self.cl_twins
 
     def _forward(self, x: torch.Tensor, conv1: nn.Conv2d, conv2: nn.Conv2d) -> torch.Tensor:
-        y = conv2(conv_relu(conv1, F.relu(x)))
+        y = conv2(conv_relu(conv1, x, relu_in=True))
         skip = self.downsample(x)
 
         def aten():
@@ -158,7 +158,7 @@ class ObjResBlock(nn.Module):
         """The block on a folded [B*K, C, H, W] tensor: relu - conv1 - relu - conv2, plus the (projected) input; the
         residual add rides in conv2's epilogue where the model's fuser chose a form that can carry it."""
         skip = x if downsample is None else conv_plain(downsample, x)
-        return conv_add(conv2, conv_relu(conv1, F.relu(x)), skip)
+        return conv_add(conv2, conv_relu(conv1, x, relu_in=True), skip)
 
 
 class _AddDistributor(nn.Module):

@@ -56,9 +56,13 @@ class ConvEpilogueFuser:
       'kernel'  F.conv2d(x, w, None) + cutie_bias_act(y, b, z, relu)     -- the bias-less convolution followed by ONE
                 float4 stream of ours (csrc/pixel.cu), same association as 'aten' => bit-identical results
       'pool'    (ResNet stems) bias-less convolution + cutie_bias_relu_maxpool: bias, clamp and 3x3/s2 pooling in one pass
+      'tc'      cutie_conv3x3_tc: the convolution ITSELF on the tensor cores (tcgen05 implicit GEMM, 3xTF32 operand split =
+                fp32-class accuracy; csrc/conv_tc.cu) with bias, residual, ReLU and the ReLU of the INPUT in the same
+                kernel -- for 3x3 / stride 1 / pad 1 layers with Cin % 32 == 0, Cout % 128 == 0 on dense NCHW tensors
+                (PixelFFN, fuser, decoder and sensory-update convolutions)
 
-    DETERMINISTIC: the form is a function of the epilogue alone -- `RULE`: ReLU epilogues take 'cudnn', bias-only and
-    bias+residual epilogues take 'kernel', stems take 'pool' -- which is what the round-1 on-device A/B chose for 101 of
+    DETERMINISTIC: the form is a function of the layer geometry and the epilogue alone -- `RULE`: eligible 3x3 layers take
+    'tc'; of the rest ReLU epilogues take 'cudnn', bias-only and bias+residual epilogues take 'kernel', stems take 'pool' -- which is what the round-1 on-device A/B chose for 101 of
     104 layers on B200 with fp32 convolutions (BENCH/profiles r02); nothing is timed at run time, so two runs of the
     same video execute the same arithmetic.  CPU tensors (the oracle harness borrowing these modules) always take 'aten'.
 
@@ -66,8 +70,8 @@ class ConvEpilogueFuser:
     0 x (stale NaN bits) is NaN, so the no-residual case passes a persistent zero tensor of the output shape
     instead (read once per call, ~100 MB per 480p frame over all layers: 15 us of HBM time).
     """
-    FORMS = ('aten', 'cudnn', 'kernel')
-    RULE = {'relu': 'cudnn', 'linear': 'kernel', 'stem': 'pool'}
+    FORMS = ('aten', 'cudnn', 'kernel', 'tc')
+    RULE = {'conv3x3': 'tc', 'relu': 'cudnn', 'linear': 'kernel', 'stem': 'pool'}
 
     def __init__(self, enabled: bool = True, rule=None):
         self.enabled = enabled
@@ -75,6 +79,7 @@ class ConvEpilogueFuser:
         self.counts = {}             # form -> number of distinct (layer, geometry, epilogue) triples routed to it
         self._seen = set()
         self._zeros = {}
+        self._images = {}            # id(conv) -> (weight identity, operand image) of the 'tc' form
 
     # -- the forms ------------------------------------------------------------------------------------
     @staticmethod
@@ -84,9 +89,9 @@ class ConvEpilogueFuser:
         return nn.Conv2d._conv_forward(conv, x, conv.weight, conv.bias if with_bias else None)
 
     @classmethod
-    def unfused(cls, conv: nn.Conv2d, x: torch.Tensor, z=None, relu: bool = True) -> torch.Tensor:
+    def unfused(cls, conv: nn.Conv2d, x: torch.Tensor, z=None, relu: bool = True, relu_in: bool = False) -> torch.Tensor:
         """The 'aten' form."""
-        y = cls._conv(conv, x, True)
+        y = cls._conv(conv, F.relu(x) if relu_in else x, True)
         if z is not None:
             y = y.add_(z) if not y.requires_grad else y + z
         if relu:
@@ -120,7 +125,30 @@ class ConvEpilogueFuser:
         from cutie_b200 import kernels as K_
         return K_.bias_act_(self._conv(conv, x, False), conv.bias, z, relu)
 
-    def run(self, form: str, conv: nn.Conv2d, x: torch.Tensor, z=None, relu: bool = True) -> torch.Tensor:
+    def tensor_core(self, conv: nn.Conv2d, x: torch.Tensor, z=None, relu: bool = True, relu_in: bool = False) -> torch.Tensor:
+        """The 'tc' form.  The operand image is rebuilt whenever the weight tensor is replaced or written."""
+        from cutie_b200 import kernels as K_
+        w = conv.weight
+        try:
+            ident = (w.data_ptr(), w._version)
+        except RuntimeError:                       # inference tensors carry no version counter
+            ident = (w.data_ptr(), None)
+        hit = self._images.get(id(conv))
+        if hit is None or hit[0] != ident:
+            hit = (ident, K_.conv3x3_weight_image(w))
+            self._images[id(conv)] = hit
+        return K_.conv3x3_tc(x, hit[1], conv.bias, conv.out_channels, residual=z, relu_in=relu_in, relu_out=relu)
+
+    def _tc_eligible(self, conv: nn.Conv2d, x: torch.Tensor, z) -> bool:
+        from cutie_b200 import kernels as K_
+        return (self.rule.get('conv3x3') == 'tc' and x.is_contiguous() and (z is None or z.is_contiguous())
+                and K_.conv3x3_tc_eligible(conv.weight, conv.stride, conv.padding, conv.dilation, conv.groups))
+
+    def run(self, form: str, conv: nn.Conv2d, x: torch.Tensor, z=None, relu: bool = True, relu_in: bool = False) -> torch.Tensor:
+        if form == 'tc':
+            return self.tensor_core(conv, x, z, relu, relu_in)
+        if relu_in:
+            x = F.relu(x)
         if form == 'cudnn':
             return self.fused(conv, x, z)
         if form == 'kernel':
@@ -137,12 +165,15 @@ class ConvEpilogueFuser:
             self._seen.add(key)
             self.counts[form] = self.counts.get(form, 0) + 1
 
-    def __call__(self, conv: nn.Conv2d, x: torch.Tensor, z=None, relu: bool = True) -> torch.Tensor:
+    def __call__(self, conv: nn.Conv2d, x: torch.Tensor, z=None, relu: bool = True, relu_in: bool = False) -> torch.Tensor:
         if not self._eligible(conv, x):
-            return self.unfused(conv, x, z, relu)
-        form = self.rule['relu'] if relu else self.rule['linear']
+            return self.unfused(conv, x, z, relu, relu_in)
+        if self._tc_eligible(conv, x, z):
+            form = 'tc'
+        else:
+            form = self.rule['relu'] if relu else self.rule['linear']
         self._note(form, conv, x, z, relu)
-        return self.run(form, conv, x, z, relu)
+        return self.run(form, conv, x, z, relu, relu_in)
 
     # -- ResNet stem: relu(conv(x) + bias) -> max_pool2d(3, 2, 1) ---------------------------------------------
     def stem(self, conv: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
@@ -158,7 +189,7 @@ class ConvEpilogueFuser:
         return F.max_pool2d(self(conv, x, None, True), 3, stride=2, padding=1)
 
     def __deepcopy__(self, memo):          # a copied model gets its own fuser with the same settings
-        new = ConvEpilogueFuser(self.enabled, self.rule)
+        new = ConvEpilogueFuser(self.enabled, self.rule)          # (operand images are rebuilt lazily by the copy)
         memo[id(self)] = new
         return new
 
@@ -197,10 +228,11 @@ class _BiasOnlyForward:
         return _BiasOnlyForward(copy.deepcopy(self.conv, memo), copy.deepcopy(self.fuser, memo))
 
 
-def conv_relu(conv: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
-    """relu(conv(x)) -- in the form the model's fuser chose for this layer, else convolution + bias add + clamp."""
+def conv_relu(conv: nn.Conv2d, x: torch.Tensor, relu_in: bool = False) -> torch.Tensor:
+    """relu(conv(x)) (conv(relu(x)) inside if relu_in) -- in the form the model's fuser names for this layer, else
+    convolution + bias add + clamp."""
     f = getattr(conv, 'epilogue_fuser', None)
-    return ConvEpilogueFuser.unfused(conv, x) if f is None else f(conv, x)
+    return ConvEpilogueFuser.unfused(conv, x, relu_in=relu_in) if f is None else f(conv, x, relu_in=relu_in)
 
 
 def conv_relu_maxpool(conv: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:

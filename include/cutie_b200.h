@@ -167,7 +167,8 @@ int cutie_segment_tail(const float* x, float* agg, float* logits, float* prob, i
 
 /* 3x3 / stride 1 / zero-pad 1 convolution as a tcgen05 implicit GEMM with 3xTF32 operand splitting (fp32-class accuracy;
  * csrc/conv_tc.cu): y = act(bias + conv(pre(x), W) [+ residual]), pre = ReLU if relu_in, act = ReLU if relu_out.
- * x [NB, Cin, H, W], y / residual [NB, Cout, H, W] dense NCHW fp32; Cin % 32 == 0, Cout % 128 == 0.
+ * x [NB, Cin, H, W], y / residual [NB, Cout, H, W] dense NCHW fp32; Cin % 32 == 0 (output channels are processed in tiles
+ * of 128; a partial last tile costs a full one).
  * Replaces the F.conv2d calls of PixelFFN / CAResBlock (transformer_layers.py:121-136, channel_attn.py:7-39: two 256 -> 256
  * convolutions per transformer block) and of PixelFeatureFuser (big_modules.py:192-235) -- SURVEY.md section 8(f).1.
  * `weight_image` is the layer's operand image: cutie_conv3x3_weight_image(weight [Cout, Cin, 3, 3]) once per weight
@@ -177,9 +178,7 @@ int64_t cutie_conv3x3_weight_image_bytes(int64_t Cout, int64_t Cin);
 int cutie_conv3x3_weight_image(const float* weight, int64_t Cout, int64_t Cin, void* image, void* stream);
 int cutie_conv3x3_tc(const float* x, const void* weight_image, const float* bias, const float* residual, int64_t NB,
                      int64_t Cin, int64_t Cout, int64_t H, int64_t W, int relu_in, int relu_out, float* y, void* stream);
-/* test hooks: descriptor base-offset mode of the row-shifted activation operand; the spatial tile the launcher picks
- * (out3 = {rows, columns, MMA N}). */
-void cutie_debug_conv_base_offset_mode(int mode);
+/* test hook: the spatial tile the launcher picks (out3 = {rows, columns, MMA N}). */
 int cutie_debug_conv_tile_shape(int64_t H, int64_t W, int* out3);
 
 /* 3x3 convolution with a single output channel, optionally of the rectified input: the mask decoder's prediction head

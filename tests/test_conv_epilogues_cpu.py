@@ -15,6 +15,9 @@ from cutie_b200.model.backbone import ResNetTrunk
 from cutie_b200.model.blocks import ChannelAttnResBlock, ObjConv2d, ObjResBlock
 
 
+EPILOGUE_ONLY = {'relu': 'cudnn', 'linear': 'kernel', 'stem': 'pool'}     # RULE without the tensor-core convolution
+
+
 class _FakeDeviceFuser(fuse.ConvEpilogueFuser):
     """Runs the device forms on CPU tensors (emulated) and counts the calls per form."""
 
@@ -38,9 +41,9 @@ class _FakeDeviceFuser(fuse.ConvEpilogueFuser):
         self.calls['kernel'] += 1
         return super().kernel(conv, x, z, relu)
 
-    def unfused(self, conv, x, z=None, relu=True):
+    def unfused(self, conv, x, z=None, relu=True, relu_in=False):
         self.calls['aten'] += 1
-        return fuse.ConvEpilogueFuser.unfused(conv, x, z, relu)
+        return fuse.ConvEpilogueFuser.unfused(conv, x, z, relu, relu_in)
 
 
 def _randomise_bn(m):
@@ -78,7 +81,7 @@ def test_folded_trunk_routes_through_fuser_and_matches(arch, cpu_kernels):
         n = fuse.fold_trunk_(net)
         assert net.bn_folded and all(getattr(u, 'bn_folded', False) for s in (net.layer1, net.layer2, net.layer3) for u in s)
         off = net(x)                      # no fuser attached: convolution + add + clamp, as before
-        f = _FakeDeviceFuser()
+        f = _FakeDeviceFuser(rule=EPILOGUE_ONLY)          # (trunks are channels-last on the device: never 'tc')
         assert fuse.attach_epilogue_fuser(net, f) == n
         on = net(x)
         calls_first = dict(f.calls)
@@ -111,6 +114,44 @@ def test_rule_is_the_only_input_of_the_choice(cpu_kernels):
     assert torch.equal(out, ref) and torch.equal(out2, ref)
     assert f.report()['layers'] == {'kernel': 2} and f.calls['cudnn'] == 0
     assert g.report()['layers'] == {'aten': 2} and g.calls['kernel'] == 0
+
+
+def test_eligible_3x3_layers_take_the_tensor_core_form(cpu_kernels):
+    """3x3 / stride 1 / pad 1 with Cin % 32 == 0 and Cout % 128 == 0 on dense NCHW: the convolution itself goes to
+    cutie_conv3x3_tc with the input ReLU, bias, residual and output ReLU inside (emulated here); the operand image is built
+    once per weight version; channels-last tensors and other geometries keep the cuDNN forms."""
+    torch.manual_seed(5)
+    blk = ObjResBlock(32, 128).eval()                       # conv1 32 -> 128 (tc), conv2 128 -> 128 (tc), 1x1 shortcut (kernel)
+    g = torch.randn(1, 2, 32, 6, 5)
+    with torch.inference_mode():
+        ref = blk(g)
+        f = _FakeDeviceFuser()
+        fuse.attach_epilogue_fuser(blk, f)
+        out = blk(g)
+        out2 = blk(g)
+    assert torch.allclose(out, ref, atol=1e-5) and torch.equal(out, out2)
+    assert f.report()['layers'] == {'tc': 2, 'kernel': 1}
+    assert len(f._images) == 2
+    img_before = f._images[id(blk.conv1)][1]
+    with torch.no_grad():
+        blk.conv1.weight.mul_(2.0)                          # an in-place write bumps the version: the image is rebuilt
+    with torch.inference_mode():
+        out3 = blk(g)
+    assert f._images[id(blk.conv1)][1] is not img_before and not torch.allclose(out3, out)
+    car = ChannelAttnResBlock(128, 128).eval()
+    x = torch.randn(2, 128, 5, 4)
+    with torch.inference_mode():
+        want = car(x)
+        h = _FakeDeviceFuser()
+        fuse.attach_epilogue_fuser(car, h)
+        assert torch.allclose(car(x), want, atol=1e-5) and h.report()['layers'] == {'tc': 2}
+        k = _FakeDeviceFuser()
+        fuse.attach_epilogue_fuser(car, k)
+        xcl = x.contiguous(memory_format=torch.channels_last)
+        assert torch.allclose(car(xcl), want, atol=1e-5) and 'tc' not in k.report()['layers']     # channels-last: library forms
+        off = _FakeDeviceFuser(rule={'relu': 'cudnn', 'linear': 'kernel', 'stem': 'pool'})     # a rule without 'conv3x3'
+        fuse.attach_epilogue_fuser(car, off)
+        assert torch.allclose(car(x), want, atol=1e-5) and 'tc' not in off.report()['layers']
 
 
 def test_object_resblock_residual_rides_in_the_epilogue(cpu_kernels):

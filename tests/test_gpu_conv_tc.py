@@ -28,17 +28,17 @@ CASES = [
     (2, 128, 128, 60, 108),       # decoder shapes
     (1, 128, 128, 120, 216),
     (1, 512, 256, 23, 40),        # 16 chunks
+    (1, 64, 64, 40, 72),          # half a channel tile (zero-padded weight rows)
+    (3, 512, 768, 30, 54),        # sensory update: 6 channel tiles
+    (1, 32, 200, 9, 9),           # ragged channel count
 ]
 
 
 @pytest.mark.parametrize('NB,Cin,Cout,H,W', CASES)
 @pytest.mark.parametrize('epi', ['plain', 'relu_in+residual', 'relu_out'])
 def test_conv3x3_tc_is_fp32_class_accurate(NB, Cin, Cout, H, W, epi):
-    import os
     import cutie_b200.kernels as K_
     torch.backends.cudnn.allow_tf32 = False
-    if os.environ.get('CUTIE_CONV_BASE_OFFSET'):             # hardware probe aid (tests/cuda/umma_probe.cu decides the default)
-        K_.lib().cutie_debug_conv_base_offset_mode(int(os.environ['CUTIE_CONV_BASE_OFFSET']))
     g = torch.Generator(device='cuda').manual_seed(NB * 1000 + Cin + H)
     x = torch.randn(NB, Cin, H, W, device='cuda', generator=g) * 1.5
     w = torch.randn(Cout, Cin, 3, 3, device='cuda', generator=g) * (2.0 / (9 * Cin)) ** 0.5
@@ -57,13 +57,14 @@ def test_conv3x3_tc_is_fp32_class_accurate(NB, Cin, Cout, H, W, epi):
     err = float((got.double() - ref).abs().max()) / scale
     err_lib = float((lib32.double() - ref).abs().max()) / scale
     print(f'[{NB},{Cin}->{Cout},{H}x{W}] {epi}: tcgen05 3xTF32 err {err:.2e}, cuDNN fp32 err {err_lib:.2e} (relative to max |y|)')
-    assert err < 2e-6, (err, err_lib)          # 1xTF32 would sit at ~3e-4
+    # fp32 accumulation over K = 9 Cin terms leaves cuDNN's own fp32 result ~1e-5 from float64 at these sizes; 3xTF32 must be
+    # of that class (measured 1.4x cuDNN's error) -- a plain 1xTF32 product sits at ~3e-4
+    assert err < 4 * err_lib + 2e-6 and err < 6e-5, (err, err_lib)
 
 
 def test_conv3x3_tc_rejects_unsupported_geometry():
     import cutie_b200.kernels as K_
-    w = torch.randn(64, 32, 3, 3, device='cuda')
-    assert not K_.conv3x3_tc_eligible(w)
+    assert not K_.conv3x3_tc_eligible(torch.empty(32, 32, 3, 3)) and not K_.conv3x3_tc_eligible(torch.empty(128, 48, 3, 3))
     assert K_.conv3x3_tc_eligible(torch.empty(128, 32, 3, 3)) and not K_.conv3x3_tc_eligible(torch.empty(128, 32, 3, 3), stride=(2, 2))
     img = K_.conv3x3_weight_image(torch.randn(128, 32, 3, 3, device='cuda'))
     with pytest.raises(K_.KernelError):
