@@ -22,8 +22,13 @@
 //     descriptor's base-offset field left 0; tests/cuda/umma_probe.cu checks this on the device:
 //     profiles/r02_umma_probe.txt.)  The two padding columns of every local row are computed and
 //     discarded (TW / (TW + 2) efficiency); image borders are zero rows.
-//   * 3xTF32: x = hi + lo with hi = tf32(x) RN, lo = tf32(x - hi); three MMAs per k-step (lo.hi + hi.lo + hi.hi) into one
-//     fp32 TMEM accumulator: relative error ~2^-21 per product.
+//   * 3xTF32: x = hi + lo with hi = tf32(x) RN, lo = tf32(x - hi); three MMAs per k-step (lo.hi + hi.lo + hi.hi), fp32
+//     accumulation in TMEM: relative error ~2^-21 per product.  The tensor core adds each MMA's result to the accumulator
+//     with TRUNCATION, a bias that grows with the number of accumulations (measured: 864 of them into one accumulator at
+//     Cin = 256 left 1.6e-5 of max|y|, cuDNN's fp32 FMA chain 1.1e-5).  So the K loop is spread over FOUR accumulators
+//     (4 x 128 TMEM columns): the small cross terms lo.hi + hi.lo (2^-11 of the result: their truncation is invisible) in
+//     one, the hi.hi products of chunk c in accumulator c % 3; the epilogue adds the four in fp32 (round to nearest).
+//     Same MMA count, ~5x smaller error.
 //   * Epilogue: thread == output channel (TMEM lane); bias, optional residual, optional ReLU; ReLU on the INPUT (the
 //     pre-activation blocks' conv(relu(x))) is applied by the producers for free.
 //
@@ -82,7 +87,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv3x3_tc_kernel(const ConvTcP
     mbar_init(smem_u32(&T.acc_full), 1);
     mbar_init_fence();
   }
-  if (warp == 12) tmem_alloc<128>(smem_u32(&T.tmem_base));
+  if (warp == 12) tmem_alloc<512>(smem_u32(&T.tmem_base));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -162,9 +167,9 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv3x3_tc_kernel(const ConvTcP
             const uint64_t da_hi = desc_sw128_kmajor(a_hi + ks * 32), da_lo = desc_sw128_kmajor(a_lo + ks * 32);
             const uint64_t db_hi = desc_sw128_kmajor(xb_hi + shift + ks * 32);
             const uint64_t db_lo = desc_sw128_kmajor(xb_lo + shift + ks * 32);
-            tc_mma_tf32(tmem, da_lo, db_hi, idesc, (i | ks) != 0 ? 1u : 0u);
-            tc_mma_tf32(tmem, da_hi, db_lo, idesc, 1u);
-            tc_mma_tf32(tmem, da_hi, db_hi, idesc, 1u);
+            tc_mma_tf32(tmem + 384, da_lo, db_hi, idesc, (i | ks) != 0 ? 1u : 0u);      // cross terms
+            tc_mma_tf32(tmem + 384, da_hi, db_lo, idesc, 1u);
+            tc_mma_tf32(tmem + (uint32_t)(c % 3) * 128u, da_hi, db_hi, idesc, (c >= 3 || (t | ks) != 0) ? 1u : 0u);
           }
           tc_commit(smem_u32(&T.a_empty[s]));
         }
@@ -182,9 +187,18 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv3x3_tc_kernel(const ConvTcP
     mbar_wait(smem_u32(&T.acc_full), 0);
     tc_fence_after();
     int ty = 0, lx = 0;                                     // position j = ty * TWp + lx
+    const int nacc = chunks < 3 ? chunks : 3;               // hi.hi accumulators in use
     for (int g = 0; g < p.N; g += 32) {
-      uint32_t o[32];
+      uint32_t o[32], q[32];
       tmem_ld32(lane_base + g, o);                          // (columns >= N of the last group are never stored)
+      for (int a = 1; a < nacc; ++a) {
+        tmem_ld32(lane_base + a * 128 + g, q);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) + __uint_as_float(q[j]));
+      }
+      tmem_ld32(lane_base + 384 + g, q);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) + __uint_as_float(q[j]));
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const int gy = ty0 + ty, gx = tx0 + lx - 1;
@@ -203,7 +217,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv3x3_tc_kernel(const ConvTcP
   __syncthreads();
   if (warp == 12) {
     tc_fence_after();
-    tmem_dealloc<128>(tmem);
+    tmem_dealloc<512>(tmem);
   }
 }
 

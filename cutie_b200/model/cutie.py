@@ -200,6 +200,9 @@ class CUTIE(nn.Module):
                     m = getattr(enc, name, None)
                     if m is not None:
                         m.to(memory_format=torch.channels_last)
+                        for c in m.modules():           # the trunk stays a cuDNN channels-last region (fuse._tc_eligible)
+                            if isinstance(c, nn.Conv2d):
+                                object.__setattr__(c, 'tc_exempt', True)
                 enc.channels_last = True
         # after the folding: fold_trunk_ replaces the trunk convolutions by new modules
         object.__setattr__(self, 'conv_epilogues', ConvEpilogueFuser(enabled=bool(fuse_epilogues)))
@@ -213,12 +216,6 @@ class CUTIE(nn.Module):
             for up in (self.mask_decoder.up_16_8, self.mask_decoder.up_8_4):
                 for tw in up.out_conv.make_channels_last_twins():
                     attach_epilogue_fuser(tw, self.conv_epilogues)
-            # the two fuser blocks already receive channels-last tensors (their input descends from the channels-last
-            # trunk): keep their weights channels-last too instead of re-laying them out on every call
-            for fz in (self.pixel_fuser.fuser, self.mask_encoder.fuser):
-                for blk in (fz.block1, fz.block2):
-                    blk.conv1.to(memory_format=torch.channels_last)
-                    blk.conv2.to(memory_format=torch.channels_last)
         # pixel-side glue (area down-sampling, channel-attention tail, sensory GRU gates): ATen chains vs our kernels
         from cutie_b200.utils.dispatch import GlueDispatch, attach_glue_dispatch
         attach_glue_dispatch(self, GlueDispatch(enabled=bool(fuse_glue)))

@@ -58,8 +58,9 @@ class ConvEpilogueFuser:
       'pool'    (ResNet stems) bias-less convolution + cutie_bias_relu_maxpool: bias, clamp and 3x3/s2 pooling in one pass
       'tc'      cutie_conv3x3_tc: the convolution ITSELF on the tensor cores (tcgen05 implicit GEMM, 3xTF32 operand split =
                 fp32-class accuracy; csrc/conv_tc.cu) with bias, residual, ReLU and the ReLU of the INPUT in the same
-                kernel -- for 3x3 / stride 1 / pad 1 layers with Cin % 32 == 0, Cout % 128 == 0 on dense NCHW tensors
-                (PixelFFN, fuser, decoder and sensory-update convolutions)
+                kernel -- for 3x3 / stride 1 / pad 1 layers with Cin % 32 == 0, Cout >= 64 outside the channels-last
+                trunks (PixelFFN, fuser, key projection, decoder and sensory-update
+                convolutions); reads and writes dense NCHW (a channels-last input is re-laid out once)
 
     DETERMINISTIC: the form is a function of the layer geometry and the epilogue alone -- `RULE`: eligible 3x3 layers take
     'tc'; of the rest ReLU epilogues take 'cudnn', bias-only and bias+residual epilogues take 'kernel', stems take 'pool' -- which is what the round-1 on-device A/B chose for 101 of
@@ -141,7 +142,9 @@ class ConvEpilogueFuser:
 
     def _tc_eligible(self, conv: nn.Conv2d, x: torch.Tensor, z) -> bool:
         from cutie_b200 import kernels as K_
-        return (self.rule.get('conv3x3') == 'tc' and x.is_contiguous() and (z is None or z.is_contiguous())
+        # `tc_exempt`: layers inside a region that runs channels-last end to end (the ResNet trunks, whose 1x1 and strided
+        # convolutions stay cuDNN calls) keep the library's 3x3 too -- a dense-NCHW island would cost two re-layouts
+        return (self.rule.get('conv3x3') == 'tc' and not getattr(conv, 'tc_exempt', False)
                 and K_.conv3x3_tc_eligible(conv.weight, conv.stride, conv.padding, conv.dilation, conv.groups))
 
     def run(self, form: str, conv: nn.Conv2d, x: torch.Tensor, z=None, relu: bool = True, relu_in: bool = False) -> torch.Tensor:

@@ -69,3 +69,33 @@ def test_conv3x3_tc_rejects_unsupported_geometry():
     img = K_.conv3x3_weight_image(torch.randn(128, 32, 3, 3, device='cuda'))
     with pytest.raises(K_.KernelError):
         K_.conv3x3_tc(torch.randn(1, 33, 4, 4, device='cuda'), img, None, 128)
+
+
+@pytest.mark.parametrize('NB,Cin,Cout,H,W', [(3, 256, 256, 30, 54), (3, 512, 768, 30, 54), (3, 256, 128, 60, 108),
+                                             (3, 128, 128, 120, 216), (1, 256, 64, 30, 54)])
+def test_conv3x3_tc_time_beside_cudnn_fp32(NB, Cin, Cout, H, W):
+    """Reported, not asserted (bench.py measures the whole step): device time per launch, L2-warm, beside cuDNN's fp32
+    convolution (TF32 off, cudnn.benchmark on) of the same layer."""
+    import cutie_b200.kernels as K_
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cudnn.benchmark = True
+    x = torch.randn(NB, Cin, H, W, device='cuda')
+    w = torch.randn(Cout, Cin, 3, 3, device='cuda') * 0.02
+    b = torch.randn(Cout, device='cuda')
+    img = K_.conv3x3_weight_image(w)
+
+    def timed(fn, n=30):
+        for _ in range(5):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n * 1e3
+    t_tc = timed(lambda: K_.conv3x3_tc(x, img, b, Cout, relu_out=True))
+    t_lib = timed(lambda: F.conv2d(x, w, b, padding=1).relu_())
+    flops = 2.0 * NB * H * W * Cout * Cin * 9
+    print(f'[{NB},{Cin}->{Cout},{H}x{W}] tcgen05 3xTF32 {t_tc:.1f} us ({flops / t_tc / 1e6:.1f} TFLOP/s fp32-equivalent), '
+          f'cuDNN fp32 {t_lib:.1f} us ({flops / t_lib / 1e6:.1f} TFLOP/s)')
