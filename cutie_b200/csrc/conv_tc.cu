@@ -1,18 +1,21 @@
-// 3x3 / stride 1 / zero-pad 1 convolution as a tcgen05 implicit GEMM with fp32-class accuracy (3xTF32), sm_100a.
+// 3x3 (stride 1, zero-pad 1) and 1x1 (stride 1 or 2) convolutions as tcgen05 implicit GEMMs with fp32-class accuracy
+// (3xTF32), sm_100a.
 //
-// the PixelFFN / CAResBlock (transformer_layers.py:121-136, channel_attn.py:7-39) and
-// PixelFeatureFuser (big_modules.py:192-235) convolutions.  With the numerics the parity tests validate -- fp32, cuDNN
-// TF32 off -- cuDNN runs them on the FP32 pipe; they are the largest cost inside the replaced subsystem.
+// the PixelFFN / CAResBlock (transformer_layers.py:121-136, channel_attn.py:7-39), PixelFeatureFuser
+// (big_modules.py:192-235), key projection (big_modules.py:66-87), MaskDecoder / SensoryUpdater (big_modules.py:238-306,
+// modules.py:46-85) and ResNet trunk (utils/resnet.py) convolutions.  With the numerics the parity tests validate -- fp32,
+// cuDNN TF32 off -- cuDNN runs them on the FP32 pipe at 7-30 TFLOP/s (profiles/r02_step_kernel_times.md): 13 of the
+// 13.7 ms of a 480p frame before this kernel.
 //
-//   Y[n, co, y, x] = act( bias[co] + sum_{ci, dy, dx} W[co, ci, dy, dx] * pre(X)[n, ci, y + dy - 1, x + dx - 1]  (+ Z[n, co, y, x]) )
+//   Y[n, co, y, x] = act( bias[co] + sum_{ci, dy, dx} W[co, ci, dy, dx] * pre(X)[n, ci, s y + dy - h, s x + dx - h]  (+ Z[n, co, y, x]) )
 //
 // GEMM view per CTA: D[co (M = 128), position (N <= 128)] += A_tap[co, ci] . B_tap[ci, position], K = 32 input channels
-// per (chunk, tap) step, 9 taps x Cin / 32 chunks.
+// per (chunk, tap) step, KS^2 taps x Cin / 32 chunks.
 //
-//   * A (weights) comes from a precomputed OPERAND IMAGE (cutie_conv3x3_weight_image, built once per layer): for every
+//   * A (weights) comes from a precomputed OPERAND IMAGE (cutie_conv_weight_image, built once per layer): for every
 //     (128-channel output tile, 32-channel input chunk, tap) the [128 x 32] tf32 hi and lo planes in K-major
 //     SWIZZLE_128B order, 32 KB, fetched by ONE cp.async.bulk per step through a 3-stage mbarrier ring.
-//   * B (activations): the CTA's spatial tile is TH x TW output pixels; its input window with the 1-pixel halo is laid
+//   * B (activations), 3x3: the CTA's spatial tile is TH x TW output pixels; its input window with the 1-pixel halo is laid
 //     out in shared memory ONCE per 32-channel chunk as rows of a local zero-padded grid -- row r = ly * (TW + 2) + lx + 1
 //     holds the 32 channels of input pixel (ty0 + ly - 1, tx0 + lx - 1) as 128 bytes, K-major SWIZZLE_128B, hi and lo
 //     planes.  Output position j = ty * (TW + 2) + lx reads, for tap (dy, dx), row j + dy * (TW + 2) + dx: EVERY TAP IS
@@ -22,6 +25,11 @@
 //     descriptor's base-offset field left 0; tests/cuda/umma_probe.cu checks this on the device:
 //     profiles/r02_umma_probe.txt.)  The two padding columns of every local row are computed and
 //     discarded (TW / (TW + 2) efficiency); image borders are zero rows.
+//     1x1: a tile is 128 consecutive output pixels of the flattened image (stride 2: of the sub-sampled one), no halo; four
+//     activation stages of 32 KB instead of two of 62 KB, filled by two producer groups that take the chunks in turn.
+//   * Layout-agnostic: X, Y and Z are addressed through (image, channel, pixel) strides -- dense NCHW (what the transformer
+//     kernels emit) and channels-last (what the cuDNN trunks run in) both work without a re-layout; channels-last is the
+//     natural one (a producer thread reads its 32 channels as 8 x 16 bytes, an epilogue warp stores 32 consecutive channels).
 //   * 3xTF32: x = hi + lo with hi = tf32(x) RN, lo = tf32(x - hi); three MMAs per k-step (lo.hi + hi.lo + hi.hi), fp32
 //     accumulation in TMEM: relative error ~2^-21 per product.  The tensor core adds each MMA's result to the accumulator
 //     with TRUNCATION, a bias that grows with the number of accumulations (measured: 864 of them into one accumulator at
@@ -46,44 +54,59 @@ constexpr int CV_M = 128;                         // output channels per CTA
 constexpr int CV_KC = 32;                         // input channels per chunk
 constexpr int CV_A_BYTES = 2 * CV_M * 128;        // hi | lo planes of one (chunk, tap) weight block: 32768
 constexpr int CV_A_STAGES = 3;
-constexpr int CV_ROWS = 248;                      // activation tile rows (31 x 8: planes stay 1024-byte aligned)
-constexpr int CV_X_PLANE = CV_ROWS * 128;         // 31744
-constexpr int CV_X_BYTES = 2 * CV_X_PLANE;        // hi | lo
 constexpr int CV_THREADS = 448;
 constexpr int CV_PROD = 256;
+constexpr int CV3_ROWS = 248;                     // 3x3: activation tile rows per stage (31 x 8: planes stay 1024-byte aligned)
+constexpr int CV1_ROWS = 128;                     // 1x1
 
 struct ConvTail {
-  unsigned long long a_full[CV_A_STAGES], a_empty[CV_A_STAGES], x_full[2], x_empty[2], acc_full;
+  unsigned long long a_full[CV_A_STAGES], a_empty[CV_A_STAGES], x_full[4], x_empty[4], acc_full;
   uint32_t tmem_base;
 };
-constexpr int CV_SMEM = 2 * CV_X_BYTES + CV_A_STAGES * CV_A_BYTES + (int)sizeof(ConvTail) + 64;
+constexpr int CV_X_BYTES3 = 2 * 2 * CV3_ROWS * 128;   // 3x3: 2 stages x (hi | lo) x 248 rows = 126976
+constexpr int CV_X_BYTES1 = 4 * 2 * CV1_ROWS * 128;   // 1x1: 4 stages x (hi | lo) x 128 rows = 131072
+constexpr int CV_SMEM3 = CV_X_BYTES3 + CV_A_STAGES * CV_A_BYTES + (int)sizeof(ConvTail) + 64;
+constexpr int CV_SMEM1 = CV_X_BYTES1 + CV_A_STAGES * CV_A_BYTES + (int)sizeof(ConvTail) + 64;
 
 struct ConvTcParams {
-  const float* x;              // [NB, Cin, H, W]
-  const unsigned char* wimg;   // [ceil(Cout / 128)][Cin / 32][9][32768]
+  const float* x;
+  const unsigned char* wimg;   // [ceil(Cout / 128)][Cin / 32][taps][32768]
   const float* bias;           // [Cout] or null
-  const float* z;              // [NB, Cout, H, W] or null
-  float* y;                    // [NB, Cout, H, W]
-  int Cin, Cout, H, W;
-  int TH, TW, tiles_x;         // spatial tile; tiles per image row
-  int N;                       // MMA N = round16(TH * (TW + 2))
-  int relu_in, relu_out;
+  const float* z;              // residual, or null
+  float* y;
+  long long xs_n, xs_c, xs_p;  // element strides of X: image, channel, pixel (pixel index = row * Wi + column)
+  long long ys_n, ys_c, ys_p;  // of Y
+  long long zs_n, zs_c, zs_p;  // of Z
+  int Cin, Cout, H, W;         // OUTPUT height / width
+  int Hi, Wi, stride;          // input height / width; stride (1x1 only: 1 or 2)
+  int TH, TW, tiles_x;         // 3x3: spatial tile and tiles per image row
+  int N;                       // MMA N (multiple of 16, <= 128)
+  int relu_in, relu_out, x_vec;
 };
 
-__global__ void __launch_bounds__(CV_THREADS, 1) conv3x3_tc_kernel(const ConvTcParams p) {
+template <int KS>
+__global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcParams p) {
+  constexpr int XROWS = KS == 3 ? CV3_ROWS : CV1_ROWS;
+  constexpr int XPLANE = XROWS * 128;
+  constexpr int XSTAGE = 2 * XPLANE;
+  constexpr int XST = KS == 3 ? 2 : 4;                       // activation stages
+  constexpr int TAPS = KS * KS;
+  constexpr int GROUPS = KS == 3 ? 1 : 2;                    // producer groups taking the chunks in turn
+  constexpr int PER_GROUP = CV_PROD / GROUPS;
   extern __shared__ __align__(1024) unsigned char smem[];
-  unsigned char* Xs = smem;                                   // 2 stages x (hi | lo)
-  unsigned char* As = smem + 2 * CV_X_BYTES;                  // CV_A_STAGES x (hi | lo)
-  ConvTail& T = *reinterpret_cast<ConvTail*>(smem + 2 * CV_X_BYTES + CV_A_STAGES * CV_A_BYTES);
+  unsigned char* Xs = smem;
+  unsigned char* As = smem + XST * XSTAGE;
+  ConvTail& T = *reinterpret_cast<ConvTail*>(smem + XST * XSTAGE + CV_A_STAGES * CV_A_BYTES);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile = blockIdx.x, cot = blockIdx.y, nb = blockIdx.z;
-  const int ty0 = (tile / p.tiles_x) * p.TH, tx0 = (tile % p.tiles_x) * p.TW;
   const int TWp = p.TW + 2;
+  const int ty0 = KS == 3 ? (tile / p.tiles_x) * p.TH : 0, tx0 = KS == 3 ? (tile % p.tiles_x) * p.TW : 0;
+  const long long pix0 = (long long)tile * p.N;              // 1x1: first flattened output pixel of the tile
   const int chunks = p.Cin / CV_KC;
   const long long HW = (long long)p.H * p.W;
   if (tid == 0) {
     for (int s = 0; s < CV_A_STAGES; ++s) { mbar_init(smem_u32(&T.a_full[s]), 1); mbar_init(smem_u32(&T.a_empty[s]), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&T.x_full[s]), CV_PROD); mbar_init(smem_u32(&T.x_empty[s]), 1); }
+    for (int s = 0; s < XST; ++s) { mbar_init(smem_u32(&T.x_full[s]), PER_GROUP); mbar_init(smem_u32(&T.x_empty[s]), 1); }
     mbar_init(smem_u32(&T.acc_full), 1);
     mbar_init_fence();
   }
@@ -95,30 +118,48 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv3x3_tc_kernel(const ConvTcP
 
   if (warp >= 4 && warp < 12) {
     // ================================== activation producers: thread == tile row ==================================
-    const int r = tid - 128;                                  // 0 .. 255; rows >= CV_ROWS do not exist
-    const int rows_used = p.N + 2 * TWp + 2;
-    const bool row_live = r < CV_ROWS;
+    const int grp = (tid - 128) / PER_GROUP;
+    const int r = (tid - 128) % PER_GROUP;
+    const bool row_live = r < XROWS;
     bool valid = false;
     long long poff = 0;
-    if (r >= 1 && r < rows_used) {
-      const int q = r - 1, ly = q / TWp, lx = q - ly * TWp;
-      const int gy = ty0 + ly - 1, gx = tx0 + lx - 1;
-      valid = ly < p.TH + 2 && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
-      poff = (long long)gy * p.W + gx;
+    if (KS == 3) {
+      const int rows_used = p.N + 2 * TWp + 2;
+      if (r >= 1 && r < rows_used) {
+        const int q = r - 1, ly = q / TWp, lx = q - ly * TWp;
+        const int gy = ty0 + ly - 1, gx = tx0 + lx - 1;
+        valid = ly < p.TH + 2 && gy >= 0 && gy < p.Hi && gx >= 0 && gx < p.Wi;
+        poff = (long long)gy * p.Wi + gx;
+      }
+    } else {
+      const long long op = pix0 + r;
+      if (r < p.N && op < HW) {
+        const int oy = (int)(op / p.W), ox = (int)(op - (long long)oy * p.W);
+        valid = true;
+        poff = (long long)(oy * p.stride) * p.Wi + ox * p.stride;
+      }
     }
-    const float* xb = p.x + (long long)nb * p.Cin * HW + poff;
+    const float* xb = p.x + (long long)nb * p.xs_n + poff * p.xs_p;
     float v[CV_KC];
     auto load = [&](int c) {
+      if (p.x_vec) {                                           // channels-last: 32 consecutive floats
 #pragma unroll
-      for (int i = 0; i < CV_KC; ++i) v[i] = valid ? __ldg(xb + (long long)(c * CV_KC + i) * HW) : 0.f;
+        for (int k4 = 0; k4 < 8; ++k4) {
+          const float4 f = valid ? __ldg(reinterpret_cast<const float4*>(xb + c * CV_KC + 4 * k4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          v[4 * k4] = f.x; v[4 * k4 + 1] = f.y; v[4 * k4 + 2] = f.z; v[4 * k4 + 3] = f.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < CV_KC; ++i) v[i] = valid ? __ldg(xb + (long long)(c * CV_KC + i) * p.xs_c) : 0.f;
+      }
     };
-    load(0);
-    for (int c = 0; c < chunks; ++c) {
-      const int s = c & 1;
-      mbar_wait(smem_u32(&T.x_empty[s]), ((c >> 1) & 1) ^ 1);
+    if (grp < chunks) load(grp);
+    for (int c = grp; c < chunks; c += GROUPS) {
+      const int s = c % XST;
+      mbar_wait(smem_u32(&T.x_empty[s]), ((c / XST) & 1) ^ 1);
       if (row_live) {
-        unsigned char* hi = Xs + s * CV_X_BYTES + r * 128;
-        unsigned char* lo = hi + CV_X_PLANE;
+        unsigned char* hi = Xs + s * XSTAGE + r * 128;
+        unsigned char* lo = hi + XPLANE;
 #pragma unroll
         for (int k4 = 0; k4 < 8; ++k4) {
           float4 f = make_float4(v[4 * k4], v[4 * k4 + 1], v[4 * k4 + 2], v[4 * k4 + 3]);
@@ -132,13 +173,13 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv3x3_tc_kernel(const ConvTcP
       }
       fence_proxy_async();
       mbar_arrive(smem_u32(&T.x_full[s]));
-      if (c + 1 < chunks) load(c + 1);
+      if (c + GROUPS < chunks) load(c + GROUPS);
     }
   } else if (warp == 13) {
     // ================================== weight loader ==================================
     if (lane == 0) {
-      const unsigned char* wsrc = p.wimg + (size_t)cot * chunks * 9 * CV_A_BYTES;
-      const int steps = chunks * 9;
+      const unsigned char* wsrc = p.wimg + (size_t)cot * chunks * TAPS * CV_A_BYTES;
+      const int steps = chunks * TAPS;
       for (int i = 0; i < steps; ++i) {
         const int s = i % CV_A_STAGES;
         mbar_wait(smem_u32(&T.a_empty[s]), ((i / CV_A_STAGES) & 1) ^ 1);
@@ -152,16 +193,18 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv3x3_tc_kernel(const ConvTcP
       const uint32_t idesc = idesc_tf32(CV_M, p.N, false, false);
       int i = 0;
       for (int c = 0; c < chunks; ++c) {
-        const int xs = c & 1;
-        mbar_wait(smem_u32(&T.x_full[xs]), (c >> 1) & 1);
+        const int xs = c % XST;
+        mbar_wait(smem_u32(&T.x_full[xs]), (c / XST) & 1);
         tc_fence_after();
-        const uint32_t xb_hi = smem_u32(Xs + xs * CV_X_BYTES), xb_lo = xb_hi + CV_X_PLANE;
-        for (int t = 0; t < 9; ++t, ++i) {
+        const uint32_t xb_hi = smem_u32(Xs + xs * XSTAGE), xb_lo = xb_hi + XPLANE;
+        const uint32_t acc_hh = tmem + (uint32_t)(c % 3) * 128u;
+#pragma unroll 1
+        for (int t = 0; t < TAPS; ++t, ++i) {
           const int s = i % CV_A_STAGES;
           mbar_wait(smem_u32(&T.a_full[s]), (i / CV_A_STAGES) & 1);
           tc_fence_after();
           const uint32_t a_hi = smem_u32(As + s * CV_A_BYTES), a_lo = a_hi + CV_M * 128;
-          const uint32_t shift = (uint32_t)((t / 3) * TWp + (t % 3)) * 128u;
+          const uint32_t shift = KS == 3 ? (uint32_t)((t / 3) * TWp + (t % 3)) * 128u : 0u;
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const uint64_t da_hi = desc_sw128_kmajor(a_hi + ks * 32), da_lo = desc_sw128_kmajor(a_lo + ks * 32);
@@ -169,7 +212,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv3x3_tc_kernel(const ConvTcP
             const uint64_t db_lo = desc_sw128_kmajor(xb_lo + shift + ks * 32);
             tc_mma_tf32(tmem + 384, da_lo, db_hi, idesc, (i | ks) != 0 ? 1u : 0u);      // cross terms
             tc_mma_tf32(tmem + 384, da_hi, db_lo, idesc, 1u);
-            tc_mma_tf32(tmem + (uint32_t)(c % 3) * 128u, da_hi, db_hi, idesc, (c >= 3 || (t | ks) != 0) ? 1u : 0u);
+            tc_mma_tf32(acc_hh, da_hi, db_hi, idesc, (c >= 3 || (t | ks) != 0) ? 1u : 0u);
           }
           tc_commit(smem_u32(&T.a_empty[s]));
         }
@@ -182,12 +225,13 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv3x3_tc_kernel(const ConvTcP
     const int co = cot * CV_M + tid;
     const bool co_ok = co < p.Cout;                           // the last channel tile may be padded (zero weight rows)
     const float b = (p.bias && co_ok) ? __ldg(p.bias + co) : 0.f;
-    const long long obase = ((long long)nb * p.Cout + co) * HW;
+    float* yb = p.y + (long long)nb * p.ys_n + (long long)co * p.ys_c;
+    const float* zb = p.z ? p.z + (long long)nb * p.zs_n + (long long)co * p.zs_c : nullptr;
     const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
     mbar_wait(smem_u32(&T.acc_full), 0);
     tc_fence_after();
-    int ty = 0, lx = 0;                                     // position j = ty * TWp + lx
     const int nacc = chunks < 3 ? chunks : 3;               // hi.hi accumulators in use
+    int ty = 0, lx = 0;                                     // 3x3: position j = ty * TWp + lx
     for (int g = 0; g < p.N; g += 32) {
       uint32_t o[32], q[32];
       tmem_ld32(lane_base + g, o);                          // (columns >= N of the last group are never stored)
@@ -201,15 +245,23 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv3x3_tc_kernel(const ConvTcP
       for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) + __uint_as_float(q[j]));
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const int gy = ty0 + ty, gx = tx0 + lx - 1;
-        if (co_ok && g + j < p.N && lx >= 1 && lx <= p.TW && ty < p.TH && gy < p.H && gx < p.W) {
-          const long long a = obase + (long long)gy * p.W + gx;
-          float val = __uint_as_float(o[j]) + b;
-          if (p.z) val += __ldg(p.z + a);
-          if (p.relu_out) val = fmaxf(val, 0.f);
-          p.y[a] = val;
+        bool ok;
+        long long pix;
+        if (KS == 3) {
+          const int gy = ty0 + ty, gx = tx0 + lx - 1;
+          ok = g + j < p.N && lx >= 1 && lx <= p.TW && ty < p.TH && gy < p.H && gx < p.W;
+          pix = (long long)gy * p.W + gx;
+          if (++lx == TWp) { lx = 0; ++ty; }
+        } else {
+          pix = pix0 + g + j;
+          ok = g + j < p.N && pix < HW;
         }
-        if (++lx == TWp) { lx = 0; ++ty; }
+        if (co_ok && ok) {
+          float val = __uint_as_float(o[j]) + b;
+          if (zb) val += __ldg(zb + pix * p.zs_p);
+          if (p.relu_out) val = fmaxf(val, 0.f);
+          yb[pix * p.ys_p] = val;
+        }
       }
     }
   }
@@ -221,26 +273,26 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv3x3_tc_kernel(const ConvTcP
   }
 }
 
-// weight operand image: one thread per (output channel, chunk, tap, 16-byte piece)
-__global__ void __launch_bounds__(256) conv3x3_weight_image_kernel(const float* __restrict__ w, int Cout, int Cin,
-                                                                   unsigned char* __restrict__ img) {
+// weight operand image: one thread per (output channel, chunk, tap, 16-byte piece); weight [Cout, Cin, KS, KS]
+__global__ void __launch_bounds__(256) conv_weight_image_kernel(const float* __restrict__ w, int Cout, int Cin, int taps,
+                                                                unsigned char* __restrict__ img) {
   const int chunks = Cin / CV_KC;
-  const long long total = (long long)((Cout + CV_M - 1) / CV_M * CV_M) * chunks * 9 * 8;
+  const long long total = (long long)((Cout + CV_M - 1) / CV_M * CV_M) * chunks * taps * 8;
   const long long f = (long long)blockIdx.x * 256 + threadIdx.x;
   if (f >= total) return;
   const int k4 = (int)(f & 7);
   long long g = f >> 3;
   const int row = (int)(g % CV_M); g /= CV_M;
-  const int t = (int)(g % 9); g /= 9;
+  const int t = (int)(g % taps); g /= taps;
   const int c = (int)(g % chunks);
   const int cot = (int)(g / chunks);
   const int co = cot * CV_M + row;
   float v[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) v[i] = co < Cout ? w[((long long)co * Cin + c * CV_KC + 4 * k4 + i) * 9 + t] : 0.f;
+  for (int i = 0; i < 4; ++i) v[i] = co < Cout ? w[((long long)co * Cin + c * CV_KC + 4 * k4 + i) * taps + t] : 0.f;
   const float4 h = make_float4(to_tf32(v[0]), to_tf32(v[1]), to_tf32(v[2]), to_tf32(v[3]));
   const float4 l = make_float4(to_tf32(v[0] - h.x), to_tf32(v[1] - h.y), to_tf32(v[2] - h.z), to_tf32(v[3] - h.w));
-  unsigned char* blk = img + (((size_t)cot * chunks + c) * 9 + t) * CV_A_BYTES;
+  unsigned char* blk = img + (((size_t)cot * chunks + c) * taps + t) * CV_A_BYTES;
   const int off = row * 128 + ((k4 ^ (row & 7)) << 4);
   *reinterpret_cast<float4*>(blk + off) = h;
   *reinterpret_cast<float4*>(blk + CV_M * 128 + off) = l;
@@ -252,30 +304,32 @@ __global__ void __launch_bounds__(256) conv3x3_weight_image_kernel(const float* 
 
 using namespace cutie;
 
-extern "C" int64_t cutie_conv3x3_weight_image_bytes(int64_t Cout, int64_t Cin) {
-  if (Cout < 1 || Cin < CV_KC || Cin % CV_KC) return -1;
-  return ((Cout + CV_M - 1) / CV_M) * (Cin / CV_KC) * 9 * (int64_t)CV_A_BYTES;
+extern "C" int64_t cutie_conv_weight_image_bytes(int64_t Cout, int64_t Cin, int ksize) {
+  if (Cout < 1 || Cin < CV_KC || Cin % CV_KC || (ksize != 1 && ksize != 3)) return -1;
+  return ((Cout + CV_M - 1) / CV_M) * (Cin / CV_KC) * ksize * ksize * (int64_t)CV_A_BYTES;
 }
 
-extern "C" int cutie_conv3x3_weight_image(const float* weight, int64_t Cout, int64_t Cin, void* image, void* stream) {
+extern "C" int cutie_conv_weight_image(const float* weight, int64_t Cout, int64_t Cin, int ksize, void* image, void* stream) {
   CUTIE_REQUIRE(weight && image, "null argument");
+  CUTIE_REQUIRE(ksize == 1 || ksize == 3, "1x1 or 3x3");
   CUTIE_REQUIRE(Cout >= 1 && Cin >= CV_KC && Cin % CV_KC == 0, "input channels must be a multiple of 32");
-  const long long total = (Cout + CV_M - 1) / CV_M * CV_M * (Cin / CV_KC) * 9 * 8;
-  conv3x3_weight_image_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      weight, (int)Cout, (int)Cin, static_cast<unsigned char*>(image));
+  const int taps = ksize * ksize;
+  const long long total = (Cout + CV_M - 1) / CV_M * CV_M * (Cin / CV_KC) * taps * 8;
+  conv_weight_image_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      weight, (int)Cout, (int)Cin, taps, static_cast<unsigned char*>(image));
   CUTIE_CHECK_LAUNCH();
   return 0;
 }
 
-// spatial tile: TW | tile width (full rows when they fit), TH rows, N = round16(TH * (TW + 2)) <= 128 and
-// N + 2 (TW + 2) + 2 <= CV_ROWS; maximise useful pixels per MMA column over the whole image (edge tiles included)
+// 3x3 spatial tile: TW | tile width (full rows when they fit), TH rows, N = round16(TH * (TW + 2)) <= 128 and
+// N + 2 (TW + 2) + 2 <= 248 rows; maximise useful pixels per MMA column over the whole image (edge tiles included)
 static void conv_tile_shape(int H, int W, int* TH, int* TW, int* N) {
   double best = -1;
   for (int parts = 1; parts <= W; ++parts) {
     const int tw = (W + parts - 1) / parts;
     for (int th = 1; th <= H && th * (tw + 2) <= 128; ++th) {
       const int n = (th * (tw + 2) + 15) / 16 * 16;
-      if (n + 2 * (tw + 2) + 2 > CV_ROWS) continue;
+      if (n + 2 * (tw + 2) + 2 > CV3_ROWS) continue;
       const long long tiles = (long long)((H + th - 1) / th) * ((W + tw - 1) / tw);
       const double eff = (double)H * W / ((double)tiles * n);
       // the most useful pixels per MMA column; among equals the larger N (fewer CTAs re-reading the weights)
@@ -285,27 +339,51 @@ static void conv_tile_shape(int H, int W, int* TH, int* TW, int* N) {
   }
 }
 
-extern "C" int cutie_conv3x3_tc(const float* x, const void* weight_image, const float* bias, const float* residual,
-                                int64_t NB, int64_t Cin, int64_t Cout, int64_t H, int64_t W, int relu_in, int relu_out,
-                                float* y, void* stream) {
-  CUTIE_REQUIRE(x && weight_image && y, "null argument");
+extern "C" int cutie_conv_tc(const float* x, const int64_t* x_strides, const void* weight_image, const float* bias,
+                             const float* residual, const int64_t* residual_strides, int64_t NB, int64_t Cin, int64_t Cout,
+                             int64_t H_in, int64_t W_in, int ksize, int stride, int relu_in, int relu_out, float* y,
+                             const int64_t* y_strides, void* stream) {
+  CUTIE_REQUIRE(x && x_strides && weight_image && y && y_strides, "null argument");
+  CUTIE_REQUIRE(residual == nullptr || residual_strides != nullptr, "residual needs strides");
+  CUTIE_REQUIRE((ksize == 3 && stride == 1) || (ksize == 1 && (stride == 1 || stride == 2)),
+                "3x3 stride 1, or 1x1 stride 1 / 2");
   CUTIE_REQUIRE(Cout >= 1 && Cin >= CV_KC && Cin % CV_KC == 0, "input channels must be a multiple of 32");
-  CUTIE_REQUIRE(NB >= 1 && NB <= 65535 && H >= 1 && W >= 1 && H * W < (1ll << 30), "bad geometry");
+  CUTIE_REQUIRE(NB >= 1 && NB <= 65535 && H_in >= 1 && W_in >= 1 && H_in * W_in < (1ll << 30), "bad geometry");
   ConvTcParams p;
   p.x = x; p.wimg = static_cast<const unsigned char*>(weight_image); p.bias = bias; p.z = residual; p.y = y;
-  p.Cin = (int)Cin; p.Cout = (int)Cout; p.H = (int)H; p.W = (int)W;
-  p.TH = 0; p.TW = 0; p.N = 0;
-  conv_tile_shape(p.H, p.W, &p.TH, &p.TW, &p.N);
-  CUTIE_REQUIRE(p.N >= 16, "no tile shape for this geometry");
-  p.tiles_x = (p.W + p.TW - 1) / p.TW;
+  p.xs_n = x_strides[0]; p.xs_c = x_strides[1]; p.xs_p = x_strides[2];
+  p.ys_n = y_strides[0]; p.ys_c = y_strides[1]; p.ys_p = y_strides[2];
+  p.zs_n = residual ? residual_strides[0] : 0;
+  p.zs_c = residual ? residual_strides[1] : 0;
+  p.zs_p = residual ? residual_strides[2] : 0;
+  p.Cin = (int)Cin; p.Cout = (int)Cout; p.Hi = (int)H_in; p.Wi = (int)W_in; p.stride = stride;
+  p.H = (int)((H_in - 1) / stride + 1); p.W = (int)((W_in - 1) / stride + 1);
   p.relu_in = relu_in; p.relu_out = relu_out;
-  const long long tiles = (long long)p.tiles_x * ((p.H + p.TH - 1) / p.TH);
+  // channels-last input: a producer thread reads its pixel's 32 channels as 8 x 16 bytes
+  p.x_vec = (p.xs_c == 1 && p.xs_p % 4 == 0 && p.xs_n % 4 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0) ? 1 : 0;
+  long long tiles;
+  p.TH = 0; p.TW = 0; p.N = 0; p.tiles_x = 1;
+  if (ksize == 3) {
+    conv_tile_shape(p.H, p.W, &p.TH, &p.TW, &p.N);
+    CUTIE_REQUIRE(p.N >= 16, "no tile shape for this geometry");
+    p.tiles_x = (p.W + p.TW - 1) / p.TW;
+    tiles = (long long)p.tiles_x * ((p.H + p.TH - 1) / p.TH);
+  } else {
+    const long long hw = (long long)p.H * p.W;
+    p.N = hw >= 128 ? 128 : (int)((hw + 15) / 16 * 16);
+    tiles = (hw + p.N - 1) / p.N;
+  }
   CUTIE_REQUIRE(tiles <= 0x7fffffff, "too many tiles");
   static bool attr_done[64] = {};
-  if (first_use_on_device(attr_done))
-    cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SMEM);
-  conv3x3_tc_kernel<<<dim3((unsigned)tiles, (unsigned)((Cout + CV_M - 1) / CV_M), (unsigned)NB), CV_THREADS, CV_SMEM,
-                      (cudaStream_t)stream>>>(p);
+  if (first_use_on_device(attr_done)) {
+    cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SMEM3);
+    cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SMEM1);
+  }
+  const dim3 grid((unsigned)tiles, (unsigned)((Cout + CV_M - 1) / CV_M), (unsigned)NB);
+  if (ksize == 3)
+    conv_tc_kernel<3><<<grid, CV_THREADS, CV_SMEM3, (cudaStream_t)stream>>>(p);
+  else
+    conv_tc_kernel<1><<<grid, CV_THREADS, CV_SMEM1, (cudaStream_t)stream>>>(p);
   CUTIE_CHECK_LAUNCH();
   return 0;
 }

@@ -436,44 +436,74 @@ def conv3x3_c1(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, relu_i
     return out
 
 
-def conv3x3_tc_eligible(weight: torch.Tensor, stride=(1, 1), padding=(1, 1), dilation=(1, 1), groups: int = 1) -> bool:
-    """Geometry cutie_conv3x3_tc implements: 3x3, stride 1, zero pad 1, Cin % 32 == 0; output channels go in tiles of 128
-    (a partial tile costs a full one, so layers with fewer than 64 output channels stay with the library)."""
-    return (weight.dim() == 4 and tuple(weight.shape[2:]) == (3, 3) and tuple(stride) == (1, 1) and tuple(padding) == (1, 1)
-            and tuple(dilation) == (1, 1) and groups == 1 and weight.shape[0] >= 64 and weight.shape[1] % 32 == 0)
+def conv_tc_eligible(weight: torch.Tensor, stride=(1, 1), padding=(1, 1), dilation=(1, 1), groups: int = 1) -> bool:
+    """Geometries cutie_conv_tc implements: 3x3 / stride 1 / zero pad 1 and 1x1 / stride 1 or 2 / no pad, Cin % 32 == 0;
+    output channels go in tiles of 128 (a partial tile costs a full one, so layers with fewer than 64 output channels stay
+    with the library)."""
+    if weight.dim() != 4 or groups != 1 or tuple(dilation) != (1, 1) or weight.shape[0] < 64 or weight.shape[1] % 32:
+        return False
+    k = tuple(weight.shape[2:])
+    if k == (3, 3):
+        return tuple(stride) == (1, 1) and tuple(padding) == (1, 1)
+    if k == (1, 1):
+        return tuple(stride) in ((1, 1), (2, 2)) and tuple(padding) == (0, 0)
+    return False
 
 
-def conv3x3_weight_image(weight: torch.Tensor) -> torch.Tensor:
+def conv_weight_image(weight: torch.Tensor) -> torch.Tensor:
     """The layer's tcgen05 operand image (tf32 hi | lo planes per (128-channel tile, 32-channel chunk, tap), swizzled):
     built once per weight version, 2x the weight bytes."""
-    Cout, Cin = weight.shape[:2]
-    assert conv3x3_tc_eligible(weight) and weight.dtype == torch.float32
-    lib().cutie_conv3x3_weight_image_bytes.restype = ctypes.c_int64
-    nbytes = lib().cutie_conv3x3_weight_image_bytes(_i64(Cout), _i64(Cin))
+    Cout, Cin, k = weight.shape[0], weight.shape[1], weight.shape[2]
+    assert weight.dtype == torch.float32 and weight.shape[2] == weight.shape[3] and k in (1, 3) and Cin % 32 == 0
+    lib().cutie_conv_weight_image_bytes.restype = ctypes.c_int64
+    nbytes = lib().cutie_conv_weight_image_bytes(_i64(Cout), _i64(Cin), int(k))
     img = torch.empty(nbytes // 4, dtype=torch.float32, device=weight.device)
     w = weight.detach().contiguous()
-    with _call('conv3x3_weight_image', 1):
-        st = lib().cutie_conv3x3_weight_image(_ptr(w), _i64(Cout), _i64(Cin), _ptr(img), _stream())
-    _check(st, 'cutie_conv3x3_weight_image')
+    with _call('conv_weight_image', 1):
+        st = lib().cutie_conv_weight_image(_ptr(w), _i64(Cout), _i64(Cin), int(k), _ptr(img), _stream())
+    _check(st, 'cutie_conv_weight_image')
     return img
 
 
-def conv3x3_tc(x: torch.Tensor, weight_image: torch.Tensor, bias: Optional[torch.Tensor], cout: int,
-               residual: Optional[torch.Tensor] = None, relu_in: bool = False, relu_out: bool = False) -> torch.Tensor:
-    """act(bias + conv3x3(pre(x)) [+ residual]) on the tensor cores with 3xTF32 splitting (fp32-class accuracy):
-    x [N, Cin, H, W] dense NCHW -> [N, cout, H, W]."""
+def _ncp_strides(t: torch.Tensor):
+    """(image, channel, pixel) element strides of a dense NCHW or channels-last [N, C, H, W] tensor, else None."""
+    N, C, H, W = t.shape
+    sn, sc, sh, sw = t.stride()
+    if W > 1 and sh != sw * W and H > 1:
+        return None
+    if H == 1 and W == 1:
+        return (sn, sc, 1)
+    return (sn, sc, sw if W > 1 else sh)
+
+
+def conv_tc(x: torch.Tensor, weight_image: torch.Tensor, bias: Optional[torch.Tensor], cout: int, ksize: int = 3,
+            stride: int = 1, residual: Optional[torch.Tensor] = None, relu_in: bool = False,
+            relu_out: bool = False) -> torch.Tensor:
+    """act(bias + conv(pre(x)) [+ residual]) on the tensor cores with 3xTF32 splitting (fp32-class accuracy).
+    x [N, Cin, H, W] dense NCHW or channels-last (the output takes the same memory format) -> [N, cout, H', W']."""
     N, Cin, H, W = x.shape
-    assert x.dtype == torch.float32
-    x = x.contiguous()
+    assert x.dtype == torch.float32 and ksize in (1, 3)
+    cl = x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous()
+    if not cl:
+        x = x.contiguous()
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    out = torch.empty(N, cout, Ho, Wo, dtype=torch.float32, device=x.device,
+                      memory_format=torch.channels_last if cl else torch.contiguous_format)
+    zs = None
     if residual is not None:
-        assert tuple(residual.shape) == (N, cout, H, W)
-        residual = residual.contiguous()
-    out = torch.empty(N, cout, H, W, dtype=torch.float32, device=x.device)
-    with _call('conv3x3_tc', 1):
-        st = lib().cutie_conv3x3_tc(_ptr(x), _ptr(weight_image), _ptr(bias.detach() if bias is not None else None),
-                                    _ptr(residual), _i64(N), _i64(Cin), _i64(cout), _i64(H), _i64(W), int(bool(relu_in)),
-                                    int(bool(relu_out)), _ptr(out), _stream())
-    _check(st, 'cutie_conv3x3_tc')
+        assert tuple(residual.shape) == (N, cout, Ho, Wo)
+        zs = _ncp_strides(residual)
+        if zs is None:
+            residual = residual.contiguous()
+            zs = _ncp_strides(residual)
+    arr = lambda t: (ctypes.c_int64 * 3)(*t)
+    with _call('conv_tc', 1):
+        st = lib().cutie_conv_tc(_ptr(x), arr(_ncp_strides(x)), _ptr(weight_image),
+                                 _ptr(bias.detach() if bias is not None else None), _ptr(residual),
+                                 arr(zs) if zs is not None else None, _i64(N), _i64(Cin), _i64(cout), _i64(H), _i64(W),
+                                 int(ksize), int(stride), int(bool(relu_in)), int(bool(relu_out)), _ptr(out),
+                                 arr(_ncp_strides(out)), _stream())
+    _check(st, 'cutie_conv_tc')
     return out
 
 

@@ -200,9 +200,6 @@ class CUTIE(nn.Module):
                     m = getattr(enc, name, None)
                     if m is not None:
                         m.to(memory_format=torch.channels_last)
-                        for c in m.modules():           # the trunk stays a cuDNN channels-last region (fuse._tc_eligible)
-                            if isinstance(c, nn.Conv2d):
-                                object.__setattr__(c, 'tc_exempt', True)
                 enc.channels_last = True
         # after the folding: fold_trunk_ replaces the trunk convolutions by new modules
         object.__setattr__(self, 'conv_epilogues', ConvEpilogueFuser(enabled=bool(fuse_epilogues)))

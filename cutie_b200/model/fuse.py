@@ -56,13 +56,13 @@ class ConvEpilogueFuser:
       'kernel'  F.conv2d(x, w, None) + cutie_bias_act(y, b, z, relu)     -- the bias-less convolution followed by ONE
                 float4 stream of ours (csrc/pixel.cu), same association as 'aten' => bit-identical results
       'pool'    (ResNet stems) bias-less convolution + cutie_bias_relu_maxpool: bias, clamp and 3x3/s2 pooling in one pass
-      'tc'      cutie_conv3x3_tc: the convolution ITSELF on the tensor cores (tcgen05 implicit GEMM, 3xTF32 operand split =
+      'tc'      cutie_conv_tc: the convolution ITSELF on the tensor cores (tcgen05 implicit GEMM, 3xTF32 operand split =
                 fp32-class accuracy; csrc/conv_tc.cu) with bias, residual, ReLU and the ReLU of the INPUT in the same
-                kernel -- for 3x3 / stride 1 / pad 1 layers with Cin % 32 == 0, Cout >= 64 outside the channels-last
-                trunks (PixelFFN, fuser, key projection, decoder and sensory-update
-                convolutions); reads and writes dense NCHW (a channels-last input is re-laid out once)
+                kernel -- 3x3 / stride 1 / pad 1 and 1x1 / stride 1 or 2 layers with Cin % 32 == 0 and Cout >= 64, dense
+                NCHW or channels-last (the output keeps the input's memory format): SURVEY.md section 8(f).1-3 --
+                PixelFFN, fuser, key projection, decoder, sensory update and the trunks' bottleneck convolutions
 
-    DETERMINISTIC: the form is a function of the layer geometry and the epilogue alone -- `RULE`: eligible 3x3 layers take
+    DETERMINISTIC: the form is a function of the layer geometry and the epilogue alone -- `RULE`: eligible 3x3 / 1x1 layers take
     'tc'; of the rest ReLU epilogues take 'cudnn', bias-only and bias+residual epilogues take 'kernel', stems take 'pool' -- which is what the round-1 on-device A/B chose for 101 of
     104 layers on B200 with fp32 convolutions (BENCH/profiles r02); nothing is timed at run time, so two runs of the
     same video execute the same arithmetic.  CPU tensors (the oracle harness borrowing these modules) always take 'aten'.
@@ -72,7 +72,7 @@ class ConvEpilogueFuser:
     instead (read once per call, ~100 MB per 480p frame over all layers: 15 us of HBM time).
     """
     FORMS = ('aten', 'cudnn', 'kernel', 'tc')
-    RULE = {'conv3x3': 'tc', 'relu': 'cudnn', 'linear': 'kernel', 'stem': 'pool'}
+    RULE = {'conv': 'tc', 'relu': 'cudnn', 'linear': 'kernel', 'stem': 'pool'}
 
     def __init__(self, enabled: bool = True, rule=None):
         self.enabled = enabled
@@ -136,16 +136,15 @@ class ConvEpilogueFuser:
             ident = (w.data_ptr(), None)
         hit = self._images.get(id(conv))
         if hit is None or hit[0] != ident:
-            hit = (ident, K_.conv3x3_weight_image(w))
+            hit = (ident, K_.conv_weight_image(w))
             self._images[id(conv)] = hit
-        return K_.conv3x3_tc(x, hit[1], conv.bias, conv.out_channels, residual=z, relu_in=relu_in, relu_out=relu)
+        return K_.conv_tc(x, hit[1], conv.bias, conv.out_channels, ksize=conv.kernel_size[0], stride=conv.stride[0],
+                          residual=z, relu_in=relu_in, relu_out=relu)
 
     def _tc_eligible(self, conv: nn.Conv2d, x: torch.Tensor, z) -> bool:
         from cutie_b200 import kernels as K_
-        # `tc_exempt`: layers inside a region that runs channels-last end to end (the ResNet trunks, whose 1x1 and strided
-        # convolutions stay cuDNN calls) keep the library's 3x3 too -- a dense-NCHW island would cost two re-layouts
-        return (self.rule.get('conv3x3') == 'tc' and not getattr(conv, 'tc_exempt', False)
-                and K_.conv3x3_tc_eligible(conv.weight, conv.stride, conv.padding, conv.dilation, conv.groups))
+        return (self.rule.get('conv') == 'tc'
+                and K_.conv_tc_eligible(conv.weight, conv.stride, conv.padding, conv.dilation, conv.groups))
 
     def run(self, form: str, conv: nn.Conv2d, x: torch.Tensor, z=None, relu: bool = True, relu_in: bool = False) -> torch.Tensor:
         if form == 'tc':

@@ -165,19 +165,25 @@ int cutie_bias_relu_maxpool(const float* y, const float* bias, float* out, int64
 int cutie_segment_tail(const float* x, float* agg, float* logits, float* prob, int64_t B, int64_t K, int64_t h, int64_t w,
                        void* stream);
 
-/* 3x3 / stride 1 / zero-pad 1 convolution as a tcgen05 implicit GEMM with 3xTF32 operand splitting (fp32-class accuracy;
- * csrc/conv_tc.cu): y = act(bias + conv(pre(x), W) [+ residual]), pre = ReLU if relu_in, act = ReLU if relu_out.
- * x [NB, Cin, H, W], y / residual [NB, Cout, H, W] dense NCHW fp32; Cin % 32 == 0 (output channels are processed in tiles
- * of 128; a partial last tile costs a full one).
- * Replaces the F.conv2d calls of PixelFFN / CAResBlock (transformer_layers.py:121-136, channel_attn.py:7-39: two 256 -> 256
- * convolutions per transformer block) and of PixelFeatureFuser (big_modules.py:192-235) -- SURVEY.md section 8(f).1.
- * `weight_image` is the layer's operand image: cutie_conv3x3_weight_image(weight [Cout, Cin, 3, 3]) once per weight
- * version, cutie_conv3x3_weight_image_bytes(Cout, Cin) bytes (tf32 hi | lo planes per (128-channel tile, 32-channel
- * chunk, tap) in K-major SWIZZLE_128B order: one 32 KB cp.async.bulk per MMA step). */
-int64_t cutie_conv3x3_weight_image_bytes(int64_t Cout, int64_t Cin);
-int cutie_conv3x3_weight_image(const float* weight, int64_t Cout, int64_t Cin, void* image, void* stream);
-int cutie_conv3x3_tc(const float* x, const void* weight_image, const float* bias, const float* residual, int64_t NB,
-                     int64_t Cin, int64_t Cout, int64_t H, int64_t W, int relu_in, int relu_out, float* y, void* stream);
+/* 3x3 (stride 1, zero-pad 1) and 1x1 (stride 1 or 2) convolutions as tcgen05 implicit GEMMs with 3xTF32 operand splitting
+ * (fp32-class accuracy, measured 2-6x closer to float64 than cuDNN's fp32 result; csrc/conv_tc.cu):
+ *     y = act(bias + conv(pre(x), W) [+ residual]),  pre = ReLU if relu_in, act = ReLU if relu_out.
+ * x [NB, Cin, H_in, W_in], y / residual [NB, Cout, H_out, W_out] fp32, each addressed through three ELEMENT strides
+ * {image, channel, pixel} (pixel = row * width + column): dense NCHW = {C*H*W, H*W, 1}, channels-last = {C*H*W, 1, C}.
+ * Cin % 32 == 0; output channels are processed in tiles of 128 (a partial last tile costs a full one).
+ * Replaces the F.conv2d calls of PixelFFN / CAResBlock (transformer_layers.py:121-136, channel_attn.py:7-39),
+ * PixelFeatureFuser (big_modules.py:192-235), KeyProjection (big_modules.py:66-87), MaskDecoder / SensoryUpdater
+ * (big_modules.py:238-306, modules.py:46-85) and the stride-1 3x3 and all 1x1 convolutions of the ResNet trunks
+ * (utils/resnet.py:77-131) -- SURVEY.md section 8(f).1-3.
+ * `weight_image` is the layer's operand image: cutie_conv_weight_image(weight [Cout, Cin, k, k]) once per weight version,
+ * cutie_conv_weight_image_bytes(Cout, Cin, k) bytes (tf32 hi | lo planes per (128-channel tile, 32-channel chunk, tap) in
+ * K-major SWIZZLE_128B order: one 32 KB cp.async.bulk per MMA step). */
+int64_t cutie_conv_weight_image_bytes(int64_t Cout, int64_t Cin, int ksize);
+int cutie_conv_weight_image(const float* weight, int64_t Cout, int64_t Cin, int ksize, void* image, void* stream);
+int cutie_conv_tc(const float* x, const int64_t* x_strides, const void* weight_image, const float* bias,
+                  const float* residual, const int64_t* residual_strides, int64_t NB, int64_t Cin, int64_t Cout,
+                  int64_t H_in, int64_t W_in, int ksize, int stride, int relu_in, int relu_out, float* y,
+                  const int64_t* y_strides, void* stream);
 /* test hook: the spatial tile the launcher picks (out3 = {rows, columns, MMA N}). */
 int cutie_debug_conv_tile_shape(int64_t H, int64_t W, int* out3);
 

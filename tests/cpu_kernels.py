@@ -268,14 +268,14 @@ def conv3x3_c1(x, weight, bias, relu_input=False):
     return F.conv2d(torch.relu(x) if relu_input else x, weight, bias, padding=1)
 
 
-def conv3x3_weight_image(weight):
+def conv_weight_image(weight):
     return weight.detach()                      # the emulation's "operand image" is the weight itself
 
 
-def conv3x3_tc(x, weight_image, bias, cout, residual=None, relu_in=False, relu_out=False):
+def conv_tc(x, weight_image, bias, cout, ksize=3, stride=1, residual=None, relu_in=False, relu_out=False):
     import torch.nn.functional as F
-    assert weight_image.shape[0] == cout
-    y = F.conv2d(torch.relu(x) if relu_in else x, weight_image, bias, padding=1)
+    assert weight_image.shape[0] == cout and weight_image.shape[2] == ksize
+    y = F.conv2d(torch.relu(x) if relu_in else x, weight_image, bias, stride=stride, padding=ksize // 2)
     if residual is not None:
         y = y + residual
     return torch.relu(y) if relu_out else y
@@ -301,7 +301,7 @@ def gated_update(h, v):
     return f * h * (1 - u) + u * n
 
 
-ALL = ['last_candidate_counts', 'bias_act_', 'bias_relu_maxpool', 'segment_tail', 'conv3x3_c1', 'conv3x3_weight_image', 'conv3x3_tc', 'area_pool', 'eca_scale_add_', 'gated_update', 'affinity_topk', 'topk_merge', 'readout_gather', 'usage_commit', 'bank_append', 'bank_export', 'bank_gather', 'bank_key_image', 'upsample2x_add', 'prob_to_mask',
+ALL = ['last_candidate_counts', 'bias_act_', 'bias_relu_maxpool', 'segment_tail', 'conv3x3_c1', 'conv_weight_image', 'conv_tc', 'area_pool', 'eca_scale_add_', 'gated_update', 'affinity_topk', 'topk_merge', 'readout_gather', 'usage_commit', 'bank_append', 'bank_export', 'bank_gather', 'bank_key_image', 'upsample2x_add', 'prob_to_mask',
        'consolidate', 'obj_summary_accumulate', 'qt_linear', 'qt_head_fold', 'qt_self_attention',
        'qt_aux_mask', 'qt_pixel_to_query', 'qt_query_to_pixel']
 

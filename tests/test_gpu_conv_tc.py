@@ -1,4 +1,4 @@
-"""cutie_conv3x3_tc (csrc/conv_tc.cu): the tcgen05 3xTF32 implicit-GEMM 3x3 convolution against F.conv2d evaluated in
+"""cutie_conv_tc (csrc/conv_tc.cu): the tcgen05 3xTF32 implicit-GEMM 3x3 / 1x1 convolution against F.conv2d evaluated in
 float64 (the ground truth) and against cuDNN's fp32 result (the library call it replaces): its error vs float64 must be of
 the same class as cuDNN's own fp32 error -- never a TF32-class (1e-3 relative) one."""
 import pytest
@@ -45,8 +45,8 @@ def test_conv3x3_tc_is_fp32_class_accurate(NB, Cin, Cout, H, W, epi):
     b = torch.randn(Cout, device='cuda', generator=g)
     z = torch.randn(NB, Cout, H, W, device='cuda', generator=g) if 'residual' in epi else None
     relu_in, relu_out = 'relu_in' in epi, 'relu_out' in epi
-    img = K_.conv3x3_weight_image(w)
-    got = K_.conv3x3_tc(x, img, b, Cout, residual=z, relu_in=relu_in, relu_out=relu_out)
+    img = K_.conv_weight_image(w)
+    got = K_.conv_tc(x, img, b, Cout, residual=z, relu_in=relu_in, relu_out=relu_out)
     ref = _ref64(x, w, b, z, relu_in, relu_out)
     lib32 = F.conv2d(x.relu() if relu_in else x, w, b, padding=1)
     if z is not None:
@@ -64,11 +64,11 @@ def test_conv3x3_tc_is_fp32_class_accurate(NB, Cin, Cout, H, W, epi):
 
 def test_conv3x3_tc_rejects_unsupported_geometry():
     import cutie_b200.kernels as K_
-    assert not K_.conv3x3_tc_eligible(torch.empty(32, 32, 3, 3)) and not K_.conv3x3_tc_eligible(torch.empty(128, 48, 3, 3))
-    assert K_.conv3x3_tc_eligible(torch.empty(128, 32, 3, 3)) and not K_.conv3x3_tc_eligible(torch.empty(128, 32, 3, 3), stride=(2, 2))
-    img = K_.conv3x3_weight_image(torch.randn(128, 32, 3, 3, device='cuda'))
+    assert not K_.conv_tc_eligible(torch.empty(32, 32, 3, 3)) and not K_.conv_tc_eligible(torch.empty(128, 48, 3, 3))
+    assert K_.conv_tc_eligible(torch.empty(128, 32, 3, 3)) and not K_.conv_tc_eligible(torch.empty(128, 32, 3, 3), stride=(2, 2))
+    img = K_.conv_weight_image(torch.randn(128, 32, 3, 3, device='cuda'))
     with pytest.raises(K_.KernelError):
-        K_.conv3x3_tc(torch.randn(1, 33, 4, 4, device='cuda'), img, None, 128)
+        K_.conv_tc(torch.randn(1, 33, 4, 4, device='cuda'), img, None, 128)
 
 
 @pytest.mark.parametrize('NB,Cin,Cout,H,W', [(3, 256, 256, 30, 54), (3, 512, 768, 30, 54), (3, 256, 128, 60, 108),
@@ -82,7 +82,7 @@ def test_conv3x3_tc_time_beside_cudnn_fp32(NB, Cin, Cout, H, W):
     x = torch.randn(NB, Cin, H, W, device='cuda')
     w = torch.randn(Cout, Cin, 3, 3, device='cuda') * 0.02
     b = torch.randn(Cout, device='cuda')
-    img = K_.conv3x3_weight_image(w)
+    img = K_.conv_weight_image(w)
 
     def timed(fn, n=30):
         for _ in range(5):
@@ -94,8 +94,93 @@ def test_conv3x3_tc_time_beside_cudnn_fp32(NB, Cin, Cout, H, W):
         e1.record()
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / n * 1e3
-    t_tc = timed(lambda: K_.conv3x3_tc(x, img, b, Cout, relu_out=True))
+    t_tc = timed(lambda: K_.conv_tc(x, img, b, Cout, relu_out=True))
     t_lib = timed(lambda: F.conv2d(x, w, b, padding=1).relu_())
     flops = 2.0 * NB * H * W * Cout * Cin * 9
     print(f'[{NB},{Cin}->{Cout},{H}x{W}] tcgen05 3xTF32 {t_tc:.1f} us ({flops / t_tc / 1e6:.1f} TFLOP/s fp32-equivalent), '
           f'cuDNN fp32 {t_lib:.1f} us ({flops / t_lib / 1e6:.1f} TFLOP/s)')
+
+
+CASES_1x1 = [
+    # NB, Cin, Cout, H, W, stride
+    (1, 1024, 256, 30, 54, 1),     # ResNet-50 layer3 bottleneck entry
+    (1, 256, 1024, 30, 54, 1),     # ... and exit
+    (1, 64, 256, 120, 216, 1),
+    (3, 256, 256, 30, 54, 1),      # pixel_init_proj
+    (1, 512, 1024, 60, 108, 2),    # layer3 projection shortcut (stride 2)
+    (2, 64, 128, 9, 7, 2),         # odd sizes, stride 2
+    (1, 32, 64, 3, 5, 1),          # fewer than 16 pixels
+]
+
+
+@pytest.mark.parametrize('NB,Cin,Cout,H,W,stride', CASES_1x1)
+@pytest.mark.parametrize('cl', [False, True])
+def test_conv1x1_tc_is_fp32_class_accurate(NB, Cin, Cout, H, W, stride, cl):
+    import cutie_b200.kernels as K_
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device='cuda').manual_seed(Cin + H)
+    x = torch.randn(NB, Cin, H, W, device='cuda', generator=g) * 1.5
+    w = torch.randn(Cout, Cin, 1, 1, device='cuda', generator=g) * (2.0 / Cin) ** 0.5
+    b = torch.randn(Cout, device='cuda', generator=g)
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    z = torch.randn(NB, Cout, Ho, Wo, device='cuda', generator=g)
+    if cl:
+        x = x.contiguous(memory_format=torch.channels_last)
+    img = K_.conv_weight_image(w)
+    got = K_.conv_tc(x, img, b, Cout, ksize=1, stride=stride, residual=z, relu_out=True)       # z stays dense NCHW
+    assert got.shape == (NB, Cout, Ho, Wo)
+    assert got.is_contiguous(memory_format=torch.channels_last if cl and Cout > 1 and Ho * Wo > 1 else torch.contiguous_format)
+    ref = (F.conv2d(x.double(), w.double(), b.double(), stride=stride) + z.double()).relu()
+    lib32 = (F.conv2d(x, w, b, stride=stride) + z).relu()
+    scale = float(ref.abs().max())
+    err = float((got.double() - ref).abs().max()) / scale
+    err_lib = float((lib32.double() - ref).abs().max()) / scale
+    print(f'1x1 [{NB},{Cin}->{Cout},{H}x{W}] s{stride} cl={cl}: tcgen05 3xTF32 err {err:.2e}, cuDNN fp32 err {err_lib:.2e}')
+    assert err < 4 * err_lib + 2e-6 and err < 6e-5, (err, err_lib)
+
+
+@pytest.mark.parametrize('NB,Cin,Cout,H,W', [(1, 64, 64, 120, 216), (1, 256, 256, 30, 54), (2, 128, 128, 17, 23)])
+def test_conv3x3_tc_channels_last_in_and_out(NB, Cin, Cout, H, W):
+    """The trunks run channels-last: same kernel, strided addressing, residual in the other layout."""
+    import cutie_b200.kernels as K_
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device='cuda').manual_seed(7)
+    x = torch.randn(NB, Cin, H, W, device='cuda', generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, device='cuda', generator=g) * (2.0 / (9 * Cin)) ** 0.5
+    b = torch.randn(Cout, device='cuda', generator=g)
+    z = torch.randn(NB, Cout, H, W, device='cuda', generator=g).contiguous(memory_format=torch.channels_last)
+    img = K_.conv_weight_image(w)
+    dense = K_.conv_tc(x, img, b, Cout, residual=z, relu_in=True, relu_out=True)
+    last = K_.conv_tc(x.contiguous(memory_format=torch.channels_last), img, b, Cout, residual=z.contiguous(), relu_in=True,
+                      relu_out=True)
+    assert dense.is_contiguous() and last.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(dense, last.contiguous())            # the same arithmetic whatever the memory format
+    ref = (F.conv2d(x.double().relu(), w.double(), b.double(), padding=1) + z.double()).relu()
+    assert float((dense.double() - ref).abs().max()) < 1e-5 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize('NB,Cin,Cout,H,W,k', [(1, 1024, 256, 30, 54, 1), (1, 256, 1024, 30, 54, 1), (1, 64, 64, 120, 216, 3),
+                                               (1, 256, 256, 30, 54, 3), (1, 128, 512, 60, 108, 1)])
+def test_trunk_layers_time_beside_cudnn_channels_last(NB, Cin, Cout, H, W, k):
+    """Reported, not asserted: the ResNet bottleneck layers, channels-last on both sides."""
+    import cutie_b200.kernels as K_
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cudnn.benchmark = True
+    x = torch.randn(NB, Cin, H, W, device='cuda').contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(Cout, Cin, k, k, device='cuda') * 0.02).contiguous(memory_format=torch.channels_last)
+    b = torch.randn(Cout, device='cuda')
+    img = K_.conv_weight_image(w)
+
+    def timed(fn, n=30):
+        for _ in range(5):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n * 1e3
+    t_tc = timed(lambda: K_.conv_tc(x, img, b, Cout, ksize=k, relu_out=True))
+    t_lib = timed(lambda: F.conv2d(x, w, b, padding=k // 2).relu_())
+    print(f'trunk {k}x{k} [{NB},{Cin}->{Cout},{H}x{W}] channels-last: tcgen05 3xTF32 {t_tc:.1f} us, cuDNN fp32 {t_lib:.1f} us')
