@@ -62,6 +62,7 @@ constexpr int CV1_ROWS = 128;                     // 1x1
 struct ConvTail {
   unsigned long long a_full[CV_A_STAGES], a_empty[CV_A_STAGES], x_full[4], x_empty[4], acc_full;
   uint32_t tmem_base;
+  int last;
 };
 constexpr int CV_X_BYTES3 = 2 * 2 * CV3_ROWS * 128;   // 3x3: 2 stages x (hi | lo) x 248 rows = 126976
 constexpr int CV_X_BYTES1 = 4 * 2 * CV1_ROWS * 128;   // 1x1: 4 stages x (hi | lo) x 128 rows = 131072
@@ -82,6 +83,9 @@ struct ConvTcParams {
   int TH, TW, tiles_x;         // 3x3: spatial tile and tiles per image row
   int N;                       // MMA N (multiple of 16, <= 128)
   int relu_in, relu_out, x_vec;
+  int split;                   // K (input-chunk) splits per output tile; > 1: partial tiles meet in `ws`
+  float* ws;                   // [tiles of the grid][split][N][128] partial sums (position-major: coalesced both ways)
+  int* counters;               // [tiles of the grid], zero on entry and on exit
 };
 
 template <int KS>
@@ -91,22 +95,25 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcPara
   constexpr int XSTAGE = 2 * XPLANE;
   constexpr int XST = KS == 3 ? 2 : 4;                       // activation stages
   constexpr int TAPS = KS * KS;
-  constexpr int GROUPS = KS == 3 ? 1 : 2;                    // producer groups taking the chunks in turn
-  constexpr int PER_GROUP = CV_PROD / GROUPS;
+  constexpr int HALVES = KS == 3 ? 1 : 2;                    // producer threads per tile row (1x1: 16 channels each)
+  constexpr int CPT = CV_KC / HALVES;                        // channels per producer thread and chunk
+  constexpr int DEPTH = KS == 3 ? 1 : 2;                     // chunks of global loads in flight per producer thread
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* Xs = smem;
   unsigned char* As = smem + XST * XSTAGE;
   ConvTail& T = *reinterpret_cast<ConvTail*>(smem + XST * XSTAGE + CV_A_STAGES * CV_A_BYTES);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tile = blockIdx.x, cot = blockIdx.y, nb = blockIdx.z;
+  const int tile = blockIdx.x / p.split, ksplit = blockIdx.x % p.split, cot = blockIdx.y, nb = blockIdx.z;
   const int TWp = p.TW + 2;
   const int ty0 = KS == 3 ? (tile / p.tiles_x) * p.TH : 0, tx0 = KS == 3 ? (tile % p.tiles_x) * p.TW : 0;
   const long long pix0 = (long long)tile * p.N;              // 1x1: first flattened output pixel of the tile
-  const int chunks = p.Cin / CV_KC;
+  const int all_chunks = p.Cin / CV_KC;
+  const int c_begin = (int)((long long)all_chunks * ksplit / p.split);       // this CTA's share of the input chunks
+  const int chunks = (int)((long long)all_chunks * (ksplit + 1) / p.split) - c_begin;
   const long long HW = (long long)p.H * p.W;
   if (tid == 0) {
     for (int s = 0; s < CV_A_STAGES; ++s) { mbar_init(smem_u32(&T.a_full[s]), 1); mbar_init(smem_u32(&T.a_empty[s]), 1); }
-    for (int s = 0; s < XST; ++s) { mbar_init(smem_u32(&T.x_full[s]), PER_GROUP); mbar_init(smem_u32(&T.x_empty[s]), 1); }
+    for (int s = 0; s < XST; ++s) { mbar_init(smem_u32(&T.x_full[s]), CV_PROD); mbar_init(smem_u32(&T.x_empty[s]), 1); }
     mbar_init(smem_u32(&T.acc_full), 1);
     mbar_init_fence();
   }
@@ -117,9 +124,9 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcPara
   const uint32_t tmem = T.tmem_base;
 
   if (warp >= 4 && warp < 12) {
-    // ================================== activation producers: thread == tile row ==================================
-    const int grp = (tid - 128) / PER_GROUP;
-    const int r = (tid - 128) % PER_GROUP;
+    // ============ activation producers: thread == tile row (1x1: half a row, 16 channels) ============
+    const int pt = tid - 128;
+    const int r = pt / HALVES, half = pt % HALVES;
     const bool row_live = r < XROWS;
     bool valid = false;
     long long poff = 0;
@@ -139,46 +146,55 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcPara
         poff = (long long)(oy * p.stride) * p.Wi + ox * p.stride;
       }
     }
-    const float* xb = p.x + (long long)nb * p.xs_n + poff * p.xs_p;
-    float v[CV_KC];
-    auto load = [&](int c) {
-      if (p.x_vec) {                                           // channels-last: 32 consecutive floats
+    const float* xb = p.x + (long long)nb * p.xs_n + poff * p.xs_p + (long long)(c_begin * CV_KC + half * CPT) * p.xs_c;
+    float v[DEPTH][CPT];
+    auto load = [&](int c, float (&dst)[CPT]) {
+      if (p.x_vec) {                                           // channels-last: consecutive floats
 #pragma unroll
-        for (int k4 = 0; k4 < 8; ++k4) {
+        for (int k4 = 0; k4 < CPT / 4; ++k4) {
           const float4 f = valid ? __ldg(reinterpret_cast<const float4*>(xb + c * CV_KC + 4 * k4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          v[4 * k4] = f.x; v[4 * k4 + 1] = f.y; v[4 * k4 + 2] = f.z; v[4 * k4 + 3] = f.w;
+          dst[4 * k4] = f.x; dst[4 * k4 + 1] = f.y; dst[4 * k4 + 2] = f.z; dst[4 * k4 + 3] = f.w;
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < CV_KC; ++i) v[i] = valid ? __ldg(xb + (long long)(c * CV_KC + i) * p.xs_c) : 0.f;
+        for (int i = 0; i < CPT; ++i) dst[i] = valid ? __ldg(xb + (long long)(c * CV_KC + i) * p.xs_c) : 0.f;
       }
     };
-    if (grp < chunks) load(grp);
-    for (int c = grp; c < chunks; c += GROUPS) {
-      const int s = c % XST;
-      mbar_wait(smem_u32(&T.x_empty[s]), ((c / XST) & 1) ^ 1);
-      if (row_live) {
-        unsigned char* hi = Xs + s * XSTAGE + r * 128;
-        unsigned char* lo = hi + XPLANE;
 #pragma unroll
-        for (int k4 = 0; k4 < 8; ++k4) {
-          float4 f = make_float4(v[4 * k4], v[4 * k4 + 1], v[4 * k4 + 2], v[4 * k4 + 3]);
-          if (p.relu_in) f = make_float4(fmaxf(f.x, 0.f), fmaxf(f.y, 0.f), fmaxf(f.z, 0.f), fmaxf(f.w, 0.f));
-          const float4 h = make_float4(to_tf32(f.x), to_tf32(f.y), to_tf32(f.z), to_tf32(f.w));
-          const float4 l = make_float4(to_tf32(f.x - h.x), to_tf32(f.y - h.y), to_tf32(f.z - h.z), to_tf32(f.w - h.w));
-          const int off = (k4 ^ (r & 7)) << 4;
-          *reinterpret_cast<float4*>(hi + off) = h;
-          *reinterpret_cast<float4*>(lo + off) = l;
+    for (int d = 0; d < DEPTH; ++d)
+      if (d < chunks) load(d, v[d]);
+#pragma unroll 1
+    for (int c0 = 0; c0 < chunks; c0 += DEPTH) {
+#pragma unroll
+      for (int d = 0; d < DEPTH; ++d) {
+        const int c = c0 + d;
+        if (c < chunks) {
+          const int s = c % XST;
+          mbar_wait(smem_u32(&T.x_empty[s]), ((c / XST) & 1) ^ 1);
+          if (row_live) {
+            unsigned char* hi = Xs + s * XSTAGE + r * 128;
+            unsigned char* lo = hi + XPLANE;
+#pragma unroll
+            for (int k4 = 0; k4 < CPT / 4; ++k4) {
+              float4 f = make_float4(v[d][4 * k4], v[d][4 * k4 + 1], v[d][4 * k4 + 2], v[d][4 * k4 + 3]);
+              if (p.relu_in) f = make_float4(fmaxf(f.x, 0.f), fmaxf(f.y, 0.f), fmaxf(f.z, 0.f), fmaxf(f.w, 0.f));
+              const float4 h = make_float4(to_tf32(f.x), to_tf32(f.y), to_tf32(f.z), to_tf32(f.w));
+              const float4 l = make_float4(to_tf32(f.x - h.x), to_tf32(f.y - h.y), to_tf32(f.z - h.z), to_tf32(f.w - h.w));
+              const int off = ((half * (CPT / 4) + k4) ^ (r & 7)) << 4;
+              *reinterpret_cast<float4*>(hi + off) = h;
+              *reinterpret_cast<float4*>(lo + off) = l;
+            }
+          }
+          fence_proxy_async();
+          mbar_arrive(smem_u32(&T.x_full[s]));
+          if (c + DEPTH < chunks) load(c + DEPTH, v[d]);
         }
       }
-      fence_proxy_async();
-      mbar_arrive(smem_u32(&T.x_full[s]));
-      if (c + GROUPS < chunks) load(c + GROUPS);
     }
   } else if (warp == 13) {
     // ================================== weight loader ==================================
     if (lane == 0) {
-      const unsigned char* wsrc = p.wimg + (size_t)cot * chunks * TAPS * CV_A_BYTES;
+      const unsigned char* wsrc = p.wimg + ((size_t)cot * all_chunks + c_begin) * TAPS * CV_A_BYTES;
       const int steps = chunks * TAPS;
       for (int i = 0; i < steps; ++i) {
         const int s = i % CV_A_STAGES;
@@ -231,38 +247,78 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcPara
     mbar_wait(smem_u32(&T.acc_full), 0);
     tc_fence_after();
     const int nacc = chunks < 3 ? chunks : 3;               // hi.hi accumulators in use
-    int ty = 0, lx = 0;                                     // 3x3: position j = ty * TWp + lx
-    for (int g = 0; g < p.N; g += 32) {
-      uint32_t o[32], q[32];
-      tmem_ld32(lane_base + g, o);                          // (columns >= N of the last group are never stored)
-      for (int a = 1; a < nacc; ++a) {
-        tmem_ld32(lane_base + a * 128 + g, q);
+    const long long tile_id = ((long long)nb * gridDim.y + cot) * (gridDim.x / p.split) + tile;
+    float* wsp = p.split > 1 ? p.ws + (tile_id * p.split) * (long long)(p.N * CV_M) : nullptr;
+    bool finish = true;                                      // this CTA applies the epilogue and stores
+    if (p.split > 1) {
+      // partial tile -> workspace [split][position][channel] (lanes == consecutive channels: coalesced)
+      float* mine = wsp + (long long)ksplit * (p.N * CV_M);
+      for (int g = 0; g < p.N; g += 32) {
+        uint32_t o[32], q[32];
+        tmem_ld32(lane_base + g, o);
+        for (int a = 1; a < nacc; ++a) {
+          tmem_ld32(lane_base + a * 128 + g, q);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) + __uint_as_float(q[j]));
+          for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) + __uint_as_float(q[j]));
+        }
+        tmem_ld32(lane_base + 384 + g, q);
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (g + j < p.N) mine[(g + j) * CV_M + tid] = __uint_as_float(o[j]) + __uint_as_float(q[j]);
       }
-      tmem_ld32(lane_base + 384 + g, q);
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps
+      if (tid == 0) T.last = atomicAdd(p.counters + tile_id, 1) == p.split - 1 ? 1 : 0;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      finish = T.last != 0;                                    // the CTA that arrives last adds the partials IN SPLIT ORDER
+      if (finish) __threadfence();
+    }
+    if (finish) {
+      int ty = 0, lx = 0;                                     // 3x3: position j = ty * TWp + lx
+      for (int g = 0; g < p.N; g += 32) {
+        uint32_t o[32], q[32];
+        if (p.split > 1) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) + __uint_as_float(q[j]));
+          for (int j = 0; j < 32; ++j) o[j] = 0u;
+          for (int k = 0; k < p.split; ++k) {
+            const float* part = wsp + (long long)k * (p.N * CV_M);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        bool ok;
-        long long pix;
-        if (KS == 3) {
-          const int gy = ty0 + ty, gx = tx0 + lx - 1;
-          ok = g + j < p.N && lx >= 1 && lx <= p.TW && ty < p.TH && gy < p.H && gx < p.W;
-          pix = (long long)gy * p.W + gx;
-          if (++lx == TWp) { lx = 0; ++ty; }
+            for (int j = 0; j < 32; ++j)
+              if (g + j < p.N) o[j] = __float_as_uint(__uint_as_float(o[j]) + __ldcg(part + (g + j) * CV_M + tid));
+          }
         } else {
-          pix = pix0 + g + j;
-          ok = g + j < p.N && pix < HW;
+          tmem_ld32(lane_base + g, o);                        // (columns >= N of the last group are never stored)
+          for (int a = 1; a < nacc; ++a) {
+            tmem_ld32(lane_base + a * 128 + g, q);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) + __uint_as_float(q[j]));
+          }
+          tmem_ld32(lane_base + 384 + g, q);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) + __uint_as_float(q[j]));
         }
-        if (co_ok && ok) {
-          float val = __uint_as_float(o[j]) + b;
-          if (zb) val += __ldg(zb + pix * p.zs_p);
-          if (p.relu_out) val = fmaxf(val, 0.f);
-          yb[pix * p.ys_p] = val;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          bool ok;
+          long long pix;
+          if (KS == 3) {
+            const int gy = ty0 + ty, gx = tx0 + lx - 1;
+            ok = g + j < p.N && lx >= 1 && lx <= p.TW && ty < p.TH && gy < p.H && gx < p.W;
+            pix = (long long)gy * p.W + gx;
+            if (++lx == TWp) { lx = 0; ++ty; }
+          } else {
+            pix = pix0 + g + j;
+            ok = g + j < p.N && pix < HW;
+          }
+          if (co_ok && ok) {
+            float val = __uint_as_float(o[j]) + b;
+            if (zb) val += __ldg(zb + pix * p.zs_p);
+            if (p.relu_out) val = fmaxf(val, 0.f);
+            yb[pix * p.ys_p] = val;
+          }
         }
       }
+      if (p.split > 1 && tid == 0) p.counters[tile_id] = 0;   // ready for the next launch
     }
   }
   tc_fence_before();
@@ -342,7 +398,7 @@ static void conv_tile_shape(int H, int W, int* TH, int* TW, int* N) {
 extern "C" int cutie_conv_tc(const float* x, const int64_t* x_strides, const void* weight_image, const float* bias,
                              const float* residual, const int64_t* residual_strides, int64_t NB, int64_t Cin, int64_t Cout,
                              int64_t H_in, int64_t W_in, int ksize, int stride, int relu_in, int relu_out, float* y,
-                             const int64_t* y_strides, void* stream) {
+                             const int64_t* y_strides, int split, float* workspace, int32_t* counters, void* stream) {
   CUTIE_REQUIRE(x && x_strides && weight_image && y && y_strides, "null argument");
   CUTIE_REQUIRE(residual == nullptr || residual_strides != nullptr, "residual needs strides");
   CUTIE_REQUIRE((ksize == 3 && stride == 1) || (ksize == 1 && (stride == 1 || stride == 2)),
@@ -373,18 +429,49 @@ extern "C" int cutie_conv_tc(const float* x, const int64_t* x_strides, const voi
     p.N = hw >= 128 ? 128 : (int)((hw + 15) / 16 * 16);
     tiles = (hw + p.N - 1) / p.N;
   }
-  CUTIE_REQUIRE(tiles <= 0x7fffffff, "too many tiles");
+  CUTIE_REQUIRE(split >= 1 && split <= Cin / CV_KC, "1 <= split <= Cin / 32");
+  CUTIE_REQUIRE(split == 1 || (workspace && counters), "split > 1 needs the workspace and zeroed counters");
+  CUTIE_REQUIRE(tiles * split <= 0x7fffffff, "too many tiles");
+  p.split = split; p.ws = workspace; p.counters = counters;
   static bool attr_done[64] = {};
   if (first_use_on_device(attr_done)) {
     cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SMEM3);
     cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SMEM1);
   }
-  const dim3 grid((unsigned)tiles, (unsigned)((Cout + CV_M - 1) / CV_M), (unsigned)NB);
+  const dim3 grid((unsigned)(tiles * split), (unsigned)((Cout + CV_M - 1) / CV_M), (unsigned)NB);
   if (ksize == 3)
     conv_tc_kernel<3><<<grid, CV_THREADS, CV_SMEM3, (cudaStream_t)stream>>>(p);
   else
     conv_tc_kernel<1><<<grid, CV_THREADS, CV_SMEM1, (cudaStream_t)stream>>>(p);
   CUTIE_CHECK_LAUNCH();
+  return 0;
+}
+
+// launch plan: {tiles per image and channel tile, MMA N, recommended K split}.  The split spreads a layer with few output
+// tiles over the SMs: largest s <= 8 with (CTAs x s) <= SMs and at least 2 input chunks per CTA.
+extern "C" int cutie_conv_plan(int64_t NB, int64_t Cin, int64_t Cout, int64_t H_in, int64_t W_in, int ksize, int stride,
+                               int64_t* out3) {
+  CUTIE_REQUIRE(out3 && (ksize == 1 || ksize == 3) && (stride == 1 || stride == 2) && Cin >= CV_KC && Cin % CV_KC == 0,
+                "bad arguments");
+  const int H = (int)((H_in - 1) / stride + 1), W = (int)((W_in - 1) / stride + 1);
+  long long tiles;
+  int N = 0;
+  if (ksize == 3) {
+    int th = 0, tw = 0;
+    conv_tile_shape(H, W, &th, &tw, &N);
+    CUTIE_REQUIRE(N >= 16, "no tile shape for this geometry");
+    tiles = (long long)((W + tw - 1) / tw) * ((H + th - 1) / th);
+  } else {
+    const long long hw = (long long)H * W;
+    N = hw >= 128 ? 128 : (int)((hw + 15) / 16 * 16);
+    tiles = (hw + N - 1) / N;
+  }
+  const long long ctas = tiles * ((Cout + CV_M - 1) / CV_M) * NB;
+  const int chunks = (int)(Cin / CV_KC);
+  int split = 1;
+  for (int s = 2; s <= 8; ++s)
+    if (ctas * s <= num_sms() && chunks / s >= 2) split = s;
+  out3[0] = tiles; out3[1] = N; out3[2] = split;
   return 0;
 }
 

@@ -136,10 +136,12 @@ class ConvEpilogueFuser:
             ident = (w.data_ptr(), None)
         hit = self._images.get(id(conv))
         if hit is None or hit[0] != ident:
-            hit = (ident, K_.conv_weight_image(w))
+            # the layer's operand image and its own split-K tile counters (zero between launches; one layer never runs
+            # twice at the same time, different layers may -- encoder look-ahead -- so counters are never shared)
+            hit = (ident, K_.conv_weight_image(w), torch.zeros(8192, dtype=torch.int32, device=w.device))
             self._images[id(conv)] = hit
         return K_.conv_tc(x, hit[1], conv.bias, conv.out_channels, ksize=conv.kernel_size[0], stride=conv.stride[0],
-                          residual=z, relu_in=relu_in, relu_out=relu)
+                          residual=z, relu_in=relu_in, relu_out=relu, counters=hit[2])
 
     def _tc_eligible(self, conv: nn.Conv2d, x: torch.Tensor, z) -> bool:
         from cutie_b200 import kernels as K_

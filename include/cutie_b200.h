@@ -183,7 +183,13 @@ int cutie_conv_weight_image(const float* weight, int64_t Cout, int64_t Cin, int 
 int cutie_conv_tc(const float* x, const int64_t* x_strides, const void* weight_image, const float* bias,
                   const float* residual, const int64_t* residual_strides, int64_t NB, int64_t Cin, int64_t Cout,
                   int64_t H_in, int64_t W_in, int ksize, int stride, int relu_in, int relu_out, float* y,
-                  const int64_t* y_strides, void* stream);
+                  const int64_t* y_strides, int split, float* workspace, int32_t* counters, void* stream);
+/* Launch plan of cutie_conv_tc: out3 = {output tiles per image and 128-channel tile, MMA N, recommended split}.
+ * split > 1 spreads a layer with few output tiles over the SMs by input-channel ranges: the partial tiles meet in
+ * `workspace` (NB * ceil(Cout/128) * tiles * split * N * 128 floats) and the CTA that arrives last at a tile adds them in
+ * split order (deterministic) before the epilogue; `counters` (NB * ceil(Cout/128) * tiles int32) must be zero on entry and
+ * are zero again on exit. */
+int cutie_conv_plan(int64_t NB, int64_t Cin, int64_t Cout, int64_t H_in, int64_t W_in, int ksize, int stride, int64_t* out3);
 /* test hook: the spatial tile the launcher picks (out3 = {rows, columns, MMA N}). */
 int cutie_debug_conv_tile_shape(int64_t H, int64_t W, int* out3);
 
