@@ -122,6 +122,42 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcPara
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = T.tmem_base;
+  // Dense-NCHW outputs: thread == channel would store 4 bytes per 128-byte line (8x write amplification in L2).  The
+  // finished tile is staged in shared memory [channel][position] instead (the operand stages are free by then) and written
+  // by the epilogue AND producer warps, a warp per (channel, tile row): 128-byte coalesced stores, residual read likewise.
+  const bool staged = p.ys_p == 1 && (p.z == nullptr || p.zs_p == 1);
+  const int LD = p.N | 1;                                     // odd row pitch: conflict-free both ways
+  auto store_staged_rows = [&](int sw) {                     // sw = 0..11
+    const float* stage = reinterpret_cast<const float*>(smem);
+    const int nseg = CV_M * (KS == 3 ? p.TH : 1);
+    for (int seg = sw; seg < nseg; seg += 12) {
+      const int col = KS == 3 ? seg / p.TH : seg, ty = KS == 3 ? seg - col * p.TH : 0;
+      const int co = cot * CV_M + col;
+      if (co >= p.Cout) continue;
+      long long pbase;
+      int len, sbase;
+      if (KS == 3) {
+        const int gy = ty0 + ty;
+        if (gy >= p.H) continue;
+        pbase = (long long)gy * p.W + tx0;
+        len = p.W - tx0 < p.TW ? p.W - tx0 : p.TW;
+        sbase = col * LD + ty * TWp + 1;
+      } else {
+        pbase = pix0;
+        len = HW - pix0 < p.N ? (int)(HW - pix0) : p.N;
+        sbase = col * LD;
+      }
+      const float b = p.bias ? __ldg(p.bias + co) : 0.f;
+      float* yrow = p.y + (long long)nb * p.ys_n + (long long)co * p.ys_c + pbase;
+      const float* zrow = p.z ? p.z + (long long)nb * p.zs_n + (long long)co * p.zs_c + pbase : nullptr;
+      for (int i = lane; i < len; i += 32) {
+        float val = stage[sbase + i] + b;
+        if (zrow) val += __ldg(zrow + i);
+        if (p.relu_out) val = fmaxf(val, 0.f);
+        yrow[i] = val;
+      }
+    }
+  };
 
   if (warp >= 4 && warp < 12) {
     // ============ activation producers: thread == tile row (1x1: half a row, 16 channels) ============
@@ -190,6 +226,10 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcPara
           if (c + DEPTH < chunks) load(c + DEPTH, v[d]);
         }
       }
+    }
+    if (staged) {
+      asm volatile("bar.sync 2, 384;" ::: "memory");          // the tile is staged (or this CTA is not the one that stores)
+      if (T.last) store_staged_rows(warp);
     }
   } else if (warp == 13) {
     // ================================== weight loader ==================================
@@ -272,6 +312,8 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcPara
       asm volatile("bar.sync 1, 128;" ::: "memory");
       finish = T.last != 0;                                    // the CTA that arrives last adds the partials IN SPLIT ORDER
       if (finish) __threadfence();
+    } else if (tid == 0) {
+      T.last = 1;
     }
     if (finish) {
       int ty = 0, lx = 0;                                     // 3x3: position j = ty * TWp + lx
@@ -297,6 +339,13 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcPara
 #pragma unroll
           for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) + __uint_as_float(q[j]));
         }
+        if (staged) {
+          float* stage = reinterpret_cast<float*>(smem);
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (g + j < p.N) stage[tid * LD + g + j] = __uint_as_float(o[j]);
+          continue;
+        }
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           bool ok;
@@ -319,6 +368,10 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcPara
         }
       }
       if (p.split > 1 && tid == 0) p.counters[tile_id] = 0;   // ready for the next launch
+    }
+    if (staged) {
+      asm volatile("bar.sync 2, 384;" ::: "memory");
+      if (finish) store_staged_rows(warp);
     }
   }
   tc_fence_before();
