@@ -83,6 +83,7 @@ struct ConvTcParams {
   int TH, TW, tiles_x;         // 3x3: spatial tile and tiles per image row
   int N;                       // MMA N (multiple of 16, <= 128)
   int relu_in, relu_out, x_vec;
+  int cl_vec;                  // channels-last Y (and Z) addressable as float4 along channels
   int split;                   // K (input-chunk) splits per output tile; > 1: partial tiles meet in `ws`
   float* ws;                   // [tiles of the grid][split][N][128] partial sums (position-major: coalesced both ways)
   int* counters;               // [tiles of the grid], zero on entry and on exit
@@ -125,10 +126,42 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcPara
   // Dense-NCHW outputs: thread == channel would store 4 bytes per 128-byte line (8x write amplification in L2).  The
   // finished tile is staged in shared memory [channel][position] instead (the operand stages are free by then) and written
   // by the epilogue AND producer warps, a warp per (channel, tile row): 128-byte coalesced stores, residual read likewise.
-  const bool staged = p.ys_p == 1 && (p.z == nullptr || p.zs_p == 1);
+  // Channels-last outputs are coalesced either way, but four epilogue warps with 32 accesses in flight each cannot keep
+  // HBM busy on the wide, shallow layers (a bottleneck's closing 1x1 + residual ran at 0.5 TB/s): the same staging
+  // ([position][channel]) lets all twelve warps move 16 bytes per lane, residual included.
+  const bool staged_nchw = p.ys_p == 1 && (p.z == nullptr || p.zs_p == 1);
+  const bool staged = staged_nchw || p.cl_vec;
   const int LD = p.N | 1;                                     // odd row pitch: conflict-free both ways
   auto store_staged_rows = [&](int sw) {                     // sw = 0..11
     const float* stage = reinterpret_cast<const float*>(smem);
+    if (!staged_nchw) {                                      // channels-last: a warp per position, 4 channels per lane
+      const int co4 = cot * CV_M + 4 * lane;
+      if (co4 >= p.Cout) return;
+      const float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + co4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = sw; j < p.N; j += 12) {
+        long long pix;
+        bool ok;
+        if (KS == 3) {
+          const int ty = j / TWp, lx = j - ty * TWp;
+          const int gy = ty0 + ty, gx = tx0 + lx - 1;
+          ok = lx >= 1 && lx <= p.TW && ty < p.TH && gy < p.H && gx < p.W;
+          pix = (long long)gy * p.W + gx;
+        } else {
+          pix = pix0 + j;
+          ok = pix < HW;
+        }
+        if (!ok) continue;
+        float4 v = *reinterpret_cast<const float4*>(stage + j * CV_M + 4 * lane);
+        v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+        if (p.z) {
+          const float4 z4 = __ldg(reinterpret_cast<const float4*>(p.z + (long long)nb * p.zs_n + pix * p.zs_p + co4));
+          v.x += z4.x; v.y += z4.y; v.z += z4.z; v.w += z4.w;
+        }
+        if (p.relu_out) v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+        *reinterpret_cast<float4*>(p.y + (long long)nb * p.ys_n + pix * p.ys_p + co4) = v;
+      }
+      return;
+    }
     const int nseg = CV_M * (KS == 3 ? p.TH : 1);
     for (int seg = sw; seg < nseg; seg += 12) {
       const int col = KS == 3 ? seg / p.TH : seg, ty = KS == 3 ? seg - col * p.TH : 0;
@@ -341,9 +374,15 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcPara
         }
         if (staged) {
           float* stage = reinterpret_cast<float*>(smem);
+          if (staged_nchw) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (g + j < p.N) stage[tid * LD + g + j] = __uint_as_float(o[j]);
+            for (int j = 0; j < 32; ++j)
+              if (g + j < p.N) stage[tid * LD + g + j] = __uint_as_float(o[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (g + j < p.N) stage[(g + j) * CV_M + tid] = __uint_as_float(o[j]);
+          }
           continue;
         }
 #pragma unroll
@@ -470,6 +509,11 @@ extern "C" int cutie_conv_tc(const float* x, const int64_t* x_strides, const voi
   p.relu_in = relu_in; p.relu_out = relu_out;
   // channels-last input: a producer thread reads its pixel's 32 channels as 8 x 16 bytes
   p.x_vec = (p.xs_c == 1 && p.xs_p % 4 == 0 && p.xs_n % 4 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0) ? 1 : 0;
+  auto vec4 = [](const void* ptr, long long sn, long long sc, long long sp) {
+    return sc == 1 && sp % 4 == 0 && sn % 4 == 0 && reinterpret_cast<uintptr_t>(ptr) % 16 == 0;
+  };
+  p.cl_vec = (Cout % 4 == 0 && vec4(y, p.ys_n, p.ys_c, p.ys_p) && (bias == nullptr || reinterpret_cast<uintptr_t>(bias) % 16 == 0) &&
+              (residual == nullptr || vec4(residual, p.zs_n, p.zs_c, p.zs_p))) ? 1 : 0;
   long long tiles;
   p.TH = 0; p.TW = 0; p.N = 0; p.tiles_x = 1;
   if (ksize == 3) {
