@@ -486,6 +486,56 @@ def northstar_read_bench(dev, iters=50):
             'roofline_time_us': bytes_alg / (peaks['hbm_gbs'] * 1e9) * 1e6}
 
 
+def conv_roofline_bench(dev, iters=40):
+    """The convolution kernel that now carries most of the step (cutie_conv_tc, tcgen05 3xTF32 implicit GEMM) on the layers
+    it runs at cfg 2, timed alone with CUDA events (L2-warm, back to back): fp32-equivalent TFLOP/s = 2 NB H W Cout Cin k^2 /
+    time; the tensor pipe executes 3 TF32 MMAs per product, so the tensor-bound ceiling of the fp32-equivalent figure is the
+    measured dense bf16 throughput / 2 (TF32 rate) / 3."""
+    import cutie_b200.kernels as K_
+    peaks = {'bf16_tflops': 1650.0}
+    pk = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    ceiling = peaks['bf16_tflops'] / 2 / 3
+    layers = [('PixelFFN / fuser 3x3 256->256 @30x54 x3 objects', 3, 256, 256, 30, 54, 3, False),
+              ('sensory update 3x3 512->768 @30x54 x3', 3, 512, 768, 30, 54, 3, False),
+              ('decoder 3x3 128->128 @120x216 x3', 3, 128, 128, 120, 216, 3, False),
+              ('ResNet-50 layer3 3x3 256->256 @30x54 (channels-last, split-K)', 1, 256, 256, 30, 54, 3, True),
+              ('ResNet-50 layer3 1x1 1024->256 @30x54 (channels-last, split-K)', 1, 1024, 256, 30, 54, 1, True),
+              ('ResNet-50 layer1 1x1 64->256 @120x216 + residual (channels-last)', 1, 64, 256, 120, 216, 1, True)]
+    out = []
+    g = torch.Generator().manual_seed(5)
+    with torch.inference_mode():
+        for name, NB, Cin, Cout, H, W, k, cl in layers:
+            x = torch.randn(NB, Cin, H, W, generator=g).to(dev)
+            z = torch.randn(NB, Cout, H, W, generator=g).to(dev)
+            if cl:
+                x, z = x.contiguous(memory_format=torch.channels_last), z.contiguous(memory_format=torch.channels_last)
+            w = (torch.randn(Cout, Cin, k, k, generator=g) * 0.02).to(dev)
+            b = torch.randn(Cout, generator=g).to(dev)
+            img = K_.conv_weight_image(w)
+            cnt = torch.zeros(8192, dtype=torch.int32, device=dev)
+            for _ in range(4):
+                K_.conv_tc(x, img, b, Cout, ksize=k, residual=z, relu_out=True, counters=cnt)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                K_.conv_tc(x, img, b, Cout, ksize=k, residual=z, relu_out=True, counters=cnt)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            us = e0.elapsed_time(e1) / iters * 1e3
+            flops = 2.0 * NB * H * W * Cout * Cin * k * k
+            nbytes = 4.0 * (x.numel() + 2 * z.numel() + 2 * w.numel())
+            out.append({'layer': name, 'us': us, 'fp32_equivalent_tflops': flops / us / 1e6, 'frac_of_3xtf32_ceiling': flops / us / 1e6 / ceiling,
+                        'hbm_view_gbs': nbytes / us / 1e3})
+    return {'kernel': 'cutie_conv_tc (csrc/conv_tc.cu)', 'bound': 'tensor', 'unit': 'TFLOP/s (fp32-equivalent)',
+            'peak': ceiling, 'peak_source': 'MEASURED_PEAKS.json bf16_tflops (burst: kernel timed alone) / 2 (TF32) / 3 (three MMAs per product)',
+            'achieved': max(o['fp32_equivalent_tflops'] for o in out), 'frac': max(o['frac_of_3xtf32_ceiling'] for o in out),
+            'layers': out, 'note': 'host-launched back to back: layers shorter than ~25 us are launch-bound here (inside the '
+                                   'frame they replay from CUDA graphs)'}
+
+
 # ---------------------------------------------------------------------------------------------------
 def run_cpu_port(args, wl, max_seconds, steps, warmup):
     """The reference's algorithm on the host cores as restated by oracle/cpu_core.py (pinned to the reference by
@@ -689,6 +739,13 @@ def main():
     if world > 1:
         torch.distributed.init_process_group('nccl', device_id=dev)
     res = run_ours(args, wl, rank, world, dev)
+    conv_roof = None
+    if rank == 0 and not args.no_northstar:
+        try:
+            conv_roof = conv_roofline_bench(dev)
+            log(f'[conv] {conv_roof}')
+        except Exception as e:                                 # noqa: BLE001 -- reported, never hidden
+            conv_roof = {'error': f'{type(e).__name__}: {e}'[:300]}
     northstar = None
     if rank == 0 and not args.no_northstar:
         try:
@@ -786,7 +843,7 @@ def main():
             'build': {'cuda_graphs': not args.no_graphs, 'optimize_for_inference': not args.no_optimize,
                       'cudnn_benchmark': not args.no_cudnn_benchmark, 'cudnn_allow_tf32': False, 'matmul_allow_tf32': False,
                       'conv_epilogues': res['epilogues'], 'glue_dispatch': res['glue']},
-            'roofline_northstar': northstar, 'sharded_read': sharded}
+            'roofline_northstar': northstar, 'roofline_conv': conv_roof, 'sharded_read': sharded}
     emit(line)
 
 
