@@ -1,4 +1,4 @@
-// 3x3 (stride 1, zero-pad 1) and 1x1 (stride 1 or 2) convolutions as tcgen05 implicit GEMMs with fp32-class accuracy
+// 3x3 (zero-pad 1) and 1x1 convolutions, stride 1 or 2, as tcgen05 implicit GEMMs with fp32-class accuracy
 // (3xTF32), sm_100a.
 //
 // the PixelFFN / CAResBlock (transformer_layers.py:121-136, channel_attn.py:7-39), PixelFeatureFuser
@@ -25,6 +25,9 @@
 //     descriptor's base-offset field left 0; tests/cuda/umma_probe.cu checks this on the device:
 //     profiles/r02_umma_probe.txt.)  The two padding columns of every local row are computed and
 //     discarded (TW / (TW + 2) efficiency); image borders are zero rows.
+//     3x3 stride 2: the same trick over four PARITY PLANES of the input window (P[a][b](u, v) = in(2u + a, 2v + b)) stored
+//     one after the other: tap (dy, dx) reads plane (dy != 1, dx != 1) at (u, v) = (oy - [dy == 0], ox - [dx == 0]) -- again
+//     a constant row shift per tap.  The tile holds 4x the input per output, so N is ~32-48 positions per CTA.
 //     1x1: a tile is 128 consecutive output pixels of the flattened image (stride 2: of the sub-sampled one), no halo; four
 //     activation stages of 32 KB instead of two of 62 KB, filled by two producer groups that take the chunks in turn.
 //   * Layout-agnostic: X, Y and Z are addressed through (image, channel, pixel) strides -- dense NCHW (what the transformer
@@ -81,6 +84,9 @@ struct ConvTcParams {
   int Cin, Cout, H, W;         // OUTPUT height / width
   int Hi, Wi, stride;          // input height / width; stride (1x1 only: 1 or 2)
   int TH, TW, tiles_x;         // 3x3: spatial tile and tiles per image row
+  int pitch, xoff;             // 3x3: positions per local row (TW + 2 | TW + 1 at stride 2); column of output x = 0 (1 | 0)
+  int plane_rows;              // 3x3 stride 2: rows of one parity plane of the activation tile
+  int shift[9];                // 3x3: activation-tile row each tap's operand window starts at
   int N;                       // MMA N (multiple of 16, <= 128)
   int relu_in, relu_out, x_vec;
   int cl_vec;                  // channels-last Y (and Z) addressable as float4 along channels
@@ -105,7 +111,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcPara
   ConvTail& T = *reinterpret_cast<ConvTail*>(smem + XST * XSTAGE + CV_A_STAGES * CV_A_BYTES);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile = blockIdx.x / p.split, ksplit = blockIdx.x % p.split, cot = blockIdx.y, nb = blockIdx.z;
-  const int TWp = p.TW + 2;
+  const int TWp = p.pitch;                                   // positions per local row of the 3x3 tile
   const int ty0 = KS == 3 ? (tile / p.tiles_x) * p.TH : 0, tx0 = KS == 3 ? (tile % p.tiles_x) * p.TW : 0;
   const long long pix0 = (long long)tile * p.N;              // 1x1: first flattened output pixel of the tile
   const int all_chunks = p.Cin / CV_KC;
@@ -143,8 +149,8 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcPara
         bool ok;
         if (KS == 3) {
           const int ty = j / TWp, lx = j - ty * TWp;
-          const int gy = ty0 + ty, gx = tx0 + lx - 1;
-          ok = lx >= 1 && lx <= p.TW && ty < p.TH && gy < p.H && gx < p.W;
+          const int gy = ty0 + ty, gx = tx0 + lx - p.xoff;
+          ok = lx >= p.xoff && lx < p.TW + p.xoff && ty < p.TH && gy < p.H && gx < p.W;
           pix = (long long)gy * p.W + gx;
         } else {
           pix = pix0 + j;
@@ -174,7 +180,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcPara
         if (gy >= p.H) continue;
         pbase = (long long)gy * p.W + tx0;
         len = p.W - tx0 < p.TW ? p.W - tx0 : p.TW;
-        sbase = col * LD + ty * TWp + 1;
+        sbase = col * LD + ty * TWp + p.xoff;
       } else {
         pbase = pix0;
         len = HW - pix0 < p.N ? (int)(HW - pix0) : p.N;
@@ -200,11 +206,21 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcPara
     bool valid = false;
     long long poff = 0;
     if (KS == 3) {
-      const int rows_used = p.N + 2 * TWp + 2;
-      if (r >= 1 && r < rows_used) {
-        const int q = r - 1, ly = q / TWp, lx = q - ly * TWp;
-        const int gy = ty0 + ly - 1, gx = tx0 + lx - 1;
-        valid = ly < p.TH + 2 && gy >= 0 && gy < p.Hi && gx >= 0 && gx < p.Wi;
+      if (p.stride == 1) {
+        const int rows_used = p.N + 2 * TWp + 2;
+        if (r >= 1 && r < rows_used) {
+          const int q = r - 1, ly = q / TWp, lx = q - ly * TWp;
+          const int gy = ty0 + ly - 1, gx = tx0 + lx - 1;
+          valid = ly < p.TH + 2 && gy >= 0 && gy < p.Hi && gx >= 0 && gx < p.Wi;
+          poff = (long long)gy * p.Wi + gx;
+        }
+      } else {
+        // stride 2: four parity planes P[a][b](u, v) = in(2u + a, 2v + b), each a local (TH + 1) x (TW + 1) grid whose first
+        // row / column is u = ty0 - 1 / v = tx0 - 1; tap (dy, dx) reads plane (dy != 1, dx != 1) shifted by (dy == 0, dx == 0)
+        const int pl = r / p.plane_rows, q = r - pl * p.plane_rows;
+        const int lu = q / TWp, lv = q - lu * TWp;
+        const int gy = 2 * (ty0 - 1 + lu) + (pl >> 1), gx = 2 * (tx0 - 1 + lv) + (pl & 1);
+        valid = pl < 4 && lu <= p.TH && gy >= 0 && gy < p.Hi && gx >= 0 && gx < p.Wi;
         poff = (long long)gy * p.Wi + gx;
       }
     } else {
@@ -293,7 +309,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcPara
           mbar_wait(smem_u32(&T.a_full[s]), (i / CV_A_STAGES) & 1);
           tc_fence_after();
           const uint32_t a_hi = smem_u32(As + s * CV_A_BYTES), a_lo = a_hi + CV_M * 128;
-          const uint32_t shift = KS == 3 ? (uint32_t)((t / 3) * TWp + (t % 3)) * 128u : 0u;
+          const uint32_t shift = KS == 3 ? (uint32_t)p.shift[t] * 128u : 0u;
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const uint64_t da_hi = desc_sw128_kmajor(a_hi + ks * 32), da_lo = desc_sw128_kmajor(a_lo + ks * 32);
@@ -390,8 +406,8 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcPara
           bool ok;
           long long pix;
           if (KS == 3) {
-            const int gy = ty0 + ty, gx = tx0 + lx - 1;
-            ok = g + j < p.N && lx >= 1 && lx <= p.TW && ty < p.TH && gy < p.H && gx < p.W;
+            const int gy = ty0 + ty, gx = tx0 + lx - p.xoff;
+            ok = g + j < p.N && lx >= p.xoff && lx < p.TW + p.xoff && ty < p.TH && gy < p.H && gx < p.W;
             pix = (long long)gy * p.W + gx;
             if (++lx == TWp) { lx = 0; ++ty; }
           } else {
@@ -471,13 +487,16 @@ extern "C" int cutie_conv_weight_image(const float* weight, int64_t Cout, int64_
 
 // 3x3 spatial tile: TW | tile width (full rows when they fit), TH rows, N = round16(TH * (TW + 2)) <= 128 and
 // N + 2 (TW + 2) + 2 <= 248 rows; maximise useful pixels per MMA column over the whole image (edge tiles included)
-static void conv_tile_shape(int H, int W, int* TH, int* TW, int* N) {
+// (stride 2: four parity planes of (TH + 1) x (TW + 1) rows each, N = round16(TH * (TW + 1)))
+static int conv_plane_rows(int th, int tw, int n) { return (th + 1) * (tw + 1) + (n - th * (tw + 1)) + 1; }
+static void conv_tile_shape(int H, int W, int stride, int* TH, int* TW, int* N) {
   double best = -1;
+  const int pad = stride == 1 ? 2 : 1;
   for (int parts = 1; parts <= W; ++parts) {
     const int tw = (W + parts - 1) / parts;
-    for (int th = 1; th <= H && th * (tw + 2) <= 128; ++th) {
-      const int n = (th * (tw + 2) + 15) / 16 * 16;
-      if (n + 2 * (tw + 2) + 2 > CV3_ROWS) continue;
+    for (int th = 1; th <= H && th * (tw + pad) <= 128; ++th) {
+      const int n = (th * (tw + pad) + 15) / 16 * 16;
+      if (stride == 1 ? n + 2 * (tw + 2) + 2 > CV3_ROWS : 4 * conv_plane_rows(th, tw, n) > CV3_ROWS) continue;
       const long long tiles = (long long)((H + th - 1) / th) * ((W + tw - 1) / tw);
       const double eff = (double)H * W / ((double)tiles * n);
       // the most useful pixels per MMA column; among equals the larger N (fewer CTAs re-reading the weights)
@@ -493,8 +512,7 @@ extern "C" int cutie_conv_tc(const float* x, const int64_t* x_strides, const voi
                              const int64_t* y_strides, int split, float* workspace, int32_t* counters, void* stream) {
   CUTIE_REQUIRE(x && x_strides && weight_image && y && y_strides, "null argument");
   CUTIE_REQUIRE(residual == nullptr || residual_strides != nullptr, "residual needs strides");
-  CUTIE_REQUIRE((ksize == 3 && stride == 1) || (ksize == 1 && (stride == 1 || stride == 2)),
-                "3x3 stride 1, or 1x1 stride 1 / 2");
+  CUTIE_REQUIRE((ksize == 3 || ksize == 1) && (stride == 1 || stride == 2), "3x3 (zero pad 1) or 1x1, stride 1 or 2");
   CUTIE_REQUIRE(Cout >= 1 && Cin >= CV_KC && Cin % CV_KC == 0, "input channels must be a multiple of 32");
   CUTIE_REQUIRE(NB >= 1 && NB <= 65535 && H_in >= 1 && W_in >= 1 && H_in * W_in < (1ll << 30), "bad geometry");
   ConvTcParams p;
@@ -515,12 +533,24 @@ extern "C" int cutie_conv_tc(const float* x, const int64_t* x_strides, const voi
   p.cl_vec = (Cout % 4 == 0 && vec4(y, p.ys_n, p.ys_c, p.ys_p) && (bias == nullptr || reinterpret_cast<uintptr_t>(bias) % 16 == 0) &&
               (residual == nullptr || vec4(residual, p.zs_n, p.zs_c, p.zs_p))) ? 1 : 0;
   long long tiles;
-  p.TH = 0; p.TW = 0; p.N = 0; p.tiles_x = 1;
+  p.TH = 0; p.TW = 0; p.N = 0; p.tiles_x = 1; p.pitch = 2; p.xoff = 0; p.plane_rows = 0;
+  for (int t = 0; t < 9; ++t) p.shift[t] = 0;
   if (ksize == 3) {
-    conv_tile_shape(p.H, p.W, &p.TH, &p.TW, &p.N);
+    conv_tile_shape(p.H, p.W, stride, &p.TH, &p.TW, &p.N);
     CUTIE_REQUIRE(p.N >= 16, "no tile shape for this geometry");
     p.tiles_x = (p.W + p.TW - 1) / p.TW;
     tiles = (long long)p.tiles_x * ((p.H + p.TH - 1) / p.TH);
+    if (stride == 1) {
+      p.pitch = p.TW + 2; p.xoff = 1; p.plane_rows = 0;
+      for (int t = 0; t < 9; ++t) p.shift[t] = (t / 3) * p.pitch + (t % 3);
+    } else {
+      p.pitch = p.TW + 1; p.xoff = 0; p.plane_rows = conv_plane_rows(p.TH, p.TW, p.N);
+      for (int t = 0; t < 9; ++t) {
+        const int dy = t / 3, dx = t % 3;
+        const int plane = (dy != 1 ? 2 : 0) + (dx != 1 ? 1 : 0);
+        p.shift[t] = plane * p.plane_rows + (dy == 0 ? 0 : 1) * p.pitch + (dx == 0 ? 0 : 1);
+      }
+    }
   } else {
     const long long hw = (long long)p.H * p.W;
     p.N = hw >= 128 ? 128 : (int)((hw + 15) / 16 * 16);
@@ -555,7 +585,7 @@ extern "C" int cutie_conv_plan(int64_t NB, int64_t Cin, int64_t Cout, int64_t H_
   int N = 0;
   if (ksize == 3) {
     int th = 0, tw = 0;
-    conv_tile_shape(H, W, &th, &tw, &N);
+    conv_tile_shape(H, W, stride, &th, &tw, &N);
     CUTIE_REQUIRE(N >= 16, "no tile shape for this geometry");
     tiles = (long long)((W + tw - 1) / tw) * ((H + th - 1) / th);
   } else {
@@ -574,7 +604,7 @@ extern "C" int cutie_conv_plan(int64_t NB, int64_t Cin, int64_t Cout, int64_t H_
 
 extern "C" int cutie_debug_conv_tile_shape(int64_t H, int64_t W, int* out3) {
   int th = 0, tw = 0, n = 0;
-  conv_tile_shape((int)H, (int)W, &th, &tw, &n);
+  conv_tile_shape((int)H, (int)W, 1, &th, &tw, &n);
   out3[0] = th; out3[1] = tw; out3[2] = n;
   return 0;
 }

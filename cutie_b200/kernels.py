@@ -437,14 +437,14 @@ def conv3x3_c1(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, relu_i
 
 
 def conv_tc_eligible(weight: torch.Tensor, stride=(1, 1), padding=(1, 1), dilation=(1, 1), groups: int = 1) -> bool:
-    """Geometries cutie_conv_tc implements: 3x3 / stride 1 / zero pad 1 and 1x1 / stride 1 or 2 / no pad, Cin % 32 == 0;
+    """Geometries cutie_conv_tc implements: 3x3 / zero pad 1 and 1x1 / no pad, stride 1 or 2, Cin % 32 == 0;
     output channels go in tiles of 128 (a partial tile costs a full one, so layers with fewer than 64 output channels stay
     with the library)."""
     if weight.dim() != 4 or groups != 1 or tuple(dilation) != (1, 1) or weight.shape[0] < 64 or weight.shape[1] % 32:
         return False
     k = tuple(weight.shape[2:])
     if k == (3, 3):
-        return tuple(stride) == (1, 1) and tuple(padding) == (1, 1)
+        return tuple(stride) in ((1, 1), (2, 2)) and tuple(padding) == (1, 1)
     if k == (1, 1):
         return tuple(stride) in ((1, 1), (2, 2)) and tuple(padding) == (0, 0)
     return False

@@ -165,7 +165,7 @@ int cutie_bias_relu_maxpool(const float* y, const float* bias, float* out, int64
 int cutie_segment_tail(const float* x, float* agg, float* logits, float* prob, int64_t B, int64_t K, int64_t h, int64_t w,
                        void* stream);
 
-/* 3x3 (stride 1, zero-pad 1) and 1x1 (stride 1 or 2) convolutions as tcgen05 implicit GEMMs with 3xTF32 operand splitting
+/* 3x3 (zero-pad 1) and 1x1 convolutions, stride 1 or 2, as tcgen05 implicit GEMMs with 3xTF32 operand splitting
  * (fp32-class accuracy, measured 2-6x closer to float64 than cuDNN's fp32 result; csrc/conv_tc.cu):
  *     y = act(bias + conv(pre(x), W) [+ residual]),  pre = ReLU if relu_in, act = ReLU if relu_out.
  * x [NB, Cin, H_in, W_in], y / residual [NB, Cout, H_out, W_out] fp32, each addressed through three ELEMENT strides
@@ -173,7 +173,7 @@ int cutie_segment_tail(const float* x, float* agg, float* logits, float* prob, i
  * Cin % 32 == 0; output channels are processed in tiles of 128 (a partial last tile costs a full one).
  * Replaces the F.conv2d calls of PixelFFN / CAResBlock (transformer_layers.py:121-136, channel_attn.py:7-39),
  * PixelFeatureFuser (big_modules.py:192-235), KeyProjection (big_modules.py:66-87), MaskDecoder / SensoryUpdater
- * (big_modules.py:238-306, modules.py:46-85) and the stride-1 3x3 and all 1x1 convolutions of the ResNet trunks
+ * (big_modules.py:238-306, modules.py:46-85) and the 3x3 and 1x1 convolutions of the ResNet trunks
  * (utils/resnet.py:77-131) -- SURVEY.md section 8(f).1-3.
  * `weight_image` is the layer's operand image: cutie_conv_weight_image(weight [Cout, Cin, k, k]) once per weight version,
  * cutie_conv_weight_image_bytes(Cout, Cin, k) bytes (tf32 hi | lo planes per (128-channel tile, 32-channel chunk, tap) in

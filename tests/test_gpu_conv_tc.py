@@ -65,7 +65,7 @@ def test_conv3x3_tc_is_fp32_class_accurate(NB, Cin, Cout, H, W, epi):
 def test_conv3x3_tc_rejects_unsupported_geometry():
     import cutie_b200.kernels as K_
     assert not K_.conv_tc_eligible(torch.empty(32, 32, 3, 3)) and not K_.conv_tc_eligible(torch.empty(128, 48, 3, 3))
-    assert K_.conv_tc_eligible(torch.empty(128, 32, 3, 3)) and not K_.conv_tc_eligible(torch.empty(128, 32, 3, 3), stride=(2, 2))
+    assert K_.conv_tc_eligible(torch.empty(128, 32, 3, 3)) and not K_.conv_tc_eligible(torch.empty(128, 32, 3, 3), stride=(3, 3))
     img = K_.conv_weight_image(torch.randn(128, 32, 3, 3, device='cuda'))
     with pytest.raises(K_.KernelError):
         K_.conv_tc(torch.randn(1, 33, 4, 4, device='cuda'), img, None, 128)
@@ -228,3 +228,29 @@ def test_conv_plan_splits_small_grids_only():
     assert p(1, 256, 256, 30, 54, 3) == (15, 112, 4)            # 30 CTAs x 4 = 120 <= 148, 2 chunks each
     assert p(1, 1024, 256, 30, 54, 1) == (13, 128, 5)           # 26 CTAs x 5 = 130
     assert p(1, 64, 256, 120, 216, 1)[2] == 1                   # 406 CTAs
+
+
+@pytest.mark.parametrize('NB,Cin,Cout,H,W', [(1, 128, 128, 120, 216), (1, 256, 256, 60, 108), (3, 64, 128, 120, 216),
+                                             (3, 128, 256, 60, 108), (2, 32, 64, 9, 7), (1, 64, 128, 10, 12), (1, 32, 128, 1, 1)])
+@pytest.mark.parametrize('cl', [False, True])
+def test_conv3x3_stride2_tc(NB, Cin, Cout, H, W, cl):
+    """The trunks' four stride-2 3x3 layers: four parity planes of the input window read through row-shifted descriptors."""
+    import cutie_b200.kernels as K_
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator(device='cuda').manual_seed(H + Cin)
+    x = torch.randn(NB, Cin, H, W, device='cuda', generator=g) * 1.5
+    w = torch.randn(Cout, Cin, 3, 3, device='cuda', generator=g) * (2.0 / (9 * Cin)) ** 0.5
+    b = torch.randn(Cout, device='cuda', generator=g)
+    if cl:
+        x = x.contiguous(memory_format=torch.channels_last)
+    assert K_.conv_tc_eligible(w, stride=(2, 2))
+    img = K_.conv_weight_image(w)
+    got = K_.conv_tc(x, img, b, Cout, ksize=3, stride=2, relu_out=True)
+    ref = F.conv2d(x.double(), w.double(), b.double(), stride=2, padding=1).relu()
+    assert got.shape == ref.shape
+    lib32 = F.conv2d(x, w, b, stride=2, padding=1).relu()
+    scale = float(ref.abs().max())
+    err = float((got.double() - ref).abs().max()) / scale
+    err_lib = float((lib32.double() - ref).abs().max()) / scale
+    print(f'3x3 s2 [{NB},{Cin}->{Cout},{H}x{W}] cl={cl}: tcgen05 3xTF32 err {err:.2e}, cuDNN fp32 err {err_lib:.2e}')
+    assert err < 4 * err_lib + 2e-6 and err < 6e-5, (err, err_lib)
