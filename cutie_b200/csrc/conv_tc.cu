@@ -63,9 +63,9 @@ constexpr int CV3_ROWS = 248;                     // 3x3: activation tile rows p
 constexpr int CV1_ROWS = 128;                     // 1x1
 
 struct ConvTail {
-  unsigned long long a_full[CV_A_STAGES], a_empty[CV_A_STAGES], x_full[4], x_empty[4], acc_full;
+  unsigned long long a_full[CV_A_STAGES], a_empty[CV_A_STAGES], x_full[4], x_empty[4], acc_full[2];
   uint32_t tmem_base;
-  int last;
+  int last[2];
 };
 constexpr int CV_X_BYTES3 = 2 * 2 * CV3_ROWS * 128;   // 3x3: 2 stages x (hi | lo) x 248 rows = 126976
 constexpr int CV_X_BYTES1 = 4 * 2 * CV1_ROWS * 128;   // 1x1: 4 stages x (hi | lo) x 128 rows = 131072
@@ -90,9 +90,20 @@ struct ConvTcParams {
   int N;                       // MMA N (multiple of 16, <= 128)
   int relu_in, relu_out, x_vec;
   int cl_vec;                  // channels-last Y (and Z) addressable as float4 along channels
-  int split;                   // K (input-chunk) splits per output tile; > 1: partial tiles meet in `ws`
-  float* ws;                   // [tiles of the grid][split][N][128] partial sums (position-major: coalesced both ways)
-  int* counters;               // [tiles of the grid], zero on entry and on exit
+  int q;                       // (tile, chunk) units per CTA (<= chunks per tile): CTA i owns units [i q, (i + 1) q)
+  int T, tiles, cots;          // output tiles in all = NB * cots * tiles; spatial tiles per image; 128-channel tiles
+  int maxslots;                // most shares a tile can have
+  float* ws;                   // [T][maxslots][N][128] partial sums (position-major: coalesced both ways)
+  int* counters;               // [T], zero on entry and on exit
+};
+
+struct ConvPart {              // one contiguous share of an output tile's input chunks
+  int tile, cot, nb;           // spatial tile, 128-channel tile, image
+  int ty0, tx0;                // 3x3: first output row / column of the tile
+  long long pix0;              // 1x1: first flattened output pixel
+  int c0, c1;                  // chunk range
+  int slot, nslots;            // this share's index among the tile's contributors; their number
+  long long tile_lin;          // (nb, cot, tile) linearised: workspace / counter index
 };
 
 template <int KS>
@@ -110,18 +121,42 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcPara
   unsigned char* As = smem + XST * XSTAGE;
   ConvTail& T = *reinterpret_cast<ConvTail*>(smem + XST * XSTAGE + CV_A_STAGES * CV_A_BYTES);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tile = blockIdx.x / p.split, ksplit = blockIdx.x % p.split, cot = blockIdx.y, nb = blockIdx.z;
   const int TWp = p.pitch;                                   // positions per local row of the 3x3 tile
-  const int ty0 = KS == 3 ? (tile / p.tiles_x) * p.TH : 0, tx0 = KS == 3 ? (tile % p.tiles_x) * p.TW : 0;
-  const long long pix0 = (long long)tile * p.N;              // 1x1: first flattened output pixel of the tile
-  const int all_chunks = p.Cin / CV_KC;
-  const int c_begin = (int)((long long)all_chunks * ksplit / p.split);       // this CTA's share of the input chunks
-  const int chunks = (int)((long long)all_chunks * (ksplit + 1) / p.split) - c_begin;
+  const int C = p.Cin / CV_KC;                               // input chunks per output tile
   const long long HW = (long long)p.H * p.W;
+  // ---- this CTA's share of the (output tile, input chunk) space: units [u0, u1), at most two tiles (host: q <= C) ----
+  const long long U = (long long)p.T * C;
+  const long long u0 = (long long)blockIdx.x * p.q, u1 = u0 + p.q < U ? u0 + p.q : U;
+  auto make_part = [&](long long ua, long long ub) {
+    ConvPart P;
+    P.tile_lin = ua / C;
+    P.c0 = (int)(ua - P.tile_lin * C);
+    P.c1 = P.c0 + (int)(ub - ua);
+    const long long first = (P.tile_lin * C) / p.q, last = (P.tile_lin * C + C - 1) / p.q;
+    P.slot = (int)(blockIdx.x - first);
+    P.nslots = (int)(last - first + 1);
+    P.tile = (int)(P.tile_lin % p.tiles);
+    const long long rest = P.tile_lin / p.tiles;
+    P.cot = (int)(rest % p.cots);
+    P.nb = (int)(rest / p.cots);
+    P.ty0 = KS == 3 ? (P.tile / p.tiles_x) * p.TH : 0;
+    P.tx0 = KS == 3 ? (P.tile % p.tiles_x) * p.TW : 0;
+    P.pix0 = (long long)P.tile * p.N;
+    return P;
+  };
+  const long long split_at = (u0 / C + 1) * C < u1 ? (u0 / C + 1) * C : u1;   // end of the first tile's share
+  const int nparts = split_at < u1 ? 2 : 1;
+  const ConvPart part0 = make_part(u0, split_at), part1 = make_part(nparts == 2 ? split_at : u0, u1);
+  // a whole tile computed by this CTA alone goes straight from TMEM to the output; shares meet in the workspace
+  const bool direct = nparts == 1 && part0.nslots == 1;
+  const int nhh = direct ? 3 : 1;                             // hi.hi accumulators per part (cross terms follow them)
+
   if (tid == 0) {
     for (int s = 0; s < CV_A_STAGES; ++s) { mbar_init(smem_u32(&T.a_full[s]), 1); mbar_init(smem_u32(&T.a_empty[s]), 1); }
     for (int s = 0; s < XST; ++s) { mbar_init(smem_u32(&T.x_full[s]), CV_PROD); mbar_init(smem_u32(&T.x_empty[s]), 1); }
-    mbar_init(smem_u32(&T.acc_full), 1);
+    mbar_init(smem_u32(&T.acc_full[0]), 1);
+    mbar_init(smem_u32(&T.acc_full[1]), 1);
+    T.last[0] = T.last[1] = 0;
     mbar_init_fence();
   }
   if (warp == 12) tmem_alloc<512>(smem_u32(&T.tmem_base));
@@ -138,10 +173,10 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcPara
   const bool staged_nchw = p.ys_p == 1 && (p.z == nullptr || p.zs_p == 1);
   const bool staged = staged_nchw || p.cl_vec;
   const int LD = p.N | 1;                                     // odd row pitch: conflict-free both ways
-  auto store_staged_rows = [&](int sw) {                     // sw = 0..11
+  auto store_staged_rows = [&](const ConvPart& P, int sw) {  // sw = 0..11
     const float* stage = reinterpret_cast<const float*>(smem);
     if (!staged_nchw) {                                      // channels-last: a warp per position, 4 channels per lane
-      const int co4 = cot * CV_M + 4 * lane;
+      const int co4 = P.cot * CV_M + 4 * lane;
       if (co4 >= p.Cout) return;
       const float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + co4)) : make_float4(0.f, 0.f, 0.f, 0.f);
       for (int j = sw; j < p.N; j += 12) {
@@ -149,46 +184,46 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcPara
         bool ok;
         if (KS == 3) {
           const int ty = j / TWp, lx = j - ty * TWp;
-          const int gy = ty0 + ty, gx = tx0 + lx - p.xoff;
+          const int gy = P.ty0 + ty, gx = P.tx0 + lx - p.xoff;
           ok = lx >= p.xoff && lx < p.TW + p.xoff && ty < p.TH && gy < p.H && gx < p.W;
           pix = (long long)gy * p.W + gx;
         } else {
-          pix = pix0 + j;
+          pix = P.pix0 + j;
           ok = pix < HW;
         }
         if (!ok) continue;
         float4 v = *reinterpret_cast<const float4*>(stage + j * CV_M + 4 * lane);
         v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
         if (p.z) {
-          const float4 z4 = __ldg(reinterpret_cast<const float4*>(p.z + (long long)nb * p.zs_n + pix * p.zs_p + co4));
+          const float4 z4 = __ldg(reinterpret_cast<const float4*>(p.z + (long long)P.nb * p.zs_n + pix * p.zs_p + co4));
           v.x += z4.x; v.y += z4.y; v.z += z4.z; v.w += z4.w;
         }
         if (p.relu_out) v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
-        *reinterpret_cast<float4*>(p.y + (long long)nb * p.ys_n + pix * p.ys_p + co4) = v;
+        *reinterpret_cast<float4*>(p.y + (long long)P.nb * p.ys_n + pix * p.ys_p + co4) = v;
       }
       return;
     }
     const int nseg = CV_M * (KS == 3 ? p.TH : 1);
     for (int seg = sw; seg < nseg; seg += 12) {
       const int col = KS == 3 ? seg / p.TH : seg, ty = KS == 3 ? seg - col * p.TH : 0;
-      const int co = cot * CV_M + col;
+      const int co = P.cot * CV_M + col;
       if (co >= p.Cout) continue;
       long long pbase;
       int len, sbase;
       if (KS == 3) {
-        const int gy = ty0 + ty;
+        const int gy = P.ty0 + ty;
         if (gy >= p.H) continue;
-        pbase = (long long)gy * p.W + tx0;
-        len = p.W - tx0 < p.TW ? p.W - tx0 : p.TW;
+        pbase = (long long)gy * p.W + P.tx0;
+        len = p.W - P.tx0 < p.TW ? p.W - P.tx0 : p.TW;
         sbase = col * LD + ty * TWp + p.xoff;
       } else {
-        pbase = pix0;
-        len = HW - pix0 < p.N ? (int)(HW - pix0) : p.N;
+        pbase = P.pix0;
+        len = HW - P.pix0 < p.N ? (int)(HW - P.pix0) : p.N;
         sbase = col * LD;
       }
       const float b = p.bias ? __ldg(p.bias + co) : 0.f;
-      float* yrow = p.y + (long long)nb * p.ys_n + (long long)co * p.ys_c + pbase;
-      const float* zrow = p.z ? p.z + (long long)nb * p.zs_n + (long long)co * p.zs_c + pbase : nullptr;
+      float* yrow = p.y + (long long)P.nb * p.ys_n + (long long)co * p.ys_c + pbase;
+      const float* zrow = p.z ? p.z + (long long)P.nb * p.zs_n + (long long)co * p.zs_c + pbase : nullptr;
       for (int i = lane; i < len; i += 32) {
         float val = stage[sbase + i] + b;
         if (zrow) val += __ldg(zrow + i);
@@ -203,148 +238,198 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcPara
     const int pt = tid - 128;
     const int r = pt / HALVES, half = pt % HALVES;
     const bool row_live = r < XROWS;
-    bool valid = false;
-    long long poff = 0;
-    if (KS == 3) {
-      if (p.stride == 1) {
-        const int rows_used = p.N + 2 * TWp + 2;
-        if (r >= 1 && r < rows_used) {
-          const int q = r - 1, ly = q / TWp, lx = q - ly * TWp;
-          const int gy = ty0 + ly - 1, gx = tx0 + lx - 1;
-          valid = ly < p.TH + 2 && gy >= 0 && gy < p.Hi && gx >= 0 && gx < p.Wi;
+    int xc = 0;                                              // chunks produced so far (stage ring position)
+    for (int pi = 0; pi < nparts; ++pi) {
+      const ConvPart& P = pi ? part1 : part0;
+      const int chunks = P.c1 - P.c0;
+      bool valid = false;
+      long long poff = 0;
+      if (KS == 3) {
+        if (p.stride == 1) {
+          const int rows_used = p.N + 2 * TWp + 2;
+          if (r >= 1 && r < rows_used) {
+            const int q = r - 1, ly = q / TWp, lx = q - ly * TWp;
+            const int gy = P.ty0 + ly - 1, gx = P.tx0 + lx - 1;
+            valid = ly < p.TH + 2 && gy >= 0 && gy < p.Hi && gx >= 0 && gx < p.Wi;
+            poff = (long long)gy * p.Wi + gx;
+          }
+        } else {
+          // stride 2: four parity planes P[a][b](u, v) = in(2u + a, 2v + b), each a local (TH + 1) x (TW + 1) grid whose first
+          // row / column is u = ty0 - 1 / v = tx0 - 1; tap (dy, dx) reads plane (dy != 1, dx != 1) shifted by (dy == 0, dx == 0)
+          const int pl = r / p.plane_rows, q = r - pl * p.plane_rows;
+          const int lu = q / TWp, lv = q - lu * TWp;
+          const int gy = 2 * (P.ty0 - 1 + lu) + (pl >> 1), gx = 2 * (P.tx0 - 1 + lv) + (pl & 1);
+          valid = pl < 4 && lu <= p.TH && gy >= 0 && gy < p.Hi && gx >= 0 && gx < p.Wi;
           poff = (long long)gy * p.Wi + gx;
         }
       } else {
-        // stride 2: four parity planes P[a][b](u, v) = in(2u + a, 2v + b), each a local (TH + 1) x (TW + 1) grid whose first
-        // row / column is u = ty0 - 1 / v = tx0 - 1; tap (dy, dx) reads plane (dy != 1, dx != 1) shifted by (dy == 0, dx == 0)
-        const int pl = r / p.plane_rows, q = r - pl * p.plane_rows;
-        const int lu = q / TWp, lv = q - lu * TWp;
-        const int gy = 2 * (ty0 - 1 + lu) + (pl >> 1), gx = 2 * (tx0 - 1 + lv) + (pl & 1);
-        valid = pl < 4 && lu <= p.TH && gy >= 0 && gy < p.Hi && gx >= 0 && gx < p.Wi;
-        poff = (long long)gy * p.Wi + gx;
-      }
-    } else {
-      const long long op = pix0 + r;
-      if (r < p.N && op < HW) {
-        const int oy = (int)(op / p.W), ox = (int)(op - (long long)oy * p.W);
-        valid = true;
-        poff = (long long)(oy * p.stride) * p.Wi + ox * p.stride;
-      }
-    }
-    const float* xb = p.x + (long long)nb * p.xs_n + poff * p.xs_p + (long long)(c_begin * CV_KC + half * CPT) * p.xs_c;
-    float v[DEPTH][CPT];
-    auto load = [&](int c, float (&dst)[CPT]) {
-      if (p.x_vec) {                                           // channels-last: consecutive floats
-#pragma unroll
-        for (int k4 = 0; k4 < CPT / 4; ++k4) {
-          const float4 f = valid ? __ldg(reinterpret_cast<const float4*>(xb + c * CV_KC + 4 * k4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          dst[4 * k4] = f.x; dst[4 * k4 + 1] = f.y; dst[4 * k4 + 2] = f.z; dst[4 * k4 + 3] = f.w;
+        const long long op = P.pix0 + r;
+        if (r < p.N && op < HW) {
+          const int oy = (int)(op / p.W), ox = (int)(op - (long long)oy * p.W);
+          valid = true;
+          poff = (long long)(oy * p.stride) * p.Wi + ox * p.stride;
         }
-      } else {
-#pragma unroll
-        for (int i = 0; i < CPT; ++i) dst[i] = valid ? __ldg(xb + (long long)(c * CV_KC + i) * p.xs_c) : 0.f;
       }
-    };
+      const float* xb = p.x + (long long)P.nb * p.xs_n + poff * p.xs_p + (long long)(P.c0 * CV_KC + half * CPT) * p.xs_c;
+      float v[DEPTH][CPT];
+      auto load = [&](int c, float (&dst)[CPT]) {
+        if (p.x_vec) {                                         // channels-last: consecutive floats
 #pragma unroll
-    for (int d = 0; d < DEPTH; ++d)
-      if (d < chunks) load(d, v[d]);
-#pragma unroll 1
-    for (int c0 = 0; c0 < chunks; c0 += DEPTH) {
-#pragma unroll
-      for (int d = 0; d < DEPTH; ++d) {
-        const int c = c0 + d;
-        if (c < chunks) {
-          const int s = c % XST;
-          mbar_wait(smem_u32(&T.x_empty[s]), ((c / XST) & 1) ^ 1);
-          if (row_live) {
-            unsigned char* hi = Xs + s * XSTAGE + r * 128;
-            unsigned char* lo = hi + XPLANE;
-#pragma unroll
-            for (int k4 = 0; k4 < CPT / 4; ++k4) {
-              float4 f = make_float4(v[d][4 * k4], v[d][4 * k4 + 1], v[d][4 * k4 + 2], v[d][4 * k4 + 3]);
-              if (p.relu_in) f = make_float4(fmaxf(f.x, 0.f), fmaxf(f.y, 0.f), fmaxf(f.z, 0.f), fmaxf(f.w, 0.f));
-              const float4 h = make_float4(to_tf32(f.x), to_tf32(f.y), to_tf32(f.z), to_tf32(f.w));
-              const float4 l = make_float4(to_tf32(f.x - h.x), to_tf32(f.y - h.y), to_tf32(f.z - h.z), to_tf32(f.w - h.w));
-              const int off = ((half * (CPT / 4) + k4) ^ (r & 7)) << 4;
-              *reinterpret_cast<float4*>(hi + off) = h;
-              *reinterpret_cast<float4*>(lo + off) = l;
-            }
+          for (int k4 = 0; k4 < CPT / 4; ++k4) {
+            const float4 f = valid ? __ldg(reinterpret_cast<const float4*>(xb + c * CV_KC + 4 * k4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            dst[4 * k4] = f.x; dst[4 * k4 + 1] = f.y; dst[4 * k4 + 2] = f.z; dst[4 * k4 + 3] = f.w;
           }
-          fence_proxy_async();
-          mbar_arrive(smem_u32(&T.x_full[s]));
-          if (c + DEPTH < chunks) load(c + DEPTH, v[d]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < CPT; ++i) dst[i] = valid ? __ldg(xb + (long long)(c * CV_KC + i) * p.xs_c) : 0.f;
+        }
+      };
+#pragma unroll
+      for (int d = 0; d < DEPTH; ++d)
+        if (d < chunks) load(d, v[d]);
+#pragma unroll 1
+      for (int cb = 0; cb < chunks; cb += DEPTH) {
+#pragma unroll
+        for (int d = 0; d < DEPTH; ++d) {
+          const int c = cb + d;
+          if (c < chunks) {
+            const int s = xc % XST;
+            mbar_wait(smem_u32(&T.x_empty[s]), ((xc / XST) & 1) ^ 1);
+            if (row_live) {
+              unsigned char* hi = Xs + s * XSTAGE + r * 128;
+              unsigned char* lo = hi + XPLANE;
+#pragma unroll
+              for (int k4 = 0; k4 < CPT / 4; ++k4) {
+                float4 f = make_float4(v[d][4 * k4], v[d][4 * k4 + 1], v[d][4 * k4 + 2], v[d][4 * k4 + 3]);
+                if (p.relu_in) f = make_float4(fmaxf(f.x, 0.f), fmaxf(f.y, 0.f), fmaxf(f.z, 0.f), fmaxf(f.w, 0.f));
+                const float4 h = make_float4(to_tf32(f.x), to_tf32(f.y), to_tf32(f.z), to_tf32(f.w));
+                const float4 l = make_float4(to_tf32(f.x - h.x), to_tf32(f.y - h.y), to_tf32(f.z - h.z), to_tf32(f.w - h.w));
+                const int off = ((half * (CPT / 4) + k4) ^ (r & 7)) << 4;
+                *reinterpret_cast<float4*>(hi + off) = h;
+                *reinterpret_cast<float4*>(lo + off) = l;
+              }
+            }
+            fence_proxy_async();
+            mbar_arrive(smem_u32(&T.x_full[s]));
+            ++xc;
+            if (c + DEPTH < chunks) load(c + DEPTH, v[d]);
+          }
         }
       }
     }
-    if (staged) {
-      asm volatile("bar.sync 2, 384;" ::: "memory");          // the tile is staged (or this CTA is not the one that stores)
-      if (T.last) store_staged_rows(warp);
+    for (int pi = 0; pi < nparts; ++pi) {                     // help the epilogue warps store the staged tile(s)
+      asm volatile("bar.sync 2, 384;" ::: "memory");          // tile pi staged (or this CTA does not store it)
+      if (staged && T.last[pi]) store_staged_rows(pi ? part1 : part0, warp);
+      if (pi + 1 < nparts) asm volatile("bar.sync 2, 384;" ::: "memory");   // staging buffer free again
     }
   } else if (warp == 13) {
     // ================================== weight loader ==================================
     if (lane == 0) {
-      const unsigned char* wsrc = p.wimg + ((size_t)cot * all_chunks + c_begin) * TAPS * CV_A_BYTES;
-      const int steps = chunks * TAPS;
-      for (int i = 0; i < steps; ++i) {
-        const int s = i % CV_A_STAGES;
-        mbar_wait(smem_u32(&T.a_empty[s]), ((i / CV_A_STAGES) & 1) ^ 1);
-        mbar_arrive_expect_tx(smem_u32(&T.a_full[s]), CV_A_BYTES);
-        bulk_g2s(smem_u32(As + s * CV_A_BYTES), wsrc + (size_t)i * CV_A_BYTES, CV_A_BYTES, smem_u32(&T.a_full[s]));
+      int i = 0;
+      for (int pi = 0; pi < nparts; ++pi) {
+        const ConvPart& P = pi ? part1 : part0;
+        const unsigned char* wsrc = p.wimg + ((size_t)P.cot * C + P.c0) * TAPS * CV_A_BYTES;
+        const int steps = (P.c1 - P.c0) * TAPS;
+        for (int k = 0; k < steps; ++k, ++i) {
+          const int s = i % CV_A_STAGES;
+          mbar_wait(smem_u32(&T.a_empty[s]), ((i / CV_A_STAGES) & 1) ^ 1);
+          mbar_arrive_expect_tx(smem_u32(&T.a_full[s]), CV_A_BYTES);
+          bulk_g2s(smem_u32(As + s * CV_A_BYTES), wsrc + (size_t)k * CV_A_BYTES, CV_A_BYTES, smem_u32(&T.a_full[s]));
+        }
       }
     }
   } else if (warp == 12) {
     // ================================== MMA issuer ==================================
     if (lane == 0) {
       const uint32_t idesc = idesc_tf32(CV_M, p.N, false, false);
-      int i = 0;
-      for (int c = 0; c < chunks; ++c) {
-        const int xs = c % XST;
-        mbar_wait(smem_u32(&T.x_full[xs]), (c / XST) & 1);
-        tc_fence_after();
-        const uint32_t xb_hi = smem_u32(Xs + xs * XSTAGE), xb_lo = xb_hi + XPLANE;
-        const uint32_t acc_hh = tmem + (uint32_t)(c % 3) * 128u;
-#pragma unroll 1
-        for (int t = 0; t < TAPS; ++t, ++i) {
-          const int s = i % CV_A_STAGES;
-          mbar_wait(smem_u32(&T.a_full[s]), (i / CV_A_STAGES) & 1);
+      int i = 0, xc = 0;
+      for (int pi = 0; pi < nparts; ++pi) {
+        const ConvPart& P = pi ? part1 : part0;
+        const int chunks = P.c1 - P.c0;
+        const uint32_t set = tmem + (uint32_t)pi * 256u;       // (direct: one part, all 512 columns)
+        const uint32_t acc_x = set + (uint32_t)nhh * 128u;     // cross terms
+        for (int c = 0; c < chunks; ++c, ++xc) {
+          const int xs = xc % XST;
+          mbar_wait(smem_u32(&T.x_full[xs]), (xc / XST) & 1);
           tc_fence_after();
-          const uint32_t a_hi = smem_u32(As + s * CV_A_BYTES), a_lo = a_hi + CV_M * 128;
-          const uint32_t shift = KS == 3 ? (uint32_t)p.shift[t] * 128u : 0u;
+          const uint32_t xb_hi = smem_u32(Xs + xs * XSTAGE), xb_lo = xb_hi + XPLANE;
+          const uint32_t acc_hh = set + (uint32_t)(c % nhh) * 128u;
+#pragma unroll 1
+          for (int t = 0; t < TAPS; ++t, ++i) {
+            const int s = i % CV_A_STAGES;
+            mbar_wait(smem_u32(&T.a_full[s]), (i / CV_A_STAGES) & 1);
+            tc_fence_after();
+            const uint32_t a_hi = smem_u32(As + s * CV_A_BYTES), a_lo = a_hi + CV_M * 128;
+            const uint32_t shift = KS == 3 ? (uint32_t)p.shift[t] * 128u : 0u;
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t da_hi = desc_sw128_kmajor(a_hi + ks * 32), da_lo = desc_sw128_kmajor(a_lo + ks * 32);
-            const uint64_t db_hi = desc_sw128_kmajor(xb_hi + shift + ks * 32);
-            const uint64_t db_lo = desc_sw128_kmajor(xb_lo + shift + ks * 32);
-            tc_mma_tf32(tmem + 384, da_lo, db_hi, idesc, (i | ks) != 0 ? 1u : 0u);      // cross terms
-            tc_mma_tf32(tmem + 384, da_hi, db_lo, idesc, 1u);
-            tc_mma_tf32(acc_hh, da_hi, db_hi, idesc, (c >= 3 || (t | ks) != 0) ? 1u : 0u);
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t da_hi = desc_sw128_kmajor(a_hi + ks * 32), da_lo = desc_sw128_kmajor(a_lo + ks * 32);
+              const uint64_t db_hi = desc_sw128_kmajor(xb_hi + shift + ks * 32);
+              const uint64_t db_lo = desc_sw128_kmajor(xb_lo + shift + ks * 32);
+              tc_mma_tf32(acc_x, da_lo, db_hi, idesc, (c | t | ks) != 0 ? 1u : 0u);
+              tc_mma_tf32(acc_x, da_hi, db_lo, idesc, 1u);
+              tc_mma_tf32(acc_hh, da_hi, db_hi, idesc, (c >= nhh || (t | ks) != 0) ? 1u : 0u);
+            }
+            tc_commit(smem_u32(&T.a_empty[s]));
           }
-          tc_commit(smem_u32(&T.a_empty[s]));
+          tc_commit(smem_u32(&T.x_empty[xs]));
         }
-        tc_commit(smem_u32(&T.x_empty[xs]));
+        tc_commit(smem_u32(&T.acc_full[pi]));
       }
-      tc_commit(smem_u32(&T.acc_full));
     }
   } else {
     // ================================== epilogue: thread == output channel ==================================
-    const int co = cot * CV_M + tid;
-    const bool co_ok = co < p.Cout;                           // the last channel tile may be padded (zero weight rows)
-    const float b = (p.bias && co_ok) ? __ldg(p.bias + co) : 0.f;
-    float* yb = p.y + (long long)nb * p.ys_n + (long long)co * p.ys_c;
-    const float* zb = p.z ? p.z + (long long)nb * p.zs_n + (long long)co * p.zs_c : nullptr;
     const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
-    mbar_wait(smem_u32(&T.acc_full), 0);
-    tc_fence_after();
-    const int nacc = chunks < 3 ? chunks : 3;               // hi.hi accumulators in use
-    const long long tile_id = ((long long)nb * gridDim.y + cot) * (gridDim.x / p.split) + tile;
-    float* wsp = p.split > 1 ? p.ws + (tile_id * p.split) * (long long)(p.N * CV_M) : nullptr;
-    bool finish = true;                                      // this CTA applies the epilogue and stores
-    if (p.split > 1) {
-      // partial tile -> workspace [split][position][channel] (lanes == consecutive channels: coalesced)
-      float* mine = wsp + (long long)ksplit * (p.N * CV_M);
+    // o[0..31] = the 32 positions from g of one part's tile: from TMEM (direct) or the contributors' partial sums
+    auto finish_group = [&](const ConvPart& P, int g, uint32_t (&o)[32], int& ty, int& lx) {
+      const int co = P.cot * CV_M + tid;
+      const bool co_ok = co < p.Cout;                         // the last channel tile may be padded (zero weight rows)
+      if (staged) {
+        float* stage = reinterpret_cast<float*>(smem);
+        if (staged_nchw) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (g + j < p.N) stage[tid * LD + g + j] = __uint_as_float(o[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (g + j < p.N) stage[(g + j) * CV_M + tid] = __uint_as_float(o[j]);
+        }
+        return;
+      }
+      const float b = (p.bias && co_ok) ? __ldg(p.bias + co) : 0.f;
+      float* yb = p.y + (long long)P.nb * p.ys_n + (long long)co * p.ys_c;
+      const float* zb = p.z ? p.z + (long long)P.nb * p.zs_n + (long long)co * p.zs_c : nullptr;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        bool ok;
+        long long pix;
+        if (KS == 3) {
+          const int gy = P.ty0 + ty, gx = P.tx0 + lx - p.xoff;
+          ok = g + j < p.N && lx >= p.xoff && lx < p.TW + p.xoff && ty < p.TH && gy < p.H && gx < p.W;
+          pix = (long long)gy * p.W + gx;
+          if (++lx == TWp) { lx = 0; ++ty; }
+        } else {
+          pix = P.pix0 + g + j;
+          ok = g + j < p.N && pix < HW;
+        }
+        if (co_ok && ok) {
+          float val = __uint_as_float(o[j]) + b;
+          if (zb) val += __ldg(zb + pix * p.zs_p);
+          if (p.relu_out) val = fmaxf(val, 0.f);
+          yb[pix * p.ys_p] = val;
+        }
+      }
+    };
+    if (direct) {
+      mbar_wait(smem_u32(&T.acc_full[0]), 0);
+      tc_fence_after();
+      const int chunks = part0.c1 - part0.c0;
+      const int nacc = chunks < 3 ? chunks : 3;
+      int ty = 0, lx = 0;
       for (int g = 0; g < p.N; g += 32) {
         uint32_t o[32], q[32];
-        tmem_ld32(lane_base + g, o);
+        tmem_ld32(lane_base + g, o);                          // (columns >= N of the last group are never stored)
         for (int a = 1; a < nacc; ++a) {
           tmem_ld32(lane_base + a * 128 + g, q);
 #pragma unroll
@@ -352,81 +437,61 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcPara
         }
         tmem_ld32(lane_base + 384 + g, q);
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (g + j < p.N) mine[(g + j) * CV_M + tid] = __uint_as_float(o[j]) + __uint_as_float(q[j]);
+        for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) + __uint_as_float(q[j]));
+        finish_group(part0, g, o, ty, lx);
+      }
+      if (tid == 0) T.last[0] = 1;
+      asm volatile("bar.sync 2, 384;" ::: "memory");
+      if (staged) store_staged_rows(part0, warp);
+    } else {
+      // ---- shares: partial tile -> workspace [tile][slot][position][channel] (lanes == consecutive channels) ----
+      for (int pi = 0; pi < nparts; ++pi) {
+        const ConvPart& P = pi ? part1 : part0;
+        mbar_wait(smem_u32(&T.acc_full[pi]), 0);
+        tc_fence_after();
+        float* mine = p.ws + (P.tile_lin * p.maxslots + P.slot) * (long long)(p.N * CV_M);
+        for (int g = 0; g < p.N; g += 32) {
+          uint32_t o[32], q[32];
+          tmem_ld32(lane_base + pi * 256 + g, o);
+          tmem_ld32(lane_base + pi * 256 + 128 + g, q);
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (g + j < p.N) mine[(g + j) * CV_M + tid] = __uint_as_float(o[j]) + __uint_as_float(q[j]);
+        }
       }
       __threadfence();
       asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps
-      if (tid == 0) T.last = atomicAdd(p.counters + tile_id, 1) == p.split - 1 ? 1 : 0;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      finish = T.last != 0;                                    // the CTA that arrives last adds the partials IN SPLIT ORDER
-      if (finish) __threadfence();
-    } else if (tid == 0) {
-      T.last = 1;
-    }
-    if (finish) {
-      int ty = 0, lx = 0;                                     // 3x3: position j = ty * TWp + lx
-      for (int g = 0; g < p.N; g += 32) {
-        uint32_t o[32], q[32];
-        if (p.split > 1) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) o[j] = 0u;
-          for (int k = 0; k < p.split; ++k) {
-            const float* part = wsp + (long long)k * (p.N * CV_M);
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (g + j < p.N) o[j] = __float_as_uint(__uint_as_float(o[j]) + __ldcg(part + (g + j) * CV_M + tid));
-          }
-        } else {
-          tmem_ld32(lane_base + g, o);                        // (columns >= N of the last group are never stored)
-          for (int a = 1; a < nacc; ++a) {
-            tmem_ld32(lane_base + a * 128 + g, q);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) + __uint_as_float(q[j]));
-          }
-          tmem_ld32(lane_base + 384 + g, q);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) + __uint_as_float(q[j]));
-        }
-        if (staged) {
-          float* stage = reinterpret_cast<float*>(smem);
-          if (staged_nchw) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (g + j < p.N) stage[tid * LD + g + j] = __uint_as_float(o[j]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (g + j < p.N) stage[(g + j) * CV_M + tid] = __uint_as_float(o[j]);
-          }
-          continue;
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          bool ok;
-          long long pix;
-          if (KS == 3) {
-            const int gy = ty0 + ty, gx = tx0 + lx - p.xoff;
-            ok = g + j < p.N && lx >= p.xoff && lx < p.TW + p.xoff && ty < p.TH && gy < p.H && gx < p.W;
-            pix = (long long)gy * p.W + gx;
-            if (++lx == TWp) { lx = 0; ++ty; }
-          } else {
-            pix = pix0 + g + j;
-            ok = g + j < p.N && pix < HW;
-          }
-          if (co_ok && ok) {
-            float val = __uint_as_float(o[j]) + b;
-            if (zb) val += __ldg(zb + pix * p.zs_p);
-            if (p.relu_out) val = fmaxf(val, 0.f);
-            yb[pix * p.ys_p] = val;
-          }
-        }
+      if (tid < nparts) {
+        const ConvPart& P = tid ? part1 : part0;
+        T.last[tid] = atomicAdd(p.counters + P.tile_lin, 1) == P.nslots - 1 ? 1 : 0;
       }
-      if (p.split > 1 && tid == 0) p.counters[tile_id] = 0;   // ready for the next launch
-    }
-    if (staged) {
-      asm volatile("bar.sync 2, 384;" ::: "memory");
-      if (finish) store_staged_rows(warp);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      // ---- the CTA that arrives last at a tile adds its shares IN SLOT ORDER and stores the tile ----
+      for (int pi = 0; pi < nparts; ++pi) {
+        const ConvPart& P = pi ? part1 : part0;
+        const bool fin = T.last[pi] != 0;
+        if (fin) {
+          __threadfence();
+          const float* wst = p.ws + (P.tile_lin * p.maxslots) * (long long)(p.N * CV_M);
+          int ty = 0, lx = 0;
+          for (int g = 0; g < p.N; g += 32) {
+            uint32_t o[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = 0u;
+            for (int k = 0; k < P.nslots; ++k) {
+              const float* sh = wst + (long long)k * (p.N * CV_M);
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (g + j < p.N) o[j] = __float_as_uint(__uint_as_float(o[j]) + __ldcg(sh + (g + j) * CV_M + tid));
+            }
+            finish_group(P, g, o, ty, lx);
+          }
+          if (tid == 0) p.counters[P.tile_lin] = 0;           // ready for the next launch
+        }
+        asm volatile("bar.sync 2, 384;" ::: "memory");        // (the producers arrive here once per part)
+        if (fin && staged) store_staged_rows(P, warp);
+        if (pi + 1 < nparts) asm volatile("bar.sync 2, 384;" ::: "memory");   // staging buffer free again
+      }
     }
   }
   tc_fence_before();
@@ -506,15 +571,64 @@ static void conv_tile_shape(int H, int W, int stride, int* TH, int* TW, int* N) 
   }
 }
 
+// Launch plan.  Work = (output tile, input chunk) units, T tiles x C chunks; CTA i owns units [i q, (i + 1) q).  Layers with
+// at least as many output tiles as SMs run one whole tile per CTA (q = C).  Smaller layers are spread evenly over the SMs:
+// q = ceil(T C / SMs) (>= 2 chunks when there are that many), so a CTA's share spans at most two tiles and a tile is shared
+// by at most ceil(C / q) + 1 CTAs, which meet in the workspace.
+struct ConvPlan { long long tiles, cots, T; int N, C, q, maxslots; long long ctas; int th, tw; };
+static int conv_make_plan(int64_t NB, int64_t Cin, int64_t Cout, int64_t H_in, int64_t W_in, int ksize, int stride, int q_override,
+                          ConvPlan* pl) {
+  const int H = (int)((H_in - 1) / stride + 1), W = (int)((W_in - 1) / stride + 1);
+  pl->th = pl->tw = 0; pl->N = 0;
+  if (ksize == 3) {
+    conv_tile_shape(H, W, stride, &pl->th, &pl->tw, &pl->N);
+    if (pl->N < 16) return -1;
+    pl->tiles = (long long)((W + pl->tw - 1) / pl->tw) * ((H + pl->th - 1) / pl->th);
+  } else {
+    const long long hw = (long long)H * W;
+    pl->N = hw >= 128 ? 128 : (int)((hw + 15) / 16 * 16);
+    pl->tiles = (hw + pl->N - 1) / pl->N;
+  }
+  pl->cots = (Cout + CV_M - 1) / CV_M;
+  pl->T = pl->tiles * pl->cots * NB;
+  pl->C = (int)(Cin / CV_KC);
+  int q = pl->C;
+  if (pl->T < num_sms()) {
+    q = (int)((pl->T * pl->C + num_sms() - 1) / num_sms());
+    if (q < 2) q = 2;
+    if (q > pl->C) q = pl->C;
+  }
+  if (q_override > 0) q = q_override < pl->C ? q_override : pl->C;
+  pl->q = q;
+  pl->maxslots = (pl->C - 1) / q + 2;
+  pl->ctas = (pl->T * pl->C + q - 1) / q;
+  return 0;
+}
+
+extern "C" int cutie_conv_plan(int64_t NB, int64_t Cin, int64_t Cout, int64_t H_in, int64_t W_in, int ksize, int stride,
+                               int units_per_cta, int64_t* out6) {
+  CUTIE_REQUIRE(out6 && (ksize == 1 || ksize == 3) && (stride == 1 || stride == 2) && Cin >= CV_KC && Cin % CV_KC == 0 && NB >= 1 &&
+                    Cout >= 1, "bad arguments");
+  ConvPlan pl;
+  CUTIE_REQUIRE(conv_make_plan(NB, Cin, Cout, H_in, W_in, ksize, stride, units_per_cta, &pl) == 0, "no tile shape for this geometry");
+  out6[0] = pl.T; out6[1] = pl.N; out6[2] = pl.C; out6[3] = pl.q; out6[4] = pl.ctas;
+  out6[5] = pl.q < pl.C ? pl.T * pl.maxslots * (long long)pl.N * CV_M : 0;          // workspace floats (0: none needed)
+  return 0;
+}
+
 extern "C" int cutie_conv_tc(const float* x, const int64_t* x_strides, const void* weight_image, const float* bias,
                              const float* residual, const int64_t* residual_strides, int64_t NB, int64_t Cin, int64_t Cout,
                              int64_t H_in, int64_t W_in, int ksize, int stride, int relu_in, int relu_out, float* y,
-                             const int64_t* y_strides, int split, float* workspace, int32_t* counters, void* stream) {
+                             const int64_t* y_strides, int units_per_cta, float* workspace, int32_t* counters, void* stream) {
   CUTIE_REQUIRE(x && x_strides && weight_image && y && y_strides, "null argument");
   CUTIE_REQUIRE(residual == nullptr || residual_strides != nullptr, "residual needs strides");
   CUTIE_REQUIRE((ksize == 3 || ksize == 1) && (stride == 1 || stride == 2), "3x3 (zero pad 1) or 1x1, stride 1 or 2");
   CUTIE_REQUIRE(Cout >= 1 && Cin >= CV_KC && Cin % CV_KC == 0, "input channels must be a multiple of 32");
   CUTIE_REQUIRE(NB >= 1 && NB <= 65535 && H_in >= 1 && W_in >= 1 && H_in * W_in < (1ll << 30), "bad geometry");
+  ConvPlan pl;
+  CUTIE_REQUIRE(conv_make_plan(NB, Cin, Cout, H_in, W_in, ksize, stride, units_per_cta, &pl) == 0, "no tile shape for this geometry");
+  CUTIE_REQUIRE(pl.q == pl.C || (workspace && counters), "shared tiles need the workspace and zeroed counters (cutie_conv_plan)");
+  CUTIE_REQUIRE(pl.ctas <= 0x7fffffff, "too many tiles");
   ConvTcParams p;
   p.x = x; p.wimg = static_cast<const unsigned char*>(weight_image); p.bias = bias; p.z = residual; p.y = y;
   p.xs_n = x_strides[0]; p.xs_c = x_strides[1]; p.xs_p = x_strides[2];
@@ -532,16 +646,12 @@ extern "C" int cutie_conv_tc(const float* x, const int64_t* x_strides, const voi
   };
   p.cl_vec = (Cout % 4 == 0 && vec4(y, p.ys_n, p.ys_c, p.ys_p) && (bias == nullptr || reinterpret_cast<uintptr_t>(bias) % 16 == 0) &&
               (residual == nullptr || vec4(residual, p.zs_n, p.zs_c, p.zs_p))) ? 1 : 0;
-  long long tiles;
-  p.TH = 0; p.TW = 0; p.N = 0; p.tiles_x = 1; p.pitch = 2; p.xoff = 0; p.plane_rows = 0;
+  p.TH = pl.th; p.TW = pl.tw; p.N = pl.N; p.tiles_x = 1; p.pitch = 2; p.xoff = 0; p.plane_rows = 0;
   for (int t = 0; t < 9; ++t) p.shift[t] = 0;
   if (ksize == 3) {
-    conv_tile_shape(p.H, p.W, stride, &p.TH, &p.TW, &p.N);
-    CUTIE_REQUIRE(p.N >= 16, "no tile shape for this geometry");
     p.tiles_x = (p.W + p.TW - 1) / p.TW;
-    tiles = (long long)p.tiles_x * ((p.H + p.TH - 1) / p.TH);
     if (stride == 1) {
-      p.pitch = p.TW + 2; p.xoff = 1; p.plane_rows = 0;
+      p.pitch = p.TW + 2; p.xoff = 1;
       for (int t = 0; t < 9; ++t) p.shift[t] = (t / 3) * p.pitch + (t % 3);
     } else {
       p.pitch = p.TW + 1; p.xoff = 0; p.plane_rows = conv_plane_rows(p.TH, p.TW, p.N);
@@ -551,54 +661,20 @@ extern "C" int cutie_conv_tc(const float* x, const int64_t* x_strides, const voi
         p.shift[t] = plane * p.plane_rows + (dy == 0 ? 0 : 1) * p.pitch + (dx == 0 ? 0 : 1);
       }
     }
-  } else {
-    const long long hw = (long long)p.H * p.W;
-    p.N = hw >= 128 ? 128 : (int)((hw + 15) / 16 * 16);
-    tiles = (hw + p.N - 1) / p.N;
   }
-  CUTIE_REQUIRE(split >= 1 && split <= Cin / CV_KC, "1 <= split <= Cin / 32");
-  CUTIE_REQUIRE(split == 1 || (workspace && counters), "split > 1 needs the workspace and zeroed counters");
-  CUTIE_REQUIRE(tiles * split <= 0x7fffffff, "too many tiles");
-  p.split = split; p.ws = workspace; p.counters = counters;
+  p.q = pl.q; p.T = (int)pl.T; p.tiles = (int)pl.tiles; p.cots = (int)pl.cots; p.maxslots = pl.maxslots;
+  p.ws = workspace; p.counters = counters;
+  CUTIE_REQUIRE(pl.T <= 0x7fffffff, "too many tiles");
   static bool attr_done[64] = {};
   if (first_use_on_device(attr_done)) {
     cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SMEM3);
     cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SMEM1);
   }
-  const dim3 grid((unsigned)(tiles * split), (unsigned)((Cout + CV_M - 1) / CV_M), (unsigned)NB);
   if (ksize == 3)
-    conv_tc_kernel<3><<<grid, CV_THREADS, CV_SMEM3, (cudaStream_t)stream>>>(p);
+    conv_tc_kernel<3><<<(unsigned)pl.ctas, CV_THREADS, CV_SMEM3, (cudaStream_t)stream>>>(p);
   else
-    conv_tc_kernel<1><<<grid, CV_THREADS, CV_SMEM1, (cudaStream_t)stream>>>(p);
+    conv_tc_kernel<1><<<(unsigned)pl.ctas, CV_THREADS, CV_SMEM1, (cudaStream_t)stream>>>(p);
   CUTIE_CHECK_LAUNCH();
-  return 0;
-}
-
-// launch plan: {tiles per image and channel tile, MMA N, recommended K split}.  The split spreads a layer with few output
-// tiles over the SMs: largest s <= 8 with (CTAs x s) <= SMs and at least 2 input chunks per CTA.
-extern "C" int cutie_conv_plan(int64_t NB, int64_t Cin, int64_t Cout, int64_t H_in, int64_t W_in, int ksize, int stride,
-                               int64_t* out3) {
-  CUTIE_REQUIRE(out3 && (ksize == 1 || ksize == 3) && (stride == 1 || stride == 2) && Cin >= CV_KC && Cin % CV_KC == 0,
-                "bad arguments");
-  const int H = (int)((H_in - 1) / stride + 1), W = (int)((W_in - 1) / stride + 1);
-  long long tiles;
-  int N = 0;
-  if (ksize == 3) {
-    int th = 0, tw = 0;
-    conv_tile_shape(H, W, stride, &th, &tw, &N);
-    CUTIE_REQUIRE(N >= 16, "no tile shape for this geometry");
-    tiles = (long long)((W + tw - 1) / tw) * ((H + th - 1) / th);
-  } else {
-    const long long hw = (long long)H * W;
-    N = hw >= 128 ? 128 : (int)((hw + 15) / 16 * 16);
-    tiles = (hw + N - 1) / N;
-  }
-  const long long ctas = tiles * ((Cout + CV_M - 1) / CV_M) * NB;
-  const int chunks = (int)(Cin / CV_KC);
-  int split = 1;
-  for (int s = 2; s <= 8; ++s)
-    if (ctas * s <= num_sms() && chunks / s >= 2) split = s;
-  out3[0] = tiles; out3[1] = N; out3[2] = split;
   return 0;
 }
 

@@ -478,12 +478,13 @@ def _ncp_strides(t: torch.Tensor):
 
 def conv_tc(x: torch.Tensor, weight_image: torch.Tensor, bias: Optional[torch.Tensor], cout: int, ksize: int = 3,
             stride: int = 1, residual: Optional[torch.Tensor] = None, relu_in: bool = False,
-            relu_out: bool = False, split_override: Optional[int] = None,
+            relu_out: bool = False, units_per_cta: Optional[int] = None,
             counters: Optional[torch.Tensor] = None) -> torch.Tensor:
     """act(bias + conv(pre(x)) [+ residual]) on the tensor cores with 3xTF32 splitting (fp32-class accuracy).
     x [N, Cin, H, W] dense NCHW or channels-last (the output takes the same memory format) -> [N, cout, H', W'].
-    Layers with few output tiles are split over input-channel ranges (cutie_conv_plan); `counters`: the layer's own zeroed
-    int32 tile counters (the kernel leaves them zero), else a fresh zeroed buffer per call."""
+    Layers with fewer output tiles than SMs are spread evenly over the SMs in (tile, input chunk) units (cutie_conv_plan):
+    `units_per_cta` overrides the plan's share size (tests); `counters`: the layer's own zeroed int32 tile counters (the
+    kernel leaves them zero), else a fresh zeroed buffer per call."""
     N, Cin, H, W = x.shape
     assert x.dtype == torch.float32 and ksize in (1, 3)
     cl = x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous()
@@ -500,23 +501,21 @@ def conv_tc(x: torch.Tensor, weight_image: torch.Tensor, bias: Optional[torch.Te
             residual = residual.contiguous()
             zs = _ncp_strides(residual)
     arr = lambda t: (ctypes.c_int64 * 3)(*t)
-    plan = (ctypes.c_int64 * 3)()
-    _check(lib().cutie_conv_plan(_i64(N), _i64(Cin), _i64(cout), _i64(H), _i64(W), int(ksize), int(stride), plan),
+    plan = (ctypes.c_int64 * 6)()
+    q = int(units_per_cta) if units_per_cta else 0
+    _check(lib().cutie_conv_plan(_i64(N), _i64(Cin), _i64(cout), _i64(H), _i64(W), int(ksize), int(stride), q, plan),
            'cutie_conv_plan')
-    tiles, n_mma, split = int(plan[0]), int(plan[1]), int(plan[2])
-    if split_override is not None:
-        split = max(1, min(int(split_override), Cin // 32))
+    ntile, ws_floats = int(plan[0]), int(plan[5])
     ws = cnt = None
-    if split > 1:
-        ntile = N * ((cout + 127) // 128) * tiles
-        ws = torch.empty(ntile * split * n_mma * 128, dtype=torch.float32, device=x.device)
+    if ws_floats:
+        ws = torch.empty(ws_floats, dtype=torch.float32, device=x.device)
         cnt = counters if counters is not None and counters.numel() >= ntile else torch.zeros(ntile, dtype=torch.int32, device=x.device)
     with _call('conv_tc', 1):
         st = lib().cutie_conv_tc(_ptr(x), arr(_ncp_strides(x)), _ptr(weight_image),
                                  _ptr(bias.detach() if bias is not None else None), _ptr(residual),
                                  arr(zs) if zs is not None else None, _i64(N), _i64(Cin), _i64(cout), _i64(H), _i64(W),
                                  int(ksize), int(stride), int(bool(relu_in)), int(bool(relu_out)), _ptr(out),
-                                 arr(_ncp_strides(out)), int(split), _ptr(ws), _ptr(cnt, torch.int32), _stream())
+                                 arr(_ncp_strides(out)), q, _ptr(ws), _ptr(cnt, torch.int32), _stream())
     _check(st, 'cutie_conv_tc')
     return out
 

@@ -183,13 +183,15 @@ int cutie_conv_weight_image(const float* weight, int64_t Cout, int64_t Cin, int 
 int cutie_conv_tc(const float* x, const int64_t* x_strides, const void* weight_image, const float* bias,
                   const float* residual, const int64_t* residual_strides, int64_t NB, int64_t Cin, int64_t Cout,
                   int64_t H_in, int64_t W_in, int ksize, int stride, int relu_in, int relu_out, float* y,
-                  const int64_t* y_strides, int split, float* workspace, int32_t* counters, void* stream);
-/* Launch plan of cutie_conv_tc: out3 = {output tiles per image and 128-channel tile, MMA N, recommended split}.
- * split > 1 spreads a layer with few output tiles over the SMs by input-channel ranges: the partial tiles meet in
- * `workspace` (NB * ceil(Cout/128) * tiles * split * N * 128 floats) and the CTA that arrives last at a tile adds them in
- * split order (deterministic) before the epilogue; `counters` (NB * ceil(Cout/128) * tiles int32) must be zero on entry and
- * are zero again on exit. */
-int cutie_conv_plan(int64_t NB, int64_t Cin, int64_t Cout, int64_t H_in, int64_t W_in, int ksize, int stride, int64_t* out3);
+                  const int64_t* y_strides, int units_per_cta, float* workspace, int32_t* counters, void* stream);
+/* Launch plan of cutie_conv_tc: out6 = {output tiles T (images x 128-channel tiles x spatial tiles), MMA N, input chunks C per
+ * tile, (tile, chunk) units per CTA q, CTAs, workspace floats}.  CTA i owns units [i q, (i + 1) q) of the T x C space: layers
+ * with at least as many tiles as SMs run one whole tile per CTA (q = C, no workspace); smaller layers are spread evenly over
+ * the SMs (q = ceil(T C / SMs)): a CTA's share spans at most two tiles, the shares of a tile meet in `workspace` and the CTA
+ * that arrives last adds them in slot order (deterministic) before the epilogue.  `counters` (T int32) must be zero on entry
+ * and are zero again on exit.  units_per_cta = 0: the plan's choice (pass the same value to both calls). */
+int cutie_conv_plan(int64_t NB, int64_t Cin, int64_t Cout, int64_t H_in, int64_t W_in, int ksize, int stride, int units_per_cta,
+                    int64_t* out6);
 /* test hook: the spatial tile the launcher picks (out3 = {rows, columns, MMA N}). */
 int cutie_debug_conv_tile_shape(int64_t H, int64_t W, int* out3);
 

@@ -272,7 +272,7 @@ def conv_weight_image(weight):
     return weight.detach()                      # the emulation's "operand image" is the weight itself
 
 
-def conv_tc(x, weight_image, bias, cout, ksize=3, stride=1, residual=None, relu_in=False, relu_out=False, split_override=None, counters=None):
+def conv_tc(x, weight_image, bias, cout, ksize=3, stride=1, residual=None, relu_in=False, relu_out=False, units_per_cta=None, counters=None):
     import torch.nn.functional as F
     assert weight_image.shape[0] == cout and weight_image.shape[2] == ksize
     y = F.conv2d(torch.relu(x) if relu_in else x, weight_image, bias, stride=stride, padding=ksize // 2)

@@ -187,47 +187,53 @@ def test_trunk_layers_time_beside_cudnn_channels_last(NB, Cin, Cout, H, W, k):
 
 
 @pytest.mark.parametrize('NB,Cin,Cout,H,W,k', [(1, 1024, 256, 30, 54, 1), (1, 256, 256, 30, 54, 3), (1, 128, 128, 60, 108, 3),
-                                               (2, 96, 200, 7, 9, 3), (1, 512, 128, 60, 108, 1)])
-@pytest.mark.parametrize('split', [2, 3, 4, 8])
-def test_split_k_is_deterministic_and_as_accurate(NB, Cin, Cout, H, W, k, split):
-    """Layers with few output tiles are split over input-channel ranges; partial tiles meet in a workspace and the CTA that
-    arrives last adds them in split order: the result does not depend on arrival order (two runs are bit-identical), the
-    counters come back zero, accuracy is that of the unsplit kernel."""
+                                               (2, 96, 200, 7, 9, 3), (1, 512, 128, 60, 108, 1), (3, 256, 256, 30, 54, 3)])
+@pytest.mark.parametrize('q', [1, 2, 3, 5, 7])
+def test_shared_tiles_are_deterministic_and_as_accurate(NB, Cin, Cout, H, W, k, q):
+    """Layers with fewer output tiles than SMs are spread over the SMs in (tile, input chunk) units, q per CTA: a CTA's share
+    may span two tiles, a tile's shares meet in a workspace and the CTA that arrives last adds them in slot order -- the
+    result does not depend on arrival order (runs are bit-identical), the counters come back zero, accuracy is that of the
+    one-tile-per-CTA kernel."""
     import cutie_b200.kernels as K_
     torch.backends.cudnn.allow_tf32 = False
-    if split > Cin // 32:
-        pytest.skip('more splits than chunks')
-    g = torch.Generator(device='cuda').manual_seed(split + Cin)
+    if q > Cin // 32:
+        pytest.skip('more units per CTA than chunks per tile')
+    g = torch.Generator(device='cuda').manual_seed(q + Cin)
     x = torch.randn(NB, Cin, H, W, device='cuda', generator=g).contiguous(memory_format=torch.channels_last)
     w = torch.randn(Cout, Cin, k, k, device='cuda', generator=g) * (2.0 / (k * k * Cin)) ** 0.5
     b = torch.randn(Cout, device='cuda', generator=g)
     z = torch.randn(NB, Cout, H, W, device='cuda', generator=g)
     img = K_.conv_weight_image(w)
     cnt = torch.zeros(8192, dtype=torch.int32, device='cuda')
-    outs = [K_.conv_tc(x, img, b, Cout, ksize=k, residual=z, relu_out=True, split_override=split, counters=cnt) for _ in range(3)]
-    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
-    assert int(cnt.abs().max()) == 0
     ref = (F.conv2d(x.double(), w.double(), b.double(), padding=k // 2) + z.double()).relu()
-    one = K_.conv_tc(x, img, b, Cout, ksize=k, residual=z, relu_out=True, split_override=1)
     scale = float(ref.abs().max())
-    e_split, e_one = float((outs[0].double() - ref).abs().max()) / scale, float((one.double() - ref).abs().max()) / scale
-    print(f'{k}x{k} [{NB},{Cin}->{Cout},{H}x{W}] split {split}: err {e_split:.2e} (unsplit {e_one:.2e})')
-    assert e_split < 2 * e_one + 1e-6
+    one = K_.conv_tc(x, img, b, Cout, ksize=k, residual=z, relu_out=True, units_per_cta=Cin // 32)
+    e_one = float((one.double() - ref).abs().max()) / scale
+    for xx, zz in ((x, z), (x.contiguous(), z), (x, z.contiguous(memory_format=torch.channels_last))):   # staged NCHW / CL / direct
+        outs = [K_.conv_tc(xx, img, b, Cout, ksize=k, residual=zz, relu_out=True, units_per_cta=q, counters=cnt) for _ in range(3)]
+        assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+        assert int(cnt.abs().max()) == 0
+        e = float((outs[0].double() - ref).abs().max()) / scale
+        assert e < 2 * e_one + 1e-6, (e, e_one)
+    print(f'{k}x{k} [{NB},{Cin}->{Cout},{H}x{W}] {q} units per CTA: err {e:.2e} (whole tiles {e_one:.2e})')
 
 
-def test_conv_plan_splits_small_grids_only():
+def test_conv_plan_spreads_small_layers_over_the_sms():
     import ctypes
     import cutie_b200.kernels as K_
-    plan = (ctypes.c_int64 * 3)()
+    plan = (ctypes.c_int64 * 6)()
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
 
     def p(NB, Cin, Cout, H, W, k, s=1):
         assert K_.lib().cutie_conv_plan(ctypes.c_int64(NB), ctypes.c_int64(Cin), ctypes.c_int64(Cout), ctypes.c_int64(H),
-                                        ctypes.c_int64(W), k, s, plan) == 0
-        return tuple(plan)
-    assert p(3, 256, 256, 30, 54, 3) == (15, 112, 1)            # 90 CTAs: no split
-    assert p(1, 256, 256, 30, 54, 3) == (15, 112, 4)            # 30 CTAs x 4 = 120 <= 148, 2 chunks each
-    assert p(1, 1024, 256, 30, 54, 1) == (13, 128, 5)           # 26 CTAs x 5 = 130
-    assert p(1, 64, 256, 120, 216, 1)[2] == 1                   # 406 CTAs
+                                        ctypes.c_int64(W), k, s, 0, plan) == 0
+        return tuple(plan)                                       # T, N, C, q, CTAs, workspace floats
+    T, N, C, q, ctas, ws = p(3, 256, 256, 30, 54, 3)              # PixelFFN: 90 tiles x 8 chunks
+    assert (T, N, C) == (90, 112, 8) and q == -(-720 // sms) and ctas == -(-720 // q) and ctas <= sms and ws > 0
+    T, N, C, q, ctas, ws = p(1, 64, 256, 120, 216, 1)             # 406 tiles: one whole tile per CTA, no workspace
+    assert q == C == 2 and ctas == T == 406 and ws == 0
+    T, N, C, q, ctas, ws = p(1, 1024, 256, 30, 54, 1)
+    assert T == 26 and C == 32 and ctas <= sms and q * ctas >= T * C
 
 
 @pytest.mark.parametrize('NB,Cin,Cout,H,W', [(1, 128, 128, 120, 216), (1, 256, 256, 60, 108), (3, 64, 128, 120, 216),
