@@ -500,8 +500,8 @@ def conv_roofline_bench(dev, iters=40):
     layers = [('PixelFFN / fuser 3x3 256->256 @30x54 x3 objects', 3, 256, 256, 30, 54, 3, False),
               ('sensory update 3x3 512->768 @30x54 x3', 3, 512, 768, 30, 54, 3, False),
               ('decoder 3x3 128->128 @120x216 x3', 3, 128, 128, 120, 216, 3, False),
-              ('ResNet-50 layer3 3x3 256->256 @30x54 (channels-last, split-K)', 1, 256, 256, 30, 54, 3, True),
-              ('ResNet-50 layer3 1x1 1024->256 @30x54 (channels-last, split-K)', 1, 1024, 256, 30, 54, 1, True),
+              ('ResNet-50 layer3 3x3 256->256 @30x54 (channels-last, shared tiles)', 1, 256, 256, 30, 54, 3, True),
+              ('ResNet-50 layer3 1x1 1024->256 @30x54 (channels-last, shared tiles)', 1, 1024, 256, 30, 54, 1, True),
               ('ResNet-50 layer1 1x1 64->256 @120x216 + residual (channels-last)', 1, 64, 256, 120, 216, 1, True)]
     out = []
     g = torch.Generator().manual_seed(5)

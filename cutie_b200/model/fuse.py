@@ -136,7 +136,7 @@ class ConvEpilogueFuser:
             ident = (w.data_ptr(), None)
         hit = self._images.get(id(conv))
         if hit is None or hit[0] != ident:
-            # the layer's operand image and its own split-K tile counters (zero between launches; one layer never runs
+            # the layer's operand image and its own shared-tile counters (zero between launches; one layer never runs
             # twice at the same time, different layers may -- encoder look-ahead -- so counters are never shared)
             hit = (ident, K_.conv_weight_image(w), torch.zeros(8192, dtype=torch.int32, device=w.device))
             self._images[id(conv)] = hit
