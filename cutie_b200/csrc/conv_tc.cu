@@ -233,6 +233,50 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcPara
     }
   };
 
+  // Shared tiles: the CTA that arrived last adds the tile's shares IN SLOT ORDER -- all twelve warps, 16 bytes per lane
+  // (four warps with scalar loads left this on the critical path at ~15 us per tile).  Channels-last outputs are finished
+  // right here; dense-NCHW ones go through the staging buffer (transposed) and store_staged_rows.
+  auto reduce_shares = [&](const ConvPart& P, int sw, bool to_stage) {
+    const int co4 = P.cot * CV_M + 4 * lane;
+    const float* wst = p.ws + (P.tile_lin * p.maxslots) * (long long)(p.N * CV_M) + 4 * lane;
+    float* stage = reinterpret_cast<float*>(smem);
+    const bool co_ok = co4 < p.Cout;
+    const float4 b4 = (!to_stage && p.bias && co_ok) ? __ldg(reinterpret_cast<const float4*>(p.bias + co4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = sw; j < p.N; j += 12) {
+      long long pix = 0;
+      bool ok = true;
+      if (!to_stage) {
+        if (KS == 3) {
+          const int ty = j / TWp, lx = j - ty * TWp;
+          const int gy = P.ty0 + ty, gx = P.tx0 + lx - p.xoff;
+          ok = lx >= p.xoff && lx < p.TW + p.xoff && ty < p.TH && gy < p.H && gx < p.W;
+          pix = (long long)gy * p.W + gx;
+        } else {
+          pix = P.pix0 + j;
+          ok = pix < HW;
+        }
+        if (!ok || !co_ok) continue;
+      }
+      float4 v = __ldcg(reinterpret_cast<const float4*>(wst + (long long)j * CV_M));
+      for (int k = 1; k < P.nslots; ++k) {
+        const float4 t = __ldcg(reinterpret_cast<const float4*>(wst + ((long long)k * p.N + j) * CV_M));
+        v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+      }
+      if (to_stage) {
+        stage[(4 * lane + 0) * LD + j] = v.x; stage[(4 * lane + 1) * LD + j] = v.y;
+        stage[(4 * lane + 2) * LD + j] = v.z; stage[(4 * lane + 3) * LD + j] = v.w;
+      } else {
+        v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+        if (p.z) {
+          const float4 z4 = __ldg(reinterpret_cast<const float4*>(p.z + (long long)P.nb * p.zs_n + pix * p.zs_p + co4));
+          v.x += z4.x; v.y += z4.y; v.z += z4.z; v.w += z4.w;
+        }
+        if (p.relu_out) v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+        *reinterpret_cast<float4*>(p.y + (long long)P.nb * p.ys_n + pix * p.ys_p + co4) = v;
+      }
+    }
+  };
+
   if (warp >= 4 && warp < 12) {
     // ============ activation producers: thread == tile row (1x1: half a row, 16 channels) ============
     const int pt = tid - 128;
@@ -316,11 +360,6 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcPara
           }
         }
       }
-    }
-    for (int pi = 0; pi < nparts; ++pi) {                     // help the epilogue warps store the staged tile(s)
-      asm volatile("bar.sync 2, 384;" ::: "memory");          // tile pi staged (or this CTA does not store it)
-      if (staged && T.last[pi]) store_staged_rows(pi ? part1 : part0, warp);
-      if (pi + 1 < nparts) asm volatile("bar.sync 2, 384;" ::: "memory");   // staging buffer free again
     }
   } else if (warp == 13) {
     // ================================== weight loader ==================================
@@ -441,8 +480,6 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcPara
         finish_group(part0, g, o, ty, lx);
       }
       if (tid == 0) T.last[0] = 1;
-      asm volatile("bar.sync 2, 384;" ::: "memory");
-      if (staged) store_staged_rows(part0, warp);
     } else {
       // ---- shares: partial tile -> workspace [tile][slot][position][channel] (lanes == consecutive channels) ----
       for (int pi = 0; pi < nparts; ++pi) {
@@ -465,33 +502,56 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_tc_kernel(const ConvTcPara
         const ConvPart& P = tid ? part1 : part0;
         T.last[tid] = atomicAdd(p.counters + P.tile_lin, 1) == P.nslots - 1 ? 1 : 0;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      // ---- the CTA that arrives last at a tile adds its shares IN SLOT ORDER and stores the tile ----
-      for (int pi = 0; pi < nparts; ++pi) {
-        const ConvPart& P = pi ? part1 : part0;
-        const bool fin = T.last[pi] != 0;
-        if (fin) {
-          __threadfence();
+    }
+  }
+  // ================================== finish: the twelve epilogue + producer warps ==================================
+  if (warp < 12) {
+    for (int pi = 0; pi < nparts; ++pi) {
+      const ConvPart& P = pi ? part1 : part0;
+      asm volatile("bar.sync 2, 384;" ::: "memory");          // direct: the tile is staged; shares: who stores it is known
+      const bool fin = T.last[pi] != 0;
+      if (!direct && fin) {
+        __threadfence();
+        if (staged_nchw) {
+          reduce_shares(P, warp, true);
+        } else if (p.cl_vec) {
+          reduce_shares(P, warp, false);
+        } else if (warp < 4) {                               // odd layouts: thread == channel, element-wise
           const float* wst = p.ws + (P.tile_lin * p.maxslots) * (long long)(p.N * CV_M);
-          int ty = 0, lx = 0;
-          for (int g = 0; g < p.N; g += 32) {
-            uint32_t o[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) o[j] = 0u;
-            for (int k = 0; k < P.nslots; ++k) {
-              const float* sh = wst + (long long)k * (p.N * CV_M);
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (g + j < p.N) o[j] = __float_as_uint(__uint_as_float(o[j]) + __ldcg(sh + (g + j) * CV_M + tid));
+          const int co = P.cot * CV_M + tid;
+          const float b = (p.bias && co < p.Cout) ? __ldg(p.bias + co) : 0.f;
+          float* yb = p.y + (long long)P.nb * p.ys_n + (long long)co * p.ys_c;
+          const float* zb = p.z ? p.z + (long long)P.nb * p.zs_n + (long long)co * p.zs_c : nullptr;
+          for (int j = 0; j < p.N; ++j) {
+            bool ok;
+            long long pix;
+            if (KS == 3) {
+              const int ty = j / TWp, lx = j - ty * TWp;
+              const int gy = P.ty0 + ty, gx = P.tx0 + lx - p.xoff;
+              ok = lx >= p.xoff && lx < p.TW + p.xoff && ty < p.TH && gy < p.H && gx < p.W;
+              pix = (long long)gy * p.W + gx;
+            } else {
+              pix = P.pix0 + j;
+              ok = pix < HW;
             }
-            finish_group(P, g, o, ty, lx);
+            if (!ok || co >= p.Cout) continue;
+            float val = 0.f;
+            for (int k = 0; k < P.nslots; ++k) val += __ldcg(wst + ((long long)k * p.N + j) * CV_M + tid);
+            val += b;
+            if (zb) val += __ldg(zb + pix * p.zs_p);
+            if (p.relu_out) val = fmaxf(val, 0.f);
+            yb[pix * p.ys_p] = val;
           }
-          if (tid == 0) p.counters[P.tile_lin] = 0;           // ready for the next launch
         }
-        asm volatile("bar.sync 2, 384;" ::: "memory");        // (the producers arrive here once per part)
-        if (fin && staged) store_staged_rows(P, warp);
-        if (pi + 1 < nparts) asm volatile("bar.sync 2, 384;" ::: "memory");   // staging buffer free again
       }
+      if (staged_nchw) {
+        if (!direct) asm volatile("bar.sync 2, 384;" ::: "memory");   // shares added up in the staging buffer
+        if (fin) store_staged_rows(P, warp);
+      } else if (direct && p.cl_vec) {
+        store_staged_rows(P, warp);
+      }
+      if (pi + 1 < nparts) asm volatile("bar.sync 2, 384;" ::: "memory");   // staging buffer free again
+      if (!direct && fin && tid == 0) p.counters[P.tile_lin] = 0;           // ready for the next launch
     }
   }
   tc_fence_before();
@@ -571,10 +631,10 @@ static void conv_tile_shape(int H, int W, int stride, int* TH, int* TW, int* N) 
   }
 }
 
-// Launch plan.  Work = (output tile, input chunk) units, T tiles x C chunks; CTA i owns units [i q, (i + 1) q).  Layers with
-// at least as many output tiles as SMs run one whole tile per CTA (q = C).  Smaller layers are spread evenly over the SMs:
-// q = ceil(T C / SMs) (>= 2 chunks when there are that many), so a CTA's share spans at most two tiles and a tile is shared
-// by at most ceil(C / q) + 1 CTAs, which meet in the workspace.
+// Launch plan.  Work = (output tile, input chunk) units, T tiles x C chunks; CTA i owns units [i q, (i + 1) q) -- any q <= C
+// is valid (a share then spans at most two tiles and a tile is shared by at most ceil(C / q) + 1 CTAs, which meet in the
+// workspace).  Layers with at least as many output tiles as SMs run one whole tile per CTA (q = C); smaller layers split
+// every tile uniformly over input-channel ranges.
 struct ConvPlan { long long tiles, cots, T; int N, C, q, maxslots; long long ctas; int th, tw; };
 static int conv_make_plan(int64_t NB, int64_t Cin, int64_t Cout, int64_t H_in, int64_t W_in, int ksize, int stride, int q_override,
                           ConvPlan* pl) {
@@ -593,11 +653,12 @@ static int conv_make_plan(int64_t NB, int64_t Cin, int64_t Cout, int64_t H_in, i
   pl->T = pl->tiles * pl->cots * NB;
   pl->C = (int)(Cin / CV_KC);
   int q = pl->C;
-  if (pl->T < num_sms()) {
-    q = (int)((pl->T * pl->C + num_sms() - 1) / num_sms());
-    if (q < 2) q = 2;
-    if (q > pl->C) q = pl->C;
-  }
+  // Shares that stay inside one tile (q | C, i.e. a uniform split of every tile) cost one partial-tile round trip through
+  // the workspace; shares that straddle two tiles pay it twice per CTA on the critical path and measured slower than not
+  // sharing at all (scripts/conv_share_sweep.py: 256->256 3x3 x3 objects 65 us whole tiles, 101 us at q = 5), so the plan
+  // only picks divisors of C: the largest split s with CTAs x s <= SMs and at least 2 chunks per CTA.
+  for (int s = 2; s <= 8; ++s)
+    if (pl->C % s == 0 && pl->T * s <= num_sms() && pl->C / s >= 2) q = pl->C / s;
   if (q_override > 0) q = q_override < pl->C ? q_override : pl->C;
   pl->q = q;
   pl->maxslots = (pl->C - 1) / q + 2;

@@ -185,10 +185,11 @@ int cutie_conv_tc(const float* x, const int64_t* x_strides, const void* weight_i
                   int64_t H_in, int64_t W_in, int ksize, int stride, int relu_in, int relu_out, float* y,
                   const int64_t* y_strides, int units_per_cta, float* workspace, int32_t* counters, void* stream);
 /* Launch plan of cutie_conv_tc: out6 = {output tiles T (images x 128-channel tiles x spatial tiles), MMA N, input chunks C per
- * tile, (tile, chunk) units per CTA q, CTAs, workspace floats}.  CTA i owns units [i q, (i + 1) q) of the T x C space: layers
- * with at least as many tiles as SMs run one whole tile per CTA (q = C, no workspace); smaller layers are spread evenly over
- * the SMs (q = ceil(T C / SMs)): a CTA's share spans at most two tiles, the shares of a tile meet in `workspace` and the CTA
- * that arrives last adds them in slot order (deterministic) before the epilogue.  `counters` (T int32) must be zero on entry
+ * tile, (tile, chunk) units per CTA q, CTAs, workspace floats}.  CTA i owns units [i q, (i + 1) q) of the T x C space (any
+ * q <= C is valid: a share spans at most two tiles): layers with at least as many tiles as SMs run one whole tile per CTA
+ * (q = C, no workspace); smaller layers split every tile uniformly over input-channel ranges (q = C / s, the largest s <= 8
+ * with CTAs <= SMs); the shares of a tile meet in `workspace` and the CTA that arrives last adds them in slot order
+ * (deterministic) before the epilogue.  `counters` (T int32) must be zero on entry
  * and are zero again on exit.  units_per_cta = 0: the plan's choice (pass the same value to both calls). */
 int cutie_conv_plan(int64_t NB, int64_t Cin, int64_t Cout, int64_t H_in, int64_t W_in, int ksize, int stride, int units_per_cta,
                     int64_t* out6);

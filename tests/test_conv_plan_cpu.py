@@ -46,8 +46,8 @@ def test_every_unit_is_computed_once_and_slots_are_dense(NB, Cin, Cout, H, W, k,
     assert C == Cin // 32 and 1 <= q <= C and 16 <= N <= 128 and N % 16 == 0
     assert ctas == -(-T * C // q)
     if q_override == 0:
-        assert q == C if T >= SMS else (ctas <= SMS and q == min(C, max(2, -(-T * C // SMS))))
-    assert (ws == 0) == (q == C)
+        assert C % q == 0 and (q == C or (ctas <= SMS and q >= 2))     # uniform splits only, never more CTAs than SMs
+    assert (ws == 0) == (q >= C)
     maxslots = ws // (T * N * 128) if ws else 1
     seen = {}
     slots = {}

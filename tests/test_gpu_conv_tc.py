@@ -229,11 +229,11 @@ def test_conv_plan_spreads_small_layers_over_the_sms():
                                         ctypes.c_int64(W), k, s, 0, plan) == 0
         return tuple(plan)                                       # T, N, C, q, CTAs, workspace floats
     T, N, C, q, ctas, ws = p(3, 256, 256, 30, 54, 3)              # PixelFFN: 90 tiles x 8 chunks
-    assert (T, N, C) == (90, 112, 8) and q == -(-720 // sms) and ctas == -(-720 // q) and ctas <= sms and ws > 0
+    assert (T, N, C) == (90, 112, 8) and q == 8 and ctas == 90 and ws == 0          # 90 x 2 > SMs: whole tiles
     T, N, C, q, ctas, ws = p(1, 64, 256, 120, 216, 1)             # 406 tiles: one whole tile per CTA, no workspace
     assert q == C == 2 and ctas == T == 406 and ws == 0
     T, N, C, q, ctas, ws = p(1, 1024, 256, 30, 54, 1)
-    assert T == 26 and C == 32 and ctas <= sms and q * ctas >= T * C
+    assert T == 26 and C == 32 and ctas <= sms and q * ctas >= T * C and C % q == 0 and ws > 0
 
 
 @pytest.mark.parametrize('NB,Cin,Cout,H,W', [(1, 128, 128, 120, 216), (1, 256, 256, 60, 108), (3, 64, 128, 120, 216),
