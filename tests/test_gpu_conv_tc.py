@@ -8,6 +8,15 @@ import torch.nn.functional as F
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600, method='thread')]
 
 
+@pytest.fixture(autouse=True)
+def _restore_cudnn_flags():
+    """The timing tests switch cudnn.benchmark on for the library's side of the comparison: never leak it into later tests
+    (the reference-comparison tests need the library convolutions of both sides to pick the same algorithms)."""
+    bench, tf32 = torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32
+    yield
+    torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32 = bench, tf32
+
+
 def _ref64(x, w, b, z, relu_in, relu_out):
     xx = x.double()
     if relu_in:

@@ -83,9 +83,11 @@ def test_stream_on_the_tcgen05_plan_is_bit_identical_to_the_exact_scan_plan(K_, 
         assert torch.equal(a, b), f'{name}: frame {ti + 1} differs by {float((a - b).abs().max()):.3e}'
 
 
-def test_teacher_forced_frame_from_a_prefilled_ring_after_the_wrap(K_):
+@pytest.mark.parametrize('optimised', [False, True])
+def test_teacher_forced_frame_from_a_prefilled_ring_after_the_wrap(K_, optimised):
     """>= 8k pre-filled tokens + real memory frames on top until the ring has wrapped and evicted, then ONE frame against
-    the CPU oracle from the exported live state (near-tied top-k members / foreground pixels reconciled vs float64)."""
+    the CPU oracle from the exported live state (near-tied top-k members / foreground pixels reconciled vs float64).
+    optimised: the product configuration -- optimize_for_inference(): BN folded, 3x3 / 1x1 convolutions on cutie_conv_tc."""
     from cutie_b200.config import default_config
     from oracle.cpu_core import OracleCore
     from oracle.state_sync import ForegroundReconciler, SelectionReconciler, export_state_to_oracle
@@ -96,6 +98,8 @@ def test_teacher_forced_frame_from_a_prefilled_ring_after_the_wrap(K_):
     HW, frames_in_bank = 405, 24
     cfg = default_config(mem_every=2, max_mem_frames=frames_in_bank)
     net = _net(cfg)
+    if optimised:
+        net.optimize_for_inference()
     T = 15
     frames, mask = synthetic_video(T + 1, 240, 432, 3, seed=9)
     g = torch.Generator().manual_seed(1)
@@ -131,7 +135,10 @@ def test_teacher_forced_frame_from_a_prefilled_ring_after_the_wrap(K_):
     finally:
         K_.affinity_topk, K_.qt_aux_mask = orig, orig_aux
     d = float((proc.last_logits.cpu() - oc.last_logits).abs().max())
-    print(f'teacher-forced frame on the hot plan ({proc.memory.work_mem.size(0)} tokens): max |logit diff| = {d:.3e}, '
+    if optimised:
+        rep = net.conv_epilogues.report()['layers']
+        assert rep.get('tc', 0) >= 80, rep                                  # the tensor-core convolutions really ran
+    print(f'teacher-forced frame on the hot plan (optimised={optimised}, {proc.memory.work_mem.size(0)} tokens): max |logit diff| = {d:.3e}, '
           f'{rec.flips} near-tied selections, {fgr.flips} near-tied foreground pixels')
     assert d < 1e-3, d
 

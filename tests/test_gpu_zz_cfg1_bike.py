@@ -142,6 +142,12 @@ def test_cuda_path_state_synced_to_the_gpu_reference(graphs):
     from tests.state_sync import load_state_from_oracle
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
+    # both sides run the SAME library convolutions here (the model is not optimize_for_inference()'d): with cuDNN's autotuner
+    # off they pick the same algorithms, so keys and queries are bit-identical and what is compared is the replaced path.
+    # (Any other convolution arithmetic -- the autotuner's pick, or cutie_conv_tc, which is closer to float64 than either --
+    # flips near-tied top-k members on some frames: the network's sensitivity the attribution test documents, covered for
+    # the optimised configuration by the reconciled oracle comparisons in test_gpu_e2e*.py and bench.py's parity_check.)
+    torch.backends.cudnn.benchmark = False
     g = np.load(os.path.join(GOLDEN, 'cfg1_bike.npz'))
     frames, mask, objects = _inputs(g)
     cfg, net = _net()
@@ -177,6 +183,7 @@ def test_cuda_path_free_running_on_the_bike_example(graphs):
     CPU between the oracle and the reference: 1e-5 -> 4e-2 -> 1.6, traced to ONE foreground-map pixel)."""
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = False           # same library algorithms as the reference child (see the state-synced test)
     g = np.load(os.path.join(GOLDEN, 'cfg1_bike.npz'))
     frames, mask, objects = _inputs(g)
     exact = _reference_on_this_gpu(frames, mask, objects, exact_similarity=True)
