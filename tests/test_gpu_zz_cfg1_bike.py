@@ -100,6 +100,17 @@ def _reference_on_this_gpu(frames, mask, objects, exact_similarity=False):
     return _REF_GPU[key]
 
 
+def _like_a_fresh_process():
+    """cuDNN's heuristics rank engines by the workspace they may use, and PyTorch offers them what the caching allocator can
+    still get: after a long test session (banks of 400k tokens, 40 MB feature maps) the library convolutions of THIS process
+    can pick other engines than the reference child's fresh process does -- different rounding in the encoder, i.e. flipped
+    near-tied top-k members (the sensitivity the attribution test documents).  Give the allocator's cache back first."""
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+
+
 def _per_frame(a, b):
     return [float((x - y).abs().max()) for x, y in zip(a, b)]
 
@@ -148,6 +159,7 @@ def test_cuda_path_state_synced_to_the_gpu_reference(graphs):
     # flips near-tied top-k members on some frames: the network's sensitivity the attribution test documents, covered for
     # the optimised configuration by the reconciled oracle comparisons in test_gpu_e2e*.py and bench.py's parity_check.)
     torch.backends.cudnn.benchmark = False
+    _like_a_fresh_process()
     g = np.load(os.path.join(GOLDEN, 'cfg1_bike.npz'))
     frames, mask, objects = _inputs(g)
     cfg, net = _net()
@@ -184,6 +196,7 @@ def test_cuda_path_free_running_on_the_bike_example(graphs):
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.benchmark = False           # same library algorithms as the reference child (see the state-synced test)
+    _like_a_fresh_process()
     g = np.load(os.path.join(GOLDEN, 'cfg1_bike.npz'))
     frames, mask, objects = _inputs(g)
     exact = _reference_on_this_gpu(frames, mask, objects, exact_similarity=True)
