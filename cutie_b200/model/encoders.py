@@ -59,7 +59,15 @@ class KeyProjection(nn.Module):
 
     def forward(self, f16, *, need_s: bool, need_e: bool):
         x = self.pix_feat_proj(f16)
-        shrinkage = self.d_proj(x).square() + 1 if need_s else None
+        shrinkage = None
+        if need_s:
+            t = getattr(self, 'glue_dispatch', None)
+            if t is None:
+                d = self.d_proj(x)
+            else:   # 3x3 with ONE output channel: cutie_conv3x3_c1 (cuDNN: a 143 us GEMM with N = 1 at 480p)
+                d = t('pred_conv3x3', (tuple(x.shape),), lambda: self.d_proj(x),
+                      lambda trial: K_.conv3x3_c1(x.contiguous(), self.d_proj.weight, self.d_proj.bias), x)
+            shrinkage = d.square() + 1
         selection = torch.sigmoid(self.e_proj(x)) if need_e else None
         return self.key_proj(x), shrinkage, selection
 
