@@ -24,13 +24,29 @@ static inline float __fadd_rn(float a, float b) { volatile float r = a + b; retu
 static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 static inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
 
-// serial launch: EMU_LAUNCH(kernel<...>, grid, block, args...)
+// Block-shared memory and one barrier: `__shared__` arrays become statics that persist between the serial thread calls,
+// and a kernel whose threads meet at ONE __syncthreads() is run in two passes per block -- pass 0 stops every thread at
+// the barrier (all shared-memory writes before it have then happened), pass 1 re-runs every thread from the top (the part
+// before the barrier must be idempotent: it recomputes and rewrites the same shared values) and continues past it.
+// Barrier-free kernels never set `emu_barrier_hit` and run once (in-place kernels must not run twice).
+static int emu_pass = 0;
+static bool emu_barrier_hit = false;
+#define __shared__ static
+#define __syncthreads() do { if (emu_pass == 0) { emu_barrier_hit = true; return; } } while (0)
+
+// serial launch: EMU_LAUNCH(kernel<...>, grid, block, args...); grid may be 1-, 2- or 3-dimensional, blocks 1-dimensional
 #define EMU_LAUNCH(kern, grid, block, ...)                                   \
   do {                                                                       \
     gridDim = dim3(grid); blockDim = dim3(block);                            \
-    for (unsigned bx = 0; bx < gridDim.x; ++bx)                              \
-      for (unsigned tx = 0; tx < blockDim.x; ++tx) {                         \
-        blockIdx = dim3(bx); threadIdx = dim3(tx);                           \
-        kern(__VA_ARGS__);                                                   \
-      }                                                                      \
+    for (unsigned bz = 0; bz < gridDim.z; ++bz)                              \
+      for (unsigned by = 0; by < gridDim.y; ++by)                            \
+        for (unsigned bx = 0; bx < gridDim.x; ++bx) {                        \
+          emu_barrier_hit = false;                                           \
+          for (emu_pass = 0; emu_pass < (emu_barrier_hit ? 2 : 1); ++emu_pass) \
+            for (unsigned tx = 0; tx < blockDim.x; ++tx) {                   \
+              blockIdx = dim3(bx, by, bz); threadIdx = dim3(tx, 0, 0);       \
+              kern(__VA_ARGS__);                                             \
+            }                                                                \
+          emu_pass = 0;                                                      \
+        }                                                                    \
   } while (0)

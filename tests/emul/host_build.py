@@ -1,6 +1,7 @@
-"""Test-only: compile csrc/pixel.cu for the HOST.  Every kernel in that file is barrier-free and uses no shared memory,
-so `kernel<<<grid, block, smem, stream>>>(args)` can be rewritten textually into a serial loop over (block, thread)
-(cuda_serial_shim.h) and the whole translation unit -- kernels AND the extern "C" dispatchers (vector / scalar path
+"""Test-only: compile csrc/pixel.cu for the HOST.  The kernels in that file are barrier-free or meet at a single
+__syncthreads() after an idempotent first half (conv3x3_c1's partial sums), so `kernel<<<grid, block, smem, stream>>>(args)`
+can be rewritten textually into a serial loop over (block, thread) -- two passes per block for the one-barrier kernels
+(cuda_serial_shim.h) -- and the whole translation unit -- kernels AND the extern "C" dispatchers (vector / scalar path
 selection, grid sizing, argument checks) -- builds with g++.  The resulting library exports the same C-ABI symbols as
 libcutie_b200.so for those entry points, so the real ctypes wrappers in cutie_b200/kernels.py can be driven on CPU
 tensors (tests/test_pixel_wrappers_on_host.py)."""
