@@ -94,6 +94,8 @@ struct ConsParams {
   float* out_shr;
   long long out_shr_bs;
   float* ws;  // [B][P][n_total]
+  float* out_max;   // optional [B][P]: the softmax's max over the candidates (the per-shard affinity maximum of the sharded path)
+  float* out_sum;   // optional [B][P]: sum_n exp(S[n,p] - max)
 };
 
 __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) {
@@ -175,6 +177,10 @@ __global__ void __launch_bounds__(256) consolidate_kernel(const ConsParams p) {
     if (tid == 0) {
       inv_sum[pp] = 1.f / se;
       p.out_shr[(long long)b * p.out_shr_bs + p0 + pp] = ss / se;
+      if (p.out_max) {
+        p.out_max[(long long)b * p.P + p0 + pp] = mx;
+        p.out_sum[(long long)b * p.P + p0 + pp] = se;
+      }
     }
   }
   __syncthreads();
@@ -266,13 +272,16 @@ extern "C" int cutie_bank_gather(int num_segments, const void* const* seg_rows, 
   return 0;
 }
 
-extern "C" int cutie_consolidate(int num_segments, const void* const* seg_key, const void* const* seg_shrinkage,
-                                 const int64_t* seg_len, const int64_t* seg_key_bstride,
-                                 const int64_t* seg_shr_bstride, const void* const* seg_val,
-                                 const int64_t* seg_val_bstride, int64_t K, const float* proto_key, int64_t pk_bstride,
-                                 const float* proto_sel, int64_t ps_bstride, int64_t B, int64_t P, int64_t CK,
-                                 int64_t CV, void* const* out_val, const int64_t* out_val_bstride, float* out_shr,
-                                 int64_t out_shr_bstride, float* workspace, int64_t n_total, void* stream) {
+extern "C" int cutie_consolidate_partial(int num_segments, const void* const* seg_key, const void* const* seg_shrinkage,
+                                         const int64_t* seg_len, const int64_t* seg_key_bstride,
+                                         const int64_t* seg_shr_bstride, const void* const* seg_val,
+                                         const int64_t* seg_val_bstride, int64_t K, const float* proto_key,
+                                         int64_t pk_bstride, const float* proto_sel, int64_t ps_bstride, int64_t B,
+                                         int64_t P, int64_t CK, int64_t CV, void* const* out_val,
+                                         const int64_t* out_val_bstride, float* out_shr, int64_t out_shr_bstride,
+                                         float* out_max, float* out_sumexp, float* workspace, int64_t n_total,
+                                         void* stream) {
+  CUTIE_REQUIRE((out_max == nullptr) == (out_sumexp == nullptr), "out_max and out_sumexp come together");
   CUTIE_REQUIRE(num_segments >= 1 && num_segments <= kMaxSeg, "1..4 segments");
   CUTIE_REQUIRE(CK == 64, "CK must be 64");
   CUTIE_REQUIRE(K >= 0 && K <= 16, "0..16 objects");
@@ -312,10 +321,24 @@ extern "C" int cutie_consolidate(int num_segments, const void* const* seg_key, c
   cp.out_shr = out_shr;
   cp.out_shr_bs = out_shr_bstride;
   cp.ws = workspace;
+  cp.out_max = out_max;
+  cp.out_sum = out_sumexp;
   dim3 grid((unsigned)((P + PT - 1) / PT), (unsigned)B);
   consolidate_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(cp);
   CUTIE_CHECK_LAUNCH();
   return 0;
+}
+
+extern "C" int cutie_consolidate(int num_segments, const void* const* seg_key, const void* const* seg_shrinkage,
+                                 const int64_t* seg_len, const int64_t* seg_key_bstride,
+                                 const int64_t* seg_shr_bstride, const void* const* seg_val,
+                                 const int64_t* seg_val_bstride, int64_t K, const float* proto_key, int64_t pk_bstride,
+                                 const float* proto_sel, int64_t ps_bstride, int64_t B, int64_t P, int64_t CK,
+                                 int64_t CV, void* const* out_val, const int64_t* out_val_bstride, float* out_shr,
+                                 int64_t out_shr_bstride, float* workspace, int64_t n_total, void* stream) {
+  return cutie_consolidate_partial(num_segments, seg_key, seg_shrinkage, seg_len, seg_key_bstride, seg_shr_bstride, seg_val,
+                                   seg_val_bstride, K, proto_key, pk_bstride, proto_sel, ps_bstride, B, P, CK, CV, out_val,
+                                   out_val_bstride, out_shr, out_shr_bstride, nullptr, nullptr, workspace, n_total, stream);
 }
 
 extern "C" int cutie_obj_summary_accumulate(float* acc, const float* add, int64_t n, void* stream) {

@@ -402,6 +402,21 @@ class KeyValueMemoryStore:
         arena.generation += 1                # tokens re-ordered by usage: remembered indices are void
         arena.dirty = [(0, max_size)]
 
+    def replace_temp_rows(self, bucket_id: int, rows: Dict[object, torch.Tensor]) -> None:
+        """Replace the whole temporary region of a linear (long-term) bucket by `rows` (name -> [B, n, C] or [B, n]): the
+        key-sharded form of remove_obsolete_features, whose survivors arrive from other ranks."""
+        bk = self._b[bucket_id]
+        arena = bk.temp
+        assert not arena.ring and set(rows) == set(arena.widths)
+        n = next(iter(rows.values())).shape[1]
+        for name, t in rows.items():
+            dst = torch.zeros_like(arena.arrays[name])
+            dst[:, :n] = t
+            arena.arrays[name] = dst
+        arena.count = n
+        arena.generation += 1
+        arena.dirty = [(0, n)] if n else []
+
     # -- object removal (kv:280-307) ---------------------------------------------------------
     def purge_except(self, obj_keep_idx: List[int]) -> None:
         keep = set(obj_keep_idx)

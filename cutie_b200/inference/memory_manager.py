@@ -25,19 +25,21 @@ log = logging.getLogger()
 
 class MemoryManager:
     def __init__(self, cfg, object_manager: ObjectManager, *, shard_group=None):
-        """shard_group (a torch.distributed process group, or None): key-shard THIS stream's working memory over the
-        group's ranks.  Every rank runs the same frames through the same model; each stores the
-        slice shard_bounds(HW, world, rank) of every memory frame's tokens and the read exchanges top-k candidates
-        (all_gather) and partial readouts (all_reduce) -- cutie_b200/inference/sharded.py."""
+        """shard_group (a torch.distributed process group, or None): key-shard THIS stream's memory over the group's
+        ranks.  Every rank runs the same frames through the same model; each stores the slice
+        shard_bounds(HW, world, rank) of every memory frame's tokens and the read exchanges top-k candidates
+        (all_gather) and partial readouts (all_reduce) -- cutie_b200/inference/sharded.py.  With use_long_term the
+        long-term store is sharded too: prototypes are chosen by a global usage ranking, potentiated shard-wise (all_gather
+        of the per-shard affinity maxima and exp-sums) and dealt to the ranks in contiguous blocks of that ranking."""
         self.object_manager = object_manager
         self.shard_group = shard_group
         self.shard_world, self.shard_rank = 1, 0
         if shard_group is not None:
             import torch.distributed as dist
             self.shard_world, self.shard_rank = dist.get_world_size(shard_group), dist.get_rank(shard_group)
-            if cfg.use_long_term:
-                raise NotImplementedError('key-sharded memory covers the FIFO working memory; long-term prototype '
-                                          'selection ranks usage globally and is not sharded yet')
+            if cfg.use_long_term and cfg.long_term.num_prototypes < self.shard_world:
+                raise ValueError(f'{cfg.long_term.num_prototypes} prototypes per consolidation cannot be dealt to '
+                                 f'{self.shard_world} ranks (every rank stores at least one)')
         self.sensory_dim = cfg.model.sensory_dim
         self.top_k = cfg.top_k
         self.chunk_size = cfg.chunk_size
@@ -59,6 +61,9 @@ class MemoryManager:
         self.engaged = False
         self.aux = None
         self._prev_topk = {}           # bucket -> (idx of the last read, layout tag): threshold seeds of the next read
+        # key-sharded long-term memory: bucket -> long-term tokens held by EVERY rank (a deterministic function of the
+        # consolidations / removals so far: no collective is needed to place a rank's tokens in the global index space)
+        self._long_counts: Dict[int, List[int]] = {}
 
     def _read_sizes(self, cfg):
         # the first frame lives in permanent memory and is not counted (memory_manager.py:27-38)
@@ -95,14 +100,26 @@ class MemoryManager:
         """Affinity -> top-k -> softmax (+ usage commits) for one bucket.  Returns gather(objects) -> [B,K,CV,Q]."""
         bs = qk.shape[0]
         if self.shard_group is not None:
-            from cutie_b200.inference.sharded import sharded_gather, sharded_topk
+            from cutie_b200.inference.sharded import shard_bounds, sharded_gather, sharded_topk
             key_segs = self._segments(bucket_id, [])
             n_local = sum(s.n for s in key_segs)
-            frames, rem = divmod(n_local, self.HW)             # self.HW is the LOCAL tokens per frame here
+            long_all = self._long_counts.get(bucket_id, [0] * self.shard_world)
+            long_n = long_all[self.shard_rank]
+            frames, rem = divmod(n_local - long_n, self.HW)    # self.HW is the LOCAL tokens per frame here
             assert rem == 0 and frames >= 1
-            n_total = frames * self.HW_global
-            idx_l, w_l, _, _ = sharded_topk(key_segs, frames * self.shard_begin, n_total, qk, qe, self.top_k,
-                                            self.shard_group)
+            # global index space = the ranks' local banks (long-term | permanent | temporary) one after the other
+            per_rank = [long_all[r] + frames * (lambda be: be[1] - be[0])(shard_bounds(self.HW_global, self.shard_world, r))
+                        for r in range(self.shard_world)]
+            assert per_rank[self.shard_rank] == n_local
+            usage_acc = None
+            if self.use_long_term:
+                usage_acc = torch.zeros(bs, n_local, dtype=torch.int64, device=qk.device)
+            idx_l, w_l, _, _ = sharded_topk(key_segs, sum(per_rank[:self.shard_rank]), sum(per_rank), qk, qe, self.top_k,
+                                            self.shard_group, usage_acc_local=usage_acc)
+            if self.use_long_term:
+                self.work_mem.update_bucket_usage(bucket_id, usage_acc, long_n + self.work_mem.perm_size(bucket_id))
+                if long_n and self.count_long_term_usage:
+                    self.long_mem.update_bucket_usage(bucket_id, usage_acc, 0)
             return lambda objects: sharded_gather(idx_l, w_l, self._segments(bucket_id, objects), self.shard_group)
         long_n = self.long_mem.size(bucket_id) if (self.use_long_term and self.long_mem.engaged(bucket_id)) else 0
         key_segs = self._segments(bucket_id, [])
@@ -255,9 +272,16 @@ class MemoryManager:
         for bucket_id in self.work_mem.buckets.keys():
             if self.use_long_term:
                 if self.work_mem.non_perm_size(bucket_id) >= self.max_work_tokens:
-                    if self.long_mem.non_perm_size(bucket_id) >= (self.max_long_tokens - self.num_prototypes):
-                        self.long_mem.remove_obsolete_features(
-                            bucket_id, self.max_long_tokens - self.num_prototypes - self.buffer_tokens)
+                    # long-term sizes are GLOBAL token counts (sharded: the sum over the ranks; every rank takes the
+                    # same branch, the branches contain collectives)
+                    long_size = (sum(self._long_counts.get(bucket_id, [0])) if self.shard_group is not None
+                                 else self.long_mem.non_perm_size(bucket_id))
+                    if long_size >= (self.max_long_tokens - self.num_prototypes):
+                        keep = self.max_long_tokens - self.num_prototypes - self.buffer_tokens
+                        if self.shard_group is not None:
+                            self._remove_obsolete_sharded(bucket_id, keep)
+                        else:
+                            self.long_mem.remove_obsolete_features(bucket_id, keep)
                     self.compress_features(bucket_id)
             else:
                 self.work_mem.remove_old_memory(bucket_id, self.max_work_tokens)
@@ -268,6 +292,7 @@ class MemoryManager:
         self.work_mem.purge_except(obj_keep_idx)
         if self.use_long_term and self.long_mem.engaged():
             self.long_mem.purge_except(obj_keep_idx)
+            self._long_counts = {b: c for b, c in self._long_counts.items() if self.long_mem.engaged(b)}
         self.sensory = {k: v for k, v in self.sensory.items() if k in obj_keep_idx}
         if not self.work_mem.engaged():
             self.engaged = False
@@ -283,6 +308,8 @@ class MemoryManager:
         """Candidates = the n_cand oldest temporary working tokens.  Prototypes = the num_prototypes most
         used candidates (:339); their values/shrinkage are the dense-softmax readout of all candidates
         (:348-356).  Results are written straight into new long-term arena slots."""
+        if self.shard_group is not None:
+            return self._consolidation_sharded(bucket_id, n_cand)
         objs = self.work_mem.buckets[bucket_id]
         arena, runs = self.work_mem.temp_runs(bucket_id, 0, n_cand)
         bs = arena.B
@@ -300,6 +327,59 @@ class MemoryManager:
         cand = self.work_mem.segments(bucket_id, objs, perm=False, temp_start=0, temp_len=n_cand)
         K_.consolidate(cand, larena.view('key', lrun), proto_sel,
                        [larena.view(('val', o), lrun) for o in objs], larena.view('shr', lrun))
+
+    # -- the same, key-sharded (cutie_b200/inference/sharded.py) ---------------------------------------
+    def _consolidation_sharded(self, bucket_id: int, n_cand: int) -> None:
+        """consolidation() with the candidates spread over the ranks (n_cand = this rank's share of them).  Prototypes =
+        the global top-P of usage (select_top); their keys / selections are fetched from the owning ranks; every rank
+        potentiates against ITS candidates (cutie_consolidate_partial) and the shards' results are combined through an
+        all_gather of the per-shard affinity maxima and exp-sums (combine_partial_softmax).  Prototype j of the global
+        ranking is stored by the rank whose block shard_bounds(P, world, rank) holds j."""
+        from cutie_b200.inference import sharded as S
+        g, world, rank = self.shard_group, self.shard_world, self.shard_rank
+        objs = self.work_mem.buckets[bucket_id]
+        arena, runs = self.work_mem.temp_runs(bucket_id, 0, n_cand)
+        bs, dev, P, CK, CV = arena.B, arena.device, self.num_prototypes, self.CK, self.CV
+        use = torch.cat([arena.view('use', r) for r in runs], 1)
+        life = torch.cat([arena.view('life', r) for r in runs], 1)
+        src_rank, src_idx = S.select_top(use / life, P, g)
+        proto_key = S.fetch_rows([arena.view('key', r) for r in runs], src_rank, src_idx, g)
+        proto_sel = S.fetch_rows([arena.view('sel', r) for r in runs], src_rank, src_idx, g)
+        cand = self.work_mem.segments(bucket_id, objs, perm=False, temp_start=0, temp_len=n_cand)
+        vals = [torch.empty(bs, P, CV, dtype=torch.float32, device=dev) for _ in objs]
+        shr = torch.empty(bs, P, dtype=torch.float32, device=dev)
+        mx, se = torch.empty(bs, P, device=dev), torch.empty(bs, P, device=dev)
+        K_.consolidate(cand, proto_key, proto_sel, vals, shr, stats=(mx, se))
+        full = S.combine_partial_softmax(torch.cat(vals + [shr.unsqueeze(-1)], dim=-1), mx, se, g)
+        lo, hi = S.shard_bounds(P, world, rank)
+        (_, larena, lruns, _), = self.long_mem.slots_for_add(objs, hi - lo, bs, CK, CV, dev, supposed_bucket_id=bucket_id)
+        (lrun,) = lruns
+        larena.view('key', lrun).copy_(proto_key[:, lo:hi])
+        for i, o in enumerate(objs):
+            larena.view(('val', o), lrun).copy_(full[:, lo:hi, i * CV:(i + 1) * CV])
+        larena.view('shr', lrun).copy_(full[:, lo:hi, -1])
+        counts = self._long_counts.setdefault(bucket_id, [0] * world)
+        for r in range(world):
+            b, e = S.shard_bounds(P, world, r)
+            counts[r] += e - b
+        assert counts[rank] == self.long_mem.non_perm_size(bucket_id)
+
+    def _remove_obsolete_sharded(self, bucket_id: int, max_size: int) -> None:
+        """KeyValueMemoryStore.remove_obsolete_features (kv_memory_store.py:209-242) over the ranks: the max_size most used
+        long-term tokens of ALL ranks survive, in descending-usage order, and rank r keeps block
+        shard_bounds(max_size, world, r) of that ranking (so every rank and every batch entry holds the same count)."""
+        from cutie_b200.inference import sharded as S
+        g, world, rank = self.shard_group, self.shard_world, self.shard_rank
+        src_rank, src_idx = S.select_top(self.long_mem.get_usage(bucket_id), max_size, g)
+        lo, hi = S.shard_bounds(max_size, world, rank)
+        arena, runs = self.long_mem.temp_runs(bucket_id)
+        fresh = {}
+        for name, width in arena.widths.items():
+            rows = [arena.view(name, r) if width else arena.view(name, r).unsqueeze(-1) for r in runs]
+            got = S.fetch_rows(rows, src_rank, src_idx, g)[:, lo:hi]
+            fresh[name] = got if width else got.squeeze(-1)
+        self.long_mem.replace_temp_rows(bucket_id, fresh)
+        self._long_counts[bucket_id] = [(lambda be: be[1] - be[0])(S.shard_bounds(max_size, world, r)) for r in range(world)]
 
     # -- sensory memory ------------------------------------------------------------------------------
     def initialize_sensory_if_needed(self, sample_key: torch.Tensor, ids: List[int]):
@@ -319,6 +399,7 @@ class MemoryManager:
         self.work_mem.clear_non_permanent_memory()
         if self.use_long_term:
             self.long_mem.clear_non_permanent_memory()
+            self._long_counts.clear()
 
     def clear_sensory_memory(self):
         self.sensory = {}

@@ -12,6 +12,17 @@ One exchange step:
 Usage counters stay with the owning shard.  The result equals the single-GPU read of the concatenated bank
 (ties resolve to the lower GLOBAL index because candidates carry global indices).  The reference has no
 multi-GPU inference path; this is new functionality named by BASELINE.json's north_star.
+
+Long-term memory under key sharding (memory_manager.py:283-358, kv_memory_store.py:209-242) adds three exchanges, all
+on memory frames only:
+
+    prototype selection   global top-P of usage = top-P of the all-gathered local top-P lists           (select_top)
+    potentiation          every shard runs the dense softmax over ITS candidates against all P prototypes
+                          (cutie_consolidate_partial) and returns its affinity maximum and exp-sum per prototype;
+                          NCCL all_gather of those per-shard maxima / sums -> each shard's exact softmax share ->
+                          all_reduce(sum) of the re-weighted partial prototypes                         (combine_partial_softmax)
+    obsolete removal      global top-max_size of the long-term usage, survivors re-dealt to the ranks in contiguous
+                          blocks of the global ranking (balanced, and identical for every batch entry)   (fetch_rows)
 """
 from typing import Optional, Sequence
 
@@ -91,3 +102,73 @@ def sharded_read(local_segments: Sequence[BankSegment], index_offset: int, n_tot
     idx_local, w_local, idx, w = sharded_topk(local_segments, index_offset, n_total, qk, qe, top_k, group,
                                               usage_acc_local)
     return sharded_gather(idx_local, w_local, local_segments, group), idx, w
+
+
+# ---- long-term memory under key sharding ---------------------------------------------------------------------------
+
+def select_top(values_local: torch.Tensor, k: int, group=None):
+    """Global top-k of a per-token score sharded over the group.  values_local [B, n_local] (n_local may differ between
+    ranks, may be 0).  Returns (src_rank [B,k], src_idx [B,k]) int64, identical on every rank, in descending order of the
+    score; ties resolve to the lower rank, then to the local top-k order.  One all_gather of the local top-k lists
+    (the global top-k is a subset of their union)."""
+    world = dist.get_world_size(group)
+    B, n_local = values_local.shape
+    dev = values_local.device
+    k_loc = min(k, n_local)
+    v = torch.full((B, k), float('-inf'), dtype=torch.float32, device=dev)
+    i = torch.full((B, k), -1, dtype=torch.int64, device=dev)
+    if k_loc > 0:
+        tv, ti = torch.topk(values_local, k=k_loc, dim=1, sorted=True)
+        v[:, :k_loc], i[:, :k_loc] = tv, ti
+    all_v = torch.empty(world * B, k, dtype=torch.float32, device=dev)
+    all_i = torch.empty(world * B, k, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_v, v, group=group)
+    dist.all_gather_into_tensor(all_i, i, group=group)
+    flat_v = all_v.view(world, B, k).permute(1, 0, 2).reshape(B, world * k)
+    flat_i = all_i.view(world, B, k).permute(1, 0, 2).reshape(B, world * k)
+    order = torch.sort(flat_v, dim=1, descending=True, stable=True)[1][:, :k]
+    src_idx = flat_i.gather(1, order)
+    if bool((src_idx < 0).any()):
+        raise ValueError(f'fewer than {k} tokens over all shards')
+    return order // k, src_idx
+
+
+def fetch_rows(rows_local: Sequence[torch.Tensor], src_rank: torch.Tensor, src_idx: torch.Tensor, group=None) -> torch.Tensor:
+    """out[b, j, :] = the row src_idx[b, j] of rank src_rank[b, j]'s concatenated `rows_local` ([B, n_i, C] token-major
+    runs), on every rank: each rank gathers the rows it owns into a zero tensor, all_reduce(sum) -- exact, every row has
+    one non-zero contributor."""
+    rank = dist.get_rank(group)
+    B, m = src_rank.shape
+    mine = src_rank == rank
+    C = rows_local[0].shape[2] if rows_local else None
+    if C is None:
+        raise ValueError('fetch_rows needs the row width: pass at least one (possibly empty) run')
+    dev = src_rank.device
+    out = torch.zeros(B, m, C, dtype=torch.float32, device=dev)
+    runs = [r for r in rows_local if r.shape[1] > 0]
+    if runs and bool(mine.any()):
+        got = torch.empty(B, m, C, dtype=torch.float32, device=dev)
+        K_.bank_gather(runs, torch.where(mine, src_idx, torch.zeros_like(src_idx)).contiguous(), got)
+        out = torch.where(mine.unsqueeze(-1), got, out)
+    dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+    return out
+
+
+def combine_partial_softmax(partial: torch.Tensor, local_max: torch.Tensor, local_sumexp: torch.Tensor, group=None) -> torch.Tensor:
+    """partial [B, P, C]: softmax-weighted sums over THIS shard's candidates, normalised by the shard's own statistics
+    local_max / local_sumexp [B, P] (cutie_consolidate_partial).  Returns the sums under the softmax over ALL shards'
+    candidates (memory_utils.py:68-71 evaluated shard-wise): all_gather of the per-shard affinity maxima and exp-sums,
+    share_r = sumexp_r exp(max_r - M) / sum_r' sumexp_r' exp(max_r' - M), then all_reduce(sum) of share_r * partial_r."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    B, P = local_max.shape
+    stats = torch.stack([local_max, local_sumexp], dim=-1).contiguous()
+    all_stats = torch.empty(world * B, P, 2, dtype=torch.float32, device=stats.device)
+    dist.all_gather_into_tensor(all_stats, stats, group=group)
+    all_stats = all_stats.view(world, B, P, 2)
+    mx, se = all_stats[..., 0], all_stats[..., 1]
+    big = mx.max(dim=0, keepdim=True)[0]
+    share = se * torch.exp(mx - big)
+    share = share / share.sum(dim=0, keepdim=True)
+    out = (partial * share[rank].unsqueeze(-1)).contiguous()
+    dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+    return out

@@ -639,11 +639,14 @@ def bank_gather(segments_rows: Sequence[torch.Tensor], index: torch.Tensor, dst_
 
 
 def consolidate(segments: Sequence[BankSegment], proto_key: torch.Tensor, proto_sel: torch.Tensor,
-                out_values: Sequence[torch.Tensor], out_shrinkage: torch.Tensor):
+                out_values: Sequence[torch.Tensor], out_shrinkage: torch.Tensor,
+                stats: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
     """Potentiation (memory_manager.py:345-356): dense max-subtracted softmax over all candidate tokens
     of `segments` for each prototype, then weighted sums of candidate values and shrinkage.
 
     proto_key, proto_sel: [B, P, CK] token-major.  out_values[k]: [B, P, CV] rows; out_shrinkage [B, P].
+    stats = (out_max, out_sumexp), both [B, P] dense (key-sharded memory): the softmax statistics of THIS shard of the
+    candidates, by which its results are normalised -- what the shards exchange to combine them (inference/sharded.py).
     """
     B, P, CK = proto_key.shape
     ns = len(segments)
@@ -659,16 +662,20 @@ def consolidate(segments: Sequence[BankSegment], proto_key: torch.Tensor, proto_
             vp.append(v.data_ptr()), vs.append(v.stride(0))
     for t in (proto_key, proto_sel):
         _rows_view_ok(t)
+    if stats is not None:
+        for t in stats:
+            assert t.shape == (B, P) and t.is_contiguous() and t.dtype == torch.float32
     with _call('consolidate', 1):
-        st = lib().cutie_consolidate(
+        st = lib().cutie_consolidate_partial(
             ctypes.c_int(ns), PA(*[s.key.data_ptr() for s in segments]), PA(*[s.shrinkage.data_ptr() for s in segments]),
             IA(*[s.n for s in segments]), IA(*[s.key.stride(0) for s in segments]),
             IA(*[s.shrinkage.stride(0) for s in segments]), VA(*vp), VI(*vs), _i64(K),
             _ptr(proto_key), _i64(proto_key.stride(0)), _ptr(proto_sel), _i64(proto_sel.stride(0)),
             _i64(B), _i64(P), _i64(CK), _i64(out_values[0].shape[2] if K else 0),
             OA(*[v.data_ptr() for v in out_values]), OI(*[v.stride(0) for v in out_values]),
-            _ptr(out_shrinkage), _i64(out_shrinkage.stride(0)), _ptr(ws), _i64(n_total), _stream())
-    _check(st, 'cutie_consolidate')
+            _ptr(out_shrinkage), _i64(out_shrinkage.stride(0)), _ptr(stats[0] if stats else None),
+            _ptr(stats[1] if stats else None), _ptr(ws), _i64(n_total), _stream())
+    _check(st, 'cutie_consolidate_partial')
 
 
 def obj_summary_accumulate(acc: torch.Tensor, new: torch.Tensor):

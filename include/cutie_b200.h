@@ -242,6 +242,18 @@ int cutie_consolidate(int num_segments, const void* const* seg_key, const void* 
                       int64_t B, int64_t P, int64_t CK, int64_t CV, void* const* out_val,
                       const int64_t* out_val_bstride, float* out_shr, int64_t out_shr_bstride, float* workspace,
                       int64_t n_total, void* stream);
+/* The same potentiation over ONE SHARD of the candidates (key-sharded memory, cutie_b200/inference/sharded.py): results are
+ * normalised by the shard's own statistics, which are also returned -- out_max[b,p] = max_n S[n,p] (the per-shard affinity
+ * maximum BASELINE.json's north_star exchanges), out_sumexp[b,p] = sum_n exp(S[n,p] - out_max[b,p]) -- so that the shards'
+ * results combine exactly like one softmax: weight_r = sumexp_r exp(max_r - M) / sum_r' (...), M = max_r max_r.
+ * Both null: identical to cutie_consolidate.  (memory_manager.py:345-356, memory_utils.py:68-71.) */
+int cutie_consolidate_partial(int num_segments, const void* const* seg_key, const void* const* seg_shrinkage,
+                              const int64_t* seg_len, const int64_t* seg_key_bstride, const int64_t* seg_shr_bstride,
+                              const void* const* seg_val, const int64_t* seg_val_bstride, int64_t K,
+                              const float* proto_key, int64_t pk_bstride, const float* proto_sel, int64_t ps_bstride,
+                              int64_t B, int64_t P, int64_t CK, int64_t CV, void* const* out_val,
+                              const int64_t* out_val_bstride, float* out_shr, int64_t out_shr_bstride, float* out_max,
+                              float* out_sumexp, float* workspace, int64_t n_total, void* stream);
 /* acc[i] += add[i].  Replaces the streaming object-memory sum (memory_manager.py:252-271). */
 int cutie_obj_summary_accumulate(float* acc, const float* add, int64_t n, void* stream);
 

@@ -129,11 +129,15 @@ def bank_gather(segments_rows, index, dst_rows):
         dst_rows[b] = allr[b][index[b]]
 
 
-def consolidate(segments, proto_key, proto_sel, out_values, out_shrinkage):
+def consolidate(segments, proto_key, proto_sel, out_values, out_shrinkage, stats=None):
     keys = _cat_rows([s.key for s in segments]).transpose(1, 2)         # [B,CK,N]
     shr = _cat_rows([s.shrinkage for s in segments]).unsqueeze(1)       # [B,1,N]
     sim = mm.similarity_expanded(keys, shr, proto_key.transpose(1, 2), proto_sel.transpose(1, 2))
     aff = mm.dense_softmax(sim)                                          # [B,N,P]
+    if stats is not None:
+        mx = sim.max(dim=1)[0]
+        stats[0].copy_(mx)
+        stats[1].copy_((sim - mx.unsqueeze(1)).exp().sum(dim=1))
     for k, ov in enumerate(out_values):
         v = _cat_rows([s.values[k] for s in segments])                   # [B,N,CV]
         ov.copy_(torch.matmul(aff.transpose(1, 2), v))

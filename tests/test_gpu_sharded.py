@@ -99,3 +99,36 @@ def test_key_sharded_stream_nccl():
     ret = mgr.dict()
     mp.spawn(_stream_worker, args=(world, 29877, ret), nprocs=world, join=True)
     assert all(ret.get(r, 1e9) < 1e-3 for r in range(world)), dict(ret)
+
+
+def _long_term_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    try:
+        from tests import sharded_memory_case
+        out = []
+        for B in (1, 2):                       # 2 = the flip-augmentation batch
+            out.append(sharded_memory_case.run(torch.device('cuda', rank), h=15, w=27, K=3, steps=12, B=B, P=32))
+        torch.cuda.synchronize()
+        ret[rank] = out
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs >= 2 GPUs')
+def test_key_sharded_long_term_memory_nccl():
+    """Long-term memory under key sharding with the real kernels over NCCL (tests/sharded_memory_case.py): global prototype
+    ranking, cutie_consolidate_partial + all-gathered affinity maxima / exp-sums, obsolete-feature removal with re-dealt
+    survivors -- reads equal the un-sharded MemoryManager's at every step."""
+    world = min(torch.cuda.device_count(), 8)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_long_term_worker, args=(world, 29911, ret), nprocs=world, join=True)
+    for r in range(world):
+        for ok, worst, trace in ret.get(r, [(False, 1e9, [])]):
+            assert ok, f'rank {r}: store sizes wrong (long-term trace {trace})'
+            assert max(trace) == 128 and any(a > b for a, b in zip(trace, trace[1:])), f'no obsolete-feature removal in {trace}'
+            assert worst < 1e-4, f'rank {r}: sharded reads deviate by {worst}'

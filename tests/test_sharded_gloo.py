@@ -121,7 +121,150 @@ def test_key_sharded_stream_matches_unsharded(world):
         assert worst < 2e-4, f'rank {r}: sharded stream deviates by {worst}'
 
 
-def test_key_sharding_rejects_long_term():
+def _long_term_stream_worker(rank, world, port, ret):
+    """The same comparison with LONG-TERM memory on (memory_manager.py:283-358): consolidations (global prototype ranking,
+    shard-wise potentiation combined through the all-gathered affinity maxima / exp-sums) and one obsolete-feature removal
+    (global usage ranking, survivors re-dealt) happen inside the clip; the sharded stream must track the un-sharded one and
+    hold the expected share of both stores."""
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from tests import cpu_kernels as ck
+        ck.install()
+        from cutie_b200.config import default_config
+        from cutie_b200.inference.inference_core import InferenceCore
+        from cutie_b200.inference.sharded import shard_bounds
+        from cutie_b200.model.cutie import CUTIE
+        from oracle.synth import synthetic_state_dict, synthetic_video
+        torch.set_num_threads(2)
+        P = 8
+        cfg = default_config(mem_every=1, use_long_term=True,
+                             long_term=dict(max_mem_frames=4, min_mem_frames=2, num_prototypes=P, max_num_tokens=40,
+                                            buffer_tokens=10))
+        net = CUTIE(cfg).eval()
+        net.load_state_dict(synthetic_state_dict(net.state_dict(), 0))
+        T, K = 13, 2
+        frames, mask = synthetic_video(T, 96, 160, K, seed=5)                   # 60 tokens per frame
+        sharded = InferenceCore(net, cfg=cfg, memory_shard_group=dist.group.WORLD)
+        plain = InferenceCore(net, cfg=cfg)
+        lo, hi = shard_bounds(60, world, rank)
+        worst, ok, long_trace = 0.0, True, []
+        with torch.inference_mode():
+            for ti in range(T):
+                args = (frames[ti], mask) if ti == 0 else (frames[ti],)
+                kw = dict(objects=[1, 2]) if ti == 0 else {}
+                ps = sharded.step(*args, **kw)
+                pp = plain.step(*args, **kw)
+                worst = max(worst, float((ps - pp).abs().max()))
+                if ti > 0:
+                    worst = max(worst, float((sharded.last_logits - plain.last_logits).abs().max()))
+                ok = ok and sharded.memory.work_mem.size(0) * 60 == plain.memory.work_mem.size(0) * (hi - lo)
+                n_long = plain.memory.long_mem.size(0) if plain.memory.long_mem.engaged(0) else 0
+                mine = sharded.memory.long_mem.size(0) if sharded.memory.long_mem.engaged(0) else 0
+                counts = sharded.memory._long_counts.get(0, [0] * world)
+                ok = ok and sum(counts) == n_long and counts[rank] == mine
+                long_trace.append(n_long)
+        ret[rank] = (ok, worst, long_trace)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_key_sharded_long_term_stream_matches_unsharded(world):
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 33500 + (os.getpid() + world * 17) % 2000
+    mp.spawn(_long_term_stream_worker, args=(world, port, ret), nprocs=world, join=True)
+    for r in range(world):
+        ok, worst, trace = ret.get(r, (False, 1e9, []))
+        assert ok, f'rank {r}: shard sizes wrong (long-term trace {trace})'
+        assert max(trace) == 32 and 22 + 8 in trace, f'the clip must consolidate and remove obsolete features: {trace}'
+        assert worst < 2e-4, f'rank {r}: sharded long-term stream deviates by {worst}'
+
+
+def _memory_case_worker(rank, world, port, B, ret):
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from tests import cpu_kernels as ck
+        ck.install()
+        from tests import sharded_memory_case
+        torch.set_num_threads(2)
+        ret[rank] = sharded_memory_case.run('cpu', B=B)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world,B', [(2, 1), (3, 2)])
+def test_key_sharded_long_term_memory_level(world, B):
+    """MemoryManager-level (no network): reads of the key-sharded long-term + working memory equal the un-sharded reads
+    at every step; B = 2 is the flip-augmentation batch (per-entry rankings, same counts on every rank)."""
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 37500 + (os.getpid() + world * 23) % 2000
+    mp.spawn(_memory_case_worker, args=(world, port, B, ret), nprocs=world, join=True)
+    for r in range(world):
+        ok, worst, trace = ret.get(r, (False, 1e9, []))
+        assert ok, f'rank {r}: store sizes wrong (long-term trace {trace})'
+        assert max(trace) == 32 and any(a > b for a, b in zip(trace, trace[1:])), f'no obsolete-feature removal in {trace}'
+        assert worst < 1e-4, f'rank {r}: sharded reads deviate by {worst}'
+
+
+def _select_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from tests import cpu_kernels as ck
+        ck.install()
+        from cutie_b200.inference import sharded as S
+        g = torch.Generator().manual_seed(1)
+        B, n, C, k = 2, 37, 5, 9
+        score = torch.rand(B, n, generator=g)
+        score[:, 30] = score[:, 2]                                        # a tie across shards: lower rank first
+        rows = torch.randn(B, n, C, generator=g)
+        sizes = [0, 30, 7] if world == 3 else [30, 7]                      # ragged shards, one of them empty
+        lo = sum(sizes[:rank])
+        sl = slice(lo, lo + sizes[rank])
+        src_rank, src_idx = S.select_top(score[:, sl], k, None)
+        want_v, want_i = torch.sort(score, dim=1, descending=True, stable=True)
+        gidx = src_idx + torch.tensor([sum(sizes[:r]) for r in range(world)])[src_rank]
+        ok = torch.equal(gidx, want_i[:, :k])
+        got = S.fetch_rows([rows[:, sl][:, :3], rows[:, sl][:, 3:]], src_rank, src_idx, None)
+        ok = ok and torch.equal(got, torch.stack([rows[b][want_i[b, :k]] for b in range(B)]))
+        # shard-wise softmax sums against the dense softmax over everything
+        sim = torch.randn(B, n, 4, generator=g) * 5
+        val = torch.randn(B, n, 6, generator=g)
+        dense = torch.einsum('bnp,bnc->bpc', torch.softmax(sim, dim=1), val)
+        if sizes[rank]:
+            mx = sim[:, sl].max(dim=1)[0]
+            e = (sim[:, sl] - mx.unsqueeze(1)).exp()
+            se = e.sum(dim=1)
+            part = torch.einsum('bnp,bnc->bpc', e, val[:, sl]) / se.unsqueeze(-1)
+        else:
+            mx, se, part = torch.full((B, 4), float('-inf')), torch.zeros(B, 4), torch.zeros(B, 4, 6)
+        full = S.combine_partial_softmax(part, mx, se, None)
+        ok = ok and torch.allclose(full, dense, rtol=1e-5, atol=1e-6)
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_sharded_selection_fetch_and_softmax_combination(world):
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 35500 + (os.getpid() + world * 19) % 2000
+    mp.spawn(_select_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert all(ret.get(r) for r in range(world)), dict(ret)
+
+
+def test_key_sharding_needs_a_prototype_per_rank():
     from cutie_b200.config import default_config
     from cutie_b200.inference.memory_manager import MemoryManager
     from cutie_b200.inference.object_manager import ObjectManager
@@ -129,11 +272,11 @@ def test_key_sharding_rejects_long_term():
     class _Group:          # never touched: the constructor must refuse before any collective
         pass
     import torch.distributed as dist_
-    cfg = default_config(use_long_term=True)
+    cfg = default_config(use_long_term=True, long_term=dict(num_prototypes=1))
     orig = (dist_.get_world_size, dist_.get_rank)
     dist_.get_world_size, dist_.get_rank = (lambda g=None: 2), (lambda g=None: 0)
     try:
-        with pytest.raises(NotImplementedError):
+        with pytest.raises(ValueError):
             MemoryManager(cfg, ObjectManager(), shard_group=_Group())
     finally:
         dist_.get_world_size, dist_.get_rank = orig
