@@ -343,11 +343,43 @@ def run_ours(args, wl, rank, world, dev):
             look = {'ms_total': lm[0].elapsed_time(lm[-1]), 'ms_e2e': le0.elapsed_time(le1)}
             log(f'[rank {rank}] look-ahead arms: device {look["ms_total"] / K:.2f} ms/step (host enqueue {lh:.2f}), '
                 f'e2e {look["ms_e2e"] / K:.2f} ms/step (host enqueue {leh:.2f})')
-    times = torch.tensor([ms_total, ms_e2e] + ([look['ms_total'], look['ms_e2e']] if look else [0.0, 0.0]),
+    # ---- the north star's own stream configuration on the same model: 480p, 3 objects, ~10k-key memory (6 memory frames),
+    # drop-in step(image), device-resident frames; every rank runs it (N streams), timed like the headline ----
+    ns_ms, ns_tokens, ns_steps = 0.0, 0, 0
+    if args.workload == 'cfg2' and not args.no_northstar:
+        wl_ns = WORKLOADS['northstar']
+        proc_ns = InferenceCore(net, cfg=make_cfg(wl_ns), use_cuda_graphs=use_graphs)
+        ns_steps = min(K, 100)
+        with torch.inference_mode():
+            proc_ns.step(frames_dev[0], mask.to(dev), objects=objs)
+            for key, shr, vals in synthetic_bank_chunks(wl_ns):
+                proc_ns.memory.work_mem.add(key.to(dev), {o: vals[:, i].to(dev) for i, o in enumerate(objs)},
+                                            shr.to(dev), None, as_permanent='no')
+            ns_tokens = proc_ns.memory.work_mem.size(0)
+            t = 1
+            for _ in range(warm):
+                proc_ns.step(frames_dev[t]); t += 1
+            barrier()
+            n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n0.record()
+            for _ in range(ns_steps):
+                proc_ns.step(frames_dev[t]); t += 1
+            n1.record()
+            barrier()
+            ns_ms = n0.elapsed_time(n1)
+        del proc_ns
+    times = torch.tensor([ms_total, ms_e2e] + ([look['ms_total'], look['ms_e2e']] if look else [0.0, 0.0]) + [ns_ms],
                          dtype=torch.float64, device=dev)
     if world > 1:
         torch.distributed.all_reduce(times, op=torch.distributed.ReduceOp.MAX)
     ms_total, ms_e2e = float(times[0]), float(times[1])
+    if ns_steps:
+        res['northstar_stream'] = {
+            'what': 'the same model on BASELINE.json north_star\'s stream: 480p, 3 objects, ~10k-key working memory '
+                    '(6 memory frames), InferenceCore.step(image) with device-resident frames, all ranks (max time over ranks)',
+            'value': world * ns_steps / (float(times[4]) * 1e-3), 'unit': 'frames/s', 'ms_per_step': float(times[4]) / ns_steps,
+            'steps': ns_steps, 'memory_tokens': ns_tokens, 'n_gpus': world}
+        log(f'[northstar stream] {res["northstar_stream"]}')
     if look:
         look = {'ms_total': float(times[2]), 'ms_e2e': float(times[3])}
     log(f'[rank {rank}] host enqueue time per step: device arm {host_dev:.2f} ms, e2e arm {host_e2e:.2f} ms')
@@ -842,8 +874,10 @@ def main():
             'key_image_levels': res['image_levels'],
             'build': {'cuda_graphs': not args.no_graphs, 'optimize_for_inference': not args.no_optimize,
                       'cudnn_benchmark': not args.no_cudnn_benchmark, 'cudnn_allow_tf32': False, 'matmul_allow_tf32': False,
-                      'conv_epilogues': res['epilogues'], 'glue_dispatch': res['glue']},
-            'roofline_northstar': northstar, 'roofline_conv': conv_roof, 'sharded_read': sharded}
+                      'conv_epilogues': res['epilogues'], 'glue_dispatch': res['glue'],
+                      'qt_chain': __import__('cutie_b200.model.object_transformer', fromlist=['QT_CHAIN']).QT_CHAIN},
+            'roofline_northstar': northstar, 'northstar_stream': res.get('northstar_stream'), 'roofline_conv': conv_roof,
+            'sharded_read': sharded}
     emit(line)
 
 

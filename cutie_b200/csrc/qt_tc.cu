@@ -30,6 +30,7 @@
 #include <math_constants.h>
 
 #include "common.cuh"
+#include "qt_combine.cuh"
 #include "tc_ptx.cuh"
 
 namespace cutie {
@@ -305,48 +306,15 @@ __global__ void __launch_bounds__(QT_THREADS, 1) qt_p2q_tc_kernel(const P2QTcPar
 }
 
 // merge the pixel tiles of one attention row (i, h), normalise, apply the per-head value projection:
-// grid (16 query rows, heads, BK), 256 threads (thread == channel, then 8 warps x 4 outputs)
+// grid (16 query rows, heads, BK), 256 threads (thread == channel, then 8 warps x 4 outputs); body in qt_combine.cuh
+// (shared with qt_chain_kernel, csrc/qt.cu)
 __global__ void __launch_bounds__(256) qt_p2q_combine_kernel(const float* __restrict__ ws, int tiles,
                                                              const float* __restrict__ wv, long long ldwv,
                                                              const float* __restrict__ bv, float* __restrict__ attn) {
   extern __shared__ float coef[];   // [tiles]: exp(m_t - M) / L
   __shared__ float zn[E_];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int i = blockIdx.x, h = blockIdx.y, r = i * H_ + h;
-  const long long bk = blockIdx.z;
-  const float* base = ws + bk * tiles * (long long)P2Q_WS;
-  if (warp == 0) {
-    float M = -CUDART_INF_F;
-    for (int t = lane; t < tiles; t += 32) M = fmaxf(M, base[(long long)t * P2Q_WS + ROWS * E_ + r]);
-    M = warp_max(M);
-    float L = 0.f;
-    for (int t = lane; t < tiles; t += 32) {
-      const float mt = base[(long long)t * P2Q_WS + ROWS * E_ + r];
-      const float f = (mt == -CUDART_INF_F) ? 0.f : expf(mt - M);
-      coef[t] = f;
-      L += f * base[(long long)t * P2Q_WS + ROWS * E_ + ROWS + r];
-    }
-    L = warp_sum(L);
-    __syncwarp();
-    const float inv = 1.f / L;
-    for (int t = lane; t < tiles; t += 32) coef[t] *= inv;
-  }
-  __syncthreads();
-  float acc = 0.f;
-  for (int t = 0; t < tiles; ++t) {
-    const float c = coef[t];
-    if (c != 0.f) acc = fmaf(c, base[(long long)t * P2Q_WS + (long long)r * E_ + tid], acc);   // skip fully masked tiles
-  }
-  zn[tid] = acc;
-  __syncthreads();
-  for (int e = warp; e < 32; e += 8) {
-    const float* wr = wv + (long long)(h * 32 + e) * ldwv;
-    float d = 0.f;
-#pragma unroll
-    for (int c = lane; c < E_; c += 32) d = fmaf(zn[c], wr[c], d);
-    d = warp_sum(d);
-    if (lane == 0) attn[(bk * NQ + i) * E_ + h * 32 + e] = d + bv[h * 32 + e];
-  }
+  qt_p2q_combine_tile<E_, H_, NQ>(ws, tiles, wv, ldwv, bv, attn, (int)blockIdx.x, (int)blockIdx.y, (long long)blockIdx.z,
+                                  coef, zn);
 }
 
 // =====================================================================================================
@@ -587,7 +555,9 @@ extern "C" int cutie_qt_pixel_to_query(const float* qfold, const float* pixel, c
                                        const uint8_t* fg, const int32_t* fg_count, const float* wv, int64_t ldwv,
                                        const float* bv, int64_t BK, int64_t E, int64_t HW, int num_queries,
                                        int num_heads, int splits, float* workspace, float* attn_out, void* stream) {
-  CUTIE_REQUIRE(qfold && pixel && pixel_pe && fg && fg_count && wv && bv && workspace && attn_out, "null argument");
+  // attn_out == nullptr: tiles only -- the merge + value projection then runs as an op of cutie_qt_chain (qt.cu)
+  CUTIE_REQUIRE(qfold && pixel && pixel_pe && fg && fg_count && workspace, "null argument");
+  CUTIE_REQUIRE(attn_out == nullptr || (wv && bv), "the combine step needs wv and bv");
   CUTIE_REQUIRE(E == E_ && num_heads == H_ && num_queries == NQ, "embed_dim 256, 8 heads, 16 queries");
   CUTIE_REQUIRE(BK >= 1 && HW >= 1, "empty");
   const int tiles = (int)((HW + P2Q_TP - 1) / P2Q_TP);
@@ -609,6 +579,7 @@ extern "C" int cutie_qt_pixel_to_query(const float* qfold, const float* pixel, c
   else
     qt_p2q_tc_kernel<false><<<dim3((unsigned)tiles, (unsigned)BK), QT_THREADS, smem, st>>>(p);
   CUTIE_CHECK_LAUNCH();
+  if (attn_out == nullptr) return 0;
   qt_p2q_combine_kernel<<<dim3(NQ, H_, (unsigned)BK), 256, (size_t)tiles * sizeof(float), st>>>(workspace, tiles, wv, ldwv, bv,
                                                                                                  attn_out);
   CUTIE_CHECK_LAUNCH();

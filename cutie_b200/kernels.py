@@ -765,6 +765,29 @@ def qt_aux_mask(pixel: torch.Tensor, w: torch.Tensor, b: torch.Tensor, B: int, K
     return logits, fg, cnt
 
 
+def qt_pixel_to_query_tiles(qfold: torch.Tensor, pixel: torch.Tensor, pixel_pe: torch.Tensor, fg: torch.Tensor,
+                            fg_count: torch.Tensor, num_queries: int, num_heads: int = 8):
+    """The tensor-core half of qt_pixel_to_query only: per 64-pixel tile and object the tile-local softmax statistics and
+    Z = P . pixel^T go to a workspace; the merge + value projection then runs as QtChain.p2q_combine inside the next fused
+    query chain.  Returns (workspace, tiles)."""
+    M, H, E = qfold.shape
+    BK, _, HW = pixel.shape
+    assert pixel.is_contiguous() and pixel_pe.is_contiguous() and qfold.is_contiguous() and fg.is_contiguous()
+    L = lib()
+    L.cutie_qt_pixel_to_query_splits.restype = ctypes.c_int
+    L.cutie_qt_pixel_to_query_workspace_floats.restype = ctypes.c_int64
+    splits = L.cutie_qt_pixel_to_query_splits(_i64(BK), _i64(HW), ctypes.c_int(num_heads))
+    ws = torch.empty(int(L.cutie_qt_pixel_to_query_workspace_floats(_i64(BK), _i64(HW))), dtype=torch.float32,
+                     device=pixel.device)
+    with _call('qt_pixel_to_query', 1):
+        st = L.cutie_qt_pixel_to_query(_ptr(qfold), _ptr(pixel), _ptr(pixel_pe), _ptr(fg, torch.uint8),
+                                       _ptr(fg_count, torch.int32), _ptr(None), _i64(0), _ptr(None),
+                                       _i64(BK), _i64(E), _i64(HW), ctypes.c_int(num_queries), ctypes.c_int(num_heads),
+                                       ctypes.c_int(splits), _ptr(ws), _ptr(None), _stream())
+    _check(st, 'cutie_qt_pixel_to_query')
+    return ws, int(splits)
+
+
 def qt_pixel_to_query(qfold: torch.Tensor, pixel: torch.Tensor, pixel_pe: torch.Tensor, fg: torch.Tensor,
                       fg_count: torch.Tensor, wv: torch.Tensor, bv: torch.Tensor, num_queries: int,
                       num_heads: int = 8) -> torch.Tensor:
@@ -811,3 +834,132 @@ def qt_query_to_pixel(kfold: torch.Tensor, kdots: torch.Tensor, vfold: torch.Ten
                                            ctypes.c_int(num_heads), _ptr(out), _stream())
     _check(st, 'cutie_qt_query_to_pixel')
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# the query-side chain of a transformer block as one launch (cutie_qt_chain)
+# ---------------------------------------------------------------------------------------------
+QT_CHAIN_MAX_OPS = 16
+QT_CHAIN_MAX_TILES = 1024           # pixel tiles the in-chain combine can merge (64 pixels each)
+_QT_LINEAR, _QT_HEAD_FOLD, _QT_SELF_ATTENTION, _QT_P2Q_COMBINE = 0, 1, 2, 3
+_QT_SYNC = {}                        # device index -> 4 x uint32 grid-barrier counters (zero between launches)
+
+
+class _QtOp(ctypes.Structure):       # mirrors `cutie_qt_op` (include/cutie_b200.h)
+    _fields_ = [('kind', ctypes.c_int32), ('phase', ctypes.c_int32), ('inp', ctypes.c_void_p * 8),
+                ('out', ctypes.c_void_p * 2), ('i', ctypes.c_int64 * 6), ('f', ctypes.c_float),
+                ('reserved', ctypes.c_int32)]
+
+
+class QtChain:
+    """Records qt_linear / qt_head_fold / qt_self_attention / combine ops (same arguments and semantics as the stand-alone
+    wrappers) and runs them as ONE persistent launch.  Ops recorded between two barrier() calls form a phase: they must
+    not depend on each other; an op may consume the outputs of earlier phases.  Outputs are allocated at record time and
+    hold their values after run()."""
+
+    def __init__(self):
+        self.ops = []                # (name, args, kwargs, outs, phase)
+        self.phase = 0
+        self.prefetch = []
+
+    def barrier(self):
+        self.phase += 1
+
+    def linear(self, x, weight, bias, *, ln=None, pe=None, summary_norm=False, relu=False, residual=None, residual_mod=0,
+               want_xhat=False):
+        M = x.shape[0]
+        N, Kd = weight.shape
+        assert weight.stride(1) == 1 and x.is_contiguous() and x.shape[1] == Kd + (1 if summary_norm else 0)
+        assert ln is None or Kd == 256, 'fused LayerNorm supports embed_dim 256'
+        out = torch.empty(M, N, dtype=torch.float32, device=x.device)
+        xhat = torch.empty(M, Kd, dtype=torch.float32, device=x.device) if want_xhat else None
+        self.ops.append(('qt_linear', (x, weight, bias), dict(ln=ln, pe=pe, summary_norm=summary_norm, relu=relu,
+                                                              residual=residual, residual_mod=residual_mod,
+                                                              xhat_out=xhat), (out,), self.phase))
+        self.prefetch.append(weight)
+        return (out, xhat) if want_xhat else out
+
+    def head_fold(self, a, weight, *, transpose_w, scale, bias_vec=None, num_heads=8):
+        M, E = a.shape
+        assert weight.shape == (E, E) and weight.stride(1) == 1 and num_heads == 8 and E == 256
+        out = torch.empty(M, num_heads, E, dtype=torch.float32, device=a.device)
+        dots = torch.empty(M, num_heads, dtype=torch.float32, device=a.device) if bias_vec is not None else None
+        self.ops.append(('qt_head_fold', (a, weight), dict(transpose_w=transpose_w, scale=scale, bias_vec=bias_vec,
+                                                           num_heads=num_heads), (out, dots), self.phase))
+        self.prefetch.append(weight)
+        return out, dots
+
+    def self_attention(self, qk, v, num_queries, num_heads=8):
+        M, E2 = qk.shape
+        assert E2 == 512 and num_queries == 16 and num_heads == 8 and M % 16 == 0
+        out = torch.empty(M, E2 // 2, dtype=torch.float32, device=qk.device)
+        self.ops.append(('qt_self_attention', (qk, v, num_queries, num_heads), {}, (out,), self.phase))
+        return out
+
+    def p2q_combine(self, ws, tiles, wv, bv, BK, num_queries=16, num_heads=8):
+        assert tiles <= QT_CHAIN_MAX_TILES and wv.stride(1) == 1
+        out = torch.empty(BK * num_queries, 256, dtype=torch.float32, device=wv.device)
+        self.ops.append(('qt_p2q_combine', (ws, tiles, wv, bv, BK, num_queries, num_heads), {}, (out,), self.phase))
+        return out
+
+    def run(self):
+        if self.ops:
+            qt_chain_run(self)
+
+
+def _vp(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def qt_chain_run(chain: QtChain):
+    """One cutie_qt_chain launch for the recorded ops."""
+    n = len(chain.ops)
+    if n > QT_CHAIN_MAX_OPS:
+        raise KernelError(f'a query chain holds at most {QT_CHAIN_MAX_OPS} ops, got {n}')
+    arr = (_QtOp * n)()
+    dev = None
+    for o, (name, args, kw, outs, phase) in zip(arr, chain.ops):
+        o.phase = phase
+        if name == 'qt_linear':
+            x, w, b = args
+            ln = kw['ln']
+            o.kind = _QT_LINEAR
+            ins = (x, w, b, ln[0] if ln else None, ln[1] if ln else None, kw['pe'], kw['residual'])
+            o.i[:] = (x.shape[0], w.shape[1], w.stride(0), w.shape[0],
+                      (1 if kw['summary_norm'] else 0) | (2 if kw['relu'] else 0), kw['residual_mod'])
+            o.out[0], o.out[1] = _ptr(outs[0]), _ptr(kw['xhat_out'])
+        elif name == 'qt_head_fold':
+            a, w = args
+            o.kind = _QT_HEAD_FOLD
+            ins = (a, w, kw['bias_vec'])
+            o.i[:] = (a.shape[0], w.stride(0), int(kw['transpose_w']), 0, 0, 0)
+            o.f = float(kw['scale'])
+            o.out[0], o.out[1] = _ptr(outs[0]), _ptr(outs[1])
+        elif name == 'qt_self_attention':
+            qk, v = args[:2]
+            o.kind = _QT_SELF_ATTENTION
+            ins = (qk, v)
+            o.i[:] = (qk.shape[0], 0, 0, 0, 0, 0)
+            o.out[0] = _ptr(outs[0])
+        else:
+            ws, tiles, wv, bv, BK = args[:5]
+            o.kind = _QT_P2Q_COMBINE
+            ins = (ws, wv, bv)
+            o.i[:] = (tiles, wv.stride(0), BK, 0, 0, 0)
+            o.out[0] = _ptr(outs[0])
+        for j, t in enumerate(ins):
+            o.inp[j] = _ptr(t)
+        dev = outs[0].device
+    sync = _QT_SYNC.get(dev.index)
+    if sync is None:
+        if torch.cuda.is_current_stream_capturing():
+            raise KernelError('the first query chain of a device must run outside CUDA-graph capture (it allocates the '
+                              'grid-barrier counters); warm the model up eagerly once')
+        sync = _QT_SYNC[dev.index] = torch.zeros(4, dtype=torch.int32, device=dev)
+    pf = [w for w in chain.prefetch if w.is_contiguous()][:16]
+    PA, IA = ctypes.c_void_p * max(len(pf), 1), ctypes.c_int64 * max(len(pf), 1)
+    with _call('qt_chain', 1):
+        st = lib().cutie_qt_chain(arr, ctypes.c_int(n), PA(*[w.data_ptr() for w in pf]),
+                                  IA(*[w.numel() * 4 for w in pf]), ctypes.c_int(len(pf)),
+                                  _ptr(sync, torch.int32), _stream())
+    _check(st, 'cutie_qt_chain')

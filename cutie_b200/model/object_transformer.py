@@ -18,6 +18,7 @@ execution plan:
 The 1x1 projections and the 3x3 PixelFFN convolutions remain cuDNN calls (section 8(f).1, "next").
 """
 import math
+import os
 from typing import Dict, Optional
 
 import torch
@@ -27,6 +28,12 @@ import torch.nn.functional as F
 from cutie_b200 import kernels as K_
 from cutie_b200.model.blocks import ChannelAttnResBlock, ObjConv2d
 from cutie_b200.model.positional import SinusoidPE
+
+
+# The query-side ops between the tensor-core cross attentions run as one persistent launch per block (cutie_qt_chain,
+# csrc/qt.cu: bit-identical to the separate launches).  A committed constant, not a run-time trial; the environment
+# variable exists for A/B measurements (bench.py echoes the setting in `build`).
+QT_CHAIN = os.environ.get('CUTIE_B200_QT_CHAIN', '1') != '0'
 
 
 class PackedAttentionParams(nn.Module):
@@ -163,6 +170,8 @@ class QueryTransformer(nn.Module):
         if T != 1:
             obj_summaries = obj_summaries.sum(dim=2, keepdim=True)      # sums and areas both add (:128-131)
         summ = obj_summaries.reshape(B * K * Q, E + 1).contiguous()
+        if QT_CHAIN and (h * w + 63) // 64 <= K_.QT_CHAIN_MAX_TILES:
+            return self._forward_chained(pixel, summ)
         x = K_.qt_linear(summ, self.summary_to_query_init.weight, self.summary_to_query_init.bias,
                          summary_norm=True, residual=self.query_init.weight, residual_mod=Q)
         query_pe = K_.qt_linear(summ, self.summary_to_query_emb.weight, self.summary_to_query_emb.bias,
@@ -179,9 +188,88 @@ class QueryTransformer(nn.Module):
             x, pix = blk(x, pix, query_pe, pixel_pe, fg, cnt, (h, w))
             logits, fg, cnt = self._aux(i + 1, pix, B, K)                          # :164-167 (always taken)
             aux_logits.append(logits.view(B, K, h, w))
+        return self._finish(pix, aux_logits, fg, B, K, E, h, w)
+
+    def _finish(self, pix, aux_logits, fg, B, K, E, h, w):
         aux: Dict[str, object] = {'logits': aux_logits, 'q_weights': None, 'p_weights': None,
                                   'fg_map': fg.view(B, K, h, w)}
         return pix.view(B, K, E, h, w), aux
+
+    def _forward_chained(self, pixel: torch.Tensor, summ: torch.Tensor):
+        """forward() with the query-side ops fused: one cutie_qt_chain launch for the query initialisation and block 0's
+        query projection, then per block [read_from_pixel tiles on tcgen05] -> ONE chain (merge + value projection,
+        out-proj, self attention, FFN, this block's key/value folds and the NEXT block's query fold) -> [read_from_query on
+        tcgen05] -> PixelFFN.  Same ops, same arguments, same arithmetic as QueryTransformerBlock.forward: 4 launches
+        instead of 41 on the query side."""
+        B, K, E, h, w = pixel.shape
+        Q, H = self.num_queries, self.num_heads
+        BK = B * K
+        scale = 1.0 / math.sqrt(E // H)
+
+        def q_side(ch, blk, x, query_pe):
+            """read_from_pixel's query projection (LayerNorm + pe) in the current phase; returns what the fold needs."""
+            (wq, wk, _), (bq, _, _) = blk.read_from_pixel.cross_attn.split()
+            rp = blk.read_from_pixel
+            qp, xhat = ch.linear(x, wq, bq, ln=(rp.norm.weight, rp.norm.bias), pe=query_pe, want_xhat=True)
+            return qp, xhat, wk
+
+        ch = K_.QtChain()
+        x = ch.linear(summ, self.summary_to_query_init.weight, self.summary_to_query_init.bias, summary_norm=True,
+                      residual=self.query_init.weight, residual_mod=Q)
+        query_pe = ch.linear(summ, self.summary_to_query_emb.weight, self.summary_to_query_emb.bias, summary_norm=True,
+                             residual=self.query_emb.weight, residual_mod=Q)
+        ch.barrier()
+        qp, xhat, wk0 = q_side(ch, self.blocks[0], x, query_pe)
+        ch.barrier()
+        qfold, _ = ch.head_fold(qp, wk0, transpose_w=False, scale=scale, num_heads=H)
+        ch.run()
+
+        pix = self.pixel_init_proj(pixel).reshape(BK, E, h * w).contiguous()
+        pe = self.spatial_pe.grid(h, w).reshape(h * w, E).t()                     # [E, HW]
+        pixel_pe = (self.pixel_emb_proj(pixel).reshape(BK, E, h * w) + pe).contiguous()
+        logits, fg, cnt = self._aux(0, pix, B, K)
+        aux_logits = [logits.view(B, K, h, w)]
+        for i, blk in enumerate(self.blocks):
+            rp, sa, f, rq = blk.read_from_pixel, blk.self_attn, blk.ffn, blk.read_from_query
+            (_, _, wv), (_, _, bv) = rp.cross_attn.split()
+            ws, tiles = K_.qt_pixel_to_query_tiles(qfold, pix, pixel_pe, fg, cnt, Q, H)
+            ch = K_.QtChain()
+            attn = ch.p2q_combine(ws, tiles, wv, bv, BK, Q, H)
+            ch.barrier()
+            x = ch.linear(attn, rp.cross_attn.out_proj.weight, rp.cross_attn.out_proj.bias, residual=xhat)
+            ch.barrier()
+            # self attention (transformer_layers.py:27-41); the value projection re-derives LayerNorm(x) itself (same code,
+            # same values) so that it shares the phase of the q/k projection
+            ln = (sa.norm.weight, sa.norm.bias)
+            qk, xhat2 = ch.linear(x, sa.self_attn.in_proj_weight[:2 * E], sa.self_attn.in_proj_bias[:2 * E], ln=ln,
+                                  pe=query_pe, want_xhat=True)
+            v = ch.linear(x, sa.self_attn.in_proj_weight[2 * E:], sa.self_attn.in_proj_bias[2 * E:], ln=ln)
+            ch.barrier()
+            attn = ch.self_attention(qk, v, Q, H)
+            ch.barrier()
+            x = ch.linear(attn, sa.self_attn.out_proj.weight, sa.self_attn.out_proj.bias, residual=xhat2)
+            ch.barrier()
+            hdn = ch.linear(x, f.linear1.weight, f.linear1.bias, ln=(f.norm.weight, f.norm.bias), relu=True)
+            ch.barrier()
+            x = ch.linear(hdn, f.linear2.weight, f.linear2.bias, residual=x)
+            ch.barrier()
+            (wq, wk, wv2), (bq, bk, bv2) = rq.cross_attn.split()
+            kp = ch.linear(x, wk, bk, pe=query_pe)
+            vp = ch.linear(x, wv2, bv2)
+            nxt = self.blocks[i + 1] if i + 1 < len(self.blocks) else None
+            if nxt is not None:
+                qp, xhat, wk_next = q_side(ch, nxt, x, query_pe)
+            ch.barrier()
+            kfold, kdots = ch.head_fold(kp, wq, transpose_w=False, scale=scale, bias_vec=bq, num_heads=H)
+            vfold, _ = ch.head_fold(vp, rq.cross_attn.out_proj.weight, transpose_w=True, scale=1.0, num_heads=H)
+            if nxt is not None:
+                qfold, _ = ch.head_fold(qp, wk_next, transpose_w=False, scale=scale, num_heads=H)
+            ch.run()
+            pix = K_.qt_query_to_pixel(kfold, kdots, vfold, rq.cross_attn.out_proj.bias, pix, pixel_pe, Q, H)
+            pix = blk.pixel_ffn.conv(pix.view(BK, E, h, w)).reshape(BK, E, -1).contiguous()
+            logits, fg, cnt = self._aux(i + 1, pix, B, K)                          # :164-167 (always taken)
+            aux_logits.append(logits.view(B, K, h, w))
+        return self._finish(pix, aux_logits, fg, B, K, E, h, w)
 
     def attn_mask_from_fg(self, fg: torch.Tensor) -> torch.Tensor:
         """Expand the 1-byte foreground map to the reference's boolean mask layout

@@ -277,6 +277,32 @@ int cutie_qt_head_fold(const float* a, int64_t M, int64_t E, int num_heads, cons
 /* 16x16 self attention per (object, head): SelfAttention core (transformer_layers.py:40). */
 int cutie_qt_self_attention(const float* qk, const float* v, int64_t M, int64_t E, int num_queries, int num_heads,
                             float* out, void* stream);
+/* The query-side chain of the object transformer as ONE launch (csrc/qt.cu, qt_chain_kernel): an op list over the
+ * [objects x 16, 256] query tile -- the same ops, with the same arguments, as cutie_qt_linear / cutie_qt_head_fold /
+ * cutie_qt_self_attention and the merge step of cutie_qt_pixel_to_query -- executed by a persistent grid.  Ops that share a
+ * `phase` are independent of each other; a grid barrier separates consecutive phases, so an op may read what ops of EARLIER
+ * phases wrote.  Results are bit-identical to the separate launches.  Replaces the addmm / layer_norm / SDPA launches of
+ * QueryTransformerBlock.forward between the two cross attentions (object_transformer.py:46-68, transformer_layers.py:12-118).
+ *   LINEAR          in = {x, W, bias, ln_w, ln_b, pe, residual}  out = {y, xhat_out}
+ *                   i = {M, Kd, ldw, N, flags (1 = summary_norm, 2 = relu), residual_mod}
+ *   HEAD_FOLD       in = {a, W, bias_vec}  out = {out, dots}  i = {M, ldw, transpose_w}  f = scale
+ *   SELF_ATTENTION  in = {qk, v}  out = {out}  i = {M}
+ *   P2Q_COMBINE     in = {workspace of cutie_qt_pixel_to_query(attn_out = NULL), wv, bv}  out = {attn}  i = {tiles, ldwv, BK}
+ * prefetch_ptr / prefetch_bytes: read-only ranges (weights) to pull into L2 at the start.  sync_ws: 4 uint32, zero before
+ * the first launch and owned by ONE stream at a time (the kernel leaves them zero). */
+enum { CUTIE_QT_OP_LINEAR = 0, CUTIE_QT_OP_HEAD_FOLD = 1, CUTIE_QT_OP_SELF_ATTENTION = 2, CUTIE_QT_OP_P2Q_COMBINE = 3 };
+#define CUTIE_QT_CHAIN_MAX_OPS 16
+#define CUTIE_QT_CHAIN_MAX_PREFETCH 16
+typedef struct cutie_qt_op {
+  int32_t kind, phase;
+  const float* in[8];
+  float* out[2];
+  int64_t i[6];
+  float f;
+  int32_t reserved;
+} cutie_qt_op;
+int cutie_qt_chain(const cutie_qt_op* ops, int nops, const void* const* prefetch_ptr, const int64_t* prefetch_bytes,
+                   int nprefetch, uint32_t* sync_ws, void* stream);
 /* mask_pred 1x1 conv on relu(pixel) + sigmoid + aggregate + foreground test + per-object foreground count.
  * Replaces mask_pred[i] and QueryTransformer._get_aux_mask (object_transformer.py:153-155,165-167,179-205;
  * cutie/utils/tensor_utils.py:47-54).  The [(B*K*heads),Q,HW] bool mask is represented by fg + fg_count. */

@@ -233,6 +233,29 @@ def qt_pixel_to_query(qfold, pixel, pixel_pe, fg, fg_count, wv, bv, num_queries,
     return attn.reshape(M, E)
 
 
+def qt_pixel_to_query_tiles(qfold, pixel, pixel_pe, fg, fg_count, num_queries, num_heads=8):
+    # the emulation has no tile workspace: hand the inputs to the chain's combine op
+    return (qfold, pixel, pixel_pe, fg, fg_count), (pixel.shape[2] + 63) // 64
+
+
+def qt_chain_run(chain):
+    """Emulation of cutie_qt_chain: the recorded ops one after the other (phases only constrain ordering)."""
+    g = globals()
+    for name, args, kw, outs, _phase in chain.ops:
+        if name == 'qt_linear':
+            g[name](*args, out=outs[0], **kw)
+        elif name == 'qt_head_fold':
+            o, d = g[name](*args, **kw)
+            outs[0].copy_(o)
+            if outs[1] is not None:
+                outs[1].copy_(d)
+        elif name == 'qt_self_attention':
+            outs[0].copy_(g[name](*args))
+        else:
+            ws, _tiles, wv, bv, _BK, Q, H = args
+            outs[0].copy_(qt_pixel_to_query(*ws, wv, bv, Q, H))
+
+
 def qt_query_to_pixel(kfold, kdots, vfold, out_bias, pixel, pixel_pe, num_queries, num_heads=8, out=None):
     BK, E, HW = pixel.shape
     Q, H = num_queries, num_heads
@@ -307,7 +330,7 @@ def gated_update(h, v):
 
 ALL = ['last_candidate_counts', 'bias_act_', 'bias_relu_maxpool', 'segment_tail', 'conv3x3_c1', 'conv_weight_image', 'conv_tc', 'area_pool', 'eca_scale_add_', 'gated_update', 'affinity_topk', 'topk_merge', 'readout_gather', 'usage_commit', 'bank_append', 'bank_export', 'bank_gather', 'bank_key_image', 'upsample2x_add', 'prob_to_mask',
        'consolidate', 'obj_summary_accumulate', 'qt_linear', 'qt_head_fold', 'qt_self_attention',
-       'qt_aux_mask', 'qt_pixel_to_query', 'qt_query_to_pixel']
+       'qt_aux_mask', 'qt_pixel_to_query', 'qt_query_to_pixel', 'qt_pixel_to_query_tiles', 'qt_chain_run']
 
 
 def last_candidate_counts():

@@ -229,6 +229,21 @@ def test_consolidate_vs_reference_fixture(K_):
     assert torch.allclose(ov[0].cpu().transpose(1, 2), torch.from_numpy(g['cons_pv1']), rtol=1e-4, atol=2e-5)
     assert torch.allclose(ov[1].cpu().transpose(1, 2), torch.from_numpy(g['cons_pv5']), rtol=1e-4, atol=2e-5)
     assert torch.allclose(osr.cpu().unsqueeze(1), torch.from_numpy(g['cons_ps']), rtol=1e-4, atol=2e-5)
+    # cutie_consolidate_partial: two shards of the candidates, each normalised by its own (returned) softmax statistics,
+    # combined the way inference/sharded.combine_partial_softmax does -> the whole-bank result
+    parts = []
+    for lo, hi in ((0, 100), (100, Nc)):
+        sh = segments_of(K_, ck[:, :, lo:hi].transpose(1, 2).contiguous(), cs[:, 0, lo:hi],
+                         [v1[:, :, lo:hi].transpose(1, 2).contiguous(), v5[:, :, lo:hi].transpose(1, 2).contiguous()], ())
+        pv = [torch.zeros(B, P, 256).cuda() for _ in range(2)]
+        ps, mx, se = torch.zeros(B, P).cuda(), torch.zeros(B, P).cuda(), torch.zeros(B, P).cuda()
+        K_.consolidate(sh, pk, pe, pv, ps, stats=(mx, se))
+        parts.append((torch.cat(pv + [ps.unsqueeze(-1)], -1), mx, se))
+    big = torch.maximum(parts[0][1], parts[1][1])
+    wgt = [se * torch.exp(mx - big) for _, mx, se in parts]
+    comb = sum(w.unsqueeze(-1) * part for w, (part, _, _) in zip(wgt, parts)) / (wgt[0] + wgt[1]).unsqueeze(-1)
+    whole = torch.cat(ov + [osr.unsqueeze(-1)], -1)
+    assert torch.allclose(comb, whole, rtol=1e-5, atol=1e-6), float((comb - whole).abs().max())
 
 
 # ---------------------------------------------------------------------------------------------
@@ -366,6 +381,59 @@ def test_query_transformer_vs_reference_fixture(K_):
     assert err < 5e-4 * max(1.0, float(ref.abs().max())), err
     for i in range(4):
         assert torch.allclose(aux['logits'][i].cpu(), torch.from_numpy(g[f'aux_logits_{i}']), atol=1e-3)
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize('K,h,w', [(3, 30, 54), (1, 7, 5), (5, 45, 80)])
+def test_query_chain_is_bit_identical_to_the_separate_launches(K_, K, h, w):
+    """cutie_qt_chain (persistent grid, grid barriers between phases) runs the stand-alone kernels' bodies: the whole
+    QueryTransformer.forward must come out bit-identical with the chain on and off, repeatedly (the barrier counters must
+    return to zero after every launch), and inside a CUDA graph replay."""
+    import cutie_b200.model.object_transformer as ot
+    from cutie_b200.config import default_config
+    from cutie_b200.model.cutie import CUTIE
+    from oracle.synth import synthetic_state_dict
+    cfg = default_config()
+    net = CUTIE(cfg).eval()
+    net.load_state_dict(synthetic_state_dict(net.state_dict(), 0))
+    qt = net.object_transformer.cuda()
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator().manual_seed(K)
+    pixel = torch.randn(1, K, 256, h, w, generator=g).cuda()
+    summ = (torch.rand(1, K, 1, 16, 257, generator=g) + 0.1).cuda()
+    old = ot.QT_CHAIN
+    try:
+        with torch.inference_mode():
+            ot.QT_CHAIN = False
+            want, aux_w = qt(pixel, summ)
+            ot.QT_CHAIN = True
+            before = K_.LAUNCH_COUNT
+            got, aux_g = qt(pixel, summ)
+            chained_launches = K_.LAUNCH_COUNT - before
+            for _ in range(3):
+                again, _ = qt(pixel, summ)
+                assert torch.equal(again, got)
+            torch.cuda.synchronize()
+            assert torch.equal(got, want), float((got - want).abs().max())
+            for a, b in zip(aux_g['logits'], aux_w['logits']):
+                assert torch.equal(a, b)
+            assert torch.equal(K_._QT_SYNC[pixel.device.index].cpu(), torch.zeros(4, dtype=torch.int32))
+            # 4 chain launches + 3 x (p2q tiles, q2p) + 4 aux masks + the convolutions' own kernels
+            assert chained_launches < 41
+            graph = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                qt(pixel, summ)
+            torch.cuda.current_stream().wait_stream(side)
+            with torch.cuda.graph(graph):
+                cap, _ = qt(pixel, summ)
+            for _ in range(3):
+                graph.replay()
+            torch.cuda.synchronize()
+            assert torch.equal(cap, want)
+    finally:
+        ot.QT_CHAIN = old
 
 
 @pytest.mark.parametrize('B,K,C,h,w', [(1, 3, 256, 30, 54), (2, 2, 16, 7, 5), (1, 1, 8, 1, 1), (1, 3, 256, 60, 108)])

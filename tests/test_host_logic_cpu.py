@@ -256,3 +256,46 @@ def test_key_image_tracks_every_written_row(cpu_kernels, monkeypatch):
     assert segs[-1].key_image.shape[1] == K_.key_image_tiles(bk.temp.cap)
     assert len(centres) == 1, 'the centre is fixed for the life of the bucket'
 
+
+
+def test_query_chain_records_the_separate_launch_plan(cpu_kernels, monkeypatch):
+    """QueryTransformer._forward_chained (one cutie_qt_chain launch per block) against the separate-launch forward on
+    the emulated kernels: same outputs, and the recorded op lists respect the chain's contract -- at most 16 ops, phases
+    never decrease, no op reads an output of its own phase."""
+    import cutie_b200.kernels as K_
+    import cutie_b200.model.object_transformer as ot
+    from cutie_b200.config import default_config
+    from cutie_b200.model.cutie import CUTIE
+    from oracle.synth import synthetic_state_dict
+    cfg = default_config()
+    net = CUTIE(cfg).eval()
+    net.load_state_dict(synthetic_state_dict(net.state_dict(), 0))
+    qt = net.object_transformer
+    g = torch.Generator().manual_seed(2)
+    pixel = torch.randn(1, 3, 256, 6, 10, generator=g)
+    summ = torch.rand(1, 3, 1, 16, 257, generator=g) + 0.1
+    chains = []
+    run = K_.qt_chain_run
+    monkeypatch.setattr(K_, 'qt_chain_run', lambda ch: (chains.append(ch), run(ch))[1])
+    with torch.inference_mode():
+        monkeypatch.setattr(ot, 'QT_CHAIN', False)
+        want, aux_w = qt(pixel, summ)
+        assert not chains
+        monkeypatch.setattr(ot, 'QT_CHAIN', True)
+        got, aux_g = qt(pixel, summ)
+    assert len(chains) == 1 + len(qt.blocks)
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-5), float((got - want).abs().max())
+    for a, b in zip(aux_g['logits'], aux_w['logits']):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-5)
+    assert torch.equal(aux_g['fg_map'], aux_w['fg_map'])
+    for ch in chains:
+        assert 1 <= len(ch.ops) <= K_.QT_CHAIN_MAX_OPS
+        phases = [op[4] for op in ch.ops]
+        assert phases == sorted(phases)
+        for name, args, kw, outs, phase in ch.ops:
+            reads = [t for t in list(args) + [v for k, v in kw.items() if k != 'xhat_out'] if isinstance(t, torch.Tensor)]
+            reads += [t for v in kw.values() if isinstance(v, tuple) for t in v if isinstance(t, torch.Tensor)]
+            same_phase_outs = [o for op in ch.ops if op[4] == phase and op is not None for o in op[3] if o is not None]
+            same_phase_outs += [op[2].get('xhat_out') for op in ch.ops if op[4] == phase and op[2].get('xhat_out') is not None]
+            for r in reads:
+                assert all(r.data_ptr() != o.data_ptr() for o in same_phase_outs), f'{name} reads an output of its own phase'
