@@ -30,10 +30,14 @@ from cutie_b200.model.blocks import ChannelAttnResBlock, ObjConv2d
 from cutie_b200.model.positional import SinusoidPE
 
 
-# The query-side ops between the tensor-core cross attentions run as one persistent launch per block (cutie_qt_chain,
-# csrc/qt.cu: bit-identical to the separate launches).  A committed constant, not a run-time trial; the environment
-# variable exists for A/B measurements (bench.py echoes the setting in `build`).
-QT_CHAIN = os.environ.get('CUTIE_B200_QT_CHAIN', '1') != '0'
+# The query-side ops between the tensor-core cross attentions can run as one persistent launch per block (cutie_qt_chain,
+# csrc/qt.cu: bit-identical to the separate launches).  MEASURED on B200 at cfg 2 (profiles/r02_step_kernel_times_qt_chain.md):
+# 4 chain launches take 377 us per frame against 330 us for the 44 separate launches they replace -- the separate kernels'
+# ~7 us are dependent-load latency, not launch overhead, and a persistent grid of one CTA per SM runs the 384- and
+# 1152-tile ops (merge, FFN 1, head folds) in several latency-bound rounds where separate launches run them in one wave.
+# So the committed plan is the separate launches; the chain stays selectable (environment variable, echoed by bench.py in
+# `build.qt_chain`) as the measured alternative and is kept under test.
+QT_CHAIN = os.environ.get('CUTIE_B200_QT_CHAIN', '0') == '1'
 
 
 class PackedAttentionParams(nn.Module):
