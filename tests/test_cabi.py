@@ -39,6 +39,55 @@ def test_argument_validation_needs_no_gpu():
     assert st == -1
 
 
+def test_query_chain_op_list_is_validated_on_the_host():
+    """cutie_qt_chain checks its op list (counts, phase order, per-kind required pointers and sizes, the two coupled
+    optional arguments of each op) before any CUDA call; cutie_consolidate_partial wants both statistics or neither."""
+    import __graft_entry__ as ge
+    from cutie_b200.kernels import _QtOp
+    ge.build()
+    lib = ctypes.CDLL(ge.LIB)
+    lib.cutie_b200_last_error.restype = ctypes.c_char_p
+    sync = (ctypes.c_uint32 * 4)()
+    one = ctypes.c_void_p(0x1000)                      # never dereferenced: validation fails first
+
+    def call(ops, n=None, sync_ws=sync):
+        arr = (_QtOp * max(len(ops), 1))(*ops)
+        return lib.cutie_qt_chain(arr, ctypes.c_int(len(ops) if n is None else n), None, None, ctypes.c_int(0), sync_ws, None)
+
+    def linear(phase=0, **kw):
+        o = _QtOp()
+        o.kind, o.phase = 0, phase
+        o.inp[0], o.inp[1], o.out[0] = one, one, one
+        o.i[:] = (48, 256, 256, 256, 0, 0)
+        for k, v in kw.items():
+            setattr(o, k, v)
+        return o
+    assert call([], n=0) == -1 and b'cutie_qt_chain' in lib.cutie_b200_last_error()
+    assert call([linear()] * 17) == -1
+    assert call([linear()], sync_ws=None) == -1
+    assert call([linear(phase=1), linear(phase=0)]) == -1 and b'phases' in lib.cutie_b200_last_error()
+    bad = linear(); bad.kind = 9
+    assert call([bad]) == -1 and b'unknown op' in lib.cutie_b200_last_error()
+    no_w = linear(); no_w.inp[1] = None
+    assert call([no_w]) == -1
+    half_ln = linear(); half_ln.inp[3] = one           # ln_w without ln_b
+    assert call([half_ln]) == -1 and b'ln_w' in lib.cutie_b200_last_error()
+    xhat_without_ln = linear(); xhat_without_ln.out[1] = one
+    assert call([xhat_without_ln]) == -1
+    attn = linear(); attn.kind = 2; attn.i[0] = 40     # self attention: M must be a multiple of 16
+    assert call([attn]) == -1
+    comb = linear(); comb.kind = 3; comb.inp[2] = one; comb.i[:] = (2000, 256, 3, 0, 0, 0)    # > 1024 pixel tiles
+    assert call([comb]) == -1 and b'pixel tiles' in lib.cutie_b200_last_error()
+    fold = linear(); fold.kind = 1; fold.out[1] = one  # dots without bias_vec
+    assert call([fold]) == -1
+    # consolidate_partial: out_max without out_sumexp
+    f = lib.cutie_consolidate_partial
+    st = f(1, None, None, None, None, None, None, None, ctypes.c_int64(0), None, ctypes.c_int64(0), None, ctypes.c_int64(0),
+           ctypes.c_int64(1), ctypes.c_int64(1), ctypes.c_int64(64), ctypes.c_int64(256), None, None, None, ctypes.c_int64(0),
+           one, None, None, ctypes.c_int64(1), None)
+    assert st == -1 and b'out_max' in lib.cutie_b200_last_error()
+
+
 def test_sass_is_sm100a():
     import __graft_entry__ as ge
     ge.build()
