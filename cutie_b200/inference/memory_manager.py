@@ -23,6 +23,53 @@ from cutie_b200.inference.object_manager import ObjectManager
 log = logging.getLogger()
 
 
+def complete_seeds(seeds: torch.Tensor, top_k: int, n_total: int, frame_tokens: int, width: int = 0) -> torch.Tensor:
+    """Threshold seeds [B, Q, kpad] in which the winners the ring has dropped since the last read are -1: those slots take
+    tokens of the NEWEST memory frame (the last `frame_tokens` tokens of the bank) -- the j-th dropped slot of query q the
+    token of the j-th nearest pixel to q's own position in that frame (`width` = feature-map width; 0 = raster neighbours),
+    where a temporally coherent video has its best new matches, so the seed bound stays close to the true k-th energy.
+    A drop only ever follows an append, so the newest frame was not in the bank at the last read: its tokens cannot
+    coincide with a surviving winner, and distinct slots get distinct tokens -- the list stays k DISTINCT valid tokens,
+    which is all the threshold needs (results never depend on seeds).  Padding slots (>= top_k) stay -1."""
+    B, Q, kpad = seeds.shape
+    if frame_tokens < 1 or n_total < frame_tokens or 2 * top_k > frame_tokens:
+        return seeds
+    dev = seeds.device
+    offs = _neighbour_offsets(top_k, width, frame_tokens, dev).to(seeds.dtype)         # [top_k], distinct mod frame_tokens
+    q = torch.arange(Q, device=dev, dtype=seeds.dtype).view(1, Q, 1)
+    s = torch.arange(kpad, device=dev, dtype=seeds.dtype).view(1, 1, kpad)
+    missing = (seeds < 0) & (s < top_k)
+    rank = (torch.cumsum(missing.to(torch.int64), dim=2) - 1).clamp_(0, top_k - 1)    # j of the j-th dropped slot
+    fill = (n_total - frame_tokens) + torch.remainder(q + offs[rank], frame_tokens)
+    return torch.where(missing, fill.to(seeds.dtype), seeds)
+
+
+_NEIGHBOURS = {}
+
+
+def _neighbour_offsets(n: int, width: int, frame_tokens: int, device) -> torch.Tensor:
+    """Linear offsets of the n nearest pixels (the pixel itself first) on a feature map `width` wide, nearest first --
+    DISTINCT modulo frame_tokens (k seeds must be k different tokens: a duplicate would void the bound); on maps too small
+    for that, or without a width, the raster neighbours 0, +1, -1, +2, ... (distinct modulo any frame of > 2 n tokens)."""
+    key = (n, width, frame_tokens, str(device))
+    t = _NEIGHBOURS.get(key)
+    if t is None:
+        lin = None
+        if width > 0:
+            r = 1
+            while (2 * r + 1) ** 2 < n:
+                r += 1
+            cand = sorted(((dy * dy + dx * dx, abs(dy), dy, dx) for dy in range(-r, r + 1) for dx in range(-r, r + 1)))
+            lin = [dy * width + dx for _, _, dy, dx in cand[:n]]
+            if len({o % frame_tokens for o in lin}) < n:
+                lin = None
+        if lin is None:
+            lin = [(j + 1) // 2 * (1 if j % 2 else -1) for j in range(n)]
+            assert len({o % frame_tokens for o in lin}) == n
+        t = _NEIGHBOURS[key] = torch.tensor(lin, dtype=torch.int64, device=device)
+    return t
+
+
 class MemoryManager:
     def __init__(self, cfg, object_manager: ObjectManager, *, shard_group=None):
         """shard_group (a torch.distributed process group, or None): key-shard THIS stream's memory over the group's
@@ -157,7 +204,8 @@ class MemoryManager:
         if d == 0:
             return idx, tag
         moved = idx - d                                  # temporary tokens slid towards the permanent prefix by d
-        return torch.where(idx < P, idx, torch.where(moved >= P, moved, torch.full_like(idx, -1))), tag
+        seeds = torch.where(idx < P, idx, torch.where(moved >= P, moved, torch.full_like(idx, -1)))
+        return complete_seeds(seeds, self.top_k, self.work_mem.size(bucket_id), self.HW, self.W or 0), tag
 
     def _segments(self, bucket_id: int, obj_ids: List[int]):
         segs = []

@@ -299,3 +299,45 @@ def test_query_chain_records_the_separate_launch_plan(cpu_kernels, monkeypatch):
             same_phase_outs += [op[2].get('xhat_out') for op in ch.ops if op[4] == phase and op[2].get('xhat_out') is not None]
             for r in reads:
                 assert all(r.data_ptr() != o.data_ptr() for o in same_phase_outs), f'{name} reads an output of its own phase'
+
+
+def test_threshold_seed_completion_keeps_k_distinct_valid_tokens():
+    """memory_manager.complete_seeds: winners the ring dropped are replaced by tokens of the newest memory frame around the
+    query's own position; the completed lists are valid, distinct per query, and untouched where they were valid."""
+    from cutie_b200.inference.memory_manager import complete_seeds
+    g = torch.Generator().manual_seed(0)
+    B, Q, kpad, top_k, HW, frames = 2, 60, 32, 30, 60, 5
+    n_total = frames * HW
+    old = torch.stack([torch.stack([torch.randperm(n_total - HW, generator=g)[:kpad] for _ in range(Q)]) for _ in range(B)]).int()
+    old[:, :, top_k:] = -1                                           # padding slots
+    seeds = old.clone()
+    dropped = torch.rand(B, Q, kpad, generator=g) < 0.3              # what the ring dropped since the last read
+    seeds[dropped] = -1
+    out = complete_seeds(seeds, top_k, n_total, HW, 10)               # a 6 x 10 feature map
+    assert torch.equal(out[:, :, top_k:], torch.full_like(out[:, :, top_k:], -1))
+    live = out[:, :, :top_k]
+    assert bool((live >= 0).all()) and bool((live < n_total).all())
+    kept = ~dropped[:, :, :top_k]
+    assert torch.equal(live[kept], old[:, :, :top_k][kept])
+    assert bool((live[~kept] >= n_total - HW).all())                 # replacements come from the newest frame only
+    for b in range(B):
+        for q in range(Q):
+            assert live[b, q].unique().numel() == top_k
+    # the first dropped slot of a query is replaced by the token at the query's own position in the newest frame
+    first = dropped[:, :, :top_k].int().argmax(dim=2)
+    has = dropped[:, :, :top_k].any(dim=2)
+    own = (n_total - HW) + torch.arange(Q).view(1, Q).expand(B, Q)
+    assert torch.equal(torch.gather(live, 2, first.unsqueeze(-1)).squeeze(-1)[has], own[has].int())
+    raster = complete_seeds(seeds, top_k, n_total, HW)               # no width given: raster neighbours, same guarantees
+    assert all(raster[b, q, :top_k].unique().numel() == top_k for b in range(B) for q in range(Q))
+    # every slot dropped, on a map so small that 2-D neighbours would wrap onto each other: still k distinct tokens
+    from cutie_b200.inference.memory_manager import _neighbour_offsets
+    for width, frame in ((10, 60), (54, 1620), (9, 63), (0, 61)):
+        offs = _neighbour_offsets(top_k, width, frame, torch.device('cpu'))
+        assert offs[0] == 0 and len({int(o) % frame for o in offs}) == top_k, (width, frame)
+    gone = torch.full((1, HW, kpad), -1, dtype=torch.int32)
+    allnew = complete_seeds(gone, top_k, n_total, HW, 10)
+    assert all(allnew[0, q, :top_k].unique().numel() == top_k for q in range(HW))
+    # nothing to do / nothing possible
+    assert torch.equal(complete_seeds(old, top_k, n_total, HW), old)
+    assert torch.equal(complete_seeds(seeds, top_k, n_total, 8), seeds)          # fewer tokens per frame than top_k
