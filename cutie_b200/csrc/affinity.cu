@@ -575,8 +575,6 @@ static int run_filter_level(const ScanParams& base, long long B, long long strid
   return launch_tc_filter(fp, B, st);
 }
 
-constexpr long long kSeedsOnlyMaxTokens = 16384;
-
 // FP16 plan over the key operand image: tile-sampled threshold pass -> k-th smallest slot minimum -> candidate filter
 // over the whole image -> exact re-rank.  Two memsets + four launches per call, whatever the bank size.
 static int run_filtered_f16(const ScanParams& base, long long B, char* ws, const WsLayout& wl, int* out_idx, float* out_w,
@@ -611,28 +609,19 @@ static int run_filtered_f16(const ScanParams& base, long long B, char* ws, const
   const int ph = phase_begin(st);
   float* group_min = (float*)(ws + wl.cand_e);
   float* emax = (float*)(ws + wl.emax0);
-  // Small banks with caller-provided seeds skip the sample pass: the seeds alone give the threshold (the largest exact
-  // energy of k distinct tokens), and a query whose seeds are unusable falls back to threshold +inf = an exhaustive exact
-  // re-rank, which at <= 16 k tokens costs less than the ~30 us of fixed cost the sample pass has at this size.  Large
-  // banks always sample as well: an exhaustive re-rank of 400 k tokens is not an acceptable worst case there.
-  const bool seeds_only = ia.seed_idx != nullptr && base.n_total <= kSeedsOnlyMaxTokens;
-  cudaError_t e = cudaSuccess;
-  int rc = 0;
-  if (!seeds_only) {
-    e = cudaMemsetAsync(group_min, 0x7f, (size_t)B * base.Q * groups * 4, st);      // 0x7f7f7f7f = 3.4e38: "empty slot"
-    if (e != cudaSuccess) return set_cuda_error("cudaMemsetAsync", e);
-    fp.tile_stride = (int)stride;
-    fp.tile_phase = 0;
-    fp.group_min = group_min;
-    fp.groups_per_query = groups;
-    rc = launch_f16_filter(fp, B, grid_x, true, st);
-    if (rc) return rc;
-  }
+  cudaError_t e = cudaMemsetAsync(group_min, 0x7f, (size_t)B * base.Q * groups * 4, st);      // 0x7f7f7f7f = 3.4e38: "empty slot"
+  if (e != cudaSuccess) return set_cuda_error("cudaMemsetAsync", e);
+  fp.tile_stride = (int)stride;
+  fp.tile_phase = 0;
+  fp.group_min = group_min;
+  fp.groups_per_query = groups;
+  int rc = launch_f16_filter(fp, B, grid_x, true, st);
+  if (rc) return rc;
   phase_mark(ph, st);
   F16ThresholdParams tp;
   memset(&tp, 0, sizeof(tp));
   tp.group_min = group_min;
-  tp.groups = seeds_only ? 0 : groups;          // 0 slots: the sampled bound is +inf, the seeds decide
+  tp.groups = groups;
   tp.top_k = base.top_k;
   tp.kpad = base.kpad;
   tp.Q = base.Q;

@@ -216,13 +216,12 @@ def test_image_path_outside_the_f16_range(K_, tc_everywhere, key_scale, q_scale,
     assert torch.equal(idx, idx_x) and torch.equal(w, w_x) and torch.equal(sim, sim_x), note
 
 
-@pytest.mark.parametrize('runs', [[(20000, 12345, 7000), (20000, 0, 5001)],          # 12 001 tokens: seeds alone (no sample pass)
-                                  [(20000, 2345, 14000), (20000, 0, 9001)]])          # 23 001 tokens: sampled bound + seeds
+@pytest.mark.parametrize('runs', [[(20000, 12345, 7000), (20000, 0, 5001)],          # 12 001 tokens
+                                  [(20000, 2345, 14000), (20000, 0, 9001)]])          # 23 001 tokens
 def test_threshold_seeds_never_change_the_result(K_, tc_everywhere, runs):
     """seed_idx only tightens the filter threshold: the previous winners (the runtime's use), random distinct tokens,
-    partly invalid lists and the true answer itself all give the bit-identical selection -- in both regimes: banks of at
-    most 16 384 tokens take their threshold from the seeds alone (an unusable list = exhaustive exact re-rank of that
-    query), larger ones from the tile sample and the seeds."""
+    partly invalid lists and the true answer itself all give the bit-identical selection (the threshold is the smaller of
+    the tile-sampled bound and the seed bound; an unusable list leaves the sampled bound)."""
     segs, key, shr = _arena_bank(K_, 1, runs, seed=4, centred=True)
     N, Q, top_k = key.shape[1], 260, 30
     g = torch.Generator().manual_seed(6)
